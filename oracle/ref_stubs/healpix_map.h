@@ -1,0 +1,5 @@
+/* test infrastructure: see healpix_stub_all.h */
+#ifndef ORACLE_STUB_HEALPIX_MAP_H
+#define ORACLE_STUB_HEALPIX_MAP_H
+#include "healpix_stub_all.h"
+#endif
