@@ -1,0 +1,333 @@
+"""ctypes binding of the C ABI in include/cmg.h (the reference-side stub of INTEGRATION.md, in Python)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_PARTS = 16
+LMAX_LIMIT = 1023
+
+_i64 = ctypes.c_int64
+_vp = ctypes.c_void_p
+
+
+class CmgError(RuntimeError):
+    """Non-zero cmg_status (the C++ wrappers raise StandardException in the same places)."""
+
+    def __init__(self, status, text):
+        super().__init__("cmg status %d: %s" % (status, text))
+        self.status = status
+
+
+class TquLayout(ctypes.Structure):
+    _fields_ = [
+        ("n_parts", ctypes.c_int32),
+        ("own", ctypes.c_int32),
+        ("begin", _i64 * (MAX_PARTS + 1)),
+        ("ptr", (_vp * 3) * MAX_PARTS),
+        ("kind", ctypes.c_int32 * MAX_PARTS),
+        ("ld", _i64 * MAX_PARTS),
+        ("row0", _i64 * MAX_PARTS),
+    ]
+
+
+def library_path():
+    return os.path.join(HERE, "lib", "libcosmopp_b200.so")
+
+
+def build_library(verbose=False):
+    """nvcc build of the CUDA library for sm_100a (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-6000:], r.stderr[-6000:])
+    if r.returncode:
+        raise RuntimeError("building libcosmopp_b200.so failed")
+
+
+_SIGNATURES = {
+    "cmg_version": (ctypes.c_int, []),
+    "cmg_device_count": (ctypes.c_int, []),
+    "cmg_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
+    "cmg_destroy": (None, [_vp]),
+    "cmg_last_error": (ctypes.c_char_p, [_vp]),
+    "cmg_set_stream": (ctypes.c_int, [_vp, _vp]),
+    "cmg_use_own_stream": (ctypes.c_int, [_vp]),
+    "cmg_synchronize": (ctypes.c_int, [_vp]),
+    "cmg_launch_count": (_i64, [_vp]),
+    "cmg_device_malloc": (ctypes.c_int, [_vp, _i64, ctypes.POINTER(_vp)]),
+    "cmg_device_free": (ctypes.c_int, [_vp, _vp]),
+    "cmg_host_malloc_pinned": (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
+    "cmg_host_free_pinned": (ctypes.c_int, [_vp]),
+    "cmg_copy_to_host": (ctypes.c_int, [_vp, _vp, _vp, _i64]),
+    "cmg_copy_to_device": (ctypes.c_int, [_vp, _vp, _vp, _i64]),
+    "cmg_nside2npix": (_i64, [_i64]),
+    "cmg_pix2ang_nest": (ctypes.c_int, [_i64, _i64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "cmg_packed_size": (_i64, [_i64]),
+    "cmg_packed_index": (_i64, [_i64, _i64]),
+    "cmg_good_pixels_from_mask": (ctypes.c_int, [_vp, _i64, _vp, ctypes.POINTER(_i64)]),
+    "cmg_beam_function": (ctypes.c_double, [ctypes.c_int, ctypes.c_double]),
+    "cmg_window_beam": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, _vp]),
+    "cmg_set_pixels": (ctypes.c_int, [_vp, _i64, _vp, _i64]),
+    "cmg_npix": (_i64, [_vp]),
+    "cmg_get_geometry": (ctypes.c_int, [_vp, _vp]),
+    "cmg_legendre_series": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _vp]),
+    "cmg_legendre_series_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _vp]),
+    "cmg_tt_weights": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "cmg_fiducial_weights": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _vp]),
+    "cmg_cl_to_cmatrix": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp]),
+    "cmg_fiducial_matrix": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp]),
+    "cmg_noise_matrix": (ctypes.c_int, [_i64, ctypes.c_double, _vp]),
+    "cmg_mask_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "cmg_tqu_layout_single": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(TquLayout)]),
+    "cmg_tqu": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(TquLayout)]),
+    "cmg_tqu_weights": (ctypes.c_int, [_vp] * 6 + [ctypes.c_int] + [_vp] * 4),
+    "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
+    "cmg_legendre_series_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _i64, _vp, _i64]),
+    "cmg_tqu_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp, _i64]),
+    "cmg_measure_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
+    "cmg_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
+    "cmg_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
+}
+
+_lib = None
+
+
+def library():
+    """Load lib/libcosmopp_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the generator has no CPU fallback)" % path)
+        L = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_names():
+    return sorted(_SIGNATURES)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return _vp(a.ctypes.data)
+    if isinstance(a, int):
+        return _vp(a)
+    return _vp(a.data_ptr())        # torch tensor
+
+
+class Context:
+    """One GPU + one stream (cmg_ctx).  Device buffers are torch tensors or raw pointers."""
+
+    def __init__(self, device=0, stream=None):
+        self._L = library()
+        h = _vp()
+        st = self._L.cmg_create(ctypes.byref(h), int(device))
+        if st:
+            raise CmgError(st, self._L.cmg_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cmg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st:
+            raise CmgError(st, self._L.cmg_last_error(self._h).decode())
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream; 0 is the legacy
+        default stream); None returns to the context's private stream."""
+        if cuda_stream is None:
+            self._check(self._L.cmg_use_own_stream(self._h))
+        else:
+            self._check(self._L.cmg_set_stream(self._h, _vp(int(cuda_stream))))
+
+    def synchronize(self):
+        self._check(self._L.cmg_synchronize(self._h))
+
+    @property
+    def launches(self):
+        return int(self._L.cmg_launch_count(self._h))
+
+    def set_timing(self, on):
+        self._check(self._L.cmg_set_timing(self._h, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        v = ctypes.c_double()
+        self._check(self._L.cmg_last_kernel_ms(self._h, ctypes.byref(v)))
+        return v.value
+
+    def measure_fp64_peak(self):
+        v = ctypes.c_double()
+        self._check(self._L.cmg_measure_fp64_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+    # ---- geometry
+    def set_pixels(self, nside, good=None):
+        if good is None:
+            self._check(self._L.cmg_set_pixels(self._h, int(nside), None, 0))
+        else:
+            g = np.ascontiguousarray(good, dtype=np.int32)
+            self._check(self._L.cmg_set_pixels(self._h, int(nside), _p(g), len(g)))
+        self.nside = int(nside)
+
+    @property
+    def npix(self):
+        return int(self._L.cmg_npix(self._h))
+
+    def geometry(self):
+        out = np.empty((8, self.npix))
+        self._check(self._L.cmg_get_geometry(self._h, _p(out)))
+        return out
+
+    # ---- TT
+    def legendre_series(self, a, d_out, col_begin=0, col_end=None):
+        a = _f64(a)
+        col_end = self.npix if col_end is None else col_end
+        self._check(self._L.cmg_legendre_series(self._h, _p(a), len(a) - 1, col_begin, col_end, _p(d_out)))
+
+    def legendre_series_dev(self, d_a, lmax, d_out, col_begin=0, col_end=None):
+        col_end = self.npix if col_end is None else col_end
+        self._check(self._L.cmg_legendre_series_dev(self._h, _p(d_a), lmax, col_begin, col_end, _p(d_out)))
+
+    def legendre_series_batched(self, a, d_out, stride, col_begin=0, col_end=None):
+        a = _f64(a)
+        col_end = self.npix if col_end is None else col_end
+        self._check(self._L.cmg_legendre_series_batched(self._h, _p(a), a.shape[1] - 1, a.shape[0], col_begin, col_end,
+                                                        _p(d_out), stride))
+
+    def cl_to_cmatrix(self, cl, fwhm, out_host, pixwin=None):
+        cl = _f64(cl)
+        pixwin = _f64(pixwin)
+        self._check(self._L.cmg_cl_to_cmatrix(self._h, _p(cl), len(cl) - 1, float(fwhm), _p(pixwin), _p(out_host)))
+
+    def fiducial_matrix(self, cl, lmax, fwhm, out_host, pixwin=None):
+        cl = _f64(cl)
+        pixwin = _f64(pixwin)
+        self._check(self._L.cmg_fiducial_matrix(self._h, _p(cl), int(lmax), float(fwhm), _p(pixwin), _p(out_host)))
+
+    def mask_matrix(self, d_in, npix_in, good, d_out):
+        g = np.ascontiguousarray(good, dtype=np.int32)
+        self._check(self._L.cmg_mask_matrix(self._h, _p(d_in), npix_in, _p(g), len(g), _p(d_out)))
+
+    # ---- TQU
+    def tqu_layout_single(self, d_packed):
+        lay = TquLayout()
+        self._check(self._L.cmg_tqu_layout_single(self._h, _p(d_packed), ctypes.byref(lay)))
+        return lay
+
+    def tqu(self, a_tt, a_te, a_ee, a_bb, layout):
+        a_tt, a_te, a_ee, a_bb = map(_f64, (a_tt, a_te, a_ee, a_bb))
+        self._check(self._L.cmg_tqu(self._h, _p(a_tt), _p(a_te), _p(a_ee), _p(a_bb), len(a_tt) - 1, ctypes.byref(layout)))
+
+    def tqu_batched(self, a, d_out, stride):
+        a = _f64(a)         # [B][4][lmax+1]
+        self._check(self._L.cmg_tqu_batched(self._h, _p(a), a.shape[2] - 1, a.shape[0], _p(d_out), stride))
+
+    def cl_to_cmatrix_pol(self, ctt, cte, cee, cbb, fwhm, out_host, pixwinT=None, pixwinP=None):
+        ctt, cte, cee, cbb = map(_f64, (ctt, cte, cee, cbb))
+        pixwinT = _f64(pixwinT)
+        pixwinP = _f64(pixwinP)
+        self._check(self._L.cmg_cl_to_cmatrix_pol(self._h, _p(ctt), _p(cte), _p(cee), _p(cbb), len(ctt) - 1, float(fwhm),
+                                                  _p(pixwinT), _p(pixwinP), _p(out_host)))
+
+
+# ---- pure-host helpers of the ABI (no GPU needed)
+
+def window_beam(lmax, fwhm, pixwin=None):
+    f = np.empty(lmax + 1)
+    pixwin = _f64(pixwin)
+    st = library().cmg_window_beam(_p(f), lmax, float(fwhm), _p(pixwin))
+    if st:
+        raise CmgError(st, "cmg_window_beam")
+    return f
+
+
+def tt_weights(cl, f):
+    cl = _f64(cl)
+    f = _f64(f)
+    a = np.empty(len(cl))
+    st = library().cmg_tt_weights(_p(cl), _p(f), len(cl) - 1, _p(a))
+    if st:
+        raise CmgError(st, "cmg_tt_weights")
+    return a
+
+
+def fiducial_weights(cl, f, nside, lmax):
+    cl = _f64(cl)
+    f = _f64(f)
+    a = np.empty(4 * nside + 1)
+    st = library().cmg_fiducial_weights(_p(cl), _p(f), nside, lmax, _p(a))
+    if st:
+        raise CmgError(st, "cmg_fiducial_weights")
+    return a
+
+
+def tqu_weights(ctt, cte, cee, cbb, fT, fP):
+    ctt, cte, cee, cbb, fT, fP = map(_f64, (ctt, cte, cee, cbb, fT, fP))
+    n = len(ctt)
+    out = [np.empty(n) for _ in range(4)]
+    st = library().cmg_tqu_weights(_p(ctt), _p(cte), _p(cee), _p(cbb), _p(fT), _p(fP), n - 1, *[_p(o) for o in out])
+    if st:
+        raise CmgError(st, "cmg_tqu_weights")
+    return out
+
+
+def pix2ang_nest(nside, ipix):
+    t = ctypes.c_double()
+    p = ctypes.c_double()
+    st = library().cmg_pix2ang_nest(nside, int(ipix), ctypes.byref(t), ctypes.byref(p))
+    if st:
+        raise CmgError(st, "cmg_pix2ang_nest: invalid nside/ipix")
+    return t.value, p.value
+
+
+def good_pixels_from_mask(mask):
+    mask = _f64(mask)
+    good = np.empty(len(mask), dtype=np.int32)
+    n = _i64()
+    st = library().cmg_good_pixels_from_mask(_p(mask), len(mask), _p(good), ctypes.byref(n))
+    if st:
+        raise CmgError(st, "cmg_good_pixels_from_mask")
+    return good[:n.value].copy()
+
+
+def packed_size(dim):
+    return int(library().cmg_packed_size(dim))
+
+
+def packed_index(i, j):
+    return int(library().cmg_packed_index(i, j))
+
+
+def noise_matrix(npix, noise):
+    out = np.empty(packed_size(npix))
+    st = library().cmg_noise_matrix(npix, float(noise), _p(out))
+    if st:
+        raise CmgError(st, "cmg_noise_matrix")
+    return out

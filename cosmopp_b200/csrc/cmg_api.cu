@@ -1,0 +1,801 @@
+// C ABI of the generator (include/cmg.h): context, geometry, launches.  No CPU fallback anywhere:
+// every compute entry point needs a live sm_100 context and fails with CMG_ECUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/cmg.h"
+#include "healpix_nest.hpp"
+#include "kernels.cuh"
+#include "series.hpp"
+
+namespace
+{
+const double kPi = 3.141592653589793;      // Math::pi of the reference (include/math_constants.hpp:8)
+const int kTabLen = CMG_LMAX_LIMIT + 2;
+thread_local std::string g_createError;
+}
+
+struct cmg_ctx
+{
+    int device = 0;
+    cudaStream_t ownStream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    int64_t nside = 0;
+    int64_t npix = 0;
+    double* dGeo = nullptr;          // [8][npix]
+    double* dTables = nullptr;       // 7 tables of kTabLen
+    double* dWeights = nullptr;      // staging for host-supplied weights
+    int64_t weightsCap = 0;          // doubles
+    double* dScratch = nullptr;      // whole-call output buffer
+    int64_t scratchCap = 0;          // bytes
+    int32_t* dIndex = nullptr;       // maskMatrix indices
+    int64_t indexCap = 0;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;
+    double lastMs = 0.0;
+    int64_t launches = 0;
+};
+
+namespace
+{
+
+cmg_status fail(cmg_ctx* ctx, cmg_status s, const std::string& msg)
+{
+    if(ctx)
+        ctx->err = msg;
+    else
+        g_createError = msg;
+    return s;
+}
+
+cmg_status cudaFail(cmg_ctx* ctx, cudaError_t e, const char* what)
+{
+    return fail(ctx, e == cudaErrorMemoryAllocation ? CMG_ENOMEM : CMG_ECUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CMG_CUDA(ctx, call)                                      \
+    do                                                           \
+    {                                                            \
+        const cudaError_t e_ = (call);                           \
+        if(e_ != cudaSuccess)                                    \
+            return cudaFail((ctx), e_, #call);                   \
+    } while(0)
+
+cmg::Geometry geometryOf(const cmg_ctx* ctx)
+{
+    cmg::Geometry g;
+    const double* b = ctx->dGeo;
+    const int64_t n = ctx->npix;
+    g.nx = b; g.ny = b + n; g.nz = b + 2 * n;
+    g.tx = b + 3 * n; g.ty = b + 4 * n; g.tz = b + 5 * n;
+    g.px = b + 6 * n; g.py = b + 7 * n;
+    g.npix = n;
+    return g;
+}
+
+cmg::DeviceTables tablesOf(const cmg_ctx* ctx)
+{
+    cmg::DeviceTables t;
+    const double* b = ctx->dTables;
+    t.N0 = b; t.g0 = b + kTabLen;
+    t.N20 = b + 2 * kTabLen; t.g20 = b + 3 * kTabLen;
+    t.N22 = b + 4 * kTabLen; t.g22 = b + 5 * kTabLen; t.c22 = b + 6 * kTabLen;
+    return t;
+}
+
+cmg_status ensureWeights(cmg_ctx* ctx, int64_t doubles)
+{
+    if(doubles <= ctx->weightsCap)
+        return CMG_OK;
+    if(ctx->dWeights)
+    {
+        CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CMG_CUDA(ctx, cudaFree(ctx->dWeights));
+        ctx->dWeights = nullptr;
+        ctx->weightsCap = 0;
+    }
+    CMG_CUDA(ctx, cudaMalloc(&ctx->dWeights, sizeof(double) * doubles));
+    ctx->weightsCap = doubles;
+    return CMG_OK;
+}
+
+cmg_status ensureScratch(cmg_ctx* ctx, int64_t bytes)
+{
+    if(bytes <= ctx->scratchCap)
+        return CMG_OK;
+    if(ctx->dScratch)
+    {
+        CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CMG_CUDA(ctx, cudaFree(ctx->dScratch));
+        ctx->dScratch = nullptr;
+        ctx->scratchCap = 0;
+    }
+    CMG_CUDA(ctx, cudaMalloc(&ctx->dScratch, bytes));
+    ctx->scratchCap = bytes;
+    return CMG_OK;
+}
+
+cmg_status checkReady(cmg_ctx* ctx, int lmax)
+{
+    if(!ctx)
+        return CMG_EINVAL;
+    if(ctx->npix <= 0)
+        return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
+    if(lmax < 0)
+        return fail(ctx, CMG_EINVAL, "lmax must be >= 0");
+    if(lmax > CMG_LMAX_LIMIT)
+        return fail(ctx, CMG_EUNSUPPORTED, "lmax exceeds CMG_LMAX_LIMIT");
+    return CMG_OK;
+}
+
+struct KernelTimer
+{
+    cmg_ctx* ctx;
+    explicit KernelTimer(cmg_ctx* c) : ctx(c)
+    {
+        if(ctx->timing)
+            cudaEventRecord(ctx->ev0, ctx->stream);
+    }
+    cmg_status finish()
+    {
+        if(!ctx->timing)
+            return CMG_OK;
+        CMG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CMG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CMG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->lastMs = ms;
+        return CMG_OK;
+    }
+};
+
+cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, int64_t nBatch,
+                          int64_t colBegin, int64_t colEnd, double* dOut, int64_t outStride)
+{
+    if(colBegin < 0 || colEnd > ctx->npix || colBegin > colEnd)
+        return fail(ctx, CMG_EINVAL, "column range outside [0, npix]");
+    if(nBatch < 1 || nBatch > 65535)
+        return fail(ctx, CMG_EINVAL, "n_batch must be in [1, 65535] per call");
+    if(colBegin == colEnd)
+        return CMG_OK;
+    if(!dOut || !dA)
+        return fail(ctx, CMG_EINVAL, "null device pointer");
+    const int64_t rowBlocks = (colEnd + cmg::TT_ROWS - 1) / cmg::TT_ROWS;
+    const int64_t colBlocks = (colEnd - colBegin + cmg::TT_COLS - 1) / cmg::TT_COLS;
+    if(colBlocks > 65535)
+        return fail(ctx, CMG_EUNSUPPORTED, "too many column blocks for one launch");
+    const dim3 grid(static_cast<unsigned>(rowBlocks), static_cast<unsigned>(colBlocks), static_cast<unsigned>(nBatch));
+    const size_t smem = sizeof(double2) * (lmax + 1);
+    const cmg::DeviceTables t = tablesOf(ctx);
+    KernelTimer timer(ctx);
+    cmg::legendreSeriesKernel<<<grid, cmg::TT_ROWS, smem, ctx->stream>>>(geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax,
+                                                                         colBegin, colEnd, dOut, outStride);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return timer.finish();
+}
+
+size_t tquSmemBytes(int lmax)
+{
+    return sizeof(double4) * 2 * (lmax + 1) + sizeof(double) * (8 * cmg::PQ_TI + 8 * cmg::PQ_TJ + 3 * cmg::PQ_TI * cmg::PQ_STAGE_LD);
+}
+
+cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, int64_t nBatch,
+                     const cmg_tqu_layout* layout, int64_t outStride)
+{
+    if(!layout || layout->n_parts < 1 || layout->n_parts > CMG_MAX_PARTS || layout->own < 0 || layout->own >= layout->n_parts)
+        return fail(ctx, CMG_EINVAL, "bad layout: n_parts / own");
+    if(layout->begin[0] != 0 || layout->begin[layout->n_parts] != ctx->npix)
+        return fail(ctx, CMG_EINVAL, "layout must cover pixel columns [0, npix]");
+    cmg::PartTable P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = layout->n_parts;
+    P.own = layout->own;
+    for(int k = 0; k <= P.n; ++k)
+    {
+        P.begin[k] = layout->begin[k];
+        if(k > 0 && P.begin[k] < P.begin[k - 1])
+            return fail(ctx, CMG_EINVAL, "layout boundaries must be non-decreasing");
+    }
+    for(int k = 0; k < P.n; ++k)
+    {
+        for(int s = 0; s < 3; ++s)
+            P.ptr[k][s] = layout->ptr[k][s];
+        P.kind[k] = layout->kind[k];
+        P.ld[k] = layout->ld[k];
+        P.row0[k] = layout->row0[k];
+        if(P.kind[k] != 0 && P.kind[k] != 1)
+            return fail(ctx, CMG_EINVAL, "layout kind must be 0 (packed) or 1 (dense blocks)");
+        // parts at or before `own` receive entries; they need storage
+        if(k <= P.own && P.begin[k + 1] > P.begin[k] && (!P.ptr[k][0] && k == P.own))
+            return fail(ctx, CMG_EINVAL, "own part has no storage");
+        if(k < P.own && P.begin[k + 1] > P.begin[k] && (!P.ptr[k][1] || !P.ptr[k][2]))
+            return fail(ctx, CMG_EINVAL, "a part left of own has no storage for the transposed entries");
+    }
+    if(P.kind[P.own] != 0 || !P.ptr[P.own][0] || !P.ptr[P.own][1] || !P.ptr[P.own][2])
+        return fail(ctx, CMG_EINVAL, "own part must be packed (kind 0) with three strips");
+    const int64_t colBegin = P.begin[P.own], colEnd = P.begin[P.own + 1];
+    if(colBegin == colEnd)
+        return CMG_OK;
+    if(nBatch < 1 || nBatch > 65535)
+        return fail(ctx, CMG_EINVAL, "n_batch must be in [1, 65535] per call");
+    const int64_t rowBlocks = (colEnd + cmg::PQ_TI - 1) / cmg::PQ_TI;
+    const int64_t colBlocks = (colEnd - colBegin + cmg::PQ_TJ - 1) / cmg::PQ_TJ;
+    if(colBlocks > 65535)
+        return fail(ctx, CMG_EUNSUPPORTED, "too many column blocks for one launch");
+    const size_t smem = tquSmemBytes(lmax);
+    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::tquKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const dim3 grid(static_cast<unsigned>(rowBlocks), static_cast<unsigned>(colBlocks), static_cast<unsigned>(nBatch));
+    KernelTimer timer(ctx);
+    cmg::tquKernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(geometryOf(ctx), dA, aStride, tablesOf(ctx), lmax, P, outStride);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return timer.finish();
+}
+
+} // namespace
+
+extern "C"
+{
+
+int cmg_version(void) { return 100; }
+
+int cmg_device_count(void)
+{
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+cmg_status cmg_create(cmg_ctx** out, int device)
+{
+    if(!out)
+        return fail(nullptr, CMG_EINVAL, "ctx output pointer is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if(e != cudaSuccess || n == 0)
+    {
+        cudaGetLastError();
+        return fail(nullptr, CMG_ECUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if(device < 0 || device >= n)
+        return fail(nullptr, CMG_EINVAL, "device index out of range");
+    cudaDeviceProp prop;
+    if((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return cudaFail(nullptr, e, "cudaGetDeviceProperties");
+    if(prop.major != 10)
+        return fail(nullptr, CMG_ECUDA, std::string("device ") + prop.name + " is not sm_100 (kernels are built for sm_100a only)");
+
+    cmg_ctx* ctx = new(std::nothrow) cmg_ctx;
+    if(!ctx)
+        return fail(nullptr, CMG_ENOMEM, "out of host memory");
+    ctx->device = device;
+    auto bail = [&](cudaError_t err, const char* what) {
+        const cmg_status s = cudaFail(nullptr, err, what);
+        cmg_destroy(ctx);
+        return s;
+    };
+    if((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    ctx->stream = ctx->ownStream;
+    if((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+
+    // recurrence tables, once per context
+    std::vector<double> host(7 * kTabLen, 0.0);
+    const cmg::SeriesTable t0 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 0, 0);
+    const cmg::SeriesTable t20 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 2, 0);
+    const cmg::SeriesTable t22 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 2, 2);
+    for(int l = 0; l < kTabLen; ++l)
+    {
+        host[0 * kTabLen + l] = t0.N[l];
+        host[1 * kTabLen + l] = t0.g[l];
+        host[2 * kTabLen + l] = t20.N[l];
+        host[3 * kTabLen + l] = t20.g[l];
+        host[4 * kTabLen + l] = t22.N[l];
+        host[5 * kTabLen + l] = t22.g[l];
+        host[6 * kTabLen + l] = t22.c[l];
+    }
+    if((e = cudaMalloc(&ctx->dTables, sizeof(double) * host.size())) != cudaSuccess) return bail(e, "cudaMalloc(tables)");
+    if((e = cudaMemcpy(ctx->dTables, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail(e, "cudaMemcpy(tables)");
+    *out = ctx;
+    return CMG_OK;
+}
+
+void cmg_destroy(cmg_ctx* ctx)
+{
+    if(!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    if(ctx->ownStream) cudaStreamSynchronize(ctx->ownStream);
+    if(ctx->dGeo) cudaFree(ctx->dGeo);
+    if(ctx->dTables) cudaFree(ctx->dTables);
+    if(ctx->dWeights) cudaFree(ctx->dWeights);
+    if(ctx->dScratch) cudaFree(ctx->dScratch);
+    if(ctx->dIndex) cudaFree(ctx->dIndex);
+    if(ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if(ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if(ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+}
+
+const char* cmg_last_error(const cmg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+cmg_status cmg_set_stream(cmg_ctx* ctx, void* s)
+{
+    if(!ctx) return CMG_EINVAL;
+    ctx->stream = static_cast<cudaStream_t>(s);
+    return CMG_OK;
+}
+
+cmg_status cmg_use_own_stream(cmg_ctx* ctx)
+{
+    if(!ctx) return CMG_EINVAL;
+    ctx->stream = ctx->ownStream;
+    return CMG_OK;
+}
+
+cmg_status cmg_synchronize(cmg_ctx* ctx)
+{
+    if(!ctx) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CMG_OK;
+}
+
+int64_t cmg_launch_count(const cmg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+cmg_status cmg_device_malloc(cmg_ctx* ctx, int64_t bytes, void** p)
+{
+    if(!ctx || !p || bytes < 0) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaMalloc(p, static_cast<size_t>(bytes)));
+    return CMG_OK;
+}
+
+cmg_status cmg_device_free(cmg_ctx* ctx, void* p)
+{
+    if(!ctx) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaFree(p));
+    return CMG_OK;
+}
+
+cmg_status cmg_host_malloc_pinned(int64_t bytes, void** p)
+{
+    if(!p || bytes < 0) return CMG_EINVAL;
+    const cudaError_t e = cudaHostAlloc(p, static_cast<size_t>(bytes), cudaHostAllocPortable);
+    if(e != cudaSuccess)
+        return cudaFail(nullptr, e, "cudaHostAlloc");
+    return CMG_OK;
+}
+
+cmg_status cmg_host_free_pinned(void* p)
+{
+    const cudaError_t e = cudaFreeHost(p);
+    if(e != cudaSuccess)
+        return cudaFail(nullptr, e, "cudaFreeHost");
+    return CMG_OK;
+}
+
+cmg_status cmg_copy_to_host(cmg_ctx* ctx, void* dst, const void* src, int64_t bytes)
+{
+    if(!ctx || !dst || !src || bytes < 0) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CMG_OK;
+}
+
+cmg_status cmg_copy_to_device(cmg_ctx* ctx, void* dst, const void* src, int64_t bytes)
+{
+    if(!ctx || !dst || !src || bytes < 0) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, ctx->stream));
+    return CMG_OK;
+}
+
+// ---------------------------------------------------------------- host pieces
+
+int64_t cmg_nside2npix(int64_t nside) { return cmg::nside2npix(nside); }
+
+cmg_status cmg_pix2ang_nest(int64_t nside, int64_t ipix, double* theta, double* phi)
+{
+    if(!theta || !phi || !cmg::validNside(nside) || ipix < 0 || ipix >= cmg::nside2npix(nside))
+        return CMG_EINVAL;
+    cmg::pix2angNest(nside, ipix, *theta, *phi);
+    return CMG_OK;
+}
+
+int64_t cmg_packed_size(int64_t dim) { return dim * (dim + 1) / 2; }
+
+int64_t cmg_packed_index(int64_t i, int64_t j)
+{
+    if(i > j)
+        std::swap(i, j);
+    return j * (j + 1) / 2 + i;
+}
+
+cmg_status cmg_good_pixels_from_mask(const double* mask, int64_t npix, int32_t* good, int64_t* nGood)
+{
+    if(!mask || !good || !nGood || npix < 0)
+        return CMG_EINVAL;
+    int64_t n = 0;
+    for(int64_t i = 0; i < npix; ++i)
+        if(mask[i] > 0.5)
+            good[n++] = static_cast<int32_t>(i);
+    *nGood = n;
+    return CMG_OK;
+}
+
+double cmg_beam_function(int l, double fwhm)
+{
+    if(fwhm == 0)
+        return 1.0;
+    const double sigma = std::sqrt(8 * std::log(2.0)) / (fwhm * kPi / 180);
+    const int ll1 = l * (l + 1);          // the reference forms l(l+1) in int and negates it (source/utils.cpp:63)
+    return std::exp(-ll1 / (2 * sigma * sigma));
+}
+
+cmg_status cmg_window_beam(double* f, int lmax, double fwhm, const double* pixwin)
+{
+    if(!f || lmax < 0 || fwhm < 0)
+        return CMG_EINVAL;
+    for(int l = 0; l <= lmax; ++l)
+    {
+        double v = pixwin ? pixwin[l] : 1.0;
+        v *= cmg_beam_function(l, fwhm);
+        f[l] = v;
+    }
+    return CMG_OK;
+}
+
+cmg_status cmg_tt_weights(const double* cl, const double* f, int lmax, double* a)
+{
+    if(!cl || !f || !a || lmax < 0)
+        return CMG_EINVAL;
+    for(int l = 0; l <= lmax; ++l)
+    {
+        if(l < 2)
+        {
+            a[l] = 0.0;                                         // monopole and dipole excluded (:190,219)
+            continue;
+        }
+        const double clCopy = cl[l] * (2 * l + 1) / (4 * kPi);  // reference c_matrix_generator.cpp:192
+        a[l] = clCopy * f[l] * f[l];
+    }
+    return CMG_OK;
+}
+
+cmg_status cmg_fiducial_weights(const double* cl, const double* f, int64_t nside, int lmax, double* a)
+{
+    if(!cl || !f || !a || nside < 1 || lmax < 0)
+        return CMG_EINVAL;
+    const int lMaxMax = static_cast<int>(4 * nside);
+    for(int l = 0; l <= lMaxMax; ++l)
+        a[l] = (l > lmax) ? cl[l] * ((2 * l + 1) / (4 * kPi)) * f[l] * f[l] : 0.0;   // :758
+    const double md = 100 * cl[2] * f[2] * f[2];                                       // :762, (1 + z) = P_0 + P_1
+    a[0] += md;
+    if(lMaxMax >= 1)
+        a[1] += md;
+    return CMG_OK;
+}
+
+cmg_status cmg_tqu_weights(const double* ctt, const double* cte, const double* cee, const double* cbb,
+                           const double* fT, const double* fP, int lmax,
+                           double* att, double* ate, double* aee, double* abb)
+{
+    if(!ctt || !cte || !cee || !cbb || !fT || !fP || !att || !ate || !aee || !abb || lmax < 0)
+        return CMG_EINVAL;
+    for(int l = 0; l <= lmax; ++l)
+    {
+        if(l < 2)
+        {
+            att[l] = ate[l] = aee[l] = abb[l] = 0.0;
+            continue;
+        }
+        const double w = (2 * l + 1) / (4 * kPi);
+        att[l] = ctt[l] * w * fT[l] * fT[l];
+        ate[l] = cte[l] * w * fT[l] * fP[l];
+        aee[l] = cee[l] * w * fP[l] * fP[l];
+        abb[l] = cbb[l] * w * fP[l] * fP[l];
+    }
+    return CMG_OK;
+}
+
+cmg_status cmg_noise_matrix(int64_t npix, double noise, double* out)
+{
+    if(!out || npix < 1)
+        return CMG_EINVAL;
+    std::memset(out, 0, sizeof(double) * static_cast<size_t>(cmg_packed_size(npix)));
+    for(int64_t i = 0; i < npix; ++i)
+        out[cmg_packed_index(i, i)] = noise * noise;
+    return CMG_OK;
+}
+
+// ---------------------------------------------------------------- geometry
+
+cmg_status cmg_set_pixels(cmg_ctx* ctx, int64_t nside, const int32_t* good, int64_t nGood)
+{
+    if(!ctx)
+        return CMG_EINVAL;
+    if(!cmg::validNside(nside))
+        return fail(ctx, CMG_EINVAL, "nside must be a power of two in [1, 8192]");
+    const int64_t full = cmg::nside2npix(nside);
+    const int64_t n = good ? nGood : full;
+    if(n < 1)
+        return fail(ctx, CMG_EINVAL, "empty pixel list");
+    std::vector<double> host(static_cast<size_t>(8 * n));
+    for(int64_t k = 0; k < n; ++k)
+    {
+        const int64_t ipix = good ? good[k] : k;
+        if(ipix < 0 || ipix >= full)
+            return fail(ctx, CMG_EINVAL, "pixel index outside [0, 12 nside^2)");
+        const cmg::PixelFrame f = cmg::pixelFrame(nside, ipix);
+        host[0 * n + k] = f.n[0];
+        host[1 * n + k] = f.n[1];
+        host[2 * n + k] = f.n[2];
+        host[3 * n + k] = f.eTheta[0];
+        host[4 * n + k] = f.eTheta[1];
+        host[5 * n + k] = f.eTheta[2];
+        host[6 * n + k] = f.ePhi[0];
+        host[7 * n + k] = f.ePhi[1];
+    }
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if(ctx->dGeo)
+    {
+        CMG_CUDA(ctx, cudaFree(ctx->dGeo));
+        ctx->dGeo = nullptr;
+        ctx->npix = 0;
+    }
+    CMG_CUDA(ctx, cudaMalloc(&ctx->dGeo, sizeof(double) * host.size()));
+    CMG_CUDA(ctx, cudaMemcpy(ctx->dGeo, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
+    ctx->nside = nside;
+    ctx->npix = n;
+    return CMG_OK;
+}
+
+int64_t cmg_npix(const cmg_ctx* ctx) { return ctx ? ctx->npix : 0; }
+
+cmg_status cmg_get_geometry(cmg_ctx* ctx, double* out)
+{
+    if(!ctx || !out) return CMG_EINVAL;
+    if(ctx->npix <= 0) return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaMemcpy(out, ctx->dGeo, sizeof(double) * 8 * ctx->npix, cudaMemcpyDeviceToHost));
+    return CMG_OK;
+}
+
+// ---------------------------------------------------------------- TT
+
+cmg_status cmg_legendre_series_dev(cmg_ctx* ctx, const double* dA, int lmax, int64_t colBegin, int64_t colEnd, double* dOut)
+{
+    const cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launchLegendre(ctx, dA, 0, lmax, 1, colBegin, colEnd, dOut, 0);
+}
+
+cmg_status cmg_legendre_series(cmg_ctx* ctx, const double* a, int lmax, int64_t colBegin, int64_t colEnd, double* dOut)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!a) return fail(ctx, CMG_EINVAL, "null weights");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if((s = ensureWeights(ctx, lmax + 1)) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * (lmax + 1), cudaMemcpyHostToDevice, ctx->stream));
+    return launchLegendre(ctx, ctx->dWeights, 0, lmax, 1, colBegin, colEnd, dOut, 0);
+}
+
+cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch,
+                                       int64_t colBegin, int64_t colEnd, double* dOut, int64_t stride)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!a || nBatch < 1) return fail(ctx, CMG_EINVAL, "bad batch arguments");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if((s = ensureWeights(ctx, nBatch * (lmax + 1))) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * (lmax + 1), cudaMemcpyHostToDevice, ctx->stream));
+    return launchLegendre(ctx, ctx->dWeights, lmax + 1, lmax, nBatch, colBegin, colEnd, dOut, stride);
+}
+
+static cmg_status wholeCallTT(cmg_ctx* ctx, const std::vector<double>& a, int lmax, double* outPacked)
+{
+    const int64_t bytes = sizeof(double) * cmg_packed_size(ctx->npix);
+    cmg_status s = ensureScratch(ctx, bytes);
+    if(s != CMG_OK) return s;
+    if((s = cmg_legendre_series(ctx, a.data(), lmax, 0, ctx->npix, ctx->dScratch)) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CMG_OK;
+}
+
+cmg_status cmg_cl_to_cmatrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* outPacked)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!cl || !outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<double> f(lmax + 1), a(lmax + 1);
+    cmg_window_beam(f.data(), lmax, fwhm, pixwin);
+    cmg_tt_weights(cl, f.data(), lmax, a.data());
+    return wholeCallTT(ctx, a, lmax, outPacked);
+}
+
+cmg_status cmg_fiducial_matrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* outPacked)
+{
+    if(!ctx) return CMG_EINVAL;
+    const int lMaxMax = static_cast<int>(4 * ctx->nside);
+    cmg_status s = checkReady(ctx, lMaxMax);
+    if(s != CMG_OK) return s;
+    if(!cl || !outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<double> f(lMaxMax + 1), a(lMaxMax + 1);
+    cmg_window_beam(f.data(), lMaxMax, fwhm, pixwin);
+    cmg_fiducial_weights(cl, f.data(), ctx->nside, lmax, a.data());
+    return wholeCallTT(ctx, a, lMaxMax, outPacked);
+}
+
+cmg_status cmg_mask_matrix(cmg_ctx* ctx, const double* dIn, int64_t npixIn, const int32_t* good, int64_t nGood, double* dOut)
+{
+    if(!ctx || !dIn || !good || !dOut || nGood < 1 || npixIn < 1) return CMG_EINVAL;
+    for(int64_t k = 0; k < nGood; ++k)
+        if(good[k] < 0 || good[k] >= npixIn)
+            return fail(ctx, CMG_EINVAL, "good pixel index outside the input matrix");
+    if(nGood > 65535)
+        return fail(ctx, CMG_EUNSUPPORTED, "maskMatrix gather is limited to 65535 good pixels per call");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if(nGood > ctx->indexCap)
+    {
+        if(ctx->dIndex)
+        {
+            CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            CMG_CUDA(ctx, cudaFree(ctx->dIndex));
+            ctx->dIndex = nullptr;
+            ctx->indexCap = 0;
+        }
+        CMG_CUDA(ctx, cudaMalloc(&ctx->dIndex, sizeof(int32_t) * nGood));
+        ctx->indexCap = nGood;
+    }
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dIndex, good, sizeof(int32_t) * nGood, cudaMemcpyHostToDevice, ctx->stream));
+    const dim3 grid(static_cast<unsigned>((nGood + 255) / 256), static_cast<unsigned>(nGood));
+    cmg::maskGatherKernel<<<grid, 256, 0, ctx->stream>>>(dIn, ctx->dIndex, nGood, dOut);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
+}
+
+// ---------------------------------------------------------------- T,Q,U
+
+cmg_status cmg_tqu_layout_single(cmg_ctx* ctx, double* dPacked, cmg_tqu_layout* layout)
+{
+    if(!ctx || !layout || !dPacked) return CMG_EINVAL;
+    if(ctx->npix <= 0) return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
+    std::memset(layout, 0, sizeof(*layout));
+    const int64_t n = ctx->npix;
+    layout->n_parts = 1;
+    layout->own = 0;
+    layout->begin[0] = 0;
+    layout->begin[1] = n;
+    layout->ptr[0][0] = dPacked;
+    layout->ptr[0][1] = dPacked + cmg_packed_size(n);          // entry (0, N)
+    layout->ptr[0][2] = dPacked + cmg_packed_size(2 * n);      // entry (0, 2N)
+    return CMG_OK;
+}
+
+cmg_status cmg_tqu(cmg_ctx* ctx, const double* att, const double* ate, const double* aee, const double* abb, int lmax,
+                   const cmg_tqu_layout* layout)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!att || !ate || !aee || !abb) return fail(ctx, CMG_EINVAL, "null weights");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n1 = lmax + 1;
+    if((s = ensureWeights(ctx, 4 * n1)) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, att, sizeof(double) * n1, cudaMemcpyHostToDevice, ctx->stream));
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights + n1, ate, sizeof(double) * n1, cudaMemcpyHostToDevice, ctx->stream));
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights + 2 * n1, aee, sizeof(double) * n1, cudaMemcpyHostToDevice, ctx->stream));
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights + 3 * n1, abb, sizeof(double) * n1, cudaMemcpyHostToDevice, ctx->stream));
+    return launchTqu(ctx, ctx->dWeights, 0, lmax, 1, layout, 0);
+}
+
+cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch, double* dOut, int64_t stride)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!a || !dOut || nBatch < 1) return fail(ctx, CMG_EINVAL, "bad batch arguments");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t per = 4 * (lmax + 1);
+    if((s = ensureWeights(ctx, nBatch * per)) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
+    cmg_tqu_layout layout;
+    if((s = cmg_tqu_layout_single(ctx, dOut, &layout)) != CMG_OK) return s;
+    return launchTqu(ctx, ctx->dWeights, per, lmax, nBatch, &layout, stride);
+}
+
+cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee, const double* cbb,
+                                 int lmax, double fwhm, const double* pixwinT, const double* pixwinP, double* outPacked)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!ctt || !cte || !cee || !cbb || !outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n1 = lmax + 1;
+    std::vector<double> fT(n1), fP(n1), a(4 * n1);
+    cmg_window_beam(fT.data(), lmax, fwhm, pixwinT);
+    cmg_window_beam(fP.data(), lmax, fwhm, pixwinP);
+    cmg_tqu_weights(ctt, cte, cee, cbb, fT.data(), fP.data(), lmax, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1);
+    const int64_t bytes = sizeof(double) * cmg_packed_size(3 * ctx->npix);
+    if((s = ensureScratch(ctx, bytes)) != CMG_OK) return s;
+    cmg_tqu_layout layout;
+    if((s = cmg_tqu_layout_single(ctx, ctx->dScratch, &layout)) != CMG_OK) return s;
+    if((s = cmg_tqu(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, &layout)) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CMG_OK;
+}
+
+// ---------------------------------------------------------------- measurement
+
+cmg_status cmg_measure_fp64_peak(cmg_ctx* ctx, double* tflops)
+{
+    if(!ctx || !tflops) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CMG_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    double* sink = nullptr;
+    CMG_CUDA(ctx, cudaMalloc(&sink, sizeof(double)));
+    const int blocks = prop.multiProcessorCount * 16;
+    double best = 0.0;
+    for(int rep = 0; rep < 6; ++rep)
+    {
+        CMG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        for(int k = 0; k < 4; ++k)
+            cmg::fp64PeakKernel<<<blocks, 256, 0, ctx->stream>>>(sink, 1.0000001, 0.9999999);
+        CMG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CMG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CMG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flop = 4.0 * blocks * 256.0 * cmg::PEAK_CHAINS * cmg::PEAK_ITERS * 2.0;
+        if(rep > 0)
+            best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    CMG_CUDA(ctx, cudaFree(sink));
+    *tflops = best;
+    return CMG_OK;
+}
+
+cmg_status cmg_last_kernel_ms(cmg_ctx* ctx, double* ms)
+{
+    if(!ctx || !ms) return CMG_EINVAL;
+    *ms = ctx->lastMs;
+    return CMG_OK;
+}
+
+cmg_status cmg_set_timing(cmg_ctx* ctx, int enabled)
+{
+    if(!ctx) return CMG_EINVAL;
+    ctx->timing = enabled != 0;
+    return CMG_OK;
+}
+
+} // extern "C"

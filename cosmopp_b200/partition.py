@@ -1,0 +1,48 @@
+"""Host-side sharding of the packed upper triangle over GPUs.
+
+Every entry depends only on replicated inputs (pixel frames, C_l), so the path shards with no
+data-path collective: rank r computes all pixel pairs (i <= j) whose column j lies in its block of
+pixel columns.  Column j holds j+1 pairs, so blocks of equal *area* have boundaries ~ N sqrt(k/G).
+For TT the rank's output is one contiguous piece of the packed triangle; for [T;Q;U] it is the three
+column strips j, N+j, 2N+j of its block (include/cmg.h, cmg_tqu_layout).
+"""
+import math
+
+
+def packed_size(dim):
+    return dim * (dim + 1) // 2
+
+
+def column_partition(npix, n_parts, align=32):
+    """Boundaries b[0..n_parts] (b[0]=0, b[-1]=npix) of equal-work pixel-column blocks, interior
+    boundaries rounded to a multiple of `align` (the kernels' column tile)."""
+    if n_parts < 1:
+        raise ValueError("n_parts must be >= 1")
+    b = [0]
+    for k in range(1, n_parts):
+        x = npix * math.sqrt(k / n_parts)
+        v = int(round(x / align)) * align
+        v = max(b[-1], min(npix, v))
+        b.append(v)
+    b.append(npix)
+    return b
+
+
+def pairs_in_block(begin, end):
+    """pixel pairs (i <= j) with begin <= j < end"""
+    return packed_size(end) - packed_size(begin)
+
+
+def tt_shard_size(begin, end):
+    """doubles in the contiguous packed piece holding columns [begin, end)"""
+    return packed_size(end) - packed_size(begin)
+
+
+def tqu_shard_sizes(npix, begin, end):
+    """doubles in the T, Q and U strips (columns s*npix + [begin, end)) of a [T;Q;U] matrix"""
+    return [packed_size(s * npix + end) - packed_size(s * npix + begin) for s in range(3)]
+
+
+def tqu_strip_offsets(npix, begin):
+    """offsets of entry (0, s*npix + begin) inside one whole packed 3N matrix"""
+    return [packed_size(s * npix + begin) for s in range(3)]

@@ -1,0 +1,199 @@
+/* cmg.h -- C ABI of the B200-native pixel-covariance (C-matrix) generator.
+ *
+ * This is the drop-in boundary for ONE hot path of Cosmo++ (aslanyan/cosmopp):
+ * CMatrixGenerator -> CMatrix, the pixel-space CMB signal covariance.  The reference has no
+ * FFI layer for this path (it is plain C++: include/c_matrix.hpp, include/c_matrix_generator.hpp),
+ * so the entry points below are what a binding of those two classes needs; each one names the
+ * reference code it replaces.  The C++ classes in include/c_matrix.hpp and
+ * include/c_matrix_generator.hpp of THIS repository are thin wrappers over this ABI.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all sizes/indices are int64_t (the reference's 32-bit `int`
+ *     indices overflow for nPix > 46340, reference source/c_matrix.cpp:24,36);
+ *   - every function returns a cmg_status (0 = ok) unless documented otherwise and never throws;
+ *     cmg_last_error() gives the text (the C++ wrappers turn it into StandardException, the
+ *     reference's error convention, include/exception_handler.hpp:10-31);
+ *   - "packed" = upper triangle, column-major: entry (i<=j) at j(j+1)/2+i
+ *     (reference source/c_matrix.cpp:27-39; identical to LAPACK 'U' packed storage);
+ *   - polarized matrices use rows/cols [T_0..T_{N-1}, Q_0..Q_{N-1}, U_0..U_{N-1}] (the reference's
+ *     [Q;U] convention, source/c_matrix_generator.cpp:678-681, with T in front), Q,U in the local
+ *     (e_theta, e_phi) basis, HEALPix-primer sign convention;
+ *   - pointers named d_* are device pointers on the context's GPU (or peer-mapped memory of
+ *     another GPU where stated); all others are host pointers;
+ *   - a context is bound to one GPU and one stream; calls on different contexts are independent
+ *     and may be made concurrently from several host threads (no hidden globals).  There is no
+ *     CPU fallback: without a usable sm_100 device cmg_create fails.
+ */
+#ifndef CMG_H
+#define CMG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmg_ctx cmg_ctx;
+
+typedef enum cmg_status {
+    CMG_OK = 0,
+    CMG_EINVAL = 1,        /* bad argument */
+    CMG_ECUDA = 2,         /* CUDA runtime / launch failure (text in cmg_last_error) */
+    CMG_ENOMEM = 3,        /* host or device allocation failed */
+    CMG_ESTATE = 4,        /* call order: geometry not set, ... */
+    CMG_EUNSUPPORTED = 5   /* size beyond what the kernels are built for (lmax > CMG_LMAX_LIMIT) */
+} cmg_status;
+
+#define CMG_LMAX_LIMIT 1023   /* series length the kernels stage in shared memory */
+#define CMG_MAX_PARTS 16      /* column-block owners in a sharded polarized layout */
+
+/* ---------------------------------------------------------------- context ------------------- */
+
+int cmg_version(void);
+/* number of visible CUDA devices (0 when there is no driver/GPU) */
+int cmg_device_count(void);
+/* binds to `device`; fails with CMG_ECUDA when no sm_100 GPU is usable (no CPU fallback) */
+cmg_status cmg_create(cmg_ctx** ctx, int device);
+void cmg_destroy(cmg_ctx* ctx);
+/* text of the last failure on this context (ctx == NULL: last failure of cmg_create on this thread) */
+const char* cmg_last_error(const cmg_ctx* ctx);
+/* launch on a caller-owned cudaStream_t (e.g. torch's current stream; NULL is the legacy default
+ * stream).  A new context launches on a private non-blocking stream until this is called. */
+cmg_status cmg_set_stream(cmg_ctx* ctx, void* cuda_stream);
+/* go back to the context's private stream */
+cmg_status cmg_use_own_stream(cmg_ctx* ctx);
+cmg_status cmg_synchronize(cmg_ctx* ctx);
+/* number of generator kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t cmg_launch_count(const cmg_ctx* ctx);
+
+/* device memory helpers for hosts that do not bring their own allocator (the C++ drop-in) */
+cmg_status cmg_device_malloc(cmg_ctx* ctx, int64_t bytes, void** d_ptr);
+cmg_status cmg_device_free(cmg_ctx* ctx, void* d_ptr);
+cmg_status cmg_host_malloc_pinned(int64_t bytes, void** ptr);
+cmg_status cmg_host_free_pinned(void* ptr);
+/* stream-ordered copies on the context's stream */
+cmg_status cmg_copy_to_host(cmg_ctx* ctx, void* dst_host, const void* d_src, int64_t bytes);
+cmg_status cmg_copy_to_device(cmg_ctx* ctx, void* d_dst, const void* src_host, int64_t bytes);
+
+/* ------------------------------------------- host pieces of the path (pure CPU, O(N) or O(lmax)) */
+
+/* chealpix nside2npix / pix2ang_nest, call sites reference source/c_matrix_generator.cpp:34,42,170,182 */
+int64_t cmg_nside2npix(int64_t nside);
+cmg_status cmg_pix2ang_nest(int64_t nside, int64_t ipix, double* theta, double* phi);
+/* CMatrix::getIndex / storage size, reference source/c_matrix.cpp:19-39 (64-bit) */
+int64_t cmg_packed_size(int64_t dim);
+int64_t cmg_packed_index(int64_t i, int64_t j);
+/* Utils::readMask selection rule, reference source/utils.cpp:45-51: ascending i with mask[i] > 0.5.
+ * good must hold npix entries; *n_good receives the count. */
+cmg_status cmg_good_pixels_from_mask(const double* mask, int64_t npix, int32_t* good, int64_t* n_good);
+/* Utils::beamFunction, reference source/utils.cpp:54-64 (fwhm in degrees; 0 => 1) */
+double cmg_beam_function(int l, double fwhm_deg);
+/* Utils::readPixelWindowFunction arithmetic, reference source/utils.cpp:154-160:
+ * f[l] = pixwin[l] * beam(l), l = 0..lmax; pixwin == NULL => window 1 */
+cmg_status cmg_window_beam(double* f, int lmax, double fwhm_deg, const double* pixwin);
+
+/* ---------------------------------------------------------------- geometry ------------------ */
+
+/* Pixel set of all following generate calls: HEALPix NESTED indices good_nest[0..n_good) in the
+ * caller's order (NULL => all 12 nside^2 pixels).  Computes unit vectors exactly as reference
+ * source/c_matrix_generator.cpp:178-185 (host libm, so they are bit-identical to the reference's)
+ * plus the local (e_theta, e_phi) bases, and keeps them resident on the GPU. */
+cmg_status cmg_set_pixels(cmg_ctx* ctx, int64_t nside, const int32_t* good_nest, int64_t n_good);
+int64_t cmg_npix(const cmg_ctx* ctx);
+/* copy back the resident geometry: out[8][npix] = x,y,z, e_theta(x,y,z), e_phi(x,y) */
+cmg_status cmg_get_geometry(cmg_ctx* ctx, double* out);
+
+/* ---------------------------------------------------------------- TT generation ------------- */
+
+/* Columns [col_begin, col_end) of  S_ij = sum_{l=0}^{lmax} a[l] P_l(n_i.n_j)  into d_out, whose first
+ * element is entry (0, col_begin) (so a rank's shard is one contiguous piece of the packed triangle).
+ * a[] is a HOST array of lmax+1 series weights.  This one entry point serves
+ *   clToCMatrix        a[l] = cl[l](2l+1)/(4pi) B_l^2, l>=2          (reference c_matrix_generator.cpp:164-232)
+ *   getFiducialMatrix  a[l] = that for lmax<l<=4nside, a[0]=a[1]=100 cl[2] B_2^2   (:705-772; (1+z) = P_0+P_1)
+ */
+cmg_status cmg_legendre_series(cmg_ctx* ctx, const double* a, int lmax,
+                               int64_t col_begin, int64_t col_end, double* d_out);
+/* same, with the lmax+1 weights already resident on the device (batched / graph-replayed use) */
+cmg_status cmg_legendre_series_dev(cmg_ctx* ctx, const double* d_a, int lmax,
+                                   int64_t col_begin, int64_t col_end, double* d_out);
+
+/* weights of clToCMatrix from C_l and the window*beam factors f[l] (cmg_window_beam): a[0]=a[1]=0 */
+cmg_status cmg_tt_weights(const double* cl, const double* f, int lmax, double* a);
+/* weights of getFiducialMatrix: cl and f hold 4*nside+1 entries, a receives 4*nside+1 */
+cmg_status cmg_fiducial_weights(const double* cl, const double* f, int64_t nside, int lmax, double* a);
+
+/* Whole-call equivalents of the reference API with HOST output (device work + copy back):
+ * CMatrixGenerator::clToCMatrix(cl, nSide, fwhm, goodPixels) -- geometry must have been set with the
+ * same nside/goodPixels.  out_packed holds npix(npix+1)/2 doubles (pinned memory makes the copy faster). */
+cmg_status cmg_cl_to_cmatrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm_deg,
+                             const double* pixwin, double* out_packed);
+cmg_status cmg_fiducial_matrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm_deg,
+                               const double* pixwin, double* out_packed);
+/* CMatrixGenerator::generateNoiseMatrix, reference c_matrix_generator.cpp:774-787 (host, trivial) */
+cmg_status cmg_noise_matrix(int64_t npix, double noise, double* out_packed);
+/* CMatrix::maskMatrix gather, reference source/c_matrix.cpp:182-201; device buffers */
+cmg_status cmg_mask_matrix(cmg_ctx* ctx, const double* d_in_packed, int64_t npix_in,
+                           const int32_t* good, int64_t n_good, double* d_out_packed);
+
+/* ---------------------------------------------------------------- T,Q,U generation ---------- */
+
+/* Where the entries of a (possibly sharded) polarized matrix live.  The 3N columns are owned in
+ * pixel-column blocks: part k owns pixel columns [begin[k], begin[k+1]) of each of the T, Q and U
+ * strips.  kind 0 (packed): ptr[s] is the address of entry (0, s*N + begin[k]) of a contiguous run
+ * of packed columns.  kind 1 (dense blocks; only for entries a rank computes on behalf of another
+ * owner): ptr[0..2] are three column-major blocks holding <Q_i T_j>, <U_i T_j>, <U_i Q_j> for
+ * owner-columns i in [begin[k], begin[k+1]) and rows j in [row0, row0+ld): element at
+ * ptr[t][(i-begin[k])*ld + (j-row0)].  Pointers may be peer-mapped memory of another GPU. */
+typedef struct cmg_tqu_layout {
+    int32_t n_parts;
+    int32_t own;                               /* the part whose pixel columns this call computes */
+    int64_t begin[CMG_MAX_PARTS + 1];
+    double* ptr[CMG_MAX_PARTS][3];
+    int32_t kind[CMG_MAX_PARTS];
+    int64_t ld[CMG_MAX_PARTS];
+    int64_t row0[CMG_MAX_PARTS];
+} cmg_tqu_layout;
+
+/* Fills a single-owner layout over one whole packed buffer of dimension 3N (n_parts = 1). */
+cmg_status cmg_tqu_layout_single(cmg_ctx* ctx, double* d_packed, cmg_tqu_layout* layout);
+
+/* All pixel pairs (i <= j), j in the pixel columns of part `own`: the 3x3 blocks
+ *   TT = sum a_tt[l] P_l,  <T Q'> = -sum a_te[l] d^l_20,  <QQ'>+<UU'> = sum (a_ee+a_bb)[l] d^l_22,
+ *   <QQ'>-<UU'> = sum (a_ee-a_bb)[l] d^l_2-2   (great-circle frame; F^10, F^12-+F^22 of Tegmark &
+ *   de Oliveira-Costa 2001), rotated into the local frames, scattered to all nine destinations.
+ * a_xx are HOST arrays of lmax+1 weights C^XX_l (2l+1)/(4pi) x window factors; entries l<2 ignored. */
+cmg_status cmg_tqu(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
+                   const double* a_bb, int lmax, const cmg_tqu_layout* layout);
+/* weights from spectra and the temperature / polarization window*beam factors */
+cmg_status cmg_tqu_weights(const double* ctt, const double* cte, const double* cee, const double* cbb,
+                           const double* fT, const double* fP, int lmax,
+                           double* a_tt, double* a_te, double* a_ee, double* a_bb);
+/* whole call with HOST output: out_packed holds 3N(3N+1)/2 doubles */
+cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee,
+                                 const double* cbb, int lmax, double fwhm_deg,
+                                 const double* pixwinT, const double* pixwinP, double* out_packed);
+
+/* ---------------------------------------------------------------- batched regeneration ------ */
+
+/* n_batch matrices for n_batch weight sets in one launch (one MCMC step's proposals):
+ * a[b][l], b < n_batch; d_out[b] receives columns [col_begin,col_end) of matrix b,
+ * consecutive matrices `stride` doubles apart. */
+cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t n_batch,
+                                       int64_t col_begin, int64_t col_end, double* d_out, int64_t stride);
+/* a[b][4][lmax+1] in the order tt, te, ee, bb; single-owner packed layout per batch element */
+cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t n_batch,
+                           double* d_out, int64_t stride);
+
+/* ---------------------------------------------------------------- measurement --------------- */
+
+/* dependent-free DFMA microbenchmark: achieved FP64 TFLOP/s on this GPU (the roofline denominator) */
+cmg_status cmg_measure_fp64_peak(cmg_ctx* ctx, double* tflops);
+/* milliseconds the last generate call's kernels took on the device (CUDA events on the launch stream) */
+cmg_status cmg_last_kernel_ms(cmg_ctx* ctx, double* ms);
+/* switch the per-call event timing on/off (off by default: it synchronises) */
+cmg_status cmg_set_timing(cmg_ctx* ctx, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMG_H */
