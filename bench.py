@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the C-matrix hot path (BASELINE.json): pixel-pair*l/s, FP64 roofline fraction, ms per matrix.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one generation of the whole covariance matrix of the workload from a C_l set.  Default
+workload is BASELINE config 5 (polarized T,Q,U matrix, HEALPix Nside=64, lmax=192: 147456 x 147456,
+87 GB packed); it fits one B200, and for N > 1 the SAME matrix is split over the ranks by equal-area
+pixel-column blocks (strong scaling, no data-path collective: every entry depends on replicated inputs).
+
+Numbers printed (one JSON line from rank 0):
+  value     pixel-pair*l/s over the K timed steps, inputs resident in HBM (geometry + C_l weights), CUDA events
+            on the launch stream, max over ranks;
+  e2e       the same metric through the reference-facing call with HOST buffers: C_l from pinned host memory
+            in, packed matrix (this rank's shard) copied back to pinned host memory, copies inside the timing;
+  roofline  algorithmic FLOP (20 per pixel-pair*l for T,Q,U; 4 for TT) / kernel time vs the FP64 peak
+            measured by cmg_measure_fp64_peak on this GPU (MEASURED_PEAKS.json has no FP64 entry);
+  cpu_baseline  the reference's own object code (oracle/_ref, TT generator) on a bounded sample, all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, nside, lmax, masked)
+    "tqu_nside64_lmax192": ("tqu", 64, 192, False),     # BASELINE configs[4]  (default; the metric's target config)
+    "tt_nside32_lmax96": ("tt", 32, 96, False),         # configs[2]
+    "tqu_nside16_lmax47_masked": ("tqu", 16, 47, True), # configs[1]
+    "tt_nside16_lmax47": ("tt", 16, 47, False),         # configs[0]
+    "tqu_nside32_lmax96": ("tqu", 32, 96, False),
+}
+FLOP_PER_UNIT = {"tt": 4.0, "tqu": 20.0}        # algorithmic FLOP per pixel-pair*l
+FWHM = 10.0
+UNIT = "pixel-pair*l/s"
+
+
+def dist_info():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, w in zip(sm, power) if w > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_geometry(name):
+    kind, nside, lmax, masked = WORKLOADS[name]
+    good = None
+    if masked:
+        # the reference test's deterministic mask (source/test_like_low.cpp:99-118), committed as a golden list
+        path = os.path.join(ROOT, "tests", "golden", "like_low_good_pixels_nside%d.npy" % nside)
+        good = np.load(path)
+    npix = 12 * nside * nside if good is None else len(good)
+    return kind, nside, lmax, good, npix
+
+
+# ------------------------------------------------------------------------------------------ reference arm / CPU baseline
+
+def reference_sample(kind, nside, lmax, budget_s=12.0, threads=None):
+    """Reference object code (oracle/_ref: CMatrixGenerator::clToCMatrix compiled from /root/reference, TT path) on a
+    bounded sample: `threads` concurrent instances, each one full small matrix over its own subset of the workload's
+    pixels, same lmax / beam / synthetic C_l.  Returns pixel-pair*l/s aggregate."""
+    from oracle import api
+    from cosmopp_b200.synthetic import synthetic_cl
+    threads = threads or os.cpu_count() or 1
+    cl = synthetic_cl(lmax)
+    have_ref = api.have_ref()
+    # per-pair cost of the reference grows like lmax^2 (Legendre restarted for every l): calibrate on 40 pixels
+    probe = np.arange(40, dtype=np.int32)
+    t0 = time.perf_counter()
+    (api.ref_cl_to_cmatrix if have_ref else lambda c, n, f, good: api.cl_to_cmatrix(c, n, f, good=good, literal=True))(cl, nside, FWHM, good=probe)
+    per_pair = (time.perf_counter() - t0) / (40 * 41 / 2)
+    n_sub = int(max(48, min(12 * nside * nside // threads, np.sqrt(2 * budget_s / per_pair))))
+    subsets = [np.arange(t * n_sub, (t + 1) * n_sub, dtype=np.int32) % (12 * nside * nside) for t in range(threads)]
+    done = [0.0] * threads
+
+    def work(t):
+        if have_ref:
+            api.ref_cl_to_cmatrix(cl, nside, FWHM, good=subsets[t])
+        else:
+            api.cl_to_cmatrix(cl, nside, FWHM, good=subsets[t], literal=True)
+        done[t] = time.perf_counter()
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    wall = max(done) - t0
+    pairs = threads * n_sub * (n_sub + 1) // 2
+    value = pairs * (lmax - 1) / wall
+    note = ""
+    if kind == "tqu":
+        note = "; TT block only - the reference has no TE/EE/BB pixel generator, so its cost per pixel-pair*l is a lower bound"
+    return {
+        "value": value, "unit": UNIT, "cores": threads, "kind": "reference" if have_ref else "port",
+        "sample": "%d concurrent instances of %s, each the full TT matrix of %d of the workload's pixels (%d pixel pairs in all), "
+                  "lmax=%d, fwhm=%g deg, %.1f s wall%s" % (threads, "the reference's clToCMatrix object code (oracle/_ref)" if have_ref else
+                                                          "the oracle's literal port of clToCMatrix", n_sub, pairs, lmax, FWHM, wall, note),
+        "wall_s": wall,
+    }
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_info()
+    if rank != 0:
+        return
+    kind, nside, lmax, good, npix = workload_geometry(args.workload)
+    for _ in range(min(args.warmup, 1)):
+        reference_sample(kind, nside, lmax, budget_s=2.0)
+    vals, walls = [], []
+    samples = None
+    for _ in range(args.steps):
+        r = reference_sample(kind, nside, lmax, budget_s=max(4.0, 60.0 / max(args.steps, 1)))
+        vals.append(r["value"]); walls.append(r["wall_s"]); samples = r
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "pixel_pair_ell_per_s", "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.workload, kind, nside, lmax, npix, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": samples["cores"], "kind": samples["kind"], "sample": samples["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def config_dict(name, kind, nside, lmax, npix, n_gpus):
+    dim = npix * (3 if kind == "tqu" else 1)
+    return {
+        "workload": name, "kind": kind, "nside": nside, "lmax": lmax, "npix": npix, "matrix_dim": dim,
+        "packed_bytes": 8 * dim * (dim + 1) // 2, "fwhm_deg": FWHM, "pixel_window": "1 (HEALPix window file unavailable offline)",
+        "sharding": "equal-area pixel-column blocks over %d rank(s), no collective" % n_gpus,
+        "l2": "each step writes its whole output (>> 126 MB L2) with streaming stores; nothing is re-read between steps",
+    }
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import cosmopp_b200 as cb
+    from cosmopp_b200 import capi, partition
+    from cosmopp_b200.synthetic import synthetic_cl
+
+    rank, world, local = dist_info()
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the generator has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    kind, nside, lmax, good, npix = workload_geometry(args.workload)
+    ctx = cb.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_pixels(nside, good)
+
+    f = capi.window_beam(lmax, FWHM)
+    bounds = partition.column_partition(npix, world, align=32)
+    a0, a1 = bounds[rank], bounds[rank + 1]
+    my_pairs = partition.pairs_in_block(a0, a1)
+    total_pairs = npix * (npix + 1) // 2
+    units_total = total_pairs * (lmax - 1)
+
+    if kind == "tt":
+        weights = capi.tt_weights(synthetic_cl(lmax), f)
+        shard = torch.empty(partition.tt_shard_size(a0, a1), dtype=torch.float64, device="cuda")
+        launch = lambda: ctx.legendre_series(weights, shard, a0, a1)
+        pieces = [shard]
+    else:
+        spectra = synthetic_cl(lmax, pol=True)
+        weights = capi.tqu_weights(*spectra, f, f)
+        sizes = partition.tqu_shard_sizes(npix, a0, a1)
+        strips = [torch.empty(s, dtype=torch.float64, device="cuda") for s in sizes]
+        lay = capi.TquLayout()
+        lay.n_parts = world
+        lay.own = rank
+        for k in range(world + 1):
+            lay.begin[k] = bounds[k]
+        outbox = []
+        for k in range(world):
+            if k == rank:
+                for s in range(3):
+                    lay.ptr[k][s] = strips[s].data_ptr()
+                lay.kind[k] = 0
+            elif k < rank and bounds[k + 1] > bounds[k]:
+                # entries <Q_i T_j>, <U_i T_j>, <U_i Q_j> this rank computes for owner-columns i of part k: dense blocks
+                blocks = [torch.empty((bounds[k + 1] - bounds[k]) * (a1 - a0), dtype=torch.float64, device="cuda") for _ in range(3)]
+                outbox.append(blocks)
+                for s in range(3):
+                    lay.ptr[k][s] = blocks[s].data_ptr()
+                lay.kind[k] = 1
+                lay.ld[k] = a1 - a0
+                lay.row0[k] = a0
+        launch = lambda: ctx.tqu(*weights, lay)
+        pieces = strips + [b for blk in outbox for b in blk]
+    d2h_bytes = sum(p.numel() for p in pieces) * 8
+    h2d_bytes = (len(weights) if kind == "tt" else 4 * (lmax + 1)) * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_tflops = ctx.measure_fp64_peak()
+
+    # ---- value: device-resident, K timed steps
+    for _ in range(max(args.warmup, 3)):
+        launch()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        launch()
+    e1.record(stream)
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = units_total / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel on this rank: its own pairs over its own time
+    kernel_ms = ms_local / args.steps
+    flop = FLOP_PER_UNIT[kind] * my_pairs * (lmax - 1)
+    achieved = flop / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof) and world == 1:
+        traffic = json.load(open(prof)).get(args.workload)
+    hbm_peak = None
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        hbm_peak = json.load(open(mp)).get("hbm_gbs")
+    roofline = {
+        "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
+        "peak_source": "cmg_measure_fp64_peak: dependent-free DFMA chains on this GPU in this run (MEASURED_PEAKS.json holds no FP64 figure)",
+        "algorithmic_flop_per_unit": FLOP_PER_UNIT[kind],
+        "hbm_write_gbs": d2h_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": hbm_peak,
+    }
+
+    # ---- e2e: host C_l in, host packed shard out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        if kind == "tqu" and world == 1:
+            del strips, pieces, lay
+            launch = None
+            torch.cuda.empty_cache()
+            host = torch.empty(capi.packed_size(3 * npix), dtype=torch.float64, pin_memory=True)
+            spectra_pinned = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in spectra]
+            step = lambda: ctx.cl_to_cmatrix_pol(*[s.numpy() for s in spectra_pinned], FWHM, host)      # reference-facing whole call
+        elif kind == "tt" and world == 1:
+            del shard, pieces
+            torch.cuda.empty_cache()
+            host = torch.empty(capi.packed_size(npix), dtype=torch.float64, pin_memory=True)
+            cl_pinned = torch.from_numpy(synthetic_cl(lmax)).pin_memory()
+            step = lambda: ctx.cl_to_cmatrix(cl_pinned.numpy(), FWHM, host)
+        else:
+            hosts = [torch.empty(p.numel(), dtype=torch.float64, pin_memory=True) for p in pieces]
+
+            def step():
+                launch()
+                for h, p in zip(hosts, pieces):
+                    h.copy_(p, non_blocking=True)
+                torch.cuda.synchronize()
+        step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        barrier()
+        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e = {"value": units_total * args.steps / float(wall.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * float(wall.item()) / args.steps,
+               "note": "per rank: C_l from pinned host memory, this rank's shard of the packed matrix back to pinned host memory"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = reference_sample(kind, nside, lmax, budget_s=12.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "pixel_pair_ell_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "ms_per_matrix": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "fp64_frac_of_peak": achieved / peak_tflops,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="tqu_nside64_lmax192", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

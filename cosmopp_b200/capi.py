@@ -89,6 +89,7 @@ _SIGNATURES = {
     "cmg_measure_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "cmg_set_kernel_variant": (ctypes.c_int, [_vp, ctypes.c_int]),
 }
 
 _lib = None
@@ -176,6 +177,9 @@ class Context:
 
     def set_timing(self, on):
         self._check(self._L.cmg_set_timing(self._h, 1 if on else 0))
+
+    def set_kernel_variant(self, v):
+        self._check(self._L.cmg_set_kernel_variant(self._h, int(v)))
 
     def last_kernel_ms(self):
         v = ctypes.c_double()

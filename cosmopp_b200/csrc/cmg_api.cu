@@ -40,6 +40,9 @@ struct cmg_ctx
     int32_t* dIndex = nullptr;       // maskMatrix indices
     int64_t indexCap = 0;
 
+    cmg::SeriesTable hostT0, hostT20, hostT22;   // host copies of the recurrence tables
+    int tquVariant = 0;                          // 0 = automatic choice (see launchTqu)
+
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false;
     double lastMs = 0.0;
@@ -186,13 +189,52 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
     return timer.finish();
 }
 
-size_t tquSmemBytes(int lmax)
+size_t tquSmemBytes(int lmax, bool isStatic)
 {
-    return sizeof(double4) * 2 * (lmax + 1) + sizeof(double) * (8 * cmg::PQ_TI + 8 * cmg::PQ_TJ + 3 * cmg::PQ_TI * cmg::PQ_STAGE_LD);
+    return (isStatic ? 0 : sizeof(double4) * 2 * (lmax + 1)) +
+           sizeof(double) * cmg::PQ_SMEM_DOUBLES;
 }
 
+// coefficient table of the static-table kernel (kernels.cuh, TquStaticTable) from host weights
+void fillStaticTable(const cmg_ctx* ctx, const double* att, const double* ate, const double* aee, const double* abb, int lmax,
+                     cmg::TquStaticTable& T)
+{
+    const cmg::SeriesTable& t0 = ctx->hostT0;
+    const cmg::SeriesTable& t20 = ctx->hostT20;
+    const cmg::SeriesTable& t22 = ctx->hostT22;
+    for(int i = 0; i < cmg::PQ_STATIC_STEPS; ++i)
+    {
+        const int k = cmg::PQ_STATIC_STEPS + 1 - i;
+        double4 A = make_double4(0.0, 0.0, 0.0, 0.0);
+        if(k <= lmax)
+        {
+            A.x = att[k] * t0.N[k];
+            A.y = ate[k] * t20.N[k] * 0.61237243569579452455;
+            A.z = (aee[k] + abb[k]) * t22.N[k] * 0.125;
+            A.w = (aee[k] - abb[k]) * t22.N[k] * 0.125;
+        }
+        T.s[2 * i] = A;
+        T.s[2 * i + 1] = make_double4(-t0.g[k + 1], -t20.g[k + 1], -t22.g[k + 1], t22.c[k]);
+    }
+    const double a1 = lmax >= 1 ? att[1] * t0.N[1] : 0.0;
+    T.s[2 * cmg::PQ_STATIC_STEPS] = make_double4(a1, -t0.g[2], att[0] * t0.N[0], -t0.g[1]);
+}
+
+template <int R, bool STATIC, int MINB>
+cmg_status launchTquVariant(cmg_ctx* ctx, const cmg::TquDynamicArgs& dyn, const cmg::TquStaticTable& T, int entryChunk,
+                            const cmg::PartTable& P, dim3 grid, int64_t outStride)
+{
+    const size_t smem = tquSmemBytes(dyn.lmax, STATIC);
+    auto kernel = cmg::tquKernel<R, STATIC, MINB>;
+    CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(geometryOf(ctx), dyn, T, entryChunk, P, outStride);
+    CMG_CUDA(ctx, cudaGetLastError());
+    return CMG_OK;
+}
+
+// hostWeights: the four host weight arrays when the caller has them (enables the static-table kernel)
 cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, int64_t nBatch,
-                     const cmg_tqu_layout* layout, int64_t outStride)
+                     const cmg_tqu_layout* layout, int64_t outStride, const double* const* hostWeights)
 {
     if(!layout || layout->n_parts < 1 || layout->n_parts > CMG_MAX_PARTS || layout->own < 0 || layout->own >= layout->n_parts)
         return fail(ctx, CMG_EINVAL, "bad layout: n_parts / own");
@@ -217,10 +259,7 @@ cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, 
         P.row0[k] = layout->row0[k];
         if(P.kind[k] != 0 && P.kind[k] != 1)
             return fail(ctx, CMG_EINVAL, "layout kind must be 0 (packed) or 1 (dense blocks)");
-        // parts at or before `own` receive entries; they need storage
-        if(k <= P.own && P.begin[k + 1] > P.begin[k] && (!P.ptr[k][0] && k == P.own))
-            return fail(ctx, CMG_EINVAL, "own part has no storage");
-        if(k < P.own && P.begin[k + 1] > P.begin[k] && (!P.ptr[k][1] || !P.ptr[k][2]))
+        if(k < P.own && P.begin[k + 1] > P.begin[k] && (!P.ptr[k][1] || !P.ptr[k][2] || (P.kind[k] == 1 && !P.ptr[k][0])))
             return fail(ctx, CMG_EINVAL, "a part left of own has no storage for the transposed entries");
     }
     if(P.kind[P.own] != 0 || !P.ptr[P.own][0] || !P.ptr[P.own][1] || !P.ptr[P.own][2])
@@ -234,12 +273,41 @@ cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, 
     const int64_t colBlocks = (colEnd - colBegin + cmg::PQ_TJ - 1) / cmg::PQ_TJ;
     if(colBlocks > 65535)
         return fail(ctx, CMG_EUNSUPPORTED, "too many column blocks for one launch");
-    const size_t smem = tquSmemBytes(lmax);
-    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::tquKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const dim3 grid(static_cast<unsigned>(rowBlocks), static_cast<unsigned>(colBlocks), static_cast<unsigned>(nBatch));
+
+    cmg::TquDynamicArgs dyn;
+    dyn.a = dA;
+    dyn.aStride = aStride;
+    dyn.tab = tablesOf(ctx);
+    dyn.lmax = lmax;
+
+    // variant code: 0 = automatic, else 100*static + 10*R + minBlocksPerSM, e.g. 123 = static table, R=2, 3 CTAs/SM;
+    // 22 = shared-memory table, R=2, 2 CTAs/SM
+    const bool canStatic = hostWeights && nBatch == 1 && lmax >= 2 && lmax <= cmg::PQ_STATIC_LMAX;
+    int variant = ctx->tquVariant;
+    if(variant == 0)
+        variant = canStatic ? 142 : 42;
+    if(variant >= 100 && !canStatic)
+        return fail(ctx, CMG_EINVAL, "static-table kernel needs host weights, one batch element and 2 <= lmax <= PQ_STATIC_LMAX");
+
+    static thread_local cmg::TquStaticTable T;      // 28 KB: keep it off the stack
+    int entryChunk = 0;
+    if(variant >= 100)
+    {
+        fillStaticTable(ctx, hostWeights[0], hostWeights[1], hostWeights[2], hostWeights[3], lmax, T);
+        entryChunk = (cmg::PQ_STATIC_STEPS + 1 - lmax) / cmg::PQ_STATIC_CHUNK;
+    }
     KernelTimer timer(ctx);
-    cmg::tquKernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(geometryOf(ctx), dA, aStride, tablesOf(ctx), lmax, P, outStride);
-    CMG_CUDA(ctx, cudaGetLastError());
+    cmg_status s = CMG_OK;
+    switch(variant)
+    {
+#define CMG_V(code, R, ST, MB) case code: s = launchTquVariant<R, ST, MB>(ctx, dyn, T, entryChunk, P, grid, outStride); break;
+    CMG_V(22, 2, false, 2) CMG_V(42, 4, false, 2) CMG_V(81, 8, false, 1)
+    CMG_V(114, 1, true, 4) CMG_V(122, 2, true, 2) CMG_V(123, 2, true, 3) CMG_V(124, 2, true, 4) CMG_V(142, 4, true, 2)
+#undef CMG_V
+    default: return fail(ctx, CMG_EINVAL, "unknown kernel variant");
+    }
+    if(s != CMG_OK) return s;
     ctx->launches += 1;
     return timer.finish();
 }
@@ -300,9 +368,12 @@ cmg_status cmg_create(cmg_ctx** out, int device)
 
     // recurrence tables, once per context
     std::vector<double> host(7 * kTabLen, 0.0);
-    const cmg::SeriesTable t0 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 0, 0);
-    const cmg::SeriesTable t20 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 2, 0);
-    const cmg::SeriesTable t22 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 2, 2);
+    ctx->hostT0 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 0, 0);
+    ctx->hostT20 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 2, 0);
+    ctx->hostT22 = cmg::makeSeriesTable(CMG_LMAX_LIMIT, 2, 2);
+    const cmg::SeriesTable& t0 = ctx->hostT0;
+    const cmg::SeriesTable& t20 = ctx->hostT20;
+    const cmg::SeriesTable& t22 = ctx->hostT22;
     for(int l = 0; l < kTabLen; ++l)
     {
         host[0 * kTabLen + l] = t0.N[l];
@@ -715,7 +786,8 @@ cmg_status cmg_tqu(cmg_ctx* ctx, const double* att, const double* ate, const dou
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights + n1, ate, sizeof(double) * n1, cudaMemcpyHostToDevice, ctx->stream));
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights + 2 * n1, aee, sizeof(double) * n1, cudaMemcpyHostToDevice, ctx->stream));
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights + 3 * n1, abb, sizeof(double) * n1, cudaMemcpyHostToDevice, ctx->stream));
-    return launchTqu(ctx, ctx->dWeights, 0, lmax, 1, layout, 0);
+    const double* hostW[4] = {att, ate, aee, abb};
+    return launchTqu(ctx, ctx->dWeights, 0, lmax, 1, layout, 0, hostW);
 }
 
 cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch, double* dOut, int64_t stride)
@@ -729,7 +801,7 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBat
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
     cmg_tqu_layout layout;
     if((s = cmg_tqu_layout_single(ctx, dOut, &layout)) != CMG_OK) return s;
-    return launchTqu(ctx, ctx->dWeights, per, lmax, nBatch, &layout, stride);
+    return launchTqu(ctx, ctx->dWeights, per, lmax, nBatch, &layout, stride, nullptr);
 }
 
 cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee, const double* cbb,
@@ -788,6 +860,13 @@ cmg_status cmg_last_kernel_ms(cmg_ctx* ctx, double* ms)
 {
     if(!ctx || !ms) return CMG_EINVAL;
     *ms = ctx->lastMs;
+    return CMG_OK;
+}
+
+cmg_status cmg_set_kernel_variant(cmg_ctx* ctx, int variant)
+{
+    if(!ctx || variant < 0) return CMG_EINVAL;
+    ctx->tquVariant = variant;
     return CMG_OK;
 }
 

@@ -69,14 +69,14 @@ __host__ __device__ inline long long packedOffset(long long col) { return col * 
 // ------------------------------------------------------------------------------------------------
 constexpr int TT_ROWS = 128;
 constexpr int TT_COLS = 16;
-constexpr int TT_R = 4;
+constexpr int TT_R = 8;
 
 __global__ void __launch_bounds__(TT_ROWS)
 legendreSeriesKernel(Geometry geo, const double* __restrict__ a, long long aStride,
                      const double* __restrict__ N0, const double* __restrict__ g0, int lmax,
                      long long colBegin, long long colEnd, double* __restrict__ out, long long outStride)
 {
-    extern __shared__ double2 ttTab[];      // [lmax + 1]  {a_k N_k, g_{k+1}}
+    extern __shared__ double2 ttTab[];      // [lmax + 1]  {a_k N_k, -g_{k+1}}
 
     const long long rowBlock = static_cast<long long>(blockIdx.x) * TT_ROWS;
     const long long c0 = colBegin + static_cast<long long>(blockIdx.y) * TT_COLS;
@@ -88,7 +88,7 @@ legendreSeriesKernel(Geometry geo, const double* __restrict__ a, long long aStri
     out += static_cast<long long>(blockIdx.z) * outStride;
 
     for(int k = threadIdx.x; k <= lmax; k += TT_ROWS)
-        ttTab[k] = make_double2(a[k] * N0[k], g0[k + 1]);
+        ttTab[k] = make_double2(a[k] * N0[k], -g0[k + 1]);
     __syncthreads();
 
     if(rowBlock + (threadIdx.x & ~31) > c1 - 1)
@@ -117,11 +117,12 @@ legendreSeriesKernel(Geometry geo, const double* __restrict__ a, long long aStri
 #pragma unroll 4
         for(int k = lmax; k >= 0; --k)
         {
-            const double2 t = ttTab[k];
+            const double2 t = ttTab[k];           // {a_k N_k, -g_{k+1}}
 #pragma unroll
             for(int r = 0; r < TT_R; ++r)
             {
-                const double b = fma(x2[r], b1[r], fma(-t.y, b2[r], t.x));
+                // (a + x2 b1) - g b2: one warp-uniform operand per DFMA (see tquStep)
+                const double b = fma(t.y, b2[r], fma(x2[r], b1[r], t.x));
                 b2[r] = b1[r];
                 b1[r] = b;
             }
@@ -150,8 +151,112 @@ legendreSeriesKernel(Geometry geo, const double* __restrict__ a, long long aStri
 constexpr int PQ_TI = 64;
 constexpr int PQ_TJ = 32;
 constexpr int PQ_THREADS = 256;
-constexpr int PQ_R = 2;
 constexpr int PQ_STAGE_LD = PQ_TJ + 1;
+
+// Static-table variant: the per-l coefficients travel in the kernel parameter block (constant bank 0)
+// at compile-time offsets, one fully unrolled Clenshaw step per table slot.  Only then does ptxas put
+// the multiplier coefficients in uniform registers (LDCU) and issue DFMA R, R, UR, R -- two vector
+// register reads instead of three.  Measured on B200 (tools/fp64_bank.cu): a DFMA reading three distinct
+// vector registers runs at <= 73% of the FP64 pipe rate (register-file bandwidth), so this matters more
+// than anything else in the loop.  The body is entered Duff-style at an 8-step boundary; slots above
+// lmax hold zero weights, which leave the (zero) Clenshaw state untouched.
+constexpr int PQ_STATIC_STEPS = 440;                 // 4-series steps k = PQ_STATIC_STEPS+1 .. 2
+constexpr int PQ_STATIC_CHUNK = 8;
+constexpr int PQ_STATIC_LMAX = PQ_STATIC_STEPS + 1;  // largest lmax the static table holds
+
+struct TquStaticTable
+{
+    // slot i <-> k = PQ_STATIC_STEPS + 1 - i:
+    //   s[2i]   = { a_tt N0,  a_te N20 sqrt(6)/4,  (a_ee+a_bb) N22 / 8,  (a_ee-a_bb) N22 / 8 }  at k
+    //   s[2i+1] = { -g0_{k+1}, -g20_{k+1}, -g22_{k+1}, c22_k }
+    // tail (TT only): s[2 STEPS] = { a_tt N0 at k=1, -g0_2, a_tt N0 at k=0, -g0_1 }
+    double4 s[2 * PQ_STATIC_STEPS + 1];
+};
+
+template <int R>
+struct TquState
+{
+    double x2[R];
+    double tt1[R], tt2[R], te1[R], te2[R], pp1[R], pp2[R], mm1[R], mm2[R];
+};
+
+// One Clenshaw step for R columns.  Association matters on this part: a DFMA whose three sources are
+// three different vector registers (none held by the operand-reuse cache) costs ~0.9 cycle more than the
+// pipe's 2-cycle rate (fitted over 20 loop variants, tools/exp/).  Written as (a + x2 b1) - g b2 every
+// operation carries exactly one warp-uniform coefficient (a, c or g), which ptxas keeps in the reuse
+// cache across the R columns; the textbook x2 b1 + (a - g b2) has an all-distinct outer operation.
+template <int R>
+__device__ __forceinline__ void tquStep(TquState<R>& s, const double4 A, const double4 G)
+{
+#pragma unroll
+    for(int r = 0; r < R; ++r)
+    {
+        const double t = fma(s.x2[r], s.tt1[r], A.x);
+        const double e = fma(s.x2[r], s.te1[r], A.y);
+        const double p = fma(s.x2[r], s.pp1[r], A.z);
+        const double m = fma(s.x2[r], s.mm1[r], A.w);
+        const double pu = fma(-G.w, s.pp1[r], p);
+        const double mu = fma(G.w, s.mm1[r], m);
+        const double tt = fma(G.x, s.tt2[r], t);
+        const double te = fma(G.y, s.te2[r], e);
+        const double pp = fma(G.z, s.pp2[r], pu);
+        const double mm = fma(G.z, s.mm2[r], mu);
+        s.tt2[r] = s.tt1[r]; s.tt1[r] = tt;
+        s.te2[r] = s.te1[r]; s.te1[r] = te;
+        s.pp2[r] = s.pp1[r]; s.pp1[r] = pp;
+        s.mm2[r] = s.mm1[r]; s.mm1[r] = mm;
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void tquStepTT(TquState<R>& s, const double a, const double g)
+{
+#pragma unroll
+    for(int r = 0; r < R; ++r)
+    {
+        const double tt = fma(g, s.tt2[r], fma(s.x2[r], s.tt1[r], a));
+        s.tt2[r] = s.tt1[r];
+        s.tt1[r] = tt;
+    }
+}
+
+template <int R, int C>
+__device__ __forceinline__ void tquStaticChunk(TquState<R>& s, const TquStaticTable& T)
+{
+#pragma unroll
+    for(int u = 0; u < PQ_STATIC_CHUNK; ++u)
+        tquStep<R>(s, T.s[2 * (C * PQ_STATIC_CHUNK + u)], T.s[2 * (C * PQ_STATIC_CHUNK + u) + 1]);
+}
+
+#define CMG_CASE(c) case c: tquStaticChunk<R, c>(s, T); [[fallthrough]];
+#define CMG_CASE5(b) CMG_CASE(b) CMG_CASE(b + 1) CMG_CASE(b + 2) CMG_CASE(b + 3) CMG_CASE(b + 4)
+
+template <int R>
+__device__ __forceinline__ void tquClenshawStatic(TquState<R>& s, const TquStaticTable& T, int entryChunk)
+{
+    static_assert(PQ_STATIC_STEPS == 55 * PQ_STATIC_CHUNK, "case list below covers 55 chunks");
+    switch(entryChunk)
+    {
+        CMG_CASE5(0) CMG_CASE5(5) CMG_CASE5(10) CMG_CASE5(15) CMG_CASE5(20) CMG_CASE5(25)
+        CMG_CASE5(30) CMG_CASE5(35) CMG_CASE5(40) CMG_CASE5(45) CMG_CASE5(50)
+        default: break;
+    }
+    const double4 tail = T.s[2 * PQ_STATIC_STEPS];
+    tquStepTT<R>(s, tail.x, tail.y);
+    tquStepTT<R>(s, tail.z, tail.w);
+}
+
+template <int R>
+__device__ __forceinline__ void tquClenshawShared(TquState<R>& s, const double4* tab4, int lmax)
+{
+    // tab4[2k] = A(k), tab4[2k+1] = G(k) in the same convention as the static table
+#pragma unroll 2
+    for(int k = lmax; k >= 2; --k)
+        tquStep<R>(s, tab4[2 * k], tab4[2 * k + 1]);
+    const double4 a1 = tab4[2], g1 = tab4[3], a0 = tab4[0], g0 = tab4[1];
+    tquStepTT<R>(s, a1.x, g1.x);
+    tquStepTT<R>(s, a0.x, g0.x);
+}
 
 __device__ inline double* partEntry(const PartTable& P, int k, int strip, long long npix, long long pixCol, long long row)
 {
@@ -169,15 +274,30 @@ __device__ inline int ownerOf(const PartTable& P, long long pixCol)
     return k;
 }
 
-__global__ void __launch_bounds__(PQ_THREADS, 2)
-tquKernel(Geometry geo, const double* __restrict__ a, long long aStride, DeviceTables tab, int lmax,
+struct TquDynamicArgs
+{
+    const double* a;        // [batch][4][lmax+1]  tt, te, ee, bb weights
+    long long aStride;
+    DeviceTables tab;
+    int lmax;
+};
+
+// shared-memory footprint of tquKernel besides the (dynamic-variant) coefficient table
+constexpr int PQ_SMEM_DOUBLES = 8 * PQ_TI + 8 * PQ_TJ + 3 * PQ_TI * PQ_STAGE_LD + 3 * PQ_TJ + 3 * PQ_TI;
+
+template <int R, bool STATIC, int MINB>
+__global__ void __launch_bounds__(PQ_THREADS, MINB)
+tquKernel(Geometry geo, TquDynamicArgs dyn, const __grid_constant__ TquStaticTable T, int entryChunk,
           const __grid_constant__ PartTable P, long long outStride)
 {
     extern __shared__ double4 pqSmem[];
-    double4* tab4 = pqSmem;                                          // [2 (lmax+1)]
-    double* sI = reinterpret_cast<double*>(tab4 + 2 * (lmax + 1));   // [8][PQ_TI]
-    double* sJ = sI + 8 * PQ_TI;                                     // [8][PQ_TJ]
-    double* stage = sJ + 8 * PQ_TJ;                                  // [3][PQ_TI][PQ_STAGE_LD]
+    const int tabSlots = STATIC ? 0 : 2 * (dyn.lmax + 1);
+    double4* tab4 = pqSmem;                                          // [2 (lmax+1)] (dynamic variant only)
+    double* sI = reinterpret_cast<double*>(tab4 + tabSlots);         // [8][PQ_TI]  frames of the tile's rows
+    double* sJ = sI + 8 * PQ_TI;                                     // [8][PQ_TJ]  frames of the tile's columns
+    double* stage = sJ + 8 * PQ_TJ;                                  // [3][PQ_TI][PQ_STAGE_LD] transposed partners
+    double** sColPtr = reinterpret_cast<double**>(stage + 3 * PQ_TI * PQ_STAGE_LD);   // [3][PQ_TJ] row 0 of columns j, N+j, 2N+j
+    double** sRowPtr = sColPtr + 3 * PQ_TJ;                          // [3][PQ_TI] destination of (kind t, row i) at column c0
 
     const long long npix = geo.npix;
     const long long colBegin = P.begin[P.own], colEnd = P.begin[P.own + 1];
@@ -187,35 +307,38 @@ tquKernel(Geometry geo, const double* __restrict__ a, long long aStride, DeviceT
     if(rowBlock > c1 - 1)
         return;
 
-    a += static_cast<long long>(blockIdx.z) * aStride;
     const long long batchOff = static_cast<long long>(blockIdx.z) * outStride;
-
     const int tid = threadIdx.x;
-    for(int k = tid; k <= lmax; k += PQ_THREADS)
+
+    if(!STATIC)
     {
-        const double* att = a;
-        const double* ate = a + (lmax + 1);
-        const double* aee = a + 2 * (lmax + 1);
-        const double* abb = a + 3 * (lmax + 1);
-        double4 t0, t1;
-        t0.x = att[k] * tab.N0[k];
-        t0.y = tab.g0[k + 1];
-        if(k >= 2)
+        const int lmax = dyn.lmax;
+        const double* att = dyn.a + static_cast<long long>(blockIdx.z) * dyn.aStride;
+        const double* ate = att + (lmax + 1);
+        const double* aee = att + 2 * (lmax + 1);
+        const double* abb = att + 3 * (lmax + 1);
+        for(int k = tid; k <= lmax; k += PQ_THREADS)
         {
-            t0.z = ate[k] * tab.N20[k] * 0.61237243569579452455;     // sqrt(6)/4 = d^2_20 / (1 - z^2)
-            t0.w = tab.g20[k + 1];
-            t1.x = (aee[k] + abb[k]) * tab.N22[k] * 0.125;            // 1/4 from d^2_2+-2, 1/2 from Re(A+-B)/2
-            t1.y = tab.g22[k + 1];
-            t1.z = (aee[k] - abb[k]) * tab.N22[k] * 0.125;
-            t1.w = tab.c22[k];
+            double4 A, G;
+            A.x = att[k] * dyn.tab.N0[k];
+            G.x = -dyn.tab.g0[k + 1];
+            if(k >= 2)
+            {
+                A.y = ate[k] * dyn.tab.N20[k] * 0.61237243569579452455;     // sqrt(6)/4 = d^2_20 / (1 - z^2)
+                A.z = (aee[k] + abb[k]) * dyn.tab.N22[k] * 0.125;            // 1/4 from d^2_2+-2, 1/2 from Re(A+-B)/2
+                A.w = (aee[k] - abb[k]) * dyn.tab.N22[k] * 0.125;
+                G.y = -dyn.tab.g20[k + 1];
+                G.z = -dyn.tab.g22[k + 1];
+                G.w = dyn.tab.c22[k];
+            }
+            else
+            {
+                A.y = A.z = A.w = 0.0;
+                G.y = G.z = G.w = 0.0;
+            }
+            tab4[2 * k] = A;
+            tab4[2 * k + 1] = G;
         }
-        else
-        {
-            t0.z = 0.0; t0.w = 0.0;
-            t1 = make_double4(0.0, 0.0, 0.0, 0.0);
-        }
-        tab4[2 * k] = t0;
-        tab4[2 * k + 1] = t1;
     }
     for(int idx = tid; idx < PQ_TI + PQ_TJ; idx += PQ_THREADS)
     {
@@ -233,6 +356,36 @@ tquKernel(Geometry geo, const double* __restrict__ a, long long aStride, DeviceT
         dst[6 * ld + loc] = geo.px[pix];
         dst[7 * ld + loc] = geo.py[pix];
     }
+    // destination pointers, once per tile instead of once per entry: the 64-bit packed-offset arithmetic and the
+    // owner lookup are warp-uniform, and every non-FP64 instruction in the epilogue costs an FP64 issue cycle
+    for(int idx = tid; idx < 3 * PQ_TJ + 3 * PQ_TI; idx += PQ_THREADS)
+    {
+        if(idx < 3 * PQ_TJ)
+        {
+            const int strip = idx / PQ_TJ;
+            const long long jcol = min(c0 + (idx - strip * PQ_TJ), colEnd - 1);
+            sColPtr[idx] = partEntry(P, P.own, strip, npix, jcol, 0) + batchOff;
+        }
+        else
+        {
+            const int q = idx - 3 * PQ_TJ;
+            const int t = q / PQ_TI;
+            const long long ir = min(rowBlock + (q - t * PQ_TI), npix - 1);
+            const int k = ownerOf(P, ir);
+            double* dst;
+            if(P.kind[k] == 0)
+            {
+                if(t == 0) dst = partEntry(P, k, 1, npix, ir, c0);              // Q_i T_j -> col N+i, row j
+                else if(t == 1) dst = partEntry(P, k, 2, npix, ir, c0);         // U_i T_j -> col 2N+i, row j
+                else dst = partEntry(P, k, 2, npix, ir, npix + c0);             // U_i Q_j -> col 2N+i, row N+j
+            }
+            else
+            {
+                dst = P.ptr[k][t] + ((ir - P.begin[k]) * P.ld[k] + (c0 - P.row0[k]));
+            }
+            sRowPtr[q] = dst + batchOff;
+        }
+    }
     __syncthreads();
 
     const int lane = tid & 31, warp = tid >> 5;
@@ -243,70 +396,37 @@ tquKernel(Geometry geo, const double* __restrict__ a, long long aStride, DeviceT
 
     const double nix = sI[0 * PQ_TI + il], niy = sI[1 * PQ_TI + il], niz = sI[2 * PQ_TI + il];
 
-    double* const ownT = P.ptr[P.own][0] + batchOff;
-    double* const ownQ = P.ptr[P.own][1] + batchOff;
-    double* const ownU = P.ptr[P.own][2] + batchOff;
-    const long long firstT = packedOffset(colBegin);
-    const long long firstQ = packedOffset(npix + colBegin);
-    const long long firstU = packedOffset(2 * npix + colBegin);
-
     if(warpLive)
     {
-        for(int pass = 0; pass < 8 / PQ_R; ++pass)
+        for(int pass = 0; pass < 8 / R; ++pass)
         {
-            const int jl0 = colGroup * 8 + pass * PQ_R;
+            const int jl0 = colGroup * 8 + pass * R;
             if(c0 + jl0 >= c1)
                 break;
-            double x2[PQ_R];
-            double tt1[PQ_R], tt2[PQ_R], te1[PQ_R], te2[PQ_R], pp1[PQ_R], pp2[PQ_R], mm1[PQ_R], mm2[PQ_R];
+            TquState<R> st;
 #pragma unroll
-            for(int r = 0; r < PQ_R; ++r)
+            for(int r = 0; r < R; ++r)
             {
                 const int jl = jl0 + r;
                 double dot = __dadd_rn(__dadd_rn(__dmul_rn(nix, sJ[0 * PQ_TJ + jl]), __dmul_rn(niy, sJ[1 * PQ_TJ + jl])),
                                        __dmul_rn(niz, sJ[2 * PQ_TJ + jl]));
                 dot = fmin(1.0, fmax(-1.0, dot));
-                x2[r] = dot + dot;
-                tt1[r] = tt2[r] = te1[r] = te2[r] = pp1[r] = pp2[r] = mm1[r] = mm2[r] = 0.0;
+                st.x2[r] = dot + dot;
+                st.tt1[r] = st.tt2[r] = st.te1[r] = st.te2[r] = st.pp1[r] = st.pp2[r] = st.mm1[r] = st.mm2[r] = 0.0;
             }
-#pragma unroll 2
-            for(int k = lmax; k >= 2; --k)
-            {
-                const double4 t0 = tab4[2 * k];
-                const double4 t1 = tab4[2 * k + 1];
-#pragma unroll
-                for(int r = 0; r < PQ_R; ++r)
-                {
-                    const double tt = fma(x2[r], tt1[r], fma(-t0.y, tt2[r], t0.x));
-                    const double te = fma(x2[r], te1[r], fma(-t0.w, te2[r], t0.z));
-                    const double pp = fma(x2[r], pp1[r], fma(-t1.w, pp1[r], fma(-t1.y, pp2[r], t1.x)));
-                    const double mm = fma(x2[r], mm1[r], fma(t1.w, mm1[r], fma(-t1.y, mm2[r], t1.z)));
-                    tt2[r] = tt1[r]; tt1[r] = tt;
-                    te2[r] = te1[r]; te1[r] = te;
-                    pp2[r] = pp1[r]; pp1[r] = pp;
-                    mm2[r] = mm1[r]; mm1[r] = mm;
-                }
-            }
-#pragma unroll
-            for(int k = 1; k >= 0; --k)
-            {
-                const double4 t0 = tab4[2 * k];
-#pragma unroll
-                for(int r = 0; r < PQ_R; ++r)
-                {
-                    const double tt = fma(x2[r], tt1[r], fma(-t0.y, tt2[r], t0.x));
-                    tt2[r] = tt1[r]; tt1[r] = tt;
-                }
-            }
+            if(STATIC)
+                tquClenshawStatic<R>(st, T, entryChunk);
+            else
+                tquClenshawShared<R>(st, tab4, dyn.lmax);
 
             // frame of pixel i (lane-contiguous shared loads)
             const double tix = sI[3 * PQ_TI + il], tiy = sI[4 * PQ_TI + il], tiz = sI[5 * PQ_TI + il];
             const double pix_ = sI[6 * PQ_TI + il], piy = sI[7 * PQ_TI + il];
 #pragma unroll
-            for(int r = 0; r < PQ_R; ++r)
+            for(int r = 0; r < R; ++r)
             {
                 const int jl = jl0 + r;
-                const long long j = c0 + jl;
+                const int j32 = static_cast<int>(c0 - rowBlock) + jl;          // j - rowBlock (fits int: tile-local)
                 const double njx = sJ[0 * PQ_TJ + jl], njy = sJ[1 * PQ_TJ + jl], njz = sJ[2 * PQ_TJ + jl];
                 const double tjx = sJ[3 * PQ_TJ + jl], tjy = sJ[4 * PQ_TJ + jl], tjz = sJ[5 * PQ_TJ + jl];
                 const double pjx = sJ[6 * PQ_TJ + jl], pjy = sJ[7 * PQ_TJ + jl];
@@ -321,22 +441,22 @@ tquKernel(Geometry geo, const double* __restrict__ a, long long aStride, DeviceT
                 const double tq = fma(tix, pjx, tiy * pjy);                   // e_theta(i) . e_phi(j)
 
                 const double su = p + q, du = rr - tq, sv = p - q, dv = tq + rr;
-                const double aRe = pp1[r] * fma(su, su, -du * du), aIm = pp1[r] * (2.0 * su * du);
-                const double bRe = mm1[r] * fma(sv, sv, -dv * dv), bIm = mm1[r] * (2.0 * sv * dv);
-                const double xt = -te1[r];
+                const double aRe = st.pp1[r] * fma(su, su, -du * du), aIm = st.pp1[r] * (2.0 * su * du);
+                const double bRe = st.mm1[r] * fma(sv, sv, -dv * dv), bIm = st.mm1[r] * (2.0 * sv * dv);
+                const double xt = -st.te1[r];
 
-                const bool valid = (i <= j) && (j < c1) && (i < npix);
-                if(valid)
+                // i <= j, j < c1 (i < npix follows: j < npix)
+                if(il <= j32 && c0 + jl < c1)
                 {
-                    double* colT = ownT + (packedOffset(j) - firstT);
-                    double* colQ = ownQ + (packedOffset(npix + j) - firstQ);
-                    double* colU = ownU + (packedOffset(2 * npix + j) - firstU);
-                    __stcs(colT + i, tt1[r]);
-                    __stcs(colQ + i, xt * fma(aj, aj, -bj * bj));       // T_i Q_j
-                    __stcs(colQ + npix + i, aRe + bRe);                 // Q_i Q_j
-                    __stcs(colU + i, xt * (2.0 * aj * bj));             // T_i U_j
-                    __stcs(colU + npix + i, bIm - aIm);                 // Q_i U_j
-                    __stcs(colU + 2 * npix + i, aRe - bRe);             // U_i U_j
+                    double* colT = sColPtr[0 * PQ_TJ + jl] + i;
+                    double* colQ = sColPtr[1 * PQ_TJ + jl] + i;
+                    double* colU = sColPtr[2 * PQ_TJ + jl] + i;
+                    __stcs(colT, st.tt1[r]);
+                    __stcs(colQ, xt * fma(aj, aj, -bj * bj));           // T_i Q_j
+                    __stcs(colQ + npix, aRe + bRe);                     // Q_i Q_j
+                    __stcs(colU, xt * (2.0 * aj * bj));                 // T_i U_j
+                    __stcs(colU + npix, bIm - aIm);                     // Q_i U_j
+                    __stcs(colU + 2 * npix, aRe - bRe);                 // U_i U_j
                 }
                 stage[(0 * PQ_TI + il) * PQ_STAGE_LD + jl] = xt * fma(ai, ai, -bi * bi);   // Q_i T_j
                 stage[(1 * PQ_TI + il) * PQ_STAGE_LD + jl] = xt * (2.0 * ai * bi);         // U_i T_j
@@ -348,32 +468,18 @@ tquKernel(Geometry geo, const double* __restrict__ a, long long aStride, DeviceT
 
     // transposed partners: for fixed i the 32 columns j of this tile are contiguous rows of column
     // (N+i) / (2N+i); one warp store per (entry kind, i)
-    const long long j = c0 + lane;
+    const int jOff = static_cast<int>(c0 - rowBlock) + lane;       // j - rowBlock
+    const bool colOk = c0 + lane < c1;
     for(int row = warp; row < 3 * PQ_TI; row += PQ_THREADS / 32)
     {
-        const int t = row / PQ_TI;
-        const int ilr = row - t * PQ_TI;
-        const long long ir = rowBlock + ilr;
-        if(ir >= npix || ir >= c1 - 1 + 1)
-            continue;
-        if(!(j < c1 && ir < j))
-            continue;
-        const double v = stage[(t * PQ_TI + ilr) * PQ_STAGE_LD + lane];
-        const int k = ownerOf(P, ir);
-        double* dst;
-        if(P.kind[k] == 0)
-        {
-            if(t == 0) dst = partEntry(P, k, 1, npix, ir, j);               // Q_i T_j -> col N+i, row j
-            else if(t == 1) dst = partEntry(P, k, 2, npix, ir, j);          // U_i T_j -> col 2N+i, row j
-            else dst = partEntry(P, k, 2, npix, ir, npix + j);              // U_i Q_j -> col 2N+i, row N+j
-        }
-        else
-        {
-            dst = P.ptr[k][t] + ((ir - P.begin[k]) * P.ld[k] + (j - P.row0[k]));
-        }
-        __stcs(dst + batchOff, v);
+        const int ilr = row % PQ_TI;
+        if(colOk && ilr < jOff)                                    // strictly above the diagonal: i < j
+            __stcs(sRowPtr[row] + lane, stage[row * PQ_STAGE_LD + lane]);
     }
 }
+
+#undef CMG_CASE
+#undef CMG_CASE5
 
 // ------------------------------------------------------------------------------------------------
 // CMatrix::maskMatrix gather (reference source/c_matrix.cpp:182-201): out(a,b) = in(good[a], good[b])

@@ -190,6 +190,10 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t n_ba
 cmg_status cmg_measure_fp64_peak(cmg_ctx* ctx, double* tflops);
 /* milliseconds the last generate call's kernels took on the device (CUDA events on the launch stream) */
 cmg_status cmg_last_kernel_ms(cmg_ctx* ctx, double* ms);
+/* tuning hook: pick the T,Q,U kernel variant.  0 = automatic; otherwise 100*S + 10*R + B with S = 1 for the
+ * coefficient table in the kernel parameter block (0 = staged in shared memory), R columns per thread and
+ * B resident CTAs per SM the kernel is compiled for (only the combinations built into the library) */
+cmg_status cmg_set_kernel_variant(cmg_ctx* ctx, int variant);
 /* switch the per-call event timing on/off (off by default: it synchronises) */
 cmg_status cmg_set_timing(cmg_ctx* ctx, int enabled);
 
