@@ -237,28 +237,14 @@ def run_gpu_arm(args):
         weights = capi.tqu_weights(*spectra, f, f)
         sizes = partition.tqu_shard_sizes(npix, a0, a1)
         strips = [torch.empty(s, dtype=torch.float64, device="cuda") for s in sizes]
-        lay = capi.TquLayout()
-        lay.n_parts = world
-        lay.own = rank
-        for k in range(world + 1):
-            lay.begin[k] = bounds[k]
-        outbox = []
-        for k in range(world):
-            if k == rank:
-                for s in range(3):
-                    lay.ptr[k][s] = strips[s].data_ptr()
-                lay.kind[k] = 0
-            elif k < rank and bounds[k + 1] > bounds[k]:
-                # entries <Q_i T_j>, <U_i T_j>, <U_i Q_j> this rank computes for owner-columns i of part k: dense blocks
-                blocks = [torch.empty((bounds[k + 1] - bounds[k]) * (a1 - a0), dtype=torch.float64, device="cuda") for _ in range(3)]
-                outbox.append(blocks)
-                for s in range(3):
-                    lay.ptr[k][s] = blocks[s].data_ptr()
-                lay.kind[k] = 1
-                lay.ld[k] = a1 - a0
-                lay.row0[k] = a0
+        plan = partition.tqu_rank_plan(npix, bounds, rank)
+        outbox = {}
+        for owner, ncols, ld, _row0 in plan["outbox"]:
+            # entries <Q_i T_j>, <U_i T_j>, <U_i Q_j> this rank computes for the owner's columns i: dense blocks, kept local
+            outbox[owner] = [torch.empty(ncols * ld, dtype=torch.float64, device="cuda") for _ in range(3)]
+        lay = capi.make_tqu_layout(bounds, rank, [t.data_ptr() for t in strips], {k: [t.data_ptr() for t in v] for k, v in outbox.items()})
         launch = lambda: ctx.tqu(*weights, lay)
-        pieces = strips + [b for blk in outbox for b in blk]
+        pieces = strips + [b for blk in outbox.values() for b in blk]
     d2h_bytes = sum(p.numel() for p in pieces) * 8
     h2d_bytes = (len(weights) if kind == "tt" else 4 * (lmax + 1)) * 8
 
@@ -301,7 +287,8 @@ def run_gpu_arm(args):
     traffic = None
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof) and world == 1:
-        traffic = json.load(open(prof)).get(args.workload)
+        entry = json.load(open(prof)).get(args.workload)
+        traffic = entry["bytes"] if entry else None
     hbm_peak = None
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(mp):

@@ -261,6 +261,31 @@ class Context:
                                                   _p(pixwinT), _p(pixwinP), _p(out_host)))
 
 
+def make_tqu_layout(bounds, rank, strip_ptrs, outbox_ptrs):
+    """cmg_tqu_layout of one rank of a sharded generation (cosmopp_b200.partition.tqu_rank_plan):
+    strip_ptrs = device addresses of its T, Q, U strips; outbox_ptrs = {owner: (three addresses)} of its dense blocks."""
+    from . import partition
+    n_parts = len(bounds) - 1
+    if n_parts > MAX_PARTS:
+        raise ValueError("at most %d parts" % MAX_PARTS)
+    plan = partition.tqu_rank_plan(bounds[-1], bounds, rank)
+    lay = TquLayout()
+    lay.n_parts = n_parts
+    lay.own = rank
+    for k in range(n_parts + 1):
+        lay.begin[k] = bounds[k]
+    for s in range(3):
+        lay.ptr[rank][s] = strip_ptrs[s]
+    lay.kind[rank] = 0
+    for owner, _ncols, ld, row0 in plan["outbox"]:
+        for s in range(3):
+            lay.ptr[owner][s] = outbox_ptrs[owner][s]
+        lay.kind[owner] = 1
+        lay.ld[owner] = ld
+        lay.row0[owner] = row0
+    return lay
+
+
 # ---- pure-host helpers of the ABI (no GPU needed)
 
 def window_beam(lmax, fwhm, pixwin=None):

@@ -46,3 +46,29 @@ def tqu_shard_sizes(npix, begin, end):
 def tqu_strip_offsets(npix, begin):
     """offsets of entry (0, s*npix + begin) inside one whole packed 3N matrix"""
     return [packed_size(s * npix + begin) for s in range(3)]
+
+
+def tqu_rank_plan(npix, bounds, rank):
+    """What rank `rank` of a sharded [T;Q;U] generation holds (no GPU needed to compute this).
+
+    Returns a dict:
+      columns   (begin, end) pixel columns whose pairs (i <= j) this rank computes
+      strips    sizes in doubles of its packed T, Q, U strips (cmg_tqu_layout kind 0)
+      outbox    list of (owner, n_owner_columns, ld, row0): for every owner left of this rank, three dense column-major
+                blocks of n_owner_columns x ld doubles holding <Q_i T_j>, <U_i T_j>, <U_i Q_j> for the owner's columns i and
+                this rank's rows j (cmg_tqu_layout kind 1); these are the entries whose packed home is another rank's strip
+      pairs     number of pixel pairs computed
+    """
+    a0, a1 = bounds[rank], bounds[rank + 1]
+    outbox = []
+    for k in range(rank):
+        if bounds[k + 1] > bounds[k] and a1 > a0:
+            outbox.append((k, bounds[k + 1] - bounds[k], a1 - a0, a0))
+    return {"columns": (a0, a1), "strips": tqu_shard_sizes(npix, a0, a1), "outbox": outbox, "pairs": pairs_in_block(a0, a1)}
+
+
+def tqu_entries_held(npix, bounds, rank):
+    """Number of matrix entries rank `rank` writes: 6 per pair on the diagonal (i == j), 9 per pair off it."""
+    a0, a1 = bounds[rank], bounds[rank + 1]
+    pairs = pairs_in_block(a0, a1)
+    return 9 * pairs - 3 * (a1 - a0)

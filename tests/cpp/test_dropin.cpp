@@ -1,0 +1,232 @@
+// Exercises the C++ drop-in classes the way the reference's own test does
+// (reference source/test_like_low.cpp:183-186: clToCMatrix, getFiducialMatrix, generateNoiseMatrix, maskMatrix),
+// plus the file formats.  Mode "cpu" needs no GPU; mode "gpu" writes matrices that tests/test_dropin_cpp.py
+// compares with the oracle.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include <c_matrix.hpp>
+#include <c_matrix_generator.hpp>
+#include <exception_handler.hpp>
+#include <utils.hpp>
+
+static int failures = 0;
+#define EXPECT(cond)                                                                   \
+    do                                                                                 \
+    {                                                                                  \
+        if(!(cond))                                                                    \
+        {                                                                              \
+            ++failures;                                                                \
+            std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond);              \
+        }                                                                              \
+    } while(0)
+
+template <typename F> static bool throwsStandard(F f)
+{
+    try { f(); }
+    catch(StandardException&) { return true; }
+    catch(...) { return false; }
+    return false;
+}
+
+static std::vector<double> readDoubles(const std::string& path)
+{
+    std::ifstream in(path.c_str(), std::ios::binary);
+    in.seekg(0, std::ios::end);
+    const std::streamsize n = in.tellg();
+    in.seekg(0);
+    std::vector<double> v(static_cast<size_t>(n / 8));
+    in.read(reinterpret_cast<char*>(v.data()), n);
+    return v;
+}
+
+static std::vector<int> readInts(const std::string& path)
+{
+    std::ifstream in(path.c_str(), std::ios::binary);
+    in.seekg(0, std::ios::end);
+    const std::streamsize n = in.tellg();
+    in.seekg(0);
+    std::vector<int> v(static_cast<size_t>(n / 4));
+    in.read(reinterpret_cast<char*>(v.data()), n);
+    return v;
+}
+
+static void cpuTests(const std::string& dir)
+{
+    // packed layout: index(i,j) = j(j+1)/2 + i, symmetric access (reference source/c_matrix.cpp:27-39)
+    CMatrix m(5);
+    EXPECT(m.getNPix() == 5);
+    for(int j = 0; j < 5; ++j)
+        for(int i = 0; i <= j; ++i)
+            m.element(i, j) = 10 * j + i + 0.25;
+    EXPECT(m.element(3, 1) == m.element(1, 3));
+    EXPECT(&m.element(2, 4) == m.packed() + (4 * 5 / 2 + 2));
+    EXPECT(m.packedSize() == 15);
+    m.comment() = "hello matrix";
+
+    // binary round trip
+    const std::string bin = dir + "/m.dat", txt = dir + "/m.txt";
+    m.writeIntoFile(bin.c_str());
+    CMatrix r(bin.c_str());
+    EXPECT(r.getNPix() == 5 && r.comment() == "hello matrix");
+    for(int k = 0; k < 15; ++k) EXPECT(r.packed()[k] == m.packed()[k]);
+    // text round trip (default ostream precision: 6 significant digits)
+    m.writeIntoTextFile(txt.c_str());
+    CMatrix t(3);
+    t.readFromTextFile(txt.c_str());
+    EXPECT(t.getNPix() == 5 && t.comment() == "hello matrix");
+    for(int k = 0; k < 15; ++k) EXPECT(std::fabs(t.packed()[k] - m.packed()[k]) <= 1e-5 * std::fabs(m.packed()[k]));
+
+    // copy semantics are deep
+    CMatrix c(m);
+    c.element(0, 0) = -1;
+    EXPECT(m.element(0, 0) == 0.25);
+    CMatrix a(2);
+    a = m;
+    EXPECT(a.getNPix() == 5 && a.element(4, 4) == m.element(4, 4));
+
+    // maskMatrix gather (reference source/c_matrix.cpp:182-201)
+    std::vector<int> good;
+    good.push_back(1); good.push_back(3); good.push_back(4);
+    CMatrix g(m);
+    g.maskMatrix(good);
+    EXPECT(g.getNPix() == 3);
+    for(int b = 0; b < 3; ++b)
+        for(int aa = 0; aa <= b; ++aa)
+            EXPECT(g.element(aa, b) == m.element(good[aa], good[b]));
+
+    // error convention
+    EXPECT(throwsStandard([] { CMatrix bad(0); }));
+    EXPECT(throwsStandard([&] { CMatrix bad((dir + "/does_not_exist.dat").c_str()); }));
+    EXPECT(throwsStandard([&] { m.writeIntoFile((dir + "/no/such/dir/x.dat").c_str()); }));
+
+    // noise matrix (reference source/c_matrix_generator.cpp:774-787)
+    CMatrix* noise = CMatrixGenerator::generateNoiseMatrix(2, 0.5);
+    EXPECT(noise->getNPix() == 48 && noise->comment() == "noise matrix");
+    EXPECT(noise->element(7, 7) == 0.25 && noise->element(7, 8) == 0);
+    delete noise;
+
+    // beam (reference source/utils.cpp:54-64)
+    EXPECT(Utils::beamFunction(10, 0) == 1.0);
+    const double sigma = std::sqrt(8 * std::log(2.0)) / (10.0 * 3.141592653589793 / 180);
+    EXPECT(std::fabs(Utils::beamFunction(30, 10.0) - std::exp(-30 * 31 / (2 * sigma * sigma))) < 1e-16);
+
+    // C_l text files
+    {
+        std::ofstream out((dir + "/cl.txt").c_str());
+        out << "0\n0\n1.5\n2.5e-1\n";
+    }
+    std::vector<double> cl;
+    Utils::readClFromFile((dir + "/cl.txt").c_str(), cl);
+    EXPECT(cl.size() == 4 && cl[2] == 1.5 && cl[3] == 0.25);
+    {
+        std::ofstream out((dir + "/dl.txt").c_str());
+        out << "0 0\n1 0\n2 6.0\n";
+    }
+    Utils::readClFromFile((dir + "/dl.txt").c_str(), cl, true, true);
+    EXPECT(cl.size() == 3 && std::fabs(cl[2] - 6.0 * 2 * 3.141592653589793 / 6) < 1e-15);
+    EXPECT(throwsStandard([&] { std::vector<double> x; Utils::readClFromFile((dir + "/nope.txt").c_str(), x); }));
+
+    // FITS mask written by the Python side (NESTED, Nside=4) -> same good pixels as the list next to it
+    {
+        long nSide = 0;
+        std::vector<int> gp;
+        Utils::readMask((dir + "/mask_nest.fits").c_str(), nSide, gp);
+        const std::vector<int> want = readInts(dir + "/mask_good.i32");
+        EXPECT(nSide == 4 && gp == want);
+        EXPECT(throwsStandard([&] { long n; std::vector<int> x; Utils::readMask((dir + "/mask_ring.fits").c_str(), n, x); }));
+    }
+
+    // Legendre container: on-demand values and the reference's file layout
+    {
+        std::vector<int> px;
+        for(int k = 0; k < 12; k += 2) px.push_back(k);
+        LegendrePolynomialContainer lp(6, 1, &px);
+        EXPECT(std::fabs(lp.value(0, 3, 1) - 1.0) < 1e-15);
+        EXPECT(std::fabs(lp.value(4, 2, 2) - 1.0) < 1e-12);          // P_l(1) = 1 on the diagonal
+        lp.writeIntoFile((dir + "/lp.dat").c_str());
+        LegendrePolynomialContainer back((dir + "/lp.dat").c_str());
+        EXPECT(back.lMax() == 6 && back.nPix() == 6);
+        for(int l = 0; l <= 6; ++l)
+            for(int j = 0; j < 6; ++j)
+                for(int i = 0; i <= j; ++i)
+                    EXPECT(back.value(l, j, i) == lp.value(l, j, i));
+    }
+
+    // the harmonic-space routes are declared but outside this library's path
+    EXPECT(throwsStandard([] { CMatrixGenerator::calculateNoiseMatrix("a", "b", 1.0, 1.0); }));
+}
+
+static void gpuTests(const std::string& dir)
+{
+    const long nSide = 8;
+    const int lMax = 20, lMaxFid = 4 * nSide;
+    const std::vector<double> cl = readDoubles(dir + "/cl_tt.f64");           // 4 nSide + 1 values
+    const std::vector<int> good = readInts(dir + "/good.i32");
+    const std::vector<double> ones(static_cast<size_t>(lMaxFid + 1), 1.0);
+    CMatrixGenerator::setPixelWindow(nSide, ones, ones);
+
+    // exactly the call sequence of reference source/test_like_low.cpp:181-186
+    std::vector<double> clCopy(cl.begin(), cl.begin() + lMax + 1);
+    CMatrix* cMatrix = CMatrixGenerator::clToCMatrix(clCopy, nSide, 10.0, &good);
+    CMatrix* fiducialMatrix = CMatrixGenerator::getFiducialMatrix(cl, nSide, lMax, 10.0, &good);
+    CMatrix* noiseMatrix = CMatrixGenerator::generateNoiseMatrix(nSide, 1e-2);
+    noiseMatrix->maskMatrix(good);
+    EXPECT(cMatrix->getNPix() == static_cast<int>(good.size()));
+    EXPECT(fiducialMatrix->comment() == "fiducial matrix");
+    EXPECT(noiseMatrix->getNPix() == static_cast<int>(good.size()));
+    cMatrix->writeIntoFile((dir + "/c.dat").c_str());
+    fiducialMatrix->writeIntoFile((dir + "/c_fiducial.dat").c_str());
+    noiseMatrix->writeIntoFile((dir + "/c_noise.dat").c_str());
+    delete cMatrix;
+    delete fiducialMatrix;
+    delete noiseMatrix;
+
+    // full sky through the file overload
+    CMatrix* full = CMatrixGenerator::clToCMatrix((dir + "/cl_short.txt").c_str(), 4, 12, 10.0);
+    EXPECT(full->getNPix() == 192);
+    full->writeIntoFile((dir + "/c_full.dat").c_str());
+    delete full;
+
+    // polarized addition
+    const std::vector<double> te = readDoubles(dir + "/cl_te.f64"), ee = readDoubles(dir + "/cl_ee.f64"), bb = readDoubles(dir + "/cl_bb.f64");
+    std::vector<double> tt(cl.begin(), cl.begin() + te.size());
+    CMatrix* pol = CMatrixGenerator::clToCMatrixPol(tt, te, ee, bb, nSide, 10.0, &good);
+    EXPECT(pol->getNPix() == 3 * static_cast<int>(good.size()));
+    pol->writeIntoFile((dir + "/c_pol.dat").c_str());
+    delete pol;
+
+    // errors surface as StandardException
+    EXPECT(throwsStandard([&] { std::vector<double> empty; CMatrixGenerator::clToCMatrix(empty, nSide, 10.0); }));
+    EXPECT(throwsStandard([&] { CMatrixGenerator::getFiducialMatrix(clCopy, nSide, lMax, 10.0); }));      // cl too short
+    EXPECT(throwsStandard([&] { CMatrixGenerator::clToCMatrix(clCopy, 12, 10.0); }));                    // nSide not a power of two
+    CMatrixGenerator::clearPixelWindow(nSide);
+    EXPECT(throwsStandard([&] { CMatrixGenerator::clToCMatrix(clCopy, nSide, 10.0, &good); }));          // no window available
+}
+
+int main(int argc, char** argv)
+{
+    if(argc < 3)
+    {
+        std::printf("usage: test_dropin cpu|gpu <dir>\n");
+        return 2;
+    }
+    const std::string mode = argv[1], dir = argv[2];
+    try
+    {
+        if(mode == "cpu") cpuTests(dir);
+        else gpuTests(dir);
+    }
+    catch(std::exception& e)
+    {
+        std::printf("UNEXPECTED EXCEPTION: %s\n", e.what());
+        return 1;
+    }
+    std::printf("%s: %d failure(s)\n", mode.c_str(), failures);
+    return failures ? 1 : 0;
+}

@@ -171,3 +171,195 @@ def test_tqu_nside16_masked_sampled(gpu_ctx, oracle_api):
             c = b * n + pj
             worst = max(worst, (np.abs(got[idx(r, c)] - blocks[:, a, b]) / scale[a, b]).max())
     assert worst <= REL_TOL
+
+
+def _whole_tqu(ctx, a, n):
+    torch = _torch()
+    from cosmopp_b200 import capi
+    whole = torch.full((capi.packed_size(3 * n),), float("nan"), dtype=torch.float64, device="cuda")
+    ctx.tqu(*a, ctx.tqu_layout_single(whole))
+    torch.cuda.synchronize()
+    return whole
+
+
+@pytest.mark.parametrize("parts", [2, 3, 5])
+def test_tqu_sharded_in_place_layout_is_bit_identical(gpu_ctx, oracle_api, parts):
+    """All parts packed (kind 0), as with peer-mapped strips of other GPUs: every rank's launch writes the transposed
+    partners straight into the owner's strip.  Run rank after rank on one GPU; the strips then tile the whole matrix."""
+    torch = _torch()
+    from cosmopp_b200 import capi, partition
+    nside, lmax = 8, 18
+    gpu_ctx.set_pixels(nside)
+    n = gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    a = capi.tqu_weights(*synthetic_cl(lmax, pol=True), f, f)
+    whole = _whole_tqu(gpu_ctx, a, n)
+    b = partition.column_partition(n, parts, align=32)
+    strips = [[torch.full((s,), float("nan"), dtype=torch.float64, device="cuda") for s in partition.tqu_shard_sizes(n, b[k], b[k + 1])]
+              for k in range(parts)]
+    for r in range(parts):
+        lay = capi.TquLayout()
+        lay.n_parts, lay.own = parts, r
+        for k in range(parts + 1):
+            lay.begin[k] = b[k]
+        for k in range(parts):
+            for s in range(3):
+                lay.ptr[k][s] = strips[k][s].data_ptr()
+        gpu_ctx.tqu(*a, lay)
+    torch.cuda.synchronize()
+    off = 0
+    for s in range(3):
+        for k in range(parts):
+            piece = strips[k][s]
+            assert torch.equal(piece, whole[partition.tqu_strip_offsets(n, b[k])[s]:][:piece.numel()])
+            off += piece.numel()
+    assert off == whole.numel()
+
+
+def test_tqu_sharded_outbox_layout_assembles_to_whole(gpu_ctx, oracle_api):
+    """The no-communication layout of the multi-GPU bench: transposed partners of cross pairs land in local dense
+    blocks (kind 1).  Scatter them into place on the host and compare with the one-piece matrix, bit for bit."""
+    torch = _torch()
+    from cosmopp_b200 import capi, partition
+    nside, lmax, parts = 8, 18, 3
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside))
+    gpu_ctx.set_pixels(nside, good)
+    n = gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    a = capi.tqu_weights(*synthetic_cl(lmax, pol=True), f, f)
+    whole = _whole_tqu(gpu_ctx, a, n).cpu().numpy()
+    b = partition.column_partition(n, parts, align=32)
+    assembled = np.full(capi.packed_size(3 * n), np.nan)
+    pk = lambda r, c: c * (c + 1) // 2 + r
+    for r in range(parts):
+        plan = partition.tqu_rank_plan(n, b, r)
+        strips = [torch.full((s,), float("nan"), dtype=torch.float64, device="cuda") for s in plan["strips"]]
+        outbox = {o: [torch.full((nc * ld,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(3)] for o, nc, ld, _ in plan["outbox"]}
+        lay = capi.make_tqu_layout(b, r, [t.data_ptr() for t in strips], {k: [t.data_ptr() for t in v] for k, v in outbox.items()})
+        gpu_ctx.tqu(*a, lay)
+        torch.cuda.synchronize()
+        a0, a1 = plan["columns"]
+        for s in range(3):
+            got = strips[s].cpu().numpy()
+            lo = partition.tqu_strip_offsets(n, a0)[s]
+            seg = assembled[lo:lo + len(got)]
+            seg[~np.isnan(got)] = got[~np.isnan(got)]
+        for o, nc, ld, row0 in plan["outbox"]:
+            for t in range(3):
+                blk = outbox[o][t].cpu().numpy().reshape(nc, ld)          # [owner column i][row j]
+                i = b[o] + np.arange(nc)[:, None]
+                j = row0 + np.arange(ld)[None, :]
+                if t == 0: dst = pk(j, n + i)                              # <Q_i T_j> -> column N+i, row j
+                elif t == 1: dst = pk(j, 2 * n + i)                        # <U_i T_j> -> column 2N+i, row j
+                else: dst = pk(n + j, 2 * n + i)                           # <U_i Q_j> -> column 2N+i, row N+j
+                assert not np.isnan(blk).any()
+                assembled[dst] = blk
+    assert not np.isnan(assembled).any()
+    assert np.array_equal(assembled, whole)
+
+
+def test_mask_matrix_gather_kernel(gpu_ctx, oracle_api):
+    torch = _torch()
+    from cosmopp_b200 import capi
+    n = 192
+    rs = np.random.RandomState(5)
+    packed = rs.standard_normal(capi.packed_size(n))
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(4))
+    d_in = torch.from_numpy(packed).cuda()
+    d_out = torch.empty(capi.packed_size(len(good)), dtype=torch.float64, device="cuda")
+    gpu_ctx.mask_matrix(d_in, n, good, d_out)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), oracle_api.mask_matrix(packed, good))
+
+
+def test_batched_generation_matches_single_calls(gpu_ctx, oracle_api):
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside, lmax, nb = 4, 12, 5
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside))
+    gpu_ctx.set_pixels(nside, good)
+    n = gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    # TT
+    a = np.stack([capi.tt_weights(synthetic_cl(lmax, seed=100 + b), f) for b in range(nb)])
+    stride = capi.packed_size(n) + 7
+    out = torch.full((nb * stride,), float("nan"), dtype=torch.float64, device="cuda")
+    gpu_ctx.legendre_series_batched(a, out, stride)
+    one = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
+    for b in range(nb):
+        gpu_ctx.legendre_series(a[b], one)
+        torch.cuda.synchronize()
+        assert torch.equal(out[b * stride:b * stride + one.numel()], one)
+        want = oracle_api.cl_to_cmatrix(synthetic_cl(lmax, seed=100 + b), nside, 10.0, good=good)
+        assert np.abs(one.cpu().numpy() - want).max() <= REL_TOL * want[0]
+    # TQU
+    ab = np.stack([np.stack(capi.tqu_weights(*synthetic_cl(lmax, seed=200 + b, pol=True), f, f)) for b in range(nb)])
+    stride = capi.packed_size(3 * n)
+    outp = torch.full((nb * stride,), float("nan"), dtype=torch.float64, device="cuda")
+    gpu_ctx.tqu_batched(ab, outp, stride)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        want = oracle_api.tqu_matrix(*synthetic_cl(lmax, seed=200 + b, pol=True), nside, 10.0, good=good)
+        _assert_tqu_close(outp[b * stride:(b + 1) * stride].cpu().numpy(), want, n)
+
+
+def test_all_kernel_variants_agree(gpu_ctx, oracle_api):
+    """Static-table and shared-memory-table kernels, all column counts: same matrix to rounding."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside, lmax = 8, 33
+    gpu_ctx.set_pixels(nside)
+    n = gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    spectra = synthetic_cl(lmax, pol=True)
+    a = capi.tqu_weights(*spectra, f, f)
+    want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
+    try:
+        for v in (22, 42, 81, 114, 122, 123, 124, 142):
+            gpu_ctx.set_kernel_variant(v)
+            got = _whole_tqu(gpu_ctx, a, n).cpu().numpy()
+            _assert_tqu_close(got, want, n)
+    finally:
+        gpu_ctx.set_kernel_variant(0)
+
+
+def test_argument_errors_are_reported_not_crashed(gpu_ctx):
+    torch = _torch()
+    from cosmopp_b200 import capi
+    import cosmopp_b200 as cb
+    gpu_ctx.set_pixels(2)
+    out = torch.empty(capi.packed_size(48), dtype=torch.float64, device="cuda")
+    with pytest.raises(cb.CmgError):
+        gpu_ctx.legendre_series(np.ones(capi.LMAX_LIMIT + 2), out)            # lmax beyond the limit
+    with pytest.raises(cb.CmgError):
+        gpu_ctx.legendre_series(np.ones(5), out, 0, 49)                        # column range outside the matrix
+    with pytest.raises(cb.CmgError):
+        gpu_ctx.set_pixels(12)                                                 # not a power of two
+    with pytest.raises(cb.CmgError):
+        gpu_ctx.set_pixels(2, [0, 48])                                         # pixel index out of range
+    fresh = cb.Context(0)
+    with pytest.raises(cb.CmgError):
+        fresh.legendre_series(np.ones(5), out)                                 # geometry not set
+    fresh.close()
+
+
+def test_tt_large_sample_nside32(gpu_ctx, oracle_api):
+    """BASELINE config 3 size (TT Nside=32, lmax=96): every diagonal entry, every antipodal pair and a random sample
+    of 10^6 entries against the oracle."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside, lmax = 32, 96
+    cl = synthetic_cl(lmax)
+    got = _tt_gpu(gpu_ctx, cl, nside, 10.0)
+    n = 12 * nside * nside
+    assert not np.isnan(got).any()
+    rs = np.random.RandomState(11)
+    pj = rs.randint(0, n, 1000000)
+    pi = (rs.uniform(size=len(pj)) * (pj + 1)).astype(np.int64)
+    v = oracle_api.unit_vectors(nside)
+    anti = np.argmin(v @ v[:2048].T, axis=0)                                   # antipodes of the first 2048 pixels
+    ai, aj = np.minimum(anti, np.arange(2048)), np.maximum(anti, np.arange(2048))
+    pi = np.concatenate([pi, np.arange(n), ai])
+    pj = np.concatenate([pj, np.arange(n), aj])
+    want = oracle_api.cl_to_cmatrix_pairs(cl, nside, 10.0, pi, pj, good=np.arange(n, dtype=np.int32))
+    assert np.abs(got[pj * (pj + 1) // 2 + pi] - want).max() <= REL_TOL * want[len(want) - 2048 - n]

@@ -1,0 +1,84 @@
+"""Host-side sharding logic (no GPU): equal-area column blocks, shard sizes, and a world_size-2 gloo run of the
+per-rank planning the multi-GPU bench does."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from cosmopp_b200 import partition
+
+
+@pytest.mark.parametrize("npix,parts", [(3072, 1), (3072, 2), (12288, 4), (49152, 8), (2548, 3), (100, 8)])
+def test_column_partition_tiles_and_balances(npix, parts):
+    b = partition.column_partition(npix, parts, align=32)
+    assert b[0] == 0 and b[-1] == npix and len(b) == parts + 1 and all(x <= y for x, y in zip(b, b[1:]))
+    assert all(x % 32 == 0 for x in b[1:-1])
+    pairs = [partition.pairs_in_block(b[k], b[k + 1]) for k in range(parts)]
+    assert sum(pairs) == npix * (npix + 1) // 2
+    if npix >= 3072:
+        assert max(pairs) <= 1.05 * sum(pairs) / parts        # balanced to the column-tile granularity
+
+
+def test_shards_tile_the_packed_triangle():
+    npix, parts = 1000, 4
+    b = partition.column_partition(npix, parts, align=32)
+    assert sum(partition.tt_shard_size(b[k], b[k + 1]) for k in range(parts)) == partition.packed_size(npix)
+    strips = sum(sum(partition.tqu_shard_sizes(npix, b[k], b[k + 1])) for k in range(parts))
+    assert strips == partition.packed_size(3 * npix)
+    # every entry is written exactly once: strips hold the natural entries, outboxes the transposed ones of cross pairs
+    held = sum(partition.tqu_entries_held(npix, b, r) for r in range(parts))
+    assert held == partition.packed_size(3 * npix)
+    for r in range(parts):
+        plan = partition.tqu_rank_plan(npix, b, r)
+        assert [o[0] for o in plan["outbox"]] == list(range(r))
+        assert all(ld == b[r + 1] - b[r] and row0 == b[r] for _, _, ld, row0 in plan["outbox"])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, npix, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bounds = partition.column_partition(npix, world, align=32)
+    plan = partition.tqu_rank_plan(npix, bounds, rank)
+    mine = torch.tensor([plan["pairs"], partition.tqu_entries_held(npix, bounds, rank), sum(plan["strips"]),
+                         sum(3 * n * ld for _, n, ld, _ in plan["outbox"])], dtype=torch.int64)
+    allr = [torch.zeros(4, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    # the timing rule of bench.py: max over ranks
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        out.put((torch.stack(allr).tolist(), float(t)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_planning_over_gloo():
+    import torch.multiprocessing as mp
+    npix, world = 3072, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, npix, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    rows, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rows = np.array(rows)
+    assert rows[:, 0].sum() == npix * (npix + 1) // 2                       # all pixel pairs, once
+    assert rows[:, 1].sum() == partition.packed_size(3 * npix)               # all matrix entries, once
+    assert rows[:, 2].sum() == partition.packed_size(3 * npix)               # strips tile the packed triangle
+    assert rows[0, 3] == 0 and rows[1, 3] > 0                                # only the right-hand rank keeps an outbox
+    assert tmax == 2.0
