@@ -170,6 +170,7 @@ static void gpuTests(const std::string& dir)
     const std::vector<int> good = readInts(dir + "/good.i32");
     const std::vector<double> ones(static_cast<size_t>(lMaxFid + 1), 1.0);
     CMatrixGenerator::setPixelWindow(nSide, ones, ones);
+    CMatrixGenerator::setPixelWindow(4, ones, ones);
 
     // exactly the call sequence of reference source/test_like_low.cpp:181-186
     std::vector<double> clCopy(cl.begin(), cl.begin() + lMax + 1);
