@@ -163,8 +163,9 @@ struct KernelTimer
     }
 };
 
+// hostWeights != NULL (single matrix, weights known on the host) enables the static-table kernel
 cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, int64_t nBatch,
-                          int64_t colBegin, int64_t colEnd, double* dOut, int64_t outStride)
+                          int64_t colBegin, int64_t colEnd, double* dOut, int64_t outStride, const double* hostWeights)
 {
     if(colBegin < 0 || colEnd > ctx->npix || colBegin > colEnd)
         return fail(ctx, CMG_EINVAL, "column range outside [0, npix]");
@@ -179,11 +180,26 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
     if(colBlocks > 65535)
         return fail(ctx, CMG_EUNSUPPORTED, "too many column blocks for one launch");
     const dim3 grid(static_cast<unsigned>(rowBlocks), static_cast<unsigned>(colBlocks), static_cast<unsigned>(nBatch));
-    const size_t smem = sizeof(double2) * (lmax + 1);
     const cmg::DeviceTables t = tablesOf(ctx);
+    const bool useStatic = hostWeights && nBatch == 1 && lmax + 1 <= cmg::TT_STATIC_STEPS && ctx->tquVariant != 1;
+    static thread_local cmg::TtStaticTable T;
+    int entryChunk = 0;
+    if(useStatic)
+    {
+        for(int i = 0; i < cmg::TT_STATIC_STEPS; ++i)
+        {
+            const int k = cmg::TT_STATIC_STEPS - 1 - i;
+            T.s[i] = make_double2(k <= lmax ? hostWeights[k] * ctx->hostT0.N[k] : 0.0, -ctx->hostT0.g[k + 1]);
+        }
+        entryChunk = (cmg::TT_STATIC_STEPS - 1 - lmax) / cmg::TT_STATIC_CHUNK;
+    }
     KernelTimer timer(ctx);
-    cmg::legendreSeriesKernel<<<grid, cmg::TT_ROWS, smem, ctx->stream>>>(geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax,
-                                                                         colBegin, colEnd, dOut, outStride);
+    if(useStatic)
+        cmg::legendreSeriesKernel<true><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, T, entryChunk,
+                                                                                 colBegin, colEnd, dOut, outStride);
+    else
+        cmg::legendreSeriesKernel<false><<<grid, cmg::TT_ROWS, sizeof(double2) * (lmax + 1), ctx->stream>>>(
+            geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, T, entryChunk, colBegin, colEnd, dOut, outStride);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return timer.finish();
@@ -285,7 +301,7 @@ cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, 
     // 22 = shared-memory table, R=2, 2 CTAs/SM
     const bool canStatic = hostWeights && nBatch == 1 && lmax >= 2 && lmax <= cmg::PQ_STATIC_LMAX;
     int variant = ctx->tquVariant;
-    if(variant == 0)
+    if(variant == 0 || variant == 900)
         variant = canStatic ? 142 : 42;
     if(variant >= 100 && !canStatic)
         return fail(ctx, CMG_EINVAL, "static-table kernel needs host weights, one batch element and 2 <= lmax <= PQ_STATIC_LMAX");
@@ -663,7 +679,7 @@ cmg_status cmg_legendre_series_dev(cmg_ctx* ctx, const double* dA, int lmax, int
     const cmg_status s = checkReady(ctx, lmax);
     if(s != CMG_OK) return s;
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
-    return launchLegendre(ctx, dA, 0, lmax, 1, colBegin, colEnd, dOut, 0);
+    return launchLegendre(ctx, dA, 0, lmax, 1, colBegin, colEnd, dOut, 0, nullptr);
 }
 
 cmg_status cmg_legendre_series(cmg_ctx* ctx, const double* a, int lmax, int64_t colBegin, int64_t colEnd, double* dOut)
@@ -674,7 +690,7 @@ cmg_status cmg_legendre_series(cmg_ctx* ctx, const double* a, int lmax, int64_t 
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     if((s = ensureWeights(ctx, lmax + 1)) != CMG_OK) return s;
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * (lmax + 1), cudaMemcpyHostToDevice, ctx->stream));
-    return launchLegendre(ctx, ctx->dWeights, 0, lmax, 1, colBegin, colEnd, dOut, 0);
+    return launchLegendre(ctx, ctx->dWeights, 0, lmax, 1, colBegin, colEnd, dOut, 0, a);
 }
 
 cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch,
@@ -686,7 +702,7 @@ cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, 
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     if((s = ensureWeights(ctx, nBatch * (lmax + 1))) != CMG_OK) return s;
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * (lmax + 1), cudaMemcpyHostToDevice, ctx->stream));
-    return launchLegendre(ctx, ctx->dWeights, lmax + 1, lmax, nBatch, colBegin, colEnd, dOut, stride);
+    return launchLegendre(ctx, ctx->dWeights, lmax + 1, lmax, nBatch, colBegin, colEnd, dOut, stride, nullptr);
 }
 
 static cmg_status wholeCallTT(cmg_ctx* ctx, const std::vector<double>& a, int lmax, double* outPacked)
@@ -801,7 +817,36 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBat
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
     cmg_tqu_layout layout;
     if((s = cmg_tqu_layout_single(ctx, dOut, &layout)) != CMG_OK) return s;
-    return launchTqu(ctx, ctx->dWeights, per, lmax, nBatch, &layout, stride, nullptr);
+    // Default: one Clenshaw pass per batch element (blockIdx.z), 0.195 ms per Nside=16 lmax=47 matrix on a B200.
+    // Variant 900 selects the shared-basis kernel (recurrences once per pixel pair and batch chunk, 4 accumulate-FMAs
+    // per element and l).  It does 2.5x fewer FP64 operations but is bound by delivering one distinct weight per FMA
+    // from shared memory (0.254 ms per matrix measured); the contraction belongs on the FP64 tensor path (DMMA) -- next round.
+    if(ctx->tquVariant != 900 || lmax < 2)
+        return launchTqu(ctx, ctx->dWeights, per, lmax, nBatch, &layout, stride, nullptr);
+    cmg::PartTable P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = 1;
+    P.begin[1] = ctx->npix;
+    for(int st = 0; st < 3; ++st) P.ptr[0][st] = layout.ptr[0][st];
+    const int64_t tiles = (ctx->npix + cmg::PB_T - 1) / cmg::PB_T;
+    const size_t smem = cmg::tquBatchedSmemBytes(lmax);
+    if(smem > 227 * 1024 || tiles > 65535)
+        return launchTqu(ctx, ctx->dWeights, per, lmax, nBatch, &layout, stride, nullptr);
+    // folded weights live behind the raw ones in the staging buffer
+    const int64_t nChunks = (nBatch + cmg::PB_BT - 1) / cmg::PB_BT;
+    const int64_t foldedDoubles = nChunks * (lmax + 1) * 4 * cmg::PB_BT;
+    if((s = ensureWeights(ctx, nBatch * per + foldedDoubles)) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
+    double* dFolded = ctx->dWeights + nBatch * per;
+    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::tquBatchedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    KernelTimer timer(ctx);
+    cmg::foldBatchedWeightsKernel<<<static_cast<unsigned>(std::min<int64_t>(1024, (foldedDoubles + 255) / 256)), 256, 0, ctx->stream>>>(
+        ctx->dWeights, tablesOf(ctx), lmax, static_cast<int>(nBatch), dFolded);
+    cmg::tquBatchedKernel<<<dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(tiles)), cmg::PB_T * cmg::PB_CW, smem, ctx->stream>>>(
+        geometryOf(ctx), dFolded, tablesOf(ctx), lmax, static_cast<int>(nBatch), P, stride);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return timer.finish();
 }
 
 cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee, const double* cbb,
@@ -865,7 +910,7 @@ cmg_status cmg_last_kernel_ms(cmg_ctx* ctx, double* ms)
 
 cmg_status cmg_set_kernel_variant(cmg_ctx* ctx, int variant)
 {
-    if(!ctx || variant < 0) return CMG_EINVAL;
+    if(!ctx || variant < 0) return CMG_EINVAL;   // (1 also selects the shared-memory-table TT kernel)
     ctx->tquVariant = variant;
     return CMG_OK;
 }

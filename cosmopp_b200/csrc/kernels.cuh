@@ -70,13 +70,63 @@ __host__ __device__ inline long long packedOffset(long long col) { return col * 
 constexpr int TT_ROWS = 128;
 constexpr int TT_COLS = 16;
 constexpr int TT_R = 8;
+constexpr int TT_STATIC_STEPS = 1024;                 // slot i <-> k = TT_STATIC_STEPS - 1 - i
+constexpr int TT_STATIC_CHUNK = 8;
 
+// coefficients in the kernel parameter block (see the note at TquStaticTable): s[i] = { a_k N_k, -g_{k+1} }
+struct TtStaticTable
+{
+    double2 s[TT_STATIC_STEPS];
+};
+
+template <int R>
+__device__ __forceinline__ void ttStep(double (&x2)[R], double (&b1)[R], double (&b2)[R], const double2 t)
+{
+#pragma unroll
+    for(int r = 0; r < R; ++r)
+    {
+        // (a + x2 b1) - g b2: one warp-uniform operand per DFMA (see tquStep)
+        const double b = fma(t.y, b2[r], fma(x2[r], b1[r], t.x));
+        b2[r] = b1[r];
+        b1[r] = b;
+    }
+}
+
+template <int R, int C>
+__device__ __forceinline__ void ttStaticChunk(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T)
+{
+#pragma unroll
+    for(int u = 0; u < TT_STATIC_CHUNK; ++u)
+        ttStep<R>(x2, b1, b2, T.s[C * TT_STATIC_CHUNK + u]);
+}
+
+#define CMG_TT_CASE(c) case c: ttStaticChunk<R, c>(x2, b1, b2, T); [[fallthrough]];
+#define CMG_TT_CASE8(b) CMG_TT_CASE(b) CMG_TT_CASE(b + 1) CMG_TT_CASE(b + 2) CMG_TT_CASE(b + 3) CMG_TT_CASE(b + 4) CMG_TT_CASE(b + 5) CMG_TT_CASE(b + 6) CMG_TT_CASE(b + 7)
+#define CMG_TT_CASE64(b) CMG_TT_CASE8(b) CMG_TT_CASE8(b + 8) CMG_TT_CASE8(b + 16) CMG_TT_CASE8(b + 24) CMG_TT_CASE8(b + 32) CMG_TT_CASE8(b + 40) CMG_TT_CASE8(b + 48) CMG_TT_CASE8(b + 56)
+
+template <int R>
+__device__ __forceinline__ void ttClenshawStatic(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T, int entryChunk)
+{
+    static_assert(TT_STATIC_STEPS == 128 * TT_STATIC_CHUNK, "case list below covers 128 chunks");
+    switch(entryChunk)
+    {
+        CMG_TT_CASE64(0) CMG_TT_CASE64(64)
+        default: break;
+    }
+}
+
+#undef CMG_TT_CASE
+#undef CMG_TT_CASE8
+#undef CMG_TT_CASE64
+
+template <bool STATIC>
 __global__ void __launch_bounds__(TT_ROWS)
 legendreSeriesKernel(Geometry geo, const double* __restrict__ a, long long aStride,
                      const double* __restrict__ N0, const double* __restrict__ g0, int lmax,
+                     const __grid_constant__ TtStaticTable T, int entryChunk,
                      long long colBegin, long long colEnd, double* __restrict__ out, long long outStride)
 {
-    extern __shared__ double2 ttTab[];      // [lmax + 1]  {a_k N_k, -g_{k+1}}
+    extern __shared__ double2 ttTab[];      // [lmax + 1]  {a_k N_k, -g_{k+1}}  (dynamic variant only)
 
     const long long rowBlock = static_cast<long long>(blockIdx.x) * TT_ROWS;
     const long long c0 = colBegin + static_cast<long long>(blockIdx.y) * TT_COLS;
@@ -84,12 +134,15 @@ legendreSeriesKernel(Geometry geo, const double* __restrict__ a, long long aStri
     if(rowBlock > c1 - 1)
         return;                              // tile entirely below the diagonal (i > j)
 
-    a += static_cast<long long>(blockIdx.z) * aStride;
     out += static_cast<long long>(blockIdx.z) * outStride;
 
-    for(int k = threadIdx.x; k <= lmax; k += TT_ROWS)
-        ttTab[k] = make_double2(a[k] * N0[k], -g0[k + 1]);
-    __syncthreads();
+    if(!STATIC)
+    {
+        a += static_cast<long long>(blockIdx.z) * aStride;
+        for(int k = threadIdx.x; k <= lmax; k += TT_ROWS)
+            ttTab[k] = make_double2(a[k] * N0[k], -g0[k + 1]);
+        __syncthreads();
+    }
 
     if(rowBlock + (threadIdx.x & ~31) > c1 - 1)
         return;                              // this warp's 32 rows are all below the diagonal
@@ -114,25 +167,22 @@ legendreSeriesKernel(Geometry geo, const double* __restrict__ a, long long aStri
             b1[r] = 0.0;
             b2[r] = 0.0;
         }
-#pragma unroll 4
-        for(int k = lmax; k >= 0; --k)
+        if(STATIC)
+            ttClenshawStatic<TT_R>(x2, b1, b2, T, entryChunk);
+        else
         {
-            const double2 t = ttTab[k];           // {a_k N_k, -g_{k+1}}
-#pragma unroll
-            for(int r = 0; r < TT_R; ++r)
-            {
-                // (a + x2 b1) - g b2: one warp-uniform operand per DFMA (see tquStep)
-                const double b = fma(t.y, b2[r], fma(x2[r], b1[r], t.x));
-                b2[r] = b1[r];
-                b1[r] = b;
-            }
+#pragma unroll 4
+            for(int k = lmax; k >= 0; --k)
+                ttStep<TT_R>(x2, b1, b2, ttTab[k]);
         }
+        double* colPtr = out + (packedOffset(c) - base + i);
 #pragma unroll
         for(int r = 0; r < TT_R; ++r)
         {
             const long long j = c + r;
             if(j < c1 && i <= j)
-                __stcs(out + (packedOffset(j) - base + i), b1[r]);
+                __stcs(colPtr, b1[r]);
+            colPtr += j + 1;                     // next column starts j+1 entries further
         }
     }
 }
@@ -480,6 +530,292 @@ tquKernel(Geometry geo, TquDynamicArgs dyn, const __grid_constant__ TquStaticTab
 
 #undef CMG_CASE
 #undef CMG_CASE5
+
+// ------------------------------------------------------------------------------------------------
+// Batched T,Q,U: many weight sets (one MCMC step's proposals) for the same pixel set.  Here the sum over l IS a
+// contraction over a shared basis: the four function families are run FORWARD once per pixel pair and batch chunk
+// (10 FP64 operations per l) and every batch element only adds 4 accumulate-FMAs per l, instead of a 10-FMA
+// Clenshaw step per element.  CTA = 32 rows x 32 columns of pixel pairs; a thread owns one pair per pass (lane =
+// row, warp = column, 4 passes of 8 columns) and accumulates PB_BT batch elements at a time (4 x PB_BT
+// accumulators in registers); the basis value is the operand the reuse cache keeps across the PB_BT accumulate
+// FMAs.  Weights arrive pre-folded (foldBatchedWeightsKernel) as [chunk][l][family][PB_BT], so staging a chunk is a
+// straight 16-byte copy.  The frame rotation factors depend on the pair only and are computed once per pass.
+// Output: matrix b at out + b * outStride, single-owner packed layout.
+// ------------------------------------------------------------------------------------------------
+constexpr int PB_BT = 16;                      // batch elements per accumulation chunk
+constexpr int PB_T = 32;                       // tile edge (rows and columns)
+constexpr int PB_CW = 8;                       // columns per pass (= warps per CTA)
+constexpr int PB_STAGE_LD = PB_CW + 1;
+
+__host__ __device__ inline size_t tquBatchedSmemBytes(int lmax)
+{
+    return sizeof(double4) * (lmax + 2)                                    // recurrence coefficients per l
+           + sizeof(double) * (static_cast<size_t>(lmax + 1) * 4 * PB_BT    // weights of the chunk [l][family][b]
+                               + 16 * PB_T                                   // frames of rows and columns
+                               + PB_BT * 3 * PB_T * PB_STAGE_LD              // transposed partners of the chunk
+                               + 6 * PB_T);                                  // destination pointers
+}
+
+// w[b][4][lmax+1] (tt, te, ee, bb weights) -> folded[chunk][l][family][PB_BT], zero padded to whole chunks
+__global__ void foldBatchedWeightsKernel(const double* __restrict__ w, DeviceTables tab, int lmax, int nBatch, double* __restrict__ folded)
+{
+    const int n1 = lmax + 1;
+    const long long total = static_cast<long long>((nBatch + PB_BT - 1) / PB_BT) * n1 * 4 * PB_BT;
+    for(long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const int bb = static_cast<int>(idx % PB_BT);
+        const int fam = static_cast<int>((idx / PB_BT) & 3);
+        const int l = static_cast<int>((idx / (4 * PB_BT)) % n1);
+        const int chunk = static_cast<int>(idx / (static_cast<long long>(4 * PB_BT) * n1));
+        const int b = chunk * PB_BT + bb;
+        double v = 0.0;
+        if(b < nBatch)
+        {
+            const double* wb = w + static_cast<long long>(b) * 4 * n1;
+            if(fam == 0) v = wb[l] * tab.N0[l];
+            else if(l >= 2)
+            {
+                if(fam == 1) v = wb[n1 + l] * tab.N20[l] * 0.61237243569579452455;
+                else if(fam == 2) v = (wb[2 * n1 + l] + wb[3 * n1 + l]) * tab.N22[l] * 0.125;
+                else v = (wb[2 * n1 + l] - wb[3 * n1 + l]) * tab.N22[l] * 0.125;
+            }
+        }
+        folded[idx] = v;
+    }
+}
+
+__global__ void __launch_bounds__(PB_T * PB_CW, 1)
+tquBatchedKernel(Geometry geo, const double* __restrict__ folded, DeviceTables tab, int lmax, int nBatch,
+                 const __grid_constant__ PartTable P, long long outStride)
+{
+    extern __shared__ double4 pbSmem[];
+    double4* sCoef = pbSmem;                                            // [lmax+2] {g0, g20, g22, c22} at l
+    double* sW = reinterpret_cast<double*>(sCoef + (lmax + 2));         // [lmax+1][4][PB_BT]
+    double* sI = sW + static_cast<size_t>(lmax + 1) * 4 * PB_BT;        // [8][PB_T]
+    double* sJ = sI + 8 * PB_T;                                         // [8][PB_T]
+    double* stage = sJ + 8 * PB_T;                                      // [PB_BT][3][PB_T][PB_STAGE_LD]
+    double** sColPtr = reinterpret_cast<double**>(stage + PB_BT * 3 * PB_T * PB_STAGE_LD);   // [3][PB_T]
+    double** sRowPtr = sColPtr + 3 * PB_T;                              // [3][PB_T]
+
+    constexpr int NT = PB_T * PB_CW;
+    const long long npix = geo.npix;
+    const long long rowBlock = static_cast<long long>(blockIdx.x) * PB_T;
+    const long long c0 = static_cast<long long>(blockIdx.y) * PB_T;
+    const long long c1 = min(c0 + static_cast<long long>(PB_T), npix);
+    if(rowBlock > c1 - 1)
+        return;
+    const int tid = threadIdx.x;
+    const int n1 = lmax + 1;
+
+    for(int k = tid; k <= lmax + 1; k += NT)
+        sCoef[k] = make_double4(tab.g0[k], tab.g20[k], tab.g22[k], tab.c22[k]);
+    for(int idx = tid; idx < 2 * PB_T; idx += NT)
+    {
+        const bool isRow = idx < PB_T;
+        const int loc = isRow ? idx : idx - PB_T;
+        const long long pix = min(isRow ? rowBlock + loc : c0 + loc, npix - 1);
+        double* dst = isRow ? sI : sJ;
+        dst[0 * PB_T + loc] = geo.nx[pix];
+        dst[1 * PB_T + loc] = geo.ny[pix];
+        dst[2 * PB_T + loc] = geo.nz[pix];
+        dst[3 * PB_T + loc] = geo.tx[pix];
+        dst[4 * PB_T + loc] = geo.ty[pix];
+        dst[5 * PB_T + loc] = geo.tz[pix];
+        dst[6 * PB_T + loc] = geo.px[pix];
+        dst[7 * PB_T + loc] = geo.py[pix];
+    }
+    for(int idx = tid; idx < 6 * PB_T; idx += NT)
+    {
+        if(idx < 3 * PB_T)
+        {
+            const int strip = idx / PB_T;
+            const long long jcol = min(c0 + (idx - strip * PB_T), npix - 1);
+            sColPtr[idx] = partEntry(P, 0, strip, npix, jcol, 0);
+        }
+        else
+        {
+            const int q = idx - 3 * PB_T;
+            const int t = q / PB_T;
+            const long long ir = min(rowBlock + (q - t * PB_T), npix - 1);
+            double* dst;
+            if(t == 0) dst = partEntry(P, 0, 1, npix, ir, c0);
+            else if(t == 1) dst = partEntry(P, 0, 2, npix, ir, c0);
+            else dst = partEntry(P, 0, 2, npix, ir, npix + c0);
+            sRowPtr[q] = dst;
+        }
+    }
+    __syncthreads();
+
+    const int il = tid & 31, warp = tid >> 5;
+    const long long i = rowBlock + il;
+    const double nix = sI[0 * PB_T + il], niy = sI[1 * PB_T + il], niz = sI[2 * PB_T + il];
+    const double tix = sI[3 * PB_T + il], tiy = sI[4 * PB_T + il], tiz = sI[5 * PB_T + il];
+    const double pix_ = sI[6 * PB_T + il], piy = sI[7 * PB_T + il];
+    const int nChunks = (nBatch + PB_BT - 1) / PB_BT;
+    const int chunkDoubles = n1 * 4 * PB_BT;
+
+    for(int pass = 0; pass < PB_T / PB_CW; ++pass)
+    {
+        if(c0 + pass * PB_CW >= c1)
+            break;                                              // uniform over the CTA
+        const int jl = pass * PB_CW + warp;
+        double x2, fTQ, fTU, fQT, fUT, reU, imU, reV, imV;
+        {
+            const double njx = sJ[0 * PB_T + jl], njy = sJ[1 * PB_T + jl], njz = sJ[2 * PB_T + jl];
+            const double tjx = sJ[3 * PB_T + jl], tjy = sJ[4 * PB_T + jl], tjz = sJ[5 * PB_T + jl];
+            const double pjx = sJ[6 * PB_T + jl], pjy = sJ[7 * PB_T + jl];
+            double dot = __dadd_rn(__dadd_rn(__dmul_rn(nix, njx), __dmul_rn(niy, njy)), __dmul_rn(niz, njz));
+            dot = fmin(1.0, fmax(-1.0, dot));
+            x2 = dot + dot;
+            const double ai = fma(njx, tix, fma(njy, tiy, njz * tiz));
+            const double bi = fma(njx, pix_, njy * piy);
+            const double aj = fma(nix, tjx, fma(niy, tjy, niz * tjz));
+            const double bj = fma(nix, pjx, niy * pjy);
+            const double p = fma(tix, tjx, fma(tiy, tjy, tiz * tjz));
+            const double q = fma(pix_, pjx, piy * pjy);
+            const double rr = fma(pix_, tjx, piy * tjy);
+            const double tq = fma(tix, pjx, tiy * pjy);
+            const double su = p + q, du = rr - tq, sv = p - q, dv = tq + rr;
+            reU = fma(su, su, -du * du); imU = 2.0 * su * du;
+            reV = fma(sv, sv, -dv * dv); imV = 2.0 * sv * dv;
+            fTQ = fma(aj, aj, -bj * bj); fTU = 2.0 * aj * bj;
+            fQT = fma(ai, ai, -bi * bi); fUT = 2.0 * ai * bi;
+        }
+        const int j32 = static_cast<int>(c0 - rowBlock) + jl;
+        const bool valid = il <= j32 && c0 + jl < c1;
+        double* colT = sColPtr[0 * PB_T + jl] + i;
+        double* colQ = sColPtr[1 * PB_T + jl] + i;
+        double* colU = sColPtr[2 * PB_T + jl] + i;
+
+        for(int chunk = 0; chunk < nChunks; ++chunk)
+        {
+            __syncthreads();                                    // previous chunk's weights and stage are free
+            {
+                const double2* src = reinterpret_cast<const double2*>(folded + static_cast<long long>(chunk) * chunkDoubles);
+                double2* dst = reinterpret_cast<double2*>(sW);
+                for(int idx = tid; idx < chunkDoubles / 2; idx += NT)
+                    dst[idx] = __ldg(src + idx);
+            }
+            __syncthreads();
+
+            double acc[4][PB_BT];
+            // l = 0 and l = 1: temperature only (phi_0 = 1, phi_1 = x2)
+#pragma unroll
+            for(int b = 0; b < PB_BT; ++b)
+            {
+                acc[0][b] = fma(x2, sW[(1 * 4 + 0) * PB_BT + b], sW[(0 * 4 + 0) * PB_BT + b]);
+                acc[1][b] = 0.0;
+                acc[2][b] = 0.0;
+                acc[3][b] = 0.0;
+            }
+            // basis values at l and l-1: P_l family continues from l = 1, spin-2 families start with phi_1 = 0, phi_2 = 1
+            double t0 = x2, t1 = fma(x2, x2, -sCoef[1].x);
+            double e0 = 0.0, e1 = 1.0, p0 = 0.0, p1 = 1.0, m0 = 0.0, m1 = 1.0;
+#pragma unroll 2
+            for(int l = 2; l <= lmax; ++l)
+            {
+                const double2* wl = reinterpret_cast<const double2*>(sW + static_cast<size_t>(l) * 4 * PB_BT);
+#pragma unroll
+                for(int b = 0; b < PB_BT; b += 2)
+                {
+                    const double2 wt = wl[(0 * PB_BT + b) / 2];
+                    acc[0][b] = fma(t1, wt.x, acc[0][b]);
+                    acc[0][b + 1] = fma(t1, wt.y, acc[0][b + 1]);
+                }
+#pragma unroll
+                for(int b = 0; b < PB_BT; b += 2)
+                {
+                    const double2 we = wl[(1 * PB_BT + b) / 2];
+                    acc[1][b] = fma(e1, we.x, acc[1][b]);
+                    acc[1][b + 1] = fma(e1, we.y, acc[1][b + 1]);
+                }
+#pragma unroll
+                for(int b = 0; b < PB_BT; b += 2)
+                {
+                    const double2 wp = wl[(2 * PB_BT + b) / 2];
+                    acc[2][b] = fma(p1, wp.x, acc[2][b]);
+                    acc[2][b + 1] = fma(p1, wp.y, acc[2][b + 1]);
+                }
+#pragma unroll
+                for(int b = 0; b < PB_BT; b += 2)
+                {
+                    const double2 wm = wl[(3 * PB_BT + b) / 2];
+                    acc[3][b] = fma(m1, wm.x, acc[3][b]);
+                    acc[3][b + 1] = fma(m1, wm.y, acc[3][b + 1]);
+                }
+                const double4 c = sCoef[l];                     // phi_{l+1} = (x2 - c_l) phi_l - g_l phi_{l-1}
+                const double tn = fma(x2, t1, -c.x * t0);
+                const double en = fma(x2, e1, -c.y * e0);
+                const double pn = fma(x2 - c.w, p1, -c.z * p0);
+                const double mn = fma(x2 + c.w, m1, -c.z * m0);
+                t0 = t1; t1 = tn;
+                e0 = e1; e1 = en;
+                p0 = p1; p1 = pn;
+                m0 = m1; m1 = mn;
+            }
+
+            // rotation + stores, one batch element after the other; running pointers instead of 64-bit multiplies
+            {
+                const long long first = static_cast<long long>(chunk) * PB_BT * outStride;
+                double* pT = colT + first;
+                double* pQ = colQ + first;
+                double* pU = colU + first;
+                double* st = stage + il * PB_STAGE_LD + warp;
+                const int nLive = min(PB_BT, nBatch - chunk * PB_BT);
+#pragma unroll
+                for(int b = 0; b < PB_BT; ++b)
+                {
+                    const double xt = -acc[1][b];
+                    const double aRe = acc[2][b] * reU, aIm = acc[2][b] * imU;
+                    const double bRe = acc[3][b] * reV, bIm = acc[3][b] * imV;
+                    if(valid && b < nLive)
+                    {
+                        __stcs(pT, acc[0][b]);
+                        __stcs(pQ, xt * fTQ);
+                        __stcs(pQ + npix, aRe + bRe);
+                        __stcs(pU, xt * fTU);
+                        __stcs(pU + npix, bIm - aIm);
+                        __stcs(pU + 2 * npix, aRe - bRe);
+                    }
+                    st[0] = xt * fQT;
+                    st[1 * PB_T * PB_STAGE_LD] = xt * fUT;
+                    st[2 * PB_T * PB_STAGE_LD] = aIm + bIm;
+                    st += 3 * PB_T * PB_STAGE_LD;
+                    pT += outStride;
+                    pQ += outStride;
+                    pU += outStride;
+                }
+            }
+            __syncthreads();
+            // transposed partners of the chunk: thread (row ilr, column c8) walks the 3 x PB_BT (kind, batch) values
+            {
+                const int c8 = tid & (PB_CW - 1);
+                const int ilr = tid >> 3;                       // 0 .. 31
+                const int jlw = pass * PB_CW + c8;
+                const int j32w = static_cast<int>(c0 - rowBlock) + jlw;
+                if(c0 + jlw < c1 && ilr < j32w)
+                {
+                    const int nLive = min(PB_BT, nBatch - chunk * PB_BT);
+                    const long long first = static_cast<long long>(chunk) * PB_BT * outStride + jlw;
+                    double* d0 = sRowPtr[0 * PB_T + ilr] + first;
+                    double* d1 = sRowPtr[1 * PB_T + ilr] + first;
+                    double* d2 = sRowPtr[2 * PB_T + ilr] + first;
+                    const double* sv = stage + ilr * PB_STAGE_LD + c8;
+                    for(int b = 0; b < nLive; ++b)
+                    {
+                        __stcs(d0, sv[0]);
+                        __stcs(d1, sv[1 * PB_T * PB_STAGE_LD]);
+                        __stcs(d2, sv[2 * PB_T * PB_STAGE_LD]);
+                        sv += 3 * PB_T * PB_STAGE_LD;
+                        d0 += outStride;
+                        d1 += outStride;
+                        d2 += outStride;
+                    }
+                }
+            }
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // CMatrix::maskMatrix gather (reference source/c_matrix.cpp:182-201): out(a,b) = in(good[a], good[b])

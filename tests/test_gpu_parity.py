@@ -295,12 +295,17 @@ def test_batched_generation_matches_single_calls(gpu_ctx, oracle_api):
     # TQU
     ab = np.stack([np.stack(capi.tqu_weights(*synthetic_cl(lmax, seed=200 + b, pol=True), f, f)) for b in range(nb)])
     stride = capi.packed_size(3 * n)
-    outp = torch.full((nb * stride,), float("nan"), dtype=torch.float64, device="cuda")
-    gpu_ctx.tqu_batched(ab, outp, stride)
-    torch.cuda.synchronize()
-    for b in range(nb):
-        want = oracle_api.tqu_matrix(*synthetic_cl(lmax, seed=200 + b, pol=True), nside, 10.0, good=good)
-        _assert_tqu_close(outp[b * stride:(b + 1) * stride].cpu().numpy(), want, n)
+    wants = [oracle_api.tqu_matrix(*synthetic_cl(lmax, seed=200 + b, pol=True), nside, 10.0, good=good) for b in range(nb)]
+    try:
+        for variant in (0, 900):          # per-element Clenshaw (default) and the shared-basis kernel
+            gpu_ctx.set_kernel_variant(variant)
+            outp = torch.full((nb * stride,), float("nan"), dtype=torch.float64, device="cuda")
+            gpu_ctx.tqu_batched(ab, outp, stride)
+            torch.cuda.synchronize()
+            for b in range(nb):
+                _assert_tqu_close(outp[b * stride:(b + 1) * stride].cpu().numpy(), wants[b], n)
+    finally:
+        gpu_ctx.set_kernel_variant(0)
 
 
 def test_all_kernel_variants_agree(gpu_ctx, oracle_api):
