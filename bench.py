@@ -186,12 +186,12 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def config_dict(name, kind, nside, lmax, npix, n_gpus):
+def config_dict(name, kind, nside, lmax, npix, n_gpus, shard_mode="outbox"):
     dim = npix * (3 if kind == "tqu" else 1)
     return {
         "workload": name, "kind": kind, "nside": nside, "lmax": lmax, "npix": npix, "matrix_dim": dim,
         "packed_bytes": 8 * dim * (dim + 1) // 2, "fwhm_deg": FWHM, "pixel_window": "1 (HEALPix window file unavailable offline)",
-        "sharding": "equal-area pixel-column blocks over %d rank(s), no collective" % n_gpus,
+        "sharding": "equal-area pixel-column blocks over %d rank(s), no collective" % n_gpus, "shard_mode": shard_mode if n_gpus > 1 else "single",
         "l2": "each step writes its whole output (>> 126 MB L2) with streaming stores; nothing is re-read between steps",
     }
 
@@ -233,18 +233,14 @@ def run_gpu_arm(args):
         launch = lambda: ctx.legendre_series(weights, shard, a0, a1)
         pieces = [shard]
     else:
+        from cosmopp_b200 import multigpu
         spectra = synthetic_cl(lmax, pol=True)
         weights = capi.tqu_weights(*spectra, f, f)
-        sizes = partition.tqu_shard_sizes(npix, a0, a1)
-        strips = [torch.empty(s, dtype=torch.float64, device="cuda") for s in sizes]
-        plan = partition.tqu_rank_plan(npix, bounds, rank)
-        outbox = {}
-        for owner, ncols, ld, _row0 in plan["outbox"]:
-            # entries <Q_i T_j>, <U_i T_j>, <U_i Q_j> this rank computes for the owner's columns i: dense blocks, kept local
-            outbox[owner] = [torch.empty(ncols * ld, dtype=torch.float64, device="cuda") for _ in range(3)]
-        lay = capi.make_tqu_layout(bounds, rank, [t.data_ptr() for t in strips], {k: [t.data_ptr() for t in v] for k, v in outbox.items()})
+        mode = args.shard_mode if world > 1 else "outbox"
+        sharded = multigpu.ShardedTQU(ctx, npix, rank, world, mode=mode)
+        lay = sharded.layout
         launch = lambda: ctx.tqu(*weights, lay)
-        pieces = strips + [b for blk in outbox.values() for b in blk]
+        pieces = [b.tensor() for b in sharded.pieces()]
     d2h_bytes = sum(p.numel() for p in pieces) * 8
     h2d_bytes = (len(weights) if kind == "tt" else 4 * (lmax + 1)) * 8
 
@@ -300,12 +296,32 @@ def run_gpu_arm(args):
         "hbm_write_gbs": d2h_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": hbm_peak,
     }
 
+    # ---- optional: whole matrix resident on every GPU (NCCL broadcasts of the strips over NVLink)
+    gather = None
+    if args.gather and kind == "tqu" and world > 1:
+        full = torch.empty(capi.packed_size(3 * npix), dtype=torch.float64, device="cuda")
+        sharded.gather_full(full)
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        sharded.gather_full(full)
+        g1.record(stream)
+        barrier()
+        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gather = {"ms": float(gt.item()), "bytes_per_gpu_in": 8 * (capi.packed_size(3 * npix) - sum(sharded.plan["strips"])),
+                  "how": "ncclBroadcast of every strip straight into place; outbox blocks via a scratch buffer + cmg_tqu_scatter_block"}
+        del full
+        torch.cuda.empty_cache()
+
     # ---- e2e: host C_l in, host packed shard out, copies inside the timed region
     e2e = None
     if not args.no_e2e:
         if kind == "tqu" and world == 1:
-            del strips, pieces, lay
+            del pieces, lay
             launch = None
+            sharded.close()
             torch.cuda.empty_cache()
             host = torch.empty(capi.packed_size(3 * npix), dtype=torch.float64, pin_memory=True)
             spectra_pinned = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in spectra]
@@ -346,9 +362,9 @@ def run_gpu_arm(args):
         line = {
             "metric": "pixel_pair_ell_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "ms_per_matrix": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world),
+            "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world, args.shard_mode),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "fp64_frac_of_peak": achieved / peak_tflops,
+            "fp64_frac_of_peak": achieved / peak_tflops, "gather": gather,
         }
         print(json.dumps(line))
     if world > 1:
@@ -362,6 +378,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="tqu_nside64_lmax192", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shard-mode", default="outbox", choices=["outbox", "peer"],
+                    help="N>1, T,Q,U: keep entries owned by another rank in local blocks (outbox) or write them into the owner's strip "
+                         "through CUDA-IPC peer memory over NVLink (peer)")
+    ap.add_argument("--gather", action="store_true", help="N>1, T,Q,U: also time the NCCL gather of the whole matrix onto every GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

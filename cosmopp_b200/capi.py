@@ -60,6 +60,9 @@ _SIGNATURES = {
     "cmg_device_free": (ctypes.c_int, [_vp, _vp]),
     "cmg_host_malloc_pinned": (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
     "cmg_host_free_pinned": (ctypes.c_int, [_vp]),
+    "cmg_ipc_export": (ctypes.c_int, [_vp, _vp, _vp]),
+    "cmg_ipc_open": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp)]),
+    "cmg_ipc_close": (ctypes.c_int, [_vp, _vp]),
     "cmg_copy_to_host": (ctypes.c_int, [_vp, _vp, _vp, _i64]),
     "cmg_copy_to_device": (ctypes.c_int, [_vp, _vp, _vp, _i64]),
     "cmg_nside2npix": (_i64, [_i64]),
@@ -82,6 +85,7 @@ _SIGNATURES = {
     "cmg_mask_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "cmg_tqu_layout_single": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(TquLayout)]),
     "cmg_tqu": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(TquLayout)]),
+    "cmg_tqu_scatter_block": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_int, _vp]),
     "cmg_tqu_weights": (ctypes.c_int, [_vp] * 6 + [ctypes.c_int] + [_vp] * 4),
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
     "cmg_legendre_series_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _i64, _vp, _i64]),
@@ -191,6 +195,31 @@ class Context:
         self._check(self._L.cmg_measure_fp64_peak(self._h, ctypes.byref(v)))
         return v.value
 
+    # ---- raw device buffers (shareable between the ranks of one box)
+    def device_malloc(self, nbytes):
+        p = _vp()
+        self._check(self._L.cmg_device_malloc(self._h, int(nbytes), ctypes.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        self._check(self._L.cmg_device_free(self._h, _vp(ptr)))
+
+    def ipc_export(self, ptr):
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._L.cmg_ipc_export(self._h, _vp(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = _vp()
+        self._check(self._L.cmg_ipc_open(self._h, ctypes.c_char_p(handle), ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(self._L.cmg_ipc_close(self._h, _vp(ptr)))
+
+    def copy_to_host(self, dst_host, d_src, nbytes):
+        self._check(self._L.cmg_copy_to_host(self._h, _p(dst_host), _p(d_src), int(nbytes)))
+
     # ---- geometry
     def set_pixels(self, nside, good=None):
         if good is None:
@@ -248,6 +277,9 @@ class Context:
     def tqu(self, a_tt, a_te, a_ee, a_bb, layout):
         a_tt, a_te, a_ee, a_bb = map(_f64, (a_tt, a_te, a_ee, a_bb))
         self._check(self._L.cmg_tqu(self._h, _p(a_tt), _p(a_te), _p(a_ee), _p(a_bb), len(a_tt) - 1, ctypes.byref(layout)))
+
+    def tqu_scatter_block(self, d_block, col0, n_cols, ld, row0, kind, d_full):
+        self._check(self._L.cmg_tqu_scatter_block(self._h, _p(d_block), col0, n_cols, ld, row0, kind, _p(d_full)))
 
     def tqu_batched(self, a, d_out, stride):
         a = _f64(a)         # [B][4][lmax+1]

@@ -466,6 +466,35 @@ cmg_status cmg_device_free(cmg_ctx* ctx, void* p)
     return CMG_OK;
 }
 
+cmg_status cmg_ipc_export(cmg_ctx* ctx, void* dPtr, void* handle)
+{
+    if(!ctx || !dPtr || !handle) return CMG_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == CMG_IPC_HANDLE_BYTES, "IPC handle size");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CMG_CUDA(ctx, cudaIpcGetMemHandle(&h, dPtr));
+    std::memcpy(handle, &h, sizeof(h));
+    return CMG_OK;
+}
+
+cmg_status cmg_ipc_open(cmg_ctx* ctx, const void* handle, void** dPeer)
+{
+    if(!ctx || !handle || !dPeer) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CMG_CUDA(ctx, cudaIpcOpenMemHandle(dPeer, h, cudaIpcMemLazyEnablePeerAccess));
+    return CMG_OK;
+}
+
+cmg_status cmg_ipc_close(cmg_ctx* ctx, void* dPeer)
+{
+    if(!ctx || !dPeer) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaIpcCloseMemHandle(dPeer));
+    return CMG_OK;
+}
+
 cmg_status cmg_host_malloc_pinned(int64_t bytes, void** p)
 {
     if(!p || bytes < 0) return CMG_EINVAL;
@@ -868,6 +897,24 @@ cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* 
     if((s = cmg_tqu(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, &layout)) != CMG_OK) return s;
     CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CMG_OK;
+}
+
+cmg_status cmg_tqu_scatter_block(cmg_ctx* ctx, const double* dBlock, int64_t col0, int64_t nCols, int64_t ld, int64_t row0, int kind,
+                                 double* dFullPacked)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(ctx->npix <= 0) return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
+    if(!dBlock || !dFullPacked || kind < 0 || kind > 2 || col0 < 0 || nCols < 0 || ld < 0 || row0 < 0 || col0 + nCols > ctx->npix ||
+       row0 + ld > ctx->npix || (nCols > 0 && ld > 0 && row0 < col0 + nCols))
+        return fail(ctx, CMG_EINVAL, "block outside the strictly-lower rectangle it can describe");
+    if(nCols == 0 || ld == 0) return CMG_OK;
+    if(nCols > 65535) return fail(ctx, CMG_EUNSUPPORTED, "more than 65535 owner columns in one block");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const dim3 grid(static_cast<unsigned>(std::min<int64_t>((ld + 255) / 256, 64)), static_cast<unsigned>(nCols));
+    cmg::scatterBlockKernel<<<grid, 256, 0, ctx->stream>>>(dBlock, ctx->npix, col0, nCols, ld, row0, kind, dFullPacked);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
     return CMG_OK;
 }
 

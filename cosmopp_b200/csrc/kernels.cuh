@@ -836,6 +836,26 @@ __global__ void maskGatherKernel(const double* __restrict__ in, const int* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Places one dense block of a kind-1 ("outbox") shard into a whole packed [T;Q;U] triangle: block kind t holds
+// <Q_i T_j> (t=0), <U_i T_j> (t=1) or <U_i Q_j> (t=2) for owner columns i in [col0, col0+nCols) and rows j in
+// [row0, row0+ld), element (i - col0) * ld + (j - row0).  Lanes run along j: both sides are contiguous.
+// ------------------------------------------------------------------------------------------------
+__global__ void scatterBlockKernel(const double* __restrict__ block, long long npix, long long col0, long long nCols,
+                                   long long ld, long long row0, int t, double* __restrict__ full)
+{
+    const long long ic = blockIdx.y;
+    if(ic >= nCols)
+        return;
+    const long long i = col0 + ic;
+    const long long col = (t == 0 ? npix : 2 * npix) + i;
+    const long long rowShift = (t == 2 ? npix : 0);
+    double* dst = full + packedOffset(col) + rowShift + row0;
+    const double* src = block + ic * ld;
+    for(long long jj = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; jj < ld; jj += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[jj] = src[jj];
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 peak: independent DFMA chains, no memory traffic.  8 chains x 4096 iterations per thread.
 // ------------------------------------------------------------------------------------------------
 constexpr int PEAK_CHAINS = 8;

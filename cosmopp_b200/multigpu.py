@@ -1,0 +1,115 @@
+"""One-process-per-GPU plumbing for a sharded [T;Q;U] matrix on one box (torch.distributed for the exchange of IPC
+handles, barriers and the optional NCCL gather; no data-path collective is needed to produce the shards).
+
+Two ways to hold the entries a rank computes for another owner's columns (include/cmg.h, cmg_tqu_layout):
+  "outbox"  keep them in local dense blocks (kind 1): nothing crosses NVLink, shards are block-distributed;
+  "peer"    write them straight into the owner's packed strip through CUDA-IPC mapped peer memory (kind 0): the kernel's
+            stores go over NVLink while the recurrences run, and afterwards every strip is complete in place.
+"""
+import numpy as np
+
+from . import capi, partition
+
+
+class DeviceBuffer:
+    """cmg_device_malloc'ed buffer of doubles exposing __cuda_array_interface__ (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ctx, n_doubles):
+        self.ctx = ctx
+        self.n = int(n_doubles)
+        self.ptr = ctx.device_malloc(8 * max(self.n, 1))
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n,), "typestr": "<f8", "data": (self.ptr, False), "version": 2}
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device="cuda")
+
+    def free(self):
+        if self.ptr:
+            self.ctx.device_free(self.ptr)
+            self.ptr = 0
+
+
+class ShardedTQU:
+    """Rank-local storage + layout of one sharded polarized matrix."""
+
+    def __init__(self, ctx, npix, rank, world, mode="outbox", align=32):
+        import torch.distributed as dist
+        self.ctx, self.npix, self.rank, self.world, self.mode = ctx, npix, rank, world, mode
+        self.bounds = partition.column_partition(npix, world, align=align)
+        plan = partition.tqu_rank_plan(npix, self.bounds, rank)
+        self.plan = plan
+        self.strips = [DeviceBuffer(ctx, s) for s in plan["strips"]]
+        self.outbox = {}
+        self.peer_ptrs = {}
+        if mode == "outbox" or world == 1:
+            for owner, ncols, ld, _ in plan["outbox"]:
+                self.outbox[owner] = [DeviceBuffer(ctx, ncols * ld) for _ in range(3)]
+            self.layout = capi.make_tqu_layout(self.bounds, rank, [b.ptr for b in self.strips],
+                                               {k: [b.ptr for b in v] for k, v in self.outbox.items()})
+        elif mode == "peer":
+            mine = [ctx.ipc_export(b.ptr) for b in self.strips]
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            lay = capi.TquLayout()
+            lay.n_parts, lay.own = world, rank
+            for k in range(world + 1):
+                lay.begin[k] = self.bounds[k]
+            for k in range(world):
+                if k == rank:
+                    ptrs = [b.ptr for b in self.strips]
+                elif k < rank and self.bounds[k + 1] > self.bounds[k]:
+                    ptrs = [ctx.ipc_open(h) for h in everyone[k]]       # only owners to the left receive entries from this rank
+                    self.peer_ptrs[k] = ptrs
+                else:
+                    continue
+                for s in range(3):
+                    lay.ptr[k][s] = ptrs[s]
+                lay.kind[k] = 0
+            self.layout = lay
+        else:
+            raise ValueError("mode must be 'outbox' or 'peer'")
+
+    def pieces(self):
+        """device buffers this rank holds (for copies to the host)"""
+        return self.strips + [b for v in self.outbox.values() for b in v]
+
+    def gather_full(self, full):
+        """NCCL: every rank ends up with the whole packed triangle in `full` (a cuda tensor of 3N(3N+1)/2 doubles).
+        Strips are contiguous pieces of the packed triangle, so each is one broadcast straight into place.  In 'outbox'
+        mode the dense blocks are broadcast into a scratch buffer and placed by cmg_tqu_scatter_block (NCCL moves large
+        contiguous buffers at NVLink speed; fine-grained remote stores do not)."""
+        import torch
+        import torch.distributed as dist
+        scratch = None
+        for k in range(self.world):
+            sizes = partition.tqu_shard_sizes(self.npix, self.bounds[k], self.bounds[k + 1])
+            offs = partition.tqu_strip_offsets(self.npix, self.bounds[k])
+            for s in range(3):
+                dst = full[offs[s]:offs[s] + sizes[s]]
+                if k == self.rank:
+                    dst.copy_(self.strips[s].tensor())
+                if self.world > 1 and sizes[s]:
+                    dist.broadcast(dst, src=k)
+        if self.mode == "outbox" and self.world > 1:
+            for r in range(self.world):                     # rank r's blocks for every owner to its left
+                plan = partition.tqu_rank_plan(self.npix, self.bounds, r)
+                for owner, ncols, ld, row0 in plan["outbox"]:
+                    n = ncols * ld
+                    if scratch is None or scratch.numel() < n:
+                        scratch = torch.empty(n, dtype=torch.float64, device="cuda")
+                    for t in range(3):
+                        buf = self.outbox[owner][t].tensor() if r == self.rank else scratch[:n]
+                        dist.broadcast(buf, src=r)
+                        self.ctx.tqu_scatter_block(buf, self.bounds[owner], ncols, ld, row0, t, full)
+
+    def close(self):
+        for ptrs in self.peer_ptrs.values():
+            for p in ptrs:
+                self.ctx.ipc_close(p)
+        self.peer_ptrs = {}
+        for b in self.pieces():
+            b.free()

@@ -71,6 +71,14 @@ cmg_status cmg_device_malloc(cmg_ctx* ctx, int64_t bytes, void** d_ptr);
 cmg_status cmg_device_free(cmg_ctx* ctx, void* d_ptr);
 cmg_status cmg_host_malloc_pinned(int64_t bytes, void** ptr);
 cmg_status cmg_host_free_pinned(void* ptr);
+/* CUDA IPC export / import of a cmg_device_malloc'ed buffer, for ranks of one box that write the entries they
+ * compute for another owner straight into that owner's strip over NVLink (cmg_tqu_layout kind 0 with peer
+ * pointers).  handle receives CMG_IPC_HANDLE_BYTES bytes; cmg_ipc_open maps a peer rank's buffer into this process
+ * (peer access is enabled on first use) and cmg_ipc_close unmaps it. */
+#define CMG_IPC_HANDLE_BYTES 64
+cmg_status cmg_ipc_export(cmg_ctx* ctx, void* d_ptr, void* handle);
+cmg_status cmg_ipc_open(cmg_ctx* ctx, const void* handle, void** d_peer_ptr);
+cmg_status cmg_ipc_close(cmg_ctx* ctx, void* d_peer_ptr);
 /* stream-ordered copies on the context's stream */
 cmg_status cmg_copy_to_host(cmg_ctx* ctx, void* dst_host, const void* d_src, int64_t bytes);
 cmg_status cmg_copy_to_device(cmg_ctx* ctx, void* d_dst, const void* src_host, int64_t bytes);
@@ -164,6 +172,11 @@ cmg_status cmg_tqu_layout_single(cmg_ctx* ctx, double* d_packed, cmg_tqu_layout*
  * a_xx are HOST arrays of lmax+1 weights C^XX_l (2l+1)/(4pi) x window factors; entries l<2 ignored. */
 cmg_status cmg_tqu(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
                    const double* a_bb, int lmax, const cmg_tqu_layout* layout);
+/* Places one dense kind-1 block (see cmg_tqu_layout) into a whole packed 3N triangle on this GPU: kind 0/1/2 =
+ * <Q_i T_j>, <U_i T_j>, <U_i Q_j> for owner columns i in [col0, col0+n_cols) and rows j in [row0, row0+ld).  Used when
+ * the unsharded matrix must be assembled (after the blocks were moved with NCCL or a copy). */
+cmg_status cmg_tqu_scatter_block(cmg_ctx* ctx, const double* d_block, int64_t col0, int64_t n_cols, int64_t ld, int64_t row0,
+                                 int kind, double* d_full_packed);
 /* weights from spectra and the temperature / polarization window*beam factors */
 cmg_status cmg_tqu_weights(const double* ctt, const double* cte, const double* cee, const double* cbb,
                            const double* fT, const double* fP, int lmax,

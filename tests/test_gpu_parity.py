@@ -368,3 +368,33 @@ def test_tt_large_sample_nside32(gpu_ctx, oracle_api):
     pj = np.concatenate([pj, np.arange(n), aj])
     want = oracle_api.cl_to_cmatrix_pairs(cl, nside, 10.0, pi, pj, good=np.arange(n, dtype=np.int32))
     assert np.abs(got[pj * (pj + 1) // 2 + pi] - want).max() <= REL_TOL * want[len(want) - 2048 - n]
+
+
+def test_scatter_block_places_outbox_entries(gpu_ctx, oracle_api):
+    """cmg_tqu_scatter_block: outbox blocks of a 3-way sharded run land where the one-piece matrix has them."""
+    torch = _torch()
+    from cosmopp_b200 import capi, partition
+    nside, lmax, parts = 8, 14, 3
+    gpu_ctx.set_pixels(nside)
+    n = gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    a = capi.tqu_weights(*synthetic_cl(lmax, pol=True), f, f)
+    whole = _whole_tqu(gpu_ctx, a, n)
+    b = partition.column_partition(n, parts, align=32)
+    full = torch.full_like(whole, float("nan"))
+    for r in range(parts):
+        plan = partition.tqu_rank_plan(n, b, r)
+        strips = [torch.full((s,), float("nan"), dtype=torch.float64, device="cuda") for s in plan["strips"]]
+        outbox = {o: [torch.full((nc * ld,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(3)] for o, nc, ld, _ in plan["outbox"]}
+        gpu_ctx.tqu(*a, capi.make_tqu_layout(b, r, [t.data_ptr() for t in strips], {k: [t.data_ptr() for t in v] for k, v in outbox.items()}))
+        torch.cuda.synchronize()
+        for s in range(3):
+            lo = partition.tqu_strip_offsets(n, b[r])[s]
+            seg = full[lo:lo + strips[s].numel()]
+            m = ~torch.isnan(strips[s])
+            seg[m] = strips[s][m]
+        for o, nc, ld, row0 in plan["outbox"]:
+            for t in range(3):
+                gpu_ctx.tqu_scatter_block(outbox[o][t], b[o], nc, ld, row0, t, full)
+    torch.cuda.synchronize()
+    assert torch.equal(full, whole)
