@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -251,13 +251,14 @@ def run_gpu_arm(args):
 
     peak_tflops = ctx.measure_fp64_peak()
 
-    # ---- value: device-resident, K timed steps
-    for _ in range(max(args.warmup, 3)):
-        launch()
-    barrier()
+    # ---- value: device-resident, K timed steps.  The clock sampler runs from the warm-up on, so that short timed
+    # regions (a few ms at N=8) still get samples taken under this very load.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        launch()
+    barrier()
     launches0 = ctx.launches
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -267,8 +268,16 @@ def run_gpu_arm(args):
     e1.record(stream)
     barrier()
     ms_local = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches - launches0
+    if rank == 0 and len(sampler.lines) < 8:
+        # timed region shorter than the sampling period: keep the same kernel running (untimed) until there are samples
+        t_end = time.perf_counter() + 1.0
+        while time.perf_counter() < t_end and len(sampler.lines) < 12:
+            launch()
+            torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
     t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -107,30 +107,24 @@ class CMatrix:
                     k += 1
 
     def readFromTextFile(self, fileName):
+        """Reads what writeIntoTextFile writes: nPix, comment line, then "i j value" rows.  (The reference's reader,
+        source/c_matrix.cpp:114-158, tokenises on white space and only picks up the first number of a row.)"""
         try:
             f = open(fileName, "r")
         except OSError:
             raise StandardException("Cannot read the input file %s." % fileName)
         with f:
-            first = f.readline()
-            n = int(first.split()[0])
+            n = int(f.readline().split()[0])
             if n <= 0:
                 raise StandardException("the number of pixels must be positive.")
             self._n = n
             self._m = np.zeros(capi.packed_size(n))
-            # the reference reads the remainder of the first line as the comment (c_matrix.cpp:125):
-            # it is what follows the number on that line, normally empty
-            self._comment = first.strip()[len(first.split()[0]):]
-            toks = f.read().split()
-            # the reference then parses whitespace-separated tokens one per `in >> s` -- i.e. it really
-            # only works when a row is a single token; we accept the i j value triplets it writes
-            body = toks
-            if len(body) % 3 and len(body) % 3 == 0:
-                pass
-            start = len(body) - 3 * capi.packed_size(n) if len(body) >= 3 * capi.packed_size(n) else len(body) % 3
-            body = body[start:]
-            for t in range(0, len(body) - 2, 3):
-                i, j, v = int(body[t]), int(body[t + 1]), float(body[t + 2])
+            self._comment = f.readline().rstrip("\n")
+            for line in f:
+                parts = line.split()
+                if len(parts) < 3:
+                    continue
+                i, j, v = int(parts[0]), int(parts[1]), float(parts[2])
                 if not (0 <= i < n):
                     raise StandardException("Invalid index i = %d." % i)
                 if not (0 <= j < n):
