@@ -398,3 +398,113 @@ def test_scatter_block_places_outbox_entries(gpu_ctx, oracle_api):
                 gpu_ctx.tqu_scatter_block(outbox[o][t], b[o], nc, ld, row0, t, full)
     torch.cuda.synchronize()
     assert torch.equal(full, whole)
+
+
+@pytest.mark.parametrize("lmax", [0, 1, 2, 3, 441, 442, 700])
+def test_tt_lmax_edges(gpu_ctx, oracle_api, lmax):
+    """Series of length 1 and 2 (monopole/dipole only, as the fiducial term uses), the last lmax of the static-table
+    kernel, the first of the shared-memory fallback, and a long series."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside = 2
+    gpu_ctx.set_pixels(nside)
+    n = gpu_ctx.npix
+    rs = np.random.RandomState(lmax)
+    a = rs.uniform(0.5, 1.5, lmax + 1) / (1.0 + np.arange(lmax + 1)) ** 2
+    out = torch.full((capi.packed_size(n),), float("nan"), dtype=torch.float64, device="cuda")
+    gpu_ctx.legendre_series(a, out)
+    torch.cuda.synchronize()
+    v = oracle_api.unit_vectors(nside)
+    z = np.clip(v @ v.T, -1, 1)
+    from numpy.polynomial import legendre as L
+    want = L.legval(z, a)
+    got = oracle_api.unpack_symmetric(out.cpu().numpy(), n)
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(a).sum()
+
+
+@pytest.mark.parametrize("lmax", [2, 3, 441, 442, 600])
+def test_tqu_lmax_edges(gpu_ctx, oracle_api, lmax):
+    nside = 2
+    spectra = synthetic_cl(lmax, pol=True)
+    got, n = _tqu_gpu(gpu_ctx, spectra, nside, 1.0)
+    want = oracle_api.tqu_matrix(*spectra, nside, 1.0)
+    _assert_tqu_close(got, want, n)
+
+
+@pytest.mark.parametrize("pixels", [[7], [3, 100], list(range(33)), list(range(0, 192, 3)), [50, 2, 2, 191, 0, 77]])
+def test_ragged_pixel_lists(gpu_ctx, oracle_api, pixels):
+    """One pixel, sizes straddling the tile edges, and an unsorted list with a repeated pixel (the reference takes
+    goodPixels in the caller's order and does not require uniqueness)."""
+    nside, lmax = 4, 9
+    good = np.array(pixels, dtype=np.int32)
+    cl = synthetic_cl(lmax)
+    got = _tt_gpu(gpu_ctx, cl, nside, 10.0, good)
+    want = oracle_api.cl_to_cmatrix(cl, nside, 10.0, good=good)
+    assert got.shape == want.shape and np.abs(got - want).max() <= REL_TOL * want[0]
+    spectra = synthetic_cl(lmax, pol=True)
+    gotp, n = _tqu_gpu(gpu_ctx, spectra, nside, 10.0, good)
+    _assert_tqu_close(gotp, oracle_api.tqu_matrix(*spectra, nside, 10.0, good=good), n)
+
+
+def test_linearity_in_the_spectra(gpu_ctx):
+    """Size-independent property: the matrix is linear in C_l (checked at Nside=16 on whole matrices)."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside, lmax = 16, 47
+    gpu_ctx.set_pixels(nside)
+    n = gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    s1, s2 = synthetic_cl(lmax, seed=1, pol=True), synthetic_cl(lmax, seed=2, pol=True)
+    mats = []
+    for sp in (s1, s2, tuple(2.0 * x + 0.5 * y for x, y in zip(s1, s2))):
+        out = torch.empty(capi.packed_size(3 * n), dtype=torch.float64, device="cuda")
+        gpu_ctx.tqu(*capi.tqu_weights(*sp, f, f), gpu_ctx.tqu_layout_single(out))
+        mats.append(out)
+    torch.cuda.synchronize()
+    resid = (mats[2] - (2.0 * mats[0] + 0.5 * mats[1])).abs().max().item()
+    assert resid <= 1e-12 * mats[2][0].item()
+
+
+def test_full_size_nside64_polarized_sampled(gpu_ctx, oracle_api):
+    """BASELINE config 5 at full size (147456 x 147456, 87 GB on the device): all nine entries of 150k random pixel
+    pairs, of every diagonal pair and of 2000 antipodal pairs against the oracle, plus the block structure on the diagonal."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    free, _total = torch.cuda.mem_get_info()
+    nside, lmax = 64, 192
+    n = 12 * nside * nside
+    need = 8 * capi.packed_size(3 * n)
+    if free < need + (4 << 30):
+        pytest.skip("needs %.0f GB of free device memory" % (need / 1e9))
+    spectra = synthetic_cl(lmax, pol=True)
+    gpu_ctx.set_pixels(nside)
+    f = capi.window_beam(lmax, 10.0)
+    a = capi.tqu_weights(*spectra, f, f)
+    out = torch.empty(capi.packed_size(3 * n), dtype=torch.float64, device="cuda")
+    out.fill_(float("nan"))
+    gpu_ctx.tqu(*a, gpu_ctx.tqu_layout_single(out))
+    torch.cuda.synchronize()
+    assert not torch.isnan(out[::4099]).any()
+    rs = np.random.RandomState(64)
+    pj = rs.randint(0, n, 150000)
+    pi = (rs.uniform(size=len(pj)) * (pj + 1)).astype(np.int64)
+    v = oracle_api.unit_vectors(nside)
+    anti = np.array([np.argmin(v @ v[k]) for k in range(2000)])
+    ai, aj = np.minimum(anti, np.arange(2000)), np.maximum(anti, np.arange(2000))
+    diag = np.arange(0, n, 7)
+    pi = np.concatenate([pi, diag, ai])
+    pj = np.concatenate([pj, diag, aj])
+    blocks = oracle_api.tqu_pairs(*spectra, nside, 10.0, pi, pj, good=np.arange(n, dtype=np.int32))
+    dT, dP = blocks[len(pj) - 2000 - 1, 0, 0], blocks[len(pj) - 2000 - 1, 1, 1]
+    scale = np.sqrt(np.outer([dT, dP, dP], [dT, dP, dP]))
+    worst = 0.0
+    for ia in range(3):
+        for ib in range(3):
+            r, c = ia * n + pi, ib * n + pj
+            lo, hi = np.minimum(r, c), np.maximum(r, c)
+            idx = torch.from_numpy(hi * (hi + 1) // 2 + lo).cuda()
+            got = out[idx].cpu().numpy()
+            worst = max(worst, (np.abs(got - blocks[:, ia, ib]) / scale[ia, ib]).max())
+    assert worst <= REL_TOL, worst
+    del out
+    torch.cuda.empty_cache()
