@@ -43,6 +43,11 @@ struct cmg_ctx
     cmg::SeriesTable hostT0, hostT20, hostT22;   // host copies of the recurrence tables
     int tquVariant = 0;                          // 0 = automatic choice (see launchTqu)
 
+    static const int kAux = 4;                   // side streams for many small independent launches (batched mode)
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t auxDone[kAux] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t forkEv = nullptr;
+
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false;
     double lastMs = 0.0;
@@ -238,12 +243,13 @@ void fillStaticTable(const cmg_ctx* ctx, const double* att, const double* ate, c
 
 template <int R, bool STATIC, int MINB>
 cmg_status launchTquVariant(cmg_ctx* ctx, const cmg::TquDynamicArgs& dyn, const cmg::TquStaticTable& T, int entryChunk,
-                            const cmg::PartTable& P, dim3 grid, int64_t outStride)
+                            const cmg::PartTable& P, dim3 grid, int64_t outStride, cudaStream_t stream = nullptr)
 {
+    if(!stream) stream = ctx->stream;
     const size_t smem = tquSmemBytes(dyn.lmax, STATIC);
     auto kernel = cmg::tquKernel<R, STATIC, MINB>;
     CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(geometryOf(ctx), dyn, T, entryChunk, P, outStride);
+    kernel<<<grid, cmg::PQ_THREADS, smem, stream>>>(geometryOf(ctx), dyn, T, entryChunk, P, outStride);
     CMG_CUDA(ctx, cudaGetLastError());
     return CMG_OK;
 }
@@ -301,7 +307,7 @@ cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, 
     // 22 = shared-memory table, R=2, 2 CTAs/SM
     const bool canStatic = hostWeights && nBatch == 1 && lmax >= 2 && lmax <= cmg::PQ_STATIC_LMAX;
     int variant = ctx->tquVariant;
-    if(variant == 0 || variant == 900)
+    if(variant == 0 || variant == 900 || variant == 901)
         variant = canStatic ? 142 : 42;
     if(variant >= 100 && !canStatic)
         return fail(ctx, CMG_EINVAL, "static-table kernel needs host weights, one batch element and 2 <= lmax <= PQ_STATIC_LMAX");
@@ -381,6 +387,12 @@ cmg_status cmg_create(cmg_ctx** out, int device)
     ctx->stream = ctx->ownStream;
     if((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if((e = cudaEventCreateWithFlags(&ctx->forkEv, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    for(int k = 0; k < cmg_ctx::kAux; ++k)
+    {
+        if((e = cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+        if((e = cudaEventCreateWithFlags(&ctx->auxDone[k], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    }
 
     // recurrence tables, once per context
     std::vector<double> host(7 * kTabLen, 0.0);
@@ -418,6 +430,12 @@ void cmg_destroy(cmg_ctx* ctx)
     if(ctx->dWeights) cudaFree(ctx->dWeights);
     if(ctx->dScratch) cudaFree(ctx->dScratch);
     if(ctx->dIndex) cudaFree(ctx->dIndex);
+    for(int k = 0; k < cmg_ctx::kAux; ++k)
+    {
+        if(ctx->aux[k]) { cudaStreamSynchronize(ctx->aux[k]); cudaStreamDestroy(ctx->aux[k]); }
+        if(ctx->auxDone[k]) cudaEventDestroy(ctx->auxDone[k]);
+    }
+    if(ctx->forkEv) cudaEventDestroy(ctx->forkEv);
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
     if(ctx->ev1) cudaEventDestroy(ctx->ev1);
     if(ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -846,12 +864,77 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBat
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
     cmg_tqu_layout layout;
     if((s = cmg_tqu_layout_single(ctx, dOut, &layout)) != CMG_OK) return s;
-    // Default: one Clenshaw pass per batch element (blockIdx.z), 0.195 ms per Nside=16 lmax=47 matrix on a B200.
+    // Otherwise (long series, or an explicit variant): one Clenshaw pass per batch element in one launch (blockIdx.z),
+    // 0.195 ms per Nside=16 lmax=47 matrix on a B200.
     // Variant 900 selects the shared-basis kernel (recurrences once per pixel pair and batch chunk, 4 accumulate-FMAs
     // per element and l).  It does 2.5x fewer FP64 operations but is bound by delivering one distinct weight per FMA
     // from shared memory (0.254 ms per matrix measured); the contraction belongs on the FP64 tensor path (DMMA) -- next round.
-    if(ctx->tquVariant != 900 || lmax < 2)
+    if(ctx->tquVariant == 0 && lmax >= 2 && lmax <= cmg::PQ_STATIC_LMAX)
+    {
+        // one static-table launch per element (every DFMA with a uniform-register operand), spread over side streams so
+        // that the small grids of low-Nside matrices overlap each other's heads and tails
+        cmg::PartTable PS;
+        std::memset(&PS, 0, sizeof(PS));
+        PS.n = 1;
+        PS.begin[1] = ctx->npix;
+        const int64_t rowBlocks = (ctx->npix + cmg::PQ_TI - 1) / cmg::PQ_TI, colBlocks = (ctx->npix + cmg::PQ_TJ - 1) / cmg::PQ_TJ;
+        if(colBlocks <= 65535)
+        {
+            const dim3 grid(static_cast<unsigned>(rowBlocks), static_cast<unsigned>(colBlocks), 1);
+            cmg::TquDynamicArgs dyn;
+            dyn.a = ctx->dWeights; dyn.aStride = 0; dyn.tab = tablesOf(ctx); dyn.lmax = lmax;
+            static thread_local cmg::TquStaticTable TB;
+            const int entryChunk = (cmg::PQ_STATIC_STEPS + 1 - lmax) / cmg::PQ_STATIC_CHUNK;
+            KernelTimer timerS(ctx);
+            CMG_CUDA(ctx, cudaEventRecord(ctx->forkEv, ctx->stream));
+            for(int k = 0; k < cmg_ctx::kAux; ++k)
+                CMG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[k], ctx->forkEv, 0));
+            for(int64_t b = 0; b < nBatch; ++b)
+            {
+                const double* wb = a + b * per;
+                fillStaticTable(ctx, wb, wb + (lmax + 1), wb + 2 * (lmax + 1), wb + 3 * (lmax + 1), lmax, TB);
+                for(int st = 0; st < 3; ++st) PS.ptr[0][st] = layout.ptr[0][st] + b * stride;
+                if((s = launchTquVariant<4, true, 2>(ctx, dyn, TB, entryChunk, PS, grid, 0, ctx->aux[b % cmg_ctx::kAux])) != CMG_OK) return s;
+            }
+            for(int k = 0; k < cmg_ctx::kAux; ++k)
+            {
+                CMG_CUDA(ctx, cudaEventRecord(ctx->auxDone[k], ctx->aux[k]));
+                CMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->auxDone[k], 0));
+            }
+            ctx->launches += nBatch;
+            return timerS.finish();
+        }
+    }
+    if((ctx->tquVariant != 900 && ctx->tquVariant != 901) || lmax < 2)
         return launchTqu(ctx, ctx->dWeights, per, lmax, nBatch, &layout, stride, nullptr);
+    if(ctx->tquVariant == 901)
+    {
+        // FP64 tensor path: the batch contraction as DMMA (kernels.cuh, tquBatchedMmaKernel)
+        cmg::PartTable PM;
+        std::memset(&PM, 0, sizeof(PM));
+        PM.n = 1;
+        PM.begin[1] = ctx->npix;
+        for(int st = 0; st < 3; ++st) PM.ptr[0][st] = layout.ptr[0][st];
+        const int64_t tilesM = (ctx->npix + cmg::MB_T - 1) / cmg::MB_T;
+        const size_t smemM = cmg::tquMmaSmemBytes(lmax);
+        if(smemM > 227 * 1024 || tilesM > 65535 || (cmg::mmaKPad(lmax) / 4) * 4 * 32 > cmg::MB_BN * 3 * cmg::MB_SP)
+            return launchTqu(ctx, ctx->dWeights, per, lmax, nBatch, &layout, stride, nullptr);
+        const int64_t nChunksM = (nBatch + cmg::MB_BN - 1) / cmg::MB_BN;
+        const int64_t fragDoubles = nChunksM * (cmg::mmaKPad(lmax) / 4) * 4 * 32;
+        if((s = ensureWeights(ctx, nBatch * per + fragDoubles)) != CMG_OK) return s;
+        CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
+        double* dFrag = ctx->dWeights + nBatch * per;
+        auto mmaKernel = cmg::mmaLd(lmax) == 52 ? cmg::tquBatchedMmaKernel<52> : cmg::tquBatchedMmaKernel<0>;   // lmax 44..47
+        CMG_CUDA(ctx, cudaFuncSetAttribute(mmaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemM)));
+        KernelTimer timerM(ctx);
+        cmg::foldMmaWeightsKernel<<<static_cast<unsigned>(std::min<int64_t>(1024, (fragDoubles + 255) / 256)), 256, 0, ctx->stream>>>(
+            ctx->dWeights, tablesOf(ctx), lmax, static_cast<int>(nBatch), dFrag);
+        mmaKernel<<<dim3(static_cast<unsigned>(tilesM), static_cast<unsigned>(tilesM)), cmg::MB_THREADS, smemM, ctx->stream>>>(
+            geometryOf(ctx), dFrag, tablesOf(ctx), lmax, static_cast<int>(nBatch), PM, stride);
+        CMG_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 2;
+        return timerM.finish();
+    }
     cmg::PartTable P;
     std::memset(&P, 0, sizeof(P));
     P.n = 1;

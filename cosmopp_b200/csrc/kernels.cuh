@@ -818,6 +818,339 @@ tquBatchedKernel(Geometry geo, const double* __restrict__ folded, DeviceTables t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Batched T,Q,U on the FP64 tensor path.  For a batch the sum over l is a contraction: per family s,
+//     Out_s[pair, b] = sum_l Phi_s[pair, l] * W_s[l, b],
+// so it runs as DMMA (mma.sync m8n8k4 f64; measured 37.0 TFLOP/s on B200, the same peak as DFMA, at 1/8 of the
+// instruction count and without the register-bandwidth limit of three-operand DFMAs).
+// CTA = 8 x 8 pixel pairs (64), 256 threads:
+//   A) every thread runs ONE family's forward recurrence for one pair and leaves Phi[s][pair][l] in shared memory
+//      (a basis value is computed once per pair for the whole batch);
+//   B) each warp takes batch chunks of 8 elements: A fragments from shared memory, B fragments (weights,
+//      pre-arranged by foldMmaWeightsKernel in fragment order) straight from L2, 8 m-tiles x 4 families of
+//      accumulators in registers;
+//   C) rotation per (pair, element) with the pair's geometric factors from shared memory, natural entries stored
+//      directly (runs of 8 rows), transposed partners through a warp-private staging tile (runs of 8 columns).
+// ------------------------------------------------------------------------------------------------
+constexpr int MB_T = 8;                        // tile edge: MB_T rows x MB_T columns of pixel pairs
+constexpr int MB_PAIRS = MB_T * MB_T;
+constexpr int MB_THREADS = 256;
+constexpr int MB_WARPS = MB_THREADS / 32;
+constexpr int MB_BN = 8;                       // batch elements per chunk (one n-tile)
+constexpr int MB_SP = MB_PAIRS + 2;            // staging row stride: (element, kind) rows land in distinct banks
+
+__host__ __device__ inline int mmaKPad(int lmax) { return (lmax + 1 + 3) / 4 * 4; }
+__host__ __device__ inline int mmaLd(int lmax)
+{
+    const int kp = mmaKPad(lmax);
+    return kp + ((4 - kp % 16) + 16) % 16;     // row stride = 4 (mod 16) doubles: conflict-free A-fragment loads
+}
+__host__ __device__ inline size_t tquMmaSmemBytes(int lmax)
+{
+    return sizeof(double) * (static_cast<size_t>(4) * MB_PAIRS * mmaLd(lmax)     // Phi
+                             + MB_PAIRS * 8                                       // rotation factors per pair
+                             + 16 * MB_T                                          // frames of rows and columns
+                             + MB_WARPS * MB_BN * 3 * MB_SP                       // staging of transposed partners
+                             + 6 * MB_T                                           // destination pointers
+                             + 4 * (mmaKPad(lmax) + 1));                          // recurrence coefficients (phase A only)
+}
+
+// w[b][4][lmax+1] -> frag[chunk][kk][family][lane] = folded weight of l = 4 kk + lane % 4, element b = 8 chunk + lane / 4
+__global__ void foldMmaWeightsKernel(const double* __restrict__ w, DeviceTables tab, int lmax, int nBatch, double* __restrict__ frag)
+{
+    const int n1 = lmax + 1;
+    const int nkk = mmaKPad(lmax) / 4;
+    const long long total = static_cast<long long>((nBatch + MB_BN - 1) / MB_BN) * nkk * 4 * 32;
+    for(long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const int lane = static_cast<int>(idx & 31);
+        const int fam = static_cast<int>((idx >> 5) & 3);
+        const int kk = static_cast<int>((idx >> 7) % nkk);
+        const int chunk = static_cast<int>((idx >> 7) / nkk);
+        const int l = 4 * kk + (lane & 3);
+        const int b = chunk * MB_BN + (lane >> 2);
+        double v = 0.0;
+        if(b < nBatch && l <= lmax)
+        {
+            const double* wb = w + static_cast<long long>(b) * 4 * n1;
+            if(fam == 0) v = wb[l] * tab.N0[l];
+            else if(l >= 2)
+            {
+                if(fam == 1) v = wb[n1 + l] * tab.N20[l] * 0.61237243569579452455;
+                else if(fam == 2) v = (wb[2 * n1 + l] + wb[3 * n1 + l]) * tab.N22[l] * 0.125;
+                else v = (wb[2 * n1 + l] - wb[3 * n1 + l]) * tab.N22[l] * 0.125;
+            }
+        }
+        frag[idx] = v;
+    }
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// LDC: compile-time row stride of Phi (0 = take it from lmax at run time); a constant stride turns the A-fragment
+// addresses into immediates
+template <int LDC>
+__global__ void __launch_bounds__(MB_THREADS, 1)
+tquBatchedMmaKernel(Geometry geo, const double* __restrict__ frag, DeviceTables tab, int lmax, int nBatch,
+                    const __grid_constant__ PartTable P, long long outStride)
+{
+    extern __shared__ double mbSmem[];
+    const int ld = LDC ? LDC : mmaLd(lmax);
+    const int nkk = mmaKPad(lmax) / 4;
+    double* sPhi = mbSmem;                                         // [4][MB_PAIRS][ld]
+    double* sFac = sPhi + static_cast<size_t>(4) * MB_PAIRS * ld;  // [MB_PAIRS][8]
+    double* sI = sFac + MB_PAIRS * 8;                              // [8][MB_T]
+    double* sJ = sI + 8 * MB_T;                                    // [8][MB_T]
+    double* sStage = sJ + 8 * MB_T;                                // [MB_WARPS][MB_BN][3][MB_SP]
+    double** sColPtr = reinterpret_cast<double**>(sStage + MB_WARPS * MB_BN * 3 * MB_SP);      // [3][MB_T]
+    double** sRowPtr = sColPtr + 3 * MB_T;                         // [3][MB_T]
+    double* sTab = reinterpret_cast<double*>(sRowPtr + 3 * MB_T);  // [4][kp + 1]: g0, g20, g22, c22
+
+    const long long npix = geo.npix;
+    const long long rowBlock = static_cast<long long>(blockIdx.x) * MB_T;
+    const long long c0 = static_cast<long long>(blockIdx.y) * MB_T;
+    const long long c1 = min(c0 + static_cast<long long>(MB_T), npix);
+    if(rowBlock > c1 - 1)
+        return;
+    const int tid = threadIdx.x;
+    const int tabLd = 4 * nkk + 1;
+    for(int k = tid; k < 4 * tabLd; k += MB_THREADS)
+    {
+        const int which = k / tabLd, l = k - which * tabLd;
+        const double* src = which == 0 ? tab.g0 : (which == 1 ? tab.g20 : (which == 2 ? tab.g22 : tab.c22));
+        sTab[k] = src[l];
+    }
+
+    if(tid < 2 * MB_T)
+    {
+        const bool isRow = tid < MB_T;
+        const int loc = isRow ? tid : tid - MB_T;
+        const long long pix = min(isRow ? rowBlock + loc : c0 + loc, npix - 1);
+        double* dst = isRow ? sI : sJ;
+        dst[0 * MB_T + loc] = geo.nx[pix];
+        dst[1 * MB_T + loc] = geo.ny[pix];
+        dst[2 * MB_T + loc] = geo.nz[pix];
+        dst[3 * MB_T + loc] = geo.tx[pix];
+        dst[4 * MB_T + loc] = geo.ty[pix];
+        dst[5 * MB_T + loc] = geo.tz[pix];
+        dst[6 * MB_T + loc] = geo.px[pix];
+        dst[7 * MB_T + loc] = geo.py[pix];
+    }
+    else if(tid < 2 * MB_T + 6 * MB_T)
+    {
+        const int idx = tid - 2 * MB_T;
+        if(idx < 3 * MB_T)
+        {
+            const int strip = idx / MB_T;
+            const long long jcol = min(c0 + (idx - strip * MB_T), npix - 1);
+            sColPtr[idx] = partEntry(P, 0, strip, npix, jcol, 0);
+        }
+        else
+        {
+            const int q = idx - 3 * MB_T;
+            const int t = q / MB_T;
+            const long long ir = min(rowBlock + (q - t * MB_T), npix - 1);
+            double* dst;
+            if(t == 0) dst = partEntry(P, 0, 1, npix, ir, c0);
+            else if(t == 1) dst = partEntry(P, 0, 2, npix, ir, c0);
+            else dst = partEntry(P, 0, 2, npix, ir, npix + c0);
+            sRowPtr[q] = dst;
+        }
+    }
+    __syncthreads();
+
+    // ---- A) basis values and rotation factors.  pair p: row il = p % MB_T, column jl = p / MB_T
+    {
+        const int p = tid & (MB_PAIRS - 1);
+        const int fam = tid >> 6;
+        const int il = p % MB_T, jl = p / MB_T;
+        const double nix = sI[0 * MB_T + il], niy = sI[1 * MB_T + il], niz = sI[2 * MB_T + il];
+        const double njx = sJ[0 * MB_T + jl], njy = sJ[1 * MB_T + jl], njz = sJ[2 * MB_T + jl];
+        double dot = __dadd_rn(__dadd_rn(__dmul_rn(nix, njx), __dmul_rn(niy, njy)), __dmul_rn(niz, njz));
+        dot = fmin(1.0, fmax(-1.0, dot));
+        const double x2 = dot + dot;
+        double* phi = sPhi + (static_cast<size_t>(fam) * MB_PAIRS + p) * ld;
+        const int kp = 4 * nkk;
+        if(fam == 0)
+        {
+            double q0 = 1.0, q1 = x2;
+            phi[0] = q0;
+            if(kp > 1) phi[1] = q1;
+            for(int l = 1; l + 1 < kp; ++l)
+            {
+                const double qn = fma(x2, q1, -sTab[l] * q0);
+                q0 = q1; q1 = qn;
+                phi[l + 1] = (l + 1 <= lmax) ? qn : 0.0;
+            }
+        }
+        else
+        {
+            const double* g = sTab + (fam == 1 ? 1 : 2) * tabLd;
+            const double* cc = sTab + 3 * tabLd;
+            const double sgn = fam == 2 ? 1.0 : (fam == 3 ? -1.0 : 0.0);
+            double q0 = 0.0, q1 = 1.0;
+            phi[0] = 0.0;
+            if(kp > 1) phi[1] = 0.0;
+            if(kp > 2) phi[2] = lmax >= 2 ? 1.0 : 0.0;
+            for(int l = 2; l + 1 < kp; ++l)
+            {
+                const double qn = fma(x2 - sgn * cc[l], q1, -g[l] * q0);
+                q0 = q1; q1 = qn;
+                phi[l + 1] = (l + 1 <= lmax) ? qn : 0.0;
+            }
+        }
+        if(fam == 0)
+        {
+            const double tix = sI[3 * MB_T + il], tiy = sI[4 * MB_T + il], tiz = sI[5 * MB_T + il];
+            const double pix_ = sI[6 * MB_T + il], piy = sI[7 * MB_T + il];
+            const double tjx = sJ[3 * MB_T + jl], tjy = sJ[4 * MB_T + jl], tjz = sJ[5 * MB_T + jl];
+            const double pjx = sJ[6 * MB_T + jl], pjy = sJ[7 * MB_T + jl];
+            const double ai = fma(njx, tix, fma(njy, tiy, njz * tiz));
+            const double bi = fma(njx, pix_, njy * piy);
+            const double aj = fma(nix, tjx, fma(niy, tjy, niz * tjz));
+            const double bj = fma(nix, pjx, niy * pjy);
+            const double pp = fma(tix, tjx, fma(tiy, tjy, tiz * tjz));
+            const double qq = fma(pix_, pjx, piy * pjy);
+            const double rr = fma(pix_, tjx, piy * tjy);
+            const double tq = fma(tix, pjx, tiy * pjy);
+            const double su = pp + qq, du = rr - tq, sv = pp - qq, dv = tq + rr;
+            double* fac = sFac + p * 8;
+            fac[0] = fma(aj, aj, -bj * bj);     // fTQ
+            fac[1] = 2.0 * aj * bj;             // fTU
+            fac[2] = fma(ai, ai, -bi * bi);     // fQT
+            fac[3] = 2.0 * ai * bi;             // fUT
+            fac[4] = fma(su, su, -du * du);     // reU
+            fac[5] = 2.0 * su * du;             // imU
+            fac[6] = fma(sv, sv, -dv * dv);     // reV
+            fac[7] = 2.0 * sv * dv;             // imV
+        }
+    }
+    __syncthreads();
+
+    // ---- B) + C) per warp and batch chunk
+    const int lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;           // fragment row (pair within the m-tile) and column
+    const int nChunks = (nBatch + MB_BN - 1) / MB_BN;
+    double* stage = sStage + warp * (MB_BN * 3 * MB_SP);
+    const int iOff = static_cast<int>(c0 - rowBlock);   // j - rowBlock = iOff + jl
+
+    for(int chunk = warp; chunk < nChunks; chunk += MB_WARPS)
+    {
+        double acc[MB_T][4][2];
+#pragma unroll
+        for(int t = 0; t < MB_T; ++t)
+#pragma unroll
+            for(int s = 0; s < 4; ++s)
+                acc[t][s][0] = acc[t][s][1] = 0.0;
+        const double* fb = frag + (static_cast<long long>(chunk) * nkk * 4) * 32 + lane;
+        // B fragments of the whole chunk (nkk x 4 families x 32 lanes, <= the staging tile in size) are copied from L2
+        // into this warp's staging region first, all loads in flight at once, so the L2 latency is paid once per chunk
+        // instead of once per k-step; the region is reused for the transposed partners after the MMA loop.
+        {
+            const double* fb = frag + (static_cast<long long>(chunk) * nkk * 4) * 32 + lane;
+            const int nFrag = nkk * 4;
+            for(int q0 = 0; q0 < nFrag; q0 += 12)
+            {
+                double v[12];
+#pragma unroll
+                for(int u = 0; u < 12; ++u)
+                    v[u] = (q0 + u < nFrag) ? __ldg(fb + (q0 + u) * 32) : 0.0;
+#pragma unroll
+                for(int u = 0; u < 12; ++u)
+                    if(q0 + u < nFrag)
+                        stage[(q0 + u) * 32 + lane] = v[u];
+            }
+        }
+        __syncwarp();
+        const double* paBase = sPhi + static_cast<size_t>(fr) * ld + fc;
+#pragma unroll 1
+        for(int kk = 0; kk < nkk; ++kk)
+        {
+#pragma unroll
+            for(int s = 0; s < 4; ++s)
+            {
+                const double bfrag = stage[(kk * 4 + s) * 32 + lane];
+                const double* pa = paBase + static_cast<size_t>(s) * MB_PAIRS * ld + 4 * kk;
+#pragma unroll
+                for(int t = 0; t < MB_T; ++t)
+                    dmma884(acc[t][s][0], acc[t][s][1], pa[t * MB_T * ld], bfrag);
+            }
+        }
+        __syncwarp();                                       // every lane is done reading the fragments
+
+        // rotation and stores: m-tile t is column jl = t, this thread's pair is row il = fr, elements 2 fc, 2 fc + 1
+        const int b0 = chunk * MB_BN + 2 * fc;
+        const long long i = rowBlock + fr;
+#pragma unroll
+        for(int t = 0; t < MB_T; ++t)
+        {
+            const int p = t * MB_T + fr;
+            const double4 f0 = *reinterpret_cast<const double4*>(sFac + p * 8);
+            const double4 f1 = *reinterpret_cast<const double4*>(sFac + p * 8 + 4);
+            const bool valid = fr <= iOff + t && c0 + t < c1;
+            double* colT = sColPtr[0 * MB_T + t] + i;
+            double* colQ = sColPtr[1 * MB_T + t] + i;
+            double* colU = sColPtr[2 * MB_T + t] + i;
+#pragma unroll
+            for(int e = 0; e < 2; ++e)
+            {
+                const double xt = -acc[t][1][e];
+                const double aRe = acc[t][2][e] * f1.x, aIm = acc[t][2][e] * f1.y;
+                const double bRe = acc[t][3][e] * f1.z, bIm = acc[t][3][e] * f1.w;
+                if(valid && b0 + e < nBatch)
+                {
+                    const long long boff = static_cast<long long>(b0 + e) * outStride;
+                    __stcs(colT + boff, acc[t][0][e]);
+                    __stcs(colQ + boff, xt * f0.x);
+                    __stcs(colQ + boff + npix, aRe + bRe);
+                    __stcs(colU + boff, xt * f0.y);
+                    __stcs(colU + boff + npix, bIm - aIm);
+                    __stcs(colU + boff + 2 * npix, aRe - bRe);
+                }
+                double* st = stage + ((2 * fc + e) * 3) * MB_SP + p;
+                st[0] = xt * f0.z;                       // Q_i T_j
+                st[MB_SP] = xt * f0.w;                   // U_i T_j
+                st[2 * MB_SP] = aIm + bIm;               // U_i Q_j
+            }
+        }
+        __syncwarp();
+        // transposed partners: lanes along j (8 consecutive rows of column N+i / 2N+i), 4 rows i per store instruction;
+        // lane -> column jl = lane & 7 and rows il = (lane >> 3) + 4 h, running pointers step from element to element
+        {
+            const int jl = lane & (MB_T - 1);
+            const bool colOk = c0 + jl < c1;
+            const int nLive = min(MB_BN, nBatch - chunk * MB_BN);
+#pragma unroll
+            for(int h = 0; h < 2; ++h)
+            {
+                const int il = (lane >> 3) + 4 * h;
+                if(colOk && il < iOff + jl)
+                {
+                    const long long first = static_cast<long long>(chunk) * MB_BN * outStride + jl;
+                    double* d0 = sRowPtr[0 * MB_T + il] + first;
+                    double* d1 = sRowPtr[1 * MB_T + il] + first;
+                    double* d2 = sRowPtr[2 * MB_T + il] + first;
+                    const double* sv = stage + jl * MB_T + il;
+                    for(int bl = 0; bl < nLive; ++bl)
+                    {
+                        __stcs(d0, sv[0]);
+                        __stcs(d1, sv[MB_SP]);
+                        __stcs(d2, sv[2 * MB_SP]);
+                        sv += 3 * MB_SP;
+                        d0 += outStride;
+                        d1 += outStride;
+                        d2 += outStride;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CMatrix::maskMatrix gather (reference source/c_matrix.cpp:182-201): out(a,b) = in(good[a], good[b])
 // ------------------------------------------------------------------------------------------------
 __global__ void maskGatherKernel(const double* __restrict__ in, const int* __restrict__ good, long long nGood,

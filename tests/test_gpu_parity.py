@@ -297,7 +297,7 @@ def test_batched_generation_matches_single_calls(gpu_ctx, oracle_api):
     stride = capi.packed_size(3 * n)
     wants = [oracle_api.tqu_matrix(*synthetic_cl(lmax, seed=200 + b, pol=True), nside, 10.0, good=good) for b in range(nb)]
     try:
-        for variant in (0, 900):          # per-element Clenshaw (default) and the shared-basis kernel
+        for variant in (0, 900, 901):     # per-element Clenshaw (default), shared-basis kernel, DMMA kernel
             gpu_ctx.set_kernel_variant(variant)
             outp = torch.full((nb * stride,), float("nan"), dtype=torch.float64, device="cuda")
             gpu_ctx.tqu_batched(ab, outp, stride)

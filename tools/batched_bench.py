@@ -14,7 +14,7 @@ a = np.stack([np.stack(capi.tqu_weights(*synthetic_cl(lmax, seed=12345 + b, pol=
 stride = capi.packed_size(3 * n)
 out = torch.empty(B * stride, dtype=torch.float64, device="cuda")
 peak = ctx.measure_fp64_peak()
-for v in (0, 900):
+for v in ([int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (0, 42, 901)):
     ctx.set_kernel_variant(v)
     ctx.tqu_batched(a, out, stride); torch.cuda.synchronize()
     ts = []
