@@ -200,11 +200,11 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
     }
     KernelTimer timer(ctx);
     if(useStatic)
-        cmg::legendreSeriesKernel<true><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, T, entryChunk,
+        cmg::legendreSeriesKernel<true><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entryChunk,
                                                                                  colBegin, colEnd, dOut, outStride);
     else
         cmg::legendreSeriesKernel<false><<<grid, cmg::TT_ROWS, sizeof(double2) * (lmax + 1), ctx->stream>>>(
-            geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, T, entryChunk, colBegin, colEnd, dOut, outStride);
+            T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entryChunk, colBegin, colEnd, dOut, outStride);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return timer.finish();
@@ -249,7 +249,7 @@ cmg_status launchTquVariant(cmg_ctx* ctx, const cmg::TquDynamicArgs& dyn, const 
     const size_t smem = tquSmemBytes(dyn.lmax, STATIC);
     auto kernel = cmg::tquKernel<R, STATIC, MINB>;
     CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kernel<<<grid, cmg::PQ_THREADS, smem, stream>>>(geometryOf(ctx), dyn, T, entryChunk, P, outStride);
+    kernel<<<grid, cmg::PQ_THREADS, smem, stream>>>(T, geometryOf(ctx), dyn, entryChunk, P, outStride);
     CMG_CUDA(ctx, cudaGetLastError());
     return CMG_OK;
 }

@@ -121,9 +121,8 @@ __device__ __forceinline__ void ttClenshawStatic(double (&x2)[R], double (&b1)[R
 
 template <bool STATIC>
 __global__ void __launch_bounds__(TT_ROWS)
-legendreSeriesKernel(Geometry geo, const double* __restrict__ a, long long aStride,
-                     const double* __restrict__ N0, const double* __restrict__ g0, int lmax,
-                     const __grid_constant__ TtStaticTable T, int entryChunk,
+legendreSeriesKernel(const __grid_constant__ TtStaticTable T, Geometry geo, const double* __restrict__ a, long long aStride,
+                     const double* __restrict__ N0, const double* __restrict__ g0, int lmax, int entryChunk,
                      long long colBegin, long long colEnd, double* __restrict__ out, long long outStride)
 {
     extern __shared__ double2 ttTab[];      // [lmax + 1]  {a_k N_k, -g_{k+1}}  (dynamic variant only)
@@ -337,8 +336,8 @@ constexpr int PQ_SMEM_DOUBLES = 8 * PQ_TI + 8 * PQ_TJ + 3 * PQ_TI * PQ_STAGE_LD 
 
 template <int R, bool STATIC, int MINB>
 __global__ void __launch_bounds__(PQ_THREADS, MINB)
-tquKernel(Geometry geo, TquDynamicArgs dyn, const __grid_constant__ TquStaticTable T, int entryChunk,
-          const __grid_constant__ PartTable P, long long outStride)
+tquKernel(const __grid_constant__ TquStaticTable T, Geometry geo, TquDynamicArgs dyn, int entryChunk,
+          const __grid_constant__ PartTable P, long long outStride)      // T first: 128-byte aligned in the constant bank
 {
     extern __shared__ double4 pqSmem[];
     const int tabSlots = STATIC ? 0 : 2 * (dyn.lmax + 1);

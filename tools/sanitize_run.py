@@ -1,0 +1,42 @@
+"""Small end-to-end run of every kernel for compute-sanitizer (memcheck / racecheck):
+    compute-sanitizer --tool memcheck python tools/sanitize_run.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import cosmopp_b200 as cb
+from cosmopp_b200 import capi, partition
+from cosmopp_b200.synthetic import synthetic_cl
+
+ctx = cb.Context(0); ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+nside, lmax = 4, 11
+good = np.array([p for p in range(192) if p % 7 != 3], dtype=np.int32)      # 165 pixels: ragged tiles
+ctx.set_pixels(nside, good); n = ctx.npix
+f = capi.window_beam(lmax, 10.0)
+a = capi.tt_weights(synthetic_cl(lmax), f)
+out = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
+for v in (0, 1):
+    ctx.set_kernel_variant(v); ctx.legendre_series(a, out)
+ctx.set_kernel_variant(0)
+ctx.legendre_series_batched(np.stack([a, 2 * a, 3 * a]), torch.empty(3 * capi.packed_size(n), dtype=torch.float64, device="cuda"), capi.packed_size(n))
+w = capi.tqu_weights(*synthetic_cl(lmax, pol=True), f, f)
+outp = torch.empty(capi.packed_size(3 * n), dtype=torch.float64, device="cuda")
+for v in (22, 42, 81, 114, 122, 123, 124, 142):
+    ctx.set_kernel_variant(v); ctx.tqu(*w, ctx.tqu_layout_single(outp))
+ab = np.stack([np.stack(w)] * 5)
+outb = torch.empty(5 * capi.packed_size(3 * n), dtype=torch.float64, device="cuda")
+for v in (0, 42, 900, 901):
+    ctx.set_kernel_variant(v); ctx.tqu_batched(ab, outb, capi.packed_size(3 * n))
+ctx.set_kernel_variant(0)
+b = partition.column_partition(n, 3, align=32)
+for r in range(3):
+    plan = partition.tqu_rank_plan(n, b, r)
+    strips = [torch.empty(s, dtype=torch.float64, device="cuda") for s in plan["strips"]]
+    outbox = {o: [torch.empty(nc * ld, dtype=torch.float64, device="cuda") for _ in range(3)] for o, nc, ld, _ in plan["outbox"]}
+    ctx.tqu(*w, capi.make_tqu_layout(b, r, [t.data_ptr() for t in strips], {k: [t.data_ptr() for t in v] for k, v in outbox.items()}))
+    for o, nc, ld, row0 in plan["outbox"]:
+        for t in range(3):
+            ctx.tqu_scatter_block(outbox[o][t], b[o], nc, ld, row0, t, outp)
+d_out = torch.empty(capi.packed_size(20), dtype=torch.float64, device="cuda")
+ctx.mask_matrix(out, n, np.arange(0, 160, 8), d_out)
+torch.cuda.synchronize()
+print("sanitize_run: all kernels launched, no error reported by the runtime")
