@@ -90,6 +90,7 @@ _SIGNATURES = {
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
     "cmg_legendre_series_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _i64, _vp, _i64]),
     "cmg_tqu_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp, _i64]),
+    "cmg_sum_unpack": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "cmg_measure_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -280,6 +281,9 @@ class Context:
 
     def tqu_scatter_block(self, d_block, col0, n_cols, ld, row0, kind, d_full):
         self._check(self._L.cmg_tqu_scatter_block(self._h, _p(d_block), col0, n_cols, ld, row0, kind, _p(d_full)))
+
+    def sum_unpack(self, d_c, d_f, d_n, n, d_full):
+        self._check(self._L.cmg_sum_unpack(self._h, _p(d_c), _p(d_f), _p(d_n), int(n), _p(d_full)))
 
     def tqu_batched(self, a, d_out, stride):
         a = _f64(a)         # [B][4][lmax+1]

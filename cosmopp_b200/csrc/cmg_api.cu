@@ -1001,6 +1001,18 @@ cmg_status cmg_tqu_scatter_block(cmg_ctx* ctx, const double* dBlock, int64_t col
     return CMG_OK;
 }
 
+cmg_status cmg_sum_unpack(cmg_ctx* ctx, const double* dC, const double* dF, const double* dN, int64_t n, double* dFull)
+{
+    if(!ctx || !dC || !dFull || n < 1) return CMG_EINVAL;
+    if((n + 31) / 32 > 65535) return fail(ctx, CMG_EUNSUPPORTED, "matrix too large for one launch");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned blocks = static_cast<unsigned>((n + 31) / 32);
+    cmg::sumUnpackKernel<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(dC, dF, dN, n, dFull);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
+}
+
 // ---------------------------------------------------------------- measurement
 
 cmg_status cmg_measure_fp64_peak(cmg_ctx* ctx, double* tflops)

@@ -1188,6 +1188,42 @@ __global__ void scatterBlockKernel(const double* __restrict__ block, long long n
 }
 
 // ------------------------------------------------------------------------------------------------
+// Consumer side (reference source/likelihood.cpp:100-110): C + F + N of three packed matrices (any of the last two may
+// be absent) written as a full symmetric column-major n x n matrix, ready for a dense Cholesky.  One pass over HBM
+// instead of three matrix reads on the host.  Tile 32 x 32 through shared memory so both triangles are written coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumUnpackKernel(const double* __restrict__ c, const double* __restrict__ f, const double* __restrict__ nz,
+                                                       long long n, double* __restrict__ full)
+{
+    __shared__ double tile[32][33];
+    const long long bi = blockIdx.x, bj = blockIdx.y;          // row block, column block; upper triangle blocks only
+    if(bi > bj)
+        return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
+    for(int r = ty; r < 32; r += 8)
+    {
+        const long long j = bj * 32 + r, i = bi * 32 + tx;     // column j, row i: lanes along i (contiguous in the packed column)
+        double v = 0.0;
+        if(j < n && i <= j)
+        {
+            const long long k = packedOffset(j) + i;
+            v = c[k];
+            if(f) v += f[k];
+            if(nz) v += nz[k];
+            full[j * n + i] = v;                               // upper triangle entry (i, j)
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for(int r = ty; r < 32; r += 8)
+    {
+        const long long i = bi * 32 + r, j = bj * 32 + tx;     // write (j, i) of the lower triangle: column i, rows j, lanes along j
+        if(j < n && i < j)
+            full[i * n + j] = tile[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 peak: independent DFMA chains, no memory traffic.  8 chains x 4096 iterations per thread.
 // ------------------------------------------------------------------------------------------------
 constexpr int PEAK_CHAINS = 8;

@@ -197,6 +197,13 @@ cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, 
 cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t n_batch,
                            double* d_out, int64_t stride);
 
+/* ---------------------------------------------------------------- towards the consumer ------- */
+
+/* First step of the likelihood that consumes these matrices (reference source/likelihood.cpp:100-110): the sum of up to
+ * three packed matrices of dimension n (d_f and/or d_n may be NULL) written as a FULL symmetric column-major n x n matrix
+ * on the device, ready for a dense Cholesky factorisation, in one pass over HBM. */
+cmg_status cmg_sum_unpack(cmg_ctx* ctx, const double* d_c, const double* d_f, const double* d_n, int64_t n, double* d_full);
+
 /* ---------------------------------------------------------------- measurement --------------- */
 
 /* dependent-free DFMA microbenchmark: achieved FP64 TFLOP/s on this GPU (the roofline denominator) */

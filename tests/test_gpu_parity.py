@@ -508,3 +508,44 @@ def test_full_size_nside64_polarized_sampled(gpu_ctx, oracle_api):
     assert worst <= REL_TOL, worst
     del out
     torch.cuda.empty_cache()
+
+
+def test_device_resident_likelihood_consumer(gpu_ctx, oracle_api):
+    """C + F + N -> Cholesky -> chi2, logDet as reference source/likelihood.cpp:100-180, everything staying on the GPU,
+    against a numpy restatement on the oracle's matrices."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    from cosmopp_b200.likelihood import Likelihood, DET_OFFSET
+    nside, lmax = 8, 20
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside))
+    cl = synthetic_cl(4 * nside)
+    gpu_ctx.set_pixels(nside, good)
+    n = gpu_ctx.npix
+    f_l = capi.window_beam(4 * nside, 10.0)
+    d_c = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
+    d_f = torch.empty_like(d_c)
+    gpu_ctx.legendre_series(capi.tt_weights(cl[:lmax + 1], f_l[:lmax + 1]), d_c)
+    gpu_ctx.legendre_series(capi.fiducial_weights(cl, f_l, nside, lmax), d_f)
+    noise = oracle_api.mask_matrix(oracle_api.noise_matrix(nside, 0.5), good)
+    d_n = torch.from_numpy(noise).cuda()
+    rs = np.random.RandomState(4)
+    fg = rs.standard_normal(n)
+    maps = rs.standard_normal((3, n)) * 5.0
+    like = Likelihood(gpu_ctx, d_c, d_f, d_n, n, foreground=fg)
+    got_like, got_chi2, got_logdet = like.calculate(maps)
+
+    C = oracle_api.unpack_symmetric(oracle_api.cl_to_cmatrix(cl[:lmax + 1], nside, 10.0, good=good)
+                                    + oracle_api.fiducial_matrix(cl, nside, lmax, 10.0, good=good) + noise, n)
+    Cinv = np.linalg.inv(C)
+    sign, logdet = np.linalg.slogdet(C)
+    assert sign > 0
+    fCf = fg @ Cinv @ fg
+    want_logdet = logdet - DET_OFFSET + np.log(fCf / n)
+    want_chi2 = np.array([t @ Cinv @ t - (t @ Cinv @ fg) ** 2 / fCf for t in maps])
+    assert abs(got_logdet - want_logdet) <= 1e-9 * abs(want_logdet)
+    assert np.abs(got_chi2 - want_chi2).max() <= 1e-8 * np.abs(want_chi2).max()
+    one = like.calculate(maps[1])
+    assert abs(one[1] - want_chi2[1]) <= 1e-8 * abs(want_chi2[1]) and abs(one[0] - (want_chi2[1] + want_logdet)) <= 1e-8 * abs(one[0])
+    # without the template
+    plain = Likelihood(gpu_ctx, d_c, d_f, d_n, n)
+    assert abs(plain.calculate(maps[0])[1] - maps[0] @ Cinv @ maps[0]) <= 1e-8 * abs(maps[0] @ Cinv @ maps[0])
