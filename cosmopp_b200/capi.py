@@ -86,6 +86,7 @@ _SIGNATURES = {
     "cmg_tqu_layout_single": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(TquLayout)]),
     "cmg_tqu": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(TquLayout)]),
     "cmg_tqu_scatter_block": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_int, _vp]),
+    "cmg_tqu_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(TquLayout)]),
     "cmg_tqu_weights": (ctypes.c_int, [_vp] * 6 + [ctypes.c_int] + [_vp] * 4),
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
     "cmg_legendre_series_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _i64, _vp, _i64]),
@@ -278,6 +279,9 @@ class Context:
     def tqu(self, a_tt, a_te, a_ee, a_bb, layout):
         a_tt, a_te, a_ee, a_bb = map(_f64, (a_tt, a_te, a_ee, a_bb))
         self._check(self._L.cmg_tqu(self._h, _p(a_tt), _p(a_te), _p(a_ee), _p(a_bb), len(a_tt) - 1, ctypes.byref(layout)))
+
+    def tqu_dev(self, d_a, lmax, layout):
+        self._check(self._L.cmg_tqu_dev(self._h, _p(d_a), int(lmax), ctypes.byref(layout)))
 
     def tqu_scatter_block(self, d_block, col0, n_cols, ld, row0, kind, d_full):
         self._check(self._L.cmg_tqu_scatter_block(self._h, _p(d_block), col0, n_cols, ld, row0, kind, _p(d_full)))

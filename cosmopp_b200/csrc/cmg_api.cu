@@ -853,6 +853,15 @@ cmg_status cmg_tqu(cmg_ctx* ctx, const double* att, const double* ate, const dou
     return launchTqu(ctx, ctx->dWeights, 0, lmax, 1, layout, 0, hostW);
 }
 
+cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* dA, int lmax, const cmg_tqu_layout* layout)
+{
+    const cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!dA) return fail(ctx, CMG_EINVAL, "null weights");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launchTqu(ctx, dA, 0, lmax, 1, layout, 0, nullptr);
+}
+
 cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch, double* dOut, int64_t stride)
 {
     cmg_status s = checkReady(ctx, lmax);

@@ -177,6 +177,10 @@ cmg_status cmg_tqu(cmg_ctx* ctx, const double* a_tt, const double* a_te, const d
  * the unsharded matrix must be assembled (after the blocks were moved with NCCL or a copy). */
 cmg_status cmg_tqu_scatter_block(cmg_ctx* ctx, const double* d_block, int64_t col0, int64_t n_cols, int64_t ld, int64_t row0,
                                  int kind, double* d_full_packed);
+/* same with the 4 x (lmax+1) weights (tt, te, ee, bb, each lmax+1 doubles, contiguous) already on the device: nothing is
+ * read from the host, so the call can be captured in a CUDA graph and replayed after the weights were updated in place
+ * (shared-memory coefficient table kernel; the parameter-block kernel needs the weights on the host at launch) */
+cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* d_a, int lmax, const cmg_tqu_layout* layout);
 /* weights from spectra and the temperature / polarization window*beam factors */
 cmg_status cmg_tqu_weights(const double* ctt, const double* cte, const double* cee, const double* cbb,
                            const double* fT, const double* fP, int lmax,

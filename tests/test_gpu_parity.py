@@ -549,3 +549,47 @@ def test_device_resident_likelihood_consumer(gpu_ctx, oracle_api):
     # without the template
     plain = Likelihood(gpu_ctx, d_c, d_f, d_n, n)
     assert abs(plain.calculate(maps[0])[1] - maps[0] @ Cinv @ maps[0]) <= 1e-8 * abs(maps[0] @ Cinv @ maps[0])
+
+
+def test_device_resident_weights_and_cuda_graph_replay(gpu_ctx, oracle_api):
+    """MCMC-style use: weights live on the device, the generate call is captured once in a CUDA graph and replayed
+    after the weights were overwritten in place; TT and T,Q,U."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside, lmax = 4, 12
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside))
+    gpu_ctx.set_pixels(nside, good)
+    n = gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    sets = [synthetic_cl(lmax, seed=s, pol=True) for s in (31, 32)]
+    w = [np.concatenate(capi.tqu_weights(*sp, f, f)) for sp in sets]
+    d_w = torch.from_numpy(w[0]).cuda()
+    d_wtt = torch.from_numpy(capi.tt_weights(sets[0][0], f)).cuda()
+    out = torch.empty(capi.packed_size(3 * n), dtype=torch.float64, device="cuda")
+    out_tt = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
+    lay = gpu_ctx.tqu_layout_single(out)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    gpu_ctx.set_stream(side.cuda_stream)
+    try:
+        with torch.cuda.stream(side):
+            gpu_ctx.tqu_dev(d_w, lmax, lay)                    # warm-up outside capture (function attributes, lazy init)
+            gpu_ctx.legendre_series_dev(d_wtt, lmax, out_tt)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                gpu_ctx.tqu_dev(d_w, lmax, lay)
+                gpu_ctx.legendre_series_dev(d_wtt, lmax, out_tt)
+        for k in (1, 0, 1):
+            d_w.copy_(torch.from_numpy(w[k]))
+            d_wtt.copy_(torch.from_numpy(capi.tt_weights(sets[k][0], f)))
+            torch.cuda.synchronize()
+            out.fill_(float("nan"))
+            out_tt.fill_(float("nan"))
+            g.replay()
+            torch.cuda.synchronize()
+            _assert_tqu_close(out.cpu().numpy(), oracle_api.tqu_matrix(*sets[k], nside, 10.0, good=good), n)
+            want = oracle_api.cl_to_cmatrix(sets[k][0], nside, 10.0, good=good)
+            assert np.abs(out_tt.cpu().numpy() - want).max() <= REL_TOL * want[0]
+    finally:
+        gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
