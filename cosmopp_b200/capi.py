@@ -91,6 +91,9 @@ _SIGNATURES = {
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
     "cmg_legendre_series_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _i64, _vp, _i64]),
     "cmg_tqu_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp, _i64]),
+    "cmg_slab_doubles": (_i64, [_i64]),
+    "cmg_tqu_batched_slab": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp]),
+    "cmg_slab_unpack": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _i64]),
     "cmg_sum_unpack": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "cmg_measure_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
@@ -134,6 +137,13 @@ def _p(a):
     if isinstance(a, int):
         return _vp(a)
     return _vp(a.data_ptr())        # torch tensor
+
+
+SLAB = 16            # CMG_SLAB: batch elements interleaved in one slab of the DMMA batched path
+
+
+def slab_doubles(dim):
+    return int(library().cmg_slab_doubles(dim))
 
 
 class Context:
@@ -292,6 +302,14 @@ class Context:
     def tqu_batched(self, a, d_out, stride):
         a = _f64(a)         # [B][4][lmax+1]
         self._check(self._L.cmg_tqu_batched(self._h, _p(a), a.shape[2] - 1, a.shape[0], _p(d_out), stride))
+
+    def tqu_batched_slab(self, a, d_slabs):
+        """DMMA path: ceil(B / 16) slabs of 16 interleaved packed matrices (include/cmg.h)."""
+        a = _f64(a)         # [B][4][lmax+1]
+        self._check(self._L.cmg_tqu_batched_slab(self._h, _p(a), a.shape[2] - 1, a.shape[0], _p(d_slabs)))
+
+    def slab_unpack(self, d_slab, dim, d_out, out_stride=0, n_live=SLAB, only_b=-1):
+        self._check(self._L.cmg_slab_unpack(self._h, _p(d_slab), dim, n_live, only_b, _p(d_out), out_stride))
 
     def cl_to_cmatrix_pol(self, ctt, cte, cee, cbb, fwhm, out_host, pixwinT=None, pixwinP=None):
         ctt, cte, cee, cbb = map(_f64, (ctt, cte, cee, cbb))

@@ -307,7 +307,7 @@ cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, 
     // 22 = shared-memory table, R=2, 2 CTAs/SM
     const bool canStatic = hostWeights && nBatch == 1 && lmax >= 2 && lmax <= cmg::PQ_STATIC_LMAX;
     int variant = ctx->tquVariant;
-    if(variant == 0 || variant == 900 || variant == 901)
+    if(variant == 0 || variant >= 900)
         variant = canStatic ? 142 : 42;
     if(variant >= 100 && !canStatic)
         return fail(ctx, CMG_EINVAL, "static-table kernel needs host weights, one batch element and 2 <= lmax <= PQ_STATIC_LMAX");
@@ -968,6 +968,57 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBat
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     return timer.finish();
+}
+
+int64_t cmg_slab_doubles(int64_t dim) { return CMG_SLAB * cmg_packed_size(dim); }
+
+cmg_status cmg_tqu_batched_slab(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch, double* dSlabs)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!a || !dSlabs || nBatch < 1) return fail(ctx, CMG_EINVAL, "bad batch arguments");
+    if(lmax < 2 || lmax > CMG_SLAB_LMAX)
+        return fail(ctx, CMG_EUNSUPPORTED, "slab generation keeps the basis fragments in registers: 2 <= lmax <= 63");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t per = 4 * (lmax + 1);
+    const int nkk = lmax <= 31 ? 8 : (lmax <= 47 ? 12 : 16);
+    const int64_t tiles = (ctx->npix + cmg::M2_T - 1) / cmg::M2_T;
+    const int64_t groups = (tiles + cmg::M2_GROUP - 1) / cmg::M2_GROUP;
+    const int64_t nChunks = (nBatch + CMG_SLAB - 1) / CMG_SLAB;
+    const int64_t fragDoubles = 2 * nChunks * nkk * 128;
+    if(groups > 65535 || tiles * cmg::M2_GROUP > 2147483647LL)
+        return fail(ctx, CMG_EUNSUPPORTED, "too many pixel tiles for one launch");
+    if((s = ensureWeights(ctx, nBatch * per + fragDoubles)) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
+    double* dFrag = ctx->dWeights + nBatch * per;
+    void (*kernel)(cmg::Geometry, const double*, cmg::DeviceTables, int, int, double*, long long);
+    size_t smem;
+    if(nkk == 8) { kernel = cmg::tquBatchedSlabKernel<8>; smem = cmg::M2Shape<8>::BYTES; }
+    else if(nkk == 12) { kernel = cmg::tquBatchedSlabKernel<12>; smem = cmg::M2Shape<12>::BYTES; }
+    else { kernel = cmg::tquBatchedSlabKernel<16>; smem = cmg::M2Shape<16>::BYTES; }
+    CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    KernelTimer timer(ctx);
+    cmg::foldSlabWeightsKernel<<<static_cast<unsigned>(std::min<int64_t>(1024, (fragDoubles + 255) / 256)), 256, 0, ctx->stream>>>(
+        ctx->dWeights, tablesOf(ctx), lmax, static_cast<int>(nBatch), nkk, dFrag);
+    kernel<<<dim3(static_cast<unsigned>(tiles * cmg::M2_GROUP), static_cast<unsigned>(groups), 2), cmg::M2_THREADS, smem, ctx->stream>>>(
+        geometryOf(ctx), dFrag, tablesOf(ctx), lmax, static_cast<int>(nBatch), dSlabs, cmg_slab_doubles(3 * ctx->npix));
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return timer.finish();
+}
+
+cmg_status cmg_slab_unpack(cmg_ctx* ctx, const double* dSlab, int64_t dim, int nLive, int onlyB, double* dOut, int64_t outStride)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!dSlab || !dOut || dim < 1 || nLive < 1 || nLive > CMG_SLAB || onlyB >= CMG_SLAB)
+        return fail(ctx, CMG_EINVAL, "bad slab arguments");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t packed = cmg_packed_size(dim);
+    const int64_t blocks = std::min<int64_t>((packed + 255) / 256, 148 * 16);
+    cmg::slabUnpackKernel<<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(dSlab, packed, nLive, onlyB, dOut, outStride);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
 }
 
 cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee, const double* cbb,

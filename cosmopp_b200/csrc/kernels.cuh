@@ -1150,6 +1150,418 @@ tquBatchedMmaKernel(Geometry geo, const double* __restrict__ frag, DeviceTables 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Batched T,Q,U on the FP64 tensor path, slab output.
+//
+// Why a second output format.  tquBatchedMmaKernel and two successors (register-resident basis; warp-specialised with
+// TMA-fed weight ring and store warps -- profiles/r1_kernel_history.md) all ended at ~25 ms per 128 Nside=16 matrices,
+// which tools/store_pattern.cu reproduces with stores alone: an m8n8k4 accumulator tile holds 8 pixel rows x 8 batch
+// elements, so the packed triangles receive 64-byte runs scattered over all matrices of the batch, and HBM takes such
+// writes at 1.7 TB/s (256-byte runs into 16 matrices at a time: 4.8 TB/s; fill: 7.5 TB/s).  The accumulator tile is
+// contiguous along the BATCH axis, so that is the axis to make contiguous in memory:
+//
+//   slab = 16 consecutive batch elements interleaved entry by entry:   slab[e * 16 + (b % 16)],  e = packed index
+//
+// i.e. each element of a slab is an ordinary packed CMatrix with element stride 16.  A warp's store instruction then
+// writes 1 KB contiguous (8 rows x 16 elements, natural entries) or 8 full 128-byte lines (transposed partners),
+// always sector-aligned, 32 bytes per lane.  cmg_slab_unpack converts a slab into 16 separate packed matrices.
+//
+//   * two independent passes (blockIdx.z): {TT, TE} -> T_iT_j, T_iQ_j, T_iU_j, Q_iT_j, U_iT_j and
+//     {EE+BB, EE-BB} -> Q_iQ_j, Q_iU_j, U_iU_j, U_iQ_j: a thread needs the basis of two families only;
+//   * CTA = 8 x 8 pixel pairs, warp w = column j = c0 + w, fragment row = pixel row i; the A fragments of the warp's
+//     m-tile (2 families x NKK k-steps of 4 multipoles) are computed once (phase A, through shared memory) and stay
+//     in REGISTERS for the whole batch; the MMA loop reads only weight fragments (one LDS.128 per two DMMAs);
+//   * weight fragments of the next chunks arrive by cp.async (3-stage ring shared by the 8 warps);
+//   * the columns of the weight fragments are permuted (element 4 (n / 2) + 2 nt + n % 2 in column n of n-tile nt) so
+//     that a lane's four accumulators of a family are four consecutive batch elements: one 256-bit store per entry;
+//   * block order: 16 adjacent column tiles per row tile, so neighbouring lines are written at about the same time.
+// ------------------------------------------------------------------------------------------------
+constexpr int M2_T = 8;
+constexpr int M2_PAIRS = M2_T * M2_T;
+constexpr int M2_THREADS = 256;
+constexpr int M2_BC = CMG_SLAB;                // batch elements per chunk = per slab: two n-tiles
+constexpr int M2_RING = 3;
+constexpr int M2_GROUP = 16;                   // column tiles walked together
+static_assert(CMG_SLAB == 16, "the fragment permutation below assumes 16-element slabs");
+
+template <int NKK>
+struct M2Shape
+{
+    static constexpr int KP = 4 * NKK;                                   // padded number of multipoles
+    static constexpr int LD = KP + ((4 - KP % 16) + 16) % 16;            // row stride of Phi
+    static constexpr int CHUNK = NKK * 2 * 32 * 2;                       // doubles of weight fragments per chunk and pass
+    static constexpr int PHI = 2 * M2_PAIRS * LD;
+    static constexpr int LOOP = M2_RING * CHUNK;
+    static constexpr int X = PHI > LOOP ? PHI : LOOP;                    // Phi is dead once the fragments are loaded
+    static constexpr size_t BYTES = sizeof(double) * (X + M2_PAIRS * 4 + 16 * M2_T + 4 * (KP + 1));
+};
+
+// w[b][4][lmax+1] -> frag[pass][chunk][kk][f][lane][nt]: folded weight of family 2 pass + f, l = 4 kk + lane % 4,
+// element b = 16 chunk + 4 (n / 2) + 2 nt + n % 2 with n = lane / 4 the fragment column
+__global__ void foldSlabWeightsKernel(const double* __restrict__ w, DeviceTables tab, int lmax, int nBatch, int nkk, double* __restrict__ frag)
+{
+    const int n1 = lmax + 1;
+    const int nChunks = (nBatch + M2_BC - 1) / M2_BC;
+    const long long total = 2LL * nChunks * nkk * 128;
+    for(long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const int nt = static_cast<int>(idx & 1);
+        const int lane = static_cast<int>((idx >> 1) & 31);
+        const int f = static_cast<int>((idx >> 6) & 1);
+        const long long rest = idx >> 7;
+        const int kk = static_cast<int>(rest % nkk);
+        const int chunk = static_cast<int>((rest / nkk) % nChunks);
+        const int pass = static_cast<int>(rest / nkk / nChunks);
+        const int fam = 2 * pass + f;
+        const int l = 4 * kk + (lane & 3);
+        const int n = lane >> 2;
+        const int b = chunk * M2_BC + 4 * (n >> 1) + 2 * nt + (n & 1);
+        double v = 0.0;
+        if(b < nBatch && l <= lmax)
+        {
+            const double* wb = w + static_cast<long long>(b) * 4 * n1;
+            if(fam == 0) v = wb[l] * tab.N0[l];
+            else if(l >= 2)
+            {
+                if(fam == 1) v = wb[n1 + l] * tab.N20[l] * 0.61237243569579452455;
+                else if(fam == 2) v = (wb[2 * n1 + l] + wb[3 * n1 + l]) * tab.N22[l] * 0.125;
+                else v = (wb[2 * n1 + l] - wb[3 * n1 + l]) * tab.N22[l] * 0.125;
+            }
+        }
+        frag[idx] = v;
+    }
+}
+
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc)
+{
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmemSrc) : "memory");
+}
+
+// four consecutive batch elements of one entry: one 256-bit store (STG.E.ENL2.256), 32-byte aligned by construction
+__device__ __forceinline__ void storeQuad(double* p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+template <int NKK, int PASS>
+__device__ __forceinline__ void slabBody(double* smem, const Geometry& geo, const double* __restrict__ frag, const DeviceTables& tab,
+                                         int lmax, int nBatch, double* __restrict__ out, long long slabDoubles,
+                                         long long rowTile, long long colTile)
+{
+    using S = M2Shape<NKK>;
+    constexpr int KP = S::KP, LD = S::LD;
+    double* sX = smem;
+    double* sFac = sX + S::X;                                      // [M2_PAIRS][4]
+    double* sI = sFac + M2_PAIRS * 4;                              // [8][M2_T]
+    double* sJ = sI + 8 * M2_T;
+    double* sTab = sJ + 8 * M2_T;                                  // [4][KP + 1]: g0, g20, g22, c22
+
+    const long long npix = geo.npix;
+    const long long rowBlock = rowTile * M2_T;
+    const long long c0 = colTile * M2_T;
+    const long long c1 = min(c0 + static_cast<long long>(M2_T), npix);
+    const int tid = threadIdx.x;
+    constexpr int tabLd = KP + 1;
+    for(int k = tid; k < 4 * tabLd; k += M2_THREADS)
+    {
+        const int which = k / tabLd, l = k - which * tabLd;
+        const double* src = which == 0 ? tab.g0 : (which == 1 ? tab.g20 : (which == 2 ? tab.g22 : tab.c22));
+        sTab[k] = src[l];
+    }
+    if(tid < 2 * M2_T)
+    {
+        const bool isRow = tid < M2_T;
+        const int loc = isRow ? tid : tid - M2_T;
+        const long long pix = min(isRow ? rowBlock + loc : c0 + loc, npix - 1);
+        double* dst = isRow ? sI : sJ;
+        dst[0 * M2_T + loc] = geo.nx[pix];
+        dst[1 * M2_T + loc] = geo.ny[pix];
+        dst[2 * M2_T + loc] = geo.nz[pix];
+        dst[3 * M2_T + loc] = geo.tx[pix];
+        dst[4 * M2_T + loc] = geo.ty[pix];
+        dst[5 * M2_T + loc] = geo.tz[pix];
+        dst[6 * M2_T + loc] = geo.px[pix];
+        dst[7 * M2_T + loc] = geo.py[pix];
+    }
+    __syncthreads();
+
+    // ---- A) basis values of this pass's two families (threads 0..127) and the rotation factors (threads 128..191).
+    //      pair p: row il = p % M2_T, column jl = p / M2_T
+    if(tid < 3 * M2_PAIRS)
+    {
+        const int p = tid & (M2_PAIRS - 1);
+        const int il = p % M2_T, jl = p / M2_T;
+        const double nix = sI[0 * M2_T + il], niy = sI[1 * M2_T + il], niz = sI[2 * M2_T + il];
+        const double njx = sJ[0 * M2_T + jl], njy = sJ[1 * M2_T + jl], njz = sJ[2 * M2_T + jl];
+        if(tid < 2 * M2_PAIRS)
+        {
+            const int f = tid >> 6;
+            const int fam = 2 * PASS + f;
+            double dot = __dadd_rn(__dadd_rn(__dmul_rn(nix, njx), __dmul_rn(niy, njy)), __dmul_rn(niz, njz));
+            dot = fmin(1.0, fmax(-1.0, dot));
+            const double x2 = dot + dot;
+            double* phi = sX + (static_cast<size_t>(f) * M2_PAIRS + p) * LD;
+            if(fam == 0)
+            {
+                double q0 = 1.0, q1 = x2;
+                phi[0] = q0;
+                phi[1] = q1;
+                for(int l0 = 1; l0 + 1 < KP; l0 += 4)
+                {
+                    double g[4];
+#pragma unroll
+                    for(int u = 0; u < 4; ++u)
+                        g[u] = sTab[min(l0 + u, KP)];
+#pragma unroll
+                    for(int u = 0; u < 4; ++u)
+                    {
+                        const int l = l0 + u;
+                        if(l + 1 < KP)
+                        {
+                            const double qn = fma(x2, q1, -g[u] * q0);
+                            q0 = q1; q1 = qn;
+                            phi[l + 1] = (l + 1 <= lmax) ? qn : 0.0;
+                        }
+                    }
+                }
+            }
+            else
+            {
+                const double* gt = sTab + (fam == 1 ? 1 : 2) * tabLd;
+                const double* ct = sTab + 3 * tabLd;
+                const double sgn = fam == 2 ? 1.0 : (fam == 3 ? -1.0 : 0.0);
+                double q0 = 0.0, q1 = 1.0;
+                phi[0] = 0.0;
+                phi[1] = 0.0;
+                phi[2] = lmax >= 2 ? 1.0 : 0.0;
+                for(int l0 = 2; l0 + 1 < KP; l0 += 4)
+                {
+                    double g[4], xc[4];
+#pragma unroll
+                    for(int u = 0; u < 4; ++u)
+                    {
+                        g[u] = gt[min(l0 + u, KP)];
+                        xc[u] = x2 - sgn * ct[min(l0 + u, KP)];
+                    }
+#pragma unroll
+                    for(int u = 0; u < 4; ++u)
+                    {
+                        const int l = l0 + u;
+                        if(l + 1 < KP)
+                        {
+                            const double qn = fma(xc[u], q1, -g[u] * q0);
+                            q0 = q1; q1 = qn;
+                            phi[l + 1] = (l + 1 <= lmax) ? qn : 0.0;
+                        }
+                    }
+                }
+            }
+        }
+        else
+        {
+            const double tix = sI[3 * M2_T + il], tiy = sI[4 * M2_T + il], tiz = sI[5 * M2_T + il];
+            const double pix_ = sI[6 * M2_T + il], piy = sI[7 * M2_T + il];
+            const double tjx = sJ[3 * M2_T + jl], tjy = sJ[4 * M2_T + jl], tjz = sJ[5 * M2_T + jl];
+            const double pjx = sJ[6 * M2_T + jl], pjy = sJ[7 * M2_T + jl];
+            double* fac = sFac + p * 4;
+            if(PASS == 0)
+            {
+                const double ai = fma(njx, tix, fma(njy, tiy, njz * tiz));
+                const double bi = fma(njx, pix_, njy * piy);
+                const double aj = fma(nix, tjx, fma(niy, tjy, niz * tjz));
+                const double bj = fma(nix, pjx, niy * pjy);
+                fac[0] = -fma(aj, aj, -bj * bj);    // -fTQ  (the TE sum enters with a minus sign)
+                fac[1] = -2.0 * aj * bj;            // -fTU
+                fac[2] = -fma(ai, ai, -bi * bi);    // -fQT
+                fac[3] = -2.0 * ai * bi;            // -fUT
+            }
+            else
+            {
+                const double pp = fma(tix, tjx, fma(tiy, tjy, tiz * tjz));
+                const double qq = fma(pix_, pjx, piy * pjy);
+                const double rr = fma(pix_, tjx, piy * tjy);
+                const double tq = fma(tix, pjx, tiy * pjy);
+                const double su = pp + qq, du = rr - tq, sv = pp - qq, dv = tq + rr;
+                fac[0] = fma(su, su, -du * du);     // reU
+                fac[1] = 2.0 * su * du;             // imU
+                fac[2] = fma(sv, sv, -dv * dv);     // reV
+                fac[3] = 2.0 * sv * dv;             // imV
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- fragments and per-pair constants to registers
+    const int lane = tid & 31, w = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    double a[2][NKK];
+    {
+        const double* src = sX + static_cast<size_t>(w * M2_T + fr) * LD + fc;
+#pragma unroll
+        for(int f = 0; f < 2; ++f)
+#pragma unroll
+            for(int kk = 0; kk < NKK; ++kk)
+                a[f][kk] = src[static_cast<size_t>(f) * M2_PAIRS * LD + 4 * kk];
+    }
+    const double2 fa = *reinterpret_cast<const double2*>(sFac + (w * M2_T + fr) * 4);
+    const double2 fb = *reinterpret_cast<const double2*>(sFac + (w * M2_T + fr) * 4 + 2);
+    const long long i = rowBlock + fr, j = c0 + w;
+    const bool natural = j < c1 && i <= j;
+    const bool transposed = j < c1 && i < j;
+    // element offsets of this lane's four batch elements (4 fc .. 4 fc + 3) of each entry
+    const long long eT = (packedOffset(j) + i) * CMG_SLAB + 4 * fc;                      // (T_i, T_j)
+    const long long eQ = (packedOffset(npix + j) + i) * CMG_SLAB + 4 * fc;               // (T_i, Q_j); + npix rows: (Q_i, Q_j)
+    const long long eU = (packedOffset(2 * npix + j) + i) * CMG_SLAB + 4 * fc;           // (T_i, U_j); + npix: (Q_i, U_j); + 2 npix: (U_i, U_j)
+    const long long eQt = (packedOffset(npix + min(i, npix - 1)) + j) * CMG_SLAB + 4 * fc;        // (T_j, Q_i)
+    const long long eUt = (packedOffset(2 * npix + min(i, npix - 1)) + j) * CMG_SLAB + 4 * fc;    // (T_j, U_i); + npix: (Q_j, U_i)
+    const long long rowN = npix * CMG_SLAB;
+    __syncthreads();                                               // Phi is dead: its storage becomes the weight ring
+
+    double* ring = sX;
+    const int nChunks = (nBatch + M2_BC - 1) / M2_BC;
+    const double* fragPass = frag + static_cast<long long>(PASS) * nChunks * S::CHUNK;
+    constexpr int PIECES = S::CHUNK / 2 / M2_THREADS;              // 16-byte pieces per thread and chunk
+    static_assert(S::CHUNK % (2 * M2_THREADS) == 0, "chunk must split evenly over the CTA");
+
+#pragma unroll
+    for(int pre = 0; pre < M2_RING - 1; ++pre)
+    {
+        if(pre < nChunks)
+        {
+#pragma unroll
+            for(int q = 0; q < PIECES; ++q)
+                cpAsync16(ring + pre * S::CHUNK + 2 * (tid + q * M2_THREADS),
+                          fragPass + static_cast<long long>(pre) * S::CHUNK + 2 * (tid + q * M2_THREADS));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    double* slab = out;
+#pragma unroll 1
+    for(int c = 0; c < nChunks; ++c, slab += slabDoubles)
+    {
+        asm volatile("cp.async.wait_group %0;" ::"n"(M2_RING - 2) : "memory");
+        __syncthreads();                                           // chunk c visible to all; stage of chunk c-1 free
+        if(c + M2_RING - 1 < nChunks)
+        {
+            double* dst = ring + ((c + M2_RING - 1) % M2_RING) * S::CHUNK;
+            const double* src = fragPass + static_cast<long long>(c + M2_RING - 1) * S::CHUNK;
+#pragma unroll
+            for(int q = 0; q < PIECES; ++q)
+                cpAsync16(dst + 2 * (tid + q * M2_THREADS), src + 2 * (tid + q * M2_THREADS));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        double acc[2][2][2];
+#pragma unroll
+        for(int f = 0; f < 2; ++f)
+#pragma unroll
+            for(int nt = 0; nt < 2; ++nt)
+                acc[f][nt][0] = acc[f][nt][1] = 0.0;
+        const double2* bs = reinterpret_cast<const double2*>(ring + (c % M2_RING) * S::CHUNK) + lane;
+#pragma unroll
+        for(int kk = 0; kk < NKK; ++kk)
+#pragma unroll
+            for(int f = 0; f < 2; ++f)
+            {
+                const double2 bv = bs[(kk * 2 + f) * 32];
+                dmma884(acc[f][0][0], acc[f][0][1], a[f][kk], bv.x);
+                dmma884(acc[f][1][0], acc[f][1][1], a[f][kk], bv.y);
+            }
+        // acc[f][nt][e] belongs to batch element 4 fc + 2 nt + e of this slab
+        if(PASS == 0)
+        {
+            if(natural)
+            {
+                storeQuad(slab + eT, acc[0][0][0], acc[0][0][1], acc[0][1][0], acc[0][1][1]);
+                storeQuad(slab + eQ, acc[1][0][0] * fa.x, acc[1][0][1] * fa.x, acc[1][1][0] * fa.x, acc[1][1][1] * fa.x);
+                storeQuad(slab + eU, acc[1][0][0] * fa.y, acc[1][0][1] * fa.y, acc[1][1][0] * fa.y, acc[1][1][1] * fa.y);
+            }
+            if(transposed)
+            {
+                storeQuad(slab + eQt, acc[1][0][0] * fb.x, acc[1][0][1] * fb.x, acc[1][1][0] * fb.x, acc[1][1][1] * fb.x);
+                storeQuad(slab + eUt, acc[1][0][0] * fb.y, acc[1][0][1] * fb.y, acc[1][1][0] * fb.y, acc[1][1][1] * fb.y);
+            }
+        }
+        else
+        {
+            double qq[4], qu[4], uu[4], uq[4];
+#pragma unroll
+            for(int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for(int e = 0; e < 2; ++e)
+                {
+                    const double s0 = acc[0][nt][e], s1 = acc[1][nt][e];
+                    const double aRe = s0 * fa.x, aIm = s0 * fa.y;
+                    qq[2 * nt + e] = fma(s1, fb.x, aRe);
+                    uu[2 * nt + e] = fma(-s1, fb.x, aRe);
+                    qu[2 * nt + e] = fma(s1, fb.y, -aIm);
+                    uq[2 * nt + e] = fma(s1, fb.y, aIm);
+                }
+            if(natural)
+            {
+                storeQuad(slab + eQ + rowN, qq[0], qq[1], qq[2], qq[3]);
+                storeQuad(slab + eU + rowN, qu[0], qu[1], qu[2], qu[3]);
+                storeQuad(slab + eU + 2 * rowN, uu[0], uu[1], uu[2], uu[3]);
+            }
+            if(transposed)
+                storeQuad(slab + eUt + rowN, uq[0], uq[1], uq[2], uq[3]);
+        }
+    }
+}
+
+template <int NKK>
+__global__ void __launch_bounds__(M2_THREADS, 2)
+tquBatchedSlabKernel(Geometry geo, const double* __restrict__ frag, DeviceTables tab, int lmax, int nBatch,
+                     double* __restrict__ out, long long slabDoubles)
+{
+    extern __shared__ __align__(16) double m2Smem[];
+    // block order: M2_GROUP adjacent column tiles of one row tile, then the next row tile, then the next group
+    const long long nTiles = (geo.npix + M2_T - 1) / M2_T;
+    const long long colTile = static_cast<long long>(blockIdx.y) * M2_GROUP + (blockIdx.x % M2_GROUP);
+    const long long rowTile = blockIdx.x / M2_GROUP;
+    if(colTile >= nTiles || rowTile > colTile)
+        return;
+    if(blockIdx.z == 0)
+        slabBody<NKK, 0>(m2Smem, geo, frag, tab, lmax, nBatch, out, slabDoubles, rowTile, colTile);
+    else
+        slabBody<NKK, 1>(m2Smem, geo, frag, tab, lmax, nBatch, out, slabDoubles, rowTile, colTile);
+}
+
+// slab -> separate packed matrices: out[b * outStride + e] = slab[e * 16 + b], b = 0 .. nLive-1 (onlyB >= 0: that element
+// alone, written to out[e]).  32 entries x 16 elements per warp pass through shared memory so that both sides move
+// whole lines.
+__global__ void __launch_bounds__(256) slabUnpackKernel(const double* __restrict__ slab, long long packed, int nLive, int onlyB,
+                                                        double* __restrict__ out, long long outStride)
+{
+    __shared__ double tile[8][32][CMG_SLAB + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long nBlocks = (packed + 255) / 256;
+    for(long long blk = blockIdx.x; blk < nBlocks; blk += gridDim.x)
+    {
+        const long long e0 = blk * 256 + w * 32;
+        // read 32 entries x 16 elements = 512 consecutive doubles
+#pragma unroll
+        for(int r = 0; r < CMG_SLAB; ++r)
+        {
+            const int q = r * 32 + lane;
+            const long long e = e0 + q / CMG_SLAB;
+            if(e < packed)
+                tile[w][q / CMG_SLAB][q % CMG_SLAB] = slab[e * CMG_SLAB + q % CMG_SLAB];
+        }
+        __syncwarp();
+        if(e0 + lane < packed)
+        {
+            if(onlyB >= 0)
+                out[e0 + lane] = tile[w][lane][onlyB];
+            else
+                for(int b = 0; b < nLive; ++b)
+                    out[b * outStride + e0 + lane] = tile[w][lane][b];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CMatrix::maskMatrix gather (reference source/c_matrix.cpp:182-201): out(a,b) = in(good[a], good[b])
 // ------------------------------------------------------------------------------------------------
 __global__ void maskGatherKernel(const double* __restrict__ in, const int* __restrict__ good, long long nGood,

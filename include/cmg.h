@@ -201,6 +201,24 @@ cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, 
 cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t n_batch,
                            double* d_out, int64_t stride);
 
+/* Batched T,Q,U on the FP64 tensor path (DMMA), slab output.  The reference has no batched generator, so the layout of
+ * a batch is this library's to define.  The tensor-core accumulator tile is contiguous along the batch axis, and that is
+ * the axis a slab keeps contiguous in memory:
+ *     slab k holds batch elements 16 k .. 16 k + 15, interleaved entry by entry:
+ *     d_slabs[k * cmg_slab_doubles(3 npix) + e * CMG_SLAB + (b % CMG_SLAB)],   e = i + j (j + 1) / 2, the reference's
+ *     packed index (source/c_matrix.cpp:19-39) in the [T;Q;U] ordering,
+ * so every batch element is an ordinary packed CMatrix with element stride CMG_SLAB.  d_slabs must hold
+ * ceil(n_batch / 16) slabs; elements beyond n_batch in the last slab are written as zeros.  2 <= lmax <= CMG_SLAB_LMAX;
+ * single-owner layout only (a batch shards over GPUs along the batch axis).  a[b][4][lmax+1] host, as above. */
+#define CMG_SLAB 16
+#define CMG_SLAB_LMAX 63
+int64_t cmg_slab_doubles(int64_t dim);
+cmg_status cmg_tqu_batched_slab(cmg_ctx* ctx, const double* a, int lmax, int64_t n_batch, double* d_slabs);
+/* one slab -> separate packed matrices of dimension dim: d_out[b * out_stride + e] for b < n_live (only_b < 0), or the
+ * single element only_b -> d_out[e] */
+cmg_status cmg_slab_unpack(cmg_ctx* ctx, const double* d_slab, int64_t dim, int n_live, int only_b,
+                           double* d_out, int64_t out_stride);
+
 /* ---------------------------------------------------------------- towards the consumer ------- */
 
 /* First step of the likelihood that consumes these matrices (reference source/likelihood.cpp:100-110): the sum of up to

@@ -308,6 +308,67 @@ def test_batched_generation_matches_single_calls(gpu_ctx, oracle_api):
         gpu_ctx.set_kernel_variant(0)
 
 
+def test_batched_slab_dmma_path(gpu_ctx, oracle_api):
+    """DMMA batched generator with slab output (cmg_tqu_batched_slab): several 16-element slabs (3-stage weight ring), a
+    batch size that is not a multiple of 16, a pixel count that is not a multiple of the 8 x 8 tile, the three
+    fragment shapes (lmax <= 31, 47, 63); every element extracted with cmg_slab_unpack and compared with the oracle,
+    the index layout position by position."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside, nb = 4, 53
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside))
+    gpu_ctx.set_pixels(nside, good)
+    n = gpu_ctx.npix
+    assert n % 8 != 0
+    packed = capi.packed_size(3 * n)
+    sd = capi.slab_doubles(3 * n)
+    assert sd == 16 * packed
+    n_slabs = (nb + 15) // 16
+    for lmax in (9, 40, 60):
+        f = capi.window_beam(lmax, 10.0)
+        ab = np.stack([np.stack(capi.tqu_weights(*synthetic_cl(lmax, seed=300 + b, pol=True), f, f)) for b in range(nb)])
+        slabs = torch.full((n_slabs * sd,), float("nan"), dtype=torch.float64, device="cuda")
+        gpu_ctx.tqu_batched_slab(ab, slabs)
+        torch.cuda.synchronize()
+        host = slabs.cpu().numpy().reshape(n_slabs, packed, 16)
+        assert not np.isnan(host).any()
+        assert (host[-1][:, nb % 16:] == 0).all()           # padding elements of the last slab are zeros
+        outs = torch.full((16, packed + 5), float("nan"), dtype=torch.float64, device="cuda")
+        one = torch.empty(packed, dtype=torch.float64, device="cuda")
+        for k in range(n_slabs):
+            live = min(16, nb - 16 * k)
+            outs.fill_(float("nan"))
+            gpu_ctx.slab_unpack(slabs[k * sd:(k + 1) * sd], 3 * n, outs, packed + 5, n_live=live)
+            torch.cuda.synchronize()
+            o = outs.cpu().numpy()
+            assert np.isnan(o[:, packed:]).all() and np.isnan(o[live:]).all()
+            assert np.array_equal(o[:live, :packed], host[k].T[:live])
+            gpu_ctx.slab_unpack(slabs[k * sd:(k + 1) * sd], 3 * n, one, only_b=live - 1)
+            torch.cuda.synchronize()
+            assert np.array_equal(one.cpu().numpy(), host[k][:, live - 1])
+        for b in (0, 15, 16, 31, 47, 52):
+            want = oracle_api.tqu_matrix(*synthetic_cl(lmax, seed=300 + b, pol=True), nside, 10.0, good=good)
+            _assert_tqu_close(np.ascontiguousarray(host[b // 16][:, b % 16]), want, n)
+    # full sky, tile-aligned pixel count, against the per-element default path
+    gpu_ctx.set_pixels(4)
+    n = gpu_ctx.npix
+    packed = capi.packed_size(3 * n)
+    lmax, nb = 12, 16
+    f = capi.window_beam(lmax, 10.0)
+    ab = np.stack([np.stack(capi.tqu_weights(*synthetic_cl(lmax, seed=400 + b, pol=True), f, f)) for b in range(nb)])
+    slabs = torch.full((capi.slab_doubles(3 * n),), float("nan"), dtype=torch.float64, device="cuda")
+    gpu_ctx.tqu_batched_slab(ab, slabs)
+    ref = torch.empty(nb * packed, dtype=torch.float64, device="cuda")
+    gpu_ctx.tqu_batched(ab, ref, packed)
+    torch.cuda.synchronize()
+    got = slabs.cpu().numpy().reshape(packed, 16).T
+    want = ref.cpu().numpy().reshape(nb, packed)
+    dP = want[0][capi.packed_index(n, n)]
+    assert np.abs(got - want).max() <= REL_TOL * dP
+    with pytest.raises(Exception):
+        gpu_ctx.tqu_batched_slab(np.zeros((2, 4, 65)), slabs)      # lmax = 64: refused, not silently rerouted
+
+
 def test_all_kernel_variants_agree(gpu_ctx, oracle_api):
     """Static-table and shared-memory-table kernels, all column counts: same matrix to rounding."""
     torch = _torch()
