@@ -1170,7 +1170,8 @@ tquBatchedMmaKernel(Geometry geo, const double* __restrict__ frag, DeviceTables 
 //   * CTA = 8 x 8 pixel pairs, warp w = column j = c0 + w, fragment row = pixel row i; the A fragments of the warp's
 //     m-tile (2 families x NKK k-steps of 4 multipoles) are computed once (phase A, through shared memory) and stay
 //     in REGISTERS for the whole batch; the MMA loop reads only weight fragments (one LDS.128 per two DMMAs);
-//   * weight fragments of the next chunks arrive by cp.async (3-stage ring shared by the 8 warps);
+//   * weight fragments of the next chunks arrive by TMA bulk copies into a 4-stage ring shared by the 8 warps
+//     (full / empty mbarriers; no CTA-wide barrier inside the batch loop);
 //   * the columns of the weight fragments are permuted (element 4 (n / 2) + 2 nt + n % 2 in column n of n-tile nt) so
 //     that a lane's four accumulators of a family are four consecutive batch elements: one 256-bit store per entry;
 //   * block order: 16 adjacent column tiles per row tile, so neighbouring lines are written at about the same time.
@@ -1179,7 +1180,7 @@ constexpr int M2_T = 8;
 constexpr int M2_PAIRS = M2_T * M2_T;
 constexpr int M2_THREADS = 256;
 constexpr int M2_BC = CMG_SLAB;                // batch elements per chunk = per slab: two n-tiles
-constexpr int M2_RING = 3;
+constexpr int M2_RING = 4;                    // weight-fragment stages (TMA bulk copies, full/empty mbarriers)
 constexpr int M2_GROUP = 16;                   // column tiles walked together
 static_assert(CMG_SLAB == 16, "the fragment permutation below assumes 16-element slabs");
 
@@ -1192,7 +1193,7 @@ struct M2Shape
     static constexpr int PHI = 2 * M2_PAIRS * LD;
     static constexpr int LOOP = M2_RING * CHUNK;
     static constexpr int X = PHI > LOOP ? PHI : LOOP;                    // Phi is dead once the fragments are loaded
-    static constexpr size_t BYTES = sizeof(double) * (X + M2_PAIRS * 4 + 16 * M2_T + 4 * (KP + 1));
+    static constexpr size_t BYTES = sizeof(double) * (X + M2_PAIRS * 4 + 16 * M2_T + 4 * (KP + 1) + 1 + 2 * M2_RING);
 };
 
 // w[b][4][lmax+1] -> frag[pass][chunk][kk][f][lane][nt]: folded weight of family 2 pass + f, l = 4 kk + lane % 4,
@@ -1231,10 +1232,33 @@ __global__ void foldSlabWeightsKernel(const double* __restrict__ w, DeviceTables
     }
 }
 
-__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc)
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(unsigned bar, unsigned count)
 {
-    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmemSrc) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    do
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while(!ok);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulkLoad(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // four consecutive batch elements of one entry: one 256-bit store (STG.E.ENL2.256), 32-byte aligned by construction
@@ -1255,6 +1279,8 @@ __device__ __forceinline__ void slabBody(double* smem, const Geometry& geo, cons
     double* sI = sFac + M2_PAIRS * 4;                              // [8][M2_T]
     double* sJ = sI + 8 * M2_T;
     double* sTab = sJ + 8 * M2_T;                                  // [4][KP + 1]: g0, g20, g22, c22
+    const unsigned bFull = smemAddr(sTab + 4 * (KP + 1) + ((4 * (KP + 1)) & 1));      // [M2_RING] full, then [M2_RING] empty
+    const unsigned bEmpty = bFull + 8 * M2_RING;
 
     const long long npix = geo.npix;
     const long long rowBlock = rowTile * M2_T;
@@ -1282,6 +1308,15 @@ __device__ __forceinline__ void slabBody(double* smem, const Geometry& geo, cons
         dst[5 * M2_T + loc] = geo.tz[pix];
         dst[6 * M2_T + loc] = geo.px[pix];
         dst[7 * M2_T + loc] = geo.py[pix];
+    }
+    else if(tid == 2 * M2_T)
+    {
+        for(int k = 0; k < M2_RING; ++k)
+        {
+            mbarInit(bFull + 8 * k, 1);
+            mbarInit(bEmpty + 8 * k, M2_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
@@ -1420,44 +1455,30 @@ __device__ __forceinline__ void slabBody(double* smem, const Geometry& geo, cons
     double* ring = sX;
     const int nChunks = (nBatch + M2_BC - 1) / M2_BC;
     const double* fragPass = frag + static_cast<long long>(PASS) * nChunks * S::CHUNK;
-    constexpr int PIECES = S::CHUNK / 2 / M2_THREADS;              // 16-byte pieces per thread and chunk
-    static_assert(S::CHUNK % (2 * M2_THREADS) == 0, "chunk must split evenly over the CTA");
-
-#pragma unroll
-    for(int pre = 0; pre < M2_RING - 1; ++pre)
+    constexpr unsigned chunkBytes = S::CHUNK * sizeof(double);
+    if(tid == 0)
     {
-        if(pre < nChunks)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses to Phi before async writes
+        for(int k = 0; k < M2_RING && k < nChunks; ++k)
         {
-#pragma unroll
-            for(int q = 0; q < PIECES; ++q)
-                cpAsync16(ring + pre * S::CHUNK + 2 * (tid + q * M2_THREADS),
-                          fragPass + static_cast<long long>(pre) * S::CHUNK + 2 * (tid + q * M2_THREADS));
+            mbarExpectTx(bFull + 8 * k, chunkBytes);
+            bulkLoad(smemAddr(ring + k * S::CHUNK), fragPass + static_cast<long long>(k) * S::CHUNK, chunkBytes, bFull + 8 * k);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
     double* slab = out;
 #pragma unroll 1
     for(int c = 0; c < nChunks; ++c, slab += slabDoubles)
     {
-        asm volatile("cp.async.wait_group %0;" ::"n"(M2_RING - 2) : "memory");
-        __syncthreads();                                           // chunk c visible to all; stage of chunk c-1 free
-        if(c + M2_RING - 1 < nChunks)
-        {
-            double* dst = ring + ((c + M2_RING - 1) % M2_RING) * S::CHUNK;
-            const double* src = fragPass + static_cast<long long>(c + M2_RING - 1) * S::CHUNK;
-#pragma unroll
-            for(int q = 0; q < PIECES; ++q)
-                cpAsync16(dst + 2 * (tid + q * M2_THREADS), src + 2 * (tid + q * M2_THREADS));
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int st = c % M2_RING;
+        mbarWait(bFull + 8 * st, (c / M2_RING) & 1);
         double acc[2][2][2];
 #pragma unroll
         for(int f = 0; f < 2; ++f)
 #pragma unroll
             for(int nt = 0; nt < 2; ++nt)
                 acc[f][nt][0] = acc[f][nt][1] = 0.0;
-        const double2* bs = reinterpret_cast<const double2*>(ring + (c % M2_RING) * S::CHUNK) + lane;
+        const double2* bs = reinterpret_cast<const double2*>(ring + st * S::CHUNK) + lane;
 #pragma unroll
         for(int kk = 0; kk < NKK; ++kk)
 #pragma unroll
@@ -1467,6 +1488,19 @@ __device__ __forceinline__ void slabBody(double* smem, const Geometry& geo, cons
                 dmma884(acc[f][0][0], acc[f][0][1], a[f][kk], bv.x);
                 dmma884(acc[f][1][0], acc[f][1][1], a[f][kk], bv.y);
             }
+        __syncwarp();
+        if(lane == 0)
+        {
+            mbarArrive(bEmpty + 8 * st);
+            // warp 0 refills the stage of chunk c-1 with chunk c+3 once all eight warps have released it
+            if(w == 0 && c >= 1 && c + M2_RING - 1 < nChunks)
+            {
+                const int sp = (c - 1) % M2_RING;
+                mbarWait(bEmpty + 8 * sp, ((c - 1) / M2_RING) & 1);
+                mbarExpectTx(bFull + 8 * sp, chunkBytes);
+                bulkLoad(smemAddr(ring + sp * S::CHUNK), fragPass + static_cast<long long>(c + M2_RING - 1) * S::CHUNK, chunkBytes, bFull + 8 * sp);
+            }
+        }
         // acc[f][nt][e] belongs to batch element 4 fc + 2 nt + e of this slab
         if(PASS == 0)
         {
