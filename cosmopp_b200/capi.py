@@ -95,6 +95,10 @@ _SIGNATURES = {
     "cmg_tqu_batched_slab": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp]),
     "cmg_slab_unpack": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _i64]),
     "cmg_sum_unpack": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "cmg_sum_unpack_strided": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "cmg_like_create": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, ctypes.POINTER(_vp)]),
+    "cmg_like_calculate": (ctypes.c_int, [_vp, _vp, _i64, _vp, ctypes.POINTER(ctypes.c_double)]),
+    "cmg_like_destroy": (None, [_vp]),
     "cmg_measure_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),

@@ -8,7 +8,9 @@
 #include <string>
 #include <vector>
 
+#include <cublas_v2.h>
 #include <cuda_runtime.h>
+#include <cusolverDn.h>
 
 #include "../../include/cmg.h"
 #include "healpix_nest.hpp"
@@ -1061,15 +1063,173 @@ cmg_status cmg_tqu_scatter_block(cmg_ctx* ctx, const double* dBlock, int64_t col
     return CMG_OK;
 }
 
-cmg_status cmg_sum_unpack(cmg_ctx* ctx, const double* dC, const double* dF, const double* dN, int64_t n, double* dFull)
+cmg_status cmg_sum_unpack_strided(cmg_ctx* ctx, const double* dC, int64_t cStride, const double* dF, const double* dN, int64_t n, double* dFull)
 {
-    if(!ctx || !dC || !dFull || n < 1) return CMG_EINVAL;
+    if(!ctx || !dC || !dFull || n < 1 || cStride < 1) return CMG_EINVAL;
     if((n + 31) / 32 > 65535) return fail(ctx, CMG_EUNSUPPORTED, "matrix too large for one launch");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const unsigned blocks = static_cast<unsigned>((n + 31) / 32);
-    cmg::sumUnpackKernel<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(dC, dF, dN, n, dFull);
+    cmg::sumUnpackKernel<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(dC, cStride, dF, dN, n, dFull);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
+    return CMG_OK;
+}
+
+cmg_status cmg_sum_unpack(cmg_ctx* ctx, const double* dC, const double* dF, const double* dN, int64_t n, double* dFull)
+{
+    return cmg_sum_unpack_strided(ctx, dC, 1, dF, dN, n, dFull);
+}
+
+// ---------------------------------------------------------------- pixel likelihood on the device
+// reference source/likelihood.cpp:68-134 (construct) and :136-180 (vmv, calculate).  The reference inverts C + F + N
+// (LAPACK dpptrf / dpptri) and evaluates t^T C^-1 t as a double loop per map; here the Cholesky factor stays on the
+// device and chi2 = |L^-1 t|^2 for all maps at once (cuSOLVER potrf, cuBLAS trsm: plain library calls), the
+// sum / unpack and the reductions are this library's kernels.
+
+struct cmg_like
+{
+    cmg_ctx* ctx = nullptr;
+    int64_t n = 0;
+    double* dL = nullptr;            // n x n, lower triangle = Cholesky factor
+    double* dYf = nullptr;           // L^-1 f
+    double* dT = nullptr;            // maps / solutions, n x tCap
+    int64_t tCap = 0;
+    double* dRed = nullptr;          // 2 x tCap reductions
+    bool hasF = false;
+    double logDet = 0.0;             // log det (C + F + N) - offset
+    double fCinvf = 0.0;
+    cusolverDnHandle_t sol = nullptr;
+    cublasHandle_t blas = nullptr;
+};
+
+namespace
+{
+const double kDetOffset = -29677.0566;          // reference source/likelihood.cpp:126
+
+cmg_status likeReserve(cmg_like* L, int64_t nMaps)
+{
+    cmg_ctx* ctx = L->ctx;
+    if(nMaps <= L->tCap)
+        return CMG_OK;
+    if(L->dT) { cudaStreamSynchronize(ctx->stream); cudaFree(L->dT); cudaFree(L->dRed); L->dT = L->dRed = nullptr; L->tCap = 0; }
+    CMG_CUDA(ctx, cudaMalloc(&L->dT, sizeof(double) * L->n * nMaps));
+    CMG_CUDA(ctx, cudaMalloc(&L->dRed, sizeof(double) * 2 * nMaps));
+    L->tCap = nMaps;
+    return CMG_OK;
+}
+}
+
+void cmg_like_destroy(cmg_like* L)
+{
+    if(!L)
+        return;
+    if(L->ctx)
+    {
+        cudaSetDevice(L->ctx->device);
+        cudaStreamSynchronize(L->ctx->stream);
+    }
+    if(L->dL) cudaFree(L->dL);
+    if(L->dYf) cudaFree(L->dYf);
+    if(L->dT) cudaFree(L->dT);
+    if(L->dRed) cudaFree(L->dRed);
+    if(L->sol) cusolverDnDestroy(L->sol);
+    if(L->blas) cublasDestroy(L->blas);
+    delete L;
+}
+
+cmg_status cmg_like_create(cmg_ctx* ctx, const double* dC, int64_t cStride, const double* dF, const double* dN, int64_t n,
+                           const double* foreground, cmg_like** out)
+{
+    if(!ctx || !out) return CMG_EINVAL;
+    *out = nullptr;
+    if(!dC || n < 1 || cStride < 1) return fail(ctx, CMG_EINVAL, "bad likelihood arguments");
+    if(n > 46340) return fail(ctx, CMG_EUNSUPPORTED, "dense factorisation limited to n <= 46340 (32-bit LAPACK-style interface)");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_like* L = new(std::nothrow) cmg_like;
+    if(!L) return fail(ctx, CMG_ENOMEM, "out of host memory");
+    L->ctx = ctx;
+    L->n = n;
+    cmg_status s = CMG_OK;
+    double* dWork = nullptr;
+    int* dInfo = nullptr;
+    auto bail = [&](cmg_status st) { if(dWork) cudaFree(dWork); if(dInfo) cudaFree(dInfo); cmg_like_destroy(L); return st; };
+    cudaError_t e;
+    if((e = cudaMalloc(&L->dL, sizeof(double) * n * n)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMalloc (full matrix)"));
+    if((s = cmg_sum_unpack_strided(ctx, dC, cStride, dF, dN, n, L->dL)) != CMG_OK) return bail(s);
+    if(cusolverDnCreate(&L->sol) != CUSOLVER_STATUS_SUCCESS || cublasCreate(&L->blas) != CUBLAS_STATUS_SUCCESS)
+        return bail(fail(ctx, CMG_ECUDA, "cuSOLVER / cuBLAS handle creation failed"));
+    cusolverDnSetStream(L->sol, ctx->stream);
+    cublasSetStream(L->blas, ctx->stream);
+    int lwork = 0;
+    if(cusolverDnDpotrf_bufferSize(L->sol, CUBLAS_FILL_MODE_LOWER, static_cast<int>(n), L->dL, static_cast<int>(n), &lwork) != CUSOLVER_STATUS_SUCCESS)
+        return bail(fail(ctx, CMG_ECUDA, "cusolverDnDpotrf_bufferSize failed"));
+    if((e = cudaMalloc(&dWork, sizeof(double) * std::max(lwork, 1))) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMalloc (potrf workspace)"));
+    if((e = cudaMalloc(&dInfo, sizeof(int))) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMalloc"));
+    if(cusolverDnDpotrf(L->sol, CUBLAS_FILL_MODE_LOWER, static_cast<int>(n), L->dL, static_cast<int>(n), dWork, lwork, dInfo) != CUSOLVER_STATUS_SUCCESS)
+        return bail(fail(ctx, CMG_ECUDA, "cusolverDnDpotrf failed"));
+    int info = 0;
+    std::vector<double> diag(n);
+    if((e = cudaMemcpyAsync(&info, dInfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMemcpy"));
+    if((e = cudaMemcpy2DAsync(diag.data(), sizeof(double), L->dL, sizeof(double) * (n + 1), sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
+        return bail(cudaFail(ctx, e, "cudaMemcpy2D (diagonal)"));
+    if((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaStreamSynchronize"));
+    if(info != 0)
+        return bail(fail(ctx, CMG_ENUMERIC, "The determinant of the covariance matrix is not positive. The covariance matrix must be positive definite."));
+    double logDet = 0.0;
+    for(int64_t i = 0; i < n; ++i)
+        logDet += std::log(diag[i]);
+    L->logDet = 2.0 * logDet - kDetOffset;
+    if(foreground)
+    {
+        if((e = cudaMalloc(&L->dYf, sizeof(double) * n)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMalloc"));
+        if((e = cudaMemcpyAsync(L->dYf, foreground, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMemcpy"));
+        const double one = 1.0;
+        if(cublasDtrsm(L->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, static_cast<int>(n), 1, &one,
+                       L->dL, static_cast<int>(n), L->dYf, static_cast<int>(n)) != CUBLAS_STATUS_SUCCESS)
+            return bail(fail(ctx, CMG_ECUDA, "cublasDtrsm failed"));
+        if((s = likeReserve(L, 1)) != CMG_OK) return bail(s);
+        cmg::columnDotsKernel<<<1, 256, 0, ctx->stream>>>(L->dYf, nullptr, n, L->dRed, nullptr);
+        if((e = cudaMemcpyAsync(&L->fCinvf, L->dRed, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMemcpy"));
+        if((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaStreamSynchronize"));
+        ctx->launches += 1;
+        L->hasF = true;
+    }
+    cudaFree(dWork);
+    cudaFree(dInfo);
+    *out = L;
+    return CMG_OK;
+}
+
+cmg_status cmg_like_calculate(cmg_like* L, const double* t, int64_t nMaps, double* chi2, double* logDet)
+{
+    if(!L || !L->ctx) return CMG_EINVAL;
+    cmg_ctx* ctx = L->ctx;
+    if(!t || !chi2 || nMaps < 1 || nMaps > 2147483647LL) return fail(ctx, CMG_EINVAL, "bad likelihood arguments");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_status s = likeReserve(L, nMaps);
+    if(s != CMG_OK) return s;
+    const int64_t n = L->n;
+    CMG_CUDA(ctx, cudaMemcpyAsync(L->dT, t, sizeof(double) * n * nMaps, cudaMemcpyHostToDevice, ctx->stream));
+    const double one = 1.0;
+    if(cublasDtrsm(L->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, static_cast<int>(n), static_cast<int>(nMaps), &one,
+                   L->dL, static_cast<int>(n), L->dT, static_cast<int>(n)) != CUBLAS_STATUS_SUCCESS)
+        return fail(ctx, CMG_ECUDA, "cublasDtrsm failed");
+    cmg::columnDotsKernel<<<static_cast<unsigned>(nMaps), 256, 0, ctx->stream>>>(L->dT, L->hasF ? L->dYf : nullptr, n, L->dRed, L->hasF ? L->dRed + nMaps : nullptr);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    std::vector<double> red(2 * nMaps, 0.0);
+    CMG_CUDA(ctx, cudaMemcpyAsync(red.data(), L->dRed, sizeof(double) * (L->hasF ? 2 : 1) * nMaps, cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ld = L->logDet;
+    if(L->hasF)
+        ld += std::log(L->fCinvf / static_cast<double>(n));                 // source/likelihood.cpp:174
+    for(int64_t k = 0; k < nMaps; ++k)
+    {
+        chi2[k] = red[k];
+        if(L->hasF)
+            chi2[k] -= red[nMaps + k] * red[nMaps + k] / L->fCinvf;          // :175
+    }
+    if(logDet) *logDet = ld;
     return CMG_OK;
 }
 

@@ -17,6 +17,8 @@
 #include <exception_handler.hpp>
 #include <utils.hpp>
 
+#include "dropin_internal.hpp"
+
 namespace
 {
 [[noreturn]] void raise(const std::string& text) { throw StandardException(text); }
@@ -40,6 +42,16 @@ cmg_ctx* context()
     return ctx;
 }
 
+} // namespace
+
+cmg_ctx* cmgDropinContext()
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    return context();
+}
+
+namespace
+{
 void check(cmg_ctx* ctx, cmg_status s)
 {
     if(s != CMG_OK)

@@ -1638,7 +1638,8 @@ __global__ void scatterBlockKernel(const double* __restrict__ block, long long n
 // be absent) written as a full symmetric column-major n x n matrix, ready for a dense Cholesky.  One pass over HBM
 // instead of three matrix reads on the host.  Tile 32 x 32 through shared memory so both triangles are written coalesced.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sumUnpackKernel(const double* __restrict__ c, const double* __restrict__ f, const double* __restrict__ nz,
+// cStride: element stride of c (1 = packed matrix, CMG_SLAB = one element of a slab)
+__global__ void __launch_bounds__(256) sumUnpackKernel(const double* __restrict__ c, long long cStride, const double* __restrict__ f, const double* __restrict__ nz,
                                                        long long n, double* __restrict__ full)
 {
     __shared__ double tile[32][33];
@@ -1653,7 +1654,7 @@ __global__ void __launch_bounds__(256) sumUnpackKernel(const double* __restrict_
         if(j < n && i <= j)
         {
             const long long k = packedOffset(j) + i;
-            v = c[k];
+            v = c[k * cStride];
             if(f) v += f[k];
             if(nz) v += nz[k];
             full[j * n + i] = v;                               // upper triangle entry (i, j)
@@ -1666,6 +1667,40 @@ __global__ void __launch_bounds__(256) sumUnpackKernel(const double* __restrict_
         const long long i = bi * 32 + r, j = bj * 32 + tx;     // write (j, i) of the lower triangle: column i, rows j, lanes along j
         if(j < n && i < j)
             full[i * n + j] = tile[tx][r];
+    }
+}
+
+// chi2 pieces of the pixel likelihood (reference source/likelihood.cpp:163-180) after the triangular solve L y = t:
+// yy[k] = sum_i y[i,k]^2 and, with a foreground template, yf[k] = sum_i y[i,k] yF[i].  One block per map, fixed
+// summation order (deterministic).
+__global__ void __launch_bounds__(256) columnDotsKernel(const double* __restrict__ y, const double* __restrict__ yF, long long n,
+                                                        double* __restrict__ yy, double* __restrict__ yf)
+{
+    __shared__ double s0[256], s1[256];
+    const double* col = y + static_cast<long long>(blockIdx.x) * n;
+    double a = 0.0, b = 0.0;
+    for(long long i = threadIdx.x; i < n; i += 256)
+    {
+        const double v = col[i];
+        a = fma(v, v, a);
+        if(yF) b = fma(v, yF[i], b);
+    }
+    s0[threadIdx.x] = a;
+    s1[threadIdx.x] = b;
+    __syncthreads();
+    for(int h = 128; h > 0; h >>= 1)
+    {
+        if(threadIdx.x < h)
+        {
+            s0[threadIdx.x] += s0[threadIdx.x + h];
+            s1[threadIdx.x] += s1[threadIdx.x + h];
+        }
+        __syncthreads();
+    }
+    if(threadIdx.x == 0)
+    {
+        yy[blockIdx.x] = s0[0];
+        if(yf) yf[blockIdx.x] = s1[0];
     }
 }
 

@@ -41,7 +41,8 @@ typedef enum cmg_status {
     CMG_ECUDA = 2,         /* CUDA runtime / launch failure (text in cmg_last_error) */
     CMG_ENOMEM = 3,        /* host or device allocation failed */
     CMG_ESTATE = 4,        /* call order: geometry not set, ... */
-    CMG_EUNSUPPORTED = 5   /* size beyond what the kernels are built for (lmax > CMG_LMAX_LIMIT) */
+    CMG_EUNSUPPORTED = 5,  /* size beyond what the kernels are built for (lmax > CMG_LMAX_LIMIT) */
+    CMG_ENUMERIC = 6       /* the matrix handed to the likelihood is not positive definite */
 } cmg_status;
 
 #define CMG_LMAX_LIMIT 1023   /* series length the kernels stage in shared memory */
@@ -225,6 +226,21 @@ cmg_status cmg_slab_unpack(cmg_ctx* ctx, const double* d_slab, int64_t dim, int 
  * three packed matrices of dimension n (d_f and/or d_n may be NULL) written as a FULL symmetric column-major n x n matrix
  * on the device, ready for a dense Cholesky factorisation, in one pass over HBM. */
 cmg_status cmg_sum_unpack(cmg_ctx* ctx, const double* d_c, const double* d_f, const double* d_n, int64_t n, double* d_full);
+/* same with an element stride on d_c: c_stride = CMG_SLAB and d_c = slab + (b % CMG_SLAB) reads element b of a slab */
+cmg_status cmg_sum_unpack_strided(cmg_ctx* ctx, const double* d_c, int64_t c_stride, const double* d_f, const double* d_n,
+                                  int64_t n, double* d_full);
+
+/* The temperature pixel likelihood of reference source/likelihood.cpp (`Likelihood::construct` :68-134, `calculate`
+ * :163-180) with everything resident on the device: C + F + N (packed, device; d_c with element stride c_stride) ->
+ * Cholesky factor -> log det - offset (the reference's constant -29677.0566, :126); `foreground` (host, n values or NULL)
+ * is the template marginalised over.  CMG_ENUMERIC if the sum is not positive definite (the reference throws). */
+typedef struct cmg_like cmg_like;
+cmg_status cmg_like_create(cmg_ctx* ctx, const double* d_c, int64_t c_stride, const double* d_f, const double* d_n,
+                           int64_t n, const double* foreground, cmg_like** out);
+/* n_maps maps (host, map k at t + k n): chi2[k] = t^T C^-1 t (minus the foreground projection), *log_det = log det term
+ * (with the foreground term when a template was given); -2 log L = chi2[k] + *log_det */
+cmg_status cmg_like_calculate(cmg_like* like, const double* t, int64_t n_maps, double* chi2, double* log_det);
+void cmg_like_destroy(cmg_like* like);
 
 /* ---------------------------------------------------------------- measurement --------------- */
 

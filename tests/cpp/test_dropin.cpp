@@ -13,6 +13,7 @@
 #include <c_matrix.hpp>
 #include <c_matrix_generator.hpp>
 #include <exception_handler.hpp>
+#include <likelihood.hpp>
 #include <utils.hpp>
 
 static int failures = 0;
@@ -184,6 +185,38 @@ static void gpuTests(const std::string& dir)
     cMatrix->writeIntoFile((dir + "/c.dat").c_str());
     fiducialMatrix->writeIntoFile((dir + "/c_fiducial.dat").c_str());
     noiseMatrix->writeIntoFile((dir + "/c_noise.dat").c_str());
+
+    // the consumer, as in reference source/test_like_low.cpp:187-191 (plus the foreground-template variant)
+    {
+        const std::vector<double> maps = readDoubles(dir + "/maps.f64"), fore = readDoubles(dir + "/fore.f64");
+        const size_t ng = good.size(), nMaps = maps.size() / ng;
+        std::vector<std::vector<double> > t(nMaps);
+        for(size_t k = 0; k < nMaps; ++k)
+            t[k].assign(maps.begin() + k * ng, maps.begin() + (k + 1) * ng);
+        std::vector<double> foreground;
+        Likelihood like(*cMatrix, *fiducialMatrix, *noiseMatrix, good, foreground);
+        std::vector<std::string> mapNames(nMaps, "test_map");
+        std::vector<LikelihoodResult> results;
+        like.calculateAll(t, mapNames, results);
+        EXPECT(results.size() == nMaps && results[0].mapName == "test_map");
+        double chi2 = 0, logDet = 0;
+        const double l0 = like.calculate(t[0], chi2, logDet);
+        // (one map or six at a time: the library's triangular solve may block differently, so equal to rounding only)
+        EXPECT(std::fabs(chi2 - results[0].chi2) <= 1e-11 * chi2 && logDet == results[0].logDet && std::fabs(l0 - results[0].like) <= 1e-11 * std::fabs(l0));
+        Likelihood likeF(*cMatrix, *fiducialMatrix, *noiseMatrix, good, fore);
+        std::vector<LikelihoodResult> resultsF;
+        likeF.calculateAll(t, mapNames, resultsF);
+        std::FILE* f = std::fopen((dir + "/like.txt").c_str(), "w");
+        for(size_t k = 0; k < nMaps; ++k)
+            std::fprintf(f, "%.17g %.17g %.17g %.17g\n", results[k].chi2, results[k].logDet, resultsF[k].chi2, resultsF[k].logDet);
+        std::fclose(f);
+        // error behaviour of the reference: size mismatches and a matrix that is not positive definite throw
+        EXPECT(throwsStandard([&] { std::vector<int> fewer(good.begin(), good.end() - 1); Likelihood bad(*cMatrix, *fiducialMatrix, *noiseMatrix, fewer, foreground); }));
+        EXPECT(throwsStandard([&] { std::vector<double> shortMap(ng - 1, 0.0); double a, b; like.calculate(shortMap, a, b); }));
+        CMatrix negative(*noiseMatrix);
+        for(int i = 0; i < negative.getNPix(); ++i) negative.element(i, i) = -1e6;
+        EXPECT(throwsStandard([&] { Likelihood bad(*cMatrix, *fiducialMatrix, negative, good, foreground); }));
+    }
     delete cMatrix;
     delete fiducialMatrix;
     delete noiseMatrix;

@@ -86,8 +86,29 @@ def test_cpp_dropin_generators_match_oracle(dropin_binary, tmp_path, oracle_api)
     short = synthetic_cl(12)
     with open(str(tmp_path / "cl_short.txt"), "w") as f:
         f.write("".join("%.17g\n" % v for v in short))
+    rng = np.random.default_rng(7)
+    maps = rng.normal(size=(6, len(good))) * 30.0
+    fore = rng.normal(size=len(good)) * 5.0 + 20.0
+    maps.astype("<f8").tofile(str(tmp_path / "maps.f64"))
+    fore.astype("<f8").tofile(str(tmp_path / "fore.f64"))
     r = subprocess.run([dropin_binary, "gpu", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+    # the Likelihood class against a numpy restatement of reference source/likelihood.cpp:100-180 on the oracle's matrices
+    ng = len(good)
+    S = (oracle_api.unpack_symmetric(oracle_api.cl_to_cmatrix(tt[:lmax + 1], nside, 10.0, good=good), ng)
+         + oracle_api.unpack_symmetric(oracle_api.fiducial_matrix(tt, nside, lmax, 10.0, good=good), ng)
+         + oracle_api.unpack_symmetric(oracle_api.mask_matrix(oracle_api.noise_matrix(nside, 1e-2), good), ng))
+    Sinv = np.linalg.inv(S)
+    logdet = np.linalg.slogdet(S)[1] + 29677.0566
+    got = np.loadtxt(str(tmp_path / "like.txt"))
+    fCf = fore @ Sinv @ fore
+    for k in range(maps.shape[0]):
+        chi2 = maps[k] @ Sinv @ maps[k]
+        assert abs(got[k, 0] - chi2) <= 1e-9 * chi2 and abs(got[k, 1] - logdet) <= 1e-9 * abs(logdet)
+        tCf = maps[k] @ Sinv @ fore
+        assert abs(got[k, 2] - (chi2 - tCf * tCf / fCf)) <= 1e-9 * chi2
+        assert abs(got[k, 3] - (logdet + np.log(fCf / ng))) <= 1e-9 * abs(logdet)
 
     n, c, _ = read_cmatrix(str(tmp_path / "c.dat"))
     want = oracle_api.cl_to_cmatrix(tt[:lmax + 1], nside, 10.0, good=good)

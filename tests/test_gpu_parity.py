@@ -610,6 +610,32 @@ def test_device_resident_likelihood_consumer(gpu_ctx, oracle_api):
     # without the template
     plain = Likelihood(gpu_ctx, d_c, d_f, d_n, n)
     assert abs(plain.calculate(maps[0])[1] - maps[0] @ Cinv @ maps[0]) <= 1e-8 * abs(maps[0] @ Cinv @ maps[0])
+    # not positive definite: the reference throws with this text (source/likelihood.cpp:119-124)
+    with pytest.raises(ValueError, match="must be positive definite"):
+        Likelihood(gpu_ctx, d_c, d_f, torch.from_numpy(-1e6 * noise).cuda(), n)
+
+    # one element of a batched slab (element stride 16) as the covariance of a T,Q,U likelihood
+    nside, lmax, nb = 4, 12, 3
+    gpu_ctx.set_pixels(nside)
+    n3 = 3 * gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    spectra = [synthetic_cl(lmax, seed=500 + b, pol=True) for b in range(nb)]
+    ab = np.stack([np.stack(capi.tqu_weights(*sp, f, f)) for sp in spectra])
+    slab = torch.empty(capi.slab_doubles(n3), dtype=torch.float64, device="cuda")
+    gpu_ctx.tqu_batched_slab(ab, slab)
+    sigma2 = 4.0
+    noise3 = np.zeros(capi.packed_size(n3))
+    noise3[[capi.packed_index(i, i) for i in range(n3)]] = sigma2
+    d_n3 = torch.from_numpy(noise3).cuda()
+    m3 = rs.standard_normal(n3) * 3.0
+    for b in range(nb):
+        lk = Likelihood(gpu_ctx, slab[b:], None, d_n3, n3, c_stride=capi.SLAB)
+        C3 = oracle_api.unpack_symmetric(oracle_api.tqu_matrix(*spectra[b], nside, 10.0), n3) + sigma2 * np.eye(n3)
+        total, chi2, logdet = lk.calculate(m3)
+        want = m3 @ np.linalg.solve(C3, m3)
+        assert abs(chi2 - want) <= 1e-8 * want
+        assert abs(logdet - (np.linalg.slogdet(C3)[1] - DET_OFFSET)) <= 1e-9 * abs(logdet)
+        lk.close()
 
 
 def test_device_resident_weights_and_cuda_graph_replay(gpu_ctx, oracle_api):
