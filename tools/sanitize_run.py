@@ -36,6 +36,19 @@ for r in range(3):
     for o, nc, ld, row0 in plan["outbox"]:
         for t in range(3):
             ctx.tqu_scatter_block(outbox[o][t], b[o], nc, ld, row0, t, outp)
+# slab path (TMA bulk copies + mbarriers), three fragment shapes, several chunks; unpack; likelihood kernels
+from cosmopp_b200.likelihood import Likelihood
+for lm in (9, 40, 60):
+    fl = capi.window_beam(lm, 10.0)
+    abl = np.stack([np.stack(capi.tqu_weights(*synthetic_cl(lm, seed=s, pol=True), fl, fl)) for s in range(37)])
+    slabs = torch.empty(3 * capi.slab_doubles(3 * n), dtype=torch.float64, device="cuda")
+    ctx.tqu_batched_slab(abl, slabs)
+ctx.slab_unpack(slabs, 3 * n, torch.empty(16 * capi.packed_size(3 * n), dtype=torch.float64, device="cuda"), capi.packed_size(3 * n))
+ctx.slab_unpack(slabs, 3 * n, outp, only_b=3)
+noise = np.zeros(capi.packed_size(3 * n)); noise[[capi.packed_index(i, i) for i in range(3 * n)]] = 5.0
+lk = Likelihood(ctx, slabs[2:], None, torch.from_numpy(noise).cuda(), 3 * n, foreground=np.ones(3 * n), c_stride=capi.SLAB)
+lk.calculate(np.random.RandomState(1).standard_normal((4, 3 * n)))
+lk.close()
 d_out = torch.empty(capi.packed_size(20), dtype=torch.float64, device="cuda")
 ctx.mask_matrix(out, n, np.arange(0, 160, 8), d_out)
 torch.cuda.synchronize()
