@@ -69,7 +69,7 @@ __host__ __device__ inline long long packedOffset(long long col) { return col * 
 // ------------------------------------------------------------------------------------------------
 constexpr int TT_ROWS = 128;
 constexpr int TT_COLS = 16;
-constexpr int TT_R = 8;
+constexpr int TT_R = 4;                                // columns per thread and pass (default variant)
 constexpr int TT_STATIC_STEPS = 1024;                 // slot i <-> k = TT_STATIC_STEPS - 1 - i
 constexpr int TT_STATIC_CHUNK = 8;
 
@@ -119,8 +119,8 @@ __device__ __forceinline__ void ttClenshawStatic(double (&x2)[R], double (&b1)[R
 #undef CMG_TT_CASE8
 #undef CMG_TT_CASE64
 
-template <bool STATIC>
-__global__ void __launch_bounds__(TT_ROWS)
+template <bool STATIC, int R, int MINB>
+__global__ void __launch_bounds__(TT_ROWS, MINB)
 legendreSeriesKernel(const __grid_constant__ TtStaticTable T, Geometry geo, const double* __restrict__ a, long long aStride,
                      const double* __restrict__ N0, const double* __restrict__ g0, int lmax, int entryChunk,
                      long long colBegin, long long colEnd, double* __restrict__ out, long long outStride)
@@ -151,11 +151,11 @@ legendreSeriesKernel(const __grid_constant__ TtStaticTable T, Geometry geo, cons
     const double xi = geo.nx[iLoad], yi = geo.ny[iLoad], zi = geo.nz[iLoad];
     const long long base = packedOffset(colBegin);
 
-    for(long long c = c0; c < c1; c += TT_R)
+    for(long long c = c0; c < c1; c += R)
     {
-        double x2[TT_R], b1[TT_R], b2[TT_R];
+        double x2[R], b1[R], b2[R];
 #pragma unroll
-        for(int r = 0; r < TT_R; ++r)
+        for(int r = 0; r < R; ++r)
         {
             const long long j = min(c + r, c1 - 1);
             // same association as the reference's ThreeVector product (include/three_vector.hpp:37)
@@ -167,16 +167,16 @@ legendreSeriesKernel(const __grid_constant__ TtStaticTable T, Geometry geo, cons
             b2[r] = 0.0;
         }
         if(STATIC)
-            ttClenshawStatic<TT_R>(x2, b1, b2, T, entryChunk);
+            ttClenshawStatic<R>(x2, b1, b2, T, entryChunk);
         else
         {
 #pragma unroll 4
             for(int k = lmax; k >= 0; --k)
-                ttStep<TT_R>(x2, b1, b2, ttTab[k]);
+                ttStep<R>(x2, b1, b2, ttTab[k]);
         }
         double* colPtr = out + (packedOffset(c) - base + i);
 #pragma unroll
-        for(int r = 0; r < TT_R; ++r)
+        for(int r = 0; r < R; ++r)
         {
             const long long j = c + r;
             if(j < c1 && i <= j)

@@ -389,6 +389,31 @@ def test_all_kernel_variants_agree(gpu_ctx, oracle_api):
         gpu_ctx.set_kernel_variant(0)
 
 
+def test_tt_kernel_variants_agree(gpu_ctx, oracle_api):
+    """TT kernel: columns-per-thread / occupancy variants (automatic choice switches at lmax = 128) and the
+    shared-memory-table kernel, against the oracle."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside = 8
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside))
+    gpu_ctx.set_pixels(nside, good)
+    n = gpu_ctx.npix
+    out = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
+    try:
+        for lmax in (20, 127, 128, 150):
+            cl = synthetic_cl(lmax)
+            a = capi.tt_weights(cl, capi.window_beam(lmax, 10.0))
+            want = oracle_api.cl_to_cmatrix(cl, nside, 10.0, good=good)
+            for v in (0, 1, 284, 248, 2216):
+                gpu_ctx.set_kernel_variant(v)
+                out.fill_(float("nan"))
+                gpu_ctx.legendre_series(a, out)
+                torch.cuda.synchronize()
+                assert np.abs(out.cpu().numpy() - want).max() <= REL_TOL * want[0], (lmax, v)
+    finally:
+        gpu_ctx.set_kernel_variant(0)
+
+
 def test_argument_errors_are_reported_not_crashed(gpu_ctx):
     torch = _torch()
     from cosmopp_b200 import capi

@@ -12,7 +12,8 @@ a = capi.tt_weights(synthetic_cl(lmax), capi.window_beam(lmax, 10.0))
 out = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
 peak = ctx.measure_fp64_peak()
 ref = None
-for v, name in ((0, "static table"), (1, "shared table")):
+VARS = [(int(x), "variant " + x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [(0, "static table"), (1, "shared table")]
+for v, name in VARS:
     ctx.set_kernel_variant(v)
     ctx.legendre_series(a, out); torch.cuda.synchronize()
     ts = []
