@@ -157,6 +157,12 @@ void CMatrixGenerator::setPixelWindow(long nSide, const std::vector<double>& tem
     g_windows[nSide] = w;
 }
 
+void cmgDropinPixelWindow(long nSide, int lMax, bool polarization, std::vector<double>& w)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    pixelWindow(nSide, lMax, polarization, w);
+}
+
 void CMatrixGenerator::clearPixelWindow(long nSide)
 {
     std::lock_guard<std::mutex> lock(g_mutex);

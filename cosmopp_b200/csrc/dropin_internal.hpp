@@ -4,6 +4,10 @@
 
 #include <cmg.h>
 
+#include <vector>
+
 cmg_ctx* cmgDropinContext();          // throws StandardException when no sm_100 GPU is usable
+// pixel window of nSide up to lMax as CMatrixGenerator resolves it (setPixelWindow / HEALPix data directory)
+void cmgDropinPixelWindow(long nSide, int lMax, bool polarization, std::vector<double>& w);
 
 #endif

@@ -1043,7 +1043,6 @@ tquBatchedMmaKernel(Geometry geo, const double* __restrict__ frag, DeviceTables 
 #pragma unroll
             for(int s = 0; s < 4; ++s)
                 acc[t][s][0] = acc[t][s][1] = 0.0;
-        const double* fb = frag + (static_cast<long long>(chunk) * nkk * 4) * 32 + lane;
         // B fragments of the whole chunk (nkk x 4 families x 32 lanes, <= the staging tile in size) are copied from L2
         // into this warp's staging region first, all loads in flight at once, so the L2 latency is paid once per chunk
         // instead of once per k-step; the region is reused for the transposed partners after the MMA loop.

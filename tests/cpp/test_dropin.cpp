@@ -14,6 +14,7 @@
 #include <c_matrix_generator.hpp>
 #include <exception_handler.hpp>
 #include <likelihood.hpp>
+#include <pixel_likelihood.hpp>
 #include <utils.hpp>
 
 static int failures = 0;
@@ -216,6 +217,47 @@ static void gpuTests(const std::string& dir)
         CMatrix negative(*noiseMatrix);
         for(int i = 0; i < negative.getNPix(); ++i) negative.element(i, i) = -1e6;
         EXPECT(throwsStandard([&] { Likelihood bad(*cMatrix, *fiducialMatrix, negative, good, foreground); }));
+    }
+    // sampler plug-in: parameters -> C_l -> device matrix -> device likelihood behind Math::LikelihoodFunction
+    {
+        struct Amplitude : public ClModel
+        {
+            std::vector<double> base;
+            void clTT(const double* params, int nParams, std::vector<double>& out)
+            {
+                for(size_t l = 0; l < out.size(); ++l)
+                    out[l] = params[0] * base[l] * std::pow((l + 1.0) / 10.0, nParams > 1 ? params[1] : 0.0);
+            }
+        } model;
+        model.base = clCopy;
+        const std::vector<double> maps = readDoubles(dir + "/maps.f64"), fore = readDoubles(dir + "/fore.f64");
+        const std::vector<double> t0(maps.begin(), maps.begin() + good.size());
+        std::vector<double> noForeground;
+        PixelLikelihoodTT plug(nSide, lMax, 10.0, good, *fiducialMatrix, *noiseMatrix, t0, noForeground, model);
+        Math::LikelihoodFunction* asSamplerSeesIt = &plug;
+        double p1[2] = {1.0, 0.0};
+        const double l1 = asSamplerSeesIt->calculate(p1, 2);
+        // same point through the classes of the reference's own test
+        Likelihood like(*cMatrix, *fiducialMatrix, *noiseMatrix, good, noForeground);
+        double chi2 = 0, logDet = 0;
+        const double lRef = like.calculate(t0, chi2, logDet);
+        EXPECT(std::fabs(l1 - lRef) <= 1e-10 * std::fabs(lRef));
+        EXPECT(std::fabs(plug.lastChi2() - chi2) <= 1e-10 * chi2);
+        // a batch of proposals equals the points one by one
+        double pts[6] = {1.0, 0.0, 1.3, 0.05, 0.7, -0.1}, batch[3];
+        plug.calculateBatch(pts, 2, 3, batch);
+        std::FILE* f = std::fopen((dir + "/plug.txt").c_str(), "w");
+        for(int k = 0; k < 3; ++k)
+        {
+            const double one = plug.calculate(pts + 2 * k, 2);
+            EXPECT(std::fabs(one - batch[k]) <= 1e-10 * std::fabs(one));
+            std::fprintf(f, "%.17g %.17g %.17g\n", pts[2 * k], pts[2 * k + 1], batch[k]);
+        }
+        std::fclose(f);
+        EXPECT(std::fabs(batch[0] - l1) <= 1e-10 * std::fabs(l1) && batch[1] != batch[0]);
+        PixelLikelihoodTT plugF(nSide, lMax, 10.0, good, *fiducialMatrix, *noiseMatrix, t0, fore, model);
+        Likelihood likeF(*cMatrix, *fiducialMatrix, *noiseMatrix, good, fore);
+        EXPECT(std::fabs(plugF.calculate(p1, 2) - likeF.calculate(t0, chi2, logDet)) <= 1e-10 * std::fabs(lRef));
     }
     delete cMatrix;
     delete fiducialMatrix;

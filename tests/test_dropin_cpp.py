@@ -110,6 +110,15 @@ def test_cpp_dropin_generators_match_oracle(dropin_binary, tmp_path, oracle_api)
         assert abs(got[k, 2] - (chi2 - tCf * tCf / fCf)) <= 1e-9 * chi2
         assert abs(got[k, 3] - (logdet + np.log(fCf / ng))) <= 1e-9 * abs(logdet)
 
+    # the sampler plug-in's batch: C_l = A * base * ((l+1)/10)^tilt through the oracle's generator and numpy
+    F = oracle_api.unpack_symmetric(oracle_api.fiducial_matrix(tt, nside, lmax, 10.0, good=good), ng)
+    N = oracle_api.unpack_symmetric(oracle_api.mask_matrix(oracle_api.noise_matrix(nside, 1e-2), good), ng)
+    for amp, tilt, got_like in np.loadtxt(str(tmp_path / "plug.txt")):
+        cl_k = amp * tt[:lmax + 1] * ((np.arange(lmax + 1) + 1.0) / 10.0) ** tilt
+        Sk = oracle_api.unpack_symmetric(oracle_api.cl_to_cmatrix(cl_k, nside, 10.0, good=good), ng) + F + N
+        want_like = maps[0] @ np.linalg.solve(Sk, maps[0]) + np.linalg.slogdet(Sk)[1] + 29677.0566
+        assert abs(got_like - want_like) <= 1e-9 * abs(want_like)
+
     n, c, _ = read_cmatrix(str(tmp_path / "c.dat"))
     want = oracle_api.cl_to_cmatrix(tt[:lmax + 1], nside, 10.0, good=good)
     assert n == len(good) and np.abs(c - want).max() <= 1e-11 * want[0]
