@@ -370,21 +370,23 @@ def test_batched_slab_dmma_path(gpu_ctx, oracle_api):
 
 
 def test_all_kernel_variants_agree(gpu_ctx, oracle_api):
-    """Static-table and shared-memory-table kernels, all column counts: same matrix to rounding."""
+    """Static-table and shared-memory-table kernels, all column counts: same matrix to rounding, on a full sky (whole
+    tiles) and on a masked sky (ragged last tiles)."""
     torch = _torch()
     from cosmopp_b200 import capi
     nside, lmax = 8, 33
-    gpu_ctx.set_pixels(nside)
-    n = gpu_ctx.npix
     f = capi.window_beam(lmax, 10.0)
     spectra = synthetic_cl(lmax, pol=True)
     a = capi.tqu_weights(*spectra, f, f)
-    want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
     try:
-        for v in (22, 42, 81, 114, 122, 123, 124, 142):
-            gpu_ctx.set_kernel_variant(v)
-            got = _whole_tqu(gpu_ctx, a, n).cpu().numpy()
-            _assert_tqu_close(got, want, n)
+        for good in (None, oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside))):
+            gpu_ctx.set_pixels(nside, good)
+            n = gpu_ctx.npix
+            want = oracle_api.tqu_matrix(*spectra, nside, 10.0, good=good)
+            for v in (22, 42, 81, 114, 122, 123, 124, 142):
+                gpu_ctx.set_kernel_variant(v)
+                got = _whole_tqu(gpu_ctx, a, n).cpu().numpy()
+                _assert_tqu_close(got, want, n)
     finally:
         gpu_ctx.set_kernel_variant(0)
 

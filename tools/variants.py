@@ -18,7 +18,7 @@ lay = ctx.tqu_layout_single(out)
 peak = ctx.measure_fp64_peak()
 ref = None
 pairs = n * (n + 1) // 2
-for v in (22, 42, 81, 114, 122, 123, 124, 142):
+for v in ([int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else (22, 42, 81, 114, 122, 123, 124, 142)):
     ctx.set_kernel_variant(v)
     out.fill_(float("nan"))
     ctx.tqu(*a, lay); torch.cuda.synchronize()
