@@ -72,3 +72,17 @@ def tqu_entries_held(npix, bounds, rank):
     a0, a1 = bounds[rank], bounds[rank + 1]
     pairs = pairs_in_block(a0, a1)
     return 9 * pairs - 3 * (a1 - a0)
+
+
+def batch_partition(n_batch, n_parts, slab=16):
+    """Batched mode shards along the batch axis (each GPU regenerates its share of the C_l proposals; no exchange):
+    boundaries b[0..n_parts] in batch elements, interior boundaries on slab multiples so that no slab of
+    cmg_tqu_batched_slab straddles two ranks."""
+    if n_parts < 1 or n_batch < 0:
+        raise ValueError("n_parts must be >= 1 and n_batch >= 0")
+    slabs = (n_batch + slab - 1) // slab
+    b = [0]
+    for k in range(1, n_parts):
+        b.append(min(n_batch, slab * ((slabs * k) // n_parts)))
+    b.append(n_batch)
+    return b

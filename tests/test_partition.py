@@ -82,3 +82,13 @@ def test_two_rank_planning_over_gloo():
     assert rows[:, 2].sum() == partition.packed_size(3 * npix)               # strips tile the packed triangle
     assert rows[0, 3] == 0 and rows[1, 3] > 0                                # only the right-hand rank keeps an outbox
     assert tmax == 2.0
+
+
+@pytest.mark.parametrize("n_batch,parts", [(1024, 8), (1000, 8), (37, 2), (5, 4), (0, 3), (16, 1)])
+def test_batch_partition_is_slab_aligned_and_complete(n_batch, parts):
+    b = partition.batch_partition(n_batch, parts)
+    assert b[0] == 0 and b[-1] == n_batch and len(b) == parts + 1
+    assert all(x <= y for x, y in zip(b, b[1:]))
+    assert all(x % 16 == 0 for x in b[1:-1])
+    sizes = [y - x for x, y in zip(b, b[1:])]
+    assert max(sizes) - min(sizes) <= 16 + 15          # balanced to one slab (plus the ragged last one)
