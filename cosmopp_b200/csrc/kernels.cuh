@@ -1191,7 +1191,8 @@ struct M2Shape
     static constexpr int CHUNK = NKK * 2 * 32 * 2;                       // doubles of weight fragments per chunk and pass
     static constexpr int PHI = 2 * M2_PAIRS * LD;
     static constexpr int LOOP = M2_RING * CHUNK;
-    static constexpr int X = PHI > LOOP ? PHI : LOOP;                    // Phi is dead once the fragments are loaded
+    static constexpr int X = PHI + LOOP;                                 // ring and Phi side by side: the first weight
+                                                                         // fragments travel while phase A computes
     static constexpr size_t BYTES = sizeof(double) * (X + M2_PAIRS * 4 + 16 * M2_T + 4 * (KP + 1) + 1 + 2 * M2_RING);
 };
 
@@ -1318,6 +1319,19 @@ __device__ __forceinline__ void slabBody(double* smem, const Geometry& geo, cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    double* ring = sX + S::PHI;
+    const int nChunks = (nBatch + M2_BC - 1) / M2_BC;
+    const double* fragPass = frag + static_cast<long long>(PASS) * nChunks * S::CHUNK;
+    constexpr unsigned chunkBytes = S::CHUNK * sizeof(double);
+    if(tid == M2_THREADS - 1)                                      // a thread with no phase-A work
+    {
+        for(int k = 0; k < M2_RING && k < nChunks; ++k)
+        {
+            mbarExpectTx(bFull + 8 * k, chunkBytes);
+            bulkLoad(smemAddr(ring + k * S::CHUNK), fragPass + static_cast<long long>(k) * S::CHUNK, chunkBytes, bFull + 8 * k);
+        }
+    }
 
     // ---- A) basis values of this pass's two families (threads 0..127) and the rotation factors (threads 128..191).
     //      pair p: row il = p % M2_T, column jl = p / M2_T
@@ -1449,21 +1463,6 @@ __device__ __forceinline__ void slabBody(double* smem, const Geometry& geo, cons
     const long long eQt = (packedOffset(npix + min(i, npix - 1)) + j) * CMG_SLAB + 4 * fc;        // (T_j, Q_i)
     const long long eUt = (packedOffset(2 * npix + min(i, npix - 1)) + j) * CMG_SLAB + 4 * fc;    // (T_j, U_i); + npix: (Q_j, U_i)
     const long long rowN = npix * CMG_SLAB;
-    __syncthreads();                                               // Phi is dead: its storage becomes the weight ring
-
-    double* ring = sX;
-    const int nChunks = (nBatch + M2_BC - 1) / M2_BC;
-    const double* fragPass = frag + static_cast<long long>(PASS) * nChunks * S::CHUNK;
-    constexpr unsigned chunkBytes = S::CHUNK * sizeof(double);
-    if(tid == 0)
-    {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses to Phi before async writes
-        for(int k = 0; k < M2_RING && k < nChunks; ++k)
-        {
-            mbarExpectTx(bFull + 8 * k, chunkBytes);
-            bulkLoad(smemAddr(ring + k * S::CHUNK), fragPass + static_cast<long long>(k) * S::CHUNK, chunkBytes, bFull + 8 * k);
-        }
-    }
 
     double* slab = out;
 #pragma unroll 1
