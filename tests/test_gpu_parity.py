@@ -369,6 +369,43 @@ def test_batched_slab_dmma_path(gpu_ctx, oracle_api):
         gpu_ctx.tqu_batched_slab(np.zeros((2, 4, 65)), slabs)      # lmax = 64: refused, not silently rerouted
 
 
+def test_batched_slab_at_config4_shape(gpu_ctx):
+    """BASELINE config 4's shape (full-sky Nside=16, lmax=47), two slabs with a ragged second one: every element of the
+    slab output against the single-matrix kernel (itself checked against the oracle at this size in
+    test_full_size_*), all 42.5 M entries, to 1e-11 of the block diagonal; plus linearity in the weights."""
+    torch = _torch()
+    from cosmopp_b200 import capi
+    nside, lmax, nb = 16, 47, 19
+    gpu_ctx.set_pixels(nside)
+    n = gpu_ctx.npix
+    packed = capi.packed_size(3 * n)
+    f = capi.window_beam(lmax, 10.0)
+    ws = [capi.tqu_weights(*synthetic_cl(lmax, seed=12345 + b, pol=True), f, f) for b in range(nb)]
+    ab = np.stack([np.stack(w) for w in ws])
+    ab[nb - 1] = 0.5 * ab[0] - 2.0 * ab[1]                       # linear combination: its matrix must be the same combination
+    slabs = torch.empty(2 * capi.slab_doubles(3 * n), dtype=torch.float64, device="cuda")
+    gpu_ctx.tqu_batched_slab(ab, slabs)
+    one = torch.empty(packed, dtype=torch.float64, device="cuda")
+    el = torch.empty(packed, dtype=torch.float64, device="cuda")
+    lay = gpu_ctx.tqu_layout_single(one)
+    i_tt, i_qq = 0, capi.packed_index(n, n)
+    keep = {}
+    for b in (0, 1, 7, 16, 17):
+        gpu_ctx.tqu(*[np.ascontiguousarray(x) for x in ab[b]], lay)
+        gpu_ctx.slab_unpack(slabs[(b // 16) * capi.slab_doubles(3 * n):], 3 * n, el, only_b=b % 16)
+        torch.cuda.synchronize()
+        dT, dP = float(one[i_tt]), float(one[i_qq])
+        assert dT > 0 and dP > 0
+        # conservative scale: the smaller (polarization) diagonal for every entry
+        assert float((el - one).abs().max()) <= REL_TOL * min(dT, dP)
+        if b in (0, 1):
+            keep[b] = el.clone()
+    gpu_ctx.slab_unpack(slabs[capi.slab_doubles(3 * n):], 3 * n, el, only_b=(nb - 1) % 16)
+    torch.cuda.synchronize()
+    combo = 0.5 * keep[0] - 2.0 * keep[1]
+    assert float((el - combo).abs().max()) <= 1e-11 * float(keep[0][i_tt])
+
+
 def test_all_kernel_variants_agree(gpu_ctx, oracle_api):
     """Static-table and shared-memory-table kernels, all column counts: same matrix to rounding, on a full sky (whole
     tiles) and on a masked sky (ragged last tiles)."""
