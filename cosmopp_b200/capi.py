@@ -99,6 +99,12 @@ _SIGNATURES = {
     "cmg_like_create": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, ctypes.POINTER(_vp)]),
     "cmg_like_calculate": (ctypes.c_int, [_vp, _vp, _i64, _vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_like_destroy": (None, [_vp]),
+    "cmg_cmatrix_file_create": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64, ctypes.POINTER(_vp)]),
+    "cmg_cmatrix_file_write_device": (ctypes.c_int, [_vp, _i64, _vp, _i64]),
+    "cmg_cmatrix_file_open": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_i64), ctypes.POINTER(_vp)]),
+    "cmg_cmatrix_file_read_device": (ctypes.c_int, [_vp, _i64, _vp, _i64]),
+    "cmg_cmatrix_file_comment": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64]),
+    "cmg_cmatrix_file_close": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "cmg_measure_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "cmg_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -314,6 +320,32 @@ class Context:
 
     def slab_unpack(self, d_slab, dim, d_out, out_stride=0, n_live=SLAB, only_b=-1):
         self._check(self._L.cmg_slab_unpack(self._h, _p(d_slab), dim, n_live, only_b, _p(d_out), out_stride))
+
+    # ---- CMatrix files straight from / to device memory (reference binary format)
+    def write_cmatrix_file(self, path, n_pix, pieces, comment=""):
+        """pieces: iterable of (first_element, device_buffer, count) in any order"""
+        h = _vp()
+        self._check(self._L.cmg_cmatrix_file_create(self._h, path.encode(), int(n_pix), ctypes.byref(h)))
+        try:
+            for first, d_src, count in pieces:
+                self._check(self._L.cmg_cmatrix_file_write_device(h, int(first), _p(d_src), int(count)))
+        finally:
+            self._check(self._L.cmg_cmatrix_file_close(h, comment.encode()))
+
+    def read_cmatrix_file(self, path, d_dst=None, first=0, count=None):
+        """-> (n_pix, comment); fills d_dst with elements [first, first + count) when given"""
+        h = _vp()
+        n = _i64()
+        self._check(self._L.cmg_cmatrix_file_open(self._h, path.encode(), ctypes.byref(n), ctypes.byref(h)))
+        try:
+            if d_dst is not None:
+                total = n.value * (n.value + 1) // 2
+                self._check(self._L.cmg_cmatrix_file_read_device(h, int(first), _p(d_dst), int(total - first if count is None else count)))
+            buf = ctypes.create_string_buffer(4096)
+            self._check(self._L.cmg_cmatrix_file_comment(h, buf, 4096))
+        finally:
+            self._L.cmg_cmatrix_file_close(h, None)
+        return n.value, buf.value.decode()
 
     def cl_to_cmatrix_pol(self, ctt, cte, cee, cbb, fwhm, out_host, pixwinT=None, pixwinP=None):
         ctt, cte, cee, cbb = map(_f64, (ctt, cte, cee, cbb))

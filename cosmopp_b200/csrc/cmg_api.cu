@@ -8,6 +8,10 @@
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cublas_v2.h>
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
@@ -1247,6 +1251,208 @@ cmg_status cmg_like_calculate(cmg_like* L, const double* t, int64_t nMaps, doubl
     }
     if(logDet) *logDet = ld;
     return CMG_OK;
+}
+
+// ---------------------------------------------------------------- CMatrix files straight from / to device memory
+// binary layout of reference source/c_matrix.cpp:41-104: int32 nPix, nPix (nPix + 1) / 2 doubles, int32 length, comment.
+// Pieces (a rank's packed strip, a sub-range) are written at their element offset with pwrite, through two pinned
+// bounce buffers so that the device-to-host copy of piece k+1 overlaps the file write of piece k.
+
+struct cmg_file
+{
+    cmg_ctx* ctx = nullptr;
+    int fd = -1;
+    int64_t nPix = 0;
+    int64_t total = 0;              // packed doubles
+    bool writing = false;
+    double* bounce[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int64_t bounceDoubles = 0;
+};
+
+namespace
+{
+const int64_t kBounceDoubles = int64_t(1) << 22;      // 32 MiB per buffer
+
+cmg_status fileBuffers(cmg_file* f)
+{
+    cmg_ctx* ctx = f->ctx;
+    for(int k = 0; k < 2; ++k)
+    {
+        CMG_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&f->bounce[k]), sizeof(double) * kBounceDoubles));
+        CMG_CUDA(ctx, cudaEventCreateWithFlags(&f->done[k], cudaEventDisableTiming));
+    }
+    f->bounceDoubles = kBounceDoubles;
+    return CMG_OK;
+}
+
+void fileRelease(cmg_file* f)
+{
+    if(!f) return;
+    for(int k = 0; k < 2; ++k)
+    {
+        if(f->bounce[k]) cudaFreeHost(f->bounce[k]);
+        if(f->done[k]) cudaEventDestroy(f->done[k]);
+    }
+    if(f->fd >= 0) ::close(f->fd);
+    delete f;
+}
+
+bool pwriteAll(int fd, const void* buf, size_t bytes, off_t off)
+{
+    const char* p = static_cast<const char*>(buf);
+    while(bytes > 0)
+    {
+        const ssize_t w = ::pwrite(fd, p, bytes, off);
+        if(w <= 0) return false;
+        p += w; off += w; bytes -= static_cast<size_t>(w);
+    }
+    return true;
+}
+
+bool preadAll(int fd, void* buf, size_t bytes, off_t off)
+{
+    char* p = static_cast<char*>(buf);
+    while(bytes > 0)
+    {
+        const ssize_t r = ::pread(fd, p, bytes, off);
+        if(r <= 0) return false;
+        p += r; off += r; bytes -= static_cast<size_t>(r);
+    }
+    return true;
+}
+}
+
+cmg_status cmg_cmatrix_file_create(cmg_ctx* ctx, const char* path, int64_t nPix, cmg_file** out)
+{
+    if(!ctx || !out) return CMG_EINVAL;
+    *out = nullptr;
+    if(!path || nPix < 1 || nPix > 2147483647LL) return fail(ctx, CMG_EINVAL, "bad file arguments (the header stores nPix as int32)");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_file* f = new(std::nothrow) cmg_file;
+    if(!f) return fail(ctx, CMG_ENOMEM, "out of host memory");
+    f->ctx = ctx; f->nPix = nPix; f->total = cmg_packed_size(nPix); f->writing = true;
+    f->fd = ::open(path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    const int32_t n32 = static_cast<int32_t>(nPix);
+    if(f->fd < 0 || !pwriteAll(f->fd, &n32, sizeof(n32), 0) || ::ftruncate(f->fd, static_cast<off_t>(4 + 8 * f->total)) != 0)
+    {
+        fileRelease(f);
+        return fail(ctx, CMG_EINVAL, std::string("Cannot write into output file ") + path + ".");      // text of source/c_matrix.cpp:86
+    }
+    const cmg_status s = fileBuffers(f);
+    if(s != CMG_OK) { fileRelease(f); return s; }
+    *out = f;
+    return CMG_OK;
+}
+
+cmg_status cmg_cmatrix_file_open(cmg_ctx* ctx, const char* path, int64_t* nPix, cmg_file** out)
+{
+    if(!ctx || !out) return CMG_EINVAL;
+    *out = nullptr;
+    if(!path) return fail(ctx, CMG_EINVAL, "null path");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_file* f = new(std::nothrow) cmg_file;
+    if(!f) return fail(ctx, CMG_ENOMEM, "out of host memory");
+    f->ctx = ctx;
+    f->fd = ::open(path, O_RDONLY);
+    int32_t n32 = 0;
+    struct stat st;
+    if(f->fd < 0 || !preadAll(f->fd, &n32, sizeof(n32), 0) || n32 < 1 || ::fstat(f->fd, &st) != 0 ||
+       st.st_size < static_cast<off_t>(4 + 8 * cmg_packed_size(n32) + 4))
+    {
+        fileRelease(f);
+        return fail(ctx, CMG_EINVAL, std::string("Covariance matrix file ") + path + " cannot be read.");  // source/c_matrix.cpp:47-54
+    }
+    f->nPix = n32; f->total = cmg_packed_size(n32);
+    const cmg_status s = fileBuffers(f);
+    if(s != CMG_OK) { fileRelease(f); return s; }
+    if(nPix) *nPix = n32;
+    *out = f;
+    return CMG_OK;
+}
+
+cmg_status cmg_cmatrix_file_write_device(cmg_file* f, int64_t firstElement, const double* dSrc, int64_t count)
+{
+    if(!f || !f->ctx) return CMG_EINVAL;
+    cmg_ctx* ctx = f->ctx;
+    if(!f->writing || !dSrc || firstElement < 0 || count < 0 || firstElement + count > f->total)
+        return fail(ctx, CMG_EINVAL, "piece outside the packed triangle (or file opened for reading)");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nPieces = (count + f->bounceDoubles - 1) / f->bounceDoubles;
+    auto pieceLen = [&](int64_t k) { return std::min(f->bounceDoubles, count - k * f->bounceDoubles); };
+    if(nPieces > 0)
+    {
+        CMG_CUDA(ctx, cudaMemcpyAsync(f->bounce[0], dSrc, sizeof(double) * pieceLen(0), cudaMemcpyDeviceToHost, ctx->stream));
+        CMG_CUDA(ctx, cudaEventRecord(f->done[0], ctx->stream));
+    }
+    for(int64_t k = 0; k < nPieces; ++k)
+    {
+        if(k + 1 < nPieces)
+        {
+            CMG_CUDA(ctx, cudaMemcpyAsync(f->bounce[(k + 1) & 1], dSrc + (k + 1) * f->bounceDoubles, sizeof(double) * pieceLen(k + 1),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            CMG_CUDA(ctx, cudaEventRecord(f->done[(k + 1) & 1], ctx->stream));
+        }
+        CMG_CUDA(ctx, cudaEventSynchronize(f->done[k & 1]));
+        if(!pwriteAll(f->fd, f->bounce[k & 1], sizeof(double) * pieceLen(k), static_cast<off_t>(4 + 8 * (firstElement + k * f->bounceDoubles))))
+            return fail(ctx, CMG_EINVAL, "write to the covariance matrix file failed");
+    }
+    return CMG_OK;
+}
+
+cmg_status cmg_cmatrix_file_read_device(cmg_file* f, int64_t firstElement, double* dDst, int64_t count)
+{
+    if(!f || !f->ctx) return CMG_EINVAL;
+    cmg_ctx* ctx = f->ctx;
+    if(f->writing || !dDst || firstElement < 0 || count < 0 || firstElement + count > f->total)
+        return fail(ctx, CMG_EINVAL, "piece outside the packed triangle (or file opened for writing)");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nPieces = (count + f->bounceDoubles - 1) / f->bounceDoubles;
+    for(int64_t k = 0; k < nPieces; ++k)
+    {
+        const int64_t len = std::min(f->bounceDoubles, count - k * f->bounceDoubles);
+        if(k >= 2)
+            CMG_CUDA(ctx, cudaEventSynchronize(f->done[k & 1]));                 // the copy out of this buffer has finished
+        if(!preadAll(f->fd, f->bounce[k & 1], sizeof(double) * len, static_cast<off_t>(4 + 8 * (firstElement + k * f->bounceDoubles))))
+            return fail(ctx, CMG_EINVAL, "read from the covariance matrix file failed");
+        CMG_CUDA(ctx, cudaMemcpyAsync(dDst + k * f->bounceDoubles, f->bounce[k & 1], sizeof(double) * len, cudaMemcpyHostToDevice, ctx->stream));
+        CMG_CUDA(ctx, cudaEventRecord(f->done[k & 1], ctx->stream));
+    }
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CMG_OK;
+}
+
+cmg_status cmg_cmatrix_file_comment(cmg_file* f, char* buffer, int64_t capacity)
+{
+    if(!f || !f->ctx) return CMG_EINVAL;
+    cmg_ctx* ctx = f->ctx;
+    if(f->writing || !buffer || capacity < 1) return fail(ctx, CMG_EINVAL, "bad comment buffer");
+    int32_t len = 0;
+    const off_t at = static_cast<off_t>(4 + 8 * f->total);
+    if(!preadAll(f->fd, &len, sizeof(len), at) || len < 0)
+        return fail(ctx, CMG_EINVAL, "cannot read the comment");
+    const int64_t take = std::min<int64_t>(len, capacity - 1);
+    if(take > 0 && !preadAll(f->fd, buffer, static_cast<size_t>(take), at + 4))
+        return fail(ctx, CMG_EINVAL, "cannot read the comment");
+    buffer[take] = 0;
+    return CMG_OK;
+}
+
+cmg_status cmg_cmatrix_file_close(cmg_file* f, const char* comment)
+{
+    if(!f) return CMG_EINVAL;
+    cmg_ctx* ctx = f->ctx;
+    cmg_status s = CMG_OK;
+    if(f->writing)
+    {
+        const std::string c = comment ? comment : "";
+        const int32_t len = static_cast<int32_t>(c.size());
+        const off_t at = static_cast<off_t>(4 + 8 * f->total);
+        if(!pwriteAll(f->fd, &len, sizeof(len), at) || (len > 0 && !pwriteAll(f->fd, c.data(), c.size(), at + 4)))
+            s = fail(ctx, CMG_EINVAL, "write to the covariance matrix file failed");
+    }
+    fileRelease(f);
+    return s;
 }
 
 // ---------------------------------------------------------------- measurement

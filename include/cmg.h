@@ -242,6 +242,21 @@ cmg_status cmg_like_create(cmg_ctx* ctx, const double* d_c, int64_t c_stride, co
 cmg_status cmg_like_calculate(cmg_like* like, const double* t, int64_t n_maps, double* chi2, double* log_det);
 void cmg_like_destroy(cmg_like* like);
 
+/* ---------------------------------------------------------------- CMatrix files from / to device memory ---- */
+
+/* The reference's binary CMatrix file (source/c_matrix.cpp:41-104: int32 nPix, packed doubles, int32 length, comment)
+ * written from and read into DEVICE buffers piece by piece, so that a matrix that lives sharded on the GPU(s) (a rank's
+ * packed strip is one contiguous element range) never has to be assembled in host memory.  Pieces may arrive in any order;
+ * copies go through pinned bounce buffers and overlap the file I/O.  Elements that no piece covers read back as 0. */
+typedef struct cmg_file cmg_file;
+cmg_status cmg_cmatrix_file_create(cmg_ctx* ctx, const char* path, int64_t n_pix, cmg_file** out);
+cmg_status cmg_cmatrix_file_write_device(cmg_file* file, int64_t first_element, const double* d_src, int64_t count);
+cmg_status cmg_cmatrix_file_open(cmg_ctx* ctx, const char* path, int64_t* n_pix, cmg_file** out);
+cmg_status cmg_cmatrix_file_read_device(cmg_file* file, int64_t first_element, double* d_dst, int64_t count);
+cmg_status cmg_cmatrix_file_comment(cmg_file* file, char* buffer, int64_t capacity);
+/* writes the comment (NULL = empty) when the file was created for writing; releases the handle either way */
+cmg_status cmg_cmatrix_file_close(cmg_file* file, const char* comment);
+
 /* ---------------------------------------------------------------- measurement --------------- */
 
 /* dependent-free DFMA microbenchmark: achieved FP64 TFLOP/s on this GPU (the roofline denominator) */

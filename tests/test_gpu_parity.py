@@ -406,6 +406,49 @@ def test_batched_slab_at_config4_shape(gpu_ctx):
     assert float((el - combo).abs().max()) <= 1e-11 * float(keep[0][i_tt])
 
 
+def test_cmatrix_file_streamed_from_device_shards(gpu_ctx, oracle_api, tmp_path):
+    """The reference's binary CMatrix file written piece by piece from device-resident shards (three ranks' TT column
+    blocks, out of order) and read back into device memory: byte-identical to the reference's own writer."""
+    torch = _torch()
+    import struct
+    from cosmopp_b200 import capi, partition
+    nside, lmax = 8, 20
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside))
+    gpu_ctx.set_pixels(nside, good)
+    n = gpu_ctx.npix
+    a = capi.tt_weights(synthetic_cl(lmax), capi.window_beam(lmax, 10.0))
+    whole = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
+    gpu_ctx.legendre_series(a, whole)
+    bounds = partition.column_partition(n, 3, align=16)
+    pieces = []
+    for r in (2, 0, 1):
+        a0, a1 = bounds[r], bounds[r + 1]
+        shard = torch.full((partition.tt_shard_size(a0, a1),), float("nan"), dtype=torch.float64, device="cuda")
+        gpu_ctx.legendre_series(a, shard, a0, a1)
+        pieces.append((partition.packed_size(a0), shard, shard.numel()))
+    path = str(tmp_path / "c.dat")
+    gpu_ctx.write_cmatrix_file(path, n, pieces, comment="streamed from shards")
+    torch.cuda.synchronize()
+    raw = open(path, "rb").read()
+    assert struct.unpack("<i", raw[:4])[0] == n
+    body = np.frombuffer(raw[4:4 + 8 * whole.numel()], dtype="<f8")
+    assert np.array_equal(body, whole.cpu().numpy())
+    assert raw[4 + 8 * whole.numel():] == struct.pack("<i", 20) + b"streamed from shards"
+    if oracle_api.have_ref():
+        oracle_api.ref_write_cmatrix(whole.cpu().numpy(), n, "streamed from shards", str(tmp_path / "ref.dat"), str(tmp_path / "ref.txt"))
+        assert open(str(tmp_path / "ref.dat"), "rb").read() == raw
+    back = torch.full((whole.numel(),), float("nan"), dtype=torch.float64, device="cuda")
+    n_read, comment = gpu_ctx.read_cmatrix_file(path, back)
+    assert n_read == n and comment == "streamed from shards" and torch.equal(back, whole)
+    part = torch.empty(100, dtype=torch.float64, device="cuda")
+    gpu_ctx.read_cmatrix_file(path, part, first=1234, count=100)
+    assert torch.equal(part, whole[1234:1334])
+    with pytest.raises(Exception):
+        gpu_ctx.read_cmatrix_file(str(tmp_path / "missing.dat"), back)
+    with pytest.raises(Exception):
+        gpu_ctx.write_cmatrix_file(path, n, [(whole.numel() - 5, whole, 10)])      # piece beyond the triangle
+
+
 def test_all_kernel_variants_agree(gpu_ctx, oracle_api):
     """Static-table and shared-memory-table kernels, all column counts: same matrix to rounding, on a full sky (whole
     tiles) and on a masked sky (ragged last tiles)."""
