@@ -205,22 +205,17 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
         entryChunk = (cmg::TT_STATIC_STEPS - 1 - lmax) / cmg::TT_STATIC_CHUNK;
     }
     KernelTimer timer(ctx);
-    // TT variants (ncu, profiles/r1_kernel_history.md): ptxas issues each column's two dependent DFMAs back to back and loads
-    // every step's coefficients (LDCU) right before their use, so a warp serialises on the FP64 latency (~20 cycles);
-    // what hides it is resident warps, not columns per thread.  R = 2 columns, 16 CTAs/SM (32 registers, 64 warps) is
-    // best for long series; for short ones the per-pass prologue (geometry loads, stores) favours R = 4, 8 CTAs/SM.
-    // Codes: 0 = automatic, 1 = shared-memory table, 284 = R 8 / 4 CTAs (the round's first version), 248, 2216.
+    // TT variants: 0 = R 8 columns per thread and pass, 4 CTAs/SM (with the rolled chunk loop the kernel is insensitive to
+    // occupancy: 87.3-88.1 % of the FP64 peak for every (R, CTAs/SM) tried at Nside=64, profiles/r1_kernel_history.md);
+    // 1 = shared-memory table; 248 and 2216 stay selectable for the variant test.
 #define CMG_TT(R_, M_) cmg::legendreSeriesKernel<true, R_, M_><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entryChunk, colBegin, colEnd, dOut, outStride)
     if(useStatic)
     {
-        int v = ctx->tquVariant;
-        if(v != 284 && v != 248 && v != 2216)
-            v = lmax >= 128 ? 2216 : 248;
-        switch(v)
+        switch(ctx->tquVariant)
         {
-            case 284: CMG_TT(8, 4); break;
             case 2216: CMG_TT(2, 16); break;
-            default: CMG_TT(4, 8); break;
+            case 248: CMG_TT(4, 8); break;
+            default: CMG_TT(8, 4); break;
         }
     }
 #undef CMG_TT

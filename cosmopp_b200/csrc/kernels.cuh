@@ -92,32 +92,26 @@ __device__ __forceinline__ void ttStep(double (&x2)[R], double (&b1)[R], double 
     }
 }
 
-template <int R, int C>
-__device__ __forceinline__ void ttStaticChunk(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T)
+template <int R>
+__device__ __forceinline__ void ttStaticChunkAt(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T, int first)
 {
 #pragma unroll
     for(int u = 0; u < TT_STATIC_CHUNK; ++u)
-        ttStep<R>(x2, b1, b2, T.s[C * TT_STATIC_CHUNK + u]);
+        ttStep<R>(x2, b1, b2, T.s[first + u]);
 }
 
-#define CMG_TT_CASE(c) case c: ttStaticChunk<R, c>(x2, b1, b2, T); [[fallthrough]];
-#define CMG_TT_CASE8(b) CMG_TT_CASE(b) CMG_TT_CASE(b + 1) CMG_TT_CASE(b + 2) CMG_TT_CASE(b + 3) CMG_TT_CASE(b + 4) CMG_TT_CASE(b + 5) CMG_TT_CASE(b + 6) CMG_TT_CASE(b + 7)
-#define CMG_TT_CASE64(b) CMG_TT_CASE8(b) CMG_TT_CASE8(b + 8) CMG_TT_CASE8(b + 16) CMG_TT_CASE8(b + 24) CMG_TT_CASE8(b + 32) CMG_TT_CASE8(b + 40) CMG_TT_CASE8(b + 48) CMG_TT_CASE8(b + 56)
-
+// A rolled loop over 8-step chunks with a warp-uniform chunk counter: ptxas addresses the table as c[0x0][UR + imm]
+// (LDCU with a uniform-register base), rotates three uniform registers so that every coefficient is loaded two groups
+// of DFMAs ahead of its use, and interleaves the R columns (all inner products, then all outer ones).  The earlier
+// fully unrolled body entered through a 128-way switch got none of this: one uniform register for every load, issued
+// right in front of its consumer, dependent DFMA pairs back to back, and 49 KB of straight-line code.
 template <int R>
 __device__ __forceinline__ void ttClenshawStatic(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T, int entryChunk)
 {
-    static_assert(TT_STATIC_STEPS == 128 * TT_STATIC_CHUNK, "case list below covers 128 chunks");
-    switch(entryChunk)
-    {
-        CMG_TT_CASE64(0) CMG_TT_CASE64(64)
-        default: break;
-    }
+#pragma unroll 1
+    for(int c = entryChunk; c < TT_STATIC_STEPS / TT_STATIC_CHUNK; ++c)
+        ttStaticChunkAt<R>(x2, b1, b2, T, c * TT_STATIC_CHUNK);
 }
-
-#undef CMG_TT_CASE
-#undef CMG_TT_CASE8
-#undef CMG_TT_CASE64
 
 template <bool STATIC, int R, int MINB>
 __global__ void __launch_bounds__(TT_ROWS, MINB)
@@ -269,27 +263,22 @@ __device__ __forceinline__ void tquStepTT(TquState<R>& s, const double a, const 
     }
 }
 
-template <int R, int C>
-__device__ __forceinline__ void tquStaticChunk(TquState<R>& s, const TquStaticTable& T)
+template <int R>
+__device__ __forceinline__ void tquStaticChunkAt(TquState<R>& s, const TquStaticTable& T, int first)
 {
 #pragma unroll
     for(int u = 0; u < PQ_STATIC_CHUNK; ++u)
-        tquStep<R>(s, T.s[2 * (C * PQ_STATIC_CHUNK + u)], T.s[2 * (C * PQ_STATIC_CHUNK + u) + 1]);
+        tquStep<R>(s, T.s[2 * (first + u)], T.s[2 * (first + u) + 1]);
 }
 
-#define CMG_CASE(c) case c: tquStaticChunk<R, c>(s, T); [[fallthrough]];
-#define CMG_CASE5(b) CMG_CASE(b) CMG_CASE(b + 1) CMG_CASE(b + 2) CMG_CASE(b + 3) CMG_CASE(b + 4)
-
+// rolled loop over 8-step chunks with a warp-uniform counter (see ttClenshawStatic): LDCU c[0x0][UR + imm], coefficient
+// loads software-pipelined by ptxas, a 6 KB loop body instead of 137 KB of straight-line code behind a 55-way switch
 template <int R>
 __device__ __forceinline__ void tquClenshawStatic(TquState<R>& s, const TquStaticTable& T, int entryChunk)
 {
-    static_assert(PQ_STATIC_STEPS == 55 * PQ_STATIC_CHUNK, "case list below covers 55 chunks");
-    switch(entryChunk)
-    {
-        CMG_CASE5(0) CMG_CASE5(5) CMG_CASE5(10) CMG_CASE5(15) CMG_CASE5(20) CMG_CASE5(25)
-        CMG_CASE5(30) CMG_CASE5(35) CMG_CASE5(40) CMG_CASE5(45) CMG_CASE5(50)
-        default: break;
-    }
+#pragma unroll 1
+    for(int c = entryChunk; c < PQ_STATIC_STEPS / PQ_STATIC_CHUNK; ++c)
+        tquStaticChunkAt<R>(s, T, c * PQ_STATIC_CHUNK);
     const double4 tail = T.s[2 * PQ_STATIC_STEPS];
     tquStepTT<R>(s, tail.x, tail.y);
     tquStepTT<R>(s, tail.z, tail.w);
