@@ -194,7 +194,7 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
     const cmg::DeviceTables t = tablesOf(ctx);
     const bool useStatic = hostWeights && nBatch == 1 && lmax + 1 <= cmg::TT_STATIC_STEPS && ctx->tquVariant != 1;
     static thread_local cmg::TtStaticTable T;
-    int entryChunk = 0;
+    int entrySlot = 0;
     if(useStatic)
     {
         for(int i = 0; i < cmg::TT_STATIC_STEPS; ++i)
@@ -202,13 +202,18 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
             const int k = cmg::TT_STATIC_STEPS - 1 - i;
             T.s[i] = make_double2(k <= lmax ? hostWeights[k] * ctx->hostT0.N[k] : 0.0, -ctx->hostT0.g[k + 1]);
         }
-        entryChunk = (cmg::TT_STATIC_STEPS - 1 - lmax) / cmg::TT_STATIC_CHUNK;
+        // first slot with a non-zero weight.  The kernel walks single steps up to the next 8-step chunk boundary and whole
+        // chunks from there; single steps are slow (no software pipelining), so more than two of them cost more than
+        // starting at the boundary below and running the zero-weight slots (which leave the zero state untouched)
+        entrySlot = cmg::TT_STATIC_STEPS - 1 - lmax;
+        if(((cmg::TT_STATIC_CHUNK - entrySlot % cmg::TT_STATIC_CHUNK) % cmg::TT_STATIC_CHUNK) > 2)
+            entrySlot -= entrySlot % cmg::TT_STATIC_CHUNK;
     }
     KernelTimer timer(ctx);
     // TT variants: 0 = R 8 columns per thread and pass, 4 CTAs/SM (with the rolled chunk loop the kernel is insensitive to
     // occupancy: 87.3-88.1 % of the FP64 peak for every (R, CTAs/SM) tried at Nside=64, profiles/r1_kernel_history.md);
     // 1 = shared-memory table; 248 and 2216 stay selectable for the variant test.
-#define CMG_TT(R_, M_) cmg::legendreSeriesKernel<true, R_, M_><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entryChunk, colBegin, colEnd, dOut, outStride)
+#define CMG_TT(R_, M_) cmg::legendreSeriesKernel<true, R_, M_><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entrySlot, colBegin, colEnd, dOut, outStride)
     if(useStatic)
     {
         switch(ctx->tquVariant)
@@ -221,7 +226,7 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
 #undef CMG_TT
     else
         cmg::legendreSeriesKernel<false, cmg::TT_R, 8><<<grid, cmg::TT_ROWS, sizeof(double2) * (lmax + 1), ctx->stream>>>(
-            T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entryChunk, colBegin, colEnd, dOut, outStride);
+            T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entrySlot, colBegin, colEnd, dOut, outStride);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return timer.finish();
@@ -259,14 +264,14 @@ void fillStaticTable(const cmg_ctx* ctx, const double* att, const double* ate, c
 }
 
 template <int R, bool STATIC, int MINB>
-cmg_status launchTquVariant(cmg_ctx* ctx, const cmg::TquDynamicArgs& dyn, const cmg::TquStaticTable& T, int entryChunk,
+cmg_status launchTquVariant(cmg_ctx* ctx, const cmg::TquDynamicArgs& dyn, const cmg::TquStaticTable& T, int entrySlot,
                             const cmg::PartTable& P, dim3 grid, int64_t outStride, cudaStream_t stream = nullptr)
 {
     if(!stream) stream = ctx->stream;
     const size_t smem = tquSmemBytes(dyn.lmax, STATIC);
     auto kernel = cmg::tquKernel<R, STATIC, MINB>;
     CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kernel<<<grid, cmg::PQ_THREADS, smem, stream>>>(T, geometryOf(ctx), dyn, entryChunk, P, outStride);
+    kernel<<<grid, cmg::PQ_THREADS, smem, stream>>>(T, geometryOf(ctx), dyn, entrySlot, P, outStride);
     CMG_CUDA(ctx, cudaGetLastError());
     return CMG_OK;
 }
@@ -330,17 +335,18 @@ cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, 
         return fail(ctx, CMG_EINVAL, "static-table kernel needs host weights, one batch element and 2 <= lmax <= PQ_STATIC_LMAX");
 
     static thread_local cmg::TquStaticTable T;      // 28 KB: keep it off the stack
-    int entryChunk = 0;
+    int entrySlot = 0;
     if(variant >= 100)
     {
         fillStaticTable(ctx, hostWeights[0], hostWeights[1], hostWeights[2], hostWeights[3], lmax, T);
-        entryChunk = (cmg::PQ_STATIC_STEPS + 1 - lmax) / cmg::PQ_STATIC_CHUNK;
+        // chunk boundary at or below the first non-zero slot (a peeled single-step prologue measured slower for T,Q,U)
+        entrySlot = (cmg::PQ_STATIC_STEPS + 1 - lmax) / cmg::PQ_STATIC_CHUNK * cmg::PQ_STATIC_CHUNK;
     }
     KernelTimer timer(ctx);
     cmg_status s = CMG_OK;
     switch(variant)
     {
-#define CMG_V(code, R, ST, MB) case code: s = launchTquVariant<R, ST, MB>(ctx, dyn, T, entryChunk, P, grid, outStride); break;
+#define CMG_V(code, R, ST, MB) case code: s = launchTquVariant<R, ST, MB>(ctx, dyn, T, entrySlot, P, grid, outStride); break;
     CMG_V(22, 2, false, 2) CMG_V(42, 4, false, 2) CMG_V(81, 8, false, 1)
     CMG_V(114, 1, true, 4) CMG_V(122, 2, true, 2) CMG_V(123, 2, true, 3) CMG_V(124, 2, true, 4) CMG_V(142, 4, true, 2)
 #undef CMG_V
@@ -910,7 +916,7 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBat
             cmg::TquDynamicArgs dyn;
             dyn.a = ctx->dWeights; dyn.aStride = 0; dyn.tab = tablesOf(ctx); dyn.lmax = lmax;
             static thread_local cmg::TquStaticTable TB;
-            const int entryChunk = (cmg::PQ_STATIC_STEPS + 1 - lmax) / cmg::PQ_STATIC_CHUNK;
+            const int entrySlot = (cmg::PQ_STATIC_STEPS + 1 - lmax) / cmg::PQ_STATIC_CHUNK * cmg::PQ_STATIC_CHUNK;
             KernelTimer timerS(ctx);
             CMG_CUDA(ctx, cudaEventRecord(ctx->forkEv, ctx->stream));
             for(int k = 0; k < cmg_ctx::kAux; ++k)
@@ -920,7 +926,7 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBat
                 const double* wb = a + b * per;
                 fillStaticTable(ctx, wb, wb + (lmax + 1), wb + 2 * (lmax + 1), wb + 3 * (lmax + 1), lmax, TB);
                 for(int st = 0; st < 3; ++st) PS.ptr[0][st] = layout.ptr[0][st] + b * stride;
-                if((s = launchTquVariant<4, true, 2>(ctx, dyn, TB, entryChunk, PS, grid, 0, ctx->aux[b % cmg_ctx::kAux])) != CMG_OK) return s;
+                if((s = launchTquVariant<4, true, 2>(ctx, dyn, TB, entrySlot, PS, grid, 0, ctx->aux[b % cmg_ctx::kAux])) != CMG_OK) return s;
             }
             for(int k = 0; k < cmg_ctx::kAux; ++k)
             {

@@ -106,17 +106,22 @@ __device__ __forceinline__ void ttStaticChunkAt(double (&x2)[R], double (&b1)[R]
 // fully unrolled body entered through a 128-way switch got none of this: one uniform register for every load, issued
 // right in front of its consumer, dependent DFMA pairs back to back, and 49 KB of straight-line code.
 template <int R>
-__device__ __forceinline__ void ttClenshawStatic(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T, int entryChunk)
+__device__ __forceinline__ void ttClenshawStatic(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T, int entrySlot)
 {
+    // entrySlot = first slot with a non-zero weight (k = lmax): single steps up to the next chunk boundary, then chunks
+    int i = entrySlot;
 #pragma unroll 1
-    for(int c = entryChunk; c < TT_STATIC_STEPS / TT_STATIC_CHUNK; ++c)
-        ttStaticChunkAt<R>(x2, b1, b2, T, c * TT_STATIC_CHUNK);
+    for(; i & (TT_STATIC_CHUNK - 1); ++i)
+        ttStep<R>(x2, b1, b2, T.s[i]);
+#pragma unroll 1
+    for(; i < TT_STATIC_STEPS; i += TT_STATIC_CHUNK)
+        ttStaticChunkAt<R>(x2, b1, b2, T, i);
 }
 
 template <bool STATIC, int R, int MINB>
 __global__ void __launch_bounds__(TT_ROWS, MINB)
 legendreSeriesKernel(const __grid_constant__ TtStaticTable T, Geometry geo, const double* __restrict__ a, long long aStride,
-                     const double* __restrict__ N0, const double* __restrict__ g0, int lmax, int entryChunk,
+                     const double* __restrict__ N0, const double* __restrict__ g0, int lmax, int entrySlot,
                      long long colBegin, long long colEnd, double* __restrict__ out, long long outStride)
 {
     extern __shared__ double2 ttTab[];      // [lmax + 1]  {a_k N_k, -g_{k+1}}  (dynamic variant only)
@@ -161,7 +166,7 @@ legendreSeriesKernel(const __grid_constant__ TtStaticTable T, Geometry geo, cons
             b2[r] = 0.0;
         }
         if(STATIC)
-            ttClenshawStatic<R>(x2, b1, b2, T, entryChunk);
+            ttClenshawStatic<R>(x2, b1, b2, T, entrySlot);
         else
         {
 #pragma unroll 4
@@ -274,11 +279,12 @@ __device__ __forceinline__ void tquStaticChunkAt(TquState<R>& s, const TquStatic
 // rolled loop over 8-step chunks with a warp-uniform counter (see ttClenshawStatic): LDCU c[0x0][UR + imm], coefficient
 // loads software-pipelined by ptxas, a 6 KB loop body instead of 137 KB of straight-line code behind a 55-way switch
 template <int R>
-__device__ __forceinline__ void tquClenshawStatic(TquState<R>& s, const TquStaticTable& T, int entryChunk)
+__device__ __forceinline__ void tquClenshawStatic(TquState<R>& s, const TquStaticTable& T, int entrySlot)
 {
+    // entrySlot: a chunk boundary at or below the first slot with a non-zero weight
 #pragma unroll 1
-    for(int c = entryChunk; c < PQ_STATIC_STEPS / PQ_STATIC_CHUNK; ++c)
-        tquStaticChunkAt<R>(s, T, c * PQ_STATIC_CHUNK);
+    for(int i = entrySlot; i < PQ_STATIC_STEPS; i += PQ_STATIC_CHUNK)
+        tquStaticChunkAt<R>(s, T, i);
     const double4 tail = T.s[2 * PQ_STATIC_STEPS];
     tquStepTT<R>(s, tail.x, tail.y);
     tquStepTT<R>(s, tail.z, tail.w);
@@ -325,7 +331,7 @@ constexpr int PQ_SMEM_DOUBLES = 8 * PQ_TI + 8 * PQ_TJ + 3 * PQ_TI * PQ_STAGE_LD 
 
 template <int R, bool STATIC, int MINB>
 __global__ void __launch_bounds__(PQ_THREADS, MINB)
-tquKernel(const __grid_constant__ TquStaticTable T, Geometry geo, TquDynamicArgs dyn, int entryChunk,
+tquKernel(const __grid_constant__ TquStaticTable T, Geometry geo, TquDynamicArgs dyn, int entrySlot,
           const __grid_constant__ PartTable P, long long outStride)      // T first: 128-byte aligned in the constant bank
 {
     extern __shared__ double4 pqSmem[];
@@ -453,7 +459,7 @@ tquKernel(const __grid_constant__ TquStaticTable T, Geometry geo, TquDynamicArgs
                 st.tt1[r] = st.tt2[r] = st.te1[r] = st.te2[r] = st.pp1[r] = st.pp2[r] = st.mm1[r] = st.mm2[r] = 0.0;
             }
             if(STATIC)
-                tquClenshawStatic<R>(st, T, entryChunk);
+                tquClenshawStatic<R>(st, T, entrySlot);
             else
                 tquClenshawShared<R>(st, tab4, dyn.lmax);
 
