@@ -93,6 +93,7 @@ _SIGNATURES = {
     "cmg_tqu_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp, _i64]),
     "cmg_slab_doubles": (_i64, [_i64]),
     "cmg_tqu_batched_slab": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp]),
+    "cmg_tqu_batched_slab_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp]),
     "cmg_slab_unpack": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _i64]),
     "cmg_sum_unpack": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "cmg_sum_unpack_strided": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
@@ -317,6 +318,10 @@ class Context:
         """DMMA path: ceil(B / 16) slabs of 16 interleaved packed matrices (include/cmg.h)."""
         a = _f64(a)         # [B][4][lmax+1]
         self._check(self._L.cmg_tqu_batched_slab(self._h, _p(a), a.shape[2] - 1, a.shape[0], _p(d_slabs)))
+
+    def tqu_batched_slab_dev(self, d_a, lmax, n_batch, d_slabs):
+        """weights [B][4][lmax+1] already on the device"""
+        self._check(self._L.cmg_tqu_batched_slab_dev(self._h, _p(d_a), int(lmax), int(n_batch), _p(d_slabs)))
 
     def slab_unpack(self, d_slab, dim, d_out, out_stride=0, n_live=SLAB, only_b=-1):
         self._check(self._L.cmg_slab_unpack(self._h, _p(d_slab), dim, n_live, only_b, _p(d_out), out_stride))

@@ -995,7 +995,19 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBat
 
 int64_t cmg_slab_doubles(int64_t dim) { return CMG_SLAB * cmg_packed_size(dim); }
 
+static cmg_status slabGenerate(cmg_ctx* ctx, const double* a, bool weightsOnDevice, int lmax, int64_t nBatch, double* dSlabs);
+
 cmg_status cmg_tqu_batched_slab(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch, double* dSlabs)
+{
+    return slabGenerate(ctx, a, false, lmax, nBatch, dSlabs);
+}
+
+cmg_status cmg_tqu_batched_slab_dev(cmg_ctx* ctx, const double* dA, int lmax, int64_t nBatch, double* dSlabs)
+{
+    return slabGenerate(ctx, dA, true, lmax, nBatch, dSlabs);
+}
+
+static cmg_status slabGenerate(cmg_ctx* ctx, const double* a, bool weightsOnDevice, int lmax, int64_t nBatch, double* dSlabs)
 {
     cmg_status s = checkReady(ctx, lmax);
     if(s != CMG_OK) return s;
@@ -1012,7 +1024,12 @@ cmg_status cmg_tqu_batched_slab(cmg_ctx* ctx, const double* a, int lmax, int64_t
     if(groups > 65535 || tiles * cmg::M2_GROUP > 2147483647LL)
         return fail(ctx, CMG_EUNSUPPORTED, "too many pixel tiles for one launch");
     if((s = ensureWeights(ctx, nBatch * per + fragDoubles)) != CMG_OK) return s;
-    CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
+    const double* dRaw = a;
+    if(!weightsOnDevice)
+    {
+        CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * per, cudaMemcpyHostToDevice, ctx->stream));
+        dRaw = ctx->dWeights;
+    }
     double* dFrag = ctx->dWeights + nBatch * per;
     void (*kernel)(cmg::Geometry, const double*, cmg::DeviceTables, int, int, double*, long long);
     size_t smem;
@@ -1022,7 +1039,7 @@ cmg_status cmg_tqu_batched_slab(cmg_ctx* ctx, const double* a, int lmax, int64_t
     CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     KernelTimer timer(ctx);
     cmg::foldSlabWeightsKernel<<<static_cast<unsigned>(std::min<int64_t>(1024, (fragDoubles + 255) / 256)), 256, 0, ctx->stream>>>(
-        ctx->dWeights, tablesOf(ctx), lmax, static_cast<int>(nBatch), nkk, dFrag);
+        dRaw, tablesOf(ctx), lmax, static_cast<int>(nBatch), nkk, dFrag);
     kernel<<<dim3(static_cast<unsigned>(tiles * cmg::M2_GROUP), static_cast<unsigned>(groups), 2), cmg::M2_THREADS, smem, ctx->stream>>>(
         geometryOf(ctx), dFrag, tablesOf(ctx), lmax, static_cast<int>(nBatch), dSlabs, cmg_slab_doubles(3 * ctx->npix));
     CMG_CUDA(ctx, cudaGetLastError());

@@ -215,6 +215,9 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t n_ba
 #define CMG_SLAB_LMAX 63
 int64_t cmg_slab_doubles(int64_t dim);
 cmg_status cmg_tqu_batched_slab(cmg_ctx* ctx, const double* a, int lmax, int64_t n_batch, double* d_slabs);
+/* same with the weights a[b][4][lmax+1] already on the device (e.g. written by a C_l emulator running on the GPU): nothing is
+ * read from the host.  Capture in a CUDA graph only after one plain call with the same n_batch (it sizes the staging buffer). */
+cmg_status cmg_tqu_batched_slab_dev(cmg_ctx* ctx, const double* d_a, int lmax, int64_t n_batch, double* d_slabs);
 /* one slab -> separate packed matrices of dimension dim: d_out[b * out_stride + e] for b < n_live (only_b < 0), or the
  * single element only_b -> d_out[e] */
 cmg_status cmg_slab_unpack(cmg_ctx* ctx, const double* d_slab, int64_t dim, int n_live, int only_b,

@@ -332,6 +332,11 @@ def test_batched_slab_dmma_path(gpu_ctx, oracle_api):
         torch.cuda.synchronize()
         host = slabs.cpu().numpy().reshape(n_slabs, packed, 16)
         assert not np.isnan(host).any()
+        # device-resident weights: the same slabs, bit for bit
+        slabs_dev = torch.full_like(slabs, float("nan"))
+        gpu_ctx.tqu_batched_slab_dev(torch.from_numpy(np.ascontiguousarray(ab)).cuda(), lmax, nb, slabs_dev)
+        torch.cuda.synchronize()
+        assert torch.equal(slabs_dev, slabs)
         assert (host[-1][:, nb % 16:] == 0).all()           # padding elements of the last slab are zeros
         outs = torch.full((16, packed + 5), float("nan"), dtype=torch.float64, device="cuda")
         one = torch.empty(packed, dtype=torch.float64, device="cuda")
