@@ -49,6 +49,18 @@ noise = np.zeros(capi.packed_size(3 * n)); noise[[capi.packed_index(i, i) for i 
 lk = Likelihood(ctx, slabs[2:], None, torch.from_numpy(noise).cuda(), 3 * n, foreground=np.ones(3 * n), c_stride=capi.SLAB)
 lk.calculate(np.random.RandomState(1).standard_normal((4, 3 * n)))
 lk.close()
+ctx.tqu_batched_slab_dev(torch.from_numpy(np.ascontiguousarray(abl)).cuda(), 60, 37, slabs)
+# TT variants and long series (peeled / chunk-aligned entry of the rolled loop), CMatrix file streaming
+for lm in (20, 127, 128, 150):
+    al = capi.tt_weights(synthetic_cl(lm), capi.window_beam(lm, 10.0))
+    for v in (0, 1, 248, 2216):
+        ctx.set_kernel_variant(v); ctx.legendre_series(al, out)
+ctx.set_kernel_variant(0)
+import tempfile
+with tempfile.TemporaryDirectory() as td:
+    path = os.path.join(td, "c.dat")
+    ctx.write_cmatrix_file(path, n, [(100, out[100:], out.numel() - 100), (0, out, 100)], comment="sanitize")
+    ctx.read_cmatrix_file(path, torch.empty_like(out))
 d_out = torch.empty(capi.packed_size(20), dtype=torch.float64, device="cuda")
 ctx.mask_matrix(out, n, np.arange(0, 160, 8), d_out)
 torch.cuda.synchronize()
