@@ -202,12 +202,7 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
             const int k = cmg::TT_STATIC_STEPS - 1 - i;
             T.s[i] = make_double2(k <= lmax ? hostWeights[k] * ctx->hostT0.N[k] : 0.0, -ctx->hostT0.g[k + 1]);
         }
-        // first slot with a non-zero weight.  The kernel walks single steps up to the next 8-step chunk boundary and whole
-        // chunks from there; single steps are slow (no software pipelining), so more than two of them cost more than
-        // starting at the boundary below and running the zero-weight slots (which leave the zero state untouched)
-        entrySlot = cmg::TT_STATIC_STEPS - 1 - lmax;
-        if(((cmg::TT_STATIC_CHUNK - entrySlot % cmg::TT_STATIC_CHUNK) % cmg::TT_STATIC_CHUNK) > 2)
-            entrySlot -= entrySlot % cmg::TT_STATIC_CHUNK;
+        entrySlot = cmg::TT_STATIC_STEPS - 1 - lmax;      // first slot with a non-zero weight (k = lmax)
     }
     KernelTimer timer(ctx);
     // TT variants: 0 = R 8 columns per thread and pass, 4 CTAs/SM (with the rolled chunk loop the kernel is insensitive to
@@ -339,8 +334,7 @@ cmg_status launchTqu(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, 
     if(variant >= 100)
     {
         fillStaticTable(ctx, hostWeights[0], hostWeights[1], hostWeights[2], hostWeights[3], lmax, T);
-        // chunk boundary at or below the first non-zero slot (a peeled single-step prologue measured slower for T,Q,U)
-        entrySlot = (cmg::PQ_STATIC_STEPS + 1 - lmax) / cmg::PQ_STATIC_CHUNK * cmg::PQ_STATIC_CHUNK;
+        entrySlot = cmg::PQ_STATIC_STEPS + 1 - lmax;      // first slot with a non-zero weight (k = lmax)
     }
     KernelTimer timer(ctx);
     cmg_status s = CMG_OK;
@@ -916,7 +910,7 @@ cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBat
             cmg::TquDynamicArgs dyn;
             dyn.a = ctx->dWeights; dyn.aStride = 0; dyn.tab = tablesOf(ctx); dyn.lmax = lmax;
             static thread_local cmg::TquStaticTable TB;
-            const int entrySlot = (cmg::PQ_STATIC_STEPS + 1 - lmax) / cmg::PQ_STATIC_CHUNK * cmg::PQ_STATIC_CHUNK;
+            const int entrySlot = cmg::PQ_STATIC_STEPS + 1 - lmax;
             KernelTimer timerS(ctx);
             CMG_CUDA(ctx, cudaEventRecord(ctx->forkEv, ctx->stream));
             for(int k = 0; k < cmg_ctx::kAux; ++k)

@@ -92,11 +92,11 @@ __device__ __forceinline__ void ttStep(double (&x2)[R], double (&b1)[R], double 
     }
 }
 
-template <int R>
+template <int R, int N = TT_STATIC_CHUNK>
 __device__ __forceinline__ void ttStaticChunkAt(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T, int first)
 {
 #pragma unroll
-    for(int u = 0; u < TT_STATIC_CHUNK; ++u)
+    for(int u = 0; u < N; ++u)
         ttStep<R>(x2, b1, b2, T.s[first + u]);
 }
 
@@ -108,11 +108,22 @@ __device__ __forceinline__ void ttStaticChunkAt(double (&x2)[R], double (&b1)[R]
 template <int R>
 __device__ __forceinline__ void ttClenshawStatic(double (&x2)[R], double (&b1)[R], double (&b2)[R], const TtStaticTable& T, int entrySlot)
 {
-    // entrySlot = first slot with a non-zero weight (k = lmax): single steps up to the next chunk boundary, then chunks
+    // entrySlot = first slot with a non-zero weight (k = lmax): one unrolled head of 1..7 steps up to the next chunk boundary
+    // (warp-uniform switch), then whole chunks
     int i = entrySlot;
-#pragma unroll 1
-    for(; i & (TT_STATIC_CHUNK - 1); ++i)
-        ttStep<R>(x2, b1, b2, T.s[i]);
+    const int head = (TT_STATIC_CHUNK - (i & (TT_STATIC_CHUNK - 1))) & (TT_STATIC_CHUNK - 1);
+    switch(head)
+    {
+        case 1: ttStaticChunkAt<R, 1>(x2, b1, b2, T, i); break;
+        case 2: ttStaticChunkAt<R, 2>(x2, b1, b2, T, i); break;
+        case 3: ttStaticChunkAt<R, 3>(x2, b1, b2, T, i); break;
+        case 4: ttStaticChunkAt<R, 4>(x2, b1, b2, T, i); break;
+        case 5: ttStaticChunkAt<R, 5>(x2, b1, b2, T, i); break;
+        case 6: ttStaticChunkAt<R, 6>(x2, b1, b2, T, i); break;
+        case 7: ttStaticChunkAt<R, 7>(x2, b1, b2, T, i); break;
+        default: break;
+    }
+    i += head;
 #pragma unroll 1
     for(; i < TT_STATIC_STEPS; i += TT_STATIC_CHUNK)
         ttStaticChunkAt<R>(x2, b1, b2, T, i);
@@ -268,11 +279,11 @@ __device__ __forceinline__ void tquStepTT(TquState<R>& s, const double a, const 
     }
 }
 
-template <int R>
+template <int R, int N = PQ_STATIC_CHUNK>
 __device__ __forceinline__ void tquStaticChunkAt(TquState<R>& s, const TquStaticTable& T, int first)
 {
 #pragma unroll
-    for(int u = 0; u < PQ_STATIC_CHUNK; ++u)
+    for(int u = 0; u < N; ++u)
         tquStep<R>(s, T.s[2 * (first + u)], T.s[2 * (first + u) + 1]);
 }
 
@@ -281,9 +292,24 @@ __device__ __forceinline__ void tquStaticChunkAt(TquState<R>& s, const TquStatic
 template <int R>
 __device__ __forceinline__ void tquClenshawStatic(TquState<R>& s, const TquStaticTable& T, int entrySlot)
 {
-    // entrySlot: a chunk boundary at or below the first slot with a non-zero weight
+    // entrySlot = first slot with a non-zero weight (k = lmax): one unrolled head of 1..7 steps up to the next chunk boundary
+    // (warp-uniform switch; a rolled single-step head measured slower than running the zero-weight slots), then chunks
+    int i = entrySlot;
+    const int head = (PQ_STATIC_CHUNK - (i & (PQ_STATIC_CHUNK - 1))) & (PQ_STATIC_CHUNK - 1);
+    switch(head)
+    {
+        case 1: tquStaticChunkAt<R, 1>(s, T, i); break;
+        case 2: tquStaticChunkAt<R, 2>(s, T, i); break;
+        case 3: tquStaticChunkAt<R, 3>(s, T, i); break;
+        case 4: tquStaticChunkAt<R, 4>(s, T, i); break;
+        case 5: tquStaticChunkAt<R, 5>(s, T, i); break;
+        case 6: tquStaticChunkAt<R, 6>(s, T, i); break;
+        case 7: tquStaticChunkAt<R, 7>(s, T, i); break;
+        default: break;
+    }
+    i += head;
 #pragma unroll 1
-    for(int i = entrySlot; i < PQ_STATIC_STEPS; i += PQ_STATIC_CHUNK)
+    for(; i < PQ_STATIC_STEPS; i += PQ_STATIC_CHUNK)
         tquStaticChunkAt<R>(s, T, i);
     const double4 tail = T.s[2 * PQ_STATIC_STEPS];
     tquStepTT<R>(s, tail.x, tail.y);
