@@ -221,6 +221,7 @@ constexpr int PQ_STAGE_LD = PQ_TJ + 1;
 // lmax hold zero weights, which leave the (zero) Clenshaw state untouched.
 constexpr int PQ_STATIC_STEPS = 440;                 // 4-series steps k = PQ_STATIC_STEPS+1 .. 2
 constexpr int PQ_STATIC_CHUNK = 8;
+constexpr int PQ_STATIC_MAIN = 16;                  // steps per iteration of the rolled loop
 constexpr int PQ_STATIC_LMAX = PQ_STATIC_STEPS + 1;  // largest lmax the static table holds
 
 struct TquStaticTable
@@ -292,11 +293,13 @@ __device__ __forceinline__ void tquStaticChunkAt(TquState<R>& s, const TquStatic
 template <int R>
 __device__ __forceinline__ void tquClenshawStatic(TquState<R>& s, const TquStaticTable& T, int entrySlot)
 {
-    // entrySlot = first slot with a non-zero weight (k = lmax): one unrolled head of 1..7 steps up to the next chunk boundary
-    // (warp-uniform switch; a rolled single-step head measured slower than running the zero-weight slots), then chunks
+    // entrySlot = first slot with a non-zero weight (k = lmax): an unrolled head of 1..15 steps (warp-uniform switch over
+    // 1..7, then one 8-step group) leaves a whole number of 16-step iterations; a rolled single-step head measured slower than
+    // running the zero-weight slots, the unrolled one is faster than both.  16-step chunks: ptxas pipelines the LDCUs inside
+    // the unrolled body but not across the back edge, so every iteration starts with a short bubble.
     int i = entrySlot;
-    const int head = (PQ_STATIC_CHUNK - (i & (PQ_STATIC_CHUNK - 1))) & (PQ_STATIC_CHUNK - 1);
-    switch(head)
+    const int head = (PQ_STATIC_STEPS - i) & (PQ_STATIC_MAIN - 1);      // the rest is a whole number of 16-step iterations
+    switch(head & 7)
     {
         case 1: tquStaticChunkAt<R, 1>(s, T, i); break;
         case 2: tquStaticChunkAt<R, 2>(s, T, i); break;
@@ -307,10 +310,15 @@ __device__ __forceinline__ void tquClenshawStatic(TquState<R>& s, const TquStati
         case 7: tquStaticChunkAt<R, 7>(s, T, i); break;
         default: break;
     }
-    i += head;
+    i += head & 7;
+    if(head & 8)
+    {
+        tquStaticChunkAt<R, 8>(s, T, i);
+        i += 8;
+    }
 #pragma unroll 1
-    for(; i < PQ_STATIC_STEPS; i += PQ_STATIC_CHUNK)
-        tquStaticChunkAt<R>(s, T, i);
+    for(; i < PQ_STATIC_STEPS; i += PQ_STATIC_MAIN)
+        tquStaticChunkAt<R, PQ_STATIC_MAIN>(s, T, i);
     const double4 tail = T.s[2 * PQ_STATIC_STEPS];
     tquStepTT<R>(s, tail.x, tail.y);
     tquStepTT<R>(s, tail.z, tail.w);
