@@ -176,8 +176,11 @@ struct KernelTimer
 
 // hostWeights != NULL (single matrix, weights known on the host) enables the static-table kernel
 cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int lmax, int64_t nBatch,
-                          int64_t colBegin, int64_t colEnd, double* dOut, int64_t outStride, const double* hostWeights)
+                          int64_t colBegin, int64_t colEnd, double* dOut, int64_t outStride, const double* hostWeights,
+                          cudaStream_t stream = nullptr)
 {
+    const bool sideStream = stream != nullptr;       // one of many launches of a batch: the caller times and counts
+    if(!stream) stream = ctx->stream;
     if(colBegin < 0 || colEnd > ctx->npix || colBegin > colEnd)
         return fail(ctx, CMG_EINVAL, "column range outside [0, npix]");
     if(nBatch < 1 || nBatch > 65535)
@@ -204,11 +207,12 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
         }
         entrySlot = cmg::TT_STATIC_STEPS - 1 - lmax;      // first slot with a non-zero weight (k = lmax)
     }
-    KernelTimer timer(ctx);
+    cudaEvent_t timed0 = nullptr;
+    if(ctx->timing && !sideStream) { timed0 = ctx->ev0; cudaEventRecord(ctx->ev0, ctx->stream); }
     // TT variants: 0 = R 8 columns per thread and pass, 4 CTAs/SM (with the rolled chunk loop the kernel is insensitive to
     // occupancy: 87.3-88.1 % of the FP64 peak for every (R, CTAs/SM) tried at Nside=64, profiles/r1_kernel_history.md);
     // 1 = shared-memory table; 248 and 2216 stay selectable for the variant test.
-#define CMG_TT(R_, M_) cmg::legendreSeriesKernel<true, R_, M_><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entrySlot, colBegin, colEnd, dOut, outStride)
+#define CMG_TT(R_, M_) cmg::legendreSeriesKernel<true, R_, M_><<<grid, cmg::TT_ROWS, 0, stream>>>(T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entrySlot, colBegin, colEnd, dOut, outStride)
     if(useStatic)
     {
         switch(ctx->tquVariant)
@@ -220,11 +224,19 @@ cmg_status launchLegendre(cmg_ctx* ctx, const double* dA, int64_t aStride, int l
     }
 #undef CMG_TT
     else
-        cmg::legendreSeriesKernel<false, cmg::TT_R, 8><<<grid, cmg::TT_ROWS, sizeof(double2) * (lmax + 1), ctx->stream>>>(
+        cmg::legendreSeriesKernel<false, cmg::TT_R, 8><<<grid, cmg::TT_ROWS, sizeof(double2) * (lmax + 1), stream>>>(
             T, geometryOf(ctx), dA, aStride, t.N0, t.g0, lmax, entrySlot, colBegin, colEnd, dOut, outStride);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
-    return timer.finish();
+    if(timed0)
+    {
+        CMG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CMG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CMG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->lastMs = ms;
+    }
+    return CMG_OK;
 }
 
 size_t tquSmemBytes(int lmax, bool isStatic)
@@ -766,6 +778,24 @@ cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, 
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     if((s = ensureWeights(ctx, nBatch * (lmax + 1))) != CMG_OK) return s;
     CMG_CUDA(ctx, cudaMemcpyAsync(ctx->dWeights, a, sizeof(double) * nBatch * (lmax + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if(ctx->tquVariant == 0 && lmax + 1 <= cmg::TT_STATIC_STEPS)
+    {
+        // one static-table launch per element over the side streams (as cmg_tqu_batched does): the static kernel is 1.2-1.3x
+        // faster than the shared-memory-table kernel and small grids overlap each other's heads and tails
+        KernelTimer timer(ctx);
+        CMG_CUDA(ctx, cudaEventRecord(ctx->forkEv, ctx->stream));
+        for(int k = 0; k < cmg_ctx::kAux; ++k)
+            CMG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[k], ctx->forkEv, 0));
+        for(int64_t b = 0; b < nBatch; ++b)
+            if((s = launchLegendre(ctx, ctx->dWeights, 0, lmax, 1, colBegin, colEnd, dOut + b * stride, 0, a + b * (lmax + 1),
+                                   ctx->aux[b % cmg_ctx::kAux])) != CMG_OK) return s;
+        for(int k = 0; k < cmg_ctx::kAux; ++k)
+        {
+            CMG_CUDA(ctx, cudaEventRecord(ctx->auxDone[k], ctx->aux[k]));
+            CMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->auxDone[k], 0));
+        }
+        return timer.finish();
+    }
     return launchLegendre(ctx, ctx->dWeights, lmax + 1, lmax, nBatch, colBegin, colEnd, dOut, stride, nullptr);
 }
 
