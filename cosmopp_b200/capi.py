@@ -87,6 +87,8 @@ _SIGNATURES = {
     "cmg_tqu": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(TquLayout)]),
     "cmg_tqu_scatter_block": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_int, _vp]),
     "cmg_tqu_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(TquLayout)]),
+    "cmg_tqu_orbit": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int]),
+    "cmg_tqu_orbit_plan": (ctypes.c_int, [_i64, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cmg_tqu_weights": (ctypes.c_int, [_vp] * 6 + [ctypes.c_int] + [_vp] * 4),
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
     "cmg_legendre_series_batched": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _i64, _vp, _i64]),
@@ -148,6 +150,20 @@ def _p(a):
     if isinstance(a, int):
         return _vp(a)
     return _vp(a.data_ptr())        # torch tensor
+
+
+def orbit_plan(nside, mode=0):
+    """Classes of base-face pairs of cmg_tqu_orbit: list of dicts (host only)."""
+    out = np.zeros((24, 17), dtype=np.int32)
+    n = ctypes.c_int32()
+    st = library().cmg_tqu_orbit_plan(int(nside), int(mode), _p(out), ctypes.byref(n))
+    if st:
+        raise CmgError(st, "cmg_tqu_orbit_plan: bad nside / mode")
+    plan = []
+    for row in out[:n.value]:
+        imgs = [(int(row[5 + 3 * k]), int(row[6 + 3 * k]), bool(row[7 + 3 * k])) for k in range(int(row[4]))]
+        plan.append(dict(row_face=int(row[0]), col_face=int(row[1]), tri=bool(row[2]), same_face=bool(row[3]), images=imgs))
+    return plan
 
 
 SLAB = 16            # CMG_SLAB: batch elements interleaved in one slab of the DMMA batched path
@@ -303,6 +319,11 @@ class Context:
 
     def tqu_dev(self, d_a, lmax, layout):
         self._check(self._L.cmg_tqu_dev(self._h, _p(d_a), int(lmax), ctypes.byref(layout)))
+
+    def tqu_orbit(self, a_tt, a_te, a_ee, a_bb, d_packed, mode=0):
+        """EXPERIMENTAL full-sky path: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid."""
+        a_tt, a_te, a_ee, a_bb = map(_f64, (a_tt, a_te, a_ee, a_bb))
+        self._check(self._L.cmg_tqu_orbit(self._h, _p(a_tt), _p(a_te), _p(a_ee), _p(a_bb), len(a_tt) - 1, _p(d_packed), int(mode)))
 
     def tqu_scatter_block(self, d_block, col0, n_cols, ld, row0, kind, d_full):
         self._check(self._L.cmg_tqu_scatter_block(self._h, _p(d_block), col0, n_cols, ld, row0, kind, _p(d_full)))

@@ -19,6 +19,7 @@
 #include "../../include/cmg.h"
 #include "healpix_nest.hpp"
 #include "kernels.cuh"
+#include "orbit.cuh"
 #include "series.hpp"
 
 namespace
@@ -37,6 +38,7 @@ struct cmg_ctx
 
     int64_t nside = 0;
     int64_t npix = 0;
+    bool fullSky = false;            // all 12 nside^2 pixels in NESTED order (what the symmetry-orbit path needs)
     double* dGeo = nullptr;          // [8][npix]
     double* dTables = nullptr;       // 7 tables of kTabLen
     double* dWeights = nullptr;      // staging for host-supplied weights
@@ -706,12 +708,14 @@ cmg_status cmg_set_pixels(cmg_ctx* ctx, int64_t nside, const int32_t* good, int6
     const int64_t n = good ? nGood : full;
     if(n < 1)
         return fail(ctx, CMG_EINVAL, "empty pixel list");
+    bool fullSky = n == full;
     std::vector<double> host(static_cast<size_t>(8 * n));
     for(int64_t k = 0; k < n; ++k)
     {
         const int64_t ipix = good ? good[k] : k;
         if(ipix < 0 || ipix >= full)
             return fail(ctx, CMG_EINVAL, "pixel index outside [0, 12 nside^2)");
+        fullSky = fullSky && ipix == k;
         const cmg::PixelFrame f = cmg::pixelFrame(nside, ipix);
         host[0 * n + k] = f.n[0];
         host[1 * n + k] = f.n[1];
@@ -729,11 +733,13 @@ cmg_status cmg_set_pixels(cmg_ctx* ctx, int64_t nside, const int32_t* good, int6
         CMG_CUDA(ctx, cudaFree(ctx->dGeo));
         ctx->dGeo = nullptr;
         ctx->npix = 0;
+        ctx->fullSky = false;
     }
     CMG_CUDA(ctx, cudaMalloc(&ctx->dGeo, sizeof(double) * host.size()));
     CMG_CUDA(ctx, cudaMemcpy(ctx->dGeo, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
     ctx->nside = nside;
     ctx->npix = n;
+    ctx->fullSky = fullSky;
     return CMG_OK;
 }
 
@@ -907,6 +913,79 @@ cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* dA, int lmax, const cmg_tqu_l
     if(!dA) return fail(ctx, CMG_EINVAL, "null weights");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     return launchTqu(ctx, dA, 0, lmax, 1, layout, 0, nullptr);
+}
+
+// ---------------------------------------------------------------- T,Q,U over symmetry orbits (experimental)
+
+cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* nClasses)
+{
+    if(!out || !nClasses || !cmg::validNside(nside) || (mode != 0 && mode != 1))
+        return CMG_EINVAL;
+    cmg::OrbitPlan plan;
+    cmg::orbitBuildPlan(nside, mode, -1, plan);
+    *nClasses = plan.n;
+    for(int c = 0; c < plan.n; ++c)
+    {
+        const cmg::OrbitClass& oc = plan.c[c];
+        int32_t* o = out + c * CMG_ORBIT_CLASS_INTS;
+        o[0] = oc.rowFace; o[1] = oc.colFace; o[2] = oc.tri; o[3] = oc.sameFace; o[4] = oc.nImg;
+        for(int k = 0; k < cmg::ORB_MAX_IMAGES; ++k)
+        {
+            o[5 + 3 * k] = oc.imgRowFace[k];
+            o[6 + 3 * k] = oc.imgColFace[k];
+            o[7 + 3 * k] = oc.imgSwap[k];
+        }
+    }
+    return CMG_OK;
+}
+
+cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* att, const double* ate, const double* aee, const double* abb, int lmax,
+                         double* dPacked, int mode)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!att || !ate || !aee || !abb || !dPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    if(mode != 0 && mode != 1) return fail(ctx, CMG_EINVAL, "orbit mode must be 0 (transposed images) or 1 (none)");
+    if(!ctx->fullSky)
+        return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs the full sky in NESTED order (cmg_set_pixels with good_nest = NULL)");
+    if(ctx->nside < 8)
+        return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs nside >= 8 (whole 64 x 32 tiles inside a base face)");
+    if(lmax < 2 || lmax > cmg::PQ_STATIC_LMAX)
+        return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs 2 <= lmax <= PQ_STATIC_LMAX");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    static thread_local cmg::TquStaticTable T;      // 28 KB: keep it off the stack
+    fillStaticTable(ctx, att, ate, aee, abb, lmax, T);
+    const int entrySlot = cmg::PQ_STATIC_STEPS + 1 - lmax;
+    const int64_t facePix = ctx->nside * ctx->nside;
+    const unsigned tiles = static_cast<unsigned>((facePix / cmg::PQ_TI) * (facePix / cmg::PQ_TJ));
+
+    KernelTimer timer(ctx);
+    for(int half = 0; half < 2; ++half)              // classes without / with a transposed image
+    {
+        cmg::OrbitPlan plan;
+        cmg::orbitBuildPlan(ctx->nside, mode, half, plan);
+        if(plan.n == 0)
+            continue;
+        const dim3 grid(tiles, static_cast<unsigned>(plan.n));
+        if(half == 0)
+        {
+            auto kernel = cmg::tquOrbitKernel<4, 2, false>;
+            const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<false>();
+            CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, dPacked);
+        }
+        else
+        {
+            auto kernel = cmg::tquOrbitKernel<4, 2, true>;
+            const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<true>();
+            CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, dPacked);
+        }
+        CMG_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return timer.finish();
 }
 
 cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch, double* dOut, int64_t stride)

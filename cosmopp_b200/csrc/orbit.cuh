@@ -1,0 +1,296 @@
+// Symmetry orbits of the full-sky HEALPix pixelisation (experimental path, cmg_tqu_orbit).
+//
+// The grid is invariant under the rotation R by pi/2 about the polar axis; in NESTED ordering R maps base face f to
+// (f & ~3) | ((f + 1) & 3) and keeps the index inside the face.  The local frames (e_theta, e_phi) rotate with the
+// pixel, so the whole 3x3 block of a pixel pair is invariant:  C[X R a, Y R b] = C[X a, Y b]  for X, Y in {T, Q, U}.
+// The four Clenshaw sums and the frame rotation are therefore evaluated once per orbit of pixel pairs and the nine
+// results stored at up to four places.  The work is cut into classes of base-face pairs (rows x columns of the upper
+// triangle); a class holds the source face pair, whether only q_row <= q_col is needed, and the images:
+//
+//   faces (rows, columns)                      pairs computed          images
+//   different rings of faces, column p = 0     whole face pair         4, all with row pixel < column pixel
+//   the same face, p = 0                       q_row <= q_col          4
+//   same ring, faces (0, 1)                    whole face pair         (0,1) (1,2) (2,3) and (3,0), which is stored
+//                                                                      TRANSPOSED: its row image has the larger index
+//   same ring, faces (0, 2)                    q_row <= q_col          (0,2) (1,3), and transposed (2,0) (3,1)
+//
+// = 18 of the 72 face-pair units of the triangle, i.e. a quarter of the recurrence work.  A transposed image needs
+// six of its nine entries staged through shared memory instead of three (kernel template SWAP).  Without transposed
+// images (mode 1) the classes (0,1) x 3 images, (0,3) alone and the whole of (0,2) x 2 images cost 22.5 units (3.2x).
+#pragma once
+
+#include "kernels.cuh"
+
+namespace cmg
+{
+
+constexpr int ORB_MAX_CLASSES = 24;
+constexpr int ORB_MAX_IMAGES = 4;
+
+struct OrbitClass
+{
+    int rowFace, colFace;                  // base faces of the source tile rows / columns
+    int tri;                               // 1: only pairs with q_row <= q_col (index inside the face)
+    int sameFace;                          // 1: q_row == q_col is ONE pixel (transposed partners need q_row < q_col)
+    int nImg;
+    int imgRowFace[ORB_MAX_IMAGES];        // image k of the rows / columns lives in these faces (image 0 = source)
+    int imgColFace[ORB_MAX_IMAGES];
+    int imgSwap[ORB_MAX_IMAGES];           // 1: the image of the rows has the LARGER pixel index
+};
+
+struct OrbitPlan
+{
+    int n;
+    int facePix;                           // nside^2
+    OrbitClass c[ORB_MAX_CLASSES];
+};
+
+inline int orbitRotateFace(int f, int k) { return (f & ~3) | ((f + k) & 3); }
+
+// mode 0: transposed images allowed (18 units); mode 1: none (22.5 units).  swapClasses selects which half of the
+// classes to emit: 0 = those without a transposed image, 1 = those with one, -1 = all.
+inline void orbitBuildPlan(int64_t nside, int mode, int swapClasses, OrbitPlan& plan)
+{
+    plan.n = 0;
+    plan.facePix = static_cast<int>(nside * nside);
+    auto add = [&](int rowFace, int colFace, int tri, int sameFace, int nImg, const int* rot, const int* swap)
+    {
+        bool anySwap = false;
+        for(int k = 0; k < nImg; ++k)
+            anySwap = anySwap || swap[k];
+        if(swapClasses >= 0 && (swapClasses == 1) != anySwap)
+            return;
+        OrbitClass& c = plan.c[plan.n++];
+        c.rowFace = rowFace;
+        c.colFace = colFace;
+        c.tri = tri;
+        c.sameFace = sameFace;
+        c.nImg = nImg;
+        for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+        {
+            const int r = k < nImg ? rot[k] : 0;
+            c.imgRowFace[k] = orbitRotateFace(rowFace, r);
+            c.imgColFace[k] = orbitRotateFace(colFace, r);
+            c.imgSwap[k] = k < nImg ? swap[k] : 0;
+        }
+    };
+    const int rot4[4] = {0, 1, 2, 3}, none[4] = {0, 0, 0, 0};
+    // different rings of faces: the column face is brought to position 0 of its ring
+    for(int gRow = 0; gRow < 3; ++gRow)
+        for(int gCol = gRow + 1; gCol < 3; ++gCol)
+            for(int p = 0; p < 4; ++p)
+                add(4 * gRow + p, 4 * gCol, 0, 0, 4, rot4, none);
+    for(int g = 0; g < 3; ++g)
+    {
+        add(4 * g, 4 * g, 1, 1, 4, rot4, none);                                  // the same face
+        if(mode == 0)
+        {
+            const int swap01[4] = {0, 0, 0, 1};                                  // (3,0) is stored as (0,3) transposed
+            add(4 * g, 4 * g + 1, 0, 0, 4, rot4, swap01);
+            const int swap02[4] = {0, 0, 1, 1};                                  // (2,0), (3,1)
+            add(4 * g, 4 * g + 2, 1, 0, 4, rot4, swap02);
+        }
+        else
+        {
+            add(4 * g, 4 * g + 1, 0, 0, 3, rot4, none);
+            add(4 * g, 4 * g + 3, 0, 0, 1, rot4, none);
+            add(4 * g, 4 * g + 2, 0, 0, 2, rot4, none);
+        }
+    }
+}
+
+// shared memory of tquOrbitKernel: frames of rows and columns, staged entries, column pointers of every image
+template <bool SWAP>
+constexpr int orbitSmemDoubles()
+{
+    return 8 * PQ_TI + 8 * PQ_TJ + (SWAP ? 6 : 3) * PQ_TI * PQ_STAGE_LD + ORB_MAX_IMAGES * 3 * PQ_TJ;
+}
+
+// One CTA = one 64 x 32 tile of pixel pairs of a class (blockIdx.y), evaluated exactly as tquKernel does, stored at
+// every image.  Entries whose contiguous direction is the column pixel go through the shared-memory stage: the three
+// transposed partners <Q_a T_b>, <U_a T_b>, <U_a Q_b> for every image, and <T T>, <Q Q>, <U U> as well for a
+// transposed image (there the row image a' has the larger index, so (X a', X b') is stored in column X a').
+// base = entry (0, 0) of the whole packed [T;Q;U] triangle (single owner).
+template <int R, int MINB, bool SWAP>
+__global__ void __launch_bounds__(PQ_THREADS, MINB)
+tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entrySlot,
+               const __grid_constant__ OrbitPlan plan, double* __restrict__ base)
+{
+    extern __shared__ double4 orbSmem[];
+    constexpr int SLOTS = SWAP ? 6 : 3;
+    double* sI = reinterpret_cast<double*>(orbSmem);                  // [8][PQ_TI]
+    double* sJ = sI + 8 * PQ_TI;                                     // [8][PQ_TJ]
+    double* stage = sJ + 8 * PQ_TJ;                                  // [SLOTS][PQ_TI][PQ_STAGE_LD]
+    double** sColPtr = reinterpret_cast<double**>(stage + SLOTS * PQ_TI * PQ_STAGE_LD);   // [image][3][PQ_TJ]
+
+    const OrbitClass& oc = plan.c[blockIdx.y];
+    const int facePix = plan.facePix;
+    const int tilesPerFaceRows = facePix / PQ_TI;
+    const int qRow0 = static_cast<int>(blockIdx.x % tilesPerFaceRows) * PQ_TI;
+    const int qCol0 = static_cast<int>(blockIdx.x / tilesPerFaceRows) * PQ_TJ;
+    const int tri = oc.tri;
+    if(tri && qRow0 > qCol0 + PQ_TJ - 1)
+        return;
+
+    const long long npix = geo.npix;
+    const long long rowBlock = static_cast<long long>(oc.rowFace) * facePix + qRow0;
+    const long long c0 = static_cast<long long>(oc.colFace) * facePix + qCol0;
+    const int nImg = oc.nImg;
+    const int tid = threadIdx.x;
+
+    for(int idx = tid; idx < PQ_TI + PQ_TJ; idx += PQ_THREADS)
+    {
+        const bool isRow = idx < PQ_TI;
+        const int loc = isRow ? idx : idx - PQ_TI;
+        const long long pix = isRow ? rowBlock + loc : c0 + loc;
+        double* dst = isRow ? sI : sJ;
+        const int ld = isRow ? PQ_TI : PQ_TJ;
+        dst[0 * ld + loc] = geo.nx[pix];
+        dst[1 * ld + loc] = geo.ny[pix];
+        dst[2 * ld + loc] = geo.nz[pix];
+        dst[3 * ld + loc] = geo.tx[pix];
+        dst[4 * ld + loc] = geo.ty[pix];
+        dst[5 * ld + loc] = geo.tz[pix];
+        dst[6 * ld + loc] = geo.px[pix];
+        dst[7 * ld + loc] = geo.py[pix];
+    }
+    // row 0 of columns b', N + b', 2N + b' for the column pixels b' of every image
+    for(int idx = tid; idx < ORB_MAX_IMAGES * 3 * PQ_TJ; idx += PQ_THREADS)
+    {
+        const int k = idx / (3 * PQ_TJ);
+        const int rem = idx - k * 3 * PQ_TJ;
+        const int strip = rem / PQ_TJ;
+        const long long col = strip * npix + static_cast<long long>(oc.imgColFace[k]) * facePix + qCol0 + (rem - strip * PQ_TJ);
+        sColPtr[idx] = base + packedOffset(col);
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int il = lane + 32 * (warp & 1);
+    const int colGroup = warp >> 1;                     // 8 columns each
+    const bool warpLive = !tri || qRow0 + 32 * (warp & 1) <= qCol0 + PQ_TJ - 1;
+
+    const double nix = sI[0 * PQ_TI + il], niy = sI[1 * PQ_TI + il], niz = sI[2 * PQ_TI + il];
+
+    if(warpLive)
+    {
+        for(int pass = 0; pass < 8 / R; ++pass)
+        {
+            const int jl0 = colGroup * 8 + pass * R;
+            TquState<R> st;
+#pragma unroll
+            for(int r = 0; r < R; ++r)
+            {
+                const int jl = jl0 + r;
+                double dot = __dadd_rn(__dadd_rn(__dmul_rn(nix, sJ[0 * PQ_TJ + jl]), __dmul_rn(niy, sJ[1 * PQ_TJ + jl])),
+                                       __dmul_rn(niz, sJ[2 * PQ_TJ + jl]));
+                dot = fmin(1.0, fmax(-1.0, dot));
+                st.x2[r] = dot + dot;
+                st.tt1[r] = st.tt2[r] = st.te1[r] = st.te2[r] = st.pp1[r] = st.pp2[r] = st.mm1[r] = st.mm2[r] = 0.0;
+            }
+            tquClenshawStatic<R>(st, T, entrySlot);
+
+            const double tix = sI[3 * PQ_TI + il], tiy = sI[4 * PQ_TI + il], tiz = sI[5 * PQ_TI + il];
+            const double pix_ = sI[6 * PQ_TI + il], piy = sI[7 * PQ_TI + il];
+#pragma unroll
+            for(int r = 0; r < R; ++r)
+            {
+                const int jl = jl0 + r;
+                const double njx = sJ[0 * PQ_TJ + jl], njy = sJ[1 * PQ_TJ + jl], njz = sJ[2 * PQ_TJ + jl];
+                const double tjx = sJ[3 * PQ_TJ + jl], tjy = sJ[4 * PQ_TJ + jl], tjz = sJ[5 * PQ_TJ + jl];
+                const double pjx = sJ[6 * PQ_TJ + jl], pjy = sJ[7 * PQ_TJ + jl];
+
+                const double ai = fma(njx, tix, fma(njy, tiy, njz * tiz));    // n_j . e_theta(i)
+                const double bi = fma(njx, pix_, njy * piy);                  // n_j . e_phi(i)
+                const double aj = fma(nix, tjx, fma(niy, tjy, niz * tjz));
+                const double bj = fma(nix, pjx, niy * pjy);
+                const double p = fma(tix, tjx, fma(tiy, tjy, tiz * tjz));     // e_theta(i) . e_theta(j)
+                const double q = fma(pix_, pjx, piy * pjy);                   // e_phi(i) . e_phi(j)
+                const double rr = fma(pix_, tjx, piy * tjy);                  // e_phi(i) . e_theta(j)
+                const double tq = fma(tix, pjx, tiy * pjy);                   // e_theta(i) . e_phi(j)
+
+                const double su = p + q, du = rr - tq, sv = p - q, dv = tq + rr;
+                const double aRe = st.pp1[r] * fma(su, su, -du * du), aIm = st.pp1[r] * (2.0 * su * du);
+                const double bRe = st.mm1[r] * fma(sv, sv, -dv * dv), bIm = st.mm1[r] * (2.0 * sv * dv);
+                const double xt = -st.te1[r];
+
+                const double vTT = st.tt1[r];
+                const double vTQ = xt * fma(aj, aj, -bj * bj);                // T_a Q_b
+                const double vQQ = aRe + bRe;
+                const double vTU = xt * (2.0 * aj * bj);                      // T_a U_b
+                const double vQU = bIm - aIm;                                 // Q_a U_b
+                const double vUU = aRe - bRe;
+
+                const int dq = (qCol0 + jl) - (qRow0 + il);                   // q_col - q_row
+                if(!tri || dq >= 0)
+                {
+#pragma unroll
+                    for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+                    {
+                        if(k < nImg)
+                        {
+                            const long long ip = static_cast<long long>(oc.imgRowFace[k]) * facePix + (qRow0 + il);
+                            double* colT = sColPtr[(k * 3 + 0) * PQ_TJ + jl] + ip;
+                            double* colQ = sColPtr[(k * 3 + 1) * PQ_TJ + jl] + ip;
+                            double* colU = sColPtr[(k * 3 + 2) * PQ_TJ + jl] + ip;
+                            if(!SWAP || !oc.imgSwap[k])
+                            {
+                                __stcs(colT, vTT);
+                                __stcs(colQ, vTQ);
+                                __stcs(colQ + npix, vQQ);
+                                __stcs(colU, vTU);
+                                __stcs(colU + npix, vQU);
+                                __stcs(colU + 2 * npix, vUU);
+                            }
+                            else if(!tri || dq > 0)          // the q_row == q_col pairs of a transposed image are image 0's own
+                            {
+                                __stcs(colQ, vTQ);
+                                __stcs(colU, vTU);
+                                __stcs(colU + npix, vQU);
+                            }
+                        }
+                    }
+                }
+                stage[(0 * PQ_TI + il) * PQ_STAGE_LD + jl] = xt * fma(ai, ai, -bi * bi);   // Q_a T_b
+                stage[(1 * PQ_TI + il) * PQ_STAGE_LD + jl] = xt * (2.0 * ai * bi);         // U_a T_b
+                stage[(2 * PQ_TI + il) * PQ_STAGE_LD + jl] = aIm + bIm;                    // U_a Q_b
+                if(SWAP)
+                {
+                    stage[(3 * PQ_TI + il) * PQ_STAGE_LD + jl] = vTT;
+                    stage[(4 * PQ_TI + il) * PQ_STAGE_LD + jl] = vQQ;
+                    stage[(5 * PQ_TI + il) * PQ_STAGE_LD + jl] = vUU;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // entries whose contiguous direction is the column pixel: for fixed row pixel a' the 32 column pixels of the tile
+    // are consecutive rows of column (X a'); one warp store per (image, entry kind, a')
+    const int sameFace = oc.sameFace;
+    for(int k = 0; k < nImg; ++k)
+    {
+        const bool swapped = SWAP && oc.imgSwap[k];
+        const int nRows = (swapped ? 6 : 3) * PQ_TI;
+        const long long rowPix0 = static_cast<long long>(oc.imgRowFace[k]) * facePix + qRow0;
+        const long long colPix0 = static_cast<long long>(oc.imgColFace[k]) * facePix + qCol0;
+        // q_col - q_row must be >= minGap: none for whole face pairs; 1 where q_row == q_col is one pixel (its partners
+        // are the direct entries) or belongs to image 0 (transposed images of a q_row <= q_col class); else 0
+        const int minGap = !tri ? -(1 << 30) : ((sameFace || swapped) ? 1 : 0);
+        for(int row = warp; row < nRows; row += PQ_THREADS / 32)
+        {
+            const int t = row / PQ_TI;
+            const int ilr = row - t * PQ_TI;
+            // t: 0 <Q T>, 1 <U T>, 2 <U Q>, 3 <T T>, 4 <Q Q>, 5 <U U>  ->  column strip X, row strip Y
+            const int stripX = t == 0 ? 1 : (t == 1 || t == 2 || t == 5) ? 2 : (t == 4 ? 1 : 0);
+            const int stripY = t == 2 ? 1 : (t == 4 ? 1 : (t == 5 ? 2 : 0));
+            if((qCol0 + lane) - (qRow0 + ilr) >= minGap)
+            {
+                double* dst = base + packedOffset(stripX * npix + rowPix0 + ilr) + (stripY * npix + colPix0 + lane);
+                __stcs(dst, stage[row * PQ_STAGE_LD + lane]);
+            }
+        }
+    }
+}
+
+} // namespace cmg

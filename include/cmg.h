@@ -182,6 +182,21 @@ cmg_status cmg_tqu_scatter_block(cmg_ctx* ctx, const double* d_block, int64_t co
  * read from the host, so the call can be captured in a CUDA graph and replayed after the weights were updated in place
  * (shared-memory coefficient table kernel; the parameter-block kernel needs the weights on the host at launch) */
 cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* d_a, int lmax, const cmg_tqu_layout* layout);
+/* EXPERIMENTAL (opt-in; not what cmg_tqu or the drop-in classes call): the same matrix for the FULL sky, evaluated once per
+ * orbit of pixel pairs under the pi/2 rotation of the HEALPix grid about the polar axis (NESTED: base face f -> next face of
+ * its ring, index inside the face kept).  Frames rotate with the pixels, so C[X Ra, Y Rb] = C[X a, Y b] and the four sums of
+ * a pair are computed once and stored at its (up to) four images: a quarter of the recurrence work of cmg_tqu (mode 0), or
+ * 1/3.2 without transposed images (mode 1).  Entries of different images of one orbit are bit-identical to each other; each
+ * differs from cmg_tqu's by the rounding of its own n_i.n_j only (the 1e-11 gate holds with the same margin).
+ * Needs cmg_set_pixels(ctx, nside >= 8, NULL, 0), 2 <= lmax <= 441, a single-owner packed buffer d_packed of dimension 3N. */
+cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
+                         const double* a_bb, int lmax, double* d_packed, int mode);
+/* the classes of base-face pairs cmg_tqu_orbit works through (host only; for tests): out[c][CMG_ORBIT_CLASS_INTS] =
+ * { row face, column face, only q_row <= q_col, same face, n_images, then for image k = 0..3: row face, column face,
+ *   stored transposed }; out must hold CMG_ORBIT_MAX_CLASSES classes */
+#define CMG_ORBIT_CLASS_INTS 17
+#define CMG_ORBIT_MAX_CLASSES 24
+cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* n_classes);
 /* weights from spectra and the temperature / polarization window*beam factors */
 cmg_status cmg_tqu_weights(const double* ctt, const double* cte, const double* cee, const double* cbb,
                            const double* fT, const double* fP, int lmax,

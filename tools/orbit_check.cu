@@ -1,0 +1,154 @@
+// Quick parity + timing probe of the experimental symmetry-orbit path (cmg_tqu_orbit) against cmg_tqu, through the C ABI
+// only (no Python: starts in a second on a fresh box).
+//   nvcc -O2 -std=c++17 -I include -o gpurun_out/orbit_check tools/orbit_check.cu -L cosmopp_b200/lib -lcosmopp_b200 \
+//        -Xlinker -rpath=$PWD/cosmopp_b200/lib
+//   gpurun_out/orbit_check [nside_max_for_timing]
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "cmg.h"
+
+#define OK(call)                                                                              \
+    do                                                                                        \
+    {                                                                                         \
+        const cmg_status s_ = (call);                                                         \
+        if(s_ != CMG_OK)                                                                      \
+        {                                                                                     \
+            std::printf("FAIL %s -> %d: %s\n", #call, (int) s_, cmg_last_error(ctx));          \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while(0)
+
+static void weights(int lmax, std::vector<double>& tt, std::vector<double>& te, std::vector<double>& ee, std::vector<double>& bb)
+{
+    tt.assign(lmax + 1, 0.0); te = tt; ee = tt; bb = tt;
+    unsigned s = 12345u;
+    auto u = [&]() { s = s * 1664525u + 1013904223u; return 0.5 + (s >> 8) / 16777216.0; };
+    for(int l = 2; l <= lmax; ++l)
+    {
+        const double w = (2 * l + 1) / (4 * 3.141592653589793) * std::exp(-l * (l + 1) * 0.0055);
+        const double ctt = 1000.0 * u() / (l * (l + 1.0));
+        const double cee = 0.03 * ctt * u(), cbb = 0.002 * ctt * u();
+        tt[l] = w * ctt; ee[l] = w * cee; bb[l] = w * cbb; te[l] = w * (u() - 1.0) * std::sqrt(ctt * cee);
+    }
+}
+
+int main(int argc, char** argv)
+{
+    const int timingNside = argc > 1 ? std::atoi(argv[1]) : 64;
+    cmg_ctx* ctx = nullptr;
+    if(cmg_create(&ctx, 0) != CMG_OK) { std::printf("no context: %s\n", cmg_last_error(nullptr)); return 1; }
+    OK(cmg_set_timing(ctx, 1));
+    int rc = 0;
+
+    // full comparison at sizes that fit twice
+    const int cases[][2] = {{8, 20}, {16, 47}, {32, 96}};
+    for(const auto& cs : cases)
+    {
+        const int nside = cs[0], lmax = cs[1];
+        OK(cmg_set_pixels(ctx, nside, nullptr, 0));
+        const int64_t n = cmg_npix(ctx), packed = cmg_packed_size(3 * n);
+        std::vector<double> tt, te, ee, bb;
+        weights(lmax, tt, te, ee, bb);
+        double *dA = nullptr, *dB = nullptr;
+        OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
+        OK(cmg_device_malloc(ctx, packed * 8, (void**) &dB));
+        cmg_tqu_layout lay;
+        OK(cmg_tqu_layout_single(ctx, dA, &lay));
+        OK(cmg_tqu(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, &lay));
+        double msBase = 0; OK(cmg_last_kernel_ms(ctx, &msBase));
+        std::vector<double> hA(packed), hB(packed);
+        OK(cmg_copy_to_host(ctx, hA.data(), dA, packed * 8));
+        OK(cmg_synchronize(ctx));
+        const double dT = hA[0], dQ = hA[cmg_packed_index(n, n)];
+        for(int mode = 1; mode >= 0; --mode)
+        {
+            cudaMemset(dB, 0xFF, packed * 8);                      // NaN pattern: an entry nobody writes shows up
+            cudaDeviceSynchronize();
+            const cmg_status s = cmg_tqu_orbit(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, dB, mode);
+            if(s != CMG_OK) { std::printf("nside %d mode %d: launch failed: %s\n", nside, mode, cmg_last_error(ctx)); rc = 1; continue; }
+            double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+            const cmg_status s2 = cmg_synchronize(ctx);
+            if(s2 != CMG_OK) { std::printf("nside %d mode %d: kernel fault: %s\n", nside, mode, cmg_last_error(ctx)); return 2; }
+            OK(cmg_copy_to_host(ctx, hB.data(), dB, packed * 8));
+            OK(cmg_synchronize(ctx));
+            int64_t nan = 0, firstBad = -1;
+            double worst = 0;
+            for(int64_t col = 0, e = 0; col < 3 * n; ++col)
+            {
+                const double scale = col < n ? dT : dQ;
+                for(int64_t row = 0; row <= col; ++row, ++e)
+                {
+                    if(std::isnan(hB[e])) { ++nan; if(firstBad < 0) firstBad = e; continue; }
+                    const double d = std::fabs(hB[e] - hA[e]) / scale;
+                    if(d > worst) { worst = d; if(d > 1e-11 && firstBad < 0) firstBad = e; }
+                }
+            }
+            std::printf("nside %d lmax %d mode %d: unwritten %lld, max |orbit - cmg_tqu| / diag = %.3e, first bad entry %lld; %.3f ms (cmg_tqu %.3f ms)\n",
+                        nside, lmax, mode, (long long) nan, worst, (long long) firstBad, ms, msBase);
+            if(nan || worst > 1e-11) rc = 1;
+        }
+        OK(cmg_device_free(ctx, dA));
+        OK(cmg_device_free(ctx, dB));
+    }
+
+    // flagship size: one buffer, three 32 MB windows compared, timings
+    if(timingNside >= 64)
+    {
+        const int nside = 64, lmax = 192;
+        OK(cmg_set_pixels(ctx, nside, nullptr, 0));
+        const int64_t n = cmg_npix(ctx), packed = cmg_packed_size(3 * n);
+        std::vector<double> tt, te, ee, bb;
+        weights(lmax, tt, te, ee, bb);
+        double* dA = nullptr;
+        OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
+        const int64_t win = 4 << 20;
+        const int64_t starts[3] = {0, packed / 2, packed - win};
+        std::vector<double> ref(3 * win), got(3 * win);
+        cmg_tqu_layout lay;
+        OK(cmg_tqu_layout_single(ctx, dA, &lay));
+        double best = 1e30;
+        for(int rep = 0; rep < 3; ++rep)
+        {
+            OK(cmg_tqu(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, &lay));
+            double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+            best = std::min(best, ms);
+        }
+        for(int w = 0; w < 3; ++w) OK(cmg_copy_to_host(ctx, ref.data() + w * win, dA + starts[w], win * 8));
+        OK(cmg_synchronize(ctx));
+        std::printf("nside 64 lmax 192: cmg_tqu %.2f ms\n", best);
+        for(int mode = 1; mode >= 0; --mode)
+        {
+            cudaMemset(dA, 0xFF, packed * 8);
+            cudaDeviceSynchronize();
+            double bestO = 1e30;
+            for(int rep = 0; rep < 3; ++rep)
+            {
+                OK(cmg_tqu_orbit(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, dA, mode));
+                double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+                bestO = std::min(bestO, ms);
+            }
+            for(int w = 0; w < 3; ++w) OK(cmg_copy_to_host(ctx, got.data() + w * win, dA + starts[w], win * 8));
+            OK(cmg_synchronize(ctx));
+            double worst = 0; int64_t nan = 0;
+            for(int64_t e = 0; e < 3 * win; ++e)
+            {
+                if(std::isnan(got[e])) { ++nan; continue; }
+                worst = std::max(worst, std::fabs(got[e] - ref[e]));
+            }
+            std::printf("nside 64 lmax 192 mode %d: %.2f ms (%.2fx), windows: unwritten %lld, max abs diff %.3e (TT diag %.3e)\n",
+                        mode, bestO, best / bestO, (long long) nan, worst, ref[0]);
+            if(nan) rc = 1;
+        }
+        OK(cmg_device_free(ctx, dA));
+    }
+    cmg_destroy(ctx);
+    std::printf(rc ? "ORBIT CHECK FAILED\n" : "ORBIT CHECK OK\n");
+    return rc;
+}
