@@ -5,16 +5,21 @@
 
 One "step" = one generation of the whole covariance matrix of the workload from a C_l set.  Default
 workload is BASELINE config 5 (polarized T,Q,U matrix, HEALPix Nside=64, lmax=192: 147456 x 147456,
-87 GB packed); it fits one B200, and for N > 1 the SAME matrix is split over the ranks by equal-area
-pixel-column blocks (strong scaling, no data-path collective: every entry depends on replicated inputs).
+87 GB packed); it fits one B200, and for N > 1 the SAME matrix is split over the ranks (strong scaling, no
+data-path collective: every entry depends on replicated inputs).  Full-sky T,Q,U workloads run over the symmetry
+orbits of the HEALPix grid (cmg_tqu_orbit: the four sums of a pixel pair are evaluated once per orbit under the
+pi/2 rotation about the pole and stored at all four images -- a quarter of the recurrence work for the same matrix);
+a rank then owns an in-face column range of all twelve base faces.  --no-orbit runs every pair (cmg_tqu, equal-area
+pixel-column blocks).
 
 Numbers printed (one JSON line from rank 0):
   value     pixel-pair*l/s over the K timed steps, inputs resident in HBM (geometry + C_l weights), CUDA events
             on the launch stream, max over ranks;
   e2e       the same metric through the reference-facing call with HOST buffers: C_l from pinned host memory
             in, packed matrix (this rank's shard) copied back to pinned host memory, copies inside the timing;
-  roofline  algorithmic FLOP (20 per pixel-pair*l for T,Q,U; 4 for TT) / kernel time vs the FP64 peak
-            measured by cmg_measure_fp64_peak on this GPU (MEASURED_PEAKS.json has no FP64 entry);
+  roofline  algorithmic FLOP (20 per EVALUATED pixel-pair*l for T,Q,U; 4 for TT) / kernel time vs the FP64 peak
+            measured by cmg_measure_fp64_peak on this GPU (MEASURED_PEAKS.json has no FP64 entry); on the orbit path only
+            a quarter of the pairs are evaluated, `value` counts all pairs of the matrix that was produced;
   cpu_baseline  the reference's own object code (oracle/_ref, TT generator) on a bounded sample, all host cores.
 """
 import argparse
@@ -186,12 +191,17 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def config_dict(name, kind, nside, lmax, npix, n_gpus, shard_mode="outbox"):
+def config_dict(name, kind, nside, lmax, npix, n_gpus, shard_mode="outbox", orbit=False):
     dim = npix * (3 if kind == "tqu" else 1)
+    sharding = "equal-area pixel-column blocks over %d rank(s), no collective" % n_gpus
+    if orbit:
+        sharding = "in-face column ranges of all 12 base faces (orbit-closed sets of pixel columns) over %d rank(s), no collective" % n_gpus
     return {
         "workload": name, "kind": kind, "nside": nside, "lmax": lmax, "npix": npix, "matrix_dim": dim,
         "packed_bytes": 8 * dim * (dim + 1) // 2, "fwhm_deg": FWHM, "pixel_window": "1 (HEALPix window file unavailable offline)",
-        "sharding": "equal-area pixel-column blocks over %d rank(s), no collective" % n_gpus, "shard_mode": shard_mode if n_gpus > 1 else "single",
+        "path": "symmetry orbits (cmg_tqu_orbit): one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid, "
+                "all images stored" if orbit else "every pixel pair evaluated",
+        "sharding": sharding, "shard_mode": shard_mode if n_gpus > 1 else "single",
         "l2": "each step writes its whole output (>> 126 MB L2) with streaming stores; nothing is re-read between steps",
     }
 
@@ -220,6 +230,11 @@ def run_gpu_arm(args):
     ctx.set_stream(stream.cuda_stream)
     ctx.set_pixels(nside, good)
 
+    # full-sky T,Q,U: the symmetry-orbit path (needs whole 64 x 32 tiles inside a base face and at least one column tile per rank)
+    use_orbit = (kind == "tqu" and good is None and nside >= 8 and 2 <= lmax <= 441 and not args.no_orbit
+                 and nside * nside // 32 >= world and args.shard_mode == "outbox")
+    if kind == "tqu" and not use_orbit and 2 <= lmax <= 441:
+        ctx.set_kernel_variant(142)          # pins the every-pair kernel for the whole-call e2e leg as well (0 = automatic routing)
     f = capi.window_beam(lmax, FWHM)
     bounds = partition.column_partition(npix, world, align=32)
     a0, a1 = bounds[rank], bounds[rank + 1]
@@ -236,10 +251,16 @@ def run_gpu_arm(args):
         from cosmopp_b200 import multigpu
         spectra = synthetic_cl(lmax, pol=True)
         weights = capi.tqu_weights(*spectra, f, f)
-        mode = args.shard_mode if world > 1 else "outbox"
-        sharded = multigpu.ShardedTQU(ctx, npix, rank, world, mode=mode)
-        lay = sharded.layout
-        launch = lambda: ctx.tqu(*weights, lay)
+        if use_orbit:
+            sharded = multigpu.OrbitShardedTQU(ctx, nside, rank, world, mode=0)
+            launch = lambda: sharded.generate(weights)
+            lay = None
+            my_pairs = sharded.pairs                      # pixel pairs this rank EVALUATES (a quarter of those it stores)
+        else:
+            mode = args.shard_mode if world > 1 else "outbox"
+            sharded = multigpu.ShardedTQU(ctx, npix, rank, world, mode=mode)
+            lay = sharded.layout
+            launch = lambda: ctx.tqu(*weights, lay)
         pieces = [b.tensor() for b in sharded.pieces()]
     d2h_bytes = sum(p.numel() for p in pieces) * 8
     h2d_bytes = (len(weights) if kind == "tt" else 4 * (lmax + 1)) * 8
@@ -292,22 +313,30 @@ def run_gpu_arm(args):
     traffic = None
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof) and world == 1:
-        entry = json.load(open(prof)).get(args.workload)
+        entry = json.load(open(prof)).get(args.workload + ("_orbit" if use_orbit else ""))
         traffic = entry["bytes"] if entry else None
     hbm_peak = None
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(mp):
         hbm_peak = json.load(open(mp)).get("hbm_gbs")
+    written = d2h_bytes
+    if use_orbit and world > 1:
+        # the outbox blocks are allocated dense; what the kernel writes is this rank's share of the 9 entries per stored pair
+        written = int(8 * 9 * total_pairs * (my_pairs / max(partition.orbit_pairs_in_range(0, nside * nside, nside * nside, 0), 1)))
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
         "peak_source": "cmg_measure_fp64_peak: dependent-free DFMA chains on this GPU in this run (MEASURED_PEAKS.json holds no FP64 figure)",
         "algorithmic_flop_per_unit": FLOP_PER_UNIT[kind],
-        "hbm_write_gbs": d2h_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": hbm_peak,
+        "evaluated_pixel_pairs": my_pairs, "stored_pixel_pairs_all_ranks": total_pairs,
+        "note": ("orbit path: FLOP counted for the pixel pairs actually evaluated (one per orbit); the matrix holds %.2fx as many"
+                 % (total_pairs / max(partition.orbit_pairs_in_range(0, nside * nside, nside * nside, 0), 1))) if use_orbit else None,
+        "hbm_write_gbs": written / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": hbm_peak,
+        "hbm_frac": (written / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
     }
 
     # ---- optional: whole matrix resident on every GPU (NCCL broadcasts of the strips over NVLink)
     gather = None
-    if args.gather and kind == "tqu" and world > 1:
+    if args.gather and kind == "tqu" and world > 1 and not use_orbit:
         full = torch.empty(capi.packed_size(3 * npix), dtype=torch.float64, device="cuda")
         sharded.gather_full(full)
         barrier()
@@ -372,7 +401,7 @@ def run_gpu_arm(args):
         line = {
             "metric": "pixel_pair_ell_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "ms_per_matrix": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world, args.shard_mode),
+            "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world, args.shard_mode, use_orbit),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "fp64_frac_of_peak": achieved / peak_tflops, "gather": gather,
         }
@@ -392,6 +421,7 @@ def main():
                     help="N>1, T,Q,U: keep entries owned by another rank in local blocks (outbox) or write them into the owner's strip "
                          "through CUDA-IPC peer memory over NVLink (peer)")
     ap.add_argument("--gather", action="store_true", help="N>1, T,Q,U: also time the NCCL gather of the whole matrix onto every GPU")
+    ap.add_argument("--no-orbit", action="store_true", help="full-sky T,Q,U: evaluate every pixel pair (cmg_tqu) instead of one per symmetry orbit")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

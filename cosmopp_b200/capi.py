@@ -33,6 +33,16 @@ class TquLayout(ctypes.Structure):
     ]
 
 
+class OrbitShard(ctypes.Structure):
+    """cmg_orbit_shard: a rank's pieces of a [T;Q;U] matrix generated over symmetry orbits (include/cmg.h)."""
+    _fields_ = [
+        ("q_begin", _i64),
+        ("q_end", _i64),
+        ("strip", (_vp * 12) * 3),
+        ("outbox", (_vp * 12) * 6),
+    ]
+
+
 def library_path():
     return os.path.join(HERE, "lib", "libcosmopp_b200.so")
 
@@ -88,6 +98,8 @@ _SIGNATURES = {
     "cmg_tqu_scatter_block": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_int, _vp]),
     "cmg_tqu_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(TquLayout)]),
     "cmg_tqu_orbit": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int]),
+    "cmg_tqu_orbit_sharded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(OrbitShard), ctypes.c_int]),
+    "cmg_tqu_orbit_assemble": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), ctypes.c_int, ctypes.c_int, _vp]),
     "cmg_tqu_orbit_plan": (ctypes.c_int, [_i64, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cmg_tqu_weights": (ctypes.c_int, [_vp] * 6 + [ctypes.c_int] + [_vp] * 4),
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
@@ -324,6 +336,15 @@ class Context:
         """EXPERIMENTAL full-sky path: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid."""
         a_tt, a_te, a_ee, a_bb = map(_f64, (a_tt, a_te, a_ee, a_bb))
         self._check(self._L.cmg_tqu_orbit(self._h, _p(a_tt), _p(a_te), _p(a_ee), _p(a_bb), len(a_tt) - 1, _p(d_packed), int(mode)))
+
+    def tqu_orbit_sharded(self, a_tt, a_te, a_ee, a_bb, shard, mode=0):
+        a_tt, a_te, a_ee, a_bb = map(_f64, (a_tt, a_te, a_ee, a_bb))
+        self._check(self._L.cmg_tqu_orbit_sharded(self._h, _p(a_tt), _p(a_te), _p(a_ee), _p(a_bb), len(a_tt) - 1,
+                                                  ctypes.byref(shard), int(mode)))
+
+    def tqu_orbit_assemble(self, shard, d_full, mode=0, parts=3):
+        """parts: 1 = strips, 2 = outbox blocks; place the strips of all ranks before any outbox (include/cmg.h)"""
+        self._check(self._L.cmg_tqu_orbit_assemble(self._h, ctypes.byref(shard), int(mode), int(parts), _p(d_full)))
 
     def tqu_scatter_block(self, d_block, col0, n_cols, ld, row0, kind, d_full):
         self._check(self._L.cmg_tqu_scatter_block(self._h, _p(d_block), col0, n_cols, ld, row0, kind, _p(d_full)))

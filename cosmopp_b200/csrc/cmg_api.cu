@@ -939,26 +939,67 @@ cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* nC
     return CMG_OK;
 }
 
-cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* att, const double* ate, const double* aee, const double* abb, int lmax,
-                         double* dPacked, int mode)
+namespace
 {
-    cmg_status s = checkReady(ctx, lmax);
-    if(s != CMG_OK) return s;
-    if(!att || !ate || !aee || !abb || !dPacked) return fail(ctx, CMG_EINVAL, "null argument");
+
+// checks a shard descriptor and turns it into the kernels' form (strip bases adjusted by the packed offset of their first column)
+cmg_status orbitShardDev(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, cmg::OrbitShardDev& sh)
+{
+    if(!shard) return fail(ctx, CMG_EINVAL, "null shard");
     if(mode != 0 && mode != 1) return fail(ctx, CMG_EINVAL, "orbit mode must be 0 (transposed images) or 1 (none)");
     if(!ctx->fullSky)
         return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs the full sky in NESTED order (cmg_set_pixels with good_nest = NULL)");
     if(ctx->nside < 8)
         return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs nside >= 8 (whole 64 x 32 tiles inside a base face)");
+    const int64_t facePix = ctx->nside * ctx->nside, n = ctx->npix;
+    if(shard->q_begin < 0 || shard->q_end > facePix || shard->q_begin > shard->q_end || shard->q_begin % cmg::PQ_TJ || shard->q_end % cmg::PQ_TJ)
+        return fail(ctx, CMG_EINVAL, "shard range must be multiples of 32 inside [0, nside^2]");
+    sh.q0 = static_cast<int>(shard->q_begin);
+    sh.q1 = static_cast<int>(shard->q_end);
+    const bool whole = sh.q0 == 0 && sh.q1 == facePix;
+    cmg::OrbitPlan plan;
+    cmg::orbitBuildPlan(ctx->nside, mode, -1, plan);
+    bool need[6][12] = {};
+    for(int c = 0; c < plan.n; ++c)
+        for(int k = 0; k < plan.c[c].nImg; ++k)
+            for(int t = 0; t < (plan.c[c].imgSwap[k] ? 6 : 3); ++t)
+                need[t][plan.c[c].imgColFace[k]] = true;
+    for(int f = 0; f < 12; ++f)
+    {
+        for(int s = 0; s < 3; ++s)
+        {
+            if(!shard->strip[s][f] && sh.q1 > sh.q0) return fail(ctx, CMG_EINVAL, "shard: null strip");
+            sh.strip[s][f] = shard->strip[s][f] - cmg::packedOffset(s * n + f * facePix + sh.q0);
+        }
+        for(int t = 0; t < 6; ++t)
+        {
+            if(!whole && need[t][f] && !shard->outbox[t][f] && sh.q1 > sh.q0) return fail(ctx, CMG_EINVAL, "shard: an outbox block this mode writes is null");
+            sh.outbox[t][f] = shard->outbox[t][f];
+        }
+    }
+    return CMG_OK;
+}
+
+} // namespace
+
+cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* att, const double* ate, const double* aee, const double* abb, int lmax,
+                                 const cmg_orbit_shard* shard, int mode)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!att || !ate || !aee || !abb) return fail(ctx, CMG_EINVAL, "null weights");
+    cmg::OrbitShardDev sh;
+    if((s = orbitShardDev(ctx, shard, mode, sh)) != CMG_OK) return s;
     if(lmax < 2 || lmax > cmg::PQ_STATIC_LMAX)
         return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs 2 <= lmax <= PQ_STATIC_LMAX");
+    if(sh.q0 == sh.q1) return CMG_OK;
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
 
     static thread_local cmg::TquStaticTable T;      // 28 KB: keep it off the stack
     fillStaticTable(ctx, att, ate, aee, abb, lmax, T);
     const int entrySlot = cmg::PQ_STATIC_STEPS + 1 - lmax;
     const int64_t facePix = ctx->nside * ctx->nside;
-    const unsigned tiles = static_cast<unsigned>((facePix / cmg::PQ_TI) * (facePix / cmg::PQ_TJ));
+    const unsigned tiles = static_cast<unsigned>((facePix / cmg::PQ_TI) * ((sh.q1 - sh.q0) / cmg::PQ_TJ));
 
     KernelTimer timer(ctx);
     for(int half = 0; half < 2; ++half)              // classes without / with a transposed image
@@ -973,19 +1014,65 @@ cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* att, const double* ate, con
             auto kernel = cmg::tquOrbitKernel<4, 2, false>;
             const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<false>();
             CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, dPacked);
+            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
         }
         else
         {
             auto kernel = cmg::tquOrbitKernel<4, 2, true>;
             const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<true>();
             CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, dPacked);
+            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
         }
         CMG_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }
     return timer.finish();
+}
+
+cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* att, const double* ate, const double* aee, const double* abb, int lmax,
+                         double* dPacked, int mode)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!dPacked) return fail(ctx, CMG_EINVAL, "null output");
+    if(ctx->npix <= 0) return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
+    cmg_orbit_shard shard;
+    std::memset(&shard, 0, sizeof(shard));
+    const int64_t facePix = ctx->nside * ctx->nside, n = ctx->npix;
+    shard.q_begin = 0;
+    shard.q_end = facePix;
+    for(int st = 0; st < 3; ++st)
+        for(int f = 0; f < 12; ++f)
+            shard.strip[st][f] = dPacked + cmg::packedOffset(st * n + f * facePix);
+    return cmg_tqu_orbit_sharded(ctx, att, ate, aee, abb, lmax, &shard, mode);
+}
+
+cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, int parts, double* dFull)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!dFull) return fail(ctx, CMG_EINVAL, "null output");
+    if(ctx->npix <= 0) return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
+    cmg::OrbitShardDev sh;
+    cmg_status s = orbitShardDev(ctx, shard, mode, sh);
+    if(s != CMG_OK) return s;
+    if(sh.q0 == sh.q1) return CMG_OK;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t facePix = ctx->nside * ctx->nside, n = ctx->npix;
+    for(int st = 0; st < 3 && (parts & 1); ++st)
+        for(int f = 0; f < 12; ++f)
+        {
+            const int64_t first = cmg::packedOffset(st * n + f * facePix + sh.q0), last = cmg::packedOffset(st * n + f * facePix + sh.q1);
+            if(shard->strip[st][f] != dFull + first)
+                CMG_CUDA(ctx, cudaMemcpyAsync(dFull + first, shard->strip[st][f], sizeof(double) * (last - first), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    if((sh.q0 == 0 && sh.q1 == facePix) || !(parts & 2))
+        return CMG_OK;
+    cmg::OrbitPlan plan;
+    cmg::orbitBuildPlan(ctx->nside, mode, -1, plan);
+    const unsigned tiles = static_cast<unsigned>((facePix / cmg::PQ_TI) * ((sh.q1 - sh.q0) / cmg::PQ_TJ));
+    cmg::orbitOutboxScatterKernel<<<dim3(tiles, static_cast<unsigned>(plan.n)), cmg::PQ_THREADS, 0, ctx->stream>>>(n, plan, sh, dFull);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
 }
 
 cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch, double* dOut, int64_t stride)
@@ -1178,9 +1265,17 @@ cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* 
     cmg_tqu_weights(ctt, cte, cee, cbb, fT.data(), fP.data(), lmax, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1);
     const int64_t bytes = sizeof(double) * cmg_packed_size(3 * ctx->npix);
     if((s = ensureScratch(ctx, bytes)) != CMG_OK) return s;
-    cmg_tqu_layout layout;
-    if((s = cmg_tqu_layout_single(ctx, ctx->dScratch, &layout)) != CMG_OK) return s;
-    if((s = cmg_tqu(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, &layout)) != CMG_OK) return s;
+    if(ctx->fullSky && ctx->nside >= 8 && lmax >= 2 && lmax <= cmg::PQ_STATIC_LMAX && ctx->tquVariant == 0)
+    {
+        // full sky: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid (orbit.cuh), a quarter of the work
+        if((s = cmg_tqu_orbit(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, ctx->dScratch, 0)) != CMG_OK) return s;
+    }
+    else
+    {
+        cmg_tqu_layout layout;
+        if((s = cmg_tqu_layout_single(ctx, ctx->dScratch, &layout)) != CMG_OK) return s;
+        if((s = cmg_tqu(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, &layout)) != CMG_OK) return s;
+    }
     CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CMG_OK;

@@ -99,6 +99,20 @@ inline void orbitBuildPlan(int64_t nside, int mode, int swapClasses, OrbitPlan& 
     }
 }
 
+// Where a rank's entries live.  A rank owns the in-face column range [q0, q1) of ALL twelve base faces (an orbit-closed set
+// of pixel columns): it evaluates the source pairs whose column pixel has q in that range and stores every image.
+//   strip[s][f]   ADJUSTED base of the packed columns s N + f F + [q0, q1): entry (row, col) at strip[s][f] + col (col+1)/2 + row
+//   outbox[t][f]  entries whose packed column belongs to another rank (the row pixel a' of the pair has q outside [q0, q1)):
+//                 kind t (0 <Q T>, 1 <U T>, 2 <U Q>, 3 <T T>, 4 <Q Q>, 5 <U U>), column pixel b' in face f:
+//                 element at outbox[t][f] + a' (q1 - q0) + (q_b' - q0)
+// One rank (q0 = 0, q1 = F): every strip[s][f] is the base of the whole packed triangle and no outbox is touched.
+struct OrbitShardDev
+{
+    int q0, q1;
+    double* strip[3][12];
+    double* outbox[6][12];
+};
+
 // shared memory of tquOrbitKernel: frames of rows and columns, staged entries, column pointers of every image
 template <bool SWAP>
 constexpr int orbitSmemDoubles()
@@ -106,15 +120,27 @@ constexpr int orbitSmemDoubles()
     return 8 * PQ_TI + 8 * PQ_TJ + (SWAP ? 6 : 3) * PQ_TI * PQ_STAGE_LD + ORB_MAX_IMAGES * 3 * PQ_TJ;
 }
 
+// staged kind t -> (column strip X, row strip Y) of the entry <X a', Y b'>
+__device__ __forceinline__ int orbitStripX(int t) { return t == 0 ? 1 : (t == 1 || t == 2 || t == 5) ? 2 : (t == 4 ? 1 : 0); }
+__device__ __forceinline__ int orbitStripY(int t) { return t == 2 ? 1 : (t == 4 ? 1 : (t == 5 ? 2 : 0)); }
+
+// tile of a CTA: class blockIdx.y, 64 rows x 32 columns of in-face indices; false = nothing to do (q_row > q_col everywhere)
+__device__ __forceinline__ bool orbitTile(const OrbitPlan& plan, const OrbitShardDev& sh, int& qRow0, int& qCol0)
+{
+    const int tilesPerFaceRows = plan.facePix / PQ_TI;
+    qRow0 = static_cast<int>(blockIdx.x % tilesPerFaceRows) * PQ_TI;
+    qCol0 = sh.q0 + static_cast<int>(blockIdx.x / tilesPerFaceRows) * PQ_TJ;
+    return !(plan.c[blockIdx.y].tri && qRow0 > qCol0 + PQ_TJ - 1);
+}
+
 // One CTA = one 64 x 32 tile of pixel pairs of a class (blockIdx.y), evaluated exactly as tquKernel does, stored at
 // every image.  Entries whose contiguous direction is the column pixel go through the shared-memory stage: the three
 // transposed partners <Q_a T_b>, <U_a T_b>, <U_a Q_b> for every image, and <T T>, <Q Q>, <U U> as well for a
 // transposed image (there the row image a' has the larger index, so (X a', X b') is stored in column X a').
-// base = entry (0, 0) of the whole packed [T;Q;U] triangle (single owner).
 template <int R, int MINB, bool SWAP>
 __global__ void __launch_bounds__(PQ_THREADS, MINB)
 tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entrySlot,
-               const __grid_constant__ OrbitPlan plan, double* __restrict__ base)
+               const __grid_constant__ OrbitPlan plan, const __grid_constant__ OrbitShardDev sh)
 {
     extern __shared__ double4 orbSmem[];
     constexpr int SLOTS = SWAP ? 6 : 3;
@@ -123,14 +149,12 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     double* stage = sJ + 8 * PQ_TJ;                                  // [SLOTS][PQ_TI][PQ_STAGE_LD]
     double** sColPtr = reinterpret_cast<double**>(stage + SLOTS * PQ_TI * PQ_STAGE_LD);   // [image][3][PQ_TJ]
 
+    int qRow0, qCol0;
+    if(!orbitTile(plan, sh, qRow0, qCol0))
+        return;
     const OrbitClass& oc = plan.c[blockIdx.y];
     const int facePix = plan.facePix;
-    const int tilesPerFaceRows = facePix / PQ_TI;
-    const int qRow0 = static_cast<int>(blockIdx.x % tilesPerFaceRows) * PQ_TI;
-    const int qCol0 = static_cast<int>(blockIdx.x / tilesPerFaceRows) * PQ_TJ;
     const int tri = oc.tri;
-    if(tri && qRow0 > qCol0 + PQ_TJ - 1)
-        return;
 
     const long long npix = geo.npix;
     const long long rowBlock = static_cast<long long>(oc.rowFace) * facePix + qRow0;
@@ -154,14 +178,15 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
         dst[6 * ld + loc] = geo.px[pix];
         dst[7 * ld + loc] = geo.py[pix];
     }
-    // row 0 of columns b', N + b', 2N + b' for the column pixels b' of every image
+    // row 0 of columns b', N + b', 2N + b' for the column pixels b' of every image (always this rank's own strips)
     for(int idx = tid; idx < ORB_MAX_IMAGES * 3 * PQ_TJ; idx += PQ_THREADS)
     {
         const int k = idx / (3 * PQ_TJ);
         const int rem = idx - k * 3 * PQ_TJ;
         const int strip = rem / PQ_TJ;
-        const long long col = strip * npix + static_cast<long long>(oc.imgColFace[k]) * facePix + qCol0 + (rem - strip * PQ_TJ);
-        sColPtr[idx] = base + packedOffset(col);
+        const int face = oc.imgColFace[k];
+        const long long col = strip * npix + static_cast<long long>(face) * facePix + qCol0 + (rem - strip * PQ_TJ);
+        sColPtr[idx] = sh.strip[strip][face] + packedOffset(col);
     }
     __syncthreads();
 
@@ -266,28 +291,73 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     __syncthreads();
 
     // entries whose contiguous direction is the column pixel: for fixed row pixel a' the 32 column pixels of the tile
-    // are consecutive rows of column (X a'); one warp store per (image, entry kind, a')
+    // are consecutive rows of column (X a'); one warp store per (image, entry kind, a').  Column (X a') is this rank's
+    // when q_a lies in its range, else the run goes to the outbox block of (kind, face of b').
     const int sameFace = oc.sameFace;
+    const int ldOut = sh.q1 - sh.q0;
+    const int qColLane = qCol0 + lane;
     for(int k = 0; k < nImg; ++k)
     {
         const bool swapped = SWAP && oc.imgSwap[k];
-        const int nRows = (swapped ? 6 : 3) * PQ_TI;
-        const long long rowPix0 = static_cast<long long>(oc.imgRowFace[k]) * facePix + qRow0;
-        const long long colPix0 = static_cast<long long>(oc.imgColFace[k]) * facePix + qCol0;
+        const int nKinds = swapped ? 6 : 3;
+        const int rowFace = oc.imgRowFace[k], colFace = oc.imgColFace[k];
+        const long long rowPix0 = static_cast<long long>(rowFace) * facePix + qRow0;
+        const long long colPix0 = static_cast<long long>(colFace) * facePix + qCol0;
         // q_col - q_row must be >= minGap: none for whole face pairs; 1 where q_row == q_col is one pixel (its partners
         // are the direct entries) or belongs to image 0 (transposed images of a q_row <= q_col class); else 0
         const int minGap = !tri ? -(1 << 30) : ((sameFace || swapped) ? 1 : 0);
+        for(int t = 0; t < nKinds; ++t)
+        {
+            // bases of this (image, kind), looked up once: own strip X of the row face, outbox block of the column face
+            const long long colStrip = orbitStripX(t) * npix + rowPix0;
+            double* const ownBase = sh.strip[orbitStripX(t)][rowFace] + (orbitStripY(t) * npix + colPix0 + lane);
+            double* const boxBase = sh.outbox[t][colFace] + (qCol0 - sh.q0 + lane);
+            const double* src = stage + (t * PQ_TI) * PQ_STAGE_LD + lane;
+#pragma unroll
+            for(int u = 0; u < PQ_TI / (PQ_THREADS / 32); ++u)
+            {
+                const int ilr = warp + u * (PQ_THREADS / 32);
+                const int qa = qRow0 + ilr;
+                if(qColLane - qa >= minGap)
+                {
+                    double* dst = (qa >= sh.q0 && qa < sh.q1) ? ownBase + packedOffset(colStrip + ilr)
+                                                              : boxBase + (rowPix0 + ilr) * ldOut;
+                    __stcs(dst, src[ilr * PQ_STAGE_LD]);
+                }
+            }
+        }
+    }
+}
+
+// Outbox blocks of a rank -> their places in a whole packed triangle (assembly of the unsharded matrix): the same tiles,
+// images and predicates as the last phase of tquOrbitKernel, reading the block instead of the stage.
+__global__ void __launch_bounds__(PQ_THREADS)
+orbitOutboxScatterKernel(long long npix, const __grid_constant__ OrbitPlan plan, const __grid_constant__ OrbitShardDev sh,
+                         double* __restrict__ full)
+{
+    int qRow0, qCol0;
+    if(!orbitTile(plan, sh, qRow0, qCol0))
+        return;
+    const OrbitClass& oc = plan.c[blockIdx.y];
+    const int facePix = plan.facePix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ldOut = sh.q1 - sh.q0;
+    for(int k = 0; k < oc.nImg; ++k)
+    {
+        const bool swapped = oc.imgSwap[k] != 0;
+        const int nRows = (swapped ? 6 : 3) * PQ_TI;
+        const long long rowPix0 = static_cast<long long>(oc.imgRowFace[k]) * facePix + qRow0;
+        const long long colPix0 = static_cast<long long>(oc.imgColFace[k]) * facePix + qCol0;
+        const int minGap = !oc.tri ? -(1 << 30) : ((oc.sameFace || swapped) ? 1 : 0);
         for(int row = warp; row < nRows; row += PQ_THREADS / 32)
         {
             const int t = row / PQ_TI;
             const int ilr = row - t * PQ_TI;
-            // t: 0 <Q T>, 1 <U T>, 2 <U Q>, 3 <T T>, 4 <Q Q>, 5 <U U>  ->  column strip X, row strip Y
-            const int stripX = t == 0 ? 1 : (t == 1 || t == 2 || t == 5) ? 2 : (t == 4 ? 1 : 0);
-            const int stripY = t == 2 ? 1 : (t == 4 ? 1 : (t == 5 ? 2 : 0));
-            if((qCol0 + lane) - (qRow0 + ilr) >= minGap)
+            const int qa = qRow0 + ilr;
+            if((qCol0 + lane) - qa >= minGap && !(qa >= sh.q0 && qa < sh.q1))
             {
-                double* dst = base + packedOffset(stripX * npix + rowPix0 + ilr) + (stripY * npix + colPix0 + lane);
-                __stcs(dst, stage[row * PQ_STAGE_LD + lane]);
+                const double v = sh.outbox[t][oc.imgColFace[k]][(rowPix0 + ilr) * ldOut + (qCol0 - sh.q0 + lane)];
+                full[packedOffset(orbitStripX(t) * npix + rowPix0 + ilr) + (orbitStripY(t) * npix + colPix0 + lane)] = v;
             }
         }
     }

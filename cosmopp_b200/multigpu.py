@@ -113,3 +113,54 @@ class ShardedTQU:
         self.peer_ptrs = {}
         for b in self.pieces():
             b.free()
+
+
+
+class OrbitShardedTQU:
+    """Rank-local storage of a full-sky [T;Q;U] matrix generated over symmetry orbits (cmg_tqu_orbit_sharded): the rank owns
+    the in-face column range [q0, q1) of all twelve base faces -- 36 contiguous runs of packed columns -- plus dense outbox
+    blocks for the entries whose packed column is another rank's.  No data-path collective."""
+
+    def __init__(self, ctx, nside, rank, world, mode=0):
+        self.ctx, self.nside, self.rank, self.world, self.mode = ctx, nside, rank, world, mode
+        self.face_pix = nside * nside
+        self.npix = 12 * self.face_pix
+        self.bounds = partition.orbit_partition(nside, world, mode)
+        self.q0, self.q1 = self.bounds[rank], self.bounds[rank + 1]
+        sizes = partition.orbit_strip_sizes(nside, self.q0, self.q1)
+        # one allocation for the 36 strips: the pieces stay individually contiguous pieces of the packed triangle
+        self.strip_sizes = sizes
+        self.strips = DeviceBuffer(ctx, sum(sum(r) for r in sizes))
+        self.shard = capi.OrbitShard()
+        self.shard.q_begin, self.shard.q_end = self.q0, self.q1
+        off = 0
+        self.strip_offsets = [[0] * 12 for _ in range(3)]
+        for s in range(3):
+            for f in range(12):
+                self.strip_offsets[s][f] = off
+                self.shard.strip[s][f] = self.strips.ptr + 8 * off
+                off += sizes[s][f]
+        self.outbox = None
+        self.outbox_kinds = []
+        if world > 1 and self.q1 > self.q0:
+            self.outbox_kinds = partition.orbit_outbox_kinds(capi.orbit_plan(nside, mode))
+            block = self.npix * (self.q1 - self.q0)
+            self.outbox = DeviceBuffer(ctx, block * len(self.outbox_kinds))
+            for i, (t, f) in enumerate(self.outbox_kinds):
+                self.shard.outbox[t][f] = self.outbox.ptr + 8 * block * i
+        self.pairs = partition.orbit_pairs_in_range(self.q0, self.q1, self.face_pix, mode)
+
+    def generate(self, weights):
+        self.ctx.tqu_orbit_sharded(*weights, self.shard, self.mode)
+
+    def pieces(self):
+        return [self.strips] + ([self.outbox] if self.outbox is not None else [])
+
+    def assemble_into(self, full, parts=3):
+        """place this rank's pieces into a whole packed triangle on this GPU (parts: 1 strips, 2 outbox; the strips of all
+        ranks go in before any outbox, a strip has holes where another rank's outbox holds the entry)"""
+        self.ctx.tqu_orbit_assemble(self.shard, full, self.mode, parts)
+
+    def close(self):
+        for b in self.pieces():
+            b.free()

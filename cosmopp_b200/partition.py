@@ -86,3 +86,55 @@ def batch_partition(n_batch, n_parts, slab=16):
         b.append(min(n_batch, slab * ((slabs * k) // n_parts)))
     b.append(n_batch)
     return b
+
+
+# ---------------------------------------------------------------- symmetry-orbit path (cmg_tqu_orbit_sharded)
+
+def orbit_column_cost(q, face_pix, mode=0):
+    """source pixel pairs evaluated for the in-face column index q: whole-face classes contribute face_pix rows each,
+    q_row <= q_col classes q + 1 (cosmopp_b200/csrc/orbit.cuh: 15 + 6 classes with transposed images, 21 + 3 without)"""
+    full, tri = (15, 6) if mode == 0 else (21, 3)
+    return full * face_pix + tri * (q + 1)
+
+
+def orbit_partition(nside, n_parts, mode=0, align=32):
+    """Boundaries b[0..n_parts] of the in-face column index (0 .. nside^2) giving every rank the same number of source pixel
+    pairs; a rank owns the columns q in [b[r], b[r+1]) of ALL twelve base faces (an orbit-closed set)."""
+    face_pix = nside * nside
+    if n_parts < 1 or face_pix % align:
+        raise ValueError("n_parts must be >= 1 and nside^2 a multiple of the column tile")
+    full, tri = (15, 6) if mode == 0 else (21, 3)
+    total = full * face_pix * face_pix + tri * face_pix * (face_pix + 1) // 2
+    b = [0]
+    for k in range(1, n_parts):
+        # cumulative cost up to q: full F q + tri q (q + 1) / 2 = target  ->  solve the quadratic
+        target = total * k / n_parts
+        a2, a1 = tri / 2.0, full * face_pix + tri / 2.0
+        q = (-a1 + math.sqrt(a1 * a1 + 4 * a2 * target)) / (2 * a2)
+        v = int(round(q / align)) * align
+        b.append(max(b[-1], min(face_pix, v)))
+    b.append(face_pix)
+    return b
+
+
+def orbit_pairs_in_range(q0, q1, face_pix, mode=0):
+    """source pixel pairs a rank owning [q0, q1) evaluates"""
+    full, tri = (15, 6) if mode == 0 else (21, 3)
+    return full * face_pix * (q1 - q0) + tri * (q1 * (q1 + 1) - q0 * (q0 + 1)) // 2
+
+
+def orbit_strip_sizes(nside, q0, q1):
+    """doubles in the 3 x 12 packed column runs s N + f nside^2 + [q0, q1) a rank owns"""
+    face_pix = nside * nside
+    n = 12 * face_pix
+    return [[packed_size(s * n + f * face_pix + q1) - packed_size(s * n + f * face_pix + q0) for f in range(12)] for s in range(3)]
+
+
+def orbit_outbox_kinds(plan):
+    """(kind t, face f) outbox blocks a plan writes: kinds 0..2 for every image, 3..5 for transposed images"""
+    need = set()
+    for c in plan:
+        for _, col_face, swap in c["images"]:
+            for t in range(6 if swap else 3):
+                need.add((t, col_face))
+    return sorted(need)

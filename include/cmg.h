@@ -191,6 +191,26 @@ cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* d_a, int lmax, const cmg_tqu_
  * Needs cmg_set_pixels(ctx, nside >= 8, NULL, 0), 2 <= lmax <= 441, a single-owner packed buffer d_packed of dimension 3N. */
 cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
                          const double* a_bb, int lmax, double* d_packed, int mode);
+/* The same over several GPUs with no data-path collective.  A rank owns the in-face index range [q_begin, q_end) of ALL
+ * twelve base faces -- an orbit-closed set of pixel columns -- evaluates the source pairs whose column pixel lies there and
+ * stores all their images:
+ *   strip[s][f]   address of entry (0, s N + f nside^2 + q_begin): the packed columns s N + f nside^2 + [q_begin, q_end), one
+ *                 contiguous piece of the packed triangle each (s = T, Q, U strip; f = base face);
+ *   outbox[t][f]  entries whose packed column belongs to another rank (row pixel a' of the pair outside the range):
+ *                 kind t = <Q_a' T_b'>, <U T>, <U Q>, and for transposed images (mode 0) <T T>, <Q Q>, <U U>, column pixel b'
+ *                 in face f; dense column-major, element at outbox[t][f][a' (q_end - q_begin) + (q_b' - q_begin)], a' in [0, N).
+ *                 Not touched (may be NULL) when the range is the whole face.
+ * q_begin, q_end multiples of 32.  cmg_tqu_orbit_assemble places a rank's pieces (wherever they were moved to) into a whole
+ * packed triangle on this GPU: parts & 1 = its strips, parts & 2 = its outbox blocks.  A strip has holes where another rank's
+ * outbox holds the entry, so place the strips of ALL ranks before any outbox. */
+typedef struct cmg_orbit_shard {
+    int64_t q_begin, q_end;
+    double* strip[3][12];
+    double* outbox[6][12];
+} cmg_orbit_shard;
+cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
+                                 const double* a_bb, int lmax, const cmg_orbit_shard* shard, int mode);
+cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, int parts, double* d_full_packed);
 /* the classes of base-face pairs cmg_tqu_orbit works through (host only; for tests): out[c][CMG_ORBIT_CLASS_INTS] =
  * { row face, column face, only q_row <= q_col, same face, n_images, then for image k = 0..3: row face, column face,
  *   stored transposed }; out must hold CMG_ORBIT_MAX_CLASSES classes */

@@ -1,0 +1,114 @@
+"""GPU parity of the symmetry-orbit path (cmg_tqu_orbit, cmg_tqu_orbit_sharded; cosmopp_b200/csrc/orbit.cuh) against the
+CPU oracle: same gate as the every-pair kernel, 1e-11 of the diagonal of the block, layout position by position."""
+import numpy as np
+import pytest
+
+from conftest import synthetic_cl
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-11
+
+
+def _scale(n, want):
+    """per-entry scale: TT diagonal for the columns of the T strip, QQ diagonal elsewhere"""
+    from cosmopp_b200 import capi
+    dim = 3 * n
+    scale = np.full(capi.packed_size(dim), want[capi.packed_index(n, n)])
+    scale[:capi.packed_size(n)] = want[0]
+    return scale
+
+
+def _inputs(ctx, nside, lmax):
+    from cosmopp_b200 import capi
+    ctx.set_kernel_variant(0)
+    ctx.set_pixels(nside)
+    spectra = synthetic_cl(lmax, pol=True)
+    f = capi.window_beam(lmax, 10.0)
+    return spectra, capi.tqu_weights(*spectra, f, f)
+
+
+@pytest.mark.parametrize("nside,lmax", [(8, 20), (16, 47)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_orbit_matches_oracle(gpu_ctx, oracle_api, nside, lmax, mode):
+    import torch
+    from cosmopp_b200 import capi
+    spectra, w = _inputs(gpu_ctx, nside, lmax)
+    n = gpu_ctx.npix
+    out = torch.full((capi.packed_size(3 * n),), float("nan"), dtype=torch.float64, device="cuda")
+    gpu_ctx.tqu_orbit(*w, out, mode)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert not np.isnan(got).any()                      # every entry of the triangle is written
+    want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
+    assert (np.abs(got - want) / _scale(n, want)).max() <= REL_TOL
+    # and against the every-pair kernel: differences are roundings of n_i.n_j only
+    ref = torch.empty_like(out)
+    gpu_ctx.tqu(*w, gpu_ctx.tqu_layout_single(ref))
+    torch.cuda.synchronize()
+    assert (np.abs(got - ref.cpu().numpy()) / _scale(n, want)).max() <= 1e-13
+
+
+@pytest.mark.parametrize("world,mode", [(2, 0), (3, 0), (3, 1)])
+def test_orbit_shards_assemble_to_the_whole_matrix(gpu_ctx, oracle_api, world, mode):
+    """every rank's pieces (36 packed column runs + outbox blocks) generated on this GPU one after the other"""
+    import torch
+    from cosmopp_b200 import capi, multigpu
+    nside, lmax = 16, 30
+    spectra, w = _inputs(gpu_ctx, nside, lmax)
+    n = gpu_ctx.npix
+    ranks = [multigpu.OrbitShardedTQU(gpu_ctx, nside, r, world, mode) for r in range(world)]
+    assert [r.q0 for r in ranks][1:] == [r.q1 for r in ranks][:-1] and ranks[-1].q1 == nside * nside
+    for r in ranks:
+        for b in r.pieces():
+            b.tensor().fill_(float("nan"))
+        r.generate(w)
+    full = torch.full((capi.packed_size(3 * n),), float("nan"), dtype=torch.float64, device="cuda")
+    for parts in (1, 2):                                # strips of all ranks first, then the outboxes
+        for r in ranks:
+            r.assemble_into(full, parts)
+    torch.cuda.synchronize()
+    got = full.cpu().numpy()
+    for r in ranks:
+        r.close()
+    assert not np.isnan(got).any()
+    want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
+    assert (np.abs(got - want) / _scale(n, want)).max() <= REL_TOL
+
+
+def test_whole_call_takes_the_orbit_path_on_the_full_sky(gpu_ctx, oracle_api):
+    import torch
+    from cosmopp_b200 import capi
+    nside, lmax = 8, 16
+    gpu_ctx.set_kernel_variant(0)
+    gpu_ctx.set_pixels(nside)
+    spectra = synthetic_cl(lmax, pol=True)
+    out = torch.empty(capi.packed_size(3 * gpu_ctx.npix), dtype=torch.float64, pin_memory=True)
+    before = gpu_ctx.launches
+    gpu_ctx.cl_to_cmatrix_pol(*spectra, 10.0, out)
+    assert gpu_ctx.launches - before == 2               # the two launches of cmg_tqu_orbit (classes without / with transposed images)
+    want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
+    assert (np.abs(out.numpy() - want) / _scale(gpu_ctx.npix, want)).max() <= REL_TOL
+    gpu_ctx.set_kernel_variant(142)                     # a pinned variant switches the routing off
+    before = gpu_ctx.launches
+    gpu_ctx.cl_to_cmatrix_pol(*spectra, 10.0, out)
+    assert gpu_ctx.launches - before == 1
+    gpu_ctx.set_kernel_variant(0)
+    assert (np.abs(out.numpy() - want) / _scale(gpu_ctx.npix, want)).max() <= REL_TOL
+
+
+def test_orbit_path_refuses_what_it_cannot_do(gpu_ctx, oracle_api):
+    import torch
+    from cosmopp_b200 import capi
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(8))
+    gpu_ctx.set_pixels(8, good)
+    spectra = synthetic_cl(12, pol=True)
+    f = capi.window_beam(12, 10.0)
+    w = capi.tqu_weights(*spectra, f, f)
+    out = torch.empty(capi.packed_size(3 * gpu_ctx.npix), dtype=torch.float64, device="cuda")
+    with pytest.raises(capi.CmgError):
+        gpu_ctx.tqu_orbit(*w, out)                      # masked sky: no rotation symmetry
+    gpu_ctx.set_pixels(4)
+    out = torch.empty(capi.packed_size(3 * gpu_ctx.npix), dtype=torch.float64, device="cuda")
+    with pytest.raises(capi.CmgError):
+        gpu_ctx.tqu_orbit(*w, out)                      # nside < 8: a 64 x 32 tile does not fit a base face

@@ -59,17 +59,30 @@ def test_plan_covers_every_face_pair_once(mode):
     assert units == (18.0 if mode == 0 else 22.5)                                  # of 72 face-pair units
 
 
-def emulate_kernel_stores(plan, nside, n, M):
-    """What tquOrbitKernel stores, entry by entry, taking the nine values of a source pair from M."""
+def emulate_kernel_stores(plan, nside, n, M, q0=0, q1=None):
+    """What tquOrbitKernel stores for the rank owning the in-face columns [q0, q1), entry by entry, taking the nine values
+    of a source pair from M.  Returns the values and store counts per packed position for the rank's own strips and for its
+    outbox (already translated to packed positions, as orbitOutboxScatterKernel does), and the store count per outbox slot."""
     F = nside * nside
+    q1 = F if q1 is None else q1
+    ld = q1 - q0
     dim = 3 * n
-    out = np.full(capi.packed_size(dim), np.nan)
-    count = np.zeros(capi.packed_size(dim), dtype=np.int32)
+    size = capi.packed_size(dim)
+    out = np.full(size, np.nan)
+    count = np.zeros(size, dtype=np.int32)
+    box_out = np.full(size, np.nan)
+    box_count = np.zeros(size, dtype=np.int32)
+    slot_count = np.zeros((6, 12, n, max(ld, 1)), dtype=np.int8)
 
     def po(col):
         return col * (col + 1) // 2
 
-    def put(pos, val, live):
+    def owned(col):                      # packed column -> pixel -> in-face index inside [q0, q1)
+        q = (col % n) % F
+        return (q >= q0) & (q < q1)
+
+    def put(pos, col, val, live):
+        assert owned(col[live]).all()    # everything stored in the strips lies in this rank's own packed columns
         np.add.at(count, pos[live], 1)
         out[pos[live]] = val[live]
 
@@ -77,8 +90,8 @@ def emulate_kernel_stores(plan, nside, n, M):
     jl = np.arange(TJ)[None, :]
     for c in plan:
         for tr in range(F // TI):
-            for tc in range(F // TJ):
-                q_row0, q_col0 = tr * TI, tc * TJ
+            for tc in range(ld // TJ):
+                q_row0, q_col0 = tr * TI, q0 + tc * TJ
                 if c["tri"] and q_row0 > q_col0 + TJ - 1:
                     continue
                 a = c["row_face"] * F + q_row0 + il + 0 * jl
@@ -88,38 +101,79 @@ def emulate_kernel_stores(plan, nside, n, M):
                 for fr, fc, swap in c["images"]:
                     ip = fr * F + q_row0 + il + 0 * jl
                     jp = fc * F + q_col0 + jl + 0 * il
-                    col = [po(s * n + jp) for s in range(3)]                      # sColPtr
-                    direct = (not c["tri"]) | (dq >= 0)
+                    cols = [s * n + jp for s in range(3)]
+                    col = [po(x) for x in cols]                                   # sColPtr
+                    direct = ((not c["tri"]) | (dq >= 0)) & (ip >= 0)
                     if not swap:
-                        put(col[0] + ip, v[0, 0], direct)
-                        put(col[1] + ip, v[0, 1], direct)
-                        put(col[1] + n + ip, v[1, 1], direct)
-                        put(col[2] + ip, v[0, 2], direct)
-                        put(col[2] + n + ip, v[1, 2], direct)
-                        put(col[2] + 2 * n + ip, v[2, 2], direct)
+                        put(col[0] + ip, cols[0], v[0, 0], direct)
+                        put(col[1] + ip, cols[1], v[0, 1], direct)
+                        put(col[1] + n + ip, cols[1], v[1, 1], direct)
+                        put(col[2] + ip, cols[2], v[0, 2], direct)
+                        put(col[2] + n + ip, cols[2], v[1, 2], direct)
+                        put(col[2] + 2 * n + ip, cols[2], v[2, 2], direct)
                     else:
-                        strict = (not c["tri"]) | (dq > 0)
-                        put(col[1] + ip, v[0, 1], strict)
-                        put(col[2] + ip, v[0, 2], strict)
-                        put(col[2] + n + ip, v[1, 2], strict)
+                        strict = ((not c["tri"]) | (dq > 0)) & (ip >= 0)
+                        put(col[1] + ip, cols[1], v[0, 1], strict)
+                        put(col[2] + ip, cols[2], v[0, 2], strict)
+                        put(col[2] + n + ip, cols[2], v[1, 2], strict)
                     min_gap = -(1 << 30) if not c["tri"] else (1 if (c["same_face"] or swap) else 0)
                     staged = [(1, 0), (2, 0), (2, 1)] + ([(0, 0), (1, 1), (2, 2)] if swap else [])
-                    for X, Y in staged:
-                        put(po(X * n + ip) + Y * n + jp, v[X, Y], dq >= min_gap)
-    return out, count
+                    qa = q_row0 + il + 0 * jl
+                    local = (qa >= q0) & (qa < q1)
+                    for t, (X, Y) in enumerate(staged):
+                        live = dq >= min_gap
+                        pos = po(X * n + ip) + Y * n + jp
+                        put(pos, X * n + ip, v[X, Y], live & local)
+                        far = live & ~local
+                        np.add.at(box_count, pos[far], 1)
+                        box_out[pos[far]] = v[X, Y][far]
+                        np.add.at(slot_count, (t, fc, ip[far], (q_col0 - q0 + jl + 0 * il)[far]), 1)
+    return out, count, box_out, box_count, slot_count
+
+
+def packed_from_full(M):
+    dim = M.shape[0]
+    iu = np.triu_indices(dim)
+    want = np.empty(capi.packed_size(dim))
+    want[iu[1] * (iu[1] + 1) // 2 + iu[0]] = M[iu]
+    return want, iu
 
 
 @pytest.mark.parametrize("mode", [0, 1])
 def test_store_rules_fill_the_packed_triangle_exactly_once(oracle_matrix, mode):
     nside, n, M = oracle_matrix
-    out, count = emulate_kernel_stores(capi.orbit_plan(nside, mode), nside, n, M)
-    assert count.min() == 1 and count.max() == 1
-    dim = 3 * n
-    iu = np.triu_indices(dim)
-    want = np.empty(capi.packed_size(dim))
-    want[iu[1] * (iu[1] + 1) // 2 + iu[0]] = M[iu]
+    out, count, _, box_count, _ = emulate_kernel_stores(capi.orbit_plan(nside, mode), nside, n, M)
+    assert count.min() == 1 and count.max() == 1 and box_count.max() == 0
+    want, iu = packed_from_full(M)
     # images take the source pair's value: equal to the oracle's own entry up to the oracle's rounding
-    scale = np.where(iu[1] < n, M[0, 0], M[n, n])
-    err = np.empty(capi.packed_size(dim))
-    err[iu[1] * (iu[1] + 1) // 2 + iu[0]] = scale
-    assert (np.abs(out - want) / err).max() < 1e-11
+    scale = np.empty_like(want)
+    scale[iu[1] * (iu[1] + 1) // 2 + iu[0]] = np.where(iu[1] < n, M[0, 0], M[n, n])
+    assert (np.abs(out - want) / scale).max() < 1e-11
+
+
+@pytest.mark.parametrize("mode,world", [(0, 2), (1, 2), (0, 3)])
+def test_sharded_store_rules_partition_the_triangle(oracle_matrix, mode, world):
+    """Ranks own in-face column ranges of all twelve faces: together their strips and outbox blocks hold every entry once,
+    strip stores stay inside the rank's own packed columns, and no outbox slot is written twice."""
+    from cosmopp_b200 import partition
+    nside, n, M = oracle_matrix
+    plan = capi.orbit_plan(nside, mode)
+    bounds = partition.orbit_partition(nside, world, mode)
+    assert bounds[0] == 0 and bounds[-1] == nside * nside and all(b % 32 == 0 for b in bounds)
+    want, _ = packed_from_full(M)
+    total = np.zeros(want.size, dtype=np.int32)
+    merged = np.full(want.size, np.nan)
+    pairs = 0
+    for r in range(world):
+        out, count, box_out, box_count, slot_count = emulate_kernel_stores(plan, nside, n, M, bounds[r], bounds[r + 1])
+        assert slot_count.max() <= 1
+        assert slot_count.sum() == box_count.sum()
+        total += count + box_count
+        merged = np.where(count > 0, out, merged)
+        merged = np.where(box_count > 0, box_out, merged)
+        pairs += partition.orbit_pairs_in_range(bounds[r], bounds[r + 1], nside * nside, mode)
+    assert total.min() == 1 and total.max() == 1
+    assert np.abs(merged - want).max() < 1e-11 * M[n, n]
+    units = 18.0 if mode == 0 else 22.5
+    f = nside * nside
+    assert abs(pairs - units * f * f) <= 6 * f          # the q_row <= q_col classes include their diagonal

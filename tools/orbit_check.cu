@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -41,11 +42,107 @@ static void weights(int lmax, std::vector<double>& tt, std::vector<double>& te, 
 
 int main(int argc, char** argv)
 {
-    const int timingNside = argc > 1 ? std::atoi(argv[1]) : 64;
+    // modes: full (default) = all parity checks + timings; ranks = per-rank timings of the balanced 2/4/8-way partitions at
+    // Nside=64; prof = one cmg_tqu_orbit call at Nside=64 (what ncu profiles)
+    const std::string what = argc > 1 ? argv[1] : "full";
+    const int timingNside = 64;
     cmg_ctx* ctx = nullptr;
     if(cmg_create(&ctx, 0) != CMG_OK) { std::printf("no context: %s\n", cmg_last_error(nullptr)); return 1; }
     OK(cmg_set_timing(ctx, 1));
     int rc = 0;
+
+    if(what == "prof" || what == "ranks")
+    {
+        const int nside = 64, lmax = 192;
+        OK(cmg_set_pixels(ctx, nside, nullptr, 0));
+        const int64_t n = cmg_npix(ctx), F = (int64_t) nside * nside, packed = cmg_packed_size(3 * n);
+        std::vector<double> tt, te, ee, bb;
+        weights(lmax, tt, te, ee, bb);
+        if(what == "prof")
+        {
+            double* dA = nullptr;
+            OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
+            OK(cmg_tqu_orbit(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, dA, 0));
+            double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+            std::printf("prof: nside 64 lmax 192 mode 0: %.2f ms\n", ms);
+            cmg_destroy(ctx);
+            return 0;
+        }
+        {
+            double* dA = nullptr;
+            OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
+            for(int mode = 1; mode >= 0; --mode)
+            {
+                double best = 1e30;
+                for(int rep = 0; rep < 4; ++rep)
+                {
+                    OK(cmg_tqu_orbit(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, dA, mode));
+                    double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+                    best = std::min(best, ms);
+                }
+                std::printf("nside 64 lmax 192, one rank, mode %d: %.2f ms\n", mode, best);
+            }
+            OK(cmg_device_free(ctx, dA));
+        }
+        const int worlds[3] = {2, 4, 8};
+        for(int world : worlds)
+        {
+            // boundaries of equal numbers of evaluated pairs (cosmopp_b200/partition.py: orbit_partition, mode 0): cumulative
+            // cost up to q = 15 F q + 6 q (q + 1) / 2
+            std::vector<int64_t> b(world + 1, 0);
+            const double total = 15.0 * F * F + 3.0 * F * (F + 1);
+            for(int k = 1; k < world; ++k)
+            {
+                const double target = total * k / world, a2 = 3.0, a1 = 15.0 * F + 3.0;
+                const double q = (-a1 + std::sqrt(a1 * a1 + 4 * a2 * target)) / (2 * a2);
+                b[k] = std::min<int64_t>(F, std::max<int64_t>(b[k - 1], (int64_t) std::llround(q / 32) * 32));
+            }
+            b[world] = F;
+            double worst = 0, sum = 0;
+            for(int r = 0; r < world; ++r)
+            {
+                cmg_orbit_shard sh;
+                std::memset(&sh, 0, sizeof(sh));
+                sh.q_begin = b[r];
+                sh.q_end = b[r + 1];
+                const int64_t ld = sh.q_end - sh.q_begin;
+                int64_t stripDoubles = 0;
+                for(int st = 0; st < 3; ++st)
+                    for(int f = 0; f < 12; ++f)
+                        stripDoubles += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
+                double *dStrips = nullptr, *dBox = nullptr;
+                OK(cmg_device_malloc(ctx, stripDoubles * 8, (void**) &dStrips));
+                OK(cmg_device_malloc(ctx, 54 * n * ld * 8, (void**) &dBox));
+                int64_t off = 0;
+                for(int st = 0; st < 3; ++st)
+                    for(int f = 0; f < 12; ++f)
+                    {
+                        sh.strip[st][f] = dStrips + off;
+                        off += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
+                    }
+                int blk = 0;                                   // kinds 0..2 for every face, 3..5 for positions 0 and 1 of a ring
+                for(int t = 0; t < 6; ++t)
+                    for(int f = 0; f < 12; ++f)
+                        if(t < 3 || (f & 3) < 2)
+                            sh.outbox[t][f] = dBox + (blk++) * n * ld;
+                double best = 1e30;
+                for(int rep = 0; rep < 3; ++rep)
+                {
+                    OK(cmg_tqu_orbit_sharded(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, &sh, 0));
+                    double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+                    best = std::min(best, ms);
+                }
+                worst = std::max(worst, best);
+                sum += best;
+                std::printf("  world %d rank %d: q [%lld, %lld): %.3f ms\n", world, r, (long long) sh.q_begin, (long long) sh.q_end, best);
+                OK(cmg_device_free(ctx, dStrips));
+                OK(cmg_device_free(ctx, dBox));
+            }
+            std::printf("nside 64 lmax 192, %d ranks (one after the other on this GPU), mode 0: slowest %.3f ms, mean %.3f ms\n", world, worst, sum / world);
+        }
+        cmg_destroy(ctx);
+        return 0;
+    }
 
     // full comparison at sizes that fit twice
     const int cases[][2] = {{8, 20}, {16, 47}, {32, 96}};
@@ -96,6 +193,135 @@ int main(int argc, char** argv)
         }
         OK(cmg_device_free(ctx, dA));
         OK(cmg_device_free(ctx, dB));
+    }
+
+    // sharded: every rank's pieces generated one after the other on this GPU, assembled, compared with cmg_tqu
+    const int shardCases[][3] = {{16, 47, 2}, {16, 47, 3}, {32, 96, 8}};
+    for(const auto& cs : shardCases)
+    {
+        const int nside = cs[0], lmax = cs[1], world = cs[2];
+        OK(cmg_set_pixels(ctx, nside, nullptr, 0));
+        const int64_t n = cmg_npix(ctx), packed = cmg_packed_size(3 * n), F = (int64_t) nside * nside;
+        std::vector<double> tt, te, ee, bb;
+        weights(lmax, tt, te, ee, bb);
+        double *dA = nullptr, *dB = nullptr;
+        OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
+        OK(cmg_device_malloc(ctx, packed * 8, (void**) &dB));
+        cmg_tqu_layout lay;
+        OK(cmg_tqu_layout_single(ctx, dA, &lay));
+        OK(cmg_tqu(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, &lay));
+        std::vector<double> hA(packed), hB(packed);
+        OK(cmg_copy_to_host(ctx, hA.data(), dA, packed * 8));
+        OK(cmg_synchronize(ctx));
+        const double dT = hA[0], dQ = hA[cmg_packed_index(n, n)];
+        for(int mode = 1; mode >= 0; --mode)
+        {
+            cudaMemset(dB, 0xFF, packed * 8);
+            double msMax = 0;
+            std::vector<cmg_orbit_shard> shards(world);
+            std::vector<double*> bufs;
+            for(int r = 0; r < world; ++r)
+            {
+                cmg_orbit_shard& sh = shards[r];
+                std::memset(&sh, 0, sizeof(sh));
+                sh.q_begin = (F * r / world) / 32 * 32;
+                sh.q_end = r + 1 == world ? F : (F * (r + 1) / world) / 32 * 32;
+                const int64_t ld = sh.q_end - sh.q_begin;
+                int64_t stripDoubles = 0;
+                for(int st = 0; st < 3; ++st)
+                    for(int f = 0; f < 12; ++f)
+                        stripDoubles += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
+                double *dStrips = nullptr, *dBox = nullptr;
+                OK(cmg_device_malloc(ctx, stripDoubles * 8, (void**) &dStrips));
+                OK(cmg_device_malloc(ctx, 72 * n * ld * 8, (void**) &dBox));
+                bufs.push_back(dStrips);
+                bufs.push_back(dBox);
+                cudaMemset(dStrips, 0xFF, stripDoubles * 8);
+                cudaMemset(dBox, 0xFF, 72 * n * ld * 8);
+                int64_t off = 0;
+                for(int st = 0; st < 3; ++st)
+                    for(int f = 0; f < 12; ++f)
+                    {
+                        sh.strip[st][f] = dStrips + off;
+                        off += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
+                    }
+                for(int t = 0; t < 6; ++t)
+                    for(int f = 0; f < 12; ++f)
+                        sh.outbox[t][f] = dBox + (t * 12 + f) * n * ld;
+                cudaDeviceSynchronize();
+                OK(cmg_tqu_orbit_sharded(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, &sh, mode));
+                double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+                msMax = std::max(msMax, ms);
+            }
+            for(int parts = 1; parts <= 2; ++parts)               // the strips of all ranks first (they have holes), then the outboxes
+                for(int r = 0; r < world; ++r)
+                    OK(cmg_tqu_orbit_assemble(ctx, &shards[r], mode, parts, dB));
+            OK(cmg_synchronize(ctx));
+            for(double* b : bufs)
+                OK(cmg_device_free(ctx, b));
+            OK(cmg_copy_to_host(ctx, hB.data(), dB, packed * 8));
+            OK(cmg_synchronize(ctx));
+            int64_t nan = 0; double worst = 0;
+            for(int64_t col = 0, e = 0; col < 3 * n; ++col)
+                for(int64_t row = 0; row <= col; ++row, ++e)
+                {
+                    if(std::isnan(hB[e])) { ++nan; continue; }
+                    worst = std::max(worst, std::fabs(hB[e] - hA[e]) / (col < n ? dT : dQ));
+                }
+            std::printf("sharded nside %d lmax %d world %d mode %d: unwritten %lld, max |assembled - cmg_tqu| / diag = %.3e; slowest rank %.3f ms\n",
+                        nside, lmax, world, mode, (long long) nan, worst, msMax);
+            if(nan || worst > 1e-11) rc = 1;
+        }
+        OK(cmg_device_free(ctx, dA));
+        OK(cmg_device_free(ctx, dB));
+    }
+
+    // flagship size, one rank of eight: time only (first and last range)
+    if(timingNside >= 64)
+    {
+        const int nside = 64, lmax = 192, world = 8;
+        OK(cmg_set_pixels(ctx, nside, nullptr, 0));
+        const int64_t n = cmg_npix(ctx), F = (int64_t) nside * nside;
+        std::vector<double> tt, te, ee, bb;
+        weights(lmax, tt, te, ee, bb);
+        for(int r = 0; r < world; r += world - 1)
+        {
+            cmg_orbit_shard sh;
+            std::memset(&sh, 0, sizeof(sh));
+            sh.q_begin = F * r / world;
+            sh.q_end = F * (r + 1) / world;
+            const int64_t ld = sh.q_end - sh.q_begin;
+            int64_t stripDoubles = 0;
+            for(int st = 0; st < 3; ++st)
+                for(int f = 0; f < 12; ++f)
+                    stripDoubles += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
+            double *dStrips = nullptr, *dBox = nullptr;
+            OK(cmg_device_malloc(ctx, stripDoubles * 8, (void**) &dStrips));
+            OK(cmg_device_malloc(ctx, 72 * n * ld * 8, (void**) &dBox));
+            int64_t off = 0;
+            for(int st = 0; st < 3; ++st)
+                for(int f = 0; f < 12; ++f)
+                {
+                    sh.strip[st][f] = dStrips + off;
+                    off += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
+                }
+            for(int t = 0; t < 6; ++t)
+                for(int f = 0; f < 12; ++f)
+                    sh.outbox[t][f] = dBox + (t * 12 + f) * n * ld;
+            for(int mode = 1; mode >= 0; --mode)
+            {
+                double best = 1e30;
+                for(int rep = 0; rep < 3; ++rep)
+                {
+                    OK(cmg_tqu_orbit_sharded(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, &sh, mode));
+                    double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+                    best = std::min(best, ms);
+                }
+                std::printf("nside 64 lmax 192, rank %d of 8 (equal q ranges), mode %d: %.2f ms, strips %.2f GB\n", r, mode, best, stripDoubles * 8e-9);
+            }
+            OK(cmg_device_free(ctx, dStrips));
+            OK(cmg_device_free(ctx, dBox));
+        }
     }
 
     // flagship size: one buffer, three 32 MB windows compared, timings
