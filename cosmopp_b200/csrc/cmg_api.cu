@@ -1002,27 +1002,25 @@ cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* att, const double* 
     const unsigned tiles = static_cast<unsigned>((facePix / cmg::PQ_TI) * ((sh.q1 - sh.q0) / cmg::PQ_TJ));
 
     KernelTimer timer(ctx);
-    for(int half = 0; half < 2; ++half)              // classes without / with a transposed image
+    const int masks[3] = {0, 8, 12};                 // classes by their transposed images: none, (3,0), (2,0) + (3,1)
+    for(int m = 0; m < 3; ++m)
     {
         cmg::OrbitPlan plan;
-        cmg::orbitBuildPlan(ctx->nside, mode, half, plan);
+        cmg::orbitBuildPlan(ctx->nside, mode, masks[m], plan);
         if(plan.n == 0)
             continue;
         const dim3 grid(tiles, static_cast<unsigned>(plan.n));
-        if(half == 0)
-        {
-            auto kernel = cmg::tquOrbitKernel<4, 2, false>;
-            const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<false>();
-            CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
+#define CMG_ORBIT_LAUNCH(MASK)                                                                                                      \
+        {                                                                                                                           \
+            auto kernel = cmg::tquOrbitKernel<4, 2, MASK>;                                                                          \
+            const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<(MASK) != 0>();                                              \
+            CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));       \
+            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);                          \
         }
-        else
-        {
-            auto kernel = cmg::tquOrbitKernel<4, 2, true>;
-            const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<true>();
-            CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
-        }
+        if(masks[m] == 0) CMG_ORBIT_LAUNCH(0)
+        else if(masks[m] == 8) CMG_ORBIT_LAUNCH(8)
+        else CMG_ORBIT_LAUNCH(12)
+#undef CMG_ORBIT_LAUNCH
         CMG_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }

@@ -47,18 +47,21 @@ struct OrbitPlan
 
 inline int orbitRotateFace(int f, int k) { return (f & ~3) | ((f + k) & 3); }
 
-// mode 0: transposed images allowed (18 units); mode 1: none (22.5 units).  swapClasses selects which half of the
-// classes to emit: 0 = those without a transposed image, 1 = those with one, -1 = all.
-inline void orbitBuildPlan(int64_t nside, int mode, int swapClasses, OrbitPlan& plan)
+// mode 0: transposed images allowed (18 units); mode 1: none (22.5 units).  swapMask selects the classes to emit by
+// their mask of transposed images (bit k = image k): 0 = none transposed, 8 = the (0,1) classes, 12 = the (0,2) classes,
+// -1 = all.  The mask is a template parameter of the kernel: with the flags read from the plan at run time ptxas no longer
+// proves the series loop warp-uniform and drops its uniform-register coefficient operands (0.84 instead of 1.0 of the FP64
+// issue rate in the loop).
+inline void orbitBuildPlan(int64_t nside, int mode, int swapMask, OrbitPlan& plan)
 {
     plan.n = 0;
     plan.facePix = static_cast<int>(nside * nside);
     auto add = [&](int rowFace, int colFace, int tri, int sameFace, int nImg, const int* rot, const int* swap)
     {
-        bool anySwap = false;
+        int mask = 0;
         for(int k = 0; k < nImg; ++k)
-            anySwap = anySwap || swap[k];
-        if(swapClasses >= 0 && (swapClasses == 1) != anySwap)
+            mask |= (swap[k] ? 1 : 0) << k;
+        if(swapMask >= 0 && swapMask != mask)
             return;
         OrbitClass& c = plan.c[plan.n++];
         c.rowFace = rowFace;
@@ -137,12 +140,14 @@ __device__ __forceinline__ bool orbitTile(const OrbitPlan& plan, const OrbitShar
 // every image.  Entries whose contiguous direction is the column pixel go through the shared-memory stage: the three
 // transposed partners <Q_a T_b>, <U_a T_b>, <U_a Q_b> for every image, and <T T>, <Q Q>, <U U> as well for a
 // transposed image (there the row image a' has the larger index, so (X a', X b') is stored in column X a').
-template <int R, int MINB, bool SWAP>
+// SWAPMASK: bit k set = image k of every class of this launch is a transposed one (orbitBuildPlan).
+template <int R, int MINB, int SWAPMASK>
 __global__ void __launch_bounds__(PQ_THREADS, MINB)
 tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entrySlot,
                const __grid_constant__ OrbitPlan plan, const __grid_constant__ OrbitShardDev sh)
 {
     extern __shared__ double4 orbSmem[];
+    constexpr bool SWAP = SWAPMASK != 0;
     constexpr int SLOTS = SWAP ? 6 : 3;
     double* sI = reinterpret_cast<double*>(orbSmem);                  // [8][PQ_TI]
     double* sJ = sI + 8 * PQ_TI;                                     // [8][PQ_TJ]
@@ -247,33 +252,31 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
                 const double vUU = aRe - bRe;
 
                 const int dq = (qCol0 + jl) - (qRow0 + il);                   // q_col - q_row
-                if(!tri || dq >= 0)
-                {
+                const bool live = !tri || dq >= 0;
+                const bool strict = !tri || dq > 0;       // the q_row == q_col pairs of a transposed image are image 0's own
 #pragma unroll
-                    for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+                for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+                {
+                    // two flat predicates per image (no nested branches: ptxas then still proves the series loop of the next
+                    // pass warp-uniform and keeps its coefficients in uniform registers)
+                    const bool sw = (SWAPMASK >> k) & 1;
+                    const bool some = k < nImg && live && (!sw || strict);          // <T Q>, <T U>, <Q U>: every image
+                    const bool all = some && !sw;                                   // <T T>, <Q Q>, <U U>: straight images only
+                    const long long ip = static_cast<long long>(oc.imgRowFace[k]) * facePix + (qRow0 + il);
+                    double* colT = sColPtr[(k * 3 + 0) * PQ_TJ + jl] + ip;
+                    double* colQ = sColPtr[(k * 3 + 1) * PQ_TJ + jl] + ip;
+                    double* colU = sColPtr[(k * 3 + 2) * PQ_TJ + jl] + ip;
+                    if(some)
                     {
-                        if(k < nImg)
-                        {
-                            const long long ip = static_cast<long long>(oc.imgRowFace[k]) * facePix + (qRow0 + il);
-                            double* colT = sColPtr[(k * 3 + 0) * PQ_TJ + jl] + ip;
-                            double* colQ = sColPtr[(k * 3 + 1) * PQ_TJ + jl] + ip;
-                            double* colU = sColPtr[(k * 3 + 2) * PQ_TJ + jl] + ip;
-                            if(!SWAP || !oc.imgSwap[k])
-                            {
-                                __stcs(colT, vTT);
-                                __stcs(colQ, vTQ);
-                                __stcs(colQ + npix, vQQ);
-                                __stcs(colU, vTU);
-                                __stcs(colU + npix, vQU);
-                                __stcs(colU + 2 * npix, vUU);
-                            }
-                            else if(!tri || dq > 0)          // the q_row == q_col pairs of a transposed image are image 0's own
-                            {
-                                __stcs(colQ, vTQ);
-                                __stcs(colU, vTU);
-                                __stcs(colU + npix, vQU);
-                            }
-                        }
+                        __stcs(colQ, vTQ);
+                        __stcs(colU, vTU);
+                        __stcs(colU + npix, vQU);
+                    }
+                    if(all)
+                    {
+                        __stcs(colT, vTT);
+                        __stcs(colQ + npix, vQQ);
+                        __stcs(colU + 2 * npix, vUU);
                     }
                 }
                 stage[(0 * PQ_TI + il) * PQ_STAGE_LD + jl] = xt * fma(ai, ai, -bi * bi);   // Q_a T_b
@@ -293,12 +296,15 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     // entries whose contiguous direction is the column pixel: for fixed row pixel a' the 32 column pixels of the tile
     // are consecutive rows of column (X a'); one warp store per (image, entry kind, a').  Column (X a') is this rank's
     // when q_a lies in its range, else the run goes to the outbox block of (kind, face of b').
+    // Addresses: row a' = a'_0 + r of column strip X sits at packedOffset(c + r) = packedOffset(c) + r c + r (r + 1) / 2 with
+    // c = X N + a'_0 warp-uniform, so a row costs one 32 x 32 -> 64 bit multiply-add on top of a base computed once per
+    // (image, kind); the outbox row is r (q1 - q0) further on.
     const int sameFace = oc.sameFace;
-    const int ldOut = sh.q1 - sh.q0;
+    const unsigned ldOut = static_cast<unsigned>(sh.q1 - sh.q0);
     const int qColLane = qCol0 + lane;
     for(int k = 0; k < nImg; ++k)
     {
-        const bool swapped = SWAP && oc.imgSwap[k];
+        const bool swapped = (SWAPMASK >> k) & 1;
         const int nKinds = swapped ? 6 : 3;
         const int rowFace = oc.imgRowFace[k], colFace = oc.imgColFace[k];
         const long long rowPix0 = static_cast<long long>(rowFace) * facePix + qRow0;
@@ -308,22 +314,22 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
         const int minGap = !tri ? -(1 << 30) : ((sameFace || swapped) ? 1 : 0);
         for(int t = 0; t < nKinds; ++t)
         {
-            // bases of this (image, kind), looked up once: own strip X of the row face, outbox block of the column face
-            const long long colStrip = orbitStripX(t) * npix + rowPix0;
-            double* const ownBase = sh.strip[orbitStripX(t)][rowFace] + (orbitStripY(t) * npix + colPix0 + lane);
-            double* const boxBase = sh.outbox[t][colFace] + (qCol0 - sh.q0 + lane);
+            const unsigned c = static_cast<unsigned>(orbitStripX(t) * npix + rowPix0);       // < 2^32 for every valid nside
+            double* const ownBase = sh.strip[orbitStripX(t)][rowFace] + packedOffset(static_cast<long long>(c)) +
+                                    (orbitStripY(t) * npix + colPix0 + lane);
+            double* const boxBase = sh.outbox[t][colFace] + rowPix0 * ldOut + (qCol0 - sh.q0 + lane);
             const double* src = stage + (t * PQ_TI) * PQ_STAGE_LD + lane;
 #pragma unroll
             for(int u = 0; u < PQ_TI / (PQ_THREADS / 32); ++u)
             {
-                const int ilr = warp + u * (PQ_THREADS / 32);
-                const int qa = qRow0 + ilr;
+                const unsigned r = static_cast<unsigned>(warp + u * (PQ_THREADS / 32));
+                const int qa = qRow0 + static_cast<int>(r);
+                const bool local = qa >= sh.q0 && qa < sh.q1;                                  // warp-uniform
+                const unsigned long long off = local ? static_cast<unsigned long long>(r) * c + (r * (r + 1)) / 2
+                                                     : static_cast<unsigned long long>(r) * ldOut;
+                double* dst = (local ? ownBase : boxBase) + off;
                 if(qColLane - qa >= minGap)
-                {
-                    double* dst = (qa >= sh.q0 && qa < sh.q1) ? ownBase + packedOffset(colStrip + ilr)
-                                                              : boxBase + (rowPix0 + ilr) * ldOut;
-                    __stcs(dst, src[ilr * PQ_STAGE_LD]);
-                }
+                    __stcs(dst, src[r * PQ_STAGE_LD]);
             }
         }
     }
