@@ -86,7 +86,7 @@ def test_whole_call_takes_the_orbit_path_on_the_full_sky(gpu_ctx, oracle_api):
     out = torch.empty(capi.packed_size(3 * gpu_ctx.npix), dtype=torch.float64, pin_memory=True)
     before = gpu_ctx.launches
     gpu_ctx.cl_to_cmatrix_pol(*spectra, 10.0, out)
-    assert gpu_ctx.launches - before == 2               # the two launches of cmg_tqu_orbit (classes without / with transposed images)
+    assert gpu_ctx.launches - before == 3               # the launches of cmg_tqu_orbit: one per transposed-image mask (0, 8, 12)
     want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
     assert (np.abs(out.numpy() - want) / _scale(gpu_ctx.npix, want)).max() <= REL_TOL
     gpu_ctx.set_kernel_variant(142)                     # a pinned variant switches the routing off

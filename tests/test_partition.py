@@ -92,3 +92,57 @@ def test_batch_partition_is_slab_aligned_and_complete(n_batch, parts):
     assert all(x % 16 == 0 for x in b[1:-1])
     sizes = [y - x for x, y in zip(b, b[1:])]
     assert max(sizes) - min(sizes) <= 16 + 15          # balanced to one slab (plus the ragged last one)
+
+
+# ---------------------------------------------------------------- symmetry-orbit sharding (cmg_tqu_orbit_sharded)
+
+@pytest.mark.parametrize("nside,world,mode", [(64, 1, 0), (64, 2, 0), (64, 4, 0), (64, 8, 0), (64, 8, 1), (16, 3, 0), (8, 2, 1)])
+def test_orbit_partition_balances_evaluated_pairs(nside, world, mode):
+    f = nside * nside
+    b = partition.orbit_partition(nside, world, mode)
+    assert b[0] == 0 and b[-1] == f and len(b) == world + 1
+    assert all(x <= y for x, y in zip(b, b[1:])) and all(x % 32 == 0 for x in b)
+    pairs = [partition.orbit_pairs_in_range(b[r], b[r + 1], f, mode) for r in range(world)]
+    assert sum(pairs) == partition.orbit_pairs_in_range(0, f, f, mode)
+    assert sum(pairs) == sum(partition.orbit_column_cost(q, f, mode) for q in range(f))
+    if nside == 64:
+        assert max(pairs) <= 1.05 * sum(pairs) / world                       # to one 32-column tile
+    # the 36 packed column runs of all ranks tile the packed triangle
+    sizes = sum(sum(sum(row) for row in partition.orbit_strip_sizes(nside, b[r], b[r + 1])) for r in range(world))
+    assert sizes == partition.packed_size(3 * 12 * f)
+
+
+def _orbit_worker(rank, world, port, nside, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    f = nside * nside
+    b = partition.orbit_partition(nside, world, 0)
+    mine = torch.tensor([b[rank], b[rank + 1], partition.orbit_pairs_in_range(b[rank], b[rank + 1], f, 0),
+                         sum(sum(r) for r in partition.orbit_strip_sizes(nside, b[rank], b[rank + 1]))], dtype=torch.int64)
+    allr = [torch.zeros(4, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    if rank == 0:
+        out.put(torch.stack(allr).tolist())
+    dist.destroy_process_group()
+
+
+def test_two_rank_orbit_planning_over_gloo():
+    import torch.multiprocessing as mp
+    nside, world = 16, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_orbit_worker, args=(r, world, port, nside, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    rows = np.array(q.get(timeout=120))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    f = nside * nside
+    assert rows[0, 0] == 0 and rows[0, 1] == rows[1, 0] and rows[1, 1] == f      # the ranks' in-face ranges tile [0, nside^2)
+    assert rows[:, 2].sum() == partition.orbit_pairs_in_range(0, f, f, 0)        # every source pair evaluated once
+    assert rows[:, 3].sum() == partition.packed_size(3 * 12 * f)                 # strips tile the packed triangle

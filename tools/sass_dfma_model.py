@@ -73,19 +73,27 @@ def model(instrs, lo, hi):
     return n, cyc, other, hist
 
 
-def main():
-    path, func = sys.argv[1], sys.argv[2]
-    mind = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-    ins = parse(path, func)
+def loops(ins):
+    """backward-branch loops of a parsed function: dicts with lo, hi, dfma (FP64 operations), cycles, other, hist"""
+    found = []
     for a, t in ins:
         m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)", t)
         if m and int(m.group(1), 16) < a:
             lo = int(m.group(1), 16)
             n, cyc, other, hist = model(ins, lo, a)
-            if n >= mind:
-                print("loop 0x%04x-0x%04x: %3d fp64 ops, %3d other; modelled %.1f cyc (ideal %.0f) -> %.1f%% of FP64 peak; "
-                      "issue slots %d; fresh-read histogram %s" % (lo, a, n, other, cyc, 2.0 * n, 200.0 * n / max(cyc, n + other),
-                                                                   n + other, hist))
+            found.append({"lo": lo, "hi": a, "dfma": n, "cycles": cyc, "other": other, "hist": hist})
+    return found
+
+
+def main():
+    path, func = sys.argv[1], sys.argv[2]
+    mind = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    for lp in loops(parse(path, func)):
+        n, cyc, other, hist = lp["dfma"], lp["cycles"], lp["other"], lp["hist"]
+        if n >= mind:
+            print("loop 0x%04x-0x%04x: %3d fp64 ops, %3d other; modelled %.1f cyc (ideal %.0f) -> %.1f%% of FP64 peak; "
+                  "issue slots %d; fresh-read histogram %s" % (lp["lo"], lp["hi"], n, other, cyc, 2.0 * n, 200.0 * n / max(cyc, n + other),
+                                                               n + other, hist))
 
 
 if __name__ == "__main__":
