@@ -370,6 +370,21 @@ def run_gpu_arm(args):
             host = torch.empty(capi.packed_size(npix), dtype=torch.float64, pin_memory=True)
             cl_pinned = torch.from_numpy(synthetic_cl(lmax)).pin_memory()
             step = lambda: ctx.cl_to_cmatrix(cl_pinned.numpy(), FWHM, host)
+        elif use_orbit:
+            # orbit shards (strips + dense outbox blocks, tens of GB per rank) stream to the host through a small pinned ring, the
+            # way a consumer such as the CMatrix file writer (cmg_cmatrix_file_write_device) takes them: every byte the rank
+            # holds crosses PCIe inside the timed region, but host memory stays bounded for any number of ranks on the box
+            ring = [torch.empty(1 << 27, dtype=torch.float64, pin_memory=True) for _ in range(2)]      # 2 x 1 GiB
+
+            def step():
+                launch()
+                k = 0
+                for p in pieces:
+                    for off in range(0, p.numel(), ring[0].numel()):
+                        n = min(ring[0].numel(), p.numel() - off)
+                        ring[k & 1][:n].copy_(p[off:off + n], non_blocking=True)
+                        k += 1
+                torch.cuda.synchronize()
         else:
             hosts = [torch.empty(p.numel(), dtype=torch.float64, pin_memory=True) for p in pieces]
 
@@ -390,7 +405,8 @@ def run_gpu_arm(args):
             dist.all_reduce(wall, op=dist.ReduceOp.MAX)
         e2e = {"value": units_total * e2e_steps / float(wall.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * float(wall.item()) / e2e_steps, "steps": e2e_steps,
-               "note": "per rank: C_l from pinned host memory, this rank's shard of the packed matrix back to pinned host memory"}
+               "note": "per rank: C_l from pinned host memory, this rank's shard of the packed matrix back to pinned host memory"
+                       + (" (strips + outbox blocks, through a 2 x 1 GiB pinned ring)" if (use_orbit and world > 1) else "")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
