@@ -100,6 +100,7 @@ _SIGNATURES = {
     "cmg_tqu_orbit": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int]),
     "cmg_tqu_orbit_sharded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(OrbitShard), ctypes.c_int]),
     "cmg_tqu_orbit_assemble": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), ctypes.c_int, ctypes.c_int, _vp]),
+    "cmg_legendre_series_orbit": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "cmg_tqu_orbit_plan": (ctypes.c_int, [_i64, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cmg_tqu_weights": (ctypes.c_int, [_vp] * 6 + [ctypes.c_int] + [_vp] * 4),
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
@@ -294,6 +295,11 @@ class Context:
         a = _f64(a)
         col_end = self.npix if col_end is None else col_end
         self._check(self._L.cmg_legendre_series(self._h, _p(a), len(a) - 1, col_begin, col_end, _p(d_out)))
+
+    def legendre_series_orbit(self, a, d_out):
+        """UNVERIFIED on a GPU (include/cmg.h): full-sky TT matrix over symmetry orbits, whole packed triangle"""
+        a = _f64(a)
+        self._check(self._L.cmg_legendre_series_orbit(self._h, _p(a), len(a) - 1, _p(d_out)))
 
     def legendre_series_dev(self, d_a, lmax, d_out, col_begin=0, col_end=None):
         col_end = self.npix if col_end is None else col_end

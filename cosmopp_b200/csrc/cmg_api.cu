@@ -1044,6 +1044,36 @@ cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* att, const double* ate, con
     return cmg_tqu_orbit_sharded(ctx, att, ate, aee, abb, lmax, &shard, mode);
 }
 
+cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, double* dOut)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!a || !dOut) return fail(ctx, CMG_EINVAL, "null argument");
+    if(!ctx->fullSky)
+        return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs the full sky in NESTED order (cmg_set_pixels with good_nest = NULL)");
+    if(ctx->nside < 16)
+        return fail(ctx, CMG_EUNSUPPORTED, "the TT symmetry-orbit path needs nside >= 16 (whole 128 x 16 tiles inside a base face)");
+    if(lmax + 1 > cmg::TT_STATIC_STEPS)
+        return fail(ctx, CMG_EUNSUPPORTED, "lmax exceeds the static coefficient table");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    static thread_local cmg::TtStaticTable T;
+    for(int i = 0; i < cmg::TT_STATIC_STEPS; ++i)
+    {
+        const int k = cmg::TT_STATIC_STEPS - 1 - i;
+        T.s[i] = make_double2(k <= lmax ? a[k] * ctx->hostT0.N[k] : 0.0, -ctx->hostT0.g[k + 1]);
+    }
+    const int entrySlot = cmg::TT_STATIC_STEPS - 1 - lmax;
+    cmg::OrbitPlan plan;
+    cmg::orbitBuildPlan(ctx->nside, 1, -1, plan);        // no transposed images: every store is a direct one
+    const int64_t facePix = ctx->nside * ctx->nside;
+    const dim3 grid(static_cast<unsigned>((facePix / cmg::TT_ROWS) * (facePix / cmg::TT_COLS)), static_cast<unsigned>(plan.n));
+    KernelTimer timer(ctx);
+    cmg::legendreSeriesOrbitKernel<8, 4><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, dOut);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return timer.finish();
+}
+
 cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, int parts, double* dFull)
 {
     if(!ctx) return CMG_EINVAL;

@@ -335,6 +335,69 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TT over symmetry orbits (NOT YET RUN ON A GPU: written after the round's GPU time was spent; opt-in through
+// cmg_legendre_series_orbit, nothing routes to it).  legendreSeriesKernel's tile (128 rows x 16 columns, a thread owns a row
+// and walks the columns R at a time) addressed by (class, tile) of the plan WITHOUT transposed images (mode 1: every image has
+// row pixel < column pixel, so every store is a direct one, lanes along the row): 22.5 of 72 face-pair units, 3.2x less work.
+// out = entry (0, 0) of the whole packed triangle of dimension N.
+// ------------------------------------------------------------------------------------------------
+template <int R, int MINB>
+__global__ void __launch_bounds__(TT_ROWS, MINB)
+legendreSeriesOrbitKernel(const __grid_constant__ TtStaticTable T, Geometry geo, int entrySlot,
+                          const __grid_constant__ OrbitPlan plan, double* __restrict__ out)
+{
+    const OrbitClass& oc = plan.c[blockIdx.y];
+    const int facePix = plan.facePix;
+    const int tilesPerFaceRows = facePix / TT_ROWS;
+    const int qRow0 = static_cast<int>(blockIdx.x % tilesPerFaceRows) * TT_ROWS;
+    const int qCol0 = static_cast<int>(blockIdx.x / tilesPerFaceRows) * TT_COLS;
+    const int tri = oc.tri;
+    if(tri && qRow0 > qCol0 + TT_COLS - 1)
+        return;                              // q_row > q_col everywhere
+    if(tri && qRow0 + static_cast<int>(threadIdx.x & ~31u) > qCol0 + TT_COLS - 1)
+        return;                              // this warp's 32 rows are all beyond the last column
+
+    const int qRow = qRow0 + static_cast<int>(threadIdx.x);
+    const long long i = static_cast<long long>(oc.rowFace) * facePix + qRow;
+    const double xi = geo.nx[i], yi = geo.ny[i], zi = geo.nz[i];
+    const int nImg = oc.nImg;
+
+    for(int c = 0; c < TT_COLS; c += R)
+    {
+        double x2[R], b1[R], b2[R];
+#pragma unroll
+        for(int r = 0; r < R; ++r)
+        {
+            const long long j = static_cast<long long>(oc.colFace) * facePix + qCol0 + c + r;
+            double dot = __dadd_rn(__dadd_rn(__dmul_rn(xi, __ldg(geo.nx + j)), __dmul_rn(yi, __ldg(geo.ny + j))),
+                                   __dmul_rn(zi, __ldg(geo.nz + j)));
+            dot = fmin(1.0, fmax(-1.0, dot));
+            x2[r] = dot + dot;
+            b1[r] = 0.0;
+            b2[r] = 0.0;
+        }
+        ttClenshawStatic<R>(x2, b1, b2, T, entrySlot);
+#pragma unroll
+        for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+        {
+            if(k < nImg)
+            {
+                const long long ip = static_cast<long long>(oc.imgRowFace[k]) * facePix + qRow;
+                const long long jp0 = static_cast<long long>(oc.imgColFace[k]) * facePix + qCol0 + c;
+                double* colPtr = out + packedOffset(jp0) + ip;
+#pragma unroll
+                for(int r = 0; r < R; ++r)
+                {
+                    if(!tri || qRow <= qCol0 + c + r)
+                        __stcs(colPtr, b1[r]);
+                    colPtr += jp0 + r + 1;                     // next column starts (column index + 1) entries further
+                }
+            }
+        }
+    }
+}
+
 // Outbox blocks of a rank -> their places in a whole packed triangle (assembly of the unsharded matrix): the same tiles,
 // images and predicates as the last phase of tquOrbitKernel, reading the block instead of the stage.
 __global__ void __launch_bounds__(PQ_THREADS)

@@ -112,3 +112,24 @@ def test_orbit_path_refuses_what_it_cannot_do(gpu_ctx, oracle_api):
     out = torch.empty(capi.packed_size(3 * gpu_ctx.npix), dtype=torch.float64, device="cuda")
     with pytest.raises(capi.CmgError):
         gpu_ctx.tqu_orbit(*w, out)                      # nside < 8: a 64 x 32 tile does not fit a base face
+
+
+@pytest.mark.skipif("not __import__('os').environ.get('CMG_TEST_UNVERIFIED')",
+                    reason="cmg_legendre_series_orbit has not been run on a GPU yet (written after the round's GPU time was spent): "
+                           "set CMG_TEST_UNVERIFIED=1 to try it")
+@pytest.mark.parametrize("nside,lmax", [(16, 47), (32, 96)])
+def test_tt_orbit_matches_the_every_pair_kernel(gpu_ctx, oracle_api, nside, lmax):
+    import torch
+    from cosmopp_b200 import capi
+    gpu_ctx.set_kernel_variant(0)
+    gpu_ctx.set_pixels(nside)
+    n = gpu_ctx.npix
+    a = capi.tt_weights(synthetic_cl(lmax), capi.window_beam(lmax, 10.0))
+    ref = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
+    gpu_ctx.legendre_series(a, ref)
+    out = torch.full_like(ref, float("nan"))
+    gpu_ctx.legendre_series_orbit(a, out)
+    torch.cuda.synchronize()
+    got, want = out.cpu().numpy(), ref.cpu().numpy()
+    assert not np.isnan(got).any()
+    assert np.abs(got - want).max() <= 1e-13 * want[0]

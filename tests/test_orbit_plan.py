@@ -177,3 +177,34 @@ def test_sharded_store_rules_partition_the_triangle(oracle_matrix, mode, world):
     units = 18.0 if mode == 0 else 22.5
     f = nside * nside
     assert abs(pairs - units * f * f) <= 6 * f          # the q_row <= q_col classes include their diagonal
+
+
+def test_tt_orbit_store_rules_fill_the_triangle_exactly_once():
+    """legendreSeriesOrbitKernel (cmg_legendre_series_orbit, not yet run on a GPU): 128 x 16 tiles of the plan without
+    transposed images, one direct store per image."""
+    nside, lmax = 16, 20
+    F, n = nside * nside, 12 * nside * nside
+    M = api.unpack_symmetric(api.cl_to_cmatrix(synthetic_cl(lmax), nside, 10.0), n)
+    size = capi.packed_size(n)
+    out = np.full(size, np.nan)
+    count = np.zeros(size, dtype=np.int32)
+    rows, cols = 128, 16                  # TT_ROWS, TT_COLS
+    il = np.arange(rows)[:, None]
+    jl = np.arange(cols)[None, :]
+    for c in capi.orbit_plan(nside, 1):
+        assert not any(swap for _, _, swap in c["images"])
+        for tr in range(F // rows):
+            for tc in range(F // cols):
+                q_row0, q_col0 = tr * rows, tc * cols
+                if c["tri"] and q_row0 > q_col0 + cols - 1:
+                    continue
+                live = np.broadcast_to((not c["tri"]) | (q_row0 + il <= q_col0 + jl), (rows, cols))
+                val = M[c["row_face"] * F + q_row0 + il + 0 * jl, c["col_face"] * F + q_col0 + jl + 0 * il]
+                for fr, fc, _ in c["images"]:
+                    jp = fc * F + q_col0 + jl + 0 * il
+                    pos = jp * (jp + 1) // 2 + fr * F + q_row0 + il
+                    np.add.at(count, pos[live], 1)
+                    out[pos[live]] = val[live]
+    assert count.min() == 1 and count.max() == 1
+    want, _ = packed_from_full(M)
+    assert np.abs(out - want).max() < 1e-11 * M[0, 0]

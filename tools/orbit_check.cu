@@ -42,7 +42,7 @@ static void weights(int lmax, std::vector<double>& tt, std::vector<double>& te, 
 
 int main(int argc, char** argv)
 {
-    // modes: full (default) = all parity checks + timings; ranks = per-rank timings of the balanced 2/4/8-way partitions at
+    // modes: tt = parity + timing of the TT orbit kernel; full (default) = all parity checks + timings; ranks = per-rank timings of the balanced 2/4/8-way partitions at
     // Nside=64; prof = one cmg_tqu_orbit call at Nside=64 (what ncu profiles)
     const std::string what = argc > 1 ? argv[1] : "full";
     const int timingNside = 64;
@@ -50,6 +50,53 @@ int main(int argc, char** argv)
     if(cmg_create(&ctx, 0) != CMG_OK) { std::printf("no context: %s\n", cmg_last_error(nullptr)); return 1; }
     OK(cmg_set_timing(ctx, 1));
     int rc = 0;
+
+    if(what == "tt")      // cmg_legendre_series_orbit (written without GPU time left: run this first in the next round)
+    {
+        const int cases[][2] = {{16, 47}, {32, 96}, {64, 192}};
+        for(const auto& cs : cases)
+        {
+            const int nside = cs[0], lmax = cs[1];
+            OK(cmg_set_pixels(ctx, nside, nullptr, 0));
+            const int64_t n = cmg_npix(ctx), packed = cmg_packed_size(n);
+            std::vector<double> tt, te, ee, bb;
+            weights(lmax, tt, te, ee, bb);
+            double *dA = nullptr, *dB = nullptr;
+            OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
+            OK(cmg_device_malloc(ctx, packed * 8, (void**) &dB));
+            double msBase = 1e30, ms = 1e30, t = 0;
+            for(int rep = 0; rep < 3; ++rep)
+            {
+                OK(cmg_legendre_series(ctx, tt.data(), lmax, 0, n, dA));
+                OK(cmg_last_kernel_ms(ctx, &t)); msBase = std::min(msBase, t);
+            }
+            cudaMemset(dB, 0xFF, packed * 8);
+            cudaDeviceSynchronize();
+            for(int rep = 0; rep < 3; ++rep)
+            {
+                OK(cmg_legendre_series_orbit(ctx, tt.data(), lmax, dB));
+                OK(cmg_last_kernel_ms(ctx, &t)); ms = std::min(ms, t);
+            }
+            std::vector<double> hA(packed), hB(packed);
+            OK(cmg_copy_to_host(ctx, hA.data(), dA, packed * 8));
+            OK(cmg_copy_to_host(ctx, hB.data(), dB, packed * 8));
+            OK(cmg_synchronize(ctx));
+            int64_t nan = 0; double worst = 0;
+            for(int64_t e = 0; e < packed; ++e)
+            {
+                if(std::isnan(hB[e])) { ++nan; continue; }
+                worst = std::max(worst, std::fabs(hB[e] - hA[e]) / hA[0]);
+            }
+            std::printf("TT nside %d lmax %d: unwritten %lld, max |orbit - every pair| / diag = %.3e; %.3f ms (every pair %.3f ms)\n",
+                        nside, lmax, (long long) nan, worst, ms, msBase);
+            if(nan || worst > 1e-11) rc = 1;
+            OK(cmg_device_free(ctx, dA));
+            OK(cmg_device_free(ctx, dB));
+        }
+        cmg_destroy(ctx);
+        std::printf(rc ? "TT ORBIT CHECK FAILED\n" : "TT ORBIT CHECK OK\n");
+        return rc;
+    }
 
     if(what == "prof" || what == "ranks")
     {
