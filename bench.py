@@ -199,8 +199,8 @@ def config_dict(name, kind, nside, lmax, npix, n_gpus, shard_mode="outbox", orbi
     return {
         "workload": name, "kind": kind, "nside": nside, "lmax": lmax, "npix": npix, "matrix_dim": dim,
         "packed_bytes": 8 * dim * (dim + 1) // 2, "fwhm_deg": FWHM, "pixel_window": "1 (HEALPix window file unavailable offline)",
-        "path": "symmetry orbits (cmg_tqu_orbit): one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid, "
-                "all images stored" if orbit else "every pixel pair evaluated",
+        "path": "symmetry orbits (cmg_tqu_orbit / cmg_legendre_series_orbit): one evaluation per orbit of pixel pairs under the pi/2 "
+                "rotation of the grid, all images stored" if orbit else "every pixel pair evaluated",
         "sharding": sharding, "shard_mode": shard_mode if n_gpus > 1 else "single",
         "l2": "each step writes its whole output (>> 126 MB L2) with streaming stores; nothing is re-read between steps",
     }
@@ -233,8 +233,15 @@ def run_gpu_arm(args):
     # full-sky T,Q,U: the symmetry-orbit path (needs whole 64 x 32 tiles inside a base face and at least one column tile per rank)
     use_orbit = (kind == "tqu" and good is None and nside >= 8 and 2 <= lmax <= 441 and not args.no_orbit
                  and nside * nside // 32 >= world and args.shard_mode == "outbox")
+    # full-sky TT on one GPU: the same orbits without transposed images (cmg_legendre_series_orbit; no sharded form yet)
+    if kind == "tt" and good is None and nside >= 16 and lmax <= 1023 and not args.no_orbit and world == 1:
+        use_orbit = True
+    orbit_mode = 0 if kind == "tqu" else 1
+    orbit_pairs_all = partition.orbit_pairs_in_range(0, nside * nside, nside * nside, orbit_mode) if use_orbit else None
     if kind == "tqu" and not use_orbit and 2 <= lmax <= 441:
         ctx.set_kernel_variant(142)          # pins the every-pair kernel for the whole-call e2e leg as well (0 = automatic routing)
+    if kind == "tt" and not use_orbit and args.no_orbit:
+        ctx.set_kernel_variant(142)          # any pinned variant switches the whole-call routing off; TT keeps its default static kernel
     f = capi.window_beam(lmax, FWHM)
     bounds = partition.column_partition(npix, world, align=32)
     a0, a1 = bounds[rank], bounds[rank + 1]
@@ -246,6 +253,9 @@ def run_gpu_arm(args):
         weights = capi.tt_weights(synthetic_cl(lmax), f)
         shard = torch.empty(partition.tt_shard_size(a0, a1), dtype=torch.float64, device="cuda")
         launch = lambda: ctx.legendre_series(weights, shard, a0, a1)
+        if use_orbit:
+            launch = lambda: ctx.legendre_series_orbit(weights, shard)
+            my_pairs = orbit_pairs_all                   # pixel pairs EVALUATED (1 / 3.2 of those stored)
         pieces = [shard]
     else:
         from cosmopp_b200 import multigpu
@@ -322,14 +332,14 @@ def run_gpu_arm(args):
     written = d2h_bytes
     if use_orbit and world > 1:
         # the outbox blocks are allocated dense; what the kernel writes is this rank's share of the 9 entries per stored pair
-        written = int(8 * 9 * total_pairs * (my_pairs / max(partition.orbit_pairs_in_range(0, nside * nside, nside * nside, 0), 1)))
+        written = int(8 * 9 * total_pairs * (my_pairs / max(orbit_pairs_all, 1)))
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
         "peak_source": "cmg_measure_fp64_peak: dependent-free DFMA chains on this GPU in this run (MEASURED_PEAKS.json holds no FP64 figure)",
         "algorithmic_flop_per_unit": FLOP_PER_UNIT[kind],
         "evaluated_pixel_pairs": my_pairs, "stored_pixel_pairs_all_ranks": total_pairs,
         "note": ("orbit path: FLOP counted for the pixel pairs actually evaluated (one per orbit); the matrix holds %.2fx as many"
-                 % (total_pairs / max(partition.orbit_pairs_in_range(0, nside * nside, nside * nside, 0), 1))) if use_orbit else None,
+                 % (total_pairs / max(orbit_pairs_all, 1))) if use_orbit else None,
         "hbm_write_gbs": written / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs_measured": hbm_peak,
         "hbm_frac": (written / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
     }

@@ -297,7 +297,7 @@ class Context:
         self._check(self._L.cmg_legendre_series(self._h, _p(a), len(a) - 1, col_begin, col_end, _p(d_out)))
 
     def legendre_series_orbit(self, a, d_out):
-        """UNVERIFIED on a GPU (include/cmg.h): full-sky TT matrix over symmetry orbits, whole packed triangle"""
+        """full-sky TT matrix over symmetry orbits (include/cmg.h), whole packed triangle"""
         a = _f64(a)
         self._check(self._L.cmg_legendre_series_orbit(self._h, _p(a), len(a) - 1, _p(d_out)))
 

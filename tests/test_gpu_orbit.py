@@ -114,9 +114,6 @@ def test_orbit_path_refuses_what_it_cannot_do(gpu_ctx, oracle_api):
         gpu_ctx.tqu_orbit(*w, out)                      # nside < 8: a 64 x 32 tile does not fit a base face
 
 
-@pytest.mark.skipif("not __import__('os').environ.get('CMG_TEST_UNVERIFIED')",
-                    reason="cmg_legendre_series_orbit has not been run on a GPU yet (written after the round's GPU time was spent): "
-                           "set CMG_TEST_UNVERIFIED=1 to try it")
 @pytest.mark.parametrize("nside,lmax", [(16, 47), (32, 96)])
 def test_tt_orbit_matches_the_every_pair_kernel(gpu_ctx, oracle_api, nside, lmax):
     import torch
@@ -133,3 +130,25 @@ def test_tt_orbit_matches_the_every_pair_kernel(gpu_ctx, oracle_api, nside, lmax
     got, want = out.cpu().numpy(), ref.cpu().numpy()
     assert not np.isnan(got).any()
     assert np.abs(got - want).max() <= 1e-13 * want[0]
+
+
+def test_tt_whole_call_takes_the_orbit_path_on_the_full_sky(gpu_ctx, oracle_api):
+    """cl_to_cmatrix and fiducial_matrix (series weights a_0 = a_1 != 0 as well) against the oracle"""
+    import torch
+    from cosmopp_b200 import capi
+    nside, lmax = 16, 30
+    gpu_ctx.set_kernel_variant(0)
+    gpu_ctx.set_pixels(nside)
+    cl = synthetic_cl(4 * nside)
+    out = torch.empty(capi.packed_size(gpu_ctx.npix), dtype=torch.float64, pin_memory=True)
+    gpu_ctx.cl_to_cmatrix(cl[:lmax + 1], 10.0, out)
+    want = oracle_api.cl_to_cmatrix(cl[:lmax + 1], nside, 10.0)
+    assert np.abs(out.numpy() - want).max() <= REL_TOL * want[0]
+    gpu_ctx.fiducial_matrix(cl, lmax, 10.0, out)
+    want = oracle_api.fiducial_matrix(cl, nside, lmax, 10.0)
+    assert np.abs(out.numpy() - want).max() <= REL_TOL * want[0]
+    gpu_ctx.set_kernel_variant(142)                     # any pinned variant: every-pair kernel, same numbers to rounding
+    again = torch.empty_like(out)
+    gpu_ctx.fiducial_matrix(cl, lmax, 10.0, again)
+    gpu_ctx.set_kernel_variant(0)
+    assert np.abs(again.numpy() - out.numpy()).max() <= 1e-13 * want[0]

@@ -77,15 +77,19 @@ int main(int argc, char** argv)
                 OK(cmg_legendre_series_orbit(ctx, tt.data(), lmax, dB));
                 OK(cmg_last_kernel_ms(ctx, &t)); ms = std::min(ms, t);
             }
-            std::vector<double> hA(packed), hB(packed);
-            OK(cmg_copy_to_host(ctx, hA.data(), dA, packed * 8));
-            OK(cmg_copy_to_host(ctx, hB.data(), dB, packed * 8));
+            // whole matrix up to Nside=32; at Nside=64 the last 64 MB of the triangle (columns of the last face: every class writes there)
+            const int64_t cmp = nside <= 32 ? packed : (int64_t) 8 << 20, first = packed - cmp;
+            std::vector<double> hA(cmp), hB(cmp);
+            double diag = 0;
+            OK(cmg_copy_to_host(ctx, &diag, dA, 8));
+            OK(cmg_copy_to_host(ctx, hA.data(), dA + first, cmp * 8));
+            OK(cmg_copy_to_host(ctx, hB.data(), dB + first, cmp * 8));
             OK(cmg_synchronize(ctx));
             int64_t nan = 0; double worst = 0;
-            for(int64_t e = 0; e < packed; ++e)
+            for(int64_t e = 0; e < cmp; ++e)
             {
                 if(std::isnan(hB[e])) { ++nan; continue; }
-                worst = std::max(worst, std::fabs(hB[e] - hA[e]) / hA[0]);
+                worst = std::max(worst, std::fabs(hB[e] - hA[e]) / diag);
             }
             std::printf("TT nside %d lmax %d: unwritten %lld, max |orbit - every pair| / diag = %.3e; %.3f ms (every pair %.3f ms)\n",
                         nside, lmax, (long long) nan, worst, ms, msBase);
