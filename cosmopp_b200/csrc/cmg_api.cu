@@ -1002,7 +1002,10 @@ cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* att, const double* 
     fillStaticTable(ctx, att, ate, aee, abb, lmax, T);
     const int entrySlot = cmg::PQ_STATIC_STEPS + 1 - lmax;
     const int64_t facePix = ctx->nside * ctx->nside;
-    const unsigned tiles = static_cast<unsigned>((facePix / cmg::PQ_TI) * ((sh.q1 - sh.q0) / cmg::PQ_TJ));
+    const int64_t tiles64 = (facePix / cmg::PQ_TI) * ((sh.q1 - sh.q0) / cmg::PQ_TJ);
+    if(tiles64 > 0x7fffffffLL)
+        return fail(ctx, CMG_EUNSUPPORTED, "too many tiles for one launch");
+    const unsigned tiles = static_cast<unsigned>(tiles64);
 
     KernelTimer timer(ctx);
     const int masks[3] = {0, 8, 12};                 // classes by their transposed images: none, (3,0), (2,0) + (3,1)
@@ -1069,6 +1072,8 @@ cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, do
     cmg::OrbitPlan plan;
     cmg::orbitBuildPlan(ctx->nside, 1, -1, plan);        // no transposed images: every store is a direct one
     const int64_t facePix = ctx->nside * ctx->nside;
+    if((facePix / cmg::TT_ROWS) * (facePix / cmg::TT_COLS) > 0x7fffffffLL)
+        return fail(ctx, CMG_EUNSUPPORTED, "too many tiles for one launch");
     const dim3 grid(static_cast<unsigned>((facePix / cmg::TT_ROWS) * (facePix / cmg::TT_COLS)), static_cast<unsigned>(plan.n));
     KernelTimer timer(ctx);
     cmg::legendreSeriesOrbitKernel<8, 4><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, dOut);

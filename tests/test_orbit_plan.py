@@ -208,3 +208,13 @@ def test_tt_orbit_store_rules_fill_the_triangle_exactly_once():
     assert count.min() == 1 and count.max() == 1
     want, _ = packed_from_full(M)
     assert np.abs(out - want).max() < 1e-11 * M[0, 0]
+
+
+def test_orbit_plan_rejects_bad_arguments():
+    with pytest.raises(capi.CmgError):
+        capi.orbit_plan(12)                 # nside must be a power of two
+    with pytest.raises(capi.CmgError):
+        capi.orbit_plan(16, mode=2)
+    for mode in (0, 1):
+        plan = capi.orbit_plan(8, mode)
+        assert len(plan) <= 24 and all(1 <= len(c["images"]) <= 4 for c in plan)

@@ -63,5 +63,23 @@ with tempfile.TemporaryDirectory() as td:
     ctx.read_cmatrix_file(path, torch.empty_like(out))
 d_out = torch.empty(capi.packed_size(20), dtype=torch.float64, device="cuda")
 ctx.mask_matrix(out, n, np.arange(0, 160, 8), d_out)
+# symmetry-orbit kernels (full sky): single owner, both modes; three ranks with outbox blocks and assembly; TT
+from cosmopp_b200 import multigpu
+ctx.set_pixels(16); n16 = ctx.npix
+f16 = capi.window_beam(20, 10.0)
+w16 = capi.tqu_weights(*synthetic_cl(20, pol=True), f16, f16)
+full16 = torch.empty(capi.packed_size(3 * n16), dtype=torch.float64, device="cuda")
+for mode in (0, 1):
+    ctx.tqu_orbit(*w16, full16, mode)
+    ranks = [multigpu.OrbitShardedTQU(ctx, 16, r, 3, mode) for r in range(3)]
+    for rk in ranks:
+        rk.generate(w16)
+    for parts in (1, 2):
+        for rk in ranks:
+            rk.assemble_into(full16, parts)
+    torch.cuda.synchronize()
+    for rk in ranks:
+        rk.close()
+ctx.legendre_series_orbit(capi.tt_weights(synthetic_cl(20), f16), torch.empty(capi.packed_size(n16), dtype=torch.float64, device="cuda"))
 torch.cuda.synchronize()
 print("sanitize_run: all kernels launched, no error reported by the runtime")
