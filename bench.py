@@ -346,7 +346,17 @@ def run_gpu_arm(args):
 
     # ---- optional: whole matrix resident on every GPU (NCCL broadcasts of the strips over NVLink)
     gather = None
-    if args.gather and kind == "tqu" and world > 1 and not use_orbit:
+    gather_ok = args.gather and kind == "tqu" and world > 1
+    if gather_ok:
+        need = 8 * capi.packed_size(3 * npix)
+        if use_orbit:
+            need += 8 * max(sharded.sizes_of(r)[1] for r in range(world))       # scratch for a peer's outbox buffer
+        ok = torch.tensor([1 if torch.cuda.mem_get_info()[0] > need + (2 << 30) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()):
+            gather_ok = False
+            gather = {"skipped": "the whole matrix plus the gather scratch do not fit next to this rank's shard (%.0f GB needed)" % (need / 1e9)}
+    if gather_ok:
         full = torch.empty(capi.packed_size(3 * npix), dtype=torch.float64, device="cuda")
         sharded.gather_full(full)
         barrier()
@@ -358,8 +368,15 @@ def run_gpu_arm(args):
         barrier()
         gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(gt.item()), "bytes_per_gpu_in": 8 * (capi.packed_size(3 * npix) - sum(sharded.plan["strips"])),
-                  "how": "ncclBroadcast of every strip straight into place; outbox blocks via a scratch buffer + cmg_tqu_scatter_block"}
+        if use_orbit:
+            own = sharded.sizes_of(rank)
+            gather = {"ms": float(gt.item()),
+                      "bytes_per_gpu_in": 8 * (capi.packed_size(3 * npix) - own[0] + sum(sharded.sizes_of(r)[1] for r in range(world) if r != rank)),
+                      "how": "ncclBroadcast of every strip straight into place; each rank's (dense) outbox buffer via a scratch buffer + "
+                             "orbitOutboxScatterKernel (cmg_tqu_orbit_assemble)"}
+        else:
+            gather = {"ms": float(gt.item()), "bytes_per_gpu_in": 8 * (capi.packed_size(3 * npix) - sum(sharded.plan["strips"])),
+                      "how": "ncclBroadcast of every strip straight into place; outbox blocks via a scratch buffer + cmg_tqu_scatter_block"}
         del full
         torch.cuda.empty_cache()
 

@@ -127,28 +127,37 @@ class OrbitShardedTQU:
         self.npix = 12 * self.face_pix
         self.bounds = partition.orbit_partition(nside, world, mode)
         self.q0, self.q1 = self.bounds[rank], self.bounds[rank + 1]
-        sizes = partition.orbit_strip_sizes(nside, self.q0, self.q1)
+        self.outbox_kinds = partition.orbit_outbox_kinds(capi.orbit_plan(nside, mode)) if world > 1 else []
+        n_strips, n_outbox = self.sizes_of(rank)
         # one allocation for the 36 strips: the pieces stay individually contiguous pieces of the packed triangle
-        self.strip_sizes = sizes
-        self.strips = DeviceBuffer(ctx, sum(sum(r) for r in sizes))
-        self.shard = capi.OrbitShard()
-        self.shard.q_begin, self.shard.q_end = self.q0, self.q1
+        self.strips = DeviceBuffer(ctx, n_strips)
+        self.outbox = DeviceBuffer(ctx, n_outbox) if n_outbox else None
+        self.shard = self.shard_of(rank, self.strips.ptr, self.outbox.ptr if self.outbox is not None else 0)
+        self.pairs = partition.orbit_pairs_in_range(self.q0, self.q1, self.face_pix, mode)
+
+    def sizes_of(self, rank):
+        """doubles in the strips buffer and in the outbox buffer of rank `rank`"""
+        q0, q1 = self.bounds[rank], self.bounds[rank + 1]
+        n_strips = sum(sum(r) for r in partition.orbit_strip_sizes(self.nside, q0, q1))
+        n_outbox = self.npix * (q1 - q0) * len(self.outbox_kinds) if (self.world > 1 and q1 > q0) else 0
+        return n_strips, n_outbox
+
+    def shard_of(self, rank, strips_ptr, outbox_ptr):
+        """cmg_orbit_shard of rank `rank` over a strips buffer and an outbox buffer laid out like this class's own"""
+        q0, q1 = self.bounds[rank], self.bounds[rank + 1]
+        sizes = partition.orbit_strip_sizes(self.nside, q0, q1)
+        shard = capi.OrbitShard()
+        shard.q_begin, shard.q_end = q0, q1
         off = 0
-        self.strip_offsets = [[0] * 12 for _ in range(3)]
         for s in range(3):
             for f in range(12):
-                self.strip_offsets[s][f] = off
-                self.shard.strip[s][f] = self.strips.ptr + 8 * off
+                shard.strip[s][f] = strips_ptr + 8 * off
                 off += sizes[s][f]
-        self.outbox = None
-        self.outbox_kinds = []
-        if world > 1 and self.q1 > self.q0:
-            self.outbox_kinds = partition.orbit_outbox_kinds(capi.orbit_plan(nside, mode))
-            block = self.npix * (self.q1 - self.q0)
-            self.outbox = DeviceBuffer(ctx, block * len(self.outbox_kinds))
+        if outbox_ptr:
+            block = self.npix * (q1 - q0)
             for i, (t, f) in enumerate(self.outbox_kinds):
-                self.shard.outbox[t][f] = self.outbox.ptr + 8 * block * i
-        self.pairs = partition.orbit_pairs_in_range(self.q0, self.q1, self.face_pix, mode)
+                shard.outbox[t][f] = outbox_ptr + 8 * block * i
+        return shard
 
     def generate(self, weights):
         self.ctx.tqu_orbit_sharded(*weights, self.shard, self.mode)
@@ -160,6 +169,37 @@ class OrbitShardedTQU:
         """place this rank's pieces into a whole packed triangle on this GPU (parts: 1 strips, 2 outbox; the strips of all
         ranks go in before any outbox, a strip has holes where another rank's outbox holds the entry)"""
         self.ctx.tqu_orbit_assemble(self.shard, full, self.mode, parts)
+
+    def gather_full(self, full):
+        """NCCL: every rank ends up with the whole packed triangle in `full` (only when a consumer needs it).  A strip is a
+        contiguous piece of the packed triangle, so each one is broadcast straight into place; a rank's outbox buffer is
+        broadcast whole into a scratch buffer and placed by orbitOutboxScatterKernel.  (The outbox is allocated dense, so
+        this moves about twice the bytes of the matrix; a tile-major outbox would halve it.)"""
+        import torch
+        import torch.distributed as dist
+        n = self.npix
+        for r in range(self.world):                       # strips of all ranks first
+            q0, q1 = self.bounds[r], self.bounds[r + 1]
+            sizes = partition.orbit_strip_sizes(self.nside, q0, q1)
+            if r == self.rank:
+                self.assemble_into(full, 1)
+            for s in range(3):
+                for f in range(12):
+                    first = partition.packed_size(s * n + f * self.face_pix + q0)
+                    if self.world > 1 and sizes[s][f]:
+                        dist.broadcast(full[first:first + sizes[s][f]], src=r)
+        if self.world == 1:
+            return
+        scratch = torch.empty(max(self.sizes_of(r)[1] for r in range(self.world)), dtype=torch.float64, device="cuda")
+        for r in range(self.world):
+            n_outbox = self.sizes_of(r)[1]
+            if not n_outbox:
+                continue
+            buf = self.outbox.tensor() if r == self.rank else scratch[:n_outbox]
+            dist.broadcast(buf, src=r)
+            # only the outbox pointers of this descriptor are read (parts = 2)
+            shard = self.shard_of(r, self.strips.ptr, buf.data_ptr())
+            self.ctx.tqu_orbit_assemble(shard, full, self.mode, 2)
 
     def close(self):
         for b in self.pieces():

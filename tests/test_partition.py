@@ -146,3 +146,61 @@ def test_two_rank_orbit_planning_over_gloo():
     assert rows[0, 0] == 0 and rows[0, 1] == rows[1, 0] and rows[1, 1] == f      # the ranks' in-face ranges tile [0, nside^2)
     assert rows[:, 2].sum() == partition.orbit_pairs_in_range(0, f, f, 0)        # every source pair evaluated once
     assert rows[:, 3].sum() == partition.packed_size(3 * 12 * f)                 # strips tile the packed triangle
+
+
+class _FakeCtx:
+    """stands in for capi.Context where only device_malloc / device_free are needed (no GPU)"""
+
+    def __init__(self):
+        self.next = 0x10000000
+        self.live = {}
+
+    def device_malloc(self, nbytes):
+        p = self.next
+        self.next += (nbytes + 255) // 256 * 256
+        self.live[p] = nbytes
+        return p
+
+    def device_free(self, ptr):
+        del self.live[ptr]
+
+
+@pytest.mark.parametrize("world,mode", [(1, 0), (2, 0), (3, 1)])
+def test_orbit_shard_descriptor_layout(world, mode):
+    """OrbitShardedTQU: the 36 strips are laid out back to back in (strip, face) order = ascending packed columns, the outbox
+    blocks follow the plan's (kind, face) list; with one rank the strips buffer IS the packed triangle."""
+    from cosmopp_b200 import capi, multigpu
+    nside = 16
+    f, n = nside * nside, 12 * nside * nside
+    for rank in range(world):
+        ctx = _FakeCtx()
+        sh = multigpu.OrbitShardedTQU(ctx, nside, rank, world, mode)
+        q0, q1 = sh.q0, sh.q1
+        assert (sh.shard.q_begin, sh.shard.q_end) == (q0, q1)
+        sizes = partition.orbit_strip_sizes(nside, q0, q1)
+        off = 0
+        for s in range(3):
+            for face in range(12):
+                assert sh.shard.strip[s][face] == sh.strips.ptr + 8 * off
+                off += sizes[s][face]
+        assert off == sh.strips.n and ctx.live[sh.strips.ptr] >= 8 * off
+        if world == 1:
+            assert sh.outbox is None and off == partition.packed_size(3 * n)
+            for s in range(3):                     # single owner: strip (s, face) starts at its packed offset
+                for face in range(12):
+                    assert sh.shard.strip[s][face] == sh.strips.ptr + 8 * partition.packed_size(s * n + face * f)
+            assert all(sh.shard.outbox[t][face] is None for t in range(6) for face in range(12))
+        else:
+            kinds = partition.orbit_outbox_kinds(capi.orbit_plan(nside, mode))
+            assert len(kinds) == (54 if mode == 0 else 36)
+            block = n * (q1 - q0)
+            assert sh.outbox.n == block * len(kinds)
+            for i, (t, face) in enumerate(kinds):
+                assert sh.shard.outbox[t][face] == sh.outbox.ptr + 8 * block * i
+            unused = [(t, face) for t in range(6) for face in range(12) if (t, face) not in kinds]
+            assert all(sh.shard.outbox[t][face] is None for t, face in unused)
+        assert sh.sizes_of(rank) == (sh.strips.n, sh.outbox.n if sh.outbox is not None else 0)
+        other = sh.shard_of(rank, 0x5000, 0x9000 if world > 1 else 0)
+        assert other.strip[0][0] == 0x5000 and (world == 1 or other.outbox[0][0] == 0x9000)
+        sh.close()
+        assert not ctx.live
