@@ -218,3 +218,30 @@ def test_orbit_plan_rejects_bad_arguments():
     for mode in (0, 1):
         plan = capi.orbit_plan(8, mode)
         assert len(plan) <= 24 and all(1 <= len(c["images"]) <= 4 for c in plan)
+
+
+def test_mirror_symmetries_of_the_oracle_matrix(oracle_matrix):
+    """The rest of the grid's symmetry group (not used by the kernels yet; DESIGN.md, open items): the equatorial mirror
+    (north face f <-> f + 8, in-face (ix, iy) -> (N-1-iy, N-1-ix)) and the meridian mirror phi -> pi/2 - phi (polar face position
+    p -> -p, equatorial p -> 1 - p, ix <-> iy).  A reflection flips the sign of every entry with exactly one U index."""
+    nside, n, M = oracle_matrix
+    F = nside * nside
+
+    def swapbits(q):
+        return (((q & 0x55555555) << 1) | ((q & 0xAAAAAAAA) >> 1)) & (F - 1)
+
+    pix = np.arange(n)
+    face, q = pix // F, pix % F
+    equatorial = np.where(face < 4, face + 8, np.where(face >= 8, face - 8, face)) * F + swapbits(~q & (F - 1))
+    ring, pos = face // 4, face % 4
+    meridian = (ring * 4 + np.where(ring == 1, (1 - pos) % 4, (-pos) % 4)) * F + swapbits(q)
+    v = api.unit_vectors(nside).reshape(n, 3)
+    assert np.abs(v[equatorial] - v * np.array([1.0, 1.0, -1.0])).max() < 1e-15
+    assert np.abs(v[meridian] - v[:, [1, 0, 2]]).max() < 2e-15
+    sign = np.concatenate([np.ones(n), np.ones(n), -np.ones(n)])
+    for perm in (equatorial, meridian):
+        assert np.array_equal(perm[perm], pix)                       # involutions
+        idx = np.concatenate([perm, n + perm, 2 * n + perm])
+        image = M[np.ix_(idx, idx)] * np.outer(sign, sign)
+        assert np.abs(image - M)[:n].max() < 1e-11 * M[0, 0]
+        assert np.abs(image - M)[n:].max() < 1e-11 * M[n, n]
