@@ -191,19 +191,24 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def config_dict(name, kind, nside, lmax, npix, n_gpus, shard_mode="outbox", orbit=False):
+def config_dict(name, kind, nside, lmax, npix, n_gpus, shard_mode="outbox"):
+    """the WORKLOAD (identical for the GPU arm and the reference arm); how the GPU arm goes about it is the line's `path`"""
     dim = npix * (3 if kind == "tqu" else 1)
-    sharding = "equal-area pixel-column blocks over %d rank(s), no collective" % n_gpus
-    if orbit:
-        sharding = "in-face column ranges of all 12 base faces (orbit-closed sets of pixel columns) over %d rank(s), no collective" % n_gpus
     return {
         "workload": name, "kind": kind, "nside": nside, "lmax": lmax, "npix": npix, "matrix_dim": dim,
         "packed_bytes": 8 * dim * (dim + 1) // 2, "fwhm_deg": FWHM, "pixel_window": "1 (HEALPix window file unavailable offline)",
-        "path": "symmetry orbits (cmg_tqu_orbit / cmg_legendre_series_orbit): one evaluation per orbit of pixel pairs under the pi/2 "
-                "rotation of the grid, all images stored" if orbit else "every pixel pair evaluated",
-        "sharding": sharding, "shard_mode": shard_mode if n_gpus > 1 else "single",
+        "sharding": "one matrix split over %d rank(s), no collective" % n_gpus, "shard_mode": shard_mode if n_gpus > 1 else "single",
         "l2": "each step writes its whole output (>> 126 MB L2) with streaming stores; nothing is re-read between steps",
     }
+
+
+def path_dict(kind, orbit, n_gpus):
+    if orbit:
+        return {"method": "symmetry orbits (cmg_tqu_orbit / cmg_legendre_series_orbit): one evaluation per orbit of pixel pairs under the "
+                          "pi/2 rotation of the HEALPix grid, every image stored -- the same packed matrix",
+                "sharding": "in-face column ranges of all 12 base faces (orbit-closed sets of pixel columns) over %d rank(s)" % n_gpus}
+    return {"method": "every pixel pair evaluated (%s)" % ("cmg_tqu" if kind == "tqu" else "cmg_legendre_series"),
+            "sharding": "equal-area pixel-column blocks over %d rank(s)" % n_gpus}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -444,8 +449,8 @@ def run_gpu_arm(args):
         line = {
             "metric": "pixel_pair_ell_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "ms_per_matrix": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world, args.shard_mode, use_orbit),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world, args.shard_mode),
+            "path": path_dict(kind, use_orbit, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "fp64_frac_of_peak": achieved / peak_tflops, "gather": gather,
         }
         print(json.dumps(line))
