@@ -339,7 +339,7 @@ class Context:
         self._check(self._L.cmg_tqu_dev(self._h, _p(d_a), int(lmax), ctypes.byref(layout)))
 
     def tqu_orbit(self, a_tt, a_te, a_ee, a_bb, d_packed, mode=0):
-        """EXPERIMENTAL full-sky path: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid."""
+        """full-sky path: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid (include/cmg.h)"""
         a_tt, a_te, a_ee, a_bb = map(_f64, (a_tt, a_te, a_ee, a_bb))
         self._check(self._L.cmg_tqu_orbit(self._h, _p(a_tt), _p(a_te), _p(a_ee), _p(a_bb), len(a_tt) - 1, _p(d_packed), int(mode)))
 

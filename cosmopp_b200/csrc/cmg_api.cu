@@ -918,7 +918,7 @@ cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* dA, int lmax, const cmg_tqu_l
     return launchTqu(ctx, dA, 0, lmax, 1, layout, 0, nullptr);
 }
 
-// ---------------------------------------------------------------- T,Q,U over symmetry orbits (experimental)
+// ---------------------------------------------------------------- T,Q,U and TT over symmetry orbits (full sky)
 
 cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* nClasses)
 {

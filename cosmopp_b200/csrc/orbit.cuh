@@ -1,4 +1,4 @@
-// Symmetry orbits of the full-sky HEALPix pixelisation (experimental path, cmg_tqu_orbit).
+// Symmetry orbits of the full-sky HEALPix pixelisation (cmg_tqu_orbit, cmg_tqu_orbit_sharded, cmg_legendre_series_orbit).
 //
 // The grid is invariant under the rotation R by pi/2 about the polar axis; in NESTED ordering R maps base face f to
 // (f & ~3) | ((f + 1) & 3) and keeps the index inside the face.  The local frames (e_theta, e_phi) rotate with the
@@ -15,7 +15,7 @@
 //   same ring, faces (0, 2)                    q_row <= q_col          (0,2) (1,3), and transposed (2,0) (3,1)
 //
 // = 18 of the 72 face-pair units of the triangle, i.e. a quarter of the recurrence work.  A transposed image needs
-// six of its nine entries staged through shared memory instead of three (kernel template SWAP).  Without transposed
+// six of its nine entries staged through shared memory instead of three (kernel template SWAPMASK).  Without transposed
 // images (mode 1) the classes (0,1) x 3 images, (0,3) alone and the whole of (0,2) x 2 images cost 22.5 units (3.2x).
 #pragma once
 

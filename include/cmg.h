@@ -182,7 +182,7 @@ cmg_status cmg_tqu_scatter_block(cmg_ctx* ctx, const double* d_block, int64_t co
  * read from the host, so the call can be captured in a CUDA graph and replayed after the weights were updated in place
  * (shared-memory coefficient table kernel; the parameter-block kernel needs the weights on the host at launch) */
 cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* d_a, int lmax, const cmg_tqu_layout* layout);
-/* EXPERIMENTAL (opt-in; not what cmg_tqu or the drop-in classes call): the same matrix for the FULL sky, evaluated once per
+/* The same matrix as cmg_tqu for the FULL sky (what cmg_cl_to_cmatrix_pol and the drop-in classes run there), evaluated once per
  * orbit of pixel pairs under the pi/2 rotation of the HEALPix grid about the polar axis (NESTED: base face f -> next face of
  * its ring, index inside the face kept).  Frames rotate with the pixels, so C[X Ra, Y Rb] = C[X a, Y b] and the four sums of
  * a pair are computed once and stored at its (up to) four images: a quarter of the recurrence work of cmg_tqu (mode 0), or
