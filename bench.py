@@ -387,6 +387,8 @@ def run_gpu_arm(args):
 
     # ---- e2e: host C_l in, host packed shard out, copies inside the timed region
     e2e = None
+    if args.host_expand > 0 and use_orbit and world == 1:
+        ctx.set_host_expand(args.host_expand)
     if not args.no_e2e:
         if kind == "tqu" and world == 1:
             del pieces, lay
@@ -437,6 +439,7 @@ def run_gpu_arm(args):
             dist.all_reduce(wall, op=dist.ReduceOp.MAX)
         e2e = {"value": units_total * e2e_steps / float(wall.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * float(wall.item()) / e2e_steps, "steps": e2e_steps,
+               "host_expand_threads": args.host_expand if (use_orbit and world == 1) else 0,
                "note": "per rank: C_l from pinned host memory, this rank's shard of the packed matrix back to pinned host memory"
                        + (" (strips + outbox blocks, through a 2 x 1 GiB pinned ring)" if (use_orbit and world > 1) else "")}
 
@@ -470,6 +473,9 @@ def main():
                          "through CUDA-IPC peer memory over NVLink (peer)")
     ap.add_argument("--gather", action="store_true", help="N>1, T,Q,U: also time the NCCL gather of the whole matrix onto every GPU")
     ap.add_argument("--no-orbit", action="store_true", help="full-sky T,Q,U: evaluate every pixel pair (cmg_tqu) instead of one per symmetry orbit")
+    ap.add_argument("--host-expand", type=int, default=0, metavar="THREADS",
+                    help="N=1, full sky, e2e leg: copy back only the last-face columns (27 %% of the matrix) and fill in the rotated images "
+                         "on THREADS host threads (cmg_set_host_expand; opt-in until it has been timed on the GPU box)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

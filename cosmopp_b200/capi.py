@@ -101,6 +101,8 @@ _SIGNATURES = {
     "cmg_tqu_orbit_sharded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(OrbitShard), ctypes.c_int]),
     "cmg_tqu_orbit_assemble": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), ctypes.c_int, ctypes.c_int, _vp]),
     "cmg_legendre_series_orbit": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "cmg_host_expand_rotations": (ctypes.c_int, [_vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "cmg_set_host_expand": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_tqu_orbit_plan": (ctypes.c_int, [_i64, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cmg_tqu_weights": (ctypes.c_int, [_vp] * 6 + [ctypes.c_int] + [_vp] * 4),
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
@@ -163,6 +165,13 @@ def _p(a):
     if isinstance(a, int):
         return _vp(a)
     return _vp(a.data_ptr())        # torch tensor
+
+
+def host_expand_rotations(packed, nside, strips, threads=1, faces=(0, 12)):
+    """cmg_host_expand_rotations on a numpy array in place (pure CPU); strips = 1 (TT) or 3 ([T;Q;U])"""
+    st = library().cmg_host_expand_rotations(_p(packed), int(nside), 0, int(strips), int(faces[0]), int(faces[1]), int(threads))
+    if st:
+        raise CmgError(st, "cmg_host_expand_rotations: bad arguments")
 
 
 def orbit_plan(nside, mode=0):
@@ -233,6 +242,10 @@ class Context:
 
     def set_timing(self, on):
         self._check(self._L.cmg_set_timing(self._h, 1 if on else 0))
+
+    def set_host_expand(self, threads):
+        """opt-in: full-sky whole calls copy back the last-face columns only and fill in the rest on `threads` host threads"""
+        self._check(self._L.cmg_set_host_expand(self._h, int(threads)))
 
     def set_kernel_variant(self, v):
         self._check(self._L.cmg_set_kernel_variant(self._h, int(v)))

@@ -50,6 +50,7 @@ struct cmg_ctx
 
     cmg::SeriesTable hostT0, hostT20, hostT22;   // host copies of the recurrence tables
     int tquVariant = 0;                          // 0 = automatic choice (see launchTqu)
+    int hostExpandThreads = 0;                   // > 0: full-sky whole calls copy back a quarter and expand on the host
 
     static const int kAux = 4;                   // side streams for many small independent launches (batched mode)
     cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
@@ -805,6 +806,34 @@ cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, 
     return launchLegendre(ctx, ctx->dWeights, lmax + 1, lmax, nBatch, colBegin, colEnd, dOut, stride, nullptr);
 }
 
+// Full sky, host output, cmg_set_host_expand: only the columns of the last face of every ring cross PCIe (contiguous pieces of
+// the packed triangle in ctx->dScratch, smallest first); the host fills in the rotated images of a piece as soon as it has
+// arrived, while the next pieces are in flight (host_expand.cpp).
+static cmg_status copyBackLastFacesAndExpand(cmg_ctx* ctx, int strips, double* outPacked)
+{
+    const int64_t n = ctx->npix, facePix = ctx->nside * ctx->nside;
+    const int pieces = 3 * strips;
+    cudaEvent_t arrived[9];
+    for(int k = 0; k < pieces; ++k)
+    {
+        const int strip = k / 3, face = 4 * (k % 3) + 3;
+        const int64_t first = cmg_packed_size(strip * n + face * facePix), last = cmg_packed_size(strip * n + (face + 1) * facePix);
+        CMG_CUDA(ctx, cudaMemcpyAsync(outPacked + first, ctx->dScratch + first, sizeof(double) * (last - first), cudaMemcpyDeviceToHost, ctx->stream));
+        CMG_CUDA(ctx, cudaEventCreateWithFlags(&arrived[k], cudaEventDisableTiming));
+        CMG_CUDA(ctx, cudaEventRecord(arrived[k], ctx->stream));
+    }
+    cmg_status st = CMG_OK;
+    for(int k = 0; k < pieces; ++k)
+    {
+        const cudaError_t e = cudaEventSynchronize(arrived[k]);
+        cudaEventDestroy(arrived[k]);
+        if(e != cudaSuccess && st == CMG_OK) st = cudaFail(ctx, e, "cudaEventSynchronize");
+        if(st == CMG_OK)
+            st = cmg_host_expand_rotations(outPacked, ctx->nside, k / 3, k / 3 + 1, 4 * (k % 3), 4 * (k % 3) + 4, ctx->hostExpandThreads);
+    }
+    return st;
+}
+
 static cmg_status wholeCallTT(cmg_ctx* ctx, const std::vector<double>& a, int lmax, double* outPacked)
 {
     const int64_t bytes = sizeof(double) * cmg_packed_size(ctx->npix);
@@ -814,6 +843,8 @@ static cmg_status wholeCallTT(cmg_ctx* ctx, const std::vector<double>& a, int lm
     const bool orbit = ctx->fullSky && ctx->nside >= 16 && lmax + 1 <= cmg::TT_STATIC_STEPS && ctx->tquVariant == 0;
     if((s = orbit ? cmg_legendre_series_orbit(ctx, a.data(), lmax, ctx->dScratch)
                   : cmg_legendre_series(ctx, a.data(), lmax, 0, ctx->npix, ctx->dScratch)) != CMG_OK) return s;
+    if(ctx->fullSky && ctx->hostExpandThreads > 0)
+        return copyBackLastFacesAndExpand(ctx, 1, outPacked);
     CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CMG_OK;
@@ -1312,6 +1343,8 @@ cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* 
         if((s = cmg_tqu_layout_single(ctx, ctx->dScratch, &layout)) != CMG_OK) return s;
         if((s = cmg_tqu(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, &layout)) != CMG_OK) return s;
     }
+    if(ctx->fullSky && ctx->hostExpandThreads > 0)
+        return copyBackLastFacesAndExpand(ctx, 3, outPacked);
     CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CMG_OK;
@@ -1748,6 +1781,13 @@ cmg_status cmg_set_kernel_variant(cmg_ctx* ctx, int variant)
 {
     if(!ctx || variant < 0) return CMG_EINVAL;   // (1 also selects the shared-memory-table TT kernel)
     ctx->tquVariant = variant;
+    return CMG_OK;
+}
+
+cmg_status cmg_set_host_expand(cmg_ctx* ctx, int threads)
+{
+    if(!ctx || threads < 0) return CMG_EINVAL;
+    ctx->hostExpandThreads = threads;
     return CMG_OK;
 }
 

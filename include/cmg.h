@@ -216,6 +216,18 @@ cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, in
  * Full sky, nside >= 16, d_out = the whole packed triangle of dimension N.  cmg_cl_to_cmatrix / cmg_fiducial_matrix take this
  * path by themselves on the full sky (any non-zero cmg_set_kernel_variant pins the every-pair kernels). */
 cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, double* d_out);
+/* Host half of a full-sky whole call (pure CPU): `packed` is a packed matrix of dimension N (TT) or 3N ([T;Q;U]) in HOST memory
+ * whose columns of the last face of every ring of four base faces (faces 3, 7, 11, of each strip) are filled in; the columns
+ * of the other faces in [face_begin, face_end), strips [strip_begin, strip_end), are written as their rotated images (runs
+ * of nside^2 rows copied from the matching column of the ring's last face), `threads` host threads.  With it only 27 % of the
+ * matrix has to cross PCIe; cmg_set_host_expand makes the whole calls work that way. */
+cmg_status cmg_host_expand_rotations(double* packed, int64_t nside, int strip_begin, int strip_end, int face_begin, int face_end,
+                                     int threads);
+/* OPT-IN, off by default (not yet timed on the GPU box: whether host block copies beat the PCIe copy they replace depends on the
+ * host): threads > 0 makes cmg_cl_to_cmatrix_pol, cmg_cl_to_cmatrix and cmg_fiducial_matrix on the full sky copy back only the
+ * last-face columns and fill in the rest with
+ * cmg_host_expand_rotations on `threads` host threads while the remaining copies are in flight; 0 restores the plain copy. */
+cmg_status cmg_set_host_expand(cmg_ctx* ctx, int threads);
 /* the classes of base-face pairs cmg_tqu_orbit works through (host only; for tests): out[c][CMG_ORBIT_CLASS_INTS] =
  * { row face, column face, only q_row <= q_col, same face, n_images, then for image k = 0..3: row face, column face,
  *   stored transposed }; out must hold CMG_ORBIT_MAX_CLASSES classes */

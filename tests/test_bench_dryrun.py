@@ -43,6 +43,9 @@ class FakeContext:
     def set_kernel_variant(self, v):
         self.variant = v
 
+    def set_host_expand(self, threads):
+        self.host_expand = threads
+
     def measure_fp64_peak(self):
         return 37.0
 
@@ -116,7 +119,7 @@ REQUIRED = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
 
 
 @pytest.mark.parametrize("workload,extra,orbit,launches_per_step", [
-    ("tqu_nside32_lmax96", [], True, 1), ("tqu_nside32_lmax96", ["--no-orbit"], False, 1),
+    ("tqu_nside32_lmax96", [], True, 1), ("tqu_nside32_lmax96", ["--no-orbit"], False, 1), ("tqu_nside32_lmax96", ["--host-expand", "4"], True, 1),
     ("tt_nside32_lmax96", [], True, 1), ("tt_nside16_lmax47", ["--no-orbit"], False, 1),
     ("tqu_nside16_lmax47_masked", [], False, 1)])
 def test_single_rank_line(fake_gpu, capsys, monkeypatch, workload, extra, orbit, launches_per_step):

@@ -245,3 +245,36 @@ def test_mirror_symmetries_of_the_oracle_matrix(oracle_matrix):
         image = M[np.ix_(idx, idx)] * np.outer(sign, sign)
         assert np.abs(image - M)[:n].max() < 1e-11 * M[0, 0]
         assert np.abs(image - M)[n:].max() < 1e-11 * M[n, n]
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_host_expansion_rebuilds_the_matrix_from_the_last_face_columns(oracle_matrix, threads):
+    """cmg_host_expand_rotations (pure CPU): keep only the columns of base faces 3, 7, 11 of every strip, the rest comes back
+    as rotated images."""
+    nside, n, M = oracle_matrix
+    F = nside * nside
+    want, iu = packed_from_full(M)
+    col = np.empty(want.size, dtype=np.int64)
+    col[iu[1] * (iu[1] + 1) // 2 + iu[0]] = iu[1]
+    kept = ((col % n) // F) % 4 == 3
+    assert 0.25 < kept.mean() < 0.29                               # 27 % of the entries cross PCIe
+    got = np.where(kept, want, np.nan)
+    capi.host_expand_rotations(got, nside, 3, threads)
+    assert not np.isnan(got).any()
+    assert np.array_equal(got[kept], want[kept])
+    scale = np.where(col < n, M[0, 0], M[n, n])
+    assert (np.abs(got - want) / scale).max() < 1e-11
+    # TT alone (one strip)
+    tt = want[:capi.packed_size(n)].copy()
+    got = np.where(kept[:tt.size], tt, np.nan)
+    capi.host_expand_rotations(got, nside, 1, threads)
+    assert (np.abs(got - tt) / M[0, 0]).max() < 1e-11
+    # a piece at a time, as the whole call does while later pieces are still in flight
+    got = np.where(kept, want, np.nan)
+    L = capi.library()
+    for strip in range(3):
+        for ring in range(3):
+            assert L.cmg_host_expand_rotations(got.ctypes.data, nside, strip, strip + 1, 4 * ring, 4 * ring + 4, threads) == 0
+    assert (np.abs(got - want) / scale).max() < 1e-11
+    with pytest.raises(capi.CmgError):
+        capi.host_expand_rotations(got, 12, 3)
