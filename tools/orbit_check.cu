@@ -1,8 +1,8 @@
 // Quick parity + timing probe of the experimental symmetry-orbit path (cmg_tqu_orbit) against cmg_tqu, through the C ABI
 // only (no Python: starts in a second on a fresh box).
-//   nvcc -O2 -std=c++17 -I include -o gpurun_out/orbit_check tools/orbit_check.cu -L cosmopp_b200/lib -lcosmopp_b200 \
-//        -Xlinker -rpath=$PWD/cosmopp_b200/lib
-//   gpurun_out/orbit_check [nside_max_for_timing]
+//   nvcc -O2 -std=c++17 -I include -o tools/bin/orbit_check tools/orbit_check.cu -L cosmopp_b200/lib -lcosmopp_b200 \
+//        -Xlinker -rpath='$ORIGIN/../../cosmopp_b200/lib'
+//   tools/bin/orbit_check [full | tt | ranks | prof]          (a call costs ~20 s of GPU box time: no Python start-up)
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
