@@ -637,9 +637,11 @@ def test_linearity_in_the_spectra(gpu_ctx):
     assert resid <= 1e-12 * mats[2][0].item()
 
 
-def test_full_size_nside64_polarized_sampled(gpu_ctx, oracle_api):
+@pytest.mark.parametrize("orbit", [False, True])
+def test_full_size_nside64_polarized_sampled(gpu_ctx, oracle_api, orbit):
     """BASELINE config 5 at full size (147456 x 147456, 87 GB on the device): all nine entries of 150k random pixel
-    pairs, of every diagonal pair and of 2000 antipodal pairs against the oracle, plus the block structure on the diagonal."""
+    pairs, of every diagonal pair and of 2000 antipodal pairs against the oracle, plus the block structure on the diagonal.
+    Once with every pair evaluated (cmg_tqu) and once over symmetry orbits (cmg_tqu_orbit, what bench.py's default runs)."""
     torch = _torch()
     from cosmopp_b200 import capi
     free, _total = torch.cuda.mem_get_info()
@@ -654,7 +656,10 @@ def test_full_size_nside64_polarized_sampled(gpu_ctx, oracle_api):
     a = capi.tqu_weights(*spectra, f, f)
     out = torch.empty(capi.packed_size(3 * n), dtype=torch.float64, device="cuda")
     out.fill_(float("nan"))
-    gpu_ctx.tqu(*a, gpu_ctx.tqu_layout_single(out))
+    if orbit:
+        gpu_ctx.tqu_orbit(*a, out, 0)
+    else:
+        gpu_ctx.tqu(*a, gpu_ctx.tqu_layout_single(out))
     torch.cuda.synchronize()
     assert not torch.isnan(out[::4099]).any()
     rs = np.random.RandomState(64)
