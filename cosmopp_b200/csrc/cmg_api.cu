@@ -980,7 +980,8 @@ namespace
 cmg_status orbitShardDev(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, cmg::OrbitShardDev& sh)
 {
     if(!shard) return fail(ctx, CMG_EINVAL, "null shard");
-    if(mode != 0 && mode != 1) return fail(ctx, CMG_EINVAL, "orbit mode must be 0 (transposed images) or 1 (none)");
+    if(mode < 0 || mode > 2) return fail(ctx, CMG_EINVAL, "orbit mode must be 0 (transposed images), 1 (none) or 2 (0 with the row-pointer table)");
+    if(mode == 2) mode = 0;                          // same classes, same storage
     if(!ctx->fullSky)
         return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs the full sky in NESTED order (cmg_set_pixels with good_nest = NULL)");
     if(ctx->nside < 8)
@@ -1043,7 +1044,7 @@ cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* att, const double* 
     for(int m = 0; m < 3; ++m)
     {
         cmg::OrbitPlan plan;
-        cmg::orbitBuildPlan(ctx->nside, mode, masks[m], plan);
+        cmg::orbitBuildPlan(ctx->nside, mode == 2 ? 0 : mode, masks[m], plan);
         if(plan.n == 0)
             continue;
         const dim3 grid(tiles, static_cast<unsigned>(plan.n));
@@ -1054,7 +1055,15 @@ cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* att, const double* 
             CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));       \
             kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);                          \
         }
-        if(masks[m] == 0) CMG_ORBIT_LAUNCH(0)
+        if(masks[m] == 0 && mode == 2)
+        {
+            // classes without transposed images, store destinations from a per-tile table in shared memory (not yet run on a GPU)
+            auto kernel = cmg::tquOrbitKernel<4, 2, 0, true>;
+            const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<false, true>();
+            CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
+        }
+        else if(masks[m] == 0) CMG_ORBIT_LAUNCH(0)
         else if(masks[m] == 8) CMG_ORBIT_LAUNCH(8)
         else CMG_ORBIT_LAUNCH(12)
 #undef CMG_ORBIT_LAUNCH
@@ -1121,6 +1130,7 @@ cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, in
     cmg::OrbitShardDev sh;
     cmg_status s = orbitShardDev(ctx, shard, mode, sh);
     if(s != CMG_OK) return s;
+    if(mode == 2) mode = 0;                          // mode 2 stores exactly what mode 0 stores
     if(sh.q0 == sh.q1) return CMG_OK;
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t facePix = ctx->nside * ctx->nside, n = ctx->npix;

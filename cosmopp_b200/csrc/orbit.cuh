@@ -117,10 +117,10 @@ struct OrbitShardDev
 };
 
 // shared memory of tquOrbitKernel: frames of rows and columns, staged entries, column pointers of every image
-template <bool SWAP>
+template <bool SWAP, bool ROWPTR = false>
 constexpr int orbitSmemDoubles()
 {
-    return 8 * PQ_TI + 8 * PQ_TJ + (SWAP ? 6 : 3) * PQ_TI * PQ_STAGE_LD + ORB_MAX_IMAGES * 3 * PQ_TJ;
+    return 8 * PQ_TI + 8 * PQ_TJ + (SWAP ? 6 : 3) * PQ_TI * PQ_STAGE_LD + ORB_MAX_IMAGES * 3 * PQ_TJ + (ROWPTR ? ORB_MAX_IMAGES * 3 * PQ_TI : 0);
 }
 
 // staged kind t -> (column strip X, row strip Y) of the entry <X a', Y b'>
@@ -141,7 +141,10 @@ __device__ __forceinline__ bool orbitTile(const OrbitPlan& plan, const OrbitShar
 // transposed partners <Q_a T_b>, <U_a T_b>, <U_a Q_b> for every image, and <T T>, <Q Q>, <U U> as well for a
 // transposed image (there the row image a' has the larger index, so (X a', X b') is stored in column X a').
 // SWAPMASK: bit k set = image k of every class of this launch is a transposed one (orbitBuildPlan).
-template <int R, int MINB, int SWAPMASK>
+// ROWPTR (SWAPMASK == 0 only; NOT YET RUN ON A GPU, selected by mode 2 of the API): the destination of every (image, kind, row)
+// of the store phase is computed once per tile into shared memory by all threads in parallel, as tquKernel does, instead of
+// ~25 instructions per warp store in the store loop.
+template <int R, int MINB, int SWAPMASK, bool ROWPTR = false>
 __global__ void __launch_bounds__(PQ_THREADS, MINB)
 tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entrySlot,
                const __grid_constant__ OrbitPlan plan, const __grid_constant__ OrbitShardDev sh)
@@ -153,6 +156,8 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     double* sJ = sI + 8 * PQ_TI;                                     // [8][PQ_TJ]
     double* stage = sJ + 8 * PQ_TJ;                                  // [SLOTS][PQ_TI][PQ_STAGE_LD]
     double** sColPtr = reinterpret_cast<double**>(stage + SLOTS * PQ_TI * PQ_STAGE_LD);   // [image][3][PQ_TJ]
+    double** sRowPtr = sColPtr + ORB_MAX_IMAGES * 3 * PQ_TJ;                              // [image][3][PQ_TI]  (ROWPTR only)
+    static_assert(!ROWPTR || SWAPMASK == 0, "the row-pointer table is sized for three staged kinds");
 
     int qRow0, qCol0;
     if(!orbitTile(plan, sh, qRow0, qCol0))
@@ -192,6 +197,24 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
         const int face = oc.imgColFace[k];
         const long long col = strip * npix + static_cast<long long>(face) * facePix + qCol0 + (rem - strip * PQ_TJ);
         sColPtr[idx] = sh.strip[strip][face] + packedOffset(col);
+    }
+    if(ROWPTR)
+    {
+        // where row (image k, kind t, a') of the store phase starts: the rank's own strip, or its outbox block
+        for(int idx = tid; idx < ORB_MAX_IMAGES * 3 * PQ_TI; idx += PQ_THREADS)
+        {
+            const int k = idx / (3 * PQ_TI);
+            const int rem = idx - k * 3 * PQ_TI;
+            const int t = rem / PQ_TI;
+            const int ilr = rem - t * PQ_TI;
+            const int rowFace = oc.imgRowFace[k], colFace = oc.imgColFace[k];
+            const long long rowPix = static_cast<long long>(rowFace) * facePix + qRow0 + ilr;
+            const long long colPix0 = static_cast<long long>(colFace) * facePix + qCol0;
+            const int qa = qRow0 + ilr;
+            sRowPtr[idx] = (qa >= sh.q0 && qa < sh.q1)
+                               ? sh.strip[orbitStripX(t)][rowFace] + packedOffset(orbitStripX(t) * npix + rowPix) + (orbitStripY(t) * npix + colPix0)
+                               : sh.outbox[t][colFace] + rowPix * (sh.q1 - sh.q0) + (qCol0 - sh.q0);
+        }
     }
     __syncthreads();
 
@@ -302,6 +325,21 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     const int sameFace = oc.sameFace;
     const unsigned ldOut = static_cast<unsigned>(sh.q1 - sh.q0);
     const int qColLane = qCol0 + lane;
+    if(ROWPTR)
+    {
+        const int minGap = !tri ? -(1 << 30) : (sameFace ? 1 : 0);
+        for(int k = 0; k < nImg; ++k)
+        {
+#pragma unroll 4
+            for(int row = warp; row < 3 * PQ_TI; row += PQ_THREADS / 32)
+            {
+                const int ilr = row & (PQ_TI - 1);
+                if(qColLane - (qRow0 + ilr) >= minGap)
+                    __stcs(sRowPtr[k * 3 * PQ_TI + row] + lane, stage[row * PQ_STAGE_LD + lane]);
+            }
+        }
+        return;
+    }
     for(int k = 0; k < nImg; ++k)
     {
         const bool swapped = (SWAPMASK >> k) & 1;

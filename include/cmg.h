@@ -188,7 +188,9 @@ cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* d_a, int lmax, const cmg_tqu_
  * a pair are computed once and stored at its (up to) four images: a quarter of the recurrence work of cmg_tqu (mode 0), or
  * 1/3.2 without transposed images (mode 1).  Entries of different images of one orbit are bit-identical to each other; each
  * differs from cmg_tqu's by the rounding of its own n_i.n_j only (the 1e-11 gate holds with the same margin).
- * Needs cmg_set_pixels(ctx, nside >= 8, NULL, 0), 2 <= lmax <= 441, a single-owner packed buffer d_packed of dimension 3N. */
+ * Needs cmg_set_pixels(ctx, nside >= 8, NULL, 0), 2 <= lmax <= 441, a single-owner packed buffer d_packed of dimension 3N.
+ * mode 2 (NOT YET RUN ON A GPU, nothing selects it by itself) = mode 0 with the store destinations of a tile precomputed in shared
+ * memory for the classes without transposed images; same classes, same storage, same results. */
 cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
                          const double* a_bb, int lmax, double* d_packed, int mode);
 /* The same over several GPUs with no data-path collective.  A rank owns the in-face index range [q_begin, q_end) of ALL

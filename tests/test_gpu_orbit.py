@@ -152,3 +152,19 @@ def test_tt_whole_call_takes_the_orbit_path_on_the_full_sky(gpu_ctx, oracle_api)
     gpu_ctx.fiducial_matrix(cl, lmax, 10.0, again)
     gpu_ctx.set_kernel_variant(0)
     assert np.abs(again.numpy() - out.numpy()).max() <= 1e-13 * want[0]
+
+
+@pytest.mark.skipif("not __import__('os').environ.get('CMG_TEST_UNVERIFIED')",
+                    reason="mode 2 (store destinations precomputed per tile) was written after the round's GPU time was spent: "
+                           "set CMG_TEST_UNVERIFIED=1 (or run tools/bin/orbit_check full) to try it")
+def test_orbit_mode2_is_bit_identical_to_mode0(gpu_ctx):
+    import torch
+    from cosmopp_b200 import capi
+    spectra, w = _inputs(gpu_ctx, 16, 40)
+    n = gpu_ctx.npix
+    a = torch.full((capi.packed_size(3 * n),), float("nan"), dtype=torch.float64, device="cuda")
+    b = torch.full_like(a, float("nan"))
+    gpu_ctx.tqu_orbit(*w, a, 0)
+    gpu_ctx.tqu_orbit(*w, b, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
