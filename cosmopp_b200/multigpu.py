@@ -127,7 +127,8 @@ class OrbitShardedTQU:
         self.npix = 12 * self.face_pix
         self.bounds = partition.orbit_partition(nside, world, mode)
         self.q0, self.q1 = self.bounds[rank], self.bounds[rank + 1]
-        self.outbox_kinds = partition.orbit_outbox_kinds(capi.orbit_plan(nside, mode)) if world > 1 else []
+        # (kind, column face, first row face, last row face + 1) of every outbox block the plan writes
+        self.outbox_blocks = partition.orbit_outbox_blocks(capi.orbit_plan(nside, mode)) if world > 1 else []
         n_strips, n_outbox = self.sizes_of(rank)
         # one allocation for the 36 strips: the pieces stay individually contiguous pieces of the packed triangle
         self.strips = DeviceBuffer(ctx, n_strips)
@@ -139,7 +140,7 @@ class OrbitShardedTQU:
         """doubles in the strips buffer and in the outbox buffer of rank `rank`"""
         q0, q1 = self.bounds[rank], self.bounds[rank + 1]
         n_strips = sum(sum(r) for r in partition.orbit_strip_sizes(self.nside, q0, q1))
-        n_outbox = self.npix * (q1 - q0) * len(self.outbox_kinds) if (self.world > 1 and q1 > q0) else 0
+        n_outbox = sum(hi - lo for _, _, lo, hi in self.outbox_blocks) * self.face_pix * (q1 - q0) if q1 > q0 else 0
         return n_strips, n_outbox
 
     def shard_of(self, rank, strips_ptr, outbox_ptr):
@@ -154,9 +155,13 @@ class OrbitShardedTQU:
                 shard.strip[s][f] = strips_ptr + 8 * off
                 off += sizes[s][f]
         if outbox_ptr:
-            block = self.npix * (q1 - q0)
-            for i, (t, f) in enumerate(self.outbox_kinds):
-                shard.outbox[t][f] = outbox_ptr + 8 * block * i
+            # only the row-pixel faces a block is ever addressed with are allocated; the pointer handed to the kernel is that of
+            # (virtual) row pixel 0, i.e. moved back by first_face x nside^2 rows of ld elements
+            per_face = self.face_pix * (q1 - q0)
+            off = 0
+            for t, f, lo, hi in self.outbox_blocks:
+                shard.outbox[t][f] = outbox_ptr + 8 * (off - lo * per_face)
+                off += (hi - lo) * per_face
         return shard
 
     def generate(self, weights):

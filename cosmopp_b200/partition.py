@@ -132,9 +132,19 @@ def orbit_strip_sizes(nside, q0, q1):
 
 def orbit_outbox_kinds(plan):
     """(kind t, face f) outbox blocks a plan writes: kinds 0..2 for every image, 3..5 for transposed images"""
-    need = set()
+    return [(t, f) for t, f, _, _ in orbit_outbox_blocks(plan)]
+
+
+def orbit_outbox_blocks(plan):
+    """Outbox blocks a plan writes, with the range of ROW-pixel faces each one is ever addressed with:
+    [(kind t, column face f, first row face, one past the last row face)].  Block (t, f) is indexed by the row pixel a' of the
+    pair (cmg_orbit_shard: outbox[t][f][a' ld + ...]), and the images of the plan pair column face f with a few row faces
+    only, so a rank allocates rows [first, last) x nside^2 of the block and passes the block pointer moved back by
+    first x nside^2 x ld elements: 26 instead of 54 block-sized allocations with transposed images."""
+    rng = {}
     for c in plan:
-        for _, col_face, swap in c["images"]:
+        for row_face, col_face, swap in c["images"]:
             for t in range(6 if swap else 3):
-                need.add((t, col_face))
-    return sorted(need)
+                lo, hi = rng.get((t, col_face), (row_face, row_face + 1))
+                rng[(t, col_face)] = (min(lo, row_face), max(hi, row_face + 1))
+    return [(t, f, lo, hi) for (t, f), (lo, hi) in sorted(rng.items())]

@@ -168,6 +168,15 @@ def test_sharded_store_rules_partition_the_triangle(oracle_matrix, mode, world):
         out, count, box_out, box_count, slot_count = emulate_kernel_stores(plan, nside, n, M, bounds[r], bounds[r + 1])
         assert slot_count.max() <= 1
         assert slot_count.sum() == box_count.sum()
+        # the rank allocates, of every outbox block, only the row-pixel faces the block is ever addressed with
+        blocks = {(t, f): (lo, hi) for t, f, lo, hi in partition.orbit_outbox_blocks(plan)}
+        F = nside * nside
+        for t in range(6):
+            for f in range(12):
+                rows = np.nonzero(slot_count[t, f].any(axis=1))[0]
+                if len(rows):
+                    lo, hi = blocks[(t, f)]
+                    assert lo * F <= rows.min() and rows.max() < hi * F
         total += count + box_count
         merged = np.where(count > 0, out, merged)
         merged = np.where(box_count > 0, box_out, merged)

@@ -191,16 +191,21 @@ def test_orbit_shard_descriptor_layout(world, mode):
                     assert sh.shard.strip[s][face] == sh.strips.ptr + 8 * partition.packed_size(s * n + face * f)
             assert all(sh.shard.outbox[t][face] is None for t in range(6) for face in range(12))
         else:
-            kinds = partition.orbit_outbox_kinds(capi.orbit_plan(nside, mode))
-            assert len(kinds) == (54 if mode == 0 else 36)
-            block = n * (q1 - q0)
-            assert sh.outbox.n == block * len(kinds)
-            for i, (t, face) in enumerate(kinds):
-                assert sh.shard.outbox[t][face] == sh.outbox.ptr + 8 * block * i
-            unused = [(t, face) for t in range(6) for face in range(12) if (t, face) not in kinds]
+            blocks = partition.orbit_outbox_blocks(capi.orbit_plan(nside, mode))
+            assert len(blocks) == (54 if mode == 0 else 36)
+            assert [(t, face) for t, face, _, _ in blocks] == partition.orbit_outbox_kinds(capi.orbit_plan(nside, mode))
+            per_face = f * (q1 - q0)
+            off = 0
+            for t, face, lo, hi in blocks:
+                assert 0 <= lo < hi <= 12
+                # the pointer is that of (virtual) row pixel 0: rows of faces [lo, hi) land inside the allocation, back to back
+                assert sh.shard.outbox[t][face] + 8 * lo * per_face == sh.outbox.ptr + 8 * off
+                off += (hi - lo) * per_face
+            assert sh.outbox.n == off and off < 0.55 * 54 * n * (q1 - q0)       # about half of 54 whole blocks (mode 0)
+            unused = [(t, face) for t in range(6) for face in range(12) if (t, face) not in [(b[0], b[1]) for b in blocks]]
             assert all(sh.shard.outbox[t][face] is None for t, face in unused)
         assert sh.sizes_of(rank) == (sh.strips.n, sh.outbox.n if sh.outbox is not None else 0)
         other = sh.shard_of(rank, 0x5000, 0x9000 if world > 1 else 0)
-        assert other.strip[0][0] == 0x5000 and (world == 1 or other.outbox[0][0] == 0x9000)
+        assert other.strip[0][0] == 0x5000 and (world == 1 or other.outbox[0][0] is not None)
         sh.close()
         assert not ctx.live
