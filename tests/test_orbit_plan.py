@@ -287,3 +287,34 @@ def test_host_expansion_rebuilds_the_matrix_from_the_last_face_columns(oracle_ma
     assert (np.abs(got - want) / scale).max() < 1e-11
     with pytest.raises(capi.CmgError):
         capi.host_expand_rotations(got, 12, 3)
+
+
+@pytest.fixture(scope="module")
+def oracle_matrix16():
+    nside, lmax = 16, 12
+    n = 12 * nside * nside
+    return nside, n, api.unpack_symmetric(api.tqu_matrix(*synthetic_cl(lmax, pol=True), nside, 10.0), 3 * n)
+
+
+@pytest.mark.parametrize("world,mode", [(2, 0), (3, 0), (3, 1)])
+def test_sharded_store_rules_at_the_gpu_test_sizes(oracle_matrix16, world, mode):
+    """the configurations tests/test_gpu_orbit.py runs on the device (Nside=16): every entry once, every outbox store inside the
+    row faces the rank allocates for that block"""
+    from cosmopp_b200 import partition
+    nside, n, M = oracle_matrix16
+    F = nside * nside
+    plan = capi.orbit_plan(nside, mode)
+    bounds = partition.orbit_partition(nside, world, mode)
+    blocks = {(t, f): (lo, hi) for t, f, lo, hi in partition.orbit_outbox_blocks(plan)}
+    total = None
+    for r in range(world):
+        _, count, _, box_count, slot_count = emulate_kernel_stores(plan, nside, n, M, bounds[r], bounds[r + 1])
+        assert slot_count.max() <= 1
+        for t in range(6):
+            for f in range(12):
+                rows = np.nonzero(slot_count[t, f].any(axis=1))[0]
+                if len(rows):
+                    lo, hi = blocks[(t, f)]
+                    assert lo * F <= rows.min() and rows.max() < hi * F
+        total = count + box_count if total is None else total + count + box_count
+    assert total.min() == 1 and total.max() == 1
