@@ -42,6 +42,7 @@ WORKLOADS = {
     "tqu_nside16_lmax47_masked": ("tqu", 16, 47, True), # configs[1]
     "tt_nside16_lmax47": ("tt", 16, 47, False),         # configs[0]
     "tqu_nside32_lmax96": ("tqu", 32, 96, False),
+    "batched_x1024_tqu_nside16_lmax47": ("batched", 16, 47, 1024),   # configs[3]: kind, nside, lmax, batch
 }
 FLOP_PER_UNIT = {"tt": 4.0, "tqu": 20.0}        # algorithmic FLOP per pixel-pair*l
 FWHM = 10.0
@@ -109,6 +110,8 @@ class ClockSampler:
 
 def workload_geometry(name):
     kind, nside, lmax, masked = WORKLOADS[name]
+    if kind == "batched":
+        masked = False                    # the fourth field is the batch size there
     good = None
     if masked:
         # the reference test's deterministic mask (source/test_like_low.cpp:99-118), committed as a golden list
@@ -157,6 +160,9 @@ def reference_sample(kind, nside, lmax, budget_s=12.0, threads=None):
     note = ""
     if kind == "tqu":
         note = "; TT block only - the reference has no TE/EE/BB pixel generator, so its cost per pixel-pair*l is a lower bound"
+    if kind == "batched":
+        note = ("; the reference has no batched mode and no TE/EE/BB pixel generator: its cost per pixel-pair*l*element is that of "
+                "generating every matrix of the batch on its own (TT block, a lower bound)")
     return {
         "value": value, "unit": UNIT, "cores": threads, "kind": "reference" if have_ref else "port",
         "sample": "%d concurrent instances of %s, each the full TT matrix of %d of the workload's pixels (%d pixel pairs in all), "
@@ -191,8 +197,19 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def batched_config(name, n_gpus):
+    _, nside, lmax, n_batch = WORKLOADS[name]
+    n = 12 * nside * nside
+    return {"workload": name, "kind": "batched tqu", "nside": nside, "lmax": lmax, "npix": n, "matrix_dim": 3 * n, "n_batch": n_batch,
+            "packed_bytes": n_batch * (3 * n * (3 * n + 1) // 2) * 8, "fwhm_deg": FWHM, "pixel_window": "1 (HEALPix window file unavailable offline)",
+            "sharding": "batch axis over %d rank(s), no collective" % n_gpus,
+            "l2": "every sub-batch of 256 matrices writes 87 GB (>> 126 MB L2) with streaming stores; nothing is re-read between steps"}
+
+
 def config_dict(name, kind, nside, lmax, npix, n_gpus, shard_mode="outbox"):
     """the WORKLOAD (identical for the GPU arm and the reference arm); how the GPU arm goes about it is the line's `path`"""
+    if kind == "batched":
+        return batched_config(name, n_gpus)
     dim = npix * (3 if kind == "tqu" else 1)
     return {
         "workload": name, "kind": kind, "nside": nside, "lmax": lmax, "npix": npix, "matrix_dim": dim,
@@ -213,6 +230,100 @@ def path_dict(kind, orbit, n_gpus):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 
+class SharedHostMatrix:
+    """One packed matrix in host memory that every rank of the box maps (POSIX shared memory): the N>1 e2e leg delivers a real
+    host-side matrix -- each rank writes its own packed columns of it.  The pages a rank's copies land in are page-locked
+    (cmg_host_register), everything else is written by that rank's host threads."""
+
+    def __init__(self, n_doubles, rank, world, dist, tag):
+        import mmap
+        self.path = "/dev/shm/cmg_bench_%s" % tag
+        self.rank, self.world, self.dist = rank, world, dist
+        nbytes = 8 * n_doubles
+        ok = 1
+        if rank == 0:
+            try:
+                fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+                os.posix_fallocate(fd, 0, nbytes)             # fails here, not with SIGBUS later, when /dev/shm is too small
+                os.close(fd)
+            except OSError as e:
+                ok = 0
+                self.error = str(e)
+        ok = self._all_min(ok)
+        self.array = None
+        self.registered = []
+        if not ok:
+            if rank == 0 and os.path.exists(self.path):
+                os.unlink(self.path)
+            return
+        fd = os.open(self.path, os.O_RDWR | os.O_CREAT, 0o600)    # exists already: rank 0 made it before the all-reduce above
+        if os.fstat(fd).st_size < nbytes:
+            os.ftruncate(fd, nbytes)
+        self.map = mmap.mmap(fd, nbytes, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        os.close(fd)
+        self.array = np.frombuffer(self.map, dtype=np.float64)
+        self._barrier()
+        if rank == 0:
+            os.unlink(self.path)                              # the mappings keep it alive; nothing is left behind on a crash
+
+    def _all_min(self, v):
+        if self.world == 1:
+            return v
+        import torch
+        t = torch.tensor([v], device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return int(t.item())
+
+    def _barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def register(self, first, count):
+        """page-lock the pages holding elements [first, first + count)"""
+        from cosmopp_b200 import capi
+        lo = (8 * first) // 4096 * 4096
+        hi = min(self.array.nbytes, (8 * (first + count) + 4095) // 4096 * 4096)
+        view = self.array[lo // 8:hi // 8]
+        capi.host_register(view)
+        self.registered.append(view)
+
+    def close(self):
+        from cosmopp_b200 import capi
+        for v in self.registered:
+            capi.host_unregister(v)
+        self.registered = []
+
+
+def spot_check(ctx, sharded, spectra, nside, n_samples, seed):
+    """Untimed checker: n_samples entries of this rank's (complete) packed columns against the CPU oracle (oracle/api.py,
+    tqu_pairs), error relative to the diagonal of the entry's block (TT for the T columns, QQ otherwise) -- the gate of the
+    parity tests (1e-11), applied to what THIS run produced on THIS rank."""
+    import torch
+    from oracle import api
+    from cosmopp_b200 import capi, partition
+    F = nside * nside
+    n = 12 * F
+    rs = np.random.RandomState(seed)
+    q0, q1 = sharded.q0, sharded.q1
+    s = rs.randint(0, 3, n_samples)
+    f = rs.randint(0, 12, n_samples)
+    q = rs.randint(q0, q1, n_samples)
+    col = s * n + f * F + q
+    row = (rs.random_sample(n_samples) * (col + 1)).astype(np.int64)
+    sizes = partition.orbit_strip_sizes(nside, q0, q1)
+    starts = np.concatenate([[0], np.cumsum([sizes[a][b] for a in range(3) for b in range(12)])])
+    first_col = s * n + f * F + q0
+    idx = starts[s * 12 + f] + (col * (col + 1) // 2 - first_col * (first_col + 1) // 2) + row
+    got = sharded.strips.tensor()[torch.from_numpy(idx).cuda()].cpu().numpy()
+    X, a = row // n, row % n
+    Y, b = col // n, col % n
+    blocks = api.tqu_pairs(*spectra, nside, FWHM, a, b)
+    want = blocks[np.arange(n_samples), X, Y]
+    diag = api.tqu_pairs(*spectra, nside, FWHM, np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int64))[0]
+    scale = np.where(Y == 0, diag[0, 0], diag[1, 1])
+    return float((np.abs(got - want) / scale).max())
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -228,6 +339,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if WORKLOADS[args.workload][0] == "batched":
+        return run_batched_arm(args, torch, dist, cb, capi, partition, synthetic_cl)
 
     kind, nside, lmax, good, npix = workload_geometry(args.workload)
     ctx = cb.Context(local)
@@ -253,6 +366,8 @@ def run_gpu_arm(args):
     my_pairs = partition.pairs_in_block(a0, a1)
     total_pairs = npix * (npix + 1) // 2
     units_total = total_pairs * (lmax - 1)
+    orbit_sharded = use_orbit and kind == "tqu"
+    spectra = None
 
     if kind == "tt":
         weights = capi.tt_weights(synthetic_cl(lmax), f)
@@ -267,7 +382,7 @@ def run_gpu_arm(args):
         spectra = synthetic_cl(lmax, pol=True)
         weights = capi.tqu_weights(*spectra, f, f)
         if use_orbit:
-            sharded = multigpu.OrbitShardedTQU(ctx, nside, rank, world, mode=0)
+            sharded = multigpu.OrbitShardedTQU(ctx, nside, rank, world, mode=0, exchange=args.exchange)
             launch = lambda: sharded.generate(weights)
             lay = None
             my_pairs = sharded.pairs                      # pixel pairs this rank EVALUATES (a quarter of those it stores)
@@ -277,13 +392,19 @@ def run_gpu_arm(args):
             lay = sharded.layout
             launch = lambda: ctx.tqu(*weights, lay)
         pieces = [b.tensor() for b in sharded.pieces()]
-    d2h_bytes = sum(p.numel() for p in pieces) * 8
+    strip_bytes = 8 * (sharded.strips.n if orbit_sharded else sum(p.numel() for p in pieces))
     h2d_bytes = (len(weights) if kind == "tt" else 4 * (lmax + 1)) * 8
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     peak_tflops = ctx.measure_fp64_peak()
 
@@ -314,10 +435,7 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.barrier()
-    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = max_over_ranks(ms_local)
     ms_per_step = ms_total / args.steps
     value = units_total / (ms_per_step * 1e-3)
 
@@ -334,9 +452,10 @@ def run_gpu_arm(args):
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(mp):
         hbm_peak = json.load(open(mp)).get("hbm_gbs")
-    written = d2h_bytes
-    if use_orbit and world > 1:
-        # the outbox blocks are allocated dense; what the kernel writes is this rank's share of the 9 entries per stored pair
+    written = sum(p.numel() for p in pieces) * 8
+    if orbit_sharded and world > 1:
+        # strips have holes where another rank's outbox holds the entry: what the kernel writes is this rank's share of the
+        # 9 entries per stored pair
         written = int(8 * 9 * total_pairs * (my_pairs / max(orbit_pairs_all, 1)))
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
@@ -349,18 +468,48 @@ def run_gpu_arm(args):
         "hbm_frac": (written / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
     }
 
-    # ---- optional: whole matrix resident on every GPU (NCCL broadcasts of the strips over NVLink)
+    # ---- N>1, orbit shards: the exchange that completes every rank's packed columns (block(r -> d) of the compact outboxes
+    # over NVLink + orbitInboxScatterKernel), timed on its own after a generation
+    exchange = None
+    if orbit_sharded and world > 1:
+        sharded.exchange()                         # warm-up: inbox allocation / IPC mapping, NCCL channels
+        times = []
+        for _ in range(min(args.steps, 5)):
+            launch()
+            barrier()
+            x0 = torch.cuda.Event(enable_timing=True)
+            x1 = torch.cuda.Event(enable_timing=True)
+            x0.record(stream)
+            sharded.exchange()
+            x1.record(stream)
+            barrier()
+            times.append(max_over_ranks(x0.elapsed_time(x1)))
+        sent = 8 * sum(sharded.send_counts)
+        recv = 8 * sum(sharded.recv_counts)
+        exchange = {"ms": float(np.median(times)), "bytes_sent_this_rank": sent, "bytes_received_this_rank": recv,
+                    "gbs_in_per_gpu": recv / (float(np.median(times)) * 1e-3) / 1e9, "mode": args.exchange,
+                    "how": ("ncclAllToAll (torch all_to_all_single, uneven splits) of the destination blocks, then orbitInboxScatterKernel per sender"
+                            if args.exchange == "nccl" else
+                            "orbitInboxScatterKernel reading every sender's outbox through CUDA-IPC mapped peer memory (NVLink loads), no staging")}
+
+    # ---- untimed checker: sampled entries of this rank's complete columns against the CPU oracle
+    parity = None
+    if orbit_sharded and args.spot_check > 0:
+        if world == 1:
+            launch()
+        torch.cuda.synchronize()
+        parity = max_over_ranks(spot_check(ctx, sharded, spectra, nside, args.spot_check, 777 + rank))
+
+    # ---- whole matrix resident on every GPU (NCCL broadcasts of the strips over NVLink): by default for N>1 where it fits
     gather = None
-    gather_ok = args.gather and kind == "tqu" and world > 1
+    gather_ok = (args.gather or (orbit_sharded and not args.no_gather)) and kind == "tqu" and world > 1
     if gather_ok:
         need = 8 * capi.packed_size(3 * npix)
-        if use_orbit:
-            need += 8 * max(sharded.sizes_of(r)[1] for r in range(world))       # scratch for a peer's outbox buffer
         ok = torch.tensor([1 if torch.cuda.mem_get_info()[0] > need + (2 << 30) else 0], device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if not int(ok.item()):
             gather_ok = False
-            gather = {"skipped": "the whole matrix plus the gather scratch do not fit next to this rank's shard (%.0f GB needed)" % (need / 1e9)}
+            gather = {"skipped": "the whole matrix does not fit next to this rank's shard (%.0f GB needed)" % (need / 1e9)}
     if gather_ok:
         full = torch.empty(capi.packed_size(3 * npix), dtype=torch.float64, device="cuda")
         sharded.gather_full(full)
@@ -371,25 +520,25 @@ def run_gpu_arm(args):
         sharded.gather_full(full)
         g1.record(stream)
         barrier()
-        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        if use_orbit:
-            own = sharded.sizes_of(rank)
-            gather = {"ms": float(gt.item()),
-                      "bytes_per_gpu_in": 8 * (capi.packed_size(3 * npix) - own[0] + sum(sharded.sizes_of(r)[1] for r in range(world) if r != rank)),
-                      "how": "ncclBroadcast of every strip straight into place; each rank's (dense) outbox buffer via a scratch buffer + "
-                             "orbitOutboxScatterKernel (cmg_tqu_orbit_assemble)"}
+        gms = max_over_ranks(g0.elapsed_time(g1))
+        inbound = 8 * capi.packed_size(3 * npix) - strip_bytes
+        if orbit_sharded:
+            gather = {"ms": gms, "bytes_per_gpu_in": inbound, "gbs_in_per_gpu": inbound / (gms * 1e-3) / 1e9, "nvlink_gbs_per_direction": 900.0,
+                      "how": "after the exchange every strip is a complete contiguous piece of the packed triangle: one ncclBroadcast each, straight into place"}
         else:
-            gather = {"ms": float(gt.item()), "bytes_per_gpu_in": 8 * (capi.packed_size(3 * npix) - sum(sharded.plan["strips"])),
+            gather = {"ms": gms, "bytes_per_gpu_in": 8 * (capi.packed_size(3 * npix) - sum(sharded.plan["strips"])),
                       "how": "ncclBroadcast of every strip straight into place; outbox blocks via a scratch buffer + cmg_tqu_scatter_block"}
         del full
         torch.cuda.empty_cache()
 
-    # ---- e2e: host C_l in, host packed shard out, copies inside the timed region
+    # ---- e2e: host C_l in, packed matrix in HOST memory out, copies inside the timed region
     e2e = None
-    if args.host_expand > 0 and use_orbit and world == 1:
-        ctx.set_host_expand(args.host_expand)
+    if world == 1:
+        ctx.set_host_expand(args.host_expand)          # -1 = the library's default (automatic), 0 = one plain copy
     if not args.no_e2e:
+        shared = None
+        d2h_bytes = strip_bytes
+        note = "C_l from pinned host memory, the packed matrix back to pinned host memory through the reference-facing whole call"
         if kind == "tqu" and world == 1:
             del pieces, lay
             launch = None
@@ -398,27 +547,49 @@ def run_gpu_arm(args):
             host = torch.empty(capi.packed_size(3 * npix), dtype=torch.float64, pin_memory=True)
             spectra_pinned = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in spectra]
             step = lambda: ctx.cl_to_cmatrix_pol(*[s.numpy() for s in spectra_pinned], FWHM, host)      # reference-facing whole call
+            if good is None and args.host_expand != 0 and host.numel() * 8 >= (1 << 30):
+                d2h_bytes = 8 * sum(partition.packed_size(s * npix + (fc + 1) * nside * nside) - partition.packed_size(s * npix + fc * nside * nside)
+                                    for s in range(3) for fc in (3, 7, 11))
+                note += "; only the columns of base faces 3, 7, 11 cross PCIe, host threads fill in the rotated images (cmg_set_host_expand)"
         elif kind == "tt" and world == 1:
             del shard, pieces
             torch.cuda.empty_cache()
             host = torch.empty(capi.packed_size(npix), dtype=torch.float64, pin_memory=True)
             cl_pinned = torch.from_numpy(synthetic_cl(lmax)).pin_memory()
             step = lambda: ctx.cl_to_cmatrix(cl_pinned.numpy(), FWHM, host)
-        elif use_orbit:
-            # orbit shards (strips + dense outbox blocks, tens of GB per rank) stream to the host through a small pinned ring, the
-            # way a consumer such as the CMatrix file writer (cmg_cmatrix_file_write_device) takes them: every byte the rank
-            # holds crosses PCIe inside the timed region, but host memory stays bounded for any number of ranks on the box
-            ring = [torch.empty(1 << 27, dtype=torch.float64, pin_memory=True) for _ in range(2)]      # 2 x 1 GiB
+            if good is None and args.host_expand != 0 and host.numel() * 8 >= (1 << 30):
+                d2h_bytes = 8 * sum(partition.packed_size((fc + 1) * nside * nside) - partition.packed_size(fc * nside * nside) for fc in (3, 7, 11))
+        elif orbit_sharded:
+            # every rank writes its own packed columns of ONE host matrix in shared memory: generation, exchange, the columns of
+            # base faces 3, 7, 11 over PCIe, the rotated images filled in by this rank's share of the host cores
+            threads = args.host_expand if args.host_expand >= 0 else max(1, (os.cpu_count() or 1) // world)
+            shared = SharedHostMatrix(capi.packed_size(3 * npix), rank, world, dist, "%d" % os.getppid())
+            if shared.array is None:
+                note = "no shared host matrix (/dev/shm too small): each rank copies its strips into private pinned memory"
+                host_priv = torch.empty(sharded.strips.n, dtype=torch.float64, pin_memory=True)
 
-            def step():
-                launch()
-                k = 0
-                for p in pieces:
-                    for off in range(0, p.numel(), ring[0].numel()):
-                        n = min(ring[0].numel(), p.numel() - off)
-                        ring[k & 1][:n].copy_(p[off:off + n], non_blocking=True)
-                        k += 1
-                torch.cuda.synchronize()
+                def step():
+                    launch()
+                    sharded.exchange()
+                    host_priv.copy_(sharded.strips.tensor(), non_blocking=True)
+                    torch.cuda.synchronize()
+            else:
+                F = nside * nside
+                faces = (3, 7, 11) if threads > 0 else range(12)
+                for s in range(3):
+                    for fc in faces:
+                        first = partition.packed_size(s * npix + fc * F + sharded.q0)
+                        shared.register(first, partition.packed_size(s * npix + fc * F + sharded.q1) - first)
+                d2h_bytes = 8 * sum(partition.packed_size(s * npix + fc * F + sharded.q1) - partition.packed_size(s * npix + fc * F + sharded.q0)
+                                    for s in range(3) for fc in faces)
+                note = ("every rank: generation + exchange, then its own packed columns of ONE host matrix in shared memory (%s): "
+                        % ("columns of base faces 3, 7, 11 over PCIe, rotated images filled in by %d host threads per rank" % threads
+                           if threads > 0 else "all 36 runs of packed columns copied"))
+
+                def step():
+                    launch()
+                    sharded.exchange()
+                    sharded.to_host(shared.array, threads)
         else:
             hosts = [torch.empty(p.numel(), dtype=torch.float64, pin_memory=True) for p in pieces]
 
@@ -429,19 +600,31 @@ def run_gpu_arm(args):
                 torch.cuda.synchronize()
         step()
         barrier()
-        e2e_steps = min(args.steps, 10)          # each step moves the whole shard over PCIe (87 GB at N=1): keep the run bounded
+        e2e_steps = min(args.steps, 10)          # each step moves the matrix into host memory (87 GB at Nside = 64): keep the run bounded
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             step()
         barrier()
-        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-        e2e = {"value": units_total * e2e_steps / float(wall.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * float(wall.item()) / e2e_steps, "steps": e2e_steps,
-               "host_expand_threads": args.host_expand if (use_orbit and world == 1) else 0,
-               "note": "per rank: C_l from pinned host memory, this rank's shard of the packed matrix back to pinned host memory"
-                       + (" (strips + outbox blocks, through a 2 x 1 GiB pinned ring)" if (use_orbit and world > 1) else "")}
+        wall = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": units_total * e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * wall / e2e_steps, "steps": e2e_steps,
+               "pcie_gbs_per_gpu": d2h_bytes / (wall / e2e_steps) / 1e9,
+               "host_expand_threads": ((args.host_expand if args.host_expand >= 0 else "auto") if good is None else 0), "note": "per rank: " + note}
+        if shared is not None and shared.array is not None:
+            # the delivered host matrix against this rank's device strips (sampled), and rank 0 reads columns other ranks wrote
+            rs = np.random.RandomState(99 + rank)
+            F = nside * nside
+            s_, f_, q_ = rs.randint(0, 3, 2000), rs.randint(0, 12, 2000), rs.randint(sharded.q0, sharded.q1, 2000)
+            col = s_ * npix + f_ * F + q_
+            row = (rs.random_sample(2000) * (col + 1)).astype(np.int64)
+            sizes = partition.orbit_strip_sizes(nside, sharded.q0, sharded.q1)
+            starts = np.concatenate([[0], np.cumsum([sizes[a][b] for a in range(3) for b in range(12)])])
+            fcol = s_ * npix + f_ * F + sharded.q0
+            idx = starts[s_ * 12 + f_] + (col * (col + 1) // 2 - fcol * (fcol + 1) // 2) + row
+            dev = sharded.strips.tensor()[torch.from_numpy(idx).cuda()].cpu().numpy()
+            same = float(np.abs(shared.array[col * (col + 1) // 2 + row] - dev).max())
+            e2e["host_matrix_max_abs_diff_vs_device"] = max_over_ranks(same)
+            shared.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -454,9 +637,127 @@ def run_gpu_arm(args):
             "ms_per_step": ms_per_step, "ms_per_matrix": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world, args.shard_mode),
             "path": path_dict(kind, use_orbit, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "fp64_frac_of_peak": achieved / peak_tflops, "gather": gather,
+            "fp64_frac_of_peak": achieved / peak_tflops, "exchange": exchange, "gather": gather, "parity_max_err": parity,
+            "parity_note": ("max over ranks of |entry - oracle| / diagonal of the block over %d sampled entries of each rank's packed columns "
+                            "(oracle/api.py tqu_pairs, untimed; gate 1e-11)" % args.spot_check) if parity is not None else None,
         }
         print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_batched_arm(args, torch, dist, cb, capi, partition, synthetic_cl):
+    """BASELINE configs[3]: one MCMC step = B synthetic C_l sets -> B polarized Nside=16, lmax=47 matrices (348 GB of output for
+    B = 1024: produced in sub-batches of 256 per GPU into one slab buffer, as a consumer working through the proposals would).
+    Batch axis sharded over the ranks, no collective.  FP64 tensor path (DMMA) over a basis shared by the batch: 8 FLOP per
+    pixel-pair*l*element; the kernel sits on the ridge, so both bounds are reported."""
+    rank, world, local = dist_info()
+    _, nside, lmax, n_batch = WORKLOADS[args.workload]
+    SUB = 256
+    ctx = cb.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_pixels(nside)
+    n = ctx.npix
+    pairs = n * (n + 1) // 2
+    f = capi.window_beam(lmax, FWHM)
+    bounds = partition.batch_partition(n_batch, world)
+    b0, b1 = bounds[rank], bounds[rank + 1]
+    a = np.stack([np.stack(capi.tqu_weights(*synthetic_cl(lmax, seed=12345 + b, pol=True), f, f)) for b in range(b0, b1)]) if b1 > b0 else None
+    slabs = torch.empty(((min(SUB, max(b1 - b0, 1)) + 15) // 16) * capi.slab_doubles(3 * n), dtype=torch.float64, device="cuda")
+    peak = ctx.measure_fp64_peak()
+
+    def step():
+        for s in range(0, b1 - b0, SUB):
+            ctx.tqu_batched_slab(a[s:s + SUB], slabs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ctx.launches
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_local = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms_local)
+    units = n_batch * pairs * (lmax - 1)
+    per_gpu_units = (b1 - b0) * pairs * (lmax - 1)
+    out_bytes = (b1 - b0) * capi.packed_size(3 * n) * 8
+    hbm_peak = None
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        hbm_peak = json.load(open(mp)).get("hbm_gbs")
+    achieved = 8.0 * per_gpu_units / (ms_local * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_flop_per_unit": 8.0,
+                "note": "ridge point: 368 FLOP per 72 B written; FP64 (DMMA at the DFMA rate) and HBM write bound at once",
+                "hbm_write_gbs": out_bytes / (ms_local * 1e-3) / 1e9, "hbm_peak_gbs_measured": hbm_peak,
+                "hbm_frac": (out_bytes / (ms_local * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                "peak_source": "cmg_measure_fp64_peak on this GPU in this run; HBM: MEASURED_PEAKS.json copy bandwidth"}
+
+    # e2e: the C_l weights of the whole step from pinned host memory in, one number per matrix back (the sum of its diagonal, what
+    # a consumer on the device would hand on): nobody copies 348 GB of proposals' matrices to the host per MCMC step
+    e2e = None
+    if not args.no_e2e and b1 > b0:
+        a_pinned = torch.from_numpy(a).pin_memory()
+        diag_idx = torch.from_numpy(np.array([capi.packed_index(i, i) for i in range(3 * n)], dtype=np.int64)).cuda()
+        sums_host = torch.empty(b1 - b0, dtype=torch.float64, pin_memory=True)
+        slab_d = capi.slab_doubles(3 * n)
+
+        def step_e2e():
+            for s in range(0, b1 - b0, SUB):
+                nb = min(SUB, b1 - b0 - s)
+                ctx.tqu_batched_slab(a_pinned[s:s + nb].numpy(), slabs)
+                view = slabs[:((nb + 15) // 16) * slab_d].view(-1, slab_d // 16, 16)          # [slab][entry][element]
+                tr = view[:, diag_idx, :].sum(dim=1).reshape(-1)[:nb]
+                sums_host[s:s + nb].copy_(tr, non_blocking=True)
+            torch.cuda.synchronize()
+        step_e2e()
+        barrier()
+        k = min(args.steps, 5)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            step_e2e()
+        barrier()
+        wall = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": units * k / wall, "unit": UNIT.replace("l/s", "l*element/s"), "h2d_bytes_per_step": int(a.nbytes), "d2h_bytes_per_step": 8 * (b1 - b0),
+               "ms_per_step": 1e3 * wall / k, "steps": k,
+               "note": "per rank: its share of the step's C_l weights from pinned host memory, every matrix generated on the device, the trace of "
+                       "each matrix back to pinned host memory (the matrices are consumed on the device)"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = reference_sample("batched", nside, lmax, budget_s=12.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "pixel_pair_ell_per_s", "value": units / (ms * 1e-3), "unit": UNIT.replace("l/s", "l*element/s"), "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "ms_per_matrix": ms / n_batch, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": batched_config(args.workload, world),
+            "path": {"method": "cmg_tqu_batched_slab: recurrences once per pixel pair, the l-sum over the batch as FP64 tensor-core (DMMA) "
+                               "contractions, slab output (16 batch elements interleaved entry by entry)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "fp64_frac_of_peak": achieved / peak}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -471,11 +772,18 @@ def main():
     ap.add_argument("--shard-mode", default="outbox", choices=["outbox", "peer"],
                     help="N>1, T,Q,U: keep entries owned by another rank in local blocks (outbox) or write them into the owner's strip "
                          "through CUDA-IPC peer memory over NVLink (peer)")
-    ap.add_argument("--gather", action="store_true", help="N>1, T,Q,U: also time the NCCL gather of the whole matrix onto every GPU")
+    ap.add_argument("--gather", action="store_true", help="N>1, T,Q,U, every-pair shards: also time the NCCL gather of the whole matrix onto every GPU "
+                                                          "(orbit shards: on by default where the matrix fits)")
+    ap.add_argument("--no-gather", action="store_true", help="N>1, orbit shards: skip the gather of the whole matrix onto every GPU")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "pull"],
+                    help="N>1, orbit shards: how block(r -> d) of the outboxes reaches rank d -- one NCCL all-to-all + a local scatter kernel, "
+                         "or the scatter kernel reading the sender's outbox through CUDA-IPC peer memory")
+    ap.add_argument("--spot-check", type=int, default=10000, metavar="N",
+                    help="full-sky T,Q,U: entries per rank compared with the CPU oracle after the run (untimed checker; 0 = off)")
     ap.add_argument("--no-orbit", action="store_true", help="full-sky T,Q,U: evaluate every pixel pair (cmg_tqu) instead of one per symmetry orbit")
-    ap.add_argument("--host-expand", type=int, default=0, metavar="THREADS",
+    ap.add_argument("--host-expand", type=int, default=-1, metavar="THREADS",
                     help="N=1, full sky, e2e leg: copy back only the last-face columns (27 %% of the matrix) and fill in the rotated images "
-                         "on THREADS host threads (cmg_set_host_expand; opt-in until it has been timed on the GPU box)")
+                         "on THREADS host threads (cmg_set_host_expand); -1 = the library's default (automatic), 0 = one plain copy of the whole matrix")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

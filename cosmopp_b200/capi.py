@@ -36,10 +36,11 @@ class TquLayout(ctypes.Structure):
 class OrbitShard(ctypes.Structure):
     """cmg_orbit_shard: a rank's pieces of a [T;Q;U] matrix generated over symmetry orbits (include/cmg.h)."""
     _fields_ = [
-        ("q_begin", _i64),
-        ("q_end", _i64),
+        ("n_ranks", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("bounds", _i64 * (MAX_PARTS + 1)),
         ("strip", (_vp * 12) * 3),
-        ("outbox", (_vp * 12) * 6),
+        ("outbox", _vp),
     ]
 
 
@@ -101,6 +102,11 @@ _SIGNATURES = {
     "cmg_tqu_orbit_sharded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(OrbitShard), ctypes.c_int]),
     "cmg_tqu_orbit_assemble": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), ctypes.c_int, ctypes.c_int, _vp]),
     "cmg_legendre_series_orbit": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "cmg_orbit_outbox_layout": (ctypes.c_int, [_i64, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp]),
+    "cmg_tqu_orbit_scatter_inbox": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), ctypes.c_int, ctypes.c_int, _vp]),
+    "cmg_orbit_strips_to_host": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), _vp, ctypes.c_int]),
+    "cmg_host_register": (ctypes.c_int, [_vp, _i64]),
+    "cmg_host_unregister": (ctypes.c_int, [_vp]),
     "cmg_host_expand_rotations": (ctypes.c_int, [_vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "cmg_set_host_expand": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_tqu_orbit_plan": (ctypes.c_int, [_i64, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int32)]),
@@ -176,7 +182,7 @@ def host_expand_rotations(packed, nside, strips, threads=1, faces=(0, 12)):
 
 def orbit_plan(nside, mode=0):
     """Classes of base-face pairs of cmg_tqu_orbit: list of dicts (host only)."""
-    out = np.zeros((24, 17), dtype=np.int32)
+    out = np.zeros((24, 21), dtype=np.int32)
     n = ctypes.c_int32()
     st = library().cmg_tqu_orbit_plan(int(nside), int(mode), _p(out), ctypes.byref(n))
     if st:
@@ -184,8 +190,30 @@ def orbit_plan(nside, mode=0):
     plan = []
     for row in out[:n.value]:
         imgs = [(int(row[5 + 3 * k]), int(row[6 + 3 * k]), bool(row[7 + 3 * k])) for k in range(int(row[4]))]
-        plan.append(dict(row_face=int(row[0]), col_face=int(row[1]), tri=bool(row[2]), same_face=bool(row[3]), images=imgs))
+        plan.append(dict(row_face=int(row[0]), col_face=int(row[1]), tri=bool(row[2]), same_face=bool(row[3]), images=imgs,
+                         combo_base=[int(row[17 + k]) for k in range(int(row[4]))]))
     return plan
+
+
+def orbit_outbox_layout(nside, mode, bounds, rank):
+    """cmg_orbit_outbox_layout: offsets (doubles) of the block for every destination rank inside `rank`'s outbox; [-1] = total"""
+    b = np.ascontiguousarray(bounds, dtype=np.int64)
+    off = np.zeros(len(b), dtype=np.int64)
+    st = library().cmg_orbit_outbox_layout(int(nside), int(mode), len(b) - 1, _p(b), int(rank), _p(off))
+    if st:
+        raise CmgError(st, "cmg_orbit_outbox_layout: bad arguments")
+    return [int(x) for x in off]
+
+
+def host_register(array):
+    """cudaHostRegister of a numpy array's memory (e.g. a shared mapping), for PCIe-speed copies into it"""
+    st = library().cmg_host_register(_p(array), int(array.nbytes))
+    if st:
+        raise CmgError(st, "cmg_host_register: %s" % library().cmg_last_error(None).decode())
+
+
+def host_unregister(array):
+    library().cmg_host_unregister(_p(array))
 
 
 SLAB = 16            # CMG_SLAB: batch elements interleaved in one slab of the DMMA batched path
@@ -206,6 +234,7 @@ class Context:
             raise CmgError(st, self._L.cmg_last_error(None).decode())
         self._h = h
         self.device = int(device)
+        self.stream_handle = None          # None = the context's private stream
         if stream is not None:
             self.set_stream(stream)
 
@@ -230,8 +259,10 @@ class Context:
         default stream); None returns to the context's private stream."""
         if cuda_stream is None:
             self._check(self._L.cmg_use_own_stream(self._h))
+            self.stream_handle = None
         else:
             self._check(self._L.cmg_set_stream(self._h, _vp(int(cuda_stream))))
+            self.stream_handle = int(cuda_stream)
 
     def synchronize(self):
         self._check(self._L.cmg_synchronize(self._h))
@@ -327,11 +358,18 @@ class Context:
     def cl_to_cmatrix(self, cl, fwhm, out_host, pixwin=None):
         cl = _f64(cl)
         pixwin = _f64(pixwin)
+        _need(len(cl) >= 3, "cl must reach l = 2")
+        _need(pixwin is None or len(pixwin) >= len(cl), "pixel window shorter than cl")
+        _need(_numel(out_host) >= packed_size(self.npix), "output buffer smaller than npix (npix + 1) / 2")
         self._check(self._L.cmg_cl_to_cmatrix(self._h, _p(cl), len(cl) - 1, float(fwhm), _p(pixwin), _p(out_host)))
 
     def fiducial_matrix(self, cl, lmax, fwhm, out_host, pixwin=None):
         cl = _f64(cl)
         pixwin = _f64(pixwin)
+        n_need = 4 * self.nside + 1                   # reference check: cl.size() >= 4 nSide + 1 (source/c_matrix_generator.cpp:709)
+        _need(len(cl) >= n_need, "cl must hold 4 nside + 1 entries for the fiducial matrix")
+        _need(pixwin is None or len(pixwin) >= n_need, "pixel window shorter than 4 nside + 1")
+        _need(_numel(out_host) >= packed_size(self.npix), "output buffer smaller than npix (npix + 1) / 2")
         self._check(self._L.cmg_fiducial_matrix(self._h, _p(cl), int(lmax), float(fwhm), _p(pixwin), _p(out_host)))
 
     def mask_matrix(self, d_in, npix_in, good, d_out):
@@ -364,6 +402,14 @@ class Context:
     def tqu_orbit_assemble(self, shard, d_full, mode=0, parts=3):
         """parts: 1 = strips, 2 = outbox blocks; place the strips of all ranks before any outbox (include/cmg.h)"""
         self._check(self._L.cmg_tqu_orbit_assemble(self._h, ctypes.byref(shard), int(mode), int(parts), _p(d_full)))
+
+    def tqu_orbit_scatter_inbox(self, shard, sender, d_block, mode=0):
+        """block(sender -> this rank) (local or IPC-mapped peer memory) into this rank's strips (include/cmg.h)"""
+        self._check(self._L.cmg_tqu_orbit_scatter_inbox(self._h, ctypes.byref(shard), int(mode), int(sender), _p(d_block)))
+
+    def orbit_strips_to_host(self, shard, host_packed, threads=0):
+        """this rank's complete strips as its columns of one whole packed host matrix (include/cmg.h)"""
+        self._check(self._L.cmg_orbit_strips_to_host(self._h, ctypes.byref(shard), _p(host_packed), int(threads)))
 
     def tqu_scatter_block(self, d_block, col0, n_cols, ld, row0, kind, d_full):
         self._check(self._L.cmg_tqu_scatter_block(self._h, _p(d_block), col0, n_cols, ld, row0, kind, _p(d_full)))
@@ -417,6 +463,9 @@ class Context:
         ctt, cte, cee, cbb = map(_f64, (ctt, cte, cee, cbb))
         pixwinT = _f64(pixwinT)
         pixwinP = _f64(pixwinP)
+        _need(len(ctt) >= 3 and len(cte) == len(ctt) and len(cee) == len(ctt) and len(cbb) == len(ctt), "tt, te, ee, bb must have one length (lmax + 1 >= 3)")
+        _need(all(w is None or len(w) >= len(ctt) for w in (pixwinT, pixwinP)), "pixel window shorter than the spectra")
+        _need(_numel(out_host) >= packed_size(3 * self.npix), "output buffer smaller than 3 npix (3 npix + 1) / 2")
         self._check(self._L.cmg_cl_to_cmatrix_pol(self._h, _p(ctt), _p(cte), _p(cee), _p(cbb), len(ctt) - 1, float(fwhm),
                                                   _p(pixwinT), _p(pixwinP), _p(out_host)))
 
@@ -448,9 +497,21 @@ def make_tqu_layout(bounds, rank, strip_ptrs, outbox_ptrs):
 
 # ---- pure-host helpers of the ABI (no GPU needed)
 
+def _need(ok, text):
+    if not ok:
+        raise CmgError(1, text)
+
+
+def _numel(buf):
+    if hasattr(buf, "numel"):
+        return int(buf.numel())
+    return int(np.asarray(buf).size) if not isinstance(buf, (int, ctypes.c_void_p)) else 1 << 62
+
+
 def window_beam(lmax, fwhm, pixwin=None):
     f = np.empty(lmax + 1)
     pixwin = _f64(pixwin)
+    _need(pixwin is None or len(pixwin) >= lmax + 1, "pixel window shorter than lmax + 1")
     st = library().cmg_window_beam(_p(f), lmax, float(fwhm), _p(pixwin))
     if st:
         raise CmgError(st, "cmg_window_beam")
@@ -460,6 +521,7 @@ def window_beam(lmax, fwhm, pixwin=None):
 def tt_weights(cl, f):
     cl = _f64(cl)
     f = _f64(f)
+    _need(len(f) >= len(cl), "window*beam factors shorter than cl")
     a = np.empty(len(cl))
     st = library().cmg_tt_weights(_p(cl), _p(f), len(cl) - 1, _p(a))
     if st:
@@ -470,6 +532,7 @@ def tt_weights(cl, f):
 def fiducial_weights(cl, f, nside, lmax):
     cl = _f64(cl)
     f = _f64(f)
+    _need(len(cl) >= 4 * nside + 1 and len(f) >= 4 * nside + 1, "cl and f must hold 4 nside + 1 entries")
     a = np.empty(4 * nside + 1)
     st = library().cmg_fiducial_weights(_p(cl), _p(f), nside, lmax, _p(a))
     if st:
@@ -480,6 +543,7 @@ def fiducial_weights(cl, f, nside, lmax):
 def tqu_weights(ctt, cte, cee, cbb, fT, fP):
     ctt, cte, cee, cbb, fT, fP = map(_f64, (ctt, cte, cee, cbb, fT, fP))
     n = len(ctt)
+    _need(all(len(x) == n for x in (cte, cee, cbb)) and len(fT) >= n and len(fP) >= n, "spectra of one length, factors at least as long")
     out = [np.empty(n) for _ in range(4)]
     st = library().cmg_tqu_weights(_p(ctt), _p(cte), _p(cee), _p(cbb), _p(fT), _p(fP), n - 1, *[_p(o) for o in out])
     if st:

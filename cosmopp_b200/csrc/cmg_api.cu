@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
@@ -18,6 +19,7 @@
 
 #include "../../include/cmg.h"
 #include "healpix_nest.hpp"
+#include "host_expand.hpp"
 #include "kernels.cuh"
 #include "orbit.cuh"
 #include "series.hpp"
@@ -50,7 +52,8 @@ struct cmg_ctx
 
     cmg::SeriesTable hostT0, hostT20, hostT22;   // host copies of the recurrence tables
     int tquVariant = 0;                          // 0 = automatic choice (see launchTqu)
-    int hostExpandThreads = 0;                   // > 0: full-sky whole calls copy back a quarter and expand on the host
+    int hostExpandThreads = -1;                  // full-sky whole calls copy back 27 % and expand on the host: > 0 threads, 0 = plain copy,
+                                                 // -1 = automatic (all host cores for matrices of 1 GiB and more; measured 1.27x at 87 GB)
 
     static const int kAux = 4;                   // side streams for many small independent launches (batched mode)
     cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
@@ -807,30 +810,53 @@ cmg_status cmg_legendre_series_batched(cmg_ctx* ctx, const double* a, int lmax, 
 }
 
 // Full sky, host output, cmg_set_host_expand: only the columns of the last face of every ring cross PCIe (contiguous pieces of
-// the packed triangle in ctx->dScratch, smallest first); the host fills in the rotated images of a piece as soon as it has
-// arrived, while the next pieces are in flight (host_expand.cpp).
-static cmg_status copyBackLastFacesAndExpand(cmg_ctx* ctx, int strips, double* outPacked)
+// the packed triangle in ctx->dScratch, in chunks of ~64 MB, smallest columns first); worker threads fill in the rotated
+// images of a chunk as soon as it has arrived, while the chunks behind it are in flight (host_expand.cpp).
+static int hostExpandThreadsFor(const cmg_ctx* ctx, int64_t bytes)
+{
+    if(!ctx->fullSky || ctx->hostExpandThreads == 0) return 0;
+    if(ctx->hostExpandThreads > 0) return ctx->hostExpandThreads;
+    if(bytes < (int64_t(1) << 30)) return 0;             // a small matrix crosses PCIe faster than a thread pool starts
+    return static_cast<int>(std::max(1u, std::min(32u, std::thread::hardware_concurrency())));
+}
+
+static cmg_status copyBackLastFacesAndExpand(cmg_ctx* ctx, int strips, double* outPacked, int threads)
 {
     const int64_t n = ctx->npix, facePix = ctx->nside * ctx->nside;
-    const int pieces = 3 * strips;
-    cudaEvent_t arrived[9];
-    for(int k = 0; k < pieces; ++k)
-    {
-        const int strip = k / 3, face = 4 * (k % 3) + 3;
-        const int64_t first = cmg_packed_size(strip * n + face * facePix), last = cmg_packed_size(strip * n + (face + 1) * facePix);
-        CMG_CUDA(ctx, cudaMemcpyAsync(outPacked + first, ctx->dScratch + first, sizeof(double) * (last - first), cudaMemcpyDeviceToHost, ctx->stream));
-        CMG_CUDA(ctx, cudaEventCreateWithFlags(&arrived[k], cudaEventDisableTiming));
-        CMG_CUDA(ctx, cudaEventRecord(arrived[k], ctx->stream));
-    }
+    struct Chunk { int strip, ring; int64_t q0, q1; cudaEvent_t arrived; };
+    std::vector<Chunk> chunks;
+    for(int strip = 0; strip < strips; ++strip)
+        for(int ring = 0; ring < 3; ++ring)
+        {
+            const int64_t col0 = strip * n + (4 * ring + 3) * facePix;
+            const int64_t step = std::max<int64_t>(8, std::min<int64_t>(facePix, (int64_t(8) << 20) / (col0 + facePix)));   // ~64 MB
+            for(int64_t q = 0; q < facePix; q += step)
+                chunks.push_back({strip, ring, q, std::min(facePix, q + step), nullptr});
+        }
     cmg_status st = CMG_OK;
-    for(int k = 0; k < pieces; ++k)
+    size_t issued = 0;
+    for(; issued < chunks.size() && st == CMG_OK; ++issued)
     {
-        const cudaError_t e = cudaEventSynchronize(arrived[k]);
-        cudaEventDestroy(arrived[k]);
+        Chunk& c = chunks[issued];
+        const int64_t col0 = c.strip * n + (4 * c.ring + 3) * facePix;
+        const int64_t first = cmg_packed_size(col0 + c.q0), last = cmg_packed_size(col0 + c.q1);
+        cudaError_t e = cudaMemcpyAsync(outPacked + first, ctx->dScratch + first, sizeof(double) * (last - first), cudaMemcpyDeviceToHost, ctx->stream);
+        if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c.arrived, cudaEventDisableTiming);
+        if(e == cudaSuccess) e = cudaEventRecord(c.arrived, ctx->stream);
+        if(e != cudaSuccess) st = cudaFail(ctx, e, "cudaMemcpyAsync (host expansion)");
+    }
+    cmg::ExpandPipeline* pipe = cmg::expandBegin(outPacked, ctx->nside, threads);
+    for(size_t k = 0; k < issued; ++k)
+    {
+        Chunk& c = chunks[k];
+        if(!c.arrived) continue;
+        const cudaError_t e = cudaEventSynchronize(c.arrived);
+        cudaEventDestroy(c.arrived);
         if(e != cudaSuccess && st == CMG_OK) st = cudaFail(ctx, e, "cudaEventSynchronize");
         if(st == CMG_OK)
-            st = cmg_host_expand_rotations(outPacked, ctx->nside, k / 3, k / 3 + 1, 4 * (k % 3), 4 * (k % 3) + 4, ctx->hostExpandThreads);
+            cmg::expandPublish(pipe, c.strip, c.ring, c.q0, c.q1);
     }
+    cmg::expandFinish(pipe);
     return st;
 }
 
@@ -843,8 +869,8 @@ static cmg_status wholeCallTT(cmg_ctx* ctx, const std::vector<double>& a, int lm
     const bool orbit = ctx->fullSky && ctx->nside >= 16 && lmax + 1 <= cmg::TT_STATIC_STEPS && ctx->tquVariant == 0;
     if((s = orbit ? cmg_legendre_series_orbit(ctx, a.data(), lmax, ctx->dScratch)
                   : cmg_legendre_series(ctx, a.data(), lmax, 0, ctx->npix, ctx->dScratch)) != CMG_OK) return s;
-    if(ctx->fullSky && ctx->hostExpandThreads > 0)
-        return copyBackLastFacesAndExpand(ctx, 1, outPacked);
+    if(const int threads = hostExpandThreadsFor(ctx, bytes))
+        return copyBackLastFacesAndExpand(ctx, 1, outPacked, threads);
     CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CMG_OK;
@@ -857,8 +883,9 @@ cmg_status cmg_cl_to_cmatrix(cmg_ctx* ctx, const double* cl, int lmax, double fw
     if(!cl || !outPacked) return fail(ctx, CMG_EINVAL, "null argument");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<double> f(lmax + 1), a(lmax + 1);
-    cmg_window_beam(f.data(), lmax, fwhm, pixwin);
-    cmg_tt_weights(cl, f.data(), lmax, a.data());
+    // the reference has check(fwhm >= 0) (source/utils.cpp:56); a negative beam must not come back as an all-zero matrix
+    if(cmg_window_beam(f.data(), lmax, fwhm, pixwin) != CMG_OK) return fail(ctx, CMG_EINVAL, "fwhm must be >= 0 (degrees)");
+    if((s = cmg_tt_weights(cl, f.data(), lmax, a.data())) != CMG_OK) return fail(ctx, s, "bad C_l / window arguments");
     return wholeCallTT(ctx, a, lmax, outPacked);
 }
 
@@ -871,8 +898,9 @@ cmg_status cmg_fiducial_matrix(cmg_ctx* ctx, const double* cl, int lmax, double 
     if(!cl || !outPacked) return fail(ctx, CMG_EINVAL, "null argument");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<double> f(lMaxMax + 1), a(lMaxMax + 1);
-    cmg_window_beam(f.data(), lMaxMax, fwhm, pixwin);
-    cmg_fiducial_weights(cl, f.data(), ctx->nside, lmax, a.data());
+    if(lmax < 2 || lmax > lMaxMax) return fail(ctx, CMG_EINVAL, "fiducial matrix: 2 <= lmax <= 4 nside");
+    if(cmg_window_beam(f.data(), lMaxMax, fwhm, pixwin) != CMG_OK) return fail(ctx, CMG_EINVAL, "fwhm must be >= 0 (degrees)");
+    if((s = cmg_fiducial_weights(cl, f.data(), ctx->nside, lmax, a.data())) != CMG_OK) return fail(ctx, s, "bad C_l / window arguments");
     return wholeCallTT(ctx, a, lMaxMax, outPacked);
 }
 
@@ -968,6 +996,7 @@ cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* nC
             o[5 + 3 * k] = oc.imgRowFace[k];
             o[6 + 3 * k] = oc.imgColFace[k];
             o[7 + 3 * k] = oc.imgSwap[k];
+            o[17 + k] = oc.comboBase[k];
         }
     }
     return CMG_OK;
@@ -976,42 +1005,71 @@ cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* nC
 namespace
 {
 
+// offsets of the destination blocks inside rank `rank`'s outbox (orbit.cuh, OrbitShardDev); off[nRanks] = total doubles
+void orbitOutboxOffsets(const cmg::OrbitPlan& plan, int nRanks, const int64_t* bounds, int rank, int64_t* off)
+{
+    const int64_t nct = (bounds[rank + 1] - bounds[rank]) / cmg::PQ_TJ;
+    int64_t at = 0;
+    for(int d = 0; d < nRanks; ++d)
+    {
+        off[d] = at;
+        if(d == rank)
+            continue;
+        const int64_t nh = (bounds[d + 1] - bounds[d]) / cmg::ORB_SUB;
+        const int64_t combos = plan.nComboA + (d < rank ? plan.nComboB : 0);
+        at += combos * nct * nh * (cmg::ORB_SUB * cmg::ORB_SUB);
+    }
+    off[nRanks] = at;
+}
+
+cmg_status orbitCheckBounds(cmg_ctx* ctx, int64_t nside, int nRanks, const int64_t* bounds, int rank)
+{
+    const int64_t facePix = nside * nside;
+    if(nRanks < 1 || nRanks > cmg::ORB_MAX_RANKS || rank < 0 || rank >= nRanks || !bounds)
+        return fail(ctx, CMG_EINVAL, "shard: 1 <= n_ranks <= 16 and 0 <= rank < n_ranks");
+    if(bounds[0] != 0 || bounds[nRanks] != facePix)
+        return fail(ctx, CMG_EINVAL, "shard: bounds must run from 0 to nside^2");
+    for(int r = 0; r < nRanks; ++r)
+        if(bounds[r] > bounds[r + 1] || bounds[r] % cmg::PQ_TJ)
+            return fail(ctx, CMG_EINVAL, "shard: bounds must be ascending multiples of 32");
+    return CMG_OK;
+}
+
 // checks a shard descriptor and turns it into the kernels' form (strip bases adjusted by the packed offset of their first column)
 cmg_status orbitShardDev(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, cmg::OrbitShardDev& sh)
 {
     if(!shard) return fail(ctx, CMG_EINVAL, "null shard");
-    if(mode < 0 || mode > 2) return fail(ctx, CMG_EINVAL, "orbit mode must be 0 (transposed images), 1 (none) or 2 (0 with the row-pointer table)");
+    if(mode < 0 || mode > 2) return fail(ctx, CMG_EINVAL, "orbit mode must be 0 (transposed images), 1 (none) or 2 (0 without the row-pointer table)");
     if(mode == 2) mode = 0;                          // same classes, same storage
     if(!ctx->fullSky)
         return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs the full sky in NESTED order (cmg_set_pixels with good_nest = NULL)");
     if(ctx->nside < 8)
         return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs nside >= 8 (whole 64 x 32 tiles inside a base face)");
     const int64_t facePix = ctx->nside * ctx->nside, n = ctx->npix;
-    if(shard->q_begin < 0 || shard->q_end > facePix || shard->q_begin > shard->q_end || shard->q_begin % cmg::PQ_TJ || shard->q_end % cmg::PQ_TJ)
-        return fail(ctx, CMG_EINVAL, "shard range must be multiples of 32 inside [0, nside^2]");
-    sh.q0 = static_cast<int>(shard->q_begin);
-    sh.q1 = static_cast<int>(shard->q_end);
-    const bool whole = sh.q0 == 0 && sh.q1 == facePix;
+    cmg_status s = orbitCheckBounds(ctx, ctx->nside, shard->n_ranks, shard->bounds, shard->rank);
+    if(s != CMG_OK) return s;
+    std::memset(&sh, 0, sizeof(sh));
+    sh.nRanks = shard->n_ranks;
+    sh.rank = shard->rank;
+    sh.q0 = static_cast<int>(shard->bounds[shard->rank]);
+    sh.q1 = static_cast<int>(shard->bounds[shard->rank + 1]);
+    for(int r = 0; r <= cmg::ORB_MAX_RANKS; ++r)       // padded behind the last rank: orbitOwnerOfHalfTile counts the boundaries <= h
+        sh.boundH[r] = r < sh.nRanks ? static_cast<int>(shard->bounds[r] / cmg::ORB_SUB) : 0x7fffffff;
+    sh.boundH[sh.nRanks] = static_cast<int>(shard->bounds[sh.nRanks] / cmg::ORB_SUB);
     cmg::OrbitPlan plan;
     cmg::orbitBuildPlan(ctx->nside, mode, -1, plan);
-    bool need[6][12] = {};
-    for(int c = 0; c < plan.n; ++c)
-        for(int k = 0; k < plan.c[c].nImg; ++k)
-            for(int t = 0; t < (plan.c[c].imgSwap[k] ? 6 : 3); ++t)
-                need[t][plan.c[c].imgColFace[k]] = true;
+    int64_t off[cmg::ORB_MAX_RANKS + 1];
+    orbitOutboxOffsets(plan, sh.nRanks, shard->bounds, sh.rank, off);
+    for(int d = 0; d < sh.nRanks; ++d)
+        sh.destOff[d] = off[d];
+    if(off[sh.nRanks] > 0 && !shard->outbox && sh.q1 > sh.q0) return fail(ctx, CMG_EINVAL, "shard: null outbox");
+    sh.outbox = shard->outbox;
     for(int f = 0; f < 12; ++f)
-    {
-        for(int s = 0; s < 3; ++s)
+        for(int st = 0; st < 3; ++st)
         {
-            if(!shard->strip[s][f] && sh.q1 > sh.q0) return fail(ctx, CMG_EINVAL, "shard: null strip");
-            sh.strip[s][f] = shard->strip[s][f] - cmg::packedOffset(s * n + f * facePix + sh.q0);
+            if(!shard->strip[st][f] && sh.q1 > sh.q0) return fail(ctx, CMG_EINVAL, "shard: null strip");
+            sh.strip[st][f] = shard->strip[st][f] - cmg::packedOffset(st * n + f * facePix + sh.q0);
         }
-        for(int t = 0; t < 6; ++t)
-        {
-            if(!whole && need[t][f] && !shard->outbox[t][f] && sh.q1 > sh.q0) return fail(ctx, CMG_EINVAL, "shard: an outbox block this mode writes is null");
-            sh.outbox[t][f] = shard->outbox[t][f];
-        }
-    }
     return CMG_OK;
 }
 
@@ -1055,9 +1113,9 @@ cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* att, const double* 
             CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));       \
             kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);                          \
         }
-        if(masks[m] == 0 && mode == 2)
+        if(masks[m] == 0 && mode == 0)
         {
-            // classes without transposed images, store destinations from a per-tile table in shared memory (not yet run on a GPU)
+            // classes without transposed images: store destinations from a per-tile table in shared memory (36.2 against 36.8 ms)
             auto kernel = cmg::tquOrbitKernel<4, 2, 0, true>;
             const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<false, true>();
             CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1082,8 +1140,10 @@ cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* att, const double* ate, con
     cmg_orbit_shard shard;
     std::memset(&shard, 0, sizeof(shard));
     const int64_t facePix = ctx->nside * ctx->nside, n = ctx->npix;
-    shard.q_begin = 0;
-    shard.q_end = facePix;
+    shard.n_ranks = 1;
+    shard.rank = 0;
+    shard.bounds[0] = 0;
+    shard.bounds[1] = facePix;
     for(int st = 0; st < 3; ++st)
         for(int f = 0; f < 12; ++f)
             shard.strip[st][f] = dPacked + cmg::packedOffset(st * n + f * facePix);
@@ -1122,6 +1182,58 @@ cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, do
     return timer.finish();
 }
 
+namespace
+{
+// block(sender -> receiver) -> the receiver's packed columns; `strips` = the receiver's ADJUSTED strip bases
+cmg_status launchInboxScatter(cmg_ctx* ctx, int mode, int nRanks, const int64_t* bounds, int sender, int receiver, const double* dBlock,
+                              double* const (*strips)[12])
+{
+    cmg::OrbitPlan plan;
+    cmg::orbitBuildPlan(ctx->nside, mode, -1, plan);
+    cmg::OrbitInboxArgs a;
+    a.npix = ctx->npix;
+    a.senderQ0 = static_cast<int>(bounds[sender]);
+    a.nct = static_cast<int>((bounds[sender + 1] - bounds[sender]) / cmg::PQ_TJ);
+    a.h0 = static_cast<int>(bounds[receiver] / cmg::ORB_SUB);
+    a.nh = static_cast<int>((bounds[receiver + 1] - bounds[receiver]) / cmg::ORB_SUB);
+    a.triLive = receiver < sender ? 1 : 0;
+    a.block = dBlock;
+    for(int st = 0; st < 3; ++st)
+        for(int f = 0; f < 12; ++f)
+            a.strip[st][f] = strips[st][f];
+    (void) nRanks;
+    if(a.nct == 0 || a.nh == 0) return CMG_OK;
+    const dim3 grid(static_cast<unsigned>(a.nct) * static_cast<unsigned>(a.nh), static_cast<unsigned>(plan.n));
+    cmg::orbitInboxScatterKernel<<<grid, cmg::PQ_THREADS, 0, ctx->stream>>>(plan, a);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
+}
+} // namespace
+
+cmg_status cmg_orbit_outbox_layout(int64_t nside, int mode, int nRanks, const int64_t* bounds, int rank, int64_t* offsets)
+{
+    if(!offsets || !cmg::validNside(nside) || nside < 8 || mode < 0 || mode > 2) return CMG_EINVAL;
+    if(orbitCheckBounds(nullptr, nside, nRanks, bounds, rank) != CMG_OK) return CMG_EINVAL;
+    cmg::OrbitPlan plan;
+    cmg::orbitBuildPlan(nside, mode == 2 ? 0 : mode, -1, plan);
+    orbitOutboxOffsets(plan, nRanks, bounds, rank, offsets);
+    return CMG_OK;
+}
+
+cmg_status cmg_tqu_orbit_scatter_inbox(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, int sender, const double* dBlock)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(ctx->npix <= 0) return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
+    cmg::OrbitShardDev sh;
+    cmg_status s = orbitShardDev(ctx, shard, mode, sh);
+    if(s != CMG_OK) return s;
+    if(sender < 0 || sender >= sh.nRanks || sender == sh.rank) return fail(ctx, CMG_EINVAL, "sender must be another rank of the shard");
+    if(!dBlock) return fail(ctx, CMG_EINVAL, "null block");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launchInboxScatter(ctx, mode == 2 ? 0 : mode, sh.nRanks, shard->bounds, sender, sh.rank, dBlock, sh.strip);
+}
+
 cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, int parts, double* dFull)
 {
     if(!ctx) return CMG_EINVAL;
@@ -1141,15 +1253,93 @@ cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, in
             if(shard->strip[st][f] != dFull + first)
                 CMG_CUDA(ctx, cudaMemcpyAsync(dFull + first, shard->strip[st][f], sizeof(double) * (last - first), cudaMemcpyDeviceToDevice, ctx->stream));
         }
-    if((sh.q0 == 0 && sh.q1 == facePix) || !(parts & 2))
+    if(sh.nRanks == 1 || !(parts & 2))
         return CMG_OK;
-    cmg::OrbitPlan plan;
-    cmg::orbitBuildPlan(ctx->nside, mode, -1, plan);
-    const unsigned tiles = static_cast<unsigned>((facePix / cmg::PQ_TI) * ((sh.q1 - sh.q0) / cmg::PQ_TJ));
-    cmg::orbitOutboxScatterKernel<<<dim3(tiles, static_cast<unsigned>(plan.n)), cmg::PQ_THREADS, 0, ctx->stream>>>(n, plan, sh, dFull);
-    CMG_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    double* whole[3][12];
+    for(int st = 0; st < 3; ++st)
+        for(int f = 0; f < 12; ++f)
+            whole[st][f] = dFull;                    // the adjusted base of every run of columns of a whole triangle is its first element
+    for(int d = 0; d < sh.nRanks; ++d)
+        if(d != sh.rank && sh.destOff[d] != (d + 1 < sh.nRanks ? sh.destOff[d + 1] : -1))
+            if((s = launchInboxScatter(ctx, mode, sh.nRanks, shard->bounds, sh.rank, d, sh.outbox + sh.destOff[d], whole)) != CMG_OK) return s;
     return CMG_OK;
+}
+
+cmg_status cmg_host_register(void* ptr, int64_t bytes)
+{
+    if(!ptr || bytes <= 0) return CMG_EINVAL;
+    const cudaError_t e = cudaHostRegister(ptr, static_cast<size_t>(bytes), cudaHostRegisterPortable);
+    if(e != cudaSuccess) return cudaFail(nullptr, e, "cudaHostRegister");
+    return CMG_OK;
+}
+
+cmg_status cmg_host_unregister(void* ptr)
+{
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if(e != cudaSuccess) return cudaFail(nullptr, e, "cudaHostUnregister");
+    return CMG_OK;
+}
+
+cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, double* hostPacked, int threads)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!hostPacked || threads < 0) return fail(ctx, CMG_EINVAL, "null destination or negative thread count");
+    if(ctx->npix <= 0) return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
+    cmg::OrbitShardDev sh;
+    cmg_status s = orbitShardDev(ctx, shard, 0, sh);
+    if(s != CMG_OK) return s;
+    if(sh.q0 == sh.q1) return CMG_OK;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t facePix = ctx->nside * ctx->nside, n = ctx->npix;
+    if(threads == 0)
+    {
+        for(int st = 0; st < 3; ++st)
+            for(int f = 0; f < 12; ++f)
+            {
+                const int64_t first = cmg::packedOffset(st * n + f * facePix + sh.q0), last = cmg::packedOffset(st * n + f * facePix + sh.q1);
+                CMG_CUDA(ctx, cudaMemcpyAsync(hostPacked + first, shard->strip[st][f], sizeof(double) * (last - first), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return CMG_OK;
+    }
+    // the rank's columns of the last face of every ring, in chunks of ~64 MB; workers fill in the images of a chunk once it is there
+    struct Chunk { int strip, ring; int64_t q0, q1; cudaEvent_t arrived; };
+    std::vector<Chunk> chunks;
+    for(int st = 0; st < 3; ++st)
+        for(int ring = 0; ring < 3; ++ring)
+        {
+            const int64_t col0 = st * n + (4 * ring + 3) * facePix;
+            const int64_t step = std::max<int64_t>(8, std::min<int64_t>(facePix, (int64_t(8) << 20) / (col0 + facePix)));
+            for(int64_t q = sh.q0; q < sh.q1; q += step)
+                chunks.push_back({st, ring, q, std::min<int64_t>(sh.q1, q + step), nullptr});
+        }
+    cmg_status st = CMG_OK;
+    size_t issued = 0;
+    for(; issued < chunks.size() && st == CMG_OK; ++issued)
+    {
+        Chunk& c = chunks[issued];
+        const int face = 4 * c.ring + 3;
+        const int64_t col0 = c.strip * n + face * facePix;
+        const int64_t first = cmg::packedOffset(col0 + c.q0), last = cmg::packedOffset(col0 + c.q1);
+        const double* src = shard->strip[c.strip][face] + (first - cmg::packedOffset(col0 + sh.q0));
+        cudaError_t e = cudaMemcpyAsync(hostPacked + first, src, sizeof(double) * (last - first), cudaMemcpyDeviceToHost, ctx->stream);
+        if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c.arrived, cudaEventDisableTiming);
+        if(e == cudaSuccess) e = cudaEventRecord(c.arrived, ctx->stream);
+        if(e != cudaSuccess) st = cudaFail(ctx, e, "cudaMemcpyAsync (strips to host)");
+    }
+    cmg::ExpandPipeline* pipe = cmg::expandBegin(hostPacked, ctx->nside, threads);
+    for(size_t k = 0; k < issued; ++k)
+    {
+        Chunk& c = chunks[k];
+        if(!c.arrived) continue;
+        const cudaError_t e = cudaEventSynchronize(c.arrived);
+        cudaEventDestroy(c.arrived);
+        if(e != cudaSuccess && st == CMG_OK) st = cudaFail(ctx, e, "cudaEventSynchronize");
+        if(st == CMG_OK)
+            cmg::expandPublish(pipe, c.strip, c.ring, c.q0, c.q1);
+    }
+    cmg::expandFinish(pipe);
+    return st;
 }
 
 cmg_status cmg_tqu_batched(cmg_ctx* ctx, const double* a, int lmax, int64_t nBatch, double* dOut, int64_t stride)
@@ -1337,9 +1527,10 @@ cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* 
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int n1 = lmax + 1;
     std::vector<double> fT(n1), fP(n1), a(4 * n1);
-    cmg_window_beam(fT.data(), lmax, fwhm, pixwinT);
-    cmg_window_beam(fP.data(), lmax, fwhm, pixwinP);
-    cmg_tqu_weights(ctt, cte, cee, cbb, fT.data(), fP.data(), lmax, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1);
+    if(cmg_window_beam(fT.data(), lmax, fwhm, pixwinT) != CMG_OK || cmg_window_beam(fP.data(), lmax, fwhm, pixwinP) != CMG_OK)
+        return fail(ctx, CMG_EINVAL, "fwhm must be >= 0 (degrees)");
+    if((s = cmg_tqu_weights(ctt, cte, cee, cbb, fT.data(), fP.data(), lmax, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1)) != CMG_OK)
+        return fail(ctx, s, "bad C_l / window arguments");
     const int64_t bytes = sizeof(double) * cmg_packed_size(3 * ctx->npix);
     if((s = ensureScratch(ctx, bytes)) != CMG_OK) return s;
     if(ctx->fullSky && ctx->nside >= 8 && lmax >= 2 && lmax <= cmg::PQ_STATIC_LMAX && ctx->tquVariant == 0)
@@ -1353,8 +1544,8 @@ cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* 
         if((s = cmg_tqu_layout_single(ctx, ctx->dScratch, &layout)) != CMG_OK) return s;
         if((s = cmg_tqu(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, &layout)) != CMG_OK) return s;
     }
-    if(ctx->fullSky && ctx->hostExpandThreads > 0)
-        return copyBackLastFacesAndExpand(ctx, 3, outPacked);
+    if(const int threads = hostExpandThreadsFor(ctx, bytes))
+        return copyBackLastFacesAndExpand(ctx, 3, outPacked, threads);
     CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CMG_OK;
@@ -1796,7 +1987,7 @@ cmg_status cmg_set_kernel_variant(cmg_ctx* ctx, int variant)
 
 cmg_status cmg_set_host_expand(cmg_ctx* ctx, int threads)
 {
-    if(!ctx || threads < 0) return CMG_EINVAL;
+    if(!ctx || threads < -1) return CMG_EINVAL;
     ctx->hostExpandThreads = threads;
     return CMG_OK;
 }

@@ -36,12 +36,14 @@ struct OrbitClass
     int imgRowFace[ORB_MAX_IMAGES];        // image k of the rows / columns lives in these faces (image 0 = source)
     int imgColFace[ORB_MAX_IMAGES];
     int imgSwap[ORB_MAX_IMAGES];           // 1: the image of the rows has the LARGER pixel index
+    int comboBase[ORB_MAX_IMAGES];         // outbox numbering of (this class, image k, staged kind 0): see OrbitShardDev
 };
 
 struct OrbitPlan
 {
     int n;
     int facePix;                           // nside^2
+    int nComboA, nComboB;                  // (class, image, staged kind) combinations of the whole-face-pair / q_row <= q_col classes
     OrbitClass c[ORB_MAX_CLASSES];
 };
 
@@ -56,14 +58,24 @@ inline void orbitBuildPlan(int64_t nside, int mode, int swapMask, OrbitPlan& pla
 {
     plan.n = 0;
     plan.facePix = static_cast<int>(nside * nside);
+    plan.nComboA = plan.nComboB = 0;
+    // the numbering of the (class, image, staged kind) combinations runs over ALL classes of the mode, whatever swapMask
+    // selects: whole-face-pair classes first (0 .. nComboA), q_row <= q_col classes behind them (fixed up below)
     auto add = [&](int rowFace, int colFace, int tri, int sameFace, int nImg, const int* rot, const int* swap)
     {
-        int mask = 0;
+        int mask = 0, base[ORB_MAX_IMAGES] = {0, 0, 0, 0};
+        int& counter = tri ? plan.nComboB : plan.nComboA;
         for(int k = 0; k < nImg; ++k)
+        {
             mask |= (swap[k] ? 1 : 0) << k;
+            base[k] = counter;
+            counter += swap[k] ? 6 : 3;
+        }
         if(swapMask >= 0 && swapMask != mask)
             return;
         OrbitClass& c = plan.c[plan.n++];
+        for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+            c.comboBase[k] = base[k];
         c.rowFace = rowFace;
         c.colFace = colFace;
         c.tri = tri;
@@ -100,21 +112,48 @@ inline void orbitBuildPlan(int64_t nside, int mode, int swapMask, OrbitPlan& pla
             add(4 * g, 4 * g + 2, 0, 0, 2, rot4, none);
         }
     }
+    for(int c = 0; c < plan.n; ++c)
+        if(plan.c[c].tri)
+            for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+                plan.c[c].comboBase[k] += plan.nComboA;
 }
 
 // Where a rank's entries live.  A rank owns the in-face column range [q0, q1) of ALL twelve base faces (an orbit-closed set
 // of pixel columns): it evaluates the source pairs whose column pixel has q in that range and stores every image.
 //   strip[s][f]   ADJUSTED base of the packed columns s N + f F + [q0, q1): entry (row, col) at strip[s][f] + col (col+1)/2 + row
-//   outbox[t][f]  entries whose packed column belongs to another rank (the row pixel a' of the pair has q outside [q0, q1)):
-//                 kind t (0 <Q T>, 1 <U T>, 2 <U Q>, 3 <T T>, 4 <Q Q>, 5 <U U>), column pixel b' in face f:
-//                 element at outbox[t][f] + a' (q1 - q0) + (q_b' - q0)
-// One rank (q0 = 0, q1 = F): every strip[s][f] is the base of the whole packed triangle and no outbox is touched.
+//   outbox        entries whose packed column belongs to another rank (the row pixel a' of the pair has q outside [q0, q1)),
+//                 compact and ordered by destination: the block for rank d starts at destOff[d] and holds, for every
+//                 (class, image, staged kind) combination that can address d -- all nComboA + nComboB for d < rank, the nComboA
+//                 of the whole-face-pair classes for d > rank (a q_row <= q_col class never pairs a column with a later row) --
+//                 the 32 x 32 sub-tiles (row half-tile h of d's range, column tile ct of this rank's range), each stored
+//                 row-major (32 consecutive column pixels of one row pixel = one 256-byte run of the destination column):
+//                     outbox[destOff[d] + ((combo nct + ct) nh_d + (h - h0_d)) 1024 + (q_a' mod 32) 32 + (q_b' mod 32)]
+//                 Every element of the outbox is written exactly once.  Staged kinds: 0 <Q T>, 1 <U T>, 2 <U Q>, and for a
+//                 transposed image 3 <T T>, 4 <Q Q>, 5 <U U>.
+// One rank (nRanks = 1): every strip[s][f] is the base of the whole packed triangle and no outbox is touched.
+constexpr int ORB_MAX_RANKS = 16;
+constexpr int ORB_SUB = 32;                // rows and columns of an outbox sub-tile
+
 struct OrbitShardDev
 {
     int q0, q1;
+    int nRanks, rank;
+    int boundH[ORB_MAX_RANKS + 1];         // range boundaries of all ranks in units of ORB_SUB rows
+    long long destOff[ORB_MAX_RANKS];      // first element of the block for destination d
     double* strip[3][12];
-    double* outbox[6][12];
+    double* outbox;
 };
+
+// host + device: destination rank of row half-tile h, and the outbox offset of sub-tile (combo 0, ct, h) with the stride per combo
+__host__ __device__ inline int orbitOwnerOfHalfTile(const OrbitShardDev& sh, int h)
+{
+    // branch-free: boundH is padded with INT_MAX behind the last rank (host)
+    int d = 0;
+#pragma unroll
+    for(int r = 1; r < ORB_MAX_RANKS; ++r)
+        d += h >= sh.boundH[r] ? 1 : 0;
+    return d;
+}
 
 // shared memory of tquOrbitKernel: frames of rows and columns, staged entries, column pointers of every image
 template <bool SWAP, bool ROWPTR = false>
@@ -126,6 +165,15 @@ constexpr int orbitSmemDoubles()
 // staged kind t -> (column strip X, row strip Y) of the entry <X a', Y b'>
 __device__ __forceinline__ int orbitStripX(int t) { return t == 0 ? 1 : (t == 1 || t == 2 || t == 5) ? 2 : (t == 4 ? 1 : 0); }
 __device__ __forceinline__ int orbitStripY(int t) { return t == 2 ? 1 : (t == 4 ? 1 : (t == 5 ? 2 : 0)); }
+
+// one row of a tile's store plan (tquOrbitKernel): destinations of (image, staged kind)
+struct OrbitStoreRow
+{
+    double* own;                           // entry (row pixel of tile row 0, first column pixel of the tile) in the rank's own strips
+    double* box[PQ_TI / ORB_SUB];          // first element of the outbox sub-tile of each 32-row half
+    unsigned c;                            // packed column of tile row 0
+    int minGap;                            // a row is stored where q_col - q_row >= minGap
+};
 
 // tile of a CTA: class blockIdx.y, 64 rows x 32 columns of in-face indices; false = nothing to do (q_row > q_col everywhere)
 __device__ __forceinline__ bool orbitTile(const OrbitPlan& plan, const OrbitShardDev& sh, int& qRow0, int& qCol0)
@@ -172,6 +220,47 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     const int nImg = oc.nImg;
     const int tid = threadIdx.x;
 
+    // Store plan of the tile: for every (image k, staged kind t) where its rows start in the rank's own strips and in its
+    // outbox (OrbitShardDev; one base per 32-row half of the tile), computed by 24 threads into shared memory.  The store
+    // phase reads nothing but this table: no kernel parameter is referenced behind the series loop, so ptxas has nothing to
+    // hoist above it -- uniform values kept live across the loop cost it its uniform-register coefficient operands
+    // (tests/test_sass_guard.py; a third of the DFMAs then read three vector registers).
+    __shared__ OrbitStoreRow sStore[ORB_MAX_IMAGES * 6];
+    __shared__ int sRange[2];
+    if(tid < ORB_MAX_IMAGES * 6)
+    {
+        const int k = tid / 6, t = tid - 6 * k;
+        const bool swapped = (SWAPMASK >> k) & 1;
+        if(k < nImg && t < (swapped ? 6 : 3))
+        {
+            const int rowFace = oc.imgRowFace[k], colFace = oc.imgColFace[k];
+            const long long rowPix0 = static_cast<long long>(rowFace) * facePix + qRow0;
+            const long long colPix0 = static_cast<long long>(colFace) * facePix + qCol0;
+            const long long c = orbitStripX(t) * npix + rowPix0;                 // < 2^32 for every valid nside
+            OrbitStoreRow e;
+            e.own = sh.strip[orbitStripX(t)][rowFace] + packedOffset(c) + (orbitStripY(t) * npix + colPix0);
+            e.c = static_cast<unsigned>(c);
+            // q_col - q_row must be >= minGap: none for whole face pairs; 1 where q_row == q_col is one pixel (its partners
+            // are the direct entries) or belongs to image 0 (transposed images of a q_row <= q_col class); else 0
+            e.minGap = !tri ? -(1 << 30) : ((oc.sameFace || swapped) ? 1 : 0);
+#pragma unroll
+            for(int half = 0; half < PQ_TI / ORB_SUB; ++half)
+            {
+                const int h = qRow0 / ORB_SUB + half;
+                const int d = orbitOwnerOfHalfTile(sh, h);
+                const int nhD = sh.boundH[d + 1] - sh.boundH[d];
+                const int nct = (sh.q1 - sh.q0) / PQ_TJ, ct = (qCol0 - sh.q0) / PQ_TJ;
+                const long long combo = oc.comboBase[k] + t;
+                e.box[half] = sh.outbox + sh.destOff[d] + ((combo * nct + ct) * nhD + (h - sh.boundH[d])) * (ORB_SUB * ORB_SUB);
+            }
+            sStore[tid] = e;
+        }
+        if(tid == 0)
+        {
+            sRange[0] = sh.q0;
+            sRange[1] = sh.q1;
+        }
+    }
     for(int idx = tid; idx < PQ_TI + PQ_TJ; idx += PQ_THREADS)
     {
         const bool isRow = idx < PQ_TI;
@@ -200,20 +289,22 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     }
     if(ROWPTR)
     {
-        // where row (image k, kind t, a') of the store phase starts: the rank's own strip, or its outbox block
+        // where row (image k, kind t, a') of the store phase starts: the rank's own strip, or its outbox sub-tile
+        __syncthreads();
         for(int idx = tid; idx < ORB_MAX_IMAGES * 3 * PQ_TI; idx += PQ_THREADS)
         {
             const int k = idx / (3 * PQ_TI);
             const int rem = idx - k * 3 * PQ_TI;
             const int t = rem / PQ_TI;
-            const int ilr = rem - t * PQ_TI;
-            const int rowFace = oc.imgRowFace[k], colFace = oc.imgColFace[k];
-            const long long rowPix = static_cast<long long>(rowFace) * facePix + qRow0 + ilr;
-            const long long colPix0 = static_cast<long long>(colFace) * facePix + qCol0;
-            const int qa = qRow0 + ilr;
-            sRowPtr[idx] = (qa >= sh.q0 && qa < sh.q1)
-                               ? sh.strip[orbitStripX(t)][rowFace] + packedOffset(orbitStripX(t) * npix + rowPix) + (orbitStripY(t) * npix + colPix0)
-                               : sh.outbox[t][colFace] + rowPix * (sh.q1 - sh.q0) + (qCol0 - sh.q0);
+            const unsigned ilr = static_cast<unsigned>(rem - t * PQ_TI);
+            if(k < nImg)
+            {
+                const OrbitStoreRow e = sStore[k * 6 + t];
+                const int qa = qRow0 + static_cast<int>(ilr);
+                static_assert(PQ_TI == 2 * ORB_SUB, "two outbox halves per tile");
+                sRowPtr[idx] = (qa >= sh.q0 && qa < sh.q1) ? e.own + (static_cast<unsigned long long>(ilr) * e.c + (ilr * (ilr + 1)) / 2)
+                                                           : (ilr >= ORB_SUB ? e.box[1] : e.box[0]) + (ilr % ORB_SUB) * ORB_SUB;
+            }
         }
     }
     __syncthreads();
@@ -322,14 +413,12 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     // Addresses: row a' = a'_0 + r of column strip X sits at packedOffset(c + r) = packedOffset(c) + r c + r (r + 1) / 2 with
     // c = X N + a'_0 warp-uniform, so a row costs one 32 x 32 -> 64 bit multiply-add on top of a base computed once per
     // (image, kind); the outbox row is r (q1 - q0) further on.
-    const int sameFace = oc.sameFace;
-    const unsigned ldOut = static_cast<unsigned>(sh.q1 - sh.q0);
     const int qColLane = qCol0 + lane;
     if(ROWPTR)
     {
-        const int minGap = !tri ? -(1 << 30) : (sameFace ? 1 : 0);
         for(int k = 0; k < nImg; ++k)
         {
+            const int minGap = sStore[k * 6].minGap;
 #pragma unroll 4
             for(int row = warp; row < 3 * PQ_TI; row += PQ_THREADS / 32)
             {
@@ -340,33 +429,25 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
         }
         return;
     }
+    const int ownQ0 = sRange[0], ownQ1 = sRange[1];
     for(int k = 0; k < nImg; ++k)
     {
-        const bool swapped = (SWAPMASK >> k) & 1;
-        const int nKinds = swapped ? 6 : 3;
-        const int rowFace = oc.imgRowFace[k], colFace = oc.imgColFace[k];
-        const long long rowPix0 = static_cast<long long>(rowFace) * facePix + qRow0;
-        const long long colPix0 = static_cast<long long>(colFace) * facePix + qCol0;
-        // q_col - q_row must be >= minGap: none for whole face pairs; 1 where q_row == q_col is one pixel (its partners
-        // are the direct entries) or belongs to image 0 (transposed images of a q_row <= q_col class); else 0
-        const int minGap = !tri ? -(1 << 30) : ((sameFace || swapped) ? 1 : 0);
+        const int nKinds = ((SWAPMASK >> k) & 1) ? 6 : 3;
         for(int t = 0; t < nKinds; ++t)
         {
-            const unsigned c = static_cast<unsigned>(orbitStripX(t) * npix + rowPix0);       // < 2^32 for every valid nside
-            double* const ownBase = sh.strip[orbitStripX(t)][rowFace] + packedOffset(static_cast<long long>(c)) +
-                                    (orbitStripY(t) * npix + colPix0 + lane);
-            double* const boxBase = sh.outbox[t][colFace] + rowPix0 * ldOut + (qCol0 - sh.q0 + lane);
+            const OrbitStoreRow e = sStore[k * 6 + t];
             const double* src = stage + (t * PQ_TI) * PQ_STAGE_LD + lane;
 #pragma unroll
             for(int u = 0; u < PQ_TI / (PQ_THREADS / 32); ++u)
             {
                 const unsigned r = static_cast<unsigned>(warp + u * (PQ_THREADS / 32));
                 const int qa = qRow0 + static_cast<int>(r);
-                const bool local = qa >= sh.q0 && qa < sh.q1;                                  // warp-uniform
-                const unsigned long long off = local ? static_cast<unsigned long long>(r) * c + (r * (r + 1)) / 2
-                                                     : static_cast<unsigned long long>(r) * ldOut;
-                double* dst = (local ? ownBase : boxBase) + off;
-                if(qColLane - qa >= minGap)
+                constexpr int HALF_U = ORB_SUB / (PQ_THREADS / 32);                            // u < HALF_U: rows of the first half
+                const bool local = qa >= ownQ0 && qa < ownQ1;                                  // the same for the whole warp
+                const unsigned long long off = local ? static_cast<unsigned long long>(r) * e.c + (r * (r + 1)) / 2
+                                                     : static_cast<unsigned long long>(r % ORB_SUB) * ORB_SUB;
+                double* dst = (local ? e.own : e.box[u / HALF_U]) + off + lane;
+                if(qColLane - qa >= e.minGap)
                     __stcs(dst, src[r * PQ_STAGE_LD]);
             }
         }
@@ -436,36 +517,49 @@ legendreSeriesOrbitKernel(const __grid_constant__ TtStaticTable T, Geometry geo,
     }
 }
 
-// Outbox blocks of a rank -> their places in a whole packed triangle (assembly of the unsharded matrix): the same tiles,
-// images and predicates as the last phase of tquOrbitKernel, reading the block instead of the stage.
-__global__ void __launch_bounds__(PQ_THREADS)
-orbitOutboxScatterKernel(long long npix, const __grid_constant__ OrbitPlan plan, const __grid_constant__ OrbitShardDev sh,
-                         double* __restrict__ full)
+// One destination block of a rank's outbox (OrbitShardDev: block(sender -> d)) -> its places in the packed columns of rank d.
+// `recv` holds the receiver's ADJUSTED strip bases (its own strips, or the base of a whole packed triangle 36 times when the
+// unsharded matrix is assembled on one GPU); `block` may be local memory (after an all-to-all) or the sender's outbox mapped
+// through CUDA IPC, in which case the loads of this kernel are the NVLink transfer.
+//   grid.x = (column tile ct of the sender's range) x (row half-tile hh of the receiver's range), grid.y = class of the full plan
+struct OrbitInboxArgs
 {
-    int qRow0, qCol0;
-    if(!orbitTile(plan, sh, qRow0, qCol0))
-        return;
+    long long npix;
+    int senderQ0, nct;                     // the sender's range starts at senderQ0 and has nct column tiles
+    int h0, nh;                            // the receiver's range in half-tiles
+    int triLive;                           // receiver rank < sender rank: the q_row <= q_col classes address it as well
+    const double* block;
+    double* strip[3][12];
+};
+
+__global__ void __launch_bounds__(PQ_THREADS)
+orbitInboxScatterKernel(const __grid_constant__ OrbitPlan plan, const __grid_constant__ OrbitInboxArgs a)
+{
     const OrbitClass& oc = plan.c[blockIdx.y];
+    if(oc.tri && !a.triLive)
+        return;
     const int facePix = plan.facePix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ldOut = sh.q1 - sh.q0;
+    const int ct = static_cast<int>(blockIdx.x) / a.nh, hh = static_cast<int>(blockIdx.x) - ct * a.nh;
+    const long long subTiles = static_cast<long long>(a.nct) * a.nh;
+    const int qRow0 = (a.h0 + hh) * ORB_SUB, qCol0 = a.senderQ0 + ct * PQ_TJ;
     for(int k = 0; k < oc.nImg; ++k)
     {
-        const bool swapped = oc.imgSwap[k] != 0;
-        const int nRows = (swapped ? 6 : 3) * PQ_TI;
+        const int nKinds = oc.imgSwap[k] ? 6 : 3;
         const long long rowPix0 = static_cast<long long>(oc.imgRowFace[k]) * facePix + qRow0;
         const long long colPix0 = static_cast<long long>(oc.imgColFace[k]) * facePix + qCol0;
-        const int minGap = !oc.tri ? -(1 << 30) : ((oc.sameFace || swapped) ? 1 : 0);
-        for(int row = warp; row < nRows; row += PQ_THREADS / 32)
+        for(int t = 0; t < nKinds; ++t)
         {
-            const int t = row / PQ_TI;
-            const int ilr = row - t * PQ_TI;
-            const int qa = qRow0 + ilr;
-            if((qCol0 + lane) - qa >= minGap && !(qa >= sh.q0 && qa < sh.q1))
-            {
-                const double v = sh.outbox[t][oc.imgColFace[k]][(rowPix0 + ilr) * ldOut + (qCol0 - sh.q0 + lane)];
-                full[packedOffset(orbitStripX(t) * npix + rowPix0 + ilr) + (orbitStripY(t) * npix + colPix0 + lane)] = v;
-            }
+            const double* src = a.block + ((oc.comboBase[k] + t) * subTiles + blockIdx.x) * (ORB_SUB * ORB_SUB) + lane;
+            double* const dstBase = a.strip[orbitStripX(t)][oc.imgRowFace[k]] + (orbitStripY(t) * a.npix + colPix0 + lane);
+            const long long c = orbitStripX(t) * a.npix + rowPix0;
+            double v[ORB_SUB / (PQ_THREADS / 32)];
+#pragma unroll
+            for(int u = 0; u < ORB_SUB / (PQ_THREADS / 32); ++u)
+                v[u] = __ldcs(src + (warp + u * (PQ_THREADS / 32)) * ORB_SUB);
+#pragma unroll
+            for(int u = 0; u < ORB_SUB / (PQ_THREADS / 32); ++u)
+                __stcs(dstBase + packedOffset(c + warp + u * (PQ_THREADS / 32)), v[u]);
         }
     }
 }

@@ -85,6 +85,15 @@ class ShardedTQU:
         import torch
         import torch.distributed as dist
         scratch = None
+        # torch's collectives run on torch's current stream, the generator and cmg_tqu_scatter_block on the context's: unless
+        # the two are one stream, every phase is fenced (generation -> broadcasts -> scatter -> next broadcast into scratch)
+        fence = self.ctx.stream_handle != torch.cuda.current_stream().cuda_stream
+
+        def sync():
+            if fence:
+                self.ctx.synchronize()
+                torch.cuda.current_stream().synchronize()
+        sync()
         for k in range(self.world):
             sizes = partition.tqu_shard_sizes(self.npix, self.bounds[k], self.bounds[k + 1])
             offs = partition.tqu_strip_offsets(self.npix, self.bounds[k])
@@ -104,7 +113,9 @@ class ShardedTQU:
                     for t in range(3):
                         buf = self.outbox[owner][t].tensor() if r == self.rank else scratch[:n]
                         dist.broadcast(buf, src=r)
+                        sync()
                         self.ctx.tqu_scatter_block(buf, self.bounds[owner], ncols, ld, row0, t, full)
+                        sync()
 
     def close(self):
         for ptrs in self.peer_ptrs.values():
@@ -118,57 +129,111 @@ class ShardedTQU:
 
 class OrbitShardedTQU:
     """Rank-local storage of a full-sky [T;Q;U] matrix generated over symmetry orbits (cmg_tqu_orbit_sharded): the rank owns
-    the in-face column range [q0, q1) of all twelve base faces -- 36 contiguous runs of packed columns -- plus dense outbox
-    blocks for the entries whose packed column is another rank's.  No data-path collective."""
+    the in-face column range [q0, q1) of all twelve base faces -- 36 contiguous runs of packed columns -- plus a compact outbox,
+    ordered by destination rank, for the entries whose packed column is another rank's (a third of the nine entries of a pair
+    whose row pixel lies outside the range).  Producing the entries needs no collective; `exchange()` completes the strips:
+    block(r -> d) of every outbox travels to rank d (one NCCL all-to-all over NVLink, or the receiver's scatter kernel reads
+    the sender's outbox through CUDA IPC) and is placed into d's packed columns.  After that a rank holds exactly its columns
+    of the matrix: N ranks hold 87 GB between them for the Nside = 64 matrix."""
 
-    def __init__(self, ctx, nside, rank, world, mode=0):
+    def __init__(self, ctx, nside, rank, world, mode=0, exchange="nccl"):
         self.ctx, self.nside, self.rank, self.world, self.mode = ctx, nside, rank, world, mode
         self.face_pix = nside * nside
         self.npix = 12 * self.face_pix
         self.bounds = partition.orbit_partition(nside, world, mode)
         self.q0, self.q1 = self.bounds[rank], self.bounds[rank + 1]
-        # (kind, column face, first row face, last row face + 1) of every outbox block the plan writes
-        self.outbox_blocks = partition.orbit_outbox_blocks(capi.orbit_plan(nside, mode)) if world > 1 else []
+        self.layouts = [capi.orbit_outbox_layout(nside, mode, self.bounds, r) for r in range(world)] if world > 1 else [[0, 0]]
         n_strips, n_outbox = self.sizes_of(rank)
         # one allocation for the 36 strips: the pieces stay individually contiguous pieces of the packed triangle
         self.strips = DeviceBuffer(ctx, n_strips)
         self.outbox = DeviceBuffer(ctx, n_outbox) if n_outbox else None
         self.shard = self.shard_of(rank, self.strips.ptr, self.outbox.ptr if self.outbox is not None else 0)
         self.pairs = partition.orbit_pairs_in_range(self.q0, self.q1, self.face_pix, mode)
+        self.exchange_mode = exchange
+        self.inbox = None
+        self.peer_outbox = {}
+        # doubles this rank receives from every sender / sends to every destination
+        self.recv_counts = [self.block_size(r, rank) for r in range(world)]
+        self.send_counts = [self.block_size(rank, d) for d in range(world)]
+
+    def block_size(self, sender, dest):
+        if sender == dest or self.world == 1:
+            return 0
+        lay = self.layouts[sender]
+        return lay[dest + 1] - lay[dest]
 
     def sizes_of(self, rank):
         """doubles in the strips buffer and in the outbox buffer of rank `rank`"""
         q0, q1 = self.bounds[rank], self.bounds[rank + 1]
         n_strips = sum(sum(r) for r in partition.orbit_strip_sizes(self.nside, q0, q1))
-        n_outbox = sum(hi - lo for _, _, lo, hi in self.outbox_blocks) * self.face_pix * (q1 - q0) if q1 > q0 else 0
-        return n_strips, n_outbox
+        return n_strips, (self.layouts[rank][-1] if self.world > 1 else 0)
 
     def shard_of(self, rank, strips_ptr, outbox_ptr):
         """cmg_orbit_shard of rank `rank` over a strips buffer and an outbox buffer laid out like this class's own"""
         q0, q1 = self.bounds[rank], self.bounds[rank + 1]
         sizes = partition.orbit_strip_sizes(self.nside, q0, q1)
         shard = capi.OrbitShard()
-        shard.q_begin, shard.q_end = q0, q1
+        shard.n_ranks, shard.rank = self.world, rank
+        for k, b in enumerate(self.bounds):
+            shard.bounds[k] = b
         off = 0
         for s in range(3):
             for f in range(12):
                 shard.strip[s][f] = strips_ptr + 8 * off
                 off += sizes[s][f]
-        if outbox_ptr:
-            # only the row-pixel faces a block is ever addressed with are allocated; the pointer handed to the kernel is that of
-            # (virtual) row pixel 0, i.e. moved back by first_face x nside^2 rows of ld elements
-            per_face = self.face_pix * (q1 - q0)
-            off = 0
-            for t, f, lo, hi in self.outbox_blocks:
-                shard.outbox[t][f] = outbox_ptr + 8 * (off - lo * per_face)
-                off += (hi - lo) * per_face
+        shard.outbox = outbox_ptr or None
         return shard
 
     def generate(self, weights):
         self.ctx.tqu_orbit_sharded(*weights, self.shard, self.mode)
 
+    def exchange(self):
+        """complete this rank's strips with the entries the other ranks computed for its columns.  Collective."""
+        if self.world == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        if self.exchange_mode == "pull":
+            # the receiver's scatter kernel reads block(r -> this rank) straight out of rank r's outbox over NVLink
+            if not self.peer_outbox:
+                mine = self.ctx.ipc_export(self.outbox.ptr)
+                everyone = [None] * self.world
+                dist.all_gather_object(everyone, mine)
+                for r in range(self.world):
+                    if r != self.rank and self.recv_counts[r]:
+                        self.peer_outbox[r] = self.ctx.ipc_open(everyone[r])
+            self._sync_streams()
+            dist.barrier()                         # every outbox is complete before anyone reads it
+            for r, base in self.peer_outbox.items():
+                self.ctx.tqu_orbit_scatter_inbox(self.shard, r, base + 8 * self.layouts[r][self.rank], self.mode)
+            self._sync_streams()
+            dist.barrier()                         # nobody overwrites an outbox a peer is still reading
+            return
+        if self.inbox is None:
+            self.inbox = torch.empty(max(sum(self.recv_counts), 1), dtype=torch.float64, device="cuda")
+        self._sync_streams()
+        out = self.outbox.tensor()
+        dist.all_to_all_single(self.inbox[:sum(self.recv_counts)], out, self.recv_counts, self.send_counts)
+        self._sync_streams()
+        off = 0
+        for r in range(self.world):
+            if self.recv_counts[r]:
+                self.ctx.tqu_orbit_scatter_inbox(self.shard, r, self.inbox[off:], self.mode)
+                off += self.recv_counts[r]
+
+    def _sync_streams(self):
+        """torch's collectives run on torch's current stream, the generator on the context's: order the two unless they are one"""
+        import torch
+        if self.ctx.stream_handle != torch.cuda.current_stream().cuda_stream:
+            self.ctx.synchronize()
+            torch.cuda.current_stream().synchronize()
+
     def pieces(self):
         return [self.strips] + ([self.outbox] if self.outbox is not None else [])
+
+    def to_host(self, host_packed, threads=0):
+        """this rank's (complete) strips as its columns of the whole packed HOST matrix (a shared mapping for several ranks)"""
+        self.ctx.orbit_strips_to_host(self.shard, host_packed, threads)
 
     def assemble_into(self, full, parts=3):
         """place this rank's pieces into a whole packed triangle on this GPU (parts: 1 strips, 2 outbox; the strips of all
@@ -176,36 +241,27 @@ class OrbitShardedTQU:
         self.ctx.tqu_orbit_assemble(self.shard, full, self.mode, parts)
 
     def gather_full(self, full):
-        """NCCL: every rank ends up with the whole packed triangle in `full` (only when a consumer needs it).  A strip is a
-        contiguous piece of the packed triangle, so each one is broadcast straight into place; a rank's outbox buffer is
-        broadcast whole into a scratch buffer and placed by orbitOutboxScatterKernel.  (The outbox is allocated dense, so
-        this moves about twice the bytes of the matrix; a tile-major outbox would halve it.)"""
-        import torch
+        """NCCL: every rank ends up with the whole packed triangle in `full` (only when a consumer needs it).  Call after
+        exchange(): the strips are then complete contiguous pieces of the packed triangle, each broadcast straight into place."""
         import torch.distributed as dist
+        self._sync_streams()
         n = self.npix
-        for r in range(self.world):                       # strips of all ranks first
+        for r in range(self.world):
             q0, q1 = self.bounds[r], self.bounds[r + 1]
             sizes = partition.orbit_strip_sizes(self.nside, q0, q1)
             if r == self.rank:
                 self.assemble_into(full, 1)
+                self._sync_streams()
             for s in range(3):
                 for f in range(12):
                     first = partition.packed_size(s * n + f * self.face_pix + q0)
                     if self.world > 1 and sizes[s][f]:
                         dist.broadcast(full[first:first + sizes[s][f]], src=r)
-        if self.world == 1:
-            return
-        scratch = torch.empty(max(self.sizes_of(r)[1] for r in range(self.world)), dtype=torch.float64, device="cuda")
-        for r in range(self.world):
-            n_outbox = self.sizes_of(r)[1]
-            if not n_outbox:
-                continue
-            buf = self.outbox.tensor() if r == self.rank else scratch[:n_outbox]
-            dist.broadcast(buf, src=r)
-            # only the outbox pointers of this descriptor are read (parts = 2)
-            shard = self.shard_of(r, self.strips.ptr, buf.data_ptr())
-            self.ctx.tqu_orbit_assemble(shard, full, self.mode, 2)
 
     def close(self):
+        for p in self.peer_outbox.values():
+            self.ctx.ipc_close(p)
+        self.peer_outbox = {}
+        self.inbox = None
         for b in self.pieces():
             b.free()

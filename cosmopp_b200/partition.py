@@ -130,21 +130,42 @@ def orbit_strip_sizes(nside, q0, q1):
     return [[packed_size(s * n + f * face_pix + q1) - packed_size(s * n + f * face_pix + q0) for f in range(12)] for s in range(3)]
 
 
-def orbit_outbox_kinds(plan):
-    """(kind t, face f) outbox blocks a plan writes: kinds 0..2 for every image, 3..5 for transposed images"""
-    return [(t, f) for t, f, _, _ in orbit_outbox_blocks(plan)]
+ORB_SUB = 32        # rows and columns of an outbox sub-tile (cosmopp_b200/csrc/orbit.cuh)
 
 
-def orbit_outbox_blocks(plan):
-    """Outbox blocks a plan writes, with the range of ROW-pixel faces each one is ever addressed with:
-    [(kind t, column face f, first row face, one past the last row face)].  Block (t, f) is indexed by the row pixel a' of the
-    pair (cmg_orbit_shard: outbox[t][f][a' ld + ...]), and the images of the plan pair column face f with a few row faces
-    only, so a rank allocates rows [first, last) x nside^2 of the block and passes the block pointer moved back by
-    first x nside^2 x ld elements: 26 instead of 54 block-sized allocations with transposed images."""
-    rng = {}
-    for c in plan:
-        for row_face, col_face, swap in c["images"]:
-            for t in range(6 if swap else 3):
-                lo, hi = rng.get((t, col_face), (row_face, row_face + 1))
-                rng[(t, col_face)] = (min(lo, row_face), max(hi, row_face + 1))
-    return [(t, f, lo, hi) for (t, f), (lo, hi) in sorted(rng.items())]
+def orbit_combo_counts(plan):
+    """(nComboA, nComboB): (class, image, staged kind) combinations of the whole-face-pair classes and of the q_row <= q_col
+    classes; a transposed image stages six kinds, a straight one three"""
+    n_a = sum(6 if swap else 3 for c in plan if not c["tri"] for _, _, swap in c["images"])
+    n_b = sum(6 if swap else 3 for c in plan if c["tri"] for _, _, swap in c["images"])
+    return n_a, n_b
+
+
+def orbit_outbox_offsets(plan, bounds, rank):
+    """Python statement of cmg_orbit_outbox_layout (include/cmg.h, cmg_orbit_shard): the outbox of `rank` is compact and ordered
+    by destination; the block for rank d holds, for every combination that can address d (all for d < rank, only those of the
+    whole-face-pair classes for d > rank), the 32 x 32 sub-tiles (row half-tile of d's range) x (column tile of rank's range).
+    Returns offsets[d] in doubles, offsets[-1] = size of the outbox."""
+    n_a, n_b = orbit_combo_counts(plan)
+    nct = (bounds[rank + 1] - bounds[rank]) // ORB_SUB
+    off, at = [], 0
+    for d in range(len(bounds) - 1):
+        off.append(at)
+        if d != rank:
+            nh = (bounds[d + 1] - bounds[d]) // ORB_SUB
+            at += (n_a + (n_b if d < rank else 0)) * nct * nh * ORB_SUB * ORB_SUB
+    off.append(at)
+    return off
+
+
+def orbit_outbox_index(bounds, rank, offsets, combo, q_row, q_col):
+    """element of rank's outbox that takes (combination, row pixel index q_row outside the rank's range, column pixel index
+    q_col inside it); numpy arrays broadcast"""
+    import numpy as np
+    b = np.asarray(bounds)
+    d = np.searchsorted(b, q_row, side="right") - 1
+    nh = (b[d + 1] - b[d]) // ORB_SUB
+    nct = (bounds[rank + 1] - bounds[rank]) // ORB_SUB
+    ct = (q_col - bounds[rank]) // ORB_SUB
+    h = q_row // ORB_SUB - b[d] // ORB_SUB
+    return (np.asarray(offsets)[d] + ((combo * nct + ct) * nh + h) * (ORB_SUB * ORB_SUB) + (q_row % ORB_SUB) * ORB_SUB + (q_col % ORB_SUB))

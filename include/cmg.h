@@ -189,30 +189,54 @@ cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* d_a, int lmax, const cmg_tqu_
  * 1/3.2 without transposed images (mode 1).  Entries of different images of one orbit are bit-identical to each other; each
  * differs from cmg_tqu's by the rounding of its own n_i.n_j only (the 1e-11 gate holds with the same margin).
  * Needs cmg_set_pixels(ctx, nside >= 8, NULL, 0), 2 <= lmax <= 441, a single-owner packed buffer d_packed of dimension 3N.
- * mode 2 (NOT YET RUN ON A GPU, nothing selects it by itself) = mode 0 with the store destinations of a tile precomputed in shared
- * memory for the classes without transposed images; same classes, same storage, same results. */
+ * mode 0 computes the store destinations of a tile once into shared memory for the classes without transposed images (measured
+ * 36.2 ms against 36.8 ms per Nside = 64 matrix); mode 2 = mode 0 without that table (kept for the comparison); same classes,
+ * same storage, same results. */
 cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
                          const double* a_bb, int lmax, double* d_packed, int mode);
-/* The same over several GPUs with no data-path collective.  A rank owns the in-face index range [q_begin, q_end) of ALL
- * twelve base faces -- an orbit-closed set of pixel columns -- evaluates the source pairs whose column pixel lies there and
- * stores all their images:
+/* The same over several GPUs.  Rank r of n_ranks owns the in-face index range [bounds[r], bounds[r+1]) of ALL twelve base
+ * faces -- an orbit-closed set of pixel columns -- evaluates the source pairs whose column pixel lies there and stores all their
+ * images (no data-path collective to PRODUCE the entries):
  *   strip[s][f]   address of entry (0, s N + f nside^2 + q_begin): the packed columns s N + f nside^2 + [q_begin, q_end), one
  *                 contiguous piece of the packed triangle each (s = T, Q, U strip; f = base face);
- *   outbox[t][f]  entries whose packed column belongs to another rank (row pixel a' of the pair outside the range):
- *                 kind t = <Q_a' T_b'>, <U T>, <U Q>, and for transposed images (mode 0) <T T>, <Q Q>, <U U>, column pixel b'
- *                 in face f; dense column-major, element at outbox[t][f][a' (q_end - q_begin) + (q_b' - q_begin)], a' in [0, N).
- *                 Not touched (may be NULL) when the range is the whole face.
- * q_begin, q_end multiples of 32.  cmg_tqu_orbit_assemble places a rank's pieces (wherever they were moved to) into a whole
- * packed triangle on this GPU: parts & 1 = its strips, parts & 2 = its outbox blocks.  A strip has holes where another rank's
- * outbox holds the entry, so place the strips of ALL ranks before any outbox. */
+ *   outbox        the entries whose packed column belongs to another rank (row pixel a' of the pair outside the range; a third
+ *                 of the nine entries of such a pair), compact -- every element is written exactly once -- and ordered by
+ *                 destination rank: cmg_orbit_outbox_layout gives the offset of the block for each destination.  Inside the
+ *                 block for rank d, for every (class, image, staged kind) combination `combo` that can address d (numbered over
+ *                 the plan of cmg_tqu_orbit_plan: whole-face-pair classes first; the q_row <= q_col classes only address d < r),
+ *                 the 32 x 32 sub-tiles (row half-tile h of d's range, column tile ct of r's range), row-major:
+ *                     block[((combo nct_r + ct) nh_d + h) 1024 + (q_a' mod 32) 32 + (q_b' mod 32)].
+ *                 NULL when n_ranks == 1.
+ * bounds are multiples of 32.  To complete the strips, block(r -> d) has to reach rank d (one all-to-all over NVLink, or the
+ * receiver reads the sender's outbox through CUDA IPC) and cmg_tqu_orbit_scatter_inbox places it; after that a rank holds
+ * exactly its 36 runs of packed columns, complete.  cmg_tqu_orbit_assemble places a rank's pieces into a whole packed triangle on
+ * this GPU (tests, single-GPU assembly): parts & 1 = its strips, parts & 2 = its outbox blocks.  A strip has holes where another
+ * rank's outbox holds the entry, so place the strips of ALL ranks before any outbox. */
 typedef struct cmg_orbit_shard {
-    int64_t q_begin, q_end;
+    int32_t n_ranks, rank;
+    int64_t bounds[CMG_MAX_PARTS + 1];
     double* strip[3][12];
-    double* outbox[6][12];
+    double* outbox;
 } cmg_orbit_shard;
 cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* a_tt, const double* a_te, const double* a_ee,
                                  const double* a_bb, int lmax, const cmg_orbit_shard* shard, int mode);
+/* offsets[d], d = 0 .. n_ranks: first element (in doubles) of the block for destination d inside rank `rank`'s outbox;
+ * offsets[n_ranks] = doubles in the whole outbox (pure host arithmetic) */
+cmg_status cmg_orbit_outbox_layout(int64_t nside, int mode, int n_ranks, const int64_t* bounds, int rank, int64_t* offsets);
+/* places block(sender -> shard->rank), wherever it is now (device memory of this GPU, or peer memory of the sender mapped with
+ * cmg_ipc_open: the kernel's loads then are the transfer), into this rank's strips */
+cmg_status cmg_tqu_orbit_scatter_inbox(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, int sender, const double* d_block);
 cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, int parts, double* d_full_packed);
+/* Brings a rank's COMPLETE strips to the host as its columns of one whole packed matrix `host_packed` (dimension 3N; for several
+ * ranks on one box a shared mapping every rank writes its own columns of).  threads > 0: only the columns of base faces 3, 7, 11
+ * cross PCIe and `threads` host threads fill in this rank's columns of the other faces as rotated images while the copies are in
+ * flight (cmg_host_expand_rotations restricted to [q_begin, q_end)); threads = 0: all 36 runs are copied.  Page-locked
+ * destinations (cmg_host_register) make the copies run at PCIe speed.  Returns when the rank's columns are complete in host
+ * memory. */
+cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, double* host_packed, int threads);
+/* cudaHostRegister / cudaHostUnregister of caller-owned memory (e.g. a shared mapping) */
+cmg_status cmg_host_register(void* ptr, int64_t bytes);
+cmg_status cmg_host_unregister(void* ptr);
 /* The TT matrix of cmg_legendre_series (any series weights: clToCMatrix, getFiducialMatrix) over the same orbits, without
  * transposed images: 22.5 of the 72 face-pair units, 3.2x less recurrence work (Nside=64 lmax=192: 8.7 ms against 27.4 ms).
  * Full sky, nside >= 16, d_out = the whole packed triangle of dimension N.  cmg_cl_to_cmatrix / cmg_fiducial_matrix take this
@@ -225,15 +249,17 @@ cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, do
  * matrix has to cross PCIe; cmg_set_host_expand makes the whole calls work that way. */
 cmg_status cmg_host_expand_rotations(double* packed, int64_t nside, int strip_begin, int strip_end, int face_begin, int face_end,
                                      int threads);
-/* OPT-IN, off by default (not yet timed on the GPU box: whether host block copies beat the PCIe copy they replace depends on the
- * host): threads > 0 makes cmg_cl_to_cmatrix_pol, cmg_cl_to_cmatrix and cmg_fiducial_matrix on the full sky copy back only the
- * last-face columns and fill in the rest with
- * cmg_host_expand_rotations on `threads` host threads while the remaining copies are in flight; 0 restores the plain copy. */
+/* How the full-sky whole calls (cmg_cl_to_cmatrix_pol, cmg_cl_to_cmatrix, cmg_fiducial_matrix) bring the matrix to the host:
+ * threads > 0 = copy back only the last-face columns and fill in the rest with the host expansion on `threads` host threads while
+ * the remaining copies are in flight; 0 = one plain copy of the whole matrix; -1 (the default) = automatic: the expansion on all
+ * host cores for matrices of 1 GiB and more.  Measured for the 87 GB matrix on a 16-core host: 1.75 s plain, 1.38 s expanded
+ * (round 2, first version; profiles/README.md has the current figure). */
 cmg_status cmg_set_host_expand(cmg_ctx* ctx, int threads);
 /* the classes of base-face pairs cmg_tqu_orbit works through (host only; for tests): out[c][CMG_ORBIT_CLASS_INTS] =
  * { row face, column face, only q_row <= q_col, same face, n_images, then for image k = 0..3: row face, column face,
- *   stored transposed }; out must hold CMG_ORBIT_MAX_CLASSES classes */
-#define CMG_ORBIT_CLASS_INTS 17
+ *   stored transposed }, then for image k = 0..3 the outbox number of (this class, image k, staged kind 0) (cmg_orbit_shard);
+ * out must hold CMG_ORBIT_MAX_CLASSES classes */
+#define CMG_ORBIT_CLASS_INTS 21
 #define CMG_ORBIT_MAX_CLASSES 24
 cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* n_classes);
 /* weights from spectra and the temperature / polarization window*beam factors */

@@ -29,12 +29,16 @@ class FakeContext:
     """the methods of capi.Context that bench.py and multigpu.py call; buffers are plain host memory"""
 
     def __init__(self, device=0, stream=None):
+        self.stream_handle = None
         self.launches = 0
         self._bufs = {}
         self.npix = 0
         self.variant = 0
 
     def set_stream(self, s):
+        self.stream_handle = s
+
+    def synchronize(self):
         pass
 
     def set_pixels(self, nside, good=None):
@@ -61,7 +65,10 @@ class FakeContext:
         self.launches += 1
 
     legendre_series = legendre_series_orbit = tqu = tqu_orbit = tqu_orbit_sharded = _launch
-    cl_to_cmatrix = cl_to_cmatrix_pol = tqu_orbit_assemble = tqu_scatter_block = _launch
+    cl_to_cmatrix = cl_to_cmatrix_pol = tqu_orbit_assemble = tqu_scatter_block = tqu_orbit_scatter_inbox = tqu_batched_slab = _launch
+
+    def orbit_strips_to_host(self, shard, host, threads=0):
+        self.to_host_calls = getattr(self, "to_host_calls", 0) + 1
 
     def close(self):
         pass
@@ -97,6 +104,12 @@ def fake_gpu(monkeypatch):
         monkeypatch.setattr(dist, name, lambda *a, **k: None)
     monkeypatch.setattr(dist, "all_reduce", lambda t, op=None: None)
     monkeypatch.setattr(dist, "broadcast", lambda t, src=0: None)
+    monkeypatch.setattr(dist, "all_to_all_single", lambda out, inp, out_splits=None, in_splits=None: None)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    from cosmopp_b200 import capi
+    monkeypatch.setattr(capi, "host_register", lambda a: None)
+    monkeypatch.setattr(capi, "host_unregister", lambda a: None)
+    monkeypatch.setattr(bench, "spot_check", lambda *a, **k: 3e-14)
     monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
     monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []})
     monkeypatch.setattr(bench, "reference_sample", lambda *a, **k: {"value": 1.0, "unit": bench.UNIT, "cores": 1, "kind": "reference",
@@ -135,7 +148,8 @@ def test_single_rank_line(fake_gpu, capsys, monkeypatch, workload, extra, orbit,
     else:
         assert r["evaluated_pixel_pairs"] == r["stored_pixel_pairs_all_ranks"]
     e = line["e2e"]
-    assert e["value"] > 0 and e["d2h_bytes_per_step"] == line["config"]["packed_bytes"] and e["h2d_bytes_per_step"] > 0
+    assert e["value"] > 0 and 0 < e["d2h_bytes_per_step"] <= line["config"]["packed_bytes"] and e["h2d_bytes_per_step"] > 0
+    assert (line["parity_max_err"] == 3e-14) == (orbit and workload.startswith("tqu"))
     assert line["cpu_baseline"]["kind"] == "reference"
     ref = fake_gpu.config_dict(workload, *fake_gpu.workload_geometry(workload)[:3], line["config"]["npix"], 1)
     assert ref == line["config"]                         # the reference arm describes the same workload
@@ -148,6 +162,26 @@ def test_rank_of_several(fake_gpu, capsys, monkeypatch, extra):
     line = _run(fake_gpu, capsys, monkeypatch, argv, rank=0, world=4)
     assert line["n_gpus"] == 4 and line["cpu_baseline"] is None
     assert line["e2e"]["d2h_bytes_per_step"] > 0
+    orbit = "--no-orbit" not in extra
+    if orbit:
+        # orbit shards: exchange timed, whole matrix gathered by default, one shared host matrix every rank writes its columns of
+        assert line["exchange"]["ms"] > 0 and line["exchange"]["bytes_sent_this_rank"] > 0 and line["parity_max_err"] == 3e-14
+        assert line["gather"]["ms"] > 0 and line["e2e"]["host_matrix_max_abs_diff_vs_device"] is not None
+        # N ranks ship at most the matrix once (here: only the last-face columns)
+        assert line["e2e"]["d2h_bytes_per_step"] * 4 <= 1.05 * line["config"]["packed_bytes"]
     if "--gather" in extra:
         assert line["gather"]["ms"] > 0 and line["gather"]["bytes_per_gpu_in"] > 0
     assert ("orbit-closed" in line["path"]["sharding"]) == ("--no-orbit" not in extra)
+
+
+def test_batched_workload_line(fake_gpu, capsys, monkeypatch):
+    """BASELINE configs[3] under the driver's command line: both bounds of the ridge-point kernel in the line"""
+    import cosmopp_b200.capi as capi
+    monkeypatch.setattr(capi, "slab_doubles", lambda dim: 16 * capi.packed_size(dim))
+    monkeypatch.setitem(fake_gpu.WORKLOADS, "batched_x1024_tqu_nside16_lmax47", ("batched", 4, 8, 40))       # small stand-in shape
+    monkeypatch.setattr(fake_gpu, "run_batched_arm", fake_gpu.run_batched_arm)
+    line = _run(fake_gpu, capsys, monkeypatch, ["--workload", "batched_x1024_tqu_nside16_lmax47", "--steps", "2", "--warmup", "3", "--no-e2e"])
+    for k in REQUIRED:
+        assert k in line, k
+    assert line["config"]["n_batch"] == 40 and line["roofline"]["algorithmic_flop_per_unit"] == 8.0 and line["roofline"]["hbm_write_gbs"] > 0
+    assert line["gpu_launches"] == 2 and "element" in line["unit"]

@@ -29,7 +29,7 @@ def _inputs(ctx, nside, lmax):
 
 
 @pytest.mark.parametrize("nside,lmax", [(8, 20), (16, 47)])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_orbit_matches_oracle(gpu_ctx, oracle_api, nside, lmax, mode):
     import torch
     from cosmopp_b200 import capi
@@ -74,6 +74,45 @@ def test_orbit_shards_assemble_to_the_whole_matrix(gpu_ctx, oracle_api, world, m
     assert not np.isnan(got).any()
     want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
     assert (np.abs(got - want) / _scale(n, want)).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("world,mode,threads", [(2, 0, 0), (3, 0, 3), (3, 1, 2), (4, 2, 0)])
+def test_orbit_exchange_completes_the_strips(gpu_ctx, oracle_api, world, mode, threads):
+    """The exchange step with every rank on this one GPU: block(r -> d) of r's outbox is placed into d's strips by
+    cmg_tqu_orbit_scatter_inbox, after which the strips alone are the matrix -- on the device (assembly of the strips only) and
+    on the host (cmg_orbit_strips_to_host into one whole packed matrix, plain or with the host filling in the rotated images)."""
+    import torch
+    from cosmopp_b200 import capi, multigpu
+    nside, lmax = 16, 30
+    spectra, w = _inputs(gpu_ctx, nside, lmax)
+    n = gpu_ctx.npix
+    ranks = [multigpu.OrbitShardedTQU(gpu_ctx, nside, r, world, mode) for r in range(world)]
+    for r in ranks:
+        for b in r.pieces():
+            b.tensor().fill_(float("nan"))
+        r.generate(w)
+    for d in ranks:
+        for s in ranks:
+            if s.rank != d.rank and d.recv_counts[s.rank]:
+                assert d.recv_counts[s.rank] == s.send_counts[d.rank]
+                gpu_ctx.tqu_orbit_scatter_inbox(d.shard, s.rank, s.outbox.ptr + 8 * s.layouts[s.rank][d.rank], mode)
+    full = torch.full((capi.packed_size(3 * n),), float("nan"), dtype=torch.float64, device="cuda")
+    host = torch.full((capi.packed_size(3 * n),), float("nan"), dtype=torch.float64).pin_memory()
+    for r in ranks:
+        r.assemble_into(full, 1)                        # strips only
+        r.to_host(host, threads)
+    torch.cuda.synchronize()
+    got = full.cpu().numpy()
+    for r in ranks:
+        r.close()
+    assert not np.isnan(got).any()
+    want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
+    assert (np.abs(got - want) / _scale(n, want)).max() <= REL_TOL
+    got_host = host.numpy()
+    assert not np.isnan(got_host).any()
+    if threads == 0:
+        assert np.array_equal(got_host, got)
+    assert (np.abs(got_host - want) / _scale(n, want)).max() <= REL_TOL
 
 
 def test_whole_call_takes_the_orbit_path_on_the_full_sky(gpu_ctx, oracle_api):

@@ -59,20 +59,24 @@ def test_plan_covers_every_face_pair_once(mode):
     assert units == (18.0 if mode == 0 else 22.5)                                  # of 72 face-pair units
 
 
-def emulate_kernel_stores(plan, nside, n, M, q0=0, q1=None):
-    """What tquOrbitKernel stores for the rank owning the in-face columns [q0, q1), entry by entry, taking the nine values
-    of a source pair from M.  Returns the values and store counts per packed position for the rank's own strips and for its
-    outbox (already translated to packed positions, as orbitOutboxScatterKernel does), and the store count per outbox slot."""
+def emulate_kernel_stores(plan, nside, n, M, bounds=None, rank=0):
+    """What tquOrbitKernel stores for rank `rank` of the partition `bounds` (in-face column ranges), entry by entry, taking the
+    nine values of a source pair from M.  Returns the values and store counts per packed position for the rank's own strips, the
+    rank's outbox (values + store count per element, laid out as cmg_orbit_shard says) and, per outbox element, the packed
+    position it belongs to (what orbitInboxScatterKernel computes on the receiving side)."""
+    from cosmopp_b200 import partition
     F = nside * nside
-    q1 = F if q1 is None else q1
+    bounds = [0, F] if bounds is None else list(bounds)
+    q0, q1 = bounds[rank], bounds[rank + 1]
+    offsets = partition.orbit_outbox_offsets(plan, bounds, rank)
     ld = q1 - q0
     dim = 3 * n
     size = capi.packed_size(dim)
     out = np.full(size, np.nan)
     count = np.zeros(size, dtype=np.int32)
-    box_out = np.full(size, np.nan)
-    box_count = np.zeros(size, dtype=np.int32)
-    slot_count = np.zeros((6, 12, n, max(ld, 1)), dtype=np.int8)
+    box_out = np.full(offsets[-1], np.nan)
+    box_count = np.zeros(offsets[-1], dtype=np.int32)
+    box_pos = np.full(offsets[-1], -1, dtype=np.int64)
 
     def po(col):
         return col * (col + 1) // 2
@@ -89,6 +93,7 @@ def emulate_kernel_stores(plan, nside, n, M, q0=0, q1=None):
     il = np.arange(TI)[:, None]
     jl = np.arange(TJ)[None, :]
     for c in plan:
+        kinds_before = 0
         for tr in range(F // TI):
             for tc in range(ld // TJ):
                 q_row0, q_col0 = tr * TI, q0 + tc * TJ
@@ -98,7 +103,7 @@ def emulate_kernel_stores(plan, nside, n, M, q0=0, q1=None):
                 b = c["col_face"] * F + q_col0 + jl + 0 * il
                 dq = (q_col0 + jl) - (q_row0 + il)
                 v = {(X, Y): M[X * n + a, Y * n + b] for X in range(3) for Y in range(3)}
-                for fr, fc, swap in c["images"]:
+                for k, (fr, fc, swap) in enumerate(c["images"]):
                     ip = fr * F + q_row0 + il + 0 * jl
                     jp = fc * F + q_col0 + jl + 0 * il
                     cols = [s * n + jp for s in range(3)]
@@ -125,10 +130,39 @@ def emulate_kernel_stores(plan, nside, n, M, q0=0, q1=None):
                         pos = po(X * n + ip) + Y * n + jp
                         put(pos, X * n + ip, v[X, Y], live & local)
                         far = live & ~local
-                        np.add.at(box_count, pos[far], 1)
-                        box_out[pos[far]] = v[X, Y][far]
-                        np.add.at(slot_count, (t, fc, ip[far], (q_col0 - q0 + jl + 0 * il)[far]), 1)
-    return out, count, box_out, box_count, slot_count
+                        if far.any():
+                            e = partition.orbit_outbox_index(bounds, rank, offsets, c["combo_base"][k] + t, qa[far], (q_col0 + jl + 0 * il)[far])
+                            np.add.at(box_count, e, 1)
+                            box_out[e] = v[X, Y][far]
+                            box_pos[e] = pos[far]
+    return out, count, box_out, box_count, box_pos
+
+
+def emulate_inbox_scatter(plan, nside, n, bounds, sender, receiver, block):
+    """orbitInboxScatterKernel: packed position of every element of block(sender -> receiver), from the layout alone"""
+    from cosmopp_b200 import partition
+    F = nside * nside
+    S = partition.ORB_SUB
+    nct = (bounds[sender + 1] - bounds[sender]) // S
+    h0, nh = bounds[receiver] // S, (bounds[receiver + 1] - bounds[receiver]) // S
+    pos = np.full(block.size, -1, dtype=np.int64)
+    X_of, Y_of = [1, 2, 2, 0, 1, 2], [0, 0, 1, 0, 1, 2]
+    r = np.arange(S)[:, None] + 0 * np.arange(S)[None, :]
+    l = np.arange(S)[None, :] + 0 * np.arange(S)[:, None]
+    for c in plan:
+        if c["tri"] and not receiver < sender:
+            continue
+        for k, (fr, fc, swap) in enumerate(c["images"]):
+            for t in range(6 if swap else 3):
+                combo = c["combo_base"][k] + t
+                for ct in range(nct):
+                    for hh in range(nh):
+                        a = fr * F + (h0 + hh) * S + r
+                        b = fc * F + bounds[sender] + ct * S + l
+                        col = X_of[t] * n + a
+                        e = ((combo * nct + ct) * nh + hh) * S * S + r * S + l
+                        pos[e] = col * (col + 1) // 2 + Y_of[t] * n + b
+    return pos
 
 
 def packed_from_full(M):
@@ -143,7 +177,7 @@ def packed_from_full(M):
 def test_store_rules_fill_the_packed_triangle_exactly_once(oracle_matrix, mode):
     nside, n, M = oracle_matrix
     out, count, _, box_count, _ = emulate_kernel_stores(capi.orbit_plan(nside, mode), nside, n, M)
-    assert count.min() == 1 and count.max() == 1 and box_count.max() == 0
+    assert count.min() == 1 and count.max() == 1 and box_count.size == 0
     want, iu = packed_from_full(M)
     # images take the source pair's value: equal to the oracle's own entry up to the oracle's rounding
     scale = np.empty_like(want)
@@ -151,41 +185,52 @@ def test_store_rules_fill_the_packed_triangle_exactly_once(oracle_matrix, mode):
     assert (np.abs(out - want) / scale).max() < 1e-11
 
 
-@pytest.mark.parametrize("mode,world", [(0, 2), (1, 2), (0, 3)])
-def test_sharded_store_rules_partition_the_triangle(oracle_matrix, mode, world):
-    """Ranks own in-face column ranges of all twelve faces: together their strips and outbox blocks hold every entry once,
-    strip stores stay inside the rank's own packed columns, and no outbox slot is written twice."""
+def check_sharded_store_rules(nside, n, M, mode, world, values=True):
+    """Ranks own in-face column ranges of all twelve faces: together their strips and outboxes hold every entry once, strip
+    stores stay inside the rank's own packed columns, every element of every (compact) outbox is written exactly once, and the
+    receiver-side scatter puts each destination block where the sender's stores belong -- inside the receiver's columns."""
     from cosmopp_b200 import partition
-    nside, n, M = oracle_matrix
+    F = nside * nside
     plan = capi.orbit_plan(nside, mode)
     bounds = partition.orbit_partition(nside, world, mode)
-    assert bounds[0] == 0 and bounds[-1] == nside * nside and all(b % 32 == 0 for b in bounds)
-    want, _ = packed_from_full(M)
-    total = np.zeros(want.size, dtype=np.int32)
-    merged = np.full(want.size, np.nan)
+    assert bounds[0] == 0 and bounds[-1] == F and all(b % 32 == 0 for b in bounds)
+    size = capi.packed_size(3 * n)
+    total = np.zeros(size, dtype=np.int32)
+    merged = np.full(size, np.nan)
     pairs = 0
     for r in range(world):
-        out, count, box_out, box_count, slot_count = emulate_kernel_stores(plan, nside, n, M, bounds[r], bounds[r + 1])
-        assert slot_count.max() <= 1
-        assert slot_count.sum() == box_count.sum()
-        # the rank allocates, of every outbox block, only the row-pixel faces the block is ever addressed with
-        blocks = {(t, f): (lo, hi) for t, f, lo, hi in partition.orbit_outbox_blocks(plan)}
-        F = nside * nside
-        for t in range(6):
-            for f in range(12):
-                rows = np.nonzero(slot_count[t, f].any(axis=1))[0]
-                if len(rows):
-                    lo, hi = blocks[(t, f)]
-                    assert lo * F <= rows.min() and rows.max() < hi * F
-        total += count + box_count
+        out, count, box_out, box_count, box_pos = emulate_kernel_stores(plan, nside, n, M, bounds, r)
+        offsets = partition.orbit_outbox_offsets(plan, bounds, r)
+        assert offsets == capi.orbit_outbox_layout(nside, mode, bounds, r)
+        assert box_count.size == offsets[-1] and (box_count.size == 0 or (box_count.min() == 1 and box_count.max() == 1))
+        for d in range(world):
+            if d == r:
+                assert offsets[d + 1] == offsets[d]
+                continue
+            pos = emulate_inbox_scatter(plan, nside, n, bounds, r, d, box_out[offsets[d]:offsets[d + 1]])
+            assert (pos == box_pos[offsets[d]:offsets[d + 1]]).all()
+            # the packed column of every element of the block is one of rank d's
+            col = np.floor((np.sqrt(8.0 * pos + 1) - 1) / 2).astype(np.int64)
+            col -= (col * (col + 1) // 2 > pos)
+            q = (col % n) % F
+            assert ((q >= bounds[d]) & (q < bounds[d + 1])).all()
+        total += count
+        np.add.at(total, box_pos, 1)
         merged = np.where(count > 0, out, merged)
-        merged = np.where(box_count > 0, box_out, merged)
-        pairs += partition.orbit_pairs_in_range(bounds[r], bounds[r + 1], nside * nside, mode)
+        merged[box_pos] = box_out
+        pairs += partition.orbit_pairs_in_range(bounds[r], bounds[r + 1], F, mode)
     assert total.min() == 1 and total.max() == 1
-    assert np.abs(merged - want).max() < 1e-11 * M[n, n]
+    if values:
+        want, _ = packed_from_full(M)
+        assert np.abs(merged - want).max() < 1e-11 * M[n, n]
     units = 18.0 if mode == 0 else 22.5
-    f = nside * nside
-    assert abs(pairs - units * f * f) <= 6 * f          # the q_row <= q_col classes include their diagonal
+    assert abs(pairs - units * F * F) <= 6 * F          # the q_row <= q_col classes include their diagonal
+
+
+@pytest.mark.parametrize("mode,world", [(0, 2), (1, 2), (0, 3)])
+def test_sharded_store_rules_partition_the_triangle(oracle_matrix, mode, world):
+    nside, n, M = oracle_matrix
+    check_sharded_store_rules(nside, n, M, mode, world)
 
 
 def test_tt_orbit_store_rules_fill_the_triangle_exactly_once():
@@ -298,23 +343,6 @@ def oracle_matrix16():
 
 @pytest.mark.parametrize("world,mode", [(2, 0), (3, 0), (3, 1)])
 def test_sharded_store_rules_at_the_gpu_test_sizes(oracle_matrix16, world, mode):
-    """the configurations tests/test_gpu_orbit.py runs on the device (Nside=16): every entry once, every outbox store inside the
-    row faces the rank allocates for that block"""
-    from cosmopp_b200 import partition
+    """the configurations tests/test_gpu_orbit.py runs on the device (Nside=16)"""
     nside, n, M = oracle_matrix16
-    F = nside * nside
-    plan = capi.orbit_plan(nside, mode)
-    bounds = partition.orbit_partition(nside, world, mode)
-    blocks = {(t, f): (lo, hi) for t, f, lo, hi in partition.orbit_outbox_blocks(plan)}
-    total = None
-    for r in range(world):
-        _, count, _, box_count, slot_count = emulate_kernel_stores(plan, nside, n, M, bounds[r], bounds[r + 1])
-        assert slot_count.max() <= 1
-        for t in range(6):
-            for f in range(12):
-                rows = np.nonzero(slot_count[t, f].any(axis=1))[0]
-                if len(rows):
-                    lo, hi = blocks[(t, f)]
-                    assert lo * F <= rows.min() and rows.max() < hi * F
-        total = count + box_count if total is None else total + count + box_count
-    assert total.min() == 1 and total.max() == 1
+    check_sharded_store_rules(nside, n, M, mode, world)

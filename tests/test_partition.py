@@ -168,7 +168,8 @@ class _FakeCtx:
 @pytest.mark.parametrize("world,mode", [(1, 0), (2, 0), (3, 1)])
 def test_orbit_shard_descriptor_layout(world, mode):
     """OrbitShardedTQU: the 36 strips are laid out back to back in (strip, face) order = ascending packed columns, the outbox
-    blocks follow the plan's (kind, face) list; with one rank the strips buffer IS the packed triangle."""
+    is one compact buffer of the size cmg_orbit_outbox_layout states, and the send / receive counts of the exchange agree
+    between every pair of ranks; with one rank the strips buffer IS the packed triangle."""
     from cosmopp_b200 import capi, multigpu
     nside = 16
     f, n = nside * nside, 12 * nside * nside
@@ -176,7 +177,7 @@ def test_orbit_shard_descriptor_layout(world, mode):
         ctx = _FakeCtx()
         sh = multigpu.OrbitShardedTQU(ctx, nside, rank, world, mode)
         q0, q1 = sh.q0, sh.q1
-        assert (sh.shard.q_begin, sh.shard.q_end) == (q0, q1)
+        assert (sh.shard.n_ranks, sh.shard.rank) == (world, rank) and [sh.shard.bounds[k] for k in range(world + 1)] == sh.bounds
         sizes = partition.orbit_strip_sizes(nside, q0, q1)
         off = 0
         for s in range(3):
@@ -189,23 +190,22 @@ def test_orbit_shard_descriptor_layout(world, mode):
             for s in range(3):                     # single owner: strip (s, face) starts at its packed offset
                 for face in range(12):
                     assert sh.shard.strip[s][face] == sh.strips.ptr + 8 * partition.packed_size(s * n + face * f)
-            assert all(sh.shard.outbox[t][face] is None for t in range(6) for face in range(12))
+            assert sh.shard.outbox is None and sh.send_counts == [0] and sh.recv_counts == [0]
         else:
-            blocks = partition.orbit_outbox_blocks(capi.orbit_plan(nside, mode))
-            assert len(blocks) == (54 if mode == 0 else 36)
-            assert [(t, face) for t, face, _, _ in blocks] == partition.orbit_outbox_kinds(capi.orbit_plan(nside, mode))
-            per_face = f * (q1 - q0)
-            off = 0
-            for t, face, lo, hi in blocks:
-                assert 0 <= lo < hi <= 12
-                # the pointer is that of (virtual) row pixel 0: rows of faces [lo, hi) land inside the allocation, back to back
-                assert sh.shard.outbox[t][face] + 8 * lo * per_face == sh.outbox.ptr + 8 * off
-                off += (hi - lo) * per_face
-            assert sh.outbox.n == off and off < 0.55 * 54 * n * (q1 - q0)       # about half of 54 whole blocks (mode 0)
-            unused = [(t, face) for t in range(6) for face in range(12) if (t, face) not in [(b[0], b[1]) for b in blocks]]
-            assert all(sh.shard.outbox[t][face] is None for t, face in unused)
+            plan = capi.orbit_plan(nside, mode)
+            offsets = partition.orbit_outbox_offsets(plan, sh.bounds, rank)
+            assert sh.layouts[rank] == offsets and sh.outbox.n == offsets[-1] and sh.shard.outbox == sh.outbox.ptr
+            assert sh.send_counts == [offsets[d + 1] - offsets[d] for d in range(world)] and sh.send_counts[rank] == 0
+            # what this rank expects from r is what r's layout says it sends here
+            for r in range(world):
+                other = partition.orbit_outbox_offsets(plan, sh.bounds, r)
+                assert sh.recv_counts[r] == (0 if r == rank else other[rank + 1] - other[rank])
+            # all ranks together: strips (with holes) + outboxes = the matrix's entries once, i.e. the outboxes are exactly the
+            # entries missing from the strips: a third of the entries of the pairs whose row pixel lies outside the column's range
+            n_a, n_b = partition.orbit_combo_counts(plan)
+            assert (n_a, n_b) == ((189, 90) if mode == 0 else (198, 36))
         assert sh.sizes_of(rank) == (sh.strips.n, sh.outbox.n if sh.outbox is not None else 0)
         other = sh.shard_of(rank, 0x5000, 0x9000 if world > 1 else 0)
-        assert other.strip[0][0] == 0x5000 and (world == 1 or other.outbox[0][0] is not None)
+        assert other.strip[0][0] == 0x5000 and (world == 1 or other.outbox == 0x9000)
         sh.close()
         assert not ctx.live

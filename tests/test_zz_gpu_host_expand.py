@@ -27,7 +27,7 @@ def test_whole_calls_with_host_expansion_match_the_oracle(gpu_ctx, oracle_api, n
         tt = torch.full((capi.packed_size(n),), float("nan"), dtype=torch.float64).pin_memory()
         gpu_ctx.cl_to_cmatrix(spectra[0], 10.0, tt)
     finally:
-        gpu_ctx.set_host_expand(0)
+        gpu_ctx.set_host_expand(-1)
     want = oracle_api.tqu_matrix(*spectra, nside, 10.0)
     scale = np.full(want.shape, want[capi.packed_index(n, n)])
     scale[:capi.packed_size(n)] = want[0]

@@ -40,6 +40,46 @@ static void weights(int lmax, std::vector<double>& tt, std::vector<double>& te, 
     }
 }
 
+// a rank's shard over freshly allocated strips + compact outbox (cmg_orbit_shard, include/cmg.h); mode fixes the outbox size
+static int makeShard(cmg_ctx* ctx, int nside, int mode, const std::vector<int64_t>& b, int r, cmg_orbit_shard& sh, double*& dStrips, double*& dBox,
+                     int64_t& stripDoubles, int64_t& boxDoubles, bool poison)
+{
+    const int64_t F = (int64_t) nside * nside, n = 12 * F;
+    const int world = (int) b.size() - 1;
+    std::memset(&sh, 0, sizeof(sh));
+    sh.n_ranks = world;
+    sh.rank = r;
+    for(int k = 0; k <= world; ++k) sh.bounds[k] = b[k];
+    stripDoubles = 0;
+    for(int st = 0; st < 3; ++st)
+        for(int f = 0; f < 12; ++f)
+            stripDoubles += cmg_packed_size(st * n + f * F + b[r + 1]) - cmg_packed_size(st * n + f * F + b[r]);
+    int64_t off[CMG_MAX_PARTS + 1];
+    if(cmg_orbit_outbox_layout(nside, mode, world, b.data(), r, off) != CMG_OK) return 1;
+    boxDoubles = off[world];
+    int64_t other[CMG_MAX_PARTS + 1];             // callers may run several modes over one shard: size the buffer for the larger layout
+    if(cmg_orbit_outbox_layout(nside, mode == 1 ? 0 : 1, world, b.data(), r, other) != CMG_OK) return 1;
+    const int64_t boxAlloc = std::max(boxDoubles, other[world]);
+    dStrips = dBox = nullptr;
+    if(cmg_device_malloc(ctx, std::max<int64_t>(stripDoubles, 1) * 8, (void**) &dStrips) != CMG_OK) return 1;
+    if(cmg_device_malloc(ctx, std::max<int64_t>(boxAlloc, 1) * 8, (void**) &dBox) != CMG_OK) return 1;
+    if(poison)
+    {
+        cudaMemset(dStrips, 0xFF, stripDoubles * 8);
+        cudaMemset(dBox, 0xFF, std::max<int64_t>(boxAlloc, 1) * 8);
+        cudaDeviceSynchronize();
+    }
+    int64_t at = 0;
+    for(int st = 0; st < 3; ++st)
+        for(int f = 0; f < 12; ++f)
+        {
+            sh.strip[st][f] = dStrips + at;
+            at += cmg_packed_size(st * n + f * F + b[r + 1]) - cmg_packed_size(st * n + f * F + b[r]);
+        }
+    sh.outbox = boxAlloc ? dBox : nullptr;
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     // modes: tt = parity + timing of the TT orbit kernel; full (default) = all parity checks + timings; ranks = per-rank timings of the balanced 2/4/8-way partitions at
@@ -153,29 +193,9 @@ int main(int argc, char** argv)
             for(int r = 0; r < world; ++r)
             {
                 cmg_orbit_shard sh;
-                std::memset(&sh, 0, sizeof(sh));
-                sh.q_begin = b[r];
-                sh.q_end = b[r + 1];
-                const int64_t ld = sh.q_end - sh.q_begin;
-                int64_t stripDoubles = 0;
-                for(int st = 0; st < 3; ++st)
-                    for(int f = 0; f < 12; ++f)
-                        stripDoubles += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
                 double *dStrips = nullptr, *dBox = nullptr;
-                OK(cmg_device_malloc(ctx, stripDoubles * 8, (void**) &dStrips));
-                OK(cmg_device_malloc(ctx, 54 * n * ld * 8, (void**) &dBox));
-                int64_t off = 0;
-                for(int st = 0; st < 3; ++st)
-                    for(int f = 0; f < 12; ++f)
-                    {
-                        sh.strip[st][f] = dStrips + off;
-                        off += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
-                    }
-                int blk = 0;                                   // kinds 0..2 for every face, 3..5 for positions 0 and 1 of a ring
-                for(int t = 0; t < 6; ++t)
-                    for(int f = 0; f < 12; ++f)
-                        if(t < 3 || (f & 3) < 2)
-                            sh.outbox[t][f] = dBox + (blk++) * n * ld;
+                int64_t stripDoubles = 0, boxDoubles = 0;
+                if(makeShard(ctx, nside, 0, b, r, sh, dStrips, dBox, stripDoubles, boxDoubles, false)) return 1;
                 double best = 1e30;
                 for(int rep = 0; rep < 3; ++rep)
                 {
@@ -185,7 +205,8 @@ int main(int argc, char** argv)
                 }
                 worst = std::max(worst, best);
                 sum += best;
-                std::printf("  world %d rank %d: q [%lld, %lld): %.3f ms\n", world, r, (long long) sh.q_begin, (long long) sh.q_end, best);
+                std::printf("  world %d rank %d: q [%lld, %lld): %.3f ms, strips %.2f GB, outbox %.2f GB\n", world, r, (long long) b[r], (long long) b[r + 1], best,
+                            stripDoubles * 8e-9, boxDoubles * 8e-9);
                 OK(cmg_device_free(ctx, dStrips));
                 OK(cmg_device_free(ctx, dBox));
             }
@@ -271,36 +292,17 @@ int main(int argc, char** argv)
             double msMax = 0;
             std::vector<cmg_orbit_shard> shards(world);
             std::vector<double*> bufs;
+            std::vector<int64_t> bnd(world + 1);
+            for(int r = 0; r <= world; ++r)
+                bnd[r] = r == world ? F : (F * r / world) / 32 * 32;
             for(int r = 0; r < world; ++r)
             {
-                cmg_orbit_shard& sh = shards[r];
-                std::memset(&sh, 0, sizeof(sh));
-                sh.q_begin = (F * r / world) / 32 * 32;
-                sh.q_end = r + 1 == world ? F : (F * (r + 1) / world) / 32 * 32;
-                const int64_t ld = sh.q_end - sh.q_begin;
-                int64_t stripDoubles = 0;
-                for(int st = 0; st < 3; ++st)
-                    for(int f = 0; f < 12; ++f)
-                        stripDoubles += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
                 double *dStrips = nullptr, *dBox = nullptr;
-                OK(cmg_device_malloc(ctx, stripDoubles * 8, (void**) &dStrips));
-                OK(cmg_device_malloc(ctx, 72 * n * ld * 8, (void**) &dBox));
+                int64_t stripDoubles = 0, boxDoubles = 0;
+                if(makeShard(ctx, nside, mode, bnd, r, shards[r], dStrips, dBox, stripDoubles, boxDoubles, true)) return 1;
                 bufs.push_back(dStrips);
                 bufs.push_back(dBox);
-                cudaMemset(dStrips, 0xFF, stripDoubles * 8);
-                cudaMemset(dBox, 0xFF, 72 * n * ld * 8);
-                int64_t off = 0;
-                for(int st = 0; st < 3; ++st)
-                    for(int f = 0; f < 12; ++f)
-                    {
-                        sh.strip[st][f] = dStrips + off;
-                        off += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
-                    }
-                for(int t = 0; t < 6; ++t)
-                    for(int f = 0; f < 12; ++f)
-                        sh.outbox[t][f] = dBox + (t * 12 + f) * n * ld;
-                cudaDeviceSynchronize();
-                OK(cmg_tqu_orbit_sharded(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, &sh, mode));
+                OK(cmg_tqu_orbit_sharded(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, &shards[r], mode));
                 double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
                 msMax = std::max(msMax, ms);
             }
@@ -338,27 +340,12 @@ int main(int argc, char** argv)
         for(int r = 0; r < world; r += world - 1)
         {
             cmg_orbit_shard sh;
-            std::memset(&sh, 0, sizeof(sh));
-            sh.q_begin = F * r / world;
-            sh.q_end = F * (r + 1) / world;
-            const int64_t ld = sh.q_end - sh.q_begin;
-            int64_t stripDoubles = 0;
-            for(int st = 0; st < 3; ++st)
-                for(int f = 0; f < 12; ++f)
-                    stripDoubles += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
+            std::vector<int64_t> bnd(world + 1);
+            for(int k = 0; k <= world; ++k)
+                bnd[k] = F * k / world;
             double *dStrips = nullptr, *dBox = nullptr;
-            OK(cmg_device_malloc(ctx, stripDoubles * 8, (void**) &dStrips));
-            OK(cmg_device_malloc(ctx, 72 * n * ld * 8, (void**) &dBox));
-            int64_t off = 0;
-            for(int st = 0; st < 3; ++st)
-                for(int f = 0; f < 12; ++f)
-                {
-                    sh.strip[st][f] = dStrips + off;
-                    off += cmg_packed_size(st * n + f * F + sh.q_end) - cmg_packed_size(st * n + f * F + sh.q_begin);
-                }
-            for(int t = 0; t < 6; ++t)
-                for(int f = 0; f < 12; ++f)
-                    sh.outbox[t][f] = dBox + (t * 12 + f) * n * ld;
+            int64_t stripDoubles = 0, boxDoubles = 0;
+            if(makeShard(ctx, nside, 0, bnd, r, sh, dStrips, dBox, stripDoubles, boxDoubles, false)) return 1;
             for(int mode = 2; mode >= 0; --mode)
             {
                 double best = 1e30;
@@ -368,7 +355,7 @@ int main(int argc, char** argv)
                     double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
                     best = std::min(best, ms);
                 }
-                std::printf("nside 64 lmax 192, rank %d of 8 (equal q ranges), mode %d: %.2f ms, strips %.2f GB\n", r, mode, best, stripDoubles * 8e-9);
+                std::printf("nside 64 lmax 192, rank %d of 8 (equal q ranges), mode %d: %.2f ms, strips %.2f GB, outbox %.2f GB\n", r, mode, best, stripDoubles * 8e-9, boxDoubles * 8e-9);
             }
             OK(cmg_device_free(ctx, dStrips));
             OK(cmg_device_free(ctx, dBox));

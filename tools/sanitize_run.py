@@ -69,7 +69,7 @@ ctx.set_pixels(16); n16 = ctx.npix
 f16 = capi.window_beam(20, 10.0)
 w16 = capi.tqu_weights(*synthetic_cl(20, pol=True), f16, f16)
 full16 = torch.empty(capi.packed_size(3 * n16), dtype=torch.float64, device="cuda")
-for mode in (0, 1):
+for mode in (0, 1, 2):
     ctx.tqu_orbit(*w16, full16, mode)
     ranks = [multigpu.OrbitShardedTQU(ctx, 16, r, 3, mode) for r in range(3)]
     for rk in ranks:
@@ -77,6 +77,13 @@ for mode in (0, 1):
     for parts in (1, 2):
         for rk in ranks:
             rk.assemble_into(full16, parts)
+    # the exchange step: block(sender -> receiver) of the compact outboxes into the receivers' strips, strips to the host
+    host16 = torch.empty(capi.packed_size(3 * n16), dtype=torch.float64).pin_memory()
+    for d in ranks:
+        for sd in ranks:
+            if sd.rank != d.rank and d.recv_counts[sd.rank]:
+                ctx.tqu_orbit_scatter_inbox(d.shard, sd.rank, sd.outbox.ptr + 8 * sd.layouts[sd.rank][d.rank], mode)
+        d.to_host(host16, 2)
     torch.cuda.synchronize()
     for rk in ranks:
         rk.close()
