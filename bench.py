@@ -522,8 +522,22 @@ def run_gpu_arm(args):
         barrier()
         gms = max_over_ranks(g0.elapsed_time(g1))
         inbound = 8 * capi.packed_size(3 * npix) - strip_bytes
+        gather_err = None
+        if orbit_sharded and args.spot_check > 0:
+            # the gathered matrix on this GPU, anywhere in the triangle (mostly other ranks' columns), against the CPU oracle
+            from oracle import api
+            rs = np.random.RandomState(4242 + rank)
+            m = max(1, args.spot_check // 5)
+            col = rs.randint(0, 3 * npix, m)
+            row = (rs.random_sample(m) * (col + 1)).astype(np.int64)
+            got = full[torch.from_numpy(col * (col + 1) // 2 + row).cuda()].cpu().numpy()
+            blocks = api.tqu_pairs(*spectra, nside, FWHM, row % npix, col % npix)
+            diag = api.tqu_pairs(*spectra, nside, FWHM, np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int64))[0]
+            want = blocks[np.arange(m), row // npix, col // npix]
+            gather_err = max_over_ranks(float((np.abs(got - want) / np.where(col // npix == 0, diag[0, 0], diag[1, 1])).max()))
         if orbit_sharded:
             gather = {"ms": gms, "bytes_per_gpu_in": inbound, "gbs_in_per_gpu": inbound / (gms * 1e-3) / 1e9, "nvlink_gbs_per_direction": 900.0,
+                      "parity_max_err": gather_err,
                       "how": "after the exchange every strip is a complete contiguous piece of the packed triangle: one ncclBroadcast each, straight into place"}
         else:
             gather = {"ms": gms, "bytes_per_gpu_in": 8 * (capi.packed_size(3 * npix) - sum(sharded.plan["strips"])),
@@ -548,9 +562,11 @@ def run_gpu_arm(args):
             spectra_pinned = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in spectra]
             step = lambda: ctx.cl_to_cmatrix_pol(*[s.numpy() for s in spectra_pinned], FWHM, host)      # reference-facing whole call
             if good is None and args.host_expand != 0 and host.numel() * 8 >= (1 << 30):
-                d2h_bytes = 8 * sum(partition.packed_size(s * npix + (fc + 1) * nside * nside) - partition.packed_size(s * npix + fc * nside * nside)
-                                    for s in range(3) for fc in (3, 7, 11))
-                note += "; only the columns of base faces 3, 7, 11 cross PCIe, host threads fill in the rotated images (cmg_set_host_expand)"
+                F = nside * nside
+                d2h_bytes = 8 * sum(partition.packed_size(s * npix + (fc + 1) * F) - partition.packed_size(s * npix + fc * F)
+                                    for s in range(3) for fc in range(12) if (fc & 3) == 3 or (s == 2 and (fc & 3) == 2))
+                note += ("; only the columns of base faces 3, 7, 11 (and, third strip, of faces 2, 6, 10) cross PCIe, host threads fill in "
+                         "the other rotated images (cmg_set_host_expand, cmg_set_host_expand_direct)")
         elif kind == "tt" and world == 1:
             del shard, pieces
             torch.cuda.empty_cache()
@@ -575,21 +591,24 @@ def run_gpu_arm(args):
                     torch.cuda.synchronize()
             else:
                 F = nside * nside
-                faces = (3, 7, 11) if threads > 0 else range(12)
-                for s in range(3):
-                    for fc in faces:
-                        first = partition.packed_size(s * npix + fc * F + sharded.q0)
-                        shared.register(first, partition.packed_size(s * npix + fc * F + sharded.q1) - first)
-                d2h_bytes = 8 * sum(partition.packed_size(s * npix + fc * F + sharded.q1) - partition.packed_size(s * npix + fc * F + sharded.q0)
-                                    for s in range(3) for fc in faces)
-                note = ("every rank: generation + exchange, then its own packed columns of ONE host matrix in shared memory (%s): "
-                        % ("columns of base faces 3, 7, 11 over PCIe, rotated images filled in by %d host threads per rank" % threads
-                           if threads > 0 else "all 36 runs of packed columns copied"))
+                direct = (0x49 if args.direct_mask < 0 else args.direct_mask) if threads > 0 else 0
+                # (strip, face) runs of this rank's columns that cross PCIe: the last face of every ring, plus the direct images
+                runs = [(s, fc) for s in range(3) for fc in range(12)
+                        if threads == 0 or (fc & 3) == 3 or ((direct >> (3 * s + (3 - (fc & 3)) - 1)) & 1)]
+                d2h_bytes = 0
+                for s, fc in runs:
+                    first = partition.packed_size(s * npix + fc * F + sharded.q0)
+                    count = partition.packed_size(s * npix + fc * F + sharded.q1) - first
+                    shared.register(first, count)
+                    d2h_bytes += 8 * count
+                note = ("every rank: generation + exchange, then its own packed columns of ONE host matrix in shared memory (%s)"
+                        % ("columns of base faces 3, 7, 11 and the images of mask 0x%x over PCIe, the other rotated images filled in by %d host "
+                           "threads per rank" % (direct, threads) if threads > 0 else "all 36 runs of packed columns copied"))
 
                 def step():
                     launch()
                     sharded.exchange()
-                    sharded.to_host(shared.array, threads)
+                    sharded.to_host(shared.array, threads, direct)
         else:
             hosts = [torch.empty(p.numel(), dtype=torch.float64, pin_memory=True) for p in pieces]
 
@@ -775,7 +794,10 @@ def main():
     ap.add_argument("--gather", action="store_true", help="N>1, T,Q,U, every-pair shards: also time the NCCL gather of the whole matrix onto every GPU "
                                                           "(orbit shards: on by default where the matrix fits)")
     ap.add_argument("--no-gather", action="store_true", help="N>1, orbit shards: skip the gather of the whole matrix onto every GPU")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "pull"],
+    ap.add_argument("--direct-mask", type=int, default=-1, metavar="MASK",
+                    help="N>1 e2e leg: images that cross PCIe next to the last-face columns instead of being filled in by host threads "
+                         "(bit 3 strip + k - 1); -1 = 0x49, the first image face of every strip")
+    ap.add_argument("--exchange", default="pull", choices=["nccl", "pull"],
                     help="N>1, orbit shards: how block(r -> d) of the outboxes reaches rank d -- one NCCL all-to-all + a local scatter kernel, "
                          "or the scatter kernel reading the sender's outbox through CUDA-IPC peer memory")
     ap.add_argument("--spot-check", type=int, default=10000, metavar="N",

@@ -104,11 +104,18 @@ _SIGNATURES = {
     "cmg_legendre_series_orbit": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "cmg_orbit_outbox_layout": (ctypes.c_int, [_i64, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp]),
     "cmg_tqu_orbit_scatter_inbox": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), ctypes.c_int, ctypes.c_int, _vp]),
-    "cmg_orbit_strips_to_host": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), _vp, ctypes.c_int]),
+    "cmg_orbit_strips_to_host": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), _vp, ctypes.c_int, ctypes.c_int]),
+    "cmg_copy_on_device": (ctypes.c_int, [_vp, _vp, _vp, _i64]),
+    "cmg_transfer_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "cmg_cl_to_cmatrix_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp]),
+    "cmg_fiducial_matrix_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp]),
+    "cmg_cl_to_cmatrix_pol_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
+    "cmg_matrix_to_host": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _vp]),
     "cmg_host_register": (ctypes.c_int, [_vp, _i64]),
     "cmg_host_unregister": (ctypes.c_int, [_vp]),
     "cmg_host_expand_rotations": (ctypes.c_int, [_vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "cmg_set_host_expand": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "cmg_set_host_expand_direct": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_tqu_orbit_plan": (ctypes.c_int, [_i64, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cmg_tqu_weights": (ctypes.c_int, [_vp] * 6 + [ctypes.c_int] + [_vp] * 4),
     "cmg_cl_to_cmatrix_pol": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
@@ -407,9 +414,22 @@ class Context:
         """block(sender -> this rank) (local or IPC-mapped peer memory) into this rank's strips (include/cmg.h)"""
         self._check(self._L.cmg_tqu_orbit_scatter_inbox(self._h, ctypes.byref(shard), int(mode), int(sender), _p(d_block)))
 
-    def orbit_strips_to_host(self, shard, host_packed, threads=0):
+    def orbit_strips_to_host(self, shard, host_packed, threads=0, direct_mask=0):
         """this rank's complete strips as its columns of one whole packed host matrix (include/cmg.h)"""
-        self._check(self._L.cmg_orbit_strips_to_host(self._h, ctypes.byref(shard), _p(host_packed), int(threads)))
+        self._check(self._L.cmg_orbit_strips_to_host(self._h, ctypes.byref(shard), _p(host_packed), int(threads), int(direct_mask)))
+
+    def set_host_expand_direct(self, direct_mask):
+        self._check(self._L.cmg_set_host_expand_direct(self._h, int(direct_mask)))
+
+    def copy_on_device(self, d_dst, d_src, nbytes):
+        """stream-ordered device-to-device copy (either side may be CUDA-IPC mapped peer memory)"""
+        self._check(self._L.cmg_copy_on_device(self._h, _p(d_dst), _p(d_src), int(nbytes)))
+
+    def transfer_counters(self):
+        """(host-to-device, device-to-host) bytes this context has moved so far"""
+        a, b = _i64(), _i64()
+        self._check(self._L.cmg_transfer_counters(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def tqu_scatter_block(self, d_block, col0, n_cols, ld, row0, kind, d_full):
         self._check(self._L.cmg_tqu_scatter_block(self._h, _p(d_block), col0, n_cols, ld, row0, kind, _p(d_full)))

@@ -52,6 +52,7 @@ struct cmg_ctx
 
     cmg::SeriesTable hostT0, hostT20, hostT22;   // host copies of the recurrence tables
     int tquVariant = 0;                          // 0 = automatic choice (see launchTqu)
+    int hostExpandDirectMask = 1 << 6;           // images that cross PCIe next to the last-face columns (bit 3 strip + k - 1)
     int hostExpandThreads = -1;                  // full-sky whole calls copy back 27 % and expand on the host: > 0 threads, 0 = plain copy,
                                                  // -1 = automatic (all host cores for matrices of 1 GiB and more; measured 1.27x at 87 GB)
 
@@ -64,6 +65,7 @@ struct cmg_ctx
     bool timing = false;
     double lastMs = 0.0;
     int64_t launches = 0;
+    int64_t bytesH2D = 0, bytesD2H = 0;          // what crossed PCIe through this context (cmg_transfer_counters)
 };
 
 namespace
@@ -571,6 +573,7 @@ cmg_status cmg_copy_to_host(cmg_ctx* ctx, void* dst, const void* src, int64_t by
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     CMG_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->bytesD2H += bytes;
     return CMG_OK;
 }
 
@@ -579,6 +582,23 @@ cmg_status cmg_copy_to_device(cmg_ctx* ctx, void* dst, const void* src, int64_t 
     if(!ctx || !dst || !src || bytes < 0) return CMG_EINVAL;
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     CMG_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->bytesH2D += bytes;
+    return CMG_OK;
+}
+
+cmg_status cmg_copy_on_device(cmg_ctx* ctx, void* dst, const void* src, int64_t bytes)
+{
+    if(!ctx || !dst || !src || bytes < 0) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    CMG_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, ctx->stream));
+    return CMG_OK;
+}
+
+cmg_status cmg_transfer_counters(const cmg_ctx* ctx, int64_t* h2d, int64_t* d2h)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(h2d) *h2d = ctx->bytesH2D;
+    if(d2h) *d2h = ctx->bytesD2H;
     return CMG_OK;
 }
 
@@ -820,32 +840,40 @@ static int hostExpandThreadsFor(const cmg_ctx* ctx, int64_t bytes)
     return static_cast<int>(std::max(1u, std::min(32u, std::thread::hardware_concurrency())));
 }
 
-static cmg_status copyBackLastFacesAndExpand(cmg_ctx* ctx, int strips, double* outPacked, int threads)
+static cmg_status copyBackLastFacesAndExpand(cmg_ctx* ctx, const double* dPacked, int strips, double* outPacked, int threads)
 {
     const int64_t n = ctx->npix, facePix = ctx->nside * ctx->nside;
-    struct Chunk { int strip, ring; int64_t q0, q1; cudaEvent_t arrived; };
+    struct Chunk { int strip, ring, face; int64_t q0, q1; cudaEvent_t arrived; };
     std::vector<Chunk> chunks;
-    for(int strip = 0; strip < strips; ++strip)
-        for(int ring = 0; ring < 3; ++ring)
-        {
-            const int64_t col0 = strip * n + (4 * ring + 3) * facePix;
-            const int64_t step = std::max<int64_t>(8, std::min<int64_t>(facePix, (int64_t(8) << 20) / (col0 + facePix)));   // ~64 MB
-            for(int64_t q = 0; q < facePix; q += step)
-                chunks.push_back({strip, ring, q, std::min(facePix, q + step), nullptr});
-        }
+    // One GPU feeds the host at ~54 GB/s while the host threads write the images at ~80 GB/s (16 cores): the copy engine would
+    // idle half of the time, so the image next to the last face of the third strip (14 % of the matrix) crosses PCIe as well.
+    const int directMask = strips == 3 ? ctx->hostExpandDirectMask : 0;
+    for(int pass = 0; pass <= 3; ++pass)
+        for(int strip = 0; strip < strips; ++strip)
+            for(int ring = 0; ring < 3; ++ring)
+            {
+                if(pass > 0 && !((directMask >> (3 * strip + pass - 1)) & 1))
+                    continue;
+                const int face = 4 * ring + 3 - pass;
+                const int64_t col0 = strip * n + face * facePix;
+                const int64_t step = std::max<int64_t>(8, std::min<int64_t>(facePix, (int64_t(8) << 20) / (col0 + facePix)));   // ~64 MB
+                for(int64_t q = 0; q < facePix; q += step)
+                    chunks.push_back({strip, ring, face, q, std::min(facePix, q + step), nullptr});
+            }
     cmg_status st = CMG_OK;
     size_t issued = 0;
     for(; issued < chunks.size() && st == CMG_OK; ++issued)
     {
         Chunk& c = chunks[issued];
-        const int64_t col0 = c.strip * n + (4 * c.ring + 3) * facePix;
+        const int64_t col0 = c.strip * n + c.face * facePix;
         const int64_t first = cmg_packed_size(col0 + c.q0), last = cmg_packed_size(col0 + c.q1);
-        cudaError_t e = cudaMemcpyAsync(outPacked + first, ctx->dScratch + first, sizeof(double) * (last - first), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(outPacked + first, dPacked + first, sizeof(double) * (last - first), cudaMemcpyDeviceToHost, ctx->stream);
         if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c.arrived, cudaEventDisableTiming);
         if(e == cudaSuccess) e = cudaEventRecord(c.arrived, ctx->stream);
         if(e != cudaSuccess) st = cudaFail(ctx, e, "cudaMemcpyAsync (host expansion)");
+        else ctx->bytesD2H += static_cast<int64_t>(sizeof(double)) * (last - first);
     }
-    cmg::ExpandPipeline* pipe = cmg::expandBegin(outPacked, ctx->nside, threads);
+    cmg::ExpandPipeline* pipe = cmg::expandBegin(outPacked, ctx->nside, threads, directMask);
     for(size_t k = 0; k < issued; ++k)
     {
         Chunk& c = chunks[k];
@@ -853,55 +881,109 @@ static cmg_status copyBackLastFacesAndExpand(cmg_ctx* ctx, int strips, double* o
         const cudaError_t e = cudaEventSynchronize(c.arrived);
         cudaEventDestroy(c.arrived);
         if(e != cudaSuccess && st == CMG_OK) st = cudaFail(ctx, e, "cudaEventSynchronize");
-        if(st == CMG_OK)
+        if(st == CMG_OK && (c.face & 3) == 3)
             cmg::expandPublish(pipe, c.strip, c.ring, c.q0, c.q1);
     }
     cmg::expandFinish(pipe);
     return st;
 }
 
-static cmg_status wholeCallTT(cmg_ctx* ctx, const std::vector<double>& a, int lmax, double* outPacked)
+// a packed matrix of dimension strips x npix from device to host memory; on the full sky (the matrix of the context's current
+// geometry) by the host expansion where that pays
+static cmg_status matrixToHost(cmg_ctx* ctx, const double* dPacked, int strips, double* outPacked)
 {
-    const int64_t bytes = sizeof(double) * cmg_packed_size(ctx->npix);
-    cmg_status s = ensureScratch(ctx, bytes);
-    if(s != CMG_OK) return s;
-    // full sky: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid (orbit.cuh), 3.2x less work
-    const bool orbit = ctx->fullSky && ctx->nside >= 16 && lmax + 1 <= cmg::TT_STATIC_STEPS && ctx->tquVariant == 0;
-    if((s = orbit ? cmg_legendre_series_orbit(ctx, a.data(), lmax, ctx->dScratch)
-                  : cmg_legendre_series(ctx, a.data(), lmax, 0, ctx->npix, ctx->dScratch)) != CMG_OK) return s;
+    const int64_t bytes = sizeof(double) * cmg_packed_size(strips * ctx->npix);
     if(const int threads = hostExpandThreadsFor(ctx, bytes))
-        return copyBackLastFacesAndExpand(ctx, 1, outPacked, threads);
-    CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return copyBackLastFacesAndExpand(ctx, dPacked, strips, outPacked, threads);
+    CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, dPacked, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->bytesD2H += bytes;
     return CMG_OK;
 }
 
-cmg_status cmg_cl_to_cmatrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* outPacked)
+static cmg_status wholeCallTT(cmg_ctx* ctx, const std::vector<double>& a, int lmax, double* dOut, double* outPacked)
+{
+    cmg_status s;
+    if(!dOut)
+    {
+        if((s = ensureScratch(ctx, sizeof(double) * cmg_packed_size(ctx->npix))) != CMG_OK) return s;
+        dOut = ctx->dScratch;
+    }
+    // full sky: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid (orbit.cuh), 3.2x less work
+    const bool orbit = ctx->fullSky && ctx->nside >= 16 && lmax + 1 <= cmg::TT_STATIC_STEPS && ctx->tquVariant == 0;
+    if((s = orbit ? cmg_legendre_series_orbit(ctx, a.data(), lmax, dOut)
+                  : cmg_legendre_series(ctx, a.data(), lmax, 0, ctx->npix, dOut)) != CMG_OK) return s;
+    return outPacked ? matrixToHost(ctx, dOut, 1, outPacked) : CMG_OK;
+}
+
+static cmg_status clToCMatrixImpl(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* dOut, double* outPacked)
 {
     cmg_status s = checkReady(ctx, lmax);
     if(s != CMG_OK) return s;
-    if(!cl || !outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    if(!cl || (!outPacked && !dOut)) return fail(ctx, CMG_EINVAL, "null argument");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<double> f(lmax + 1), a(lmax + 1);
     // the reference has check(fwhm >= 0) (source/utils.cpp:56); a negative beam must not come back as an all-zero matrix
     if(cmg_window_beam(f.data(), lmax, fwhm, pixwin) != CMG_OK) return fail(ctx, CMG_EINVAL, "fwhm must be >= 0 (degrees)");
     if((s = cmg_tt_weights(cl, f.data(), lmax, a.data())) != CMG_OK) return fail(ctx, s, "bad C_l / window arguments");
-    return wholeCallTT(ctx, a, lmax, outPacked);
+    return wholeCallTT(ctx, a, lmax, dOut, outPacked);
 }
 
-cmg_status cmg_fiducial_matrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* outPacked)
+static cmg_status fiducialImpl(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* dOut, double* outPacked)
 {
     if(!ctx) return CMG_EINVAL;
     const int lMaxMax = static_cast<int>(4 * ctx->nside);
     cmg_status s = checkReady(ctx, lMaxMax);
     if(s != CMG_OK) return s;
-    if(!cl || !outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    if(!cl || (!outPacked && !dOut)) return fail(ctx, CMG_EINVAL, "null argument");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<double> f(lMaxMax + 1), a(lMaxMax + 1);
     if(lmax < 2 || lmax > lMaxMax) return fail(ctx, CMG_EINVAL, "fiducial matrix: 2 <= lmax <= 4 nside");
     if(cmg_window_beam(f.data(), lMaxMax, fwhm, pixwin) != CMG_OK) return fail(ctx, CMG_EINVAL, "fwhm must be >= 0 (degrees)");
     if((s = cmg_fiducial_weights(cl, f.data(), ctx->nside, lmax, a.data())) != CMG_OK) return fail(ctx, s, "bad C_l / window arguments");
-    return wholeCallTT(ctx, a, lMaxMax, outPacked);
+    return wholeCallTT(ctx, a, lMaxMax, dOut, outPacked);
+}
+
+cmg_status cmg_cl_to_cmatrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* outPacked)
+{
+    if(!outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    return clToCMatrixImpl(ctx, cl, lmax, fwhm, pixwin, nullptr, outPacked);
+}
+
+cmg_status cmg_cl_to_cmatrix_dev(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* dOut)
+{
+    if(!dOut) return fail(ctx, CMG_EINVAL, "null argument");
+    return clToCMatrixImpl(ctx, cl, lmax, fwhm, pixwin, dOut, nullptr);
+}
+
+cmg_status cmg_fiducial_matrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* outPacked)
+{
+    if(!outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    return fiducialImpl(ctx, cl, lmax, fwhm, pixwin, nullptr, outPacked);
+}
+
+cmg_status cmg_fiducial_matrix_dev(cmg_ctx* ctx, const double* cl, int lmax, double fwhm, const double* pixwin, double* dOut)
+{
+    if(!dOut) return fail(ctx, CMG_EINVAL, "null argument");
+    return fiducialImpl(ctx, cl, lmax, fwhm, pixwin, dOut, nullptr);
+}
+
+cmg_status cmg_matrix_to_host(cmg_ctx* ctx, const double* dPacked, int64_t dim, int full_sky_strips, double* outPacked)
+{
+    if(!ctx || !dPacked || !outPacked || dim < 1) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if(full_sky_strips == 1 || full_sky_strips == 3)
+    {
+        // the caller vouches that this is the full-sky NESTED matrix of the context's current geometry ([T] or [T;Q;U])
+        if(!ctx->fullSky || dim != full_sky_strips * ctx->npix)
+            return fail(ctx, CMG_EINVAL, "cmg_matrix_to_host: not the full-sky matrix of the current geometry");
+        return matrixToHost(ctx, dPacked, full_sky_strips, outPacked);
+    }
+    const int64_t bytes = sizeof(double) * cmg_packed_size(dim);
+    CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, dPacked, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->bytesD2H += bytes;
+    return CMG_OK;
 }
 
 cmg_status cmg_mask_matrix(cmg_ctx* ctx, const double* dIn, int64_t npixIn, const int32_t* good, int64_t nGood, double* dOut)
@@ -1280,10 +1362,10 @@ cmg_status cmg_host_unregister(void* ptr)
     return CMG_OK;
 }
 
-cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, double* hostPacked, int threads)
+cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, double* hostPacked, int threads, int directMask)
 {
     if(!ctx) return CMG_EINVAL;
-    if(!hostPacked || threads < 0) return fail(ctx, CMG_EINVAL, "null destination or negative thread count");
+    if(!hostPacked || threads < 0 || directMask < 0 || directMask > 511) return fail(ctx, CMG_EINVAL, "null destination, negative thread count or direct mask outside 0..511");
     if(ctx->npix <= 0) return fail(ctx, CMG_ESTATE, "cmg_set_pixels has not been called on this context");
     cmg::OrbitShardDev sh;
     cmg_status s = orbitShardDev(ctx, shard, 0, sh);
@@ -1298,27 +1380,34 @@ cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, 
             {
                 const int64_t first = cmg::packedOffset(st * n + f * facePix + sh.q0), last = cmg::packedOffset(st * n + f * facePix + sh.q1);
                 CMG_CUDA(ctx, cudaMemcpyAsync(hostPacked + first, shard->strip[st][f], sizeof(double) * (last - first), cudaMemcpyDeviceToHost, ctx->stream));
+                ctx->bytesD2H += static_cast<int64_t>(sizeof(double)) * (last - first);
             }
         CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return CMG_OK;
     }
-    // the rank's columns of the last face of every ring, in chunks of ~64 MB; workers fill in the images of a chunk once it is there
-    struct Chunk { int strip, ring; int64_t q0, q1; cudaEvent_t arrived; };
+    // the rank's columns of the last face of every ring, in chunks of ~64 MB; workers fill in the images of a chunk once it is there.
+    // Images selected by directMask (bit 3 strip + k - 1: the face k below the last one) come over PCIe as well, behind the
+    // last-face columns: the split between the copy engines and the host threads is the caller's to balance.
+    struct Chunk { int strip, ring, face; int64_t q0, q1; cudaEvent_t arrived; };
     std::vector<Chunk> chunks;
-    for(int st = 0; st < 3; ++st)
-        for(int ring = 0; ring < 3; ++ring)
-        {
-            const int64_t col0 = st * n + (4 * ring + 3) * facePix;
-            const int64_t step = std::max<int64_t>(8, std::min<int64_t>(facePix, (int64_t(8) << 20) / (col0 + facePix)));
-            for(int64_t q = sh.q0; q < sh.q1; q += step)
-                chunks.push_back({st, ring, q, std::min<int64_t>(sh.q1, q + step), nullptr});
-        }
+    for(int pass = 0; pass <= 3; ++pass)
+        for(int st = 0; st < 3; ++st)
+            for(int ring = 0; ring < 3; ++ring)
+            {
+                if(pass > 0 && !((directMask >> (3 * st + pass - 1)) & 1))
+                    continue;
+                const int face = 4 * ring + 3 - pass;
+                const int64_t col0 = st * n + face * facePix;
+                const int64_t step = std::max<int64_t>(8, std::min<int64_t>(facePix, (int64_t(8) << 20) / (col0 + facePix)));
+                for(int64_t q = sh.q0; q < sh.q1; q += step)
+                    chunks.push_back({st, ring, face, q, std::min<int64_t>(sh.q1, q + step), nullptr});
+            }
     cmg_status st = CMG_OK;
     size_t issued = 0;
     for(; issued < chunks.size() && st == CMG_OK; ++issued)
     {
         Chunk& c = chunks[issued];
-        const int face = 4 * c.ring + 3;
+        const int face = c.face;
         const int64_t col0 = c.strip * n + face * facePix;
         const int64_t first = cmg::packedOffset(col0 + c.q0), last = cmg::packedOffset(col0 + c.q1);
         const double* src = shard->strip[c.strip][face] + (first - cmg::packedOffset(col0 + sh.q0));
@@ -1326,8 +1415,9 @@ cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, 
         if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c.arrived, cudaEventDisableTiming);
         if(e == cudaSuccess) e = cudaEventRecord(c.arrived, ctx->stream);
         if(e != cudaSuccess) st = cudaFail(ctx, e, "cudaMemcpyAsync (strips to host)");
+        else ctx->bytesD2H += static_cast<int64_t>(sizeof(double)) * (last - first);
     }
-    cmg::ExpandPipeline* pipe = cmg::expandBegin(hostPacked, ctx->nside, threads);
+    cmg::ExpandPipeline* pipe = cmg::expandBegin(hostPacked, ctx->nside, threads, directMask);
     for(size_t k = 0; k < issued; ++k)
     {
         Chunk& c = chunks[k];
@@ -1335,7 +1425,7 @@ cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, 
         const cudaError_t e = cudaEventSynchronize(c.arrived);
         cudaEventDestroy(c.arrived);
         if(e != cudaSuccess && st == CMG_OK) st = cudaFail(ctx, e, "cudaEventSynchronize");
-        if(st == CMG_OK)
+        if(st == CMG_OK && (c.face & 3) == 3)
             cmg::expandPublish(pipe, c.strip, c.ring, c.q0, c.q1);
     }
     cmg::expandFinish(pipe);
@@ -1518,12 +1608,12 @@ cmg_status cmg_slab_unpack(cmg_ctx* ctx, const double* dSlab, int64_t dim, int n
     return CMG_OK;
 }
 
-cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee, const double* cbb,
-                                 int lmax, double fwhm, const double* pixwinT, const double* pixwinP, double* outPacked)
+static cmg_status clToCMatrixPolImpl(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee, const double* cbb,
+                                     int lmax, double fwhm, const double* pixwinT, const double* pixwinP, double* dOut, double* outPacked)
 {
     cmg_status s = checkReady(ctx, lmax);
     if(s != CMG_OK) return s;
-    if(!ctt || !cte || !cee || !cbb || !outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    if(!ctt || !cte || !cee || !cbb || (!outPacked && !dOut)) return fail(ctx, CMG_EINVAL, "null argument");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int n1 = lmax + 1;
     std::vector<double> fT(n1), fP(n1), a(4 * n1);
@@ -1531,24 +1621,37 @@ cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* 
         return fail(ctx, CMG_EINVAL, "fwhm must be >= 0 (degrees)");
     if((s = cmg_tqu_weights(ctt, cte, cee, cbb, fT.data(), fP.data(), lmax, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1)) != CMG_OK)
         return fail(ctx, s, "bad C_l / window arguments");
-    const int64_t bytes = sizeof(double) * cmg_packed_size(3 * ctx->npix);
-    if((s = ensureScratch(ctx, bytes)) != CMG_OK) return s;
+    if(!dOut)
+    {
+        if((s = ensureScratch(ctx, sizeof(double) * cmg_packed_size(3 * ctx->npix))) != CMG_OK) return s;
+        dOut = ctx->dScratch;
+    }
     if(ctx->fullSky && ctx->nside >= 8 && lmax >= 2 && lmax <= cmg::PQ_STATIC_LMAX && ctx->tquVariant == 0)
     {
         // full sky: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid (orbit.cuh), a quarter of the work
-        if((s = cmg_tqu_orbit(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, ctx->dScratch, 0)) != CMG_OK) return s;
+        if((s = cmg_tqu_orbit(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, dOut, 0)) != CMG_OK) return s;
     }
     else
     {
         cmg_tqu_layout layout;
-        if((s = cmg_tqu_layout_single(ctx, ctx->dScratch, &layout)) != CMG_OK) return s;
+        if((s = cmg_tqu_layout_single(ctx, dOut, &layout)) != CMG_OK) return s;
         if((s = cmg_tqu(ctx, a.data(), a.data() + n1, a.data() + 2 * n1, a.data() + 3 * n1, lmax, &layout)) != CMG_OK) return s;
     }
-    if(const int threads = hostExpandThreadsFor(ctx, bytes))
-        return copyBackLastFacesAndExpand(ctx, 3, outPacked, threads);
-    CMG_CUDA(ctx, cudaMemcpyAsync(outPacked, ctx->dScratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return CMG_OK;
+    return outPacked ? matrixToHost(ctx, dOut, 3, outPacked) : CMG_OK;
+}
+
+cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee, const double* cbb,
+                                 int lmax, double fwhm, const double* pixwinT, const double* pixwinP, double* outPacked)
+{
+    if(!outPacked) return fail(ctx, CMG_EINVAL, "null argument");
+    return clToCMatrixPolImpl(ctx, ctt, cte, cee, cbb, lmax, fwhm, pixwinT, pixwinP, nullptr, outPacked);
+}
+
+cmg_status cmg_cl_to_cmatrix_pol_dev(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee, const double* cbb,
+                                     int lmax, double fwhm, const double* pixwinT, const double* pixwinP, double* dOut)
+{
+    if(!dOut) return fail(ctx, CMG_EINVAL, "null argument");
+    return clToCMatrixPolImpl(ctx, ctt, cte, cee, cbb, lmax, fwhm, pixwinT, pixwinP, dOut, nullptr);
 }
 
 cmg_status cmg_tqu_scatter_block(cmg_ctx* ctx, const double* dBlock, int64_t col0, int64_t nCols, int64_t ld, int64_t row0, int kind,
@@ -1989,6 +2092,13 @@ cmg_status cmg_set_host_expand(cmg_ctx* ctx, int threads)
 {
     if(!ctx || threads < -1) return CMG_EINVAL;
     ctx->hostExpandThreads = threads;
+    return CMG_OK;
+}
+
+cmg_status cmg_set_host_expand_direct(cmg_ctx* ctx, int directMask)
+{
+    if(!ctx || directMask < 0 || directMask > 511) return CMG_EINVAL;
+    ctx->hostExpandDirectMask = directMask;
     return CMG_OK;
 }
 

@@ -74,7 +74,7 @@ CopyFn pickCopy()
 
 // images of the columns [qBegin, qEnd) of (strip, last face of `ring`): every run of rows is read once and written to the
 // matching run of the same column index in the three other faces of the ring
-void expandColumns(double* packed, int64_t facePix, int strip, int ring, int64_t qBegin, int64_t qEnd, CopyFn copy)
+void expandColumns(double* packed, int64_t facePix, int strip, int ring, int64_t qBegin, int64_t qEnd, CopyFn copy, int directMask)
 {
     const int64_t n = 12 * facePix;
     const int lastFace = 4 * ring + 3;
@@ -84,6 +84,9 @@ void expandColumns(double* packed, int64_t facePix, int strip, int ring, int64_t
         double* dst[4];
         for(int k = 1; k <= 3; ++k)
             dst[k] = packed + packedOffset(strip * n + (lastFace - k) * facePix + q);
+        const int skip = (directMask >> (3 * strip)) & 7;             // bit k - 1: image k of this strip arrives by itself
+        if(skip == 7)
+            continue;
         for(int x = 0; x <= strip; ++x)
         {
             // faces of the row pixel of the source column: all twelve for an earlier strip, up to the last face for its own
@@ -93,6 +96,8 @@ void expandColumns(double* packed, int64_t facePix, int strip, int ring, int64_t
                 const double* run = src + x * n + fs * facePix;
                 for(int k = 1; k <= 3; ++k)
                 {
+                    if((skip >> (k - 1)) & 1)
+                        continue;                                          // a direct copy brings this image
                     const int face = lastFace - k;                         // destination column face: rotation by -k
                     const int fa = (fs & ~3) | ((fs - k) & 3);             // destination row face
                     if(x == strip && fa > face)
@@ -117,6 +122,7 @@ struct ExpandPipeline
     double* packed;
     int64_t facePix;
     CopyFn copy;
+    int directMask;
     std::mutex m;
     std::condition_variable cv;
     std::deque<Item> items;
@@ -136,15 +142,16 @@ struct ExpandPipeline
                 it = items.front();
                 items.pop_front();
             }
-            expandColumns(packed, facePix, it.strip, it.ring, it.q0, it.q1, copy);
+            expandColumns(packed, facePix, it.strip, it.ring, it.q0, it.q1, copy, directMask);
         }
     }
 };
 
-ExpandPipeline* expandBegin(double* packed, int64_t nside, int threads)
+ExpandPipeline* expandBegin(double* packed, int64_t nside, int threads, int directMask)
 {
     ExpandPipeline* p = new ExpandPipeline;
     p->packed = packed;
+    p->directMask = directMask;
     p->facePix = nside * nside;
     p->copy = pickCopy();
     p->closed = false;

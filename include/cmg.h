@@ -80,9 +80,14 @@ cmg_status cmg_host_free_pinned(void* ptr);
 cmg_status cmg_ipc_export(cmg_ctx* ctx, void* d_ptr, void* handle);
 cmg_status cmg_ipc_open(cmg_ctx* ctx, const void* handle, void** d_peer_ptr);
 cmg_status cmg_ipc_close(cmg_ctx* ctx, void* d_peer_ptr);
-/* stream-ordered copies on the context's stream */
+/* stream-ordered copies on the context's stream (cmg_copy_to_host returns when the data is there) */
 cmg_status cmg_copy_to_host(cmg_ctx* ctx, void* dst_host, const void* d_src, int64_t bytes);
 cmg_status cmg_copy_to_device(cmg_ctx* ctx, void* d_dst, const void* src_host, int64_t bytes);
+/* device to device; either side may be peer memory mapped with cmg_ipc_open (the copy then crosses NVLink) */
+cmg_status cmg_copy_on_device(cmg_ctx* ctx, void* d_dst, const void* d_src, int64_t bytes);
+/* bytes this context has moved over PCIe so far: cmg_copy_to_device / cmg_copy_to_host, the whole calls with host output,
+ * cmg_matrix_to_host, cmg_orbit_strips_to_host (the few KB of series weights of a launch are not counted) */
+cmg_status cmg_transfer_counters(const cmg_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 /* ------------------------------------------- host pieces of the path (pure CPU, O(N) or O(lmax)) */
 
@@ -138,6 +143,14 @@ cmg_status cmg_cl_to_cmatrix(cmg_ctx* ctx, const double* cl, int lmax, double fw
                              const double* pixwin, double* out_packed);
 cmg_status cmg_fiducial_matrix(cmg_ctx* ctx, const double* cl, int lmax, double fwhm_deg,
                                const double* pixwin, double* out_packed);
+/* The same two with DEVICE output (d_out: npix(npix+1)/2 doubles on the context's GPU): nothing but C_l crosses PCIe.  What the
+ * C++ drop-in's device-resident CMatrix is filled by. */
+cmg_status cmg_cl_to_cmatrix_dev(cmg_ctx* ctx, const double* cl, int lmax, double fwhm_deg, const double* pixwin, double* d_out);
+cmg_status cmg_fiducial_matrix_dev(cmg_ctx* ctx, const double* cl, int lmax, double fwhm_deg, const double* pixwin, double* d_out);
+/* A packed matrix of dimension dim from device to host memory.  full_sky_strips = 1 or 3 vouches that it is the full-sky NESTED
+ * [T] / [T;Q;U] matrix of the context's current geometry (dim = strips x npix), which lets the copy use the host expansion
+ * (cmg_set_host_expand); 0 = any packed matrix, one plain copy. */
+cmg_status cmg_matrix_to_host(cmg_ctx* ctx, const double* d_packed, int64_t dim, int full_sky_strips, double* out_packed);
 /* CMatrixGenerator::generateNoiseMatrix, reference c_matrix_generator.cpp:774-787 (host, trivial) */
 cmg_status cmg_noise_matrix(int64_t npix, double noise, double* out_packed);
 /* CMatrix::maskMatrix gather, reference source/c_matrix.cpp:182-201; device buffers */
@@ -231,9 +244,11 @@ cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, in
  * ranks on one box a shared mapping every rank writes its own columns of).  threads > 0: only the columns of base faces 3, 7, 11
  * cross PCIe and `threads` host threads fill in this rank's columns of the other faces as rotated images while the copies are in
  * flight (cmg_host_expand_rotations restricted to [q_begin, q_end)); threads = 0: all 36 runs are copied.  Page-locked
- * destinations (cmg_host_register) make the copies run at PCIe speed.  Returns when the rank's columns are complete in host
- * memory. */
-cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, double* host_packed, int threads);
+ * destinations (cmg_host_register) make the copies run at PCIe speed.  direct_mask (with threads > 0), bit 3 s + k - 1: the image
+ * of strip s in the k-th face below the last one of every ring is copied over PCIe as well instead of being filled in by the
+ * host threads -- the balance between the copy engines and the host's memory bandwidth is the caller's to choose (several GPUs
+ * feeding one host: 0x49, the first image face of every strip).  Returns when the rank's columns are complete in host memory. */
+cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, double* host_packed, int threads, int direct_mask);
 /* cudaHostRegister / cudaHostUnregister of caller-owned memory (e.g. a shared mapping) */
 cmg_status cmg_host_register(void* ptr, int64_t bytes);
 cmg_status cmg_host_unregister(void* ptr);
@@ -255,6 +270,9 @@ cmg_status cmg_host_expand_rotations(double* packed, int64_t nside, int strip_be
  * host cores for matrices of 1 GiB and more.  Measured for the 87 GB matrix on a 16-core host: 1.75 s plain, 1.38 s expanded
  * (round 2, first version; profiles/README.md has the current figure). */
 cmg_status cmg_set_host_expand(cmg_ctx* ctx, int threads);
+/* which images the [T;Q;U] whole call copies over PCIe next to the last-face columns (bit 3 strip + k - 1, as direct_mask of
+ * cmg_orbit_strips_to_host); default 0x40: one GPU's copy engine and 16 host cores finish together that way */
+cmg_status cmg_set_host_expand_direct(cmg_ctx* ctx, int direct_mask);
 /* the classes of base-face pairs cmg_tqu_orbit works through (host only; for tests): out[c][CMG_ORBIT_CLASS_INTS] =
  * { row face, column face, only q_row <= q_col, same face, n_images, then for image k = 0..3: row face, column face,
  *   stored transposed }, then for image k = 0..3 the outbox number of (this class, image k, staged kind 0) (cmg_orbit_shard);
@@ -266,10 +284,16 @@ cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* n_
 cmg_status cmg_tqu_weights(const double* ctt, const double* cte, const double* cee, const double* cbb,
                            const double* fT, const double* fP, int lmax,
                            double* a_tt, double* a_te, double* a_ee, double* a_bb);
-/* whole call with HOST output: out_packed holds 3N(3N+1)/2 doubles */
+/* whole call with HOST output: out_packed holds 3N(3N+1)/2 doubles.  TT carries pixwinT^2, TE pixwinT pixwinP, EE and BB
+ * pixwinP^2 (each times the beam); the reference's own polarization routine uses the TEMPERATURE table throughout
+ * (source/c_matrix_generator.cpp:534: readPixelWindowFunction without the polarization flag) -- pass pixwinP = pixwinT for that. */
 cmg_status cmg_cl_to_cmatrix_pol(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee,
                                  const double* cbb, int lmax, double fwhm_deg,
                                  const double* pixwinT, const double* pixwinP, double* out_packed);
+/* same with DEVICE output */
+cmg_status cmg_cl_to_cmatrix_pol_dev(cmg_ctx* ctx, const double* ctt, const double* cte, const double* cee,
+                                     const double* cbb, int lmax, double fwhm_deg,
+                                     const double* pixwinT, const double* pixwinP, double* d_out);
 
 /* ---------------------------------------------------------------- batched regeneration ------ */
 

@@ -249,6 +249,14 @@ def unpack_symmetric(packed, n):
 
 # ------------------------------------------------------------------ helpers over the reference objects
 
+def ref_set_pixel_window(wT=None, wP=None):
+    """HEALPix pixel window the reference object code sees through its Utils::readPixelWindowFunction shim (oracle/ref_shim.cpp):
+    wT / wP = temperature / polarization table from l = 0; None = window 1 (what every other helper here assumes: reset it)."""
+    wT = _f64(wT)
+    wP = _f64(wP)
+    ref().ref_set_pixel_window(_ptr(wT), ctypes.c_int(0 if wT is None else len(wT)), _ptr(wP), ctypes.c_int(0 if wP is None else len(wP)))
+
+
 def ref_cl_to_cmatrix(cl, nside, fwhm, good=None, use_lp=False):
     cl = _f64(cl)
     good = _i32(good)

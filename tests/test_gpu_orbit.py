@@ -76,8 +76,8 @@ def test_orbit_shards_assemble_to_the_whole_matrix(gpu_ctx, oracle_api, world, m
     assert (np.abs(got - want) / _scale(n, want)).max() <= REL_TOL
 
 
-@pytest.mark.parametrize("world,mode,threads", [(2, 0, 0), (3, 0, 3), (3, 1, 2), (4, 2, 0)])
-def test_orbit_exchange_completes_the_strips(gpu_ctx, oracle_api, world, mode, threads):
+@pytest.mark.parametrize("world,mode,threads,direct", [(2, 0, 0, 0), (3, 0, 3, 0), (3, 1, 2, 0x49), (4, 2, 0, 0), (2, 0, 2, 0x1a5)])
+def test_orbit_exchange_completes_the_strips(gpu_ctx, oracle_api, world, mode, threads, direct):
     """The exchange step with every rank on this one GPU: block(r -> d) of r's outbox is placed into d's strips by
     cmg_tqu_orbit_scatter_inbox, after which the strips alone are the matrix -- on the device (assembly of the strips only) and
     on the host (cmg_orbit_strips_to_host into one whole packed matrix, plain or with the host filling in the rotated images)."""
@@ -100,7 +100,7 @@ def test_orbit_exchange_completes_the_strips(gpu_ctx, oracle_api, world, mode, t
     host = torch.full((capi.packed_size(3 * n),), float("nan"), dtype=torch.float64).pin_memory()
     for r in ranks:
         r.assemble_into(full, 1)                        # strips only
-        r.to_host(host, threads)
+        r.to_host(host, threads, direct)
     torch.cuda.synchronize()
     got = full.cpu().numpy()
     for r in ranks:
