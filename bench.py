@@ -487,9 +487,9 @@ def run_gpu_arm(args):
         sent = 8 * sum(sharded.send_counts)
         recv = 8 * sum(sharded.recv_counts)
         exchange = {"ms": float(np.median(times)), "bytes_sent_this_rank": sent, "bytes_received_this_rank": recv,
-                    "gbs_in_per_gpu": recv / (float(np.median(times)) * 1e-3) / 1e9, "mode": args.exchange,
+                    "gbs_in_per_gpu": recv / (float(np.median(times)) * 1e-3) / 1e9, "mode": sharded.exchange_mode,
                     "how": ("ncclAllToAll (torch all_to_all_single, uneven splits) of the destination blocks, then orbitInboxScatterKernel per sender"
-                            if args.exchange == "nccl" else
+                            if sharded.exchange_mode == "nccl" else
                             "orbitInboxScatterKernel reading every sender's outbox through CUDA-IPC mapped peer memory (NVLink loads), no staging")}
 
     # ---- untimed checker: sampled entries of this rank's complete columns against the CPU oracle

@@ -111,6 +111,11 @@ _SIGNATURES = {
     "cmg_fiducial_matrix_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp]),
     "cmg_cl_to_cmatrix_pol_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
     "cmg_matrix_to_host": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _vp]),
+    "cmg_packed_cholesky": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64)]),
+    "cmg_packed_cholesky_logdet": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(ctypes.c_double)]),
+    "cmg_packed_cholesky_solve": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64]),
+    "cmg_packed_sum": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "cmg_set_like_method": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_host_register": (ctypes.c_int, [_vp, _i64]),
     "cmg_host_unregister": (ctypes.c_int, [_vp]),
     "cmg_host_expand_rotations": (ctypes.c_int, [_vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
@@ -420,6 +425,26 @@ class Context:
 
     def set_host_expand_direct(self, direct_mask):
         self._check(self._L.cmg_set_host_expand_direct(self._h, int(direct_mask)))
+
+    def packed_cholesky(self, d_packed, n):
+        """in-place A = U^T U on a packed upper triangle (include/cmg.h); returns LAPACK's info (0 = positive definite)"""
+        info = _i64()
+        self._check(self._L.cmg_packed_cholesky(self._h, _p(d_packed), int(n), ctypes.byref(info)))
+        return info.value
+
+    def packed_cholesky_logdet(self, d_factor, n):
+        v = ctypes.c_double()
+        self._check(self._L.cmg_packed_cholesky_logdet(self._h, _p(d_factor), int(n), ctypes.byref(v)))
+        return v.value
+
+    def packed_cholesky_solve(self, d_factor, n, d_rhs, n_rhs):
+        self._check(self._L.cmg_packed_cholesky_solve(self._h, _p(d_factor), int(n), _p(d_rhs), int(n_rhs)))
+
+    def packed_sum(self, d_c, d_f, d_n, n, d_out, c_stride=1):
+        self._check(self._L.cmg_packed_sum(self._h, _p(d_c), int(c_stride), _p(d_f), _p(d_n), int(n), _p(d_out)))
+
+    def set_like_method(self, method):
+        self._check(self._L.cmg_set_like_method(self._h, int(method)))
 
     def copy_on_device(self, d_dst, d_src, nbytes):
         """stream-ordered device-to-device copy (either side may be CUDA-IPC mapped peer memory)"""

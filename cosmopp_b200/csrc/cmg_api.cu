@@ -20,6 +20,7 @@
 #include "../../include/cmg.h"
 #include "healpix_nest.hpp"
 #include "host_expand.hpp"
+#include "cholesky.cuh"
 #include "kernels.cuh"
 #include "orbit.cuh"
 #include "series.hpp"
@@ -66,6 +67,9 @@ struct cmg_ctx
     double lastMs = 0.0;
     int64_t launches = 0;
     int64_t bytesH2D = 0, bytesD2H = 0;          // what crossed PCIe through this context (cmg_transfer_counters)
+    long long* dCholInfo = nullptr;              // status word of cmg_packed_cholesky
+    double* dCholRed = nullptr;                  // log det / reductions of the packed solves
+    int likeMethod = 0;                          // cmg_like_create: 0 = this library's packed factorisation, 1 = cuSOLVER on the unpacked matrix
 };
 
 namespace
@@ -467,6 +471,8 @@ void cmg_destroy(cmg_ctx* ctx)
     if(ctx->dWeights) cudaFree(ctx->dWeights);
     if(ctx->dScratch) cudaFree(ctx->dScratch);
     if(ctx->dIndex) cudaFree(ctx->dIndex);
+    if(ctx->dCholInfo) cudaFree(ctx->dCholInfo);
+    if(ctx->dCholRed) cudaFree(ctx->dCholRed);
     for(int k = 0; k < cmg_ctx::kAux; ++k)
     {
         if(ctx->aux[k]) { cudaStreamSynchronize(ctx->aux[k]); cudaStreamDestroy(ctx->aux[k]); }
@@ -1689,17 +1695,129 @@ cmg_status cmg_sum_unpack(cmg_ctx* ctx, const double* dC, const double* dF, cons
     return cmg_sum_unpack_strided(ctx, dC, 1, dF, dN, n, dFull);
 }
 
+// ---------------------------------------------------------------- packed Cholesky (cholesky.cuh)
+
+namespace
+{
+cmg_status cholBuffers(cmg_ctx* ctx)
+{
+    if(!ctx->dCholInfo)
+        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholInfo, sizeof(long long)));
+    if(!ctx->dCholRed)
+        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholRed, sizeof(double) * 4));
+    return CMG_OK;
+}
+}
+
+cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* info)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!dA || n < 1 || !info) return fail(ctx, CMG_EINVAL, "cmg_packed_cholesky: null argument or n < 1");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_status s = cholBuffers(ctx);
+    if(s != CMG_OK) return s;
+    const int diagSmem = cmg::CH_NB * cmg::CH_LD * sizeof(double), panelSmem = cmg::CH_NB * cmg::CH_PANEL_COLS * sizeof(double);
+    const int syrkSmem = 2 * 2 * cmg::CH_TILE * cmg::CH_SLD * sizeof(double);
+    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diagSmem));
+    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panelSmem));
+    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholSyrkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, syrkSmem));
+    CMG_CUDA(ctx, cudaMemsetAsync(ctx->dCholInfo, 0, sizeof(long long), ctx->stream));
+    KernelTimer timer(ctx);
+    for(int64_t k0 = 0; k0 < n; k0 += cmg::CH_NB)
+    {
+        const int kb = static_cast<int>(std::min<int64_t>(cmg::CH_NB, n - k0));
+        cmg::cholDiagKernel<<<1, 512, diagSmem, ctx->stream>>>(dA, k0, kb, ctx->dCholInfo);
+        const int64_t rem = n - k0 - kb;
+        ctx->launches += 1;
+        if(rem <= 0)
+            break;
+        cmg::cholPanelKernel<<<static_cast<unsigned>((rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS), cmg::CH_PANEL_COLS, panelSmem, ctx->stream>>>(
+            dA, k0, kb, n, ctx->dCholInfo);
+        const int64_t tiles = (rem + cmg::CH_TILE - 1) / cmg::CH_TILE;
+        cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles * (tiles + 1) / 2), cmg::CH_SYRK_THREADS, syrkSmem, ctx->stream>>>(dA, k0, kb, n, ctx->dCholInfo);
+        ctx->launches += 2;
+    }
+    CMG_CUDA(ctx, cudaGetLastError());
+    if((s = timer.finish()) != CMG_OK) return s;
+    long long hInfo = 0;
+    CMG_CUDA(ctx, cudaMemcpyAsync(&hInfo, ctx->dCholInfo, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *info = hInfo;
+    return CMG_OK;
+}
+
+cmg_status cmg_packed_cholesky_logdet(cmg_ctx* ctx, const double* dU, int64_t n, double* logDet)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!dU || n < 1 || !logDet) return fail(ctx, CMG_EINVAL, "cmg_packed_cholesky_logdet: null argument or n < 1");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_status s = cholBuffers(ctx);
+    if(s != CMG_OK) return s;
+    cmg::cholLogDetKernel<<<1, 256, 0, ctx->stream>>>(dU, n, ctx->dCholRed);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    CMG_CUDA(ctx, cudaMemcpyAsync(logDet, ctx->dCholRed, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CMG_OK;
+}
+
+cmg_status cmg_packed_cholesky_solve(cmg_ctx* ctx, const double* dU, int64_t n, double* dT, int64_t nRhs)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!dU || !dT || n < 1 || nRhs < 1 || nRhs > 65535) return fail(ctx, CMG_EINVAL, "cmg_packed_cholesky_solve: bad arguments");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int perPass = static_cast<int>(std::min<int64_t>(8, nRhs));
+    const dim3 block(cmg::CH_NB, perPass);
+    const unsigned passes = static_cast<unsigned>((nRhs + perPass - 1) / perPass);
+    for(int64_t k0 = 0; k0 < n; k0 += cmg::CH_NB)
+    {
+        const int kb = static_cast<int>(std::min<int64_t>(cmg::CH_NB, n - k0));
+        cmg::cholSolveDiagKernel<<<passes, block, 0, ctx->stream>>>(dU, k0, kb, n, dT, static_cast<int>(nRhs));
+        ctx->launches += 1;
+        const int64_t rem = n - k0 - kb;
+        if(rem <= 0)
+            break;
+        cmg::cholSolveUpdateKernel<<<static_cast<unsigned>((rem + 7) / 8), 256, 0, ctx->stream>>>(dU, k0, kb, n, dT, static_cast<int>(nRhs));
+        ctx->launches += 1;
+    }
+    CMG_CUDA(ctx, cudaGetLastError());
+    return CMG_OK;
+}
+
+cmg_status cmg_packed_sum(cmg_ctx* ctx, const double* dC, int64_t cStride, const double* dF, const double* dN, int64_t n, double* dOut)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!dC || !dOut || n < 1 || cStride < 1) return fail(ctx, CMG_EINVAL, "cmg_packed_sum: bad arguments");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t count = cmg_packed_size(n);
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((count + 255) / 256, 148 * 32));
+    cmg::packedSumKernel<<<blocks, 256, 0, ctx->stream>>>(dC, cStride, dF, dN, count, dOut);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
+}
+
+cmg_status cmg_set_like_method(cmg_ctx* ctx, int method)
+{
+    if(!ctx || method < 0 || method > 1) return CMG_EINVAL;
+    ctx->likeMethod = method;
+    return CMG_OK;
+}
+
 // ---------------------------------------------------------------- pixel likelihood on the device
 // reference source/likelihood.cpp:68-134 (construct) and :136-180 (vmv, calculate).  The reference inverts C + F + N
 // (LAPACK dpptrf / dpptri) and evaluates t^T C^-1 t as a double loop per map; here the Cholesky factor stays on the
-// device and chi2 = |L^-1 t|^2 for all maps at once (cuSOLVER potrf, cuBLAS trsm: plain library calls), the
-// sum / unpack and the reductions are this library's kernels.
+// device and chi2 = |L^-1 t|^2 for all maps at once.  Default: this library's packed factorisation (cholesky.cuh), in place on
+// the packed sum -- n (n + 1) / 2 doubles, no unpacked copy, any n that fits the GPU.  cmg_set_like_method(ctx, 1) selects the
+// dense route instead (cusolverDnDpotrf + cublasDtrsm on the unpacked n x n matrix: plain library calls, kept as the bar to
+// compare with; twice the memory, n <= 46340).
 
 struct cmg_like
 {
     cmg_ctx* ctx = nullptr;
     int64_t n = 0;
-    double* dL = nullptr;            // n x n, lower triangle = Cholesky factor
+    double* dL = nullptr;            // dense method: n x n, lower triangle = Cholesky factor
+    double* dU = nullptr;            // packed method: U of A = U^T U, packed upper triangle
     double* dYf = nullptr;           // L^-1 f
     double* dT = nullptr;            // maps / solutions, n x tCap
     int64_t tCap = 0;
@@ -1738,6 +1856,7 @@ void cmg_like_destroy(cmg_like* L)
         cudaStreamSynchronize(L->ctx->stream);
     }
     if(L->dL) cudaFree(L->dL);
+    if(L->dU) cudaFree(L->dU);
     if(L->dYf) cudaFree(L->dYf);
     if(L->dT) cudaFree(L->dT);
     if(L->dRed) cudaFree(L->dRed);
@@ -1752,7 +1871,7 @@ cmg_status cmg_like_create(cmg_ctx* ctx, const double* dC, int64_t cStride, cons
     if(!ctx || !out) return CMG_EINVAL;
     *out = nullptr;
     if(!dC || n < 1 || cStride < 1) return fail(ctx, CMG_EINVAL, "bad likelihood arguments");
-    if(n > 46340) return fail(ctx, CMG_EUNSUPPORTED, "dense factorisation limited to n <= 46340 (32-bit LAPACK-style interface)");
+    if(ctx->likeMethod == 1 && n > 46340) return fail(ctx, CMG_EUNSUPPORTED, "dense factorisation limited to n <= 46340 (32-bit LAPACK-style interface)");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     cmg_like* L = new(std::nothrow) cmg_like;
     if(!L) return fail(ctx, CMG_ENOMEM, "out of host memory");
@@ -1763,6 +1882,33 @@ cmg_status cmg_like_create(cmg_ctx* ctx, const double* dC, int64_t cStride, cons
     int* dInfo = nullptr;
     auto bail = [&](cmg_status st) { if(dWork) cudaFree(dWork); if(dInfo) cudaFree(dInfo); cmg_like_destroy(L); return st; };
     cudaError_t e;
+    if(ctx->likeMethod == 0)
+    {
+        // packed: C + F + N in one pass, factorised where it lies
+        if((e = cudaMalloc(&L->dU, sizeof(double) * cmg_packed_size(n))) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMalloc (packed sum)"));
+        if((s = cmg_packed_sum(ctx, dC, cStride, dF, dN, n, L->dU)) != CMG_OK) return bail(s);
+        int64_t info = 0;
+        if((s = cmg_packed_cholesky(ctx, L->dU, n, &info)) != CMG_OK) return bail(s);
+        if(info != 0)
+            return bail(fail(ctx, CMG_ENUMERIC, "The determinant of the covariance matrix is not positive. The covariance matrix must be positive definite."));
+        double logDet = 0.0;
+        if((s = cmg_packed_cholesky_logdet(ctx, L->dU, n, &logDet)) != CMG_OK) return bail(s);
+        L->logDet = logDet - kDetOffset;
+        if(foreground)
+        {
+            if((e = cudaMalloc(&L->dYf, sizeof(double) * n)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMalloc"));
+            if((e = cudaMemcpyAsync(L->dYf, foreground, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMemcpy"));
+            if((s = cmg_packed_cholesky_solve(ctx, L->dU, n, L->dYf, 1)) != CMG_OK) return bail(s);
+            if((s = likeReserve(L, 1)) != CMG_OK) return bail(s);
+            cmg::columnDotsKernel<<<1, 256, 0, ctx->stream>>>(L->dYf, nullptr, n, L->dRed, nullptr);
+            if((e = cudaMemcpyAsync(&L->fCinvf, L->dRed, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMemcpy"));
+            if((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaStreamSynchronize"));
+            ctx->launches += 1;
+            L->hasF = true;
+        }
+        *out = L;
+        return CMG_OK;
+    }
     if((e = cudaMalloc(&L->dL, sizeof(double) * n * n)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMalloc (full matrix)"));
     if((s = cmg_sum_unpack_strided(ctx, dC, cStride, dF, dN, n, L->dL)) != CMG_OK) return bail(s);
     if(cusolverDnCreate(&L->sol) != CUSOLVER_STATUS_SUCCESS || cublasCreate(&L->blas) != CUBLAS_STATUS_SUCCESS)
@@ -1820,8 +1966,12 @@ cmg_status cmg_like_calculate(cmg_like* L, const double* t, int64_t nMaps, doubl
     const int64_t n = L->n;
     CMG_CUDA(ctx, cudaMemcpyAsync(L->dT, t, sizeof(double) * n * nMaps, cudaMemcpyHostToDevice, ctx->stream));
     const double one = 1.0;
-    if(cublasDtrsm(L->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, static_cast<int>(n), static_cast<int>(nMaps), &one,
-                   L->dL, static_cast<int>(n), L->dT, static_cast<int>(n)) != CUBLAS_STATUS_SUCCESS)
+    if(L->dU)
+    {
+        if((s = cmg_packed_cholesky_solve(ctx, L->dU, n, L->dT, nMaps)) != CMG_OK) return s;
+    }
+    else if(cublasDtrsm(L->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, static_cast<int>(n), static_cast<int>(nMaps), &one,
+                        L->dL, static_cast<int>(n), L->dT, static_cast<int>(n)) != CUBLAS_STATUS_SUCCESS)
         return fail(ctx, CMG_ECUDA, "cublasDtrsm failed");
     cmg::columnDotsKernel<<<static_cast<unsigned>(nMaps), 256, 0, ctx->stream>>>(L->dT, L->hasF ? L->dYf : nullptr, n, L->dRed, L->hasF ? L->dRed + nMaps : nullptr);
     CMG_CUDA(ctx, cudaGetLastError());

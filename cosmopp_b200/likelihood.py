@@ -1,9 +1,9 @@
 """Device-resident consumer of the generated matrices: the low-l pixel likelihood of reference source/likelihood.cpp
 (`Likelihood::construct` :68-134, `calculate` :163-180), fed straight from GPU memory -- no round trip of the matrices
-to the host.  Python mirror of include/likelihood.hpp over the C ABI (cmg_like_create / cmg_like_calculate): the
-C + F + N sum / unpack and the chi2 reductions are this repo's kernels, the dense factorisation and the triangular
-solves are plain library calls inside the shared library (cuSOLVER potrf, cuBLAS trsm), the GPU counterpart of the
-reference's LAPACK dpptrf / dpptri.
+to the host.  Python mirror of include/likelihood.hpp over the C ABI (cmg_like_create / cmg_like_calculate): the packed sum
+C + F + N is factorised in place by this library's packed Cholesky (cmg_packed_cholesky: FP64 tensor-core trailing updates
+on the packed triangle, no unpacked copy), the GPU counterpart of the reference's LAPACK dpptrf / dpptri on the same storage;
+Context.set_like_method(1) selects cuSOLVER potrf + cuBLAS trsm on the unpacked matrix instead (kept for comparison).
 """
 import ctypes
 

@@ -337,6 +337,24 @@ cmg_status cmg_sum_unpack(cmg_ctx* ctx, const double* d_c, const double* d_f, co
 cmg_status cmg_sum_unpack_strided(cmg_ctx* ctx, const double* d_c, int64_t c_stride, const double* d_f, const double* d_n,
                                   int64_t n, double* d_full);
 
+/* The factorisation of that consumer, on the device and IN PLACE on the packed triangle: A = U^T U with U upper triangular in the
+ * same packed layout (LAPACK dpptrf 'U', what the reference runs on the host: source/matrix_impl.cpp:236-263 on the storage of
+ * include/matrix_impl.hpp:495-502).  Blocked right-looking; the trailing updates -- the n^3 / 3 -- are FP64 tensor-core
+ * contractions (mma.sync.m8n8k4.f64) whose operands are contiguous runs of packed columns.  Nothing is unpacked: memory is the
+ * n (n + 1) / 2 doubles of the matrix itself, so the 147456-dimensional matrix of Nside = 64 is factorised where the generator
+ * left it.  *info = 0, or k > 0 when the leading minor of order k is not positive definite (d_packed is then partly overwritten). */
+cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* d_packed, int64_t n, int64_t* info);
+/* log det A = 2 sum_i log U_ii from the factor */
+cmg_status cmg_packed_cholesky_logdet(cmg_ctx* ctx, const double* d_factor, int64_t n, double* log_det);
+/* y = U^-T t for n_rhs right-hand sides, in place: d_rhs is n x n_rhs column-major on the device; t^T A^-1 t = |y|^2 */
+cmg_status cmg_packed_cholesky_solve(cmg_ctx* ctx, const double* d_factor, int64_t n, double* d_rhs, int64_t n_rhs);
+/* d_out = C + F + N, all packed of dimension n (d_f, d_n may be NULL; element stride c_stride on d_c as in cmg_sum_unpack_strided;
+ * d_out may be d_c when c_stride = 1) */
+cmg_status cmg_packed_sum(cmg_ctx* ctx, const double* d_c, int64_t c_stride, const double* d_f, const double* d_n, int64_t n, double* d_out);
+/* how cmg_like_create factorises: 0 (default) = cmg_packed_cholesky on the packed sum; 1 = cusolverDnDpotrf on the unpacked
+ * n x n matrix (a plain library call, twice the memory, n <= 46340; kept for comparison) */
+cmg_status cmg_set_like_method(cmg_ctx* ctx, int method);
+
 /* The temperature pixel likelihood of reference source/likelihood.cpp (`Likelihood::construct` :68-134, `calculate`
  * :163-180) with everything resident on the device: C + F + N (packed, device; d_c with element stride c_stride) ->
  * Cholesky factor -> log det - offset (the reference's constant -29677.0566, :126); `foreground` (host, n values or NULL)

@@ -67,8 +67,20 @@ class FakeContext:
     legendre_series = legendre_series_orbit = tqu = tqu_orbit = tqu_orbit_sharded = _launch
     cl_to_cmatrix = cl_to_cmatrix_pol = tqu_orbit_assemble = tqu_scatter_block = tqu_orbit_scatter_inbox = tqu_batched_slab = _launch
 
-    def orbit_strips_to_host(self, shard, host, threads=0):
+    def orbit_strips_to_host(self, shard, host, threads=0, direct_mask=0):
         self.to_host_calls = getattr(self, "to_host_calls", 0) + 1
+
+    def ipc_export(self, ptr):
+        return b"handle-of-%d" % ptr
+
+    def ipc_open(self, handle):
+        return 0x7000000
+
+    def ipc_close(self, ptr):
+        pass
+
+    def copy_on_device(self, dst, src, nbytes):
+        pass
 
     def close(self):
         pass
@@ -105,6 +117,7 @@ def fake_gpu(monkeypatch):
     monkeypatch.setattr(dist, "all_reduce", lambda t, op=None: None)
     monkeypatch.setattr(dist, "broadcast", lambda t, src=0: None)
     monkeypatch.setattr(dist, "all_to_all_single", lambda out, inp, out_splits=None, in_splits=None: None)
+    monkeypatch.setattr(dist, "all_gather_object", lambda lst, obj: [lst.__setitem__(i, obj) for i in range(len(lst))])
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     from cosmopp_b200 import capi
     monkeypatch.setattr(capi, "host_register", lambda a: None)
@@ -155,7 +168,7 @@ def test_single_rank_line(fake_gpu, capsys, monkeypatch, workload, extra, orbit,
     assert ref == line["config"]                         # the reference arm describes the same workload
 
 
-@pytest.mark.parametrize("extra", [[], ["--no-orbit"], ["--gather"], ["--no-orbit", "--gather"]])
+@pytest.mark.parametrize("extra", [[], ["--exchange", "nccl"], ["--no-orbit"], ["--gather"], ["--no-orbit", "--gather"], ["--direct-mask", "0"]])
 def test_rank_of_several(fake_gpu, capsys, monkeypatch, extra):
     argv = ["--workload", "tqu_nside32_lmax96", "--gpus", "4", "--steps", "2", "--warmup", "3"] + extra
     assert _run(fake_gpu, capsys, monkeypatch, argv, rank=3, world=4) is None          # only rank 0 prints
@@ -169,6 +182,7 @@ def test_rank_of_several(fake_gpu, capsys, monkeypatch, extra):
         assert line["gather"]["ms"] > 0 and line["e2e"]["host_matrix_max_abs_diff_vs_device"] is not None
         # N ranks ship at most the matrix once (here: only the last-face columns)
         assert line["e2e"]["d2h_bytes_per_step"] * 4 <= 1.05 * line["config"]["packed_bytes"]
+        assert line["exchange"]["mode"] == ("nccl" if "nccl" in extra else "pull")
     if "--gather" in extra:
         assert line["gather"]["ms"] > 0 and line["gather"]["bytes_per_gpu_in"] > 0
     assert ("orbit-closed" in line["path"]["sharding"]) == ("--no-orbit" not in extra)

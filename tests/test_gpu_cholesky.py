@@ -1,0 +1,106 @@
+"""GPU: the packed in-place Cholesky factorisation and the consumer built on it (cmg_packed_cholesky, cmg_like_*; reference
+source/matrix_impl.cpp:236-263 = LAPACK dpptrf 'U' on the packed storage of include/matrix_impl.hpp:495-502, called from
+Likelihood::construct, source/likelihood.cpp:100-133).  Checked against numpy on the same matrices; tolerance 1e-9 relative for
+chi^2 and log det (the reference's own test compares likelihoods statistically only)."""
+import numpy as np
+import pytest
+
+from conftest import synthetic_cl
+
+pytestmark = pytest.mark.gpu
+
+
+def pack_upper(M):
+    n = M.shape[0]
+    iu = np.triu_indices(n)
+    out = np.empty(n * (n + 1) // 2)
+    out[iu[1] * (iu[1] + 1) // 2 + iu[0]] = M[iu]
+    return out
+
+
+def unpack_upper(p, n):
+    U = np.zeros((n, n))
+    iu = np.triu_indices(n)
+    U[iu] = p[iu[1] * (iu[1] + 1) // 2 + iu[0]]
+    return U
+
+
+def random_spd(n, seed):
+    rs = np.random.RandomState(seed)
+    B = rs.normal(size=(n, n // 2 + 3))
+    return B @ B.T + 0.5 * n * np.diag(rs.uniform(0.5, 1.5, n))
+
+
+@pytest.mark.parametrize("n", [1, 7, 128, 129, 300, 1000, 1537])
+def test_packed_cholesky_matches_numpy(gpu_ctx, n):
+    import torch
+    A = random_spd(n, 100 + n)
+    d = torch.from_numpy(pack_upper(A)).cuda()
+    assert gpu_ctx.packed_cholesky(d, n) == 0
+    U = unpack_upper(d.cpu().numpy(), n)
+    want = np.linalg.cholesky(A).T
+    assert np.abs(U - want).max() <= 1e-12 * np.abs(want).max()
+    assert np.abs(U.T @ U - A).max() <= 1e-13 * np.abs(A).max() * n
+    assert abs(gpu_ctx.packed_cholesky_logdet(d, n) - np.linalg.slogdet(A)[1]) <= 1e-12 * abs(np.linalg.slogdet(A)[1]) + 1e-12
+    # y = U^-T t for several right-hand sides (more than one pass of eight)
+    rs = np.random.RandomState(5)
+    T = rs.normal(size=(11, n))
+    t = torch.from_numpy(T.copy()).cuda()                    # row k = right-hand side k = column-major n x 11
+    gpu_ctx.packed_cholesky_solve(d, n, t, 11)
+    Y = t.cpu().numpy()
+    want_y = np.linalg.solve(want.T, T.T).T
+    assert np.abs(Y - want_y).max() <= 1e-11 * np.abs(want_y).max()
+
+
+def test_packed_cholesky_reports_the_failing_minor(gpu_ctx):
+    import torch
+    n = 400
+    A = random_spd(n, 3)
+    A[250, 250] = -1.0                                       # leading minors up to 250 are fine, the 251st is not
+    d = torch.from_numpy(pack_upper(A)).cuda()
+    assert gpu_ctx.packed_cholesky(d, n) == 251
+
+
+@pytest.mark.parametrize("masked", [True, False])
+def test_tqu_likelihood_consumer_on_the_packed_factor(gpu_ctx, oracle_api, masked):
+    """the polarized matrix this library's headline produces, consumed where it lies: [T;Q;U] at Nside = 16 (BASELINE configs[1];
+    full sky: dimension 9216) + noise -> packed Cholesky -> chi^2, log det for a few maps, against numpy on the oracle's matrix;
+    and against the cuSOLVER route on the same device buffers"""
+    import torch
+    from cosmopp_b200 import capi
+    nside, lmax = 16, 47
+    spectra = synthetic_cl(lmax, pol=True)
+    good = oracle_api.good_pixels_from_mask(oracle_api.like_low_mask(nside)) if masked else None
+    gpu_ctx.set_kernel_variant(0)
+    gpu_ctx.set_pixels(nside, good)
+    n = 3 * gpu_ctx.npix
+    f = capi.window_beam(lmax, 10.0)
+    w = capi.tqu_weights(*spectra, f, f)
+    d_c = torch.empty(capi.packed_size(n), dtype=torch.float64, device="cuda")
+    if good is None:
+        gpu_ctx.tqu_orbit(*w, d_c, 0)
+    else:
+        gpu_ctx.tqu(*w, gpu_ctx.tqu_layout_single(d_c))
+    noise = np.zeros(capi.packed_size(n))
+    sig = np.where(np.arange(n) < n // 3, 2.0, 0.3)         # white noise: 2 muK in T, 0.3 in Q and U
+    noise[np.arange(n) * (np.arange(n) + 1) // 2 + np.arange(n)] = sig ** 2
+    d_n = torch.from_numpy(noise).cuda()
+    rs = np.random.RandomState(11)
+    maps = rs.normal(size=(5, n)) * 10.0
+    from cosmopp_b200.likelihood import Likelihood
+    like = Likelihood(gpu_ctx, d_c, None, d_n, n)
+    _, chi2, logdet = like.calculate(maps)
+    like.close()
+    gpu_ctx.set_like_method(1)
+    try:
+        dense = Likelihood(gpu_ctx, d_c, None, d_n, n)
+        _, chi2_d, logdet_d = dense.calculate(maps)
+        dense.close()
+    finally:
+        gpu_ctx.set_like_method(0)
+    S = oracle_api.unpack_symmetric(oracle_api.tqu_matrix(*spectra, nside, 10.0, good=good), n) + np.diag(sig ** 2)
+    want_logdet = np.linalg.slogdet(S)[1] + 29677.0566
+    want_chi2 = np.einsum("kn,nk->k", maps, np.linalg.solve(S, maps.T))
+    assert np.abs(chi2 - want_chi2).max() <= 1e-9 * np.abs(want_chi2).max()
+    assert abs(logdet - want_logdet) <= 1e-9 * abs(want_logdet)
+    assert np.abs(chi2 - chi2_d).max() <= 1e-9 * np.abs(chi2_d).max() and abs(logdet - logdet_d) <= 1e-9 * abs(logdet_d)
