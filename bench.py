@@ -564,9 +564,8 @@ def run_gpu_arm(args):
             if good is None and args.host_expand != 0 and host.numel() * 8 >= (1 << 30):
                 F = nside * nside
                 d2h_bytes = 8 * sum(partition.packed_size(s * npix + (fc + 1) * F) - partition.packed_size(s * npix + fc * F)
-                                    for s in range(3) for fc in range(12) if (fc & 3) == 3 or (s == 2 and (fc & 3) == 2))
-                note += ("; only the columns of base faces 3, 7, 11 (and, third strip, of faces 2, 6, 10) cross PCIe, host threads fill in "
-                         "the other rotated images (cmg_set_host_expand, cmg_set_host_expand_direct)")
+                                    for s in range(3) for fc in (3, 7, 11))
+                note += "; only the columns of base faces 3, 7, 11 cross PCIe, host threads fill in the rotated images (cmg_set_host_expand)"
         elif kind == "tt" and world == 1:
             del shard, pieces
             torch.cuda.empty_cache()
@@ -591,7 +590,7 @@ def run_gpu_arm(args):
                     torch.cuda.synchronize()
             else:
                 F = nside * nside
-                direct = (0x49 if args.direct_mask < 0 else args.direct_mask) if threads > 0 else 0
+                direct = max(args.direct_mask, 0) if threads > 0 else 0
                 # (strip, face) runs of this rank's columns that cross PCIe: the last face of every ring, plus the direct images
                 runs = [(s, fc) for s in range(3) for fc in range(12)
                         if threads == 0 or (fc & 3) == 3 or ((direct >> (3 * s + (3 - (fc & 3)) - 1)) & 1)]
@@ -794,9 +793,9 @@ def main():
     ap.add_argument("--gather", action="store_true", help="N>1, T,Q,U, every-pair shards: also time the NCCL gather of the whole matrix onto every GPU "
                                                           "(orbit shards: on by default where the matrix fits)")
     ap.add_argument("--no-gather", action="store_true", help="N>1, orbit shards: skip the gather of the whole matrix onto every GPU")
-    ap.add_argument("--direct-mask", type=int, default=-1, metavar="MASK",
+    ap.add_argument("--direct-mask", type=int, default=0, metavar="MASK",
                     help="N>1 e2e leg: images that cross PCIe next to the last-face columns instead of being filled in by host threads "
-                         "(bit 3 strip + k - 1); -1 = 0x49, the first image face of every strip")
+                         "(bit 3 strip + k - 1); default 0 (the host's memory write bandwidth bounds the delivery, whoever writes)")
     ap.add_argument("--exchange", default="pull", choices=["nccl", "pull"],
                     help="N>1, orbit shards: how block(r -> d) of the outboxes reaches rank d -- one NCCL all-to-all + a local scatter kernel, "
                          "or the scatter kernel reading the sender's outbox through CUDA-IPC peer memory")

@@ -116,6 +116,7 @@ _SIGNATURES = {
     "cmg_packed_cholesky_solve": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64]),
     "cmg_packed_sum": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "cmg_set_like_method": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "cmg_like_create_ninv": (ctypes.c_int, [_vp, _vp, _vp, _i64, ctypes.c_double, ctypes.POINTER(_vp)]),
     "cmg_host_register": (ctypes.c_int, [_vp, _i64]),
     "cmg_host_unregister": (ctypes.c_int, [_vp]),
     "cmg_host_expand_rotations": (ctypes.c_int, [_vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),

@@ -5,9 +5,9 @@
 // of Nside = 64 (87 GB packed, 174 GB square) is factorised where the generator left it.
 //
 // Right-looking, block size CH_NB = 128.  Step k (rows k0 .. k0 + kb of U):
-//   cholDiagKernel    one CTA: the kb x kb diagonal block in shared memory, U_kk
+//   cholDiagKernel    one CTA: the kb x kb diagonal block in shared memory, U_kk (sub-blocks of 16 rows)
 //   cholPanelKernel   U[k0.., j] = U_kk^-T A[k0.., j] for every column j behind the block: a thread per column, forward
-//                     substitution; in packed storage the kb rows of a column are one contiguous run
+//                     substitution in blocks of 16 rows; in packed storage the kb rows of a column are one contiguous run
 //   cholSyrkKernel    A[i, j] -= sum_r U[r, i] U[r, j] for k1 <= i <= j: the n^3 / 3 of the work.  This IS a contraction, so it runs
 //                     on the FP64 tensor path (mma.sync.m8n8k4.f64; on B200 its rate equals the DFMA rate, 37 TFLOP/s, but an
 //                     instruction carries 256 FMAs and the operands come from shared memory once per 128 x 128 tile).  Both
@@ -25,23 +25,31 @@ constexpr int CH_LD = CH_NB + 1;           // leading dimension of the diagonal 
 constexpr int CH_TILE = 128;               // syrk: tile edge
 constexpr int CH_KC = 32;                  // syrk: k-chunk staged in shared memory
 constexpr int CH_SLD = CH_KC + 4;          // its leading dimension: (lane / 4) * 36 + lane % 4 hits 16 distinct 8-byte banks per half-warp
-constexpr int CH_PANEL_COLS = 64;          // panel solve: columns (threads) per CTA
+constexpr int CH_PANEL_COLS = 128;         // panel solve: columns (threads) per CTA
 
 __host__ __device__ __forceinline__ long long chOff(long long col) { return col * (col + 1) / 2; }
 
 // ------------------------------------------------------------------------------------------------ diagonal block
-// A[k0 .. k0 + kb, k0 .. k0 + kb] -> U_kk, in place.  Thread t owns column c = t % CH_NB and the rows r = g, g + G, ... <= c
-// (g = t / CH_NB of G = blockDim / CH_NB row groups).  Step j: every thread reads the pivot d = S[j][j] and the two row-j entries
-// it needs, and updates its rows r > j: S[r][c] -= S[j][r] S[j][c] / d; group 0 then scales row j.  *info = k0 + j + 1 (first
-// one wins) when a pivot is not positive (LAPACK's convention).
+// A[k0 .. k0 + kb, k0 .. k0 + kb] -> U_kk, in place: one CTA, the block in shared memory (S(r, c) at chS[c * CH_LD + r], r <= c),
+// factorised in sub-blocks of CH_DB = 16 rows:
+//   (a) warp 0 factorises the 16 x 16 diagonal sub-block (a lane per column, 16 dependent steps);
+//   (b) a thread per column behind it solves its 16 rows against that triangle (registers);
+//   (c) all threads apply the rank-16 update to the rest: thread (column c, row group g) keeps its 16 row-block entries in
+//       registers and walks its rows r = g, g + G, ... <= c -- 16 FMAs per entry read and written.
+// *info = k0 + j + 1 when pivot j is not positive (LAPACK's convention; the first failing block wins).
+constexpr int CH_DB = 16;
+
 __global__ void __launch_bounds__(512)
 cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restrict__ info)
 {
-    extern __shared__ double chS[];                      // [kb][CH_LD], S[c * CH_LD + r], r <= c
-    const int tid = threadIdx.x;
+    extern __shared__ double chS[];                      // [kb][CH_LD]
+    __shared__ int failed;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = tid % CH_NB, g = tid / CH_NB, G = blockDim.x / CH_NB;
     if(*info != 0)
         return;                                          // an earlier block already failed
+    if(tid == 0)
+        failed = 0;
     for(int idx = tid; idx < kb * kb; idx += blockDim.x)
     {
         const int cc = idx / kb, r = idx - cc * kb;
@@ -49,32 +57,80 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
             chS[cc * CH_LD + r] = A[chOff(k0 + cc) + k0 + r];
     }
     __syncthreads();
-    for(int j = 0; j < kb; ++j)
+    for(int jb = 0; jb < kb; jb += CH_DB)
     {
-        const double d = chS[j * CH_LD + j];
-        if(!(d > 0.0))
+        const int wb = min(CH_DB, kb - jb);
+        if(warp == 0)
         {
-            if(tid == 0)
-                *info = k0 + j + 1;
-            return;                                      // the same decision in every thread
-        }
-        const double inv = 1.0 / d;
-        double ujc = 0.0;
-        if(c > j && c < kb)
-        {
-            ujc = chS[c * CH_LD + j];
-            const double s = ujc * inv;
-            // rows r > j of this thread's group
-            int r = j + 1 + ((g - (j + 1)) % G + G) % G;
-            for(; r <= c; r += G)
-                chS[c * CH_LD + r] -= chS[r * CH_LD + j] * s;
+            // (a) lane = column jb + lane of the sub-block
+            for(int j = 0; j < wb; ++j)
+            {
+                const double d = chS[(jb + j) * CH_LD + jb + j];
+                if(!(d > 0.0))
+                {
+                    if(lane == 0)
+                        failed = jb + j + 1;
+                    break;                               // the same in every lane
+                }
+                double ujc = 0.0;
+                if(lane > j && lane < wb)
+                {
+                    ujc = chS[(jb + lane) * CH_LD + jb + j];
+                    const double sc = ujc / d;
+                    for(int r = j + 1; r <= lane; ++r)
+                        chS[(jb + lane) * CH_LD + jb + r] -= chS[(jb + r) * CH_LD + jb + j] * sc;
+                }
+                __syncwarp();
+                if(lane >= j && lane < wb)
+                    chS[(jb + lane) * CH_LD + jb + j] = lane == j ? sqrt(d) : ujc / sqrt(d);
+                __syncwarp();
+            }
         }
         __syncthreads();
-        // row j is final now and never read again by a later step, so no barrier is needed behind the scaling
-        if(g == 0 && c >= j && c < kb)
-            chS[c * CH_LD + j] = c == j ? sqrt(d) : ujc / sqrt(d);
+        if(failed)
+        {
+            if(tid == 0)
+                *info = k0 + failed;
+            return;
+        }
+        // (b) rows jb .. jb + wb of the columns behind the sub-block: x = U_bb^-T b
+        if(tid < kb && tid >= jb + wb)
+        {
+            double x[CH_DB];
+#pragma unroll
+            for(int i = 0; i < CH_DB; ++i)
+            {
+                if(i < wb)
+                {
+                    double acc = chS[tid * CH_LD + jb + i];
+#pragma unroll
+                    for(int q = 0; q < i; ++q)
+                        acc = fma(-chS[(jb + i) * CH_LD + jb + q], x[q], acc);
+                    x[i] = acc / chS[(jb + i) * CH_LD + jb + i];
+                    chS[tid * CH_LD + jb + i] = x[i];
+                }
+            }
+        }
+        __syncthreads();
+        // (c) rank-wb update of everything behind the sub-block
+        if(c < kb && c >= jb + wb)
+        {
+            double uc[CH_DB];
+#pragma unroll
+            for(int i = 0; i < CH_DB; ++i)
+                uc[i] = i < wb ? chS[c * CH_LD + jb + i] : 0.0;
+            const int first = jb + wb;
+            for(int r = first + ((g - first) % G + G) % G; r <= c; r += G)
+            {
+                double acc = chS[c * CH_LD + r];
+#pragma unroll
+                for(int i = 0; i < CH_DB; ++i)
+                    acc = fma(-chS[r * CH_LD + jb + i], uc[i], acc);         // entries i >= wb of a short last sub-block meet uc = 0
+                chS[c * CH_LD + r] = acc;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for(int idx = tid; idx < kb * kb; idx += blockDim.x)
     {
         const int cc = idx / kb, r = idx - cc * kb;
@@ -84,9 +140,12 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ panel
-// Column j >= k1 = k0 + kb: x = U_kk^-T b with b = A[k0 .. k0 + kb, j] (one contiguous run of the packed column), in place.
-// Forward substitution x_r = (b_r - sum_{s < r} U[s][r] x_s) / U[r][r]: U_kk is read through L1 (the same address in every
-// thread, contiguous in s), x lives in shared memory, one column per thread.
+// Column j >= k1 = k0 + kb: x = U_kk^-T b with b = A[k0 .. k0 + kb, j] (one contiguous run of the packed column), in place; one
+// column per thread.  Forward substitution in blocks of 16 rows: the contributions of the rows already solved are 16 independent
+// FMA chains per thread (x_s from shared memory, U[s][r] the same address in every thread, through L1), then the 16 x 16
+// triangle in registers.  (The first version ran one dependent chain per row: 0.4 - 0.8 ms per step, latency bound.)
+constexpr int CH_PB = 16;
+
 __global__ void __launch_bounds__(CH_PANEL_COLS)
 cholPanelKernel(double* __restrict__ A, long long k0, int kb, long long n, const long long* __restrict__ info)
 {
@@ -98,19 +157,33 @@ cholPanelKernel(double* __restrict__ A, long long k0, int kb, long long n, const
     if(j >= n)
         return;
     double* col = A + chOff(j) + k0;
-    for(int r = 0; r < kb; ++r)
+    // kb is a multiple of CH_PB here: only the LAST block of a matrix can be short, and nothing lies behind it
+    for(int rb = 0; rb < kb; rb += CH_PB)
     {
-        const double* u = A + chOff(k0 + r) + k0;        // U[0 .. r][r]
-        double acc0 = col[r], acc1 = 0.0;
-        int s = 0;
-        for(; s + 1 < r; s += 2)
+        double acc[CH_PB];
+        const double* ucol[CH_PB];                       // U[0 ..][rb + i]: column rb + i of the diagonal block
+#pragma unroll
+        for(int i = 0; i < CH_PB; ++i)
         {
-            acc0 = fma(-__ldg(u + s), chX[s * CH_PANEL_COLS + tid], acc0);
-            acc1 = fma(-__ldg(u + s + 1), chX[(s + 1) * CH_PANEL_COLS + tid], acc1);
+            acc[i] = col[rb + i];
+            ucol[i] = A + chOff(k0 + rb + i) + k0;
         }
-        if(s < r)
-            acc0 = fma(-__ldg(u + s), chX[s * CH_PANEL_COLS + tid], acc0);
-        chX[r * CH_PANEL_COLS + tid] = (acc0 + acc1) / __ldg(u + r);
+        for(int s = 0; s < rb; ++s)
+        {
+            const double xs = chX[s * CH_PANEL_COLS + tid];
+#pragma unroll
+            for(int i = 0; i < CH_PB; ++i)
+                acc[i] = fma(-__ldg(ucol[i] + s), xs, acc[i]);
+        }
+#pragma unroll
+        for(int i = 0; i < CH_PB; ++i)
+        {
+            const double x = acc[i] / __ldg(ucol[i] + rb + i);
+            chX[(rb + i) * CH_PANEL_COLS + tid] = x;
+#pragma unroll
+            for(int i2 = i + 1; i2 < CH_PB; ++i2)
+                acc[i2] = fma(-__ldg(ucol[i2] + rb + i), x, acc[i2]);
+        }
     }
     for(int r = 0; r < kb; ++r)
         col[r] = chX[r * CH_PANEL_COLS + tid];
@@ -122,13 +195,17 @@ __device__ __forceinline__ void chDmma(double& c0, double& c1, const double a, c
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Tile (ti <= tj) of the trailing matrix, 128 x 128: C[i][j] -= sum_{r < kb} P[r][i] P[r][j], P[r][x] = A[chOff(x) + k0 + r] the
-// panel just solved (x >= k1).  16 warps as 4 x 4: a warp owns 32 rows x 32 columns = 4 x 4 m8n8 accumulator tiles, which START
-// as the C entries themselves (loaded while the first operand chunk is in flight); the A fragments are negated on the way in, so
-// the tensor-core accumulation leaves C - P^T P and the epilogue is stores only.  The k-chunks of both operands are staged by
-// cp.async as [column][k] with leading dimension 36, double buffered: an A fragment element (row i = lane / 4, k = lane % 4)
-// and a B fragment element (k = lane % 4, column j = lane / 4) are the same access pattern, conflict-free.
-constexpr int CH_SYRK_THREADS = 512;
+// Tile of the trailing matrix, 128 rows (i) x 64 columns (j): C[i][j] -= sum_{r < kb} P[r][i] P[r][j], P[r][x] = A[chOff(x) + k0 + r]
+// the panel just solved (x >= k1).  8 warps as 4 x 2: a warp owns 32 rows x 32 columns = 4 x 4 m8n8 accumulator tiles, which START
+// as the C entries themselves (loaded while the first operand chunk is in flight); the A fragments enter negated (DMMA's operand
+// modifier), so the tensor-core accumulation leaves C - P^T P and the epilogue is stores only.  The k-chunks of both operands are
+// staged by cp.async as [column][k] with leading dimension 36, double buffered: an A fragment element (row i = lane / 4,
+// k = lane % 4) and a B fragment element (k = lane % 4, column j = lane / 4) are the same access pattern, conflict-free.
+// Two CTAs per SM (110 KB of shared memory, 126 registers each): one CTA's loads of C, its barriers and its stores hide behind
+// the other's DMMAs -- the first version (one 128 x 128 CTA of 512 threads per SM) left the DMMA pipe idle 46 % of the time
+// (profiles/r2_syrk_v1_metrics.txt: stalls math-pipe throttle AND wait / lg-throttle / barrier: bursts, then drains).
+constexpr int CH_TJ = 64;                  // syrk: columns of a tile
+constexpr int CH_SYRK_THREADS = 256;
 
 __device__ __forceinline__ void chCpAsync8(double* dstShared, const double* src, bool live)
 {
@@ -137,38 +214,47 @@ __device__ __forceinline__ void chCpAsync8(double* dstShared, const double* src,
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(CH_SYRK_THREADS, 1)
+// tiles behind k1, column block b (64 wide) outermost: it meets the row tiles ti = 0 .. b / 2 (128 high); cumulative count
+__host__ __device__ __forceinline__ long long chSyrkTilesBefore(long long b)
+{
+    const long long m = b >> 1, r = b & 1;
+    return b + m * (m - 1) + r * m;
+}
+
+__global__ void __launch_bounds__(CH_SYRK_THREADS, 2)
 cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const long long* __restrict__ info)
 {
     if(*info != 0)
         return;
-    // tiles of the upper triangle in column-major order: t = tj (tj + 1) / 2 + ti, ti <= tj
     const long long t = blockIdx.x;
-    int tj = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
-    while(static_cast<long long>(tj + 1) * (tj + 2) / 2 <= t) ++tj;
-    while(static_cast<long long>(tj) * (tj + 1) / 2 > t) --tj;
-    const int ti = static_cast<int>(t - static_cast<long long>(tj) * (tj + 1) / 2);
-    extern __shared__ double chSm[];                     // [2 stages][A, B][CH_TILE][CH_SLD]
+    long long bj = static_cast<long long>(2.0 * sqrt(static_cast<double>(t)));
+    while(chSyrkTilesBefore(bj + 1) <= t) ++bj;
+    while(chSyrkTilesBefore(bj) > t) --bj;
+    const int ti = static_cast<int>(t - chSyrkTilesBefore(bj));
+    extern __shared__ double chSm[];                     // [2 stages][CH_TILE + CH_TJ][CH_SLD], then the column offsets
     const long long k1 = k0 + kb;
-    const long long i0 = k1 + static_cast<long long>(ti) * CH_TILE, j0 = k1 + static_cast<long long>(tj) * CH_TILE;
+    const long long i0 = k1 + static_cast<long long>(ti) * CH_TILE, j0 = k1 + bj * CH_TJ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wi = warp >> 2, wj = warp & 3;             // warp tile: rows wi * 32, columns wj * 32
-    const bool diagTile = ti == tj;
-    constexpr int STAGE = 2 * CH_TILE * CH_SLD;
+    const int wi = warp >> 1, wj = warp & 1;             // warp tile: rows wi * 32, columns wj * 32
+    constexpr int STAGE = (CH_TILE + CH_TJ) * CH_SLD;
+    long long* sOff = reinterpret_cast<long long*>(chSm + 2 * STAGE);     // first element of the panel run of every operand column, -1 = none
+    if(tid < CH_TILE + CH_TJ)
+    {
+        const long long x = tid < CH_TILE ? i0 + tid : j0 + (tid - CH_TILE);
+        sOff[tid] = x < n ? chOff(x) + k0 : -1;
+    }
+    __syncthreads();
 
     auto stage = [&](int buf, int kc)
     {
-        double* sA = chSm + buf * STAGE;
-        double* sB = sA + CH_TILE * CH_SLD;
+        double* sP = chSm + buf * STAGE;
         const bool live = kc + lane < kb;
         // a warp copies the 32 k-values of one panel column (256 contiguous bytes) at a time
-        for(int x = warp; x < CH_TILE; x += CH_SYRK_THREADS / 32)
+        for(int x = warp; x < CH_TILE + CH_TJ; x += CH_SYRK_THREADS / 32)
         {
-            const long long ci = i0 + x, cj = j0 + x;
-            const bool li = live && ci < n, lj = live && cj < n;
-            chCpAsync8(sA + x * CH_SLD + lane, li ? A + chOff(ci) + k0 + kc + lane : A, li);
-            if(!diagTile)
-                chCpAsync8(sB + x * CH_SLD + lane, lj ? A + chOff(cj) + k0 + kc + lane : A, lj);
+            const long long off = sOff[x];
+            const bool l = live && off >= 0;
+            chCpAsync8(sP + x * CH_SLD + lane, l ? A + off + kc + lane : A, l);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -176,17 +262,20 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
 
     // accumulators = the C entries: thread holds rows i = .. + lane / 4 and the column pair j = .. + 2 (lane % 4) + {0, 1}
     double acc[4][4][2];
+    const long long iBase = i0 + wi * 32 + (lane >> 2);
 #pragma unroll
     for(int b = 0; b < 4; ++b)
 #pragma unroll
         for(int e = 0; e < 2; ++e)
         {
-            const long long j = j0 + wj * 32 + b * 8 + 2 * (lane & 3) + e;
+            const int jl = wj * 32 + b * 8 + 2 * (lane & 3) + e;
+            const long long j = j0 + jl;
+            const long long cOff = sOff[CH_TILE + jl] - k0;          // chOff(j), or negative when j >= n
 #pragma unroll
             for(int a = 0; a < 4; ++a)
             {
-                const long long i = i0 + wi * 32 + a * 8 + (lane >> 2);
-                acc[a][b][e] = (j < n && i <= j) ? A[chOff(j) + i] : 0.0;
+                const long long i = iBase + a * 8;
+                acc[a][b][e] = (cOff >= 0 && i <= j) ? A[cOff + i] : 0.0;
             }
         }
 
@@ -202,7 +291,7 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const double* sA = chSm + (ch & 1) * STAGE;
-        const double* pB = diagTile ? sA : sA + CH_TILE * CH_SLD;
+        const double* sB = sA + CH_TILE * CH_SLD;
 #pragma unroll
         for(int k4 = 0; k4 < CH_KC; k4 += 4)
         {
@@ -212,7 +301,7 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
                 fa[a] = -sA[(wi * 32 + a * 8 + (lane >> 2)) * CH_SLD + k4 + (lane & 3)];
 #pragma unroll
             for(int b = 0; b < 4; ++b)
-                fb[b] = pB[(wj * 32 + b * 8 + (lane >> 2)) * CH_SLD + k4 + (lane & 3)];
+                fb[b] = sB[(wj * 32 + b * 8 + (lane >> 2)) * CH_SLD + k4 + (lane & 3)];
 #pragma unroll
             for(int a = 0; a < 4; ++a)
 #pragma unroll
@@ -227,13 +316,15 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
 #pragma unroll
         for(int e = 0; e < 2; ++e)
         {
-            const long long j = j0 + wj * 32 + b * 8 + 2 * (lane & 3) + e;
+            const int jl = wj * 32 + b * 8 + 2 * (lane & 3) + e;
+            const long long j = j0 + jl;
+            const long long cOff = sOff[CH_TILE + jl] - k0;
 #pragma unroll
             for(int a = 0; a < 4; ++a)
             {
-                const long long i = i0 + wi * 32 + a * 8 + (lane >> 2);
-                if(j < n && i <= j)                      // upper triangle only (matters on diagonal tiles); i < n follows
-                    A[chOff(j) + i] = acc[a][b][e];
+                const long long i = iBase + a * 8;
+                if(cOff >= 0 && i <= j)                  // upper triangle only (matters on tiles the diagonal crosses); i < n follows
+                    A[cOff + i] = acc[a][b][e];
             }
         }
 }
@@ -323,6 +414,15 @@ packedSumKernel(const double* __restrict__ C, long long cStride, const double* _
         if(N) v += N[e];
         out[e] = v;
     }
+}
+
+// upper triangle of a dense column-major n x n matrix -> packed
+__global__ void __launch_bounds__(256)
+packUpperKernel(const double* __restrict__ full, long long n, double* __restrict__ packed)
+{
+    const long long j = blockIdx.y;
+    for(long long i = blockIdx.x * 256LL + threadIdx.x; i <= j; i += static_cast<long long>(gridDim.x) * 256)
+        packed[chOff(j) + i] = full[j * n + i];
 }
 
 } // namespace cmg

@@ -53,7 +53,7 @@ struct cmg_ctx
 
     cmg::SeriesTable hostT0, hostT20, hostT22;   // host copies of the recurrence tables
     int tquVariant = 0;                          // 0 = automatic choice (see launchTqu)
-    int hostExpandDirectMask = 1 << 6;           // images that cross PCIe next to the last-face columns (bit 3 strip + k - 1)
+    int hostExpandDirectMask = 0;                // images that cross PCIe next to the last-face columns (bit 3 strip + k - 1)
     int hostExpandThreads = -1;                  // full-sky whole calls copy back 27 % and expand on the host: > 0 threads, 0 = plain copy,
                                                  // -1 = automatic (all host cores for matrices of 1 GiB and more; measured 1.27x at 87 GB)
 
@@ -851,8 +851,10 @@ static cmg_status copyBackLastFacesAndExpand(cmg_ctx* ctx, const double* dPacked
     const int64_t n = ctx->npix, facePix = ctx->nside * ctx->nside;
     struct Chunk { int strip, ring, face; int64_t q0, q1; cudaEvent_t arrived; };
     std::vector<Chunk> chunks;
-    // One GPU feeds the host at ~54 GB/s while the host threads write the images at ~80 GB/s (16 cores): the copy engine would
-    // idle half of the time, so the image next to the last face of the third strip (14 % of the matrix) crosses PCIe as well.
+    // Images selected by cmg_set_host_expand_direct cross PCIe as well.  Off by default: on the measured host (16 cores, one
+    // GPU) the copy engine idles for half of the call, yet handing it the third strip's first image made the call SLOWER
+    // (991 ms against 840 ms) -- DMA writes and the host threads' streaming stores draw on one host memory write bandwidth
+    // (~105 GB/s there), which is what bounds the call, not PCIe and not the cores.
     const int directMask = strips == 3 ? ctx->hostExpandDirectMask : 0;
     for(int pass = 0; pass <= 3; ++pass)
         for(int strip = 0; strip < strips; ++strip)
@@ -1717,7 +1719,7 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
     cmg_status s = cholBuffers(ctx);
     if(s != CMG_OK) return s;
     const int diagSmem = cmg::CH_NB * cmg::CH_LD * sizeof(double), panelSmem = cmg::CH_NB * cmg::CH_PANEL_COLS * sizeof(double);
-    const int syrkSmem = 2 * 2 * cmg::CH_TILE * cmg::CH_SLD * sizeof(double);
+    const int syrkSmem = 2 * (cmg::CH_TILE + cmg::CH_TJ) * cmg::CH_SLD * sizeof(double) + (cmg::CH_TILE + cmg::CH_TJ) * sizeof(long long);
     CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diagSmem));
     CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panelSmem));
     CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholSyrkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, syrkSmem));
@@ -1731,10 +1733,12 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
         ctx->launches += 1;
         if(rem <= 0)
             break;
+        // (kb == CH_NB from here on: a short block can only be the last one)
         cmg::cholPanelKernel<<<static_cast<unsigned>((rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS), cmg::CH_PANEL_COLS, panelSmem, ctx->stream>>>(
             dA, k0, kb, n, ctx->dCholInfo);
-        const int64_t tiles = (rem + cmg::CH_TILE - 1) / cmg::CH_TILE;
-        cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles * (tiles + 1) / 2), cmg::CH_SYRK_THREADS, syrkSmem, ctx->stream>>>(dA, k0, kb, n, ctx->dCholInfo);
+        const int64_t colBlocks = (rem + cmg::CH_TJ - 1) / cmg::CH_TJ;           // 64-column blocks; block b meets the row tiles 0 .. b / 2
+        cmg::cholSyrkKernel<<<static_cast<unsigned>(cmg::chSyrkTilesBefore(colBlocks)), cmg::CH_SYRK_THREADS, syrkSmem, ctx->stream>>>(
+            dA, k0, kb, n, ctx->dCholInfo);
         ctx->launches += 2;
     }
     CMG_CUDA(ctx, cudaGetLastError());
@@ -1951,6 +1955,66 @@ cmg_status cmg_like_create(cmg_ctx* ctx, const double* dC, int64_t cStride, cons
     }
     cudaFree(dWork);
     cudaFree(dInfo);
+    *out = L;
+    return CMG_OK;
+}
+
+// reference source/likelihood.cpp:341-406 (LikelihoodPolarization's constructor): cInv = N^-1 + N^-1 C N^-1, Cholesky, log det,
+// inverse.  Here: the two products as plain library GEMMs on the unpacked matrices (cublasDgemm), the packed upper triangle of
+// the result factorised by cmg_packed_cholesky; chi^2 = v^T cInv^-1 v = |U^-T v|^2 comes from cmg_like_calculate.
+cmg_status cmg_like_create_ninv(cmg_ctx* ctx, const double* dC, const double* dNinv, int64_t m, double detOffset, cmg_like** out)
+{
+    if(!ctx || !out) return CMG_EINVAL;
+    *out = nullptr;
+    if(!dC || !dNinv || m < 1 || m > 46340) return fail(ctx, CMG_EINVAL, "cmg_like_create_ninv: null matrix or dimension outside 1 .. 46340");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_like* L = new(std::nothrow) cmg_like;
+    if(!L) return fail(ctx, CMG_ENOMEM, "out of host memory");
+    L->ctx = ctx;
+    L->n = m;
+    double *fC = nullptr, *fN = nullptr, *fT = nullptr;
+    cublasHandle_t blas = nullptr;
+    auto bail = [&](cmg_status st)
+    {
+        if(fC) cudaFree(fC);
+        if(fN) cudaFree(fN);
+        if(fT) cudaFree(fT);
+        if(blas) cublasDestroy(blas);
+        cmg_like_destroy(L);
+        return st;
+    };
+    cudaError_t e;
+    const size_t dense = sizeof(double) * static_cast<size_t>(m) * static_cast<size_t>(m);
+    if((e = cudaMalloc(&fC, dense)) != cudaSuccess || (e = cudaMalloc(&fN, dense)) != cudaSuccess || (e = cudaMalloc(&fT, dense)) != cudaSuccess)
+        return bail(cudaFail(ctx, e, "cudaMalloc (dense work matrices)"));
+    if((e = cudaMalloc(&L->dU, sizeof(double) * cmg_packed_size(m))) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMalloc (packed factor)"));
+    cmg_status s;
+    if((s = cmg_sum_unpack(ctx, dC, nullptr, nullptr, m, fC)) != CMG_OK) return bail(s);
+    if((s = cmg_sum_unpack(ctx, dNinv, nullptr, nullptr, m, fN)) != CMG_OK) return bail(s);
+    if(cublasCreate(&blas) != CUBLAS_STATUS_SUCCESS) return bail(fail(ctx, CMG_ECUDA, "cublasCreate failed"));
+    cublasSetStream(blas, ctx->stream);
+    const double one = 1.0, zero = 0.0;
+    const int mi = static_cast<int>(m);
+    // T = C N^-1;  K = N^-1 T + N^-1 (accumulated onto a copy of N^-1 held in fC afterwards)
+    if(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, mi, mi, mi, &one, fC, mi, fN, mi, &zero, fT, mi) != CUBLAS_STATUS_SUCCESS)
+        return bail(fail(ctx, CMG_ECUDA, "cublasDgemm failed"));
+    if((e = cudaMemcpyAsync(fC, fN, dense, cudaMemcpyDeviceToDevice, ctx->stream)) != cudaSuccess) return bail(cudaFail(ctx, e, "cudaMemcpy"));
+    if(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, mi, mi, mi, &one, fN, mi, fT, mi, &one, fC, mi) != CUBLAS_STATUS_SUCCESS)
+        return bail(fail(ctx, CMG_ECUDA, "cublasDgemm failed"));
+    cmg::packUpperKernel<<<dim3(static_cast<unsigned>(std::min<int64_t>((m + 255) / 256, 64)), static_cast<unsigned>(m)), 256, 0, ctx->stream>>>(fC, m, L->dU);
+    if((e = cudaGetLastError()) != cudaSuccess) return bail(cudaFail(ctx, e, "packUpperKernel"));
+    ctx->launches += 1;
+    int64_t info = 0;
+    if((s = cmg_packed_cholesky(ctx, L->dU, m, &info)) != CMG_OK) return bail(s);
+    if(info != 0)
+        return bail(fail(ctx, CMG_ENUMERIC, "The determinant of the covariance matrix is not positive. The covariance matrix must be positive definite."));
+    double logDet = 0.0;
+    if((s = cmg_packed_cholesky_logdet(ctx, L->dU, m, &logDet)) != CMG_OK) return bail(s);
+    L->logDet = logDet - detOffset;
+    cudaFree(fC);
+    cudaFree(fN);
+    cudaFree(fT);
+    cublasDestroy(blas);
     *out = L;
     return CMG_OK;
 }

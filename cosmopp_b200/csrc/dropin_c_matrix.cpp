@@ -14,6 +14,8 @@
 #include <exception_handler.hpp>
 #include <utils.hpp>
 
+#include "dropin_internal.hpp"
+
 namespace
 {
 [[noreturn]] void raise(const std::string& text)
@@ -30,7 +32,7 @@ void CMatrix::allocate(int nPix)
     const std::int64_t bytes = packedSize() * static_cast<std::int64_t>(sizeof(double));
     void* p = NULL;
     pinned_ = false;
-    // page-locked when a GPU is there (the generators copy device results straight into it)
+    // page-locked when a GPU is there (copies to and from the device run at PCIe speed)
     if(cmg_device_count() > 0 && cmg_host_malloc_pinned(bytes, &p) == CMG_OK)
         pinned_ = true;
     else
@@ -41,37 +43,190 @@ void CMatrix::allocate(int nPix)
     }
     data_ = static_cast<double*>(p);
     std::memset(data_, 0, static_cast<size_t>(bytes));
+    state_.store(kHost, std::memory_order_release);
+}
+
+void CMatrix::dropDevice() const
+{
+    if(dev_)
+    {
+        DropinLock lock(device_);
+        cmg_synchronize(lock.ctx());
+        cmg_device_free(lock.ctx(), dev_);
+        dev_ = NULL;
+    }
+    state_.store(state_.load() & ~kDevice, std::memory_order_release);
 }
 
 void CMatrix::release()
 {
-    if(!data_)
-        return;
-    if(pinned_)
-        cmg_host_free_pinned(data_);
-    else
-        std::free(data_);
-    data_ = NULL;
+    dropDevice();
+    if(data_)
+    {
+        if(pinned_)
+            cmg_host_free_pinned(data_);
+        else
+            std::free(data_);
+        data_ = NULL;
+    }
+    state_.store(0, std::memory_order_release);
 }
 
-CMatrix::CMatrix(int nPix) : nPix_(0), data_(NULL), pinned_(false) { allocate(nPix); }
+CMatrix::CMatrix(int nPix) : nPix_(0), data_(NULL), pinned_(false), dev_(NULL), device_(0), state_(0), symNSide_(0), symStrips_(0) { allocate(nPix); }
 
-CMatrix::CMatrix(const char* fileName) : nPix_(0), data_(NULL), pinned_(false) { readFromFile(fileName); }
-
-CMatrix::CMatrix(const CMatrix& other) : nPix_(0), data_(NULL), pinned_(false), comment_(other.comment_)
+CMatrix::CMatrix(const char* fileName) : nPix_(0), data_(NULL), pinned_(false), dev_(NULL), device_(0), state_(0), symNSide_(0), symStrips_(0)
 {
-    allocate(other.nPix_);
-    std::memcpy(data_, other.data_, static_cast<size_t>(packedSize()) * sizeof(double));
+    readFromFile(fileName);
+}
+
+CMatrix::CMatrix(DeviceOnly, int nPix) : nPix_(nPix), data_(NULL), pinned_(false), dev_(NULL), device_(0), state_(0), symNSide_(0), symStrips_(0)
+{
+    if(nPix <= 0)
+        raise("the number of pixels must be positive.");
+}
+
+CMatrix* CMatrix::newOnDevice(int nPix, int device, double** dPacked, long fullSkyNSide, int strips)
+{
+    CMatrix* m = new CMatrix(DeviceOnly(), nPix);
+    DropinLock lock(device);
+    void* p = NULL;
+    if(cmg_device_malloc(lock.ctx(), m->packedSize() * static_cast<std::int64_t>(sizeof(double)), &p) != CMG_OK)
+    {
+        const std::string text = std::string("CMatrix: ") + cmg_last_error(lock.ctx());
+        delete m;
+        raise(text);
+    }
+    m->dev_ = static_cast<double*>(p);
+    m->device_ = device;
+    m->symNSide_ = fullSkyNSide;
+    m->symStrips_ = strips;
+    m->state_.store(kDevice, std::memory_order_release);
+    if(dPacked)
+        *dPacked = m->dev_;
+    return m;
+}
+
+// first host-side use of a matrix that lives on the device: one copy over PCIe (with the host expansion of the rotated images
+// where the matrix is a full-sky one and large enough for that to pay, cmg_matrix_to_host)
+void CMatrix::hostForRead() const
+{
+    DropinLock lock(device_);
+    if(state_.load(std::memory_order_acquire) & kHost)
+        return;                                  // another thread got here first
+    if(!(state_.load() & kDevice) || !dev_)
+        raise("CMatrix: the matrix holds no data");
+    if(!data_)
+    {
+        const std::int64_t bytes = packedSize() * static_cast<std::int64_t>(sizeof(double));
+        void* p = NULL;
+        if(cmg_host_malloc_pinned(bytes, &p) == CMG_OK)
+            pinned_ = true;
+        else
+        {
+            p = std::malloc(static_cast<size_t>(bytes));
+            pinned_ = false;
+            if(!p)
+                raise("out of memory allocating a covariance matrix");
+        }
+        data_ = static_cast<double*>(p);
+    }
+    int strips = 0;
+    if(symNSide_ > 0 && (symStrips_ == 1 || symStrips_ == 3) && cmg_nside2npix(symNSide_) * symStrips_ == nPix_)
+    {
+        // the symmetric copy needs the full-sky geometry of that nSide bound to the context (someone may have re-bound it)
+        if(cmg_set_pixels(lock.ctx(), symNSide_, NULL, 0) == CMG_OK)
+            strips = symStrips_;
+    }
+    if(cmg_matrix_to_host(lock.ctx(), dev_, nPix_, strips, data_) != CMG_OK)
+        raise(std::string("CMatrix: ") + cmg_last_error(lock.ctx()));
+    state_.store(kHost | kDevice, std::memory_order_release);
+}
+
+void CMatrix::hostForWrite()
+{
+    if(!(state_.load(std::memory_order_acquire) & kHost))
+        hostForRead();
+    dropDevice();                                // the caller is about to change entries: the host copy is the matrix now
+    symNSide_ = 0;
+    symStrips_ = 0;
+}
+
+const double* CMatrix::devicePacked(int device) const
+{
+    DropinLock lock(device);
+    if((state_.load(std::memory_order_acquire) & kDevice) && device_ == device)
+        return dev_;
+    if(state_.load() & kDevice)
+    {
+        hostForRead();                           // lives on another GPU: through the host
+        dropDevice();
+    }
+    if(!(state_.load() & kHost))
+        raise("CMatrix: the matrix holds no data");
+    void* p = NULL;
+    const std::int64_t bytes = packedSize() * static_cast<std::int64_t>(sizeof(double));
+    if(cmg_device_malloc(lock.ctx(), bytes, &p) != CMG_OK || cmg_copy_to_device(lock.ctx(), p, data_, bytes) != CMG_OK ||
+       cmg_synchronize(lock.ctx()) != CMG_OK)
+    {
+        const std::string text = std::string("CMatrix: cannot place the matrix on the GPU: ") + cmg_last_error(lock.ctx());
+        if(p) cmg_device_free(lock.ctx(), p);
+        raise(text);
+    }
+    dev_ = static_cast<double*>(p);
+    device_ = device;
+    state_.store(kHost | kDevice, std::memory_order_release);
+    return dev_;
+}
+
+CMatrix::CMatrix(const CMatrix& other)
+    : nPix_(other.nPix_), data_(NULL), pinned_(false), dev_(NULL), device_(other.device_), state_(0), symNSide_(other.symNSide_),
+      symStrips_(other.symStrips_), comment_(other.comment_)
+{
+    const int st = other.state_.load(std::memory_order_acquire);
+    if(st & kHost)
+    {
+        allocate(other.nPix_);
+        std::memcpy(data_, other.data_, static_cast<size_t>(packedSize()) * sizeof(double));
+    }
+    else if(st & kDevice)
+    {
+        // a device-resident matrix is copied on the device
+        DropinLock lock(other.device_);
+        void* p = NULL;
+        const std::int64_t bytes = packedSize() * static_cast<std::int64_t>(sizeof(double));
+        if(cmg_device_malloc(lock.ctx(), bytes, &p) != CMG_OK || cmg_copy_on_device(lock.ctx(), p, other.dev_, bytes) != CMG_OK ||
+           cmg_synchronize(lock.ctx()) != CMG_OK)
+        {
+            const std::string text = std::string("CMatrix: ") + cmg_last_error(lock.ctx());
+            if(p) cmg_device_free(lock.ctx(), p);
+            raise(text);
+        }
+        dev_ = static_cast<double*>(p);
+        state_.store(kDevice, std::memory_order_release);
+    }
+}
+
+void CMatrix::swap(CMatrix& other)
+{
+    std::swap(nPix_, other.nPix_);
+    std::swap(data_, other.data_);
+    std::swap(pinned_, other.pinned_);
+    std::swap(dev_, other.dev_);
+    std::swap(device_, other.device_);
+    const int a = state_.load(), b = other.state_.load();
+    state_.store(b);
+    other.state_.store(a);
+    std::swap(symNSide_, other.symNSide_);
+    std::swap(symStrips_, other.symStrips_);
+    comment_.swap(other.comment_);
 }
 
 CMatrix& CMatrix::operator=(const CMatrix& other)
 {
     if(this == &other)
         return *this;
-    release();
-    allocate(other.nPix_);
-    std::memcpy(data_, other.data_, static_cast<size_t>(packedSize()) * sizeof(double));
-    comment_ = other.comment_;
+    CMatrix copy(other);                         // may throw: *this is untouched then
+    swap(copy);
     return *this;
 }
 
@@ -89,6 +244,7 @@ std::int64_t CMatrix::index(int i, int j) const
 // int32 nPix | packed doubles | int32 comment length | comment bytes   (reference source/c_matrix.cpp:41-85)
 void CMatrix::writeIntoFile(const char* fileName) const
 {
+    packed();                                    // the host copy (made now if the matrix lives on the device)
     std::FILE* f = std::fopen(fileName, "wb");
     if(!f)
         raise(std::string("Cannot write into output file ") + fileName + ".");
@@ -123,6 +279,8 @@ void CMatrix::readFromFile(const char* fileName)
         raise(std::string("Covariance matrix file ") + fileName + " cannot be read.");
     }
     release();
+    symNSide_ = 0;
+    symStrips_ = 0;
     allocate(n);
     const std::int64_t total = packedSize();
     bool ok = true;
@@ -148,6 +306,7 @@ void CMatrix::readFromFile(const char* fileName)
 // (reference source/c_matrix.cpp:87-112)
 void CMatrix::writeIntoTextFile(const char* fileName) const
 {
+    packed();
     std::ofstream out(fileName);
     if(!out)
         raise(std::string("Cannot write into output file ") + fileName + ".");
@@ -172,6 +331,8 @@ void CMatrix::readFromTextFile(const char* fileName)
     if(!in || n <= 0)
         raise(std::string("Cannot read the input file ") + fileName + ".");
     release();
+    symNSide_ = 0;
+    symStrips_ = 0;
     allocate(n);
     std::string rest;
     std::getline(in, rest);          // remainder of the first line
@@ -218,7 +379,8 @@ void CMatrix::maskMatrix(const char* maskFileName)
     maskMatrix(good);
 }
 
-// gather of reference source/c_matrix.cpp:182-201, on the host: the object lives in host memory
+// gather of reference source/c_matrix.cpp:182-201: on the device when the matrix lives there (maskGatherKernel through
+// cmg_mask_matrix, nothing crosses PCIe), on the host otherwise
 void CMatrix::maskMatrix(const std::vector<int>& goodPixels)
 {
     const int n = static_cast<int>(goodPixels.size());
@@ -227,13 +389,30 @@ void CMatrix::maskMatrix(const std::vector<int>& goodPixels)
     for(int a = 0; a < n; ++a)
         if(goodPixels[a] < 0 || goodPixels[a] >= nPix_)
             raise("invalid index in goodPixels");
+    const int st = state_.load(std::memory_order_acquire);
+    if((st & kDevice) && !(st & kHost) && n <= 65535)
+    {
+        double* dOut = NULL;
+        CMatrix* reduced = newOnDevice(n, device_, &dOut);
+        DropinLock lock(device_);
+        const cmg_status s = cmg_mask_matrix(lock.ctx(), dev_, nPix_, &goodPixels[0], n, dOut);
+        if(s != CMG_OK || cmg_synchronize(lock.ctx()) != CMG_OK)
+        {
+            const std::string text = std::string("CMatrix::maskMatrix: ") + cmg_last_error(lock.ctx());
+            delete reduced;
+            raise(text);
+        }
+        reduced->comment_ = comment_;
+        swap(*reduced);
+        delete reduced;
+        return;
+    }
+    const double* src = packed();
     CMatrix reduced(n);
     std::int64_t k = 0;
     for(int b = 0; b < n; ++b)
         for(int a = 0; a <= b; ++a)
-            reduced.data_[k++] = data_[cmg_packed_index(goodPixels[a], goodPixels[b])];
+            reduced.data_[k++] = src[cmg_packed_index(goodPixels[a], goodPixels[b])];
     reduced.comment_ = comment_;
-    std::swap(nPix_, reduced.nPix_);
-    std::swap(data_, reduced.data_);
-    std::swap(pinned_, reduced.pinned_);
+    swap(reduced);
 }

@@ -23,32 +23,35 @@ namespace
 {
 [[noreturn]] void raise(const std::string& text) { throw StandardException(text); }
 
-std::mutex g_mutex;
-int g_device = 0;
+std::mutex g_mutex;                              // guards the registries below (not the GPU work: that is per device)
+thread_local int t_device = 0;                   // CMatrixGenerator::setDevice is per host thread: one rank / chain per thread can
+                                                 // each drive its own GPU from one process
+bool g_deviceResident = true;
+bool g_polarizationUsesTemperatureWindow = false;
 std::string g_healpixDir;
 struct Window { std::vector<double> t, p; };
 std::map<long, Window> g_windows;
-std::map<int, cmg_ctx*> g_contexts;
-
-cmg_ctx* context()
-{
-    std::map<int, cmg_ctx*>::iterator it = g_contexts.find(g_device);
-    if(it != g_contexts.end())
-        return it->second;
-    cmg_ctx* ctx = NULL;
-    if(cmg_create(&ctx, g_device) != CMG_OK)
-        raise(std::string("CMatrixGenerator: ") + cmg_last_error(NULL));
-    g_contexts[g_device] = ctx;
-    return ctx;
-}
+std::map<int, DropinDevice*> g_devices;
 
 } // namespace
 
-cmg_ctx* cmgDropinContext()
+DropinDevice& cmgDropinDevice(int device)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    return context();
+    std::map<int, DropinDevice*>::iterator it = g_devices.find(device);
+    if(it != g_devices.end())
+        return *it->second;
+    cmg_ctx* ctx = NULL;
+    if(cmg_create(&ctx, device) != CMG_OK)
+        raise(std::string("CMatrixGenerator: ") + cmg_last_error(NULL));
+    DropinDevice* d = new DropinDevice;
+    d->ctx = ctx;
+    d->device = device;
+    g_devices[device] = d;                       // lives until the process ends (objects on that GPU may outlive any scope)
+    return *d;
 }
+
+int cmgDropinCurrentDevice() { return t_device; }
 
 namespace
 {
@@ -169,29 +172,69 @@ void CMatrixGenerator::clearPixelWindow(long nSide)
     g_windows.erase(nSide);
 }
 
-void CMatrixGenerator::setDevice(int device)
+void CMatrixGenerator::setDevice(int device) { t_device = device; }
+
+void CMatrixGenerator::transferCounters(long long& hostToDevice, long long& deviceToHost)
+{
+    DropinLock lock(cmgDropinCurrentDevice());
+    std::int64_t a = 0, b = 0;
+    cmg_transfer_counters(lock.ctx(), &a, &b);
+    hostToDevice = a;
+    deviceToHost = b;
+}
+
+void CMatrixGenerator::setDeviceResident(bool on)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    g_device = device;
+    g_deviceResident = on;
+}
+
+void CMatrixGenerator::setPolarizationUsesTemperatureWindow(bool on)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    g_polarizationUsesTemperatureWindow = on;
+}
+
+namespace
+{
+// the result of a generator: on the device (the default), or in host memory as the reference's objects are
+CMatrix* newResult(int nPix, int device, double** dPacked, long fullSkyNSide, int strips)
+{
+    bool resident;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        resident = g_deviceResident;
+    }
+    if(resident)
+        return CMatrix::newOnDevice(nPix, device, dPacked, fullSkyNSide, strips);
+    *dPacked = NULL;
+    return new CMatrix(nPix);
+}
 }
 
 CMatrix* CMatrixGenerator::clToCMatrix(const std::vector<double>& cl, long nSide, double fwhm, const std::vector<int>* goodPixels,
-                                       const LegendrePolynomialContainer*)
+                                       const LegendrePolynomialContainer* lp)
 {
     if(cl.empty())
         raise("CHECK FAILED");                      // check(!cl.empty()) of reference source/c_matrix_generator.cpp:167
     const int lMax = static_cast<int>(cl.size()) - 1;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    // P_l is recomputed on the GPU whether or not a container is given (recomputing beats reading 1.8 - 58 GB of cached
+    // values); a container that does not describe this call is still an error, as it would be in the reference (:198-204)
+    if(lp && (lp->lMax() < lMax || lp->nPix() != static_cast<int>(goodPixels ? goodPixels->size() : cmg_nside2npix(nSide))))
+        raise("CHECK FAILED");
     std::vector<double> w;
-    pixelWindow(nSide, lMax, false, w);
-    cmg_ctx* ctx = context();
+    cmgDropinPixelWindow(nSide, lMax, false, w);
+    const int device = cmgDropinCurrentDevice();
+    DropinLock lock(device);
+    cmg_ctx* ctx = lock.ctx();
     setPixels(ctx, nSide, goodPixels);
-    CMatrix* m = new CMatrix(static_cast<int>(cmg_npix(ctx)));
-    const cmg_status s = cmg_cl_to_cmatrix(ctx, &cl[0], lMax, fwhm, &w[0], m->packed());
-    if(s != CMG_OK)
+    double* dOut = NULL;
+    CMatrix* m = newResult(static_cast<int>(cmg_npix(ctx)), device, &dOut, goodPixels ? 0 : nSide, 1);
+    const cmg_status s = dOut ? cmg_cl_to_cmatrix_dev(ctx, &cl[0], lMax, fwhm, &w[0], dOut) : cmg_cl_to_cmatrix(ctx, &cl[0], lMax, fwhm, &w[0], m->packed());
+    if(s != CMG_OK || cmg_synchronize(ctx) != CMG_OK)
     {
         delete m;
-        check(ctx, s);
+        check(ctx, s == CMG_OK ? CMG_ECUDA : s);
     }
     return m;
 }
@@ -206,23 +249,27 @@ CMatrix* CMatrixGenerator::clToCMatrix(const char* clFileName, long nSide, int, 
 }
 
 CMatrix* CMatrixGenerator::getFiducialMatrix(const std::vector<double>& cl, long nSide, int lMax, double fwhm, const std::vector<int>* goodPixels,
-                                             const LegendrePolynomialContainer*)
+                                             const LegendrePolynomialContainer* lp)
 {
     const int lMaxMax = static_cast<int>(4 * nSide);
     if(static_cast<int>(cl.size()) < lMaxMax + 1)
         raise("CHECK FAILED");                      // check(cl.size() >= lMaxMax + 1), :709
-    std::lock_guard<std::mutex> lock(g_mutex);
+    if(lp && (lp->lMax() < lMaxMax || lp->nPix() != static_cast<int>(goodPixels ? goodPixels->size() : cmg_nside2npix(nSide))))
+        raise("CHECK FAILED");                      // :726-733
     std::vector<double> w;
-    pixelWindow(nSide, lMaxMax, false, w);
-    cmg_ctx* ctx = context();
+    cmgDropinPixelWindow(nSide, lMaxMax, false, w);
+    const int device = cmgDropinCurrentDevice();
+    DropinLock lock(device);
+    cmg_ctx* ctx = lock.ctx();
     setPixels(ctx, nSide, goodPixels);
-    CMatrix* m = new CMatrix(static_cast<int>(cmg_npix(ctx)));
+    double* dOut = NULL;
+    CMatrix* m = newResult(static_cast<int>(cmg_npix(ctx)), device, &dOut, goodPixels ? 0 : nSide, 1);
     m->comment() = "fiducial matrix";
-    const cmg_status s = cmg_fiducial_matrix(ctx, &cl[0], lMax, fwhm, &w[0], m->packed());
-    if(s != CMG_OK)
+    const cmg_status s = dOut ? cmg_fiducial_matrix_dev(ctx, &cl[0], lMax, fwhm, &w[0], dOut) : cmg_fiducial_matrix(ctx, &cl[0], lMax, fwhm, &w[0], m->packed());
+    if(s != CMG_OK || cmg_synchronize(ctx) != CMG_OK)
     {
         delete m;
-        check(ctx, s);
+        check(ctx, s == CMG_OK ? CMG_ECUDA : s);
     }
     return m;
 }
@@ -251,22 +298,32 @@ CMatrix* CMatrixGenerator::clToCMatrixPol(const std::vector<double>& clTT, const
     if(clTT.empty() || clTE.size() != clTT.size() || clEE.size() != clTT.size() || clBB.size() != clTT.size())
         raise("CMatrixGenerator::clToCMatrixPol: the four spectra must be non-empty and of equal length");
     const int lMax = static_cast<int>(clTT.size()) - 1;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    // HEALPix's temperature window for T, its polarization window for Q and U; the reference's own polarization routine takes
+    // the temperature table for both (source/c_matrix_generator.cpp:534) -- setPolarizationUsesTemperatureWindow(true) does that
+    bool sameWindow;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        sameWindow = g_polarizationUsesTemperatureWindow;
+    }
     std::vector<double> wT, wP;
-    pixelWindow(nSide, lMax, false, wT);
-    pixelWindow(nSide, lMax, true, wP);
-    cmg_ctx* ctx = context();
+    cmgDropinPixelWindow(nSide, lMax, false, wT);
+    cmgDropinPixelWindow(nSide, lMax, !sameWindow, wP);
+    const int device = cmgDropinCurrentDevice();
+    DropinLock lock(device);
+    cmg_ctx* ctx = lock.ctx();
     setPixels(ctx, nSide, goodPixels);
     const std::int64_t dim = 3 * cmg_npix(ctx);
     if(dim > 2147483647)
         raise("CMatrixGenerator::clToCMatrixPol: dimension exceeds the int interface of CMatrix");
-    CMatrix* m = new CMatrix(static_cast<int>(dim));
+    double* dOut = NULL;
+    CMatrix* m = newResult(static_cast<int>(dim), device, &dOut, goodPixels ? 0 : nSide, 3);
     m->comment() = "TQU covariance matrix";
-    const cmg_status s = cmg_cl_to_cmatrix_pol(ctx, &clTT[0], &clTE[0], &clEE[0], &clBB[0], lMax, fwhm, &wT[0], &wP[0], m->packed());
-    if(s != CMG_OK)
+    const cmg_status s = dOut ? cmg_cl_to_cmatrix_pol_dev(ctx, &clTT[0], &clTE[0], &clEE[0], &clBB[0], lMax, fwhm, &wT[0], &wP[0], dOut)
+                              : cmg_cl_to_cmatrix_pol(ctx, &clTT[0], &clTE[0], &clEE[0], &clBB[0], lMax, fwhm, &wT[0], &wP[0], m->packed());
+    if(s != CMG_OK || cmg_synchronize(ctx) != CMG_OK)
     {
         delete m;
-        check(ctx, s);
+        check(ctx, s == CMG_OK ? CMG_ECUDA : s);
     }
     return m;
 }

@@ -7,8 +7,6 @@
 #include <string>
 #include <vector>
 
-#include <cuda_runtime_api.h>
-
 #include <cmg.h>
 #include <exception_handler.hpp>
 #include <likelihood.hpp>
@@ -53,22 +51,10 @@ void pick(const std::vector<double>& map, const std::vector<int>& goodPixels, co
     }
 }
 
-struct DeviceBuffer
-{
-    double* p;
-    DeviceBuffer() : p(NULL) {}
-    ~DeviceBuffer() { if(p) cudaFree(p); }
-    void upload(const CMatrix& m)
-    {
-        const size_t bytes = sizeof(double) * static_cast<size_t>(m.packedSize());
-        if(cudaMalloc(reinterpret_cast<void**>(&p), bytes) != cudaSuccess || cudaMemcpy(p, m.packed(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
-            raise(std::string("Likelihood: cannot place the matrices on the GPU: ") + cudaGetErrorString(cudaGetLastError()));
-    }
-};
 }
 
 Likelihood::Likelihood(const CMatrix& cMatrix, const CMatrix& fiducialMatrix, const CMatrix& noiseMatrix, const char* maskFileName, const char* foregroundFileName)
-    : like_(NULL)
+    : like_(NULL), device_(0)
 {
     long nSideMask = 0, nSideFore = 0;
     std::vector<int> goodPixels;
@@ -89,14 +75,18 @@ Likelihood::Likelihood(const CMatrix& cMatrix, const CMatrix& fiducialMatrix, co
 }
 
 Likelihood::Likelihood(const CMatrix& cMatrix, const CMatrix& fiducialMatrix, const CMatrix& noiseMatrix, const std::vector<int>& goodPixels, const std::vector<double>& foreground)
-    : like_(NULL)
+    : like_(NULL), device_(0)
 {
     construct(cMatrix, fiducialMatrix, noiseMatrix, goodPixels, foreground);
 }
 
 Likelihood::~Likelihood()
 {
-    cmg_like_destroy(like_);
+    if(like_)
+    {
+        DropinLock lock(device_);
+        cmg_like_destroy(like_);
+    }
 }
 
 void Likelihood::construct(const CMatrix& cMatrix, const CMatrix& fiducialMatrix, const CMatrix& noiseMatrix, const std::vector<int>& goodPixels, const std::vector<double>& foreground)
@@ -115,12 +105,16 @@ void Likelihood::construct(const CMatrix& cMatrix, const CMatrix& fiducialMatrix
     if(!foreground.empty() && foreground.size() != goodPixels_.size())
         raise("The foreground map must have one value per unmasked pixel.");
 
-    cmg_ctx* ctx = cmgDropinContext();
-    DeviceBuffer c, f, n;
-    c.upload(cMatrix);
-    f.upload(fiducialMatrix);
-    n.upload(noiseMatrix);
-    const cmg_status s = cmg_like_create(ctx, c.p, 1, f.p, n.p, static_cast<std::int64_t>(goodPixels_.size()),
+    // the three matrices where they are: a matrix a generator produced is already on the GPU (CMatrix is a handle), a host-side
+    // one (generateNoiseMatrix, a file) is uploaded once; nothing comes back to the host.  The factorisation owns its own
+    // packed buffer (cmg_like_create), the inputs stay untouched.
+    device_ = cmgDropinCurrentDevice();
+    DropinLock lock(device_);
+    cmg_ctx* ctx = lock.ctx();
+    const double* c = cMatrix.devicePacked(device_);
+    const double* f = fiducialMatrix.devicePacked(device_);
+    const double* n = noiseMatrix.devicePacked(device_);
+    const cmg_status s = cmg_like_create(ctx, c, 1, f, n, static_cast<std::int64_t>(goodPixels_.size()),
                                          foreground.empty() ? NULL : &foreground[0], &like_);
     if(s == CMG_ENUMERIC)
         raise(cmg_last_error(ctx));           // the reference's text: "The determinant of the covariance matrix is not positive. ..."
@@ -132,9 +126,10 @@ double Likelihood::calculate(const std::vector<double>& t, double& chi2, double&
 {
     if(t.size() != goodPixels_.size())
         raise("CHECK FAILED");                // check() of the reference (source/likelihood.cpp:165)
+    DropinLock lock(device_);
     const cmg_status s = cmg_like_calculate(like_, &t[0], 1, &chi2, &logDet);
     if(s != CMG_OK)
-        raise(std::string("Likelihood: ") + cmg_last_error(cmgDropinContext()));
+        raise(std::string("Likelihood: ") + cmg_last_error(lock.ctx()));
     return chi2 + logDet;
 }
 
@@ -162,9 +157,10 @@ void Likelihood::calculateAll(const std::vector<std::vector<double> >& t, const 
         std::copy(t[k].begin(), t[k].end(), flat.begin() + k * n);
     }
     double logDet = 0;
+    DropinLock lock(device_);
     const cmg_status s = cmg_like_calculate(like_, &flat[0], static_cast<std::int64_t>(numOfMaps), &chi2[0], &logDet);
     if(s != CMG_OK)
-        raise(std::string("Likelihood: ") + cmg_last_error(cmgDropinContext()));
+        raise(std::string("Likelihood: ") + cmg_last_error(lock.ctx()));
     LikelihoodResult res;
     for(size_t k = 0; k < numOfMaps; ++k)
     {
@@ -237,4 +233,138 @@ void Likelihood::readInput(const char* inputListName, const std::vector<int>& go
         mapNames[i] = mapName;
         readMapAndNoise(mapName.c_str(), noiseName.c_str(), goodPixels, nSide, t[i]);
     }
+}
+
+// ---------------------------------------------------------------- LikelihoodPolarization (pixel-space part)
+
+namespace
+{
+// [Q(good); U(good)] restriction of a matrix over [Q(all); U(all)], as reference source/likelihood.cpp:375-389
+CMatrix* restrictQU(const CMatrix& full, const std::vector<int>& goodPixels)
+{
+    const int half = full.getNPix() / 2;
+    std::vector<int> index(2 * goodPixels.size());
+    for(size_t i = 0; i < goodPixels.size(); ++i)
+    {
+        if(goodPixels[i] < 0 || goodPixels[i] >= half)
+            raise("LikelihoodPolarization: unmasked pixel index outside the map");
+        index[i] = goodPixels[i];
+        index[goodPixels.size() + i] = half + goodPixels[i];
+    }
+    CMatrix* reduced = new CMatrix(full);          // a device-resident matrix is copied and gathered on the device
+    reduced->maskMatrix(index);
+    return reduced;
+}
+}
+
+LikelihoodPolarization::LikelihoodPolarization(const CMatrix& cMatrix, long nSide, const std::vector<int>& goodPixels, const CMatrix& nInv)
+    : like_(NULL), device_(0), goodPixels_(goodPixels)
+{
+    construct(cMatrix, nSide, nInv);
+}
+
+LikelihoodPolarization::LikelihoodPolarization(const CMatrix& cMatrix, long nSide, const std::vector<int>& goodPixels, const char* nInvFileName)
+    : like_(NULL), device_(0), goodPixels_(goodPixels)
+{
+    const int size = cMatrix.getNPix();
+    std::ifstream in(nInvFileName);
+    if(!in)
+        raise(std::string("Cannot read the input file ") + nInvFileName + ".");      // the reference's text (source/likelihood.cpp:357)
+    CMatrix nInv(size);
+    for(int i = 0; i < size; ++i)
+        for(int j = 0; j < size; ++j)
+        {
+            double v = 0;
+            in >> v;
+            if(!in)
+                raise(std::string("The file ") + nInvFileName + " does not hold size x size numbers.");
+            if(i <= j)
+                nInv.element(i, j) = v;
+        }
+    construct(cMatrix, nSide, nInv);
+}
+
+void LikelihoodPolarization::construct(const CMatrix& cMatrix, long nSide, const CMatrix& nInv)
+{
+    const int size = cMatrix.getNPix(), goodSize = static_cast<int>(goodPixels_.size());
+    if(size % 2 != 0)
+        raise("polarization c matrix includes q and u parts, so size must be even");       // check() of the reference, :346
+    if(size / 2 < goodSize || goodSize == 0)
+        raise("CHECK FAILED");
+    if(nSide > 0 && static_cast<std::int64_t>(size / 2) != cmg_nside2npix(nSide))
+        raise("LikelihoodPolarization: the covariance matrix does not cover the pixels of this nSide");
+    if(nInv.getNPix() != size)
+        raise("LikelihoodPolarization: the inverse noise matrix must have the dimension of the covariance matrix");
+    CMatrix* c = restrictQU(cMatrix, goodPixels_);
+    CMatrix* ni = NULL;
+    try
+    {
+        ni = restrictQU(nInv, goodPixels_);
+        const int m = 2 * goodSize;
+        nInvGood_.resize(static_cast<size_t>(m) * m);
+        for(int i = 0; i < m; ++i)
+            for(int j = 0; j < m; ++j)
+                nInvGood_[static_cast<size_t>(i) * m + j] = ni->element(i, j);
+        device_ = cmgDropinCurrentDevice();
+        DropinLock lock(device_);
+        const double detOffset = 16078.083180;       // reference source/likelihood.cpp:397
+        const cmg_status s = cmg_like_create_ninv(lock.ctx(), c->devicePacked(device_), ni->devicePacked(device_), m, detOffset, &like_);
+        if(s == CMG_ENUMERIC)
+            raise(cmg_last_error(lock.ctx()));
+        if(s != CMG_OK)
+            raise(std::string("LikelihoodPolarization: ") + cmg_last_error(lock.ctx()));
+    }
+    catch(...)
+    {
+        delete c;
+        delete ni;
+        throw;
+    }
+    delete c;
+    delete ni;
+}
+
+LikelihoodPolarization::~LikelihoodPolarization()
+{
+    if(like_)
+    {
+        DropinLock lock(device_);
+        cmg_like_destroy(like_);
+    }
+}
+
+double LikelihoodPolarization::calculate(const std::vector<double>& v, const std::vector<double>& prediction, double& chi2, double& logDet) const
+{
+    const size_t m = 2 * goodPixels_.size();
+    if(v.size() != m || (!prediction.empty() && prediction.size() != m))
+        raise("CHECK FAILED");                       // check(vCopy.size() == 2 * goodPixels_.size()), :548
+    std::vector<double> vCopy(v);
+    if(!prediction.empty())
+        for(size_t i = 0; i < m; ++i)                // vCopy[i] -= nInv_(i, j) * subtractMap[j], :592-596
+        {
+            double s = 0;
+            for(size_t j = 0; j < m; ++j)
+                s += nInvGood_[i * m + j] * prediction[j];
+            vCopy[i] -= s;
+        }
+    DropinLock lock(device_);
+    const cmg_status s = cmg_like_calculate(like_, &vCopy[0], 1, &chi2, &logDet);
+    if(s != CMG_OK)
+        raise(std::string("LikelihoodPolarization: ") + cmg_last_error(lock.ctx()));
+    return chi2 + logDet;
+}
+
+CMatrix* LikelihoodPolarization::polarizationBlock(const CMatrix& tqu)
+{
+    const int dim = tqu.getNPix();
+    if(dim % 3 != 0)
+        raise("LikelihoodPolarization::polarizationBlock: the matrix is not a [T;Q;U] matrix");
+    const int n = dim / 3;
+    std::vector<int> index(2 * n);
+    for(int i = 0; i < 2 * n; ++i)
+        index[i] = n + i;
+    CMatrix* block = new CMatrix(tqu);
+    block->maskMatrix(index);
+    block->comment() = "QU covariance matrix";
+    return block;
 }

@@ -2,8 +2,6 @@
 #include <string>
 #include <vector>
 
-#include <cuda_runtime_api.h>
-
 #include <cmg.h>
 #include <exception_handler.hpp>
 #include <pixel_likelihood.hpp>
@@ -20,20 +18,12 @@ void check(cmg_ctx* ctx, cmg_status s)
         raise(std::string("PixelLikelihoodTT: ") + cmg_last_error(ctx));
 }
 
-double* upload(const CMatrix& m)
-{
-    double* p = NULL;
-    const size_t bytes = sizeof(double) * static_cast<size_t>(m.packedSize());
-    if(cudaMalloc(reinterpret_cast<void**>(&p), bytes) != cudaSuccess || cudaMemcpy(p, m.packed(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
-        raise(std::string("PixelLikelihoodTT: cannot place the matrices on the GPU: ") + cudaGetErrorString(cudaGetLastError()));
-    return p;
-}
 }
 
 PixelLikelihoodTT::PixelLikelihoodTT(long nSide, int lMax, double fwhm, const std::vector<int>& goodPixels, const CMatrix& fiducialMatrix,
                                      const CMatrix& noiseMatrix, const std::vector<double>& map, const std::vector<double>& foreground, ClModel& model)
-    : nSide_(nSide), lMax_(lMax), goodPixels_(goodPixels), map_(map), foreground_(foreground), model_(model), dFiducial_(NULL), dNoise_(NULL),
-      dC_(NULL), cCapacity_(0), chi2_(0), logDet_(0)
+    : nSide_(nSide), lMax_(lMax), goodPixels_(goodPixels), map_(map), foreground_(foreground), model_(model), fiducial_(fiducialMatrix),
+      noise_(noiseMatrix), device_(cmgDropinCurrentDevice()), dC_(NULL), cCapacity_(0), chi2_(0), logDet_(0)
 {
     const size_t n = goodPixels_.size();
     if(n == 0 || lMax_ < 2)
@@ -44,16 +34,20 @@ PixelLikelihoodTT::PixelLikelihoodTT(long nSide, int lMax, double fwhm, const st
     std::vector<double> w;
     cmgDropinPixelWindow(nSide_, lMax_, false, w);
     windowBeam_.resize(lMax_ + 1);
-    cmg_window_beam(&windowBeam_[0], lMax_, fwhm, &w[0]);
-    dFiducial_ = upload(fiducialMatrix);
-    dNoise_ = upload(noiseMatrix);
+    if(cmg_window_beam(&windowBeam_[0], lMax_, fwhm, &w[0]) != CMG_OK)
+        raise("PixelLikelihoodTT: fwhm must be >= 0");
+    fiducial_.devicePacked(device_);
+    noise_.devicePacked(device_);
 }
 
 PixelLikelihoodTT::~PixelLikelihoodTT()
 {
-    if(dFiducial_) cudaFree(dFiducial_);
-    if(dNoise_) cudaFree(dNoise_);
-    if(dC_) cudaFree(dC_);
+    if(dC_)
+    {
+        DropinLock lock(device_);
+        cmg_synchronize(lock.ctx());
+        cmg_device_free(lock.ctx(), dC_);
+    }
 }
 
 double PixelLikelihoodTT::calculate(double* params, int nParams)
@@ -67,17 +61,28 @@ void PixelLikelihoodTT::calculateBatch(const double* params, int nParams, int nS
 {
     if(nSets < 1 || !like)
         raise("PixelLikelihoodTT: nothing to calculate");
-    cmg_ctx* ctx = cmgDropinContext();
+    // the GPU's context is shared with everything else this process runs on that GPU: the whole evaluation holds its lock
+    DropinLock lock(device_);
+    cmg_ctx* ctx = lock.ctx();
     const std::int64_t n = static_cast<std::int64_t>(goodPixels_.size());
     const std::int64_t packed = cmg_packed_size(n);
-    // the process-wide context may have been used for another mask meanwhile: (re)bind the pixel set (O(N) host work)
+    // the context may have been used for another mask meanwhile: (re)bind the pixel set (O(N) host work)
     check(ctx, cmg_set_pixels(ctx, nSide_, &goodPixels_[0], n));
+    const double* dFiducial = fiducial_.devicePacked(device_);
+    const double* dNoise = noise_.devicePacked(device_);
     if(cCapacity_ < nSets)
     {
-        if(dC_) cudaFree(dC_);
+        if(dC_)
+        {
+            cmg_synchronize(ctx);
+            cmg_device_free(ctx, dC_);
+        }
         dC_ = NULL;
-        if(cudaMalloc(reinterpret_cast<void**>(&dC_), sizeof(double) * packed * nSets) != cudaSuccess)
+        cCapacity_ = 0;
+        void* p = NULL;
+        if(cmg_device_malloc(ctx, static_cast<std::int64_t>(sizeof(double)) * packed * nSets, &p) != CMG_OK)
             raise("PixelLikelihoodTT: out of device memory for the batch of matrices");
+        dC_ = static_cast<double*>(p);
         cCapacity_ = nSets;
     }
     std::vector<double> cl(lMax_ + 1), a(static_cast<size_t>(nSets) * (lMax_ + 1));
@@ -96,7 +101,7 @@ void PixelLikelihoodTT::calculateBatch(const double* params, int nParams, int nS
     for(int s = 0; s < nSets; ++s)
     {
         cmg_like* lk = NULL;
-        const cmg_status st = cmg_like_create(ctx, dC_ + s * packed, 1, dFiducial_, dNoise_, n, foreground_.empty() ? NULL : &foreground_[0], &lk);
+        const cmg_status st = cmg_like_create(ctx, dC_ + s * packed, 1, dFiducial, dNoise, n, foreground_.empty() ? NULL : &foreground_[0], &lk);
         if(st == CMG_ENUMERIC)
             raise(cmg_last_error(ctx));
         check(ctx, st);

@@ -77,8 +77,18 @@ public:
     static void setPixelWindow(long nSide, const std::vector<double>& temperature, const std::vector<double>& polarization);
     static void clearPixelWindow(long nSide);
 
-    // GPU to run on (default 0)
+    // which of the two tables the Q, U part of clToCMatrixPol is smoothed with: HEALPix's polarization window (default), or the
+    // temperature window as in the reference's own polarization routine (source/c_matrix_generator.cpp:534)
+    static void setPolarizationUsesTemperatureWindow(bool on);
+
+    // GPU the calling THREAD's generator calls run on (default 0): several host threads -- one per chain or rank -- can each
+    // drive their own GPU from one process; calls on one GPU are serialised, calls on different GPUs run concurrently
     static void setDevice(int device);
+    // true (default): the generators return matrices that live in GPU memory and reach the host lazily (CMatrix);
+    // false: results are copied to host memory inside the call, as the reference's objects are
+    static void setDeviceResident(bool on);
+    // bytes the calling thread's GPU context has moved over PCIe so far (cmg_transfer_counters): what a test asserts on
+    static void transferCounters(long long& hostToDevice, long long& deviceToHost);
 };
 
 #endif

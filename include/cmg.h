@@ -246,8 +246,8 @@ cmg_status cmg_tqu_orbit_assemble(cmg_ctx* ctx, const cmg_orbit_shard* shard, in
  * flight (cmg_host_expand_rotations restricted to [q_begin, q_end)); threads = 0: all 36 runs are copied.  Page-locked
  * destinations (cmg_host_register) make the copies run at PCIe speed.  direct_mask (with threads > 0), bit 3 s + k - 1: the image
  * of strip s in the k-th face below the last one of every ring is copied over PCIe as well instead of being filled in by the
- * host threads -- the balance between the copy engines and the host's memory bandwidth is the caller's to choose (several GPUs
- * feeding one host: 0x49, the first image face of every strip).  Returns when the rank's columns are complete in host memory. */
+ * host threads -- a balance between the copy engines and the host threads for hosts where the two do not share one memory
+ * write bandwidth (0 on the measured one).  Returns when the rank's columns are complete in host memory. */
 cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, double* host_packed, int threads, int direct_mask);
 /* cudaHostRegister / cudaHostUnregister of caller-owned memory (e.g. a shared mapping) */
 cmg_status cmg_host_register(void* ptr, int64_t bytes);
@@ -271,7 +271,8 @@ cmg_status cmg_host_expand_rotations(double* packed, int64_t nside, int strip_be
  * (round 2, first version; profiles/README.md has the current figure). */
 cmg_status cmg_set_host_expand(cmg_ctx* ctx, int threads);
 /* which images the [T;Q;U] whole call copies over PCIe next to the last-face columns (bit 3 strip + k - 1, as direct_mask of
- * cmg_orbit_strips_to_host); default 0x40: one GPU's copy engine and 16 host cores finish together that way */
+ * cmg_orbit_strips_to_host); default 0.  Measured with 0x40 on a 16-core host: 991 ms against 840 ms for the 87 GB matrix -- the
+ * call is bound by the host's memory WRITE bandwidth (~105 GB/s there), which DMA and streaming stores share. */
 cmg_status cmg_set_host_expand_direct(cmg_ctx* ctx, int direct_mask);
 /* the classes of base-face pairs cmg_tqu_orbit works through (host only; for tests): out[c][CMG_ORBIT_CLASS_INTS] =
  * { row face, column face, only q_row <= q_col, same face, n_images, then for image k = 0..3: row face, column face,
@@ -366,6 +367,12 @@ cmg_status cmg_like_create(cmg_ctx* ctx, const double* d_c, int64_t c_stride, co
  * (with the foreground term when a template was given); -2 log L = chi2[k] + *log_det */
 cmg_status cmg_like_calculate(cmg_like* like, const double* t, int64_t n_maps, double* chi2, double* log_det);
 void cmg_like_destroy(cmg_like* like);
+/* The same consumer in the inverse-noise form of the reference's LikelihoodPolarization (source/likelihood.cpp:341-406):
+ * K = N^-1 + N^-1 C N^-1 from the packed covariance d_c and the packed symmetric inverse noise matrix d_ninv (dimension m, e.g. the
+ * [Q;U] block over the unmasked pixels), factorised on the device; log det K - det_offset (the reference subtracts 16078.083180).
+ * cmg_like_calculate on the handle gives chi2 = v^T K^-1 v for v = N^-1 d (the reference's `v`, source/likelihood.cpp:536-612,
+ * minus N^-1 times the temperature-predicted map, which needs the reference's SHT machinery and is the caller's to subtract). */
+cmg_status cmg_like_create_ninv(cmg_ctx* ctx, const double* d_c, const double* d_ninv, int64_t m, double det_offset, cmg_like** out);
 
 /* ---------------------------------------------------------------- CMatrix files from / to device memory ---- */
 

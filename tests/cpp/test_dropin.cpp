@@ -8,6 +8,7 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <c_matrix.hpp>
@@ -162,6 +163,29 @@ static void cpuTests(const std::string& dir)
 
     // the harmonic-space routes are declared but outside this library's path
     EXPECT(throwsStandard([] { CMatrixGenerator::calculateNoiseMatrix("a", "b", 1.0, 1.0); }));
+
+    // HEALPix pixel window table (reference source/utils.cpp:66-170): HEALPIX_DATA_DIR/pixel_window_n0016.fits, HDU 2, column 1
+    // = temperature, column 2 = polarization, times the beam.  tests/test_dropin_cpp.py wrote the files and checks the numbers.
+    {
+        std::ifstream probe((dir + "/pixel_window_n0016.fits").c_str());
+        if(probe)
+        {
+            CMatrixGenerator::setHealpixDataDir(dir.c_str());
+            std::vector<double> fT, fP, f0;
+            Utils::readPixelWindowFunction(fT, 16, 47, 10.0, false);
+            Utils::readPixelWindowFunction(fP, 16, 47, 10.0, true);
+            Utils::readPixelWindowFunction(f0, 16, 20, 0.0, false);                       // fwhm = 0: the window alone
+            EXPECT(fT.size() == 48 && fP.size() == 48 && f0.size() == 21);
+            std::FILE* f = std::fopen((dir + "/window_read.txt").c_str(), "w");
+            for(int l = 0; l <= 47; ++l)
+                std::fprintf(f, "%.17g %.17g %.17g\n", fT[l], fP[l], l <= 20 ? f0[l] : 0.0);
+            std::fclose(f);
+            // the reference's error behaviour: a table that stops short of lMax, a missing file
+            EXPECT(throwsStandard([&] { std::vector<double> g; Utils::readPixelWindowFunction(g, 16, 64, 10.0, false); }));
+            EXPECT(throwsStandard([&] { std::vector<double> g; Utils::readPixelWindowFunction(g, 32, 10, 10.0, false); }));
+            CMatrixGenerator::setHealpixDataDir("");
+        }
+    }
 }
 
 static void gpuTests(const std::string& dir)
@@ -183,6 +207,35 @@ static void gpuTests(const std::string& dir)
     EXPECT(cMatrix->getNPix() == static_cast<int>(good.size()));
     EXPECT(fiducialMatrix->comment() == "fiducial matrix");
     EXPECT(noiseMatrix->getNPix() == static_cast<int>(good.size()));
+    // the generated matrices live on the GPU; the consumer takes them there: generate -> mask -> factorise -> evaluate moves
+    // no matrix data from the device to the host (the noise matrix is built on the host and goes up once)
+    EXPECT(cMatrix->hasDeviceCopy() && !cMatrix->hasHostCopy() && fiducialMatrix->hasDeviceCopy() && !fiducialMatrix->hasHostCopy());
+    {
+        long long h2d0 = 0, d2h0 = 0, h2d1 = 0, d2h1 = 0;
+        CMatrixGenerator::transferCounters(h2d0, d2h0);
+        std::vector<double> noForeground;
+        Likelihood residentLike(*cMatrix, *fiducialMatrix, *noiseMatrix, good, noForeground);
+        const std::vector<double> maps = readDoubles(dir + "/maps.f64");
+        std::vector<double> t0(maps.begin(), maps.begin() + good.size());
+        double chi2 = 0, logDet = 0;
+        residentLike.calculate(t0, chi2, logDet);
+        CMatrixGenerator::transferCounters(h2d1, d2h1);
+        EXPECT(d2h1 == d2h0);                                                  // zero bytes of matrix data came back
+        EXPECT(h2d1 - h2d0 == 8LL * noiseMatrix->packedSize());                // and only the host-built noise matrix went up
+        EXPECT(!cMatrix->hasHostCopy() && !fiducialMatrix->hasHostCopy());
+        std::FILE* f = std::fopen((dir + "/like_resident.txt").c_str(), "w");
+        std::fprintf(f, "%.17g %.17g\n", chi2, logDet);
+        std::fclose(f);
+        // a copy of a device-resident matrix is made on the device; writing to the copy leaves the original alone
+        CMatrix copy(*cMatrix);
+        EXPECT(copy.hasDeviceCopy() && !copy.hasHostCopy());
+        const double c00 = copy.element(0, 0);                                 // lazily materialised on the host
+        EXPECT(copy.hasHostCopy() && c00 > 0);
+        copy.element(0, 0) = 2 * c00;
+        EXPECT(!copy.hasDeviceCopy() && static_cast<const CMatrix&>(*cMatrix).element(0, 0) == c00);
+        CMatrixGenerator::transferCounters(h2d1, d2h1);
+        EXPECT(d2h1 - d2h0 == 2 * 8LL * cMatrix->packedSize());                // the copy and the original, once each
+    }
     cMatrix->writeIntoFile((dir + "/c.dat").c_str());
     fiducialMatrix->writeIntoFile((dir + "/c_fiducial.dat").c_str());
     noiseMatrix->writeIntoFile((dir + "/c_noise.dat").c_str());
@@ -276,6 +329,111 @@ static void gpuTests(const std::string& dir)
     EXPECT(pol->getNPix() == 3 * static_cast<int>(good.size()));
     pol->writeIntoFile((dir + "/c_pol.dat").c_str());
     delete pol;
+
+    // which pixel window the polarized part is smoothed with: HEALPix's polarization table (default) or, as the reference's own
+    // polarization routine does (source/c_matrix_generator.cpp:534), the temperature table
+    {
+        const std::vector<double> wT = readDoubles(dir + "/win_t.f64"), wP = readDoubles(dir + "/win_p.f64");
+        CMatrixGenerator::setPixelWindow(nSide, wT, wP);
+        CMatrix* a = CMatrixGenerator::clToCMatrixPol(tt, te, ee, bb, nSide, 10.0, &good);
+        a->writeIntoFile((dir + "/c_pol_wtp.dat").c_str());
+        delete a;
+        CMatrixGenerator::setPolarizationUsesTemperatureWindow(true);
+        CMatrix* b = CMatrixGenerator::clToCMatrixPol(tt, te, ee, bb, nSide, 10.0, &good);
+        b->writeIntoFile((dir + "/c_pol_wtt.dat").c_str());
+        delete b;
+        CMatrixGenerator::setPolarizationUsesTemperatureWindow(false);
+        CMatrixGenerator::setPixelWindow(nSide, ones, ones);
+    }
+
+    // LikelihoodPolarization, pixel-space part (reference source/likelihood.cpp:341-406, 536-612): full-sky [T;Q;U] matrix ->
+    // its [Q;U] block -> restricted to the unmasked pixels with a diagonal N^-1 -> chi2 and log det
+    {
+        const long nSideP = 4;
+        const std::vector<double> onesP(static_cast<size_t>(4 * nSideP + 1), 1.0);
+        CMatrixGenerator::setPixelWindow(nSideP, onesP, onesP);
+        std::vector<double> tt4(tt.begin(), tt.begin() + 13), te4(te.begin(), te.begin() + 13), ee4(ee.begin(), ee.begin() + 13), bb4(bb.begin(), bb.begin() + 13);
+        CMatrix* tqu = CMatrixGenerator::clToCMatrixPol(tt4, te4, ee4, bb4, nSideP, 10.0);
+        CMatrix* qu = LikelihoodPolarization::polarizationBlock(*tqu);
+        EXPECT(qu->getNPix() == 2 * 192 && qu->hasDeviceCopy() && !qu->hasHostCopy());
+        qu->writeIntoFile((dir + "/c_qu.dat").c_str());
+        const std::vector<int> goodP = readInts(dir + "/good_p.i32");
+        const std::vector<double> vP = readDoubles(dir + "/v_p.f64"), predP = readDoubles(dir + "/pred_p.f64"), nInvDiag = readDoubles(dir + "/ninv_diag.f64");
+        CMatrix nInv(2 * 192);
+        for(int i = 0; i < 2 * 192; ++i)
+            nInv.element(i, i) = nInvDiag[i];
+        nInv.element(3, 200) = 0.01;                                           // and one off-diagonal entry, so that N^-1 is not just a scaling
+        LikelihoodPolarization likeP(*qu, nSideP, goodP, nInv);
+        double chi2 = 0, logDet = 0, chi2b = 0, logDetb = 0;
+        std::vector<double> none;
+        const double l1 = likeP.calculate(vP, none, chi2, logDet);
+        const double l2 = likeP.calculate(vP, predP, chi2b, logDetb);
+        EXPECT(l1 == chi2 + logDet && l2 == chi2b + logDetb && logDet == logDetb && chi2 != chi2b);
+        std::FILE* f = std::fopen((dir + "/like_pol.txt").c_str(), "w");
+        std::fprintf(f, "%.17g %.17g %.17g\n", chi2, chi2b, logDet);
+        std::fclose(f);
+        // the text-file form of N^-1 (the reference's n_inv.txt) gives the same object
+        {
+            std::ofstream out((dir + "/n_inv.txt").c_str());
+            out.precision(17);
+            for(int i = 0; i < 2 * 192; ++i)
+            {
+                for(int j = 0; j < 2 * 192; ++j)
+                    out << static_cast<const CMatrix&>(nInv).element(i, j) << ' ';
+                out << '\n';
+            }
+        }
+        LikelihoodPolarization likeFile(*qu, nSideP, goodP, (dir + "/n_inv.txt").c_str());
+        double chi2f = 0, logDetf = 0;
+        likeFile.calculate(vP, predP, chi2f, logDetf);
+        EXPECT(std::fabs(chi2f - chi2b) <= 1e-12 * std::fabs(chi2b) && std::fabs(logDetf - logDetb) <= 1e-12 * std::fabs(logDetb));
+        EXPECT(throwsStandard([&] { std::vector<double> shortV(3, 0.0); double a, b; likeP.calculate(shortV, none, a, b); }));
+        EXPECT(throwsStandard([&] { CMatrix odd(5); LikelihoodPolarization bad(odd, 0, goodP, nInv); }));
+        EXPECT(throwsStandard([&] { LikelihoodPolarization bad(*qu, nSideP, goodP, (dir + "/no_such_n_inv.txt").c_str()); }));
+        delete tqu;
+        delete qu;
+    }
+
+    // two host threads on one GPU: a sampler thread evaluating the plug-in while another thread generates matrices for a
+    // different pixel set -- every call holds the device's lock for its duration, so neither sees the other's geometry
+    {
+        struct Flat : public ClModel
+        {
+            std::vector<double> base;
+            void clTT(const double* params, int, std::vector<double>& out) { for(size_t l = 0; l < out.size(); ++l) out[l] = params[0] * base[l]; }
+        } model;
+        model.base = clCopy;
+        const std::vector<double> maps = readDoubles(dir + "/maps.f64");
+        const std::vector<double> t0(maps.begin(), maps.begin() + good.size());
+        std::vector<double> noForeground;
+        CMatrix* fid = CMatrixGenerator::getFiducialMatrix(cl, nSide, lMax, 10.0, &good);
+        CMatrix* noise = CMatrixGenerator::generateNoiseMatrix(nSide, 1e-2);
+        noise->maskMatrix(good);
+        PixelLikelihoodTT plug(nSide, lMax, 10.0, good, *fid, *noise, t0, noForeground, model);
+        double p[1] = {1.1};
+        const double want = plug.calculate(p, 1);
+        std::vector<double> short4(cl.begin(), cl.begin() + 13);
+        CMatrix* ref4 = CMatrixGenerator::clToCMatrix(short4, 4, 10.0);
+        const double ref00 = static_cast<const CMatrix&>(*ref4).element(0, 0), ref17 = static_cast<const CMatrix&>(*ref4).element(1, 7);
+        int bad = 0;
+        std::thread sampler([&] { for(int k = 0; k < 12; ++k) { double q[1] = {1.1}; if(plug.calculate(q, 1) != want) ++bad; } });
+        std::thread generator([&]
+        {
+            for(int k = 0; k < 12; ++k)
+            {
+                CMatrix* m = CMatrixGenerator::clToCMatrix(short4, 4, 10.0);
+                const CMatrix& cm = *m;
+                if(cm.element(0, 0) != ref00 || cm.element(1, 7) != ref17) ++bad;
+                delete m;
+            }
+        });
+        sampler.join();
+        generator.join();
+        EXPECT(bad == 0);
+        delete fid;
+        delete noise;
+        delete ref4;
+    }
 
     // errors surface as StandardException
     EXPECT(throwsStandard([&] { std::vector<double> empty; CMatrixGenerator::clToCMatrix(empty, nSide, 10.0); }));

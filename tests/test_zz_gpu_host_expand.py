@@ -30,7 +30,7 @@ def test_whole_calls_with_host_expansion_match_the_oracle(gpu_ctx, oracle_api, n
         gpu_ctx.cl_to_cmatrix(spectra[0], 10.0, tt)
     finally:
         gpu_ctx.set_host_expand(-1)
-        gpu_ctx.set_host_expand_direct(0x40)
+        gpu_ctx.set_host_expand_direct(0)
     # what crossed PCIe: the last face of every ring and the direct images, nothing else
     F = nside * nside
     expect = 8 * sum(capi.packed_size(s * n + (fc + 1) * F) - capi.packed_size(s * n + fc * F) for s in range(3) for fc in range(12)
