@@ -221,8 +221,8 @@ def config_dict(name, kind, nside, lmax, npix, n_gpus, shard_mode="outbox"):
 
 def path_dict(kind, orbit, n_gpus):
     if orbit:
-        return {"method": "symmetry orbits (cmg_tqu_orbit / cmg_legendre_series_orbit): one evaluation per orbit of pixel pairs under the "
-                          "pi/2 rotation of the HEALPix grid, every image stored -- the same packed matrix",
+        return {"method": "symmetry orbits (cmg_tqu_orbit / cmg_legendre_series_orbit[_sharded]): one evaluation per orbit of pixel pairs under "
+                          "the pi/2 rotation of the HEALPix grid, every image stored -- the same packed matrix",
                 "sharding": "in-face column ranges of all 12 base faces (orbit-closed sets of pixel columns) over %d rank(s)" % n_gpus}
     return {"method": "every pixel pair evaluated (%s)" % ("cmg_tqu" if kind == "tqu" else "cmg_legendre_series"),
             "sharding": "equal-area pixel-column blocks over %d rank(s)" % n_gpus}
@@ -351,10 +351,11 @@ def run_gpu_arm(args):
     # full-sky T,Q,U: the symmetry-orbit path (needs whole 64 x 32 tiles inside a base face and at least one column tile per rank)
     use_orbit = (kind == "tqu" and good is None and nside >= 8 and 2 <= lmax <= 441 and not args.no_orbit
                  and nside * nside // 32 >= world and args.shard_mode == "outbox")
-    # full-sky TT on one GPU: the same orbits without transposed images (cmg_legendre_series_orbit; no sharded form yet)
-    if kind == "tt" and good is None and nside >= 16 and lmax <= 1023 and not args.no_orbit and world == 1:
+    # full-sky TT: the same orbits (cmg_legendre_series_orbit with transposed images on one GPU; several ranks take the plan
+    # without them, cmg_legendre_series_orbit_sharded: no entry leaves the rank that evaluated it)
+    if kind == "tt" and good is None and nside >= 16 and lmax <= 1023 and not args.no_orbit and nside * nside // 16 >= world:
         use_orbit = True
-    orbit_mode = 0 if kind == "tqu" else 1
+    orbit_mode = 0 if (kind == "tqu" or world == 1) else 1
     orbit_pairs_all = partition.orbit_pairs_in_range(0, nside * nside, nside * nside, orbit_mode) if use_orbit else None
     if kind == "tqu" and not use_orbit and 2 <= lmax <= 441:
         ctx.set_kernel_variant(142)          # pins the every-pair kernel for the whole-call e2e leg as well (0 = automatic routing)
@@ -371,12 +372,17 @@ def run_gpu_arm(args):
 
     if kind == "tt":
         weights = capi.tt_weights(synthetic_cl(lmax), f)
-        shard = torch.empty(partition.tt_shard_size(a0, a1), dtype=torch.float64, device="cuda")
-        launch = lambda: ctx.legendre_series(weights, shard, a0, a1)
-        if use_orbit:
-            launch = lambda: ctx.legendre_series_orbit(weights, shard)
-            my_pairs = orbit_pairs_all                   # pixel pairs EVALUATED (1 / 3.2 of those stored)
-        pieces = [shard]
+        if not use_orbit:
+            shard = torch.empty(partition.tt_shard_size(a0, a1), dtype=torch.float64, device="cuda")
+            launch = lambda: ctx.legendre_series(weights, shard, a0, a1)
+            pieces = [shard]
+        else:
+            from cosmopp_b200 import multigpu
+            tt_sharded = multigpu.OrbitShardedTT(ctx, nside, rank, world)
+            launch = lambda: tt_sharded.generate(weights)
+            my_pairs = tt_sharded.pairs                  # pixel pairs EVALUATED (a quarter of those stored on one GPU, 1 / 3.2 on several)
+            shard = tt_sharded.strips.tensor()
+            pieces = [shard]
     else:
         from cosmopp_b200 import multigpu
         spectra = synthetic_cl(lmax, pol=True)

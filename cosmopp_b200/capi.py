@@ -102,6 +102,7 @@ _SIGNATURES = {
     "cmg_tqu_orbit_sharded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(OrbitShard), ctypes.c_int]),
     "cmg_tqu_orbit_assemble": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), ctypes.c_int, ctypes.c_int, _vp]),
     "cmg_legendre_series_orbit": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "cmg_legendre_series_orbit_sharded": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _i64, _vp]),
     "cmg_orbit_outbox_layout": (ctypes.c_int, [_i64, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp]),
     "cmg_tqu_orbit_scatter_inbox": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), ctypes.c_int, ctypes.c_int, _vp]),
     "cmg_orbit_strips_to_host": (ctypes.c_int, [_vp, ctypes.POINTER(OrbitShard), _vp, ctypes.c_int, ctypes.c_int]),
@@ -401,6 +402,12 @@ class Context:
 
     def tqu_dev(self, d_a, lmax, layout):
         self._check(self._L.cmg_tqu_dev(self._h, _p(d_a), int(lmax), ctypes.byref(layout)))
+
+    def legendre_series_orbit_sharded(self, a, q_begin, q_end, strip_ptrs):
+        """a rank's columns of the full-sky TT matrix over symmetry orbits: 12 strips, no exchange (include/cmg.h)"""
+        a = _f64(a)
+        ptrs = (_vp * 12)(*[_vp(int(p)) for p in strip_ptrs])
+        self._check(self._L.cmg_legendre_series_orbit_sharded(self._h, _p(a), len(a) - 1, int(q_begin), int(q_end), ctypes.cast(ptrs, _vp)))
 
     def tqu_orbit(self, a_tt, a_te, a_ee, a_bb, d_packed, mode=0):
         """full-sky path: one evaluation per orbit of pixel pairs under the pi/2 rotation of the grid (include/cmg.h)"""

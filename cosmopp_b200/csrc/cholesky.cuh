@@ -40,11 +40,12 @@ __host__ __device__ __forceinline__ long long chOff(long long col) { return col 
 constexpr int CH_DB = 16;
 
 __global__ void __launch_bounds__(512)
-cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restrict__ info)
+cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restrict__ info, double* __restrict__ invDiag)
 {
     extern __shared__ double chS[];                      // [kb][CH_LD]
     __shared__ int failed;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double sPivot, sRow[CH_DB], sInv[CH_NB];   // sInv[r] = 1 / U(r, r): the solves multiply, a double division is ~300 cycles
+    const int tid = threadIdx.x;
     const int c = tid % CH_NB, g = tid / CH_NB, G = blockDim.x / CH_NB;
     if(*info != 0)
         return;                                          // an earlier block already failed
@@ -60,31 +61,40 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
     for(int jb = 0; jb < kb; jb += CH_DB)
     {
         const int wb = min(CH_DB, kb - jb);
-        if(warp == 0)
+        if(tid < CH_DB * CH_DB)
         {
-            // (a) lane = column jb + lane of the sub-block
+            // (a) thread (r, c) keeps element S(jb + r, jb + c) of the sub-block in a register; step j: the pivot and then row j
+            // go through shared memory to everyone, every element of the remaining triangle is updated at once -- 16 steps of
+            // two (256-thread) barriers instead of a dependent walk through shared memory per lane
+            const int r = tid >> 4, cc = tid & (CH_DB - 1);
+            const bool mine = r <= cc && cc < wb;
+            double v = mine ? chS[(jb + cc) * CH_LD + jb + r] : 0.0;
             for(int j = 0; j < wb; ++j)
             {
-                const double d = chS[(jb + j) * CH_LD + jb + j];
+                if(r == j && cc == j)
+                    sPivot = v;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const double d = sPivot;
                 if(!(d > 0.0))
                 {
-                    if(lane == 0)
+                    if(tid == 0)
                         failed = jb + j + 1;
-                    break;                               // the same in every lane
+                    break;                               // the same in all 256 threads
                 }
-                double ujc = 0.0;
-                if(lane > j && lane < wb)
+                if(r == j && cc >= j && cc < wb)
                 {
-                    ujc = chS[(jb + lane) * CH_LD + jb + j];
-                    const double sc = ujc / d;
-                    for(int r = j + 1; r <= lane; ++r)
-                        chS[(jb + lane) * CH_LD + jb + r] -= chS[(jb + r) * CH_LD + jb + j] * sc;
+                    const double root = sqrt(d);
+                    v = cc == j ? root : v / root;
+                    sRow[cc] = v;
+                    if(cc == j)
+                        sInv[jb + j] = 1.0 / root;
                 }
-                __syncwarp();
-                if(lane >= j && lane < wb)
-                    chS[(jb + lane) * CH_LD + jb + j] = lane == j ? sqrt(d) : ujc / sqrt(d);
-                __syncwarp();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if(mine && r > j)
+                    v = fma(-sRow[r], sRow[cc], v);
             }
+            if(mine)
+                chS[(jb + cc) * CH_LD + jb + r] = v;
         }
         __syncthreads();
         if(failed)
@@ -106,7 +116,7 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
 #pragma unroll
                     for(int q = 0; q < i; ++q)
                         acc = fma(-chS[(jb + i) * CH_LD + jb + q], x[q], acc);
-                    x[i] = acc / chS[(jb + i) * CH_LD + jb + i];
+                    x[i] = acc * sInv[jb + i];
                     chS[tid * CH_LD + jb + i] = x[i];
                 }
             }
@@ -137,22 +147,36 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
         if(r <= cc)
             A[chOff(k0 + cc) + k0 + r] = chS[cc * CH_LD + r];
     }
+    if(tid < kb)
+        invDiag[tid] = sInv[tid];
 }
 
 // ------------------------------------------------------------------------------------------------ panel
 // Column j >= k1 = k0 + kb: x = U_kk^-T b with b = A[k0 .. k0 + kb, j] (one contiguous run of the packed column), in place; one
 // column per thread.  Forward substitution in blocks of 16 rows: the contributions of the rows already solved are 16 independent
-// FMA chains per thread (x_s from shared memory, U[s][r] the same address in every thread, through L1), then the 16 x 16
-// triangle in registers.  (The first version ran one dependent chain per row: 0.4 - 0.8 ms per step, latency bound.)
+// FMA chains per thread, then the 16 x 16 triangle in registers.  U_kk (packed, 66 KB), the reciprocals of its diagonal and the
+// solved x (128 KB) all live in shared memory: every operand of the inner loop is a shared-memory read, U at a warp-uniform
+// address.  (First version: one dependent chain per row, 0.4 - 0.8 ms per step; second: U through L1 and divisions,
+// 0.23 ms, stall long_scoreboard 9 cycles per instruction -- profiles/r2_chol_panel_v2_metrics.txt.)
 constexpr int CH_PB = 16;
+constexpr int CH_PANEL_SMEM_DOUBLES = CH_NB * CH_PANEL_COLS + CH_NB * (CH_NB + 1) / 2 + CH_NB;
 
 __global__ void __launch_bounds__(CH_PANEL_COLS)
-cholPanelKernel(double* __restrict__ A, long long k0, int kb, long long n, const long long* __restrict__ info)
+cholPanelKernel(double* __restrict__ A, long long k0, int kb, long long n, const long long* __restrict__ info,
+                const double* __restrict__ invDiag)
 {
-    extern __shared__ double chX[];                      // [kb][CH_PANEL_COLS]
+    extern __shared__ double chX[];                      // [kb][CH_PANEL_COLS], then U_kk packed, then 1 / diagonal
     if(*info != 0)
         return;
+    double* sU = chX + CH_NB * CH_PANEL_COLS;            // U(s, r) at sU[r (r + 1) / 2 + s]
+    double* sInv = sU + CH_NB * (CH_NB + 1) / 2;
     const int tid = threadIdx.x;
+    for(int r = 0; r < kb; ++r)                          // column r of the block: r + 1 contiguous doubles
+        if(tid <= r)
+            sU[r * (r + 1) / 2 + tid] = A[chOff(k0 + r) + k0 + tid];
+    if(tid < kb)
+        sInv[tid] = invDiag[tid];
+    __syncthreads();
     const long long j = k0 + kb + static_cast<long long>(blockIdx.x) * CH_PANEL_COLS + tid;
     if(j >= n)
         return;
@@ -161,28 +185,28 @@ cholPanelKernel(double* __restrict__ A, long long k0, int kb, long long n, const
     for(int rb = 0; rb < kb; rb += CH_PB)
     {
         double acc[CH_PB];
-        const double* ucol[CH_PB];                       // U[0 ..][rb + i]: column rb + i of the diagonal block
+        const double* ucol[CH_PB];                       // U(0 .., rb + i): column rb + i of the diagonal block
 #pragma unroll
         for(int i = 0; i < CH_PB; ++i)
         {
             acc[i] = col[rb + i];
-            ucol[i] = A + chOff(k0 + rb + i) + k0;
+            ucol[i] = sU + (rb + i) * (rb + i + 1) / 2;
         }
         for(int s = 0; s < rb; ++s)
         {
             const double xs = chX[s * CH_PANEL_COLS + tid];
 #pragma unroll
             for(int i = 0; i < CH_PB; ++i)
-                acc[i] = fma(-__ldg(ucol[i] + s), xs, acc[i]);
+                acc[i] = fma(-ucol[i][s], xs, acc[i]);
         }
 #pragma unroll
         for(int i = 0; i < CH_PB; ++i)
         {
-            const double x = acc[i] / __ldg(ucol[i] + rb + i);
+            const double x = acc[i] * sInv[rb + i];
             chX[(rb + i) * CH_PANEL_COLS + tid] = x;
 #pragma unroll
             for(int i2 = i + 1; i2 < CH_PB; ++i2)
-                acc[i2] = fma(-__ldg(ucol[i2] + rb + i), x, acc[i2]);
+                acc[i2] = fma(-ucol[i2][rb + i], x, acc[i2]);
         }
     }
     for(int r = 0; r < kb; ++r)
@@ -249,12 +273,24 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
     {
         double* sP = chSm + buf * STAGE;
         const bool live = kc + lane < kb;
-        // a warp copies the 32 k-values of one panel column (256 contiguous bytes) at a time
-        for(int x = warp; x < CH_TILE + CH_TJ; x += CH_SYRK_THREADS / 32)
+        // a warp copies the 32 k-values of one panel column (256 contiguous bytes) at a time; the column offsets are read
+        // eight at a time (the first version read one, waited for it, issued one copy: a quarter of the loop's stall samples)
+        constexpr int PER_WARP = (CH_TILE + CH_TJ) / (CH_SYRK_THREADS / 32);
+        static_assert(PER_WARP % 8 == 0, "staging loop is unrolled by eight");
+#pragma unroll
+        for(int m0 = 0; m0 < PER_WARP; m0 += 8)
         {
-            const long long off = sOff[x];
-            const bool l = live && off >= 0;
-            chCpAsync8(sP + x * CH_SLD + lane, l ? A + off + kc + lane : A, l);
+            long long off[8];
+#pragma unroll
+            for(int m = 0; m < 8; ++m)
+                off[m] = sOff[warp + (m0 + m) * (CH_SYRK_THREADS / 32)];
+#pragma unroll
+            for(int m = 0; m < 8; ++m)
+            {
+                const int x = warp + (m0 + m) * (CH_SYRK_THREADS / 32);
+                const bool l = live && off[m] >= 0;
+                chCpAsync8(sP + x * CH_SLD + lane, l ? A + off[m] + kc + lane : A, l);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };

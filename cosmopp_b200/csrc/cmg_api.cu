@@ -1240,18 +1240,12 @@ cmg_status cmg_tqu_orbit(cmg_ctx* ctx, const double* att, const double* ate, con
     return cmg_tqu_orbit_sharded(ctx, att, ate, aee, abb, lmax, &shard, mode);
 }
 
-cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, double* dOut)
+namespace
 {
-    cmg_status s = checkReady(ctx, lmax);
-    if(s != CMG_OK) return s;
-    if(!a || !dOut) return fail(ctx, CMG_EINVAL, "null argument");
-    if(!ctx->fullSky)
-        return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs the full sky in NESTED order (cmg_set_pixels with good_nest = NULL)");
-    if(ctx->nside < 16)
-        return fail(ctx, CMG_EUNSUPPORTED, "the TT symmetry-orbit path needs nside >= 16 (whole 128 x 16 tiles inside a base face)");
-    if(lmax + 1 > cmg::TT_STATIC_STEPS)
-        return fail(ctx, CMG_EUNSUPPORTED, "lmax exceeds the static coefficient table");
-    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+// TT over orbits: columns [q0, q1) of all twelve faces into strip[f] (f F + [q0, q1) each); mode 0 needs the single owner
+cmg_status launchTtOrbit(cmg_ctx* ctx, const double* a, int lmax, int mode, int64_t q0, int64_t q1, double* const* strip)
+{
+    const int64_t facePix = ctx->nside * ctx->nside;
     static thread_local cmg::TtStaticTable T;
     for(int i = 0; i < cmg::TT_STATIC_STEPS; ++i)
     {
@@ -1259,17 +1253,79 @@ cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, do
         T.s[i] = make_double2(k <= lmax ? a[k] * ctx->hostT0.N[k] : 0.0, -ctx->hostT0.g[k + 1]);
     }
     const int entrySlot = cmg::TT_STATIC_STEPS - 1 - lmax;
-    cmg::OrbitPlan plan;
-    cmg::orbitBuildPlan(ctx->nside, 1, -1, plan);        // no transposed images: every store is a direct one
-    const int64_t facePix = ctx->nside * ctx->nside;
-    if((facePix / cmg::TT_ROWS) * (facePix / cmg::TT_COLS) > 0x7fffffffLL)
+    cmg::OrbitTtShardDev sh;
+    sh.q0 = static_cast<int>(q0);
+    sh.q1 = static_cast<int>(q1);
+    for(int f = 0; f < 12; ++f)
+        sh.strip[f] = strip[f] - cmg::packedOffset(f * facePix + q0);
+    const int64_t tiles64 = (facePix / cmg::TT_ROWS) * ((q1 - q0) / cmg::TT_COLS);
+    if(tiles64 > 0x7fffffffLL)
         return fail(ctx, CMG_EUNSUPPORTED, "too many tiles for one launch");
-    const dim3 grid(static_cast<unsigned>((facePix / cmg::TT_ROWS) * (facePix / cmg::TT_COLS)), static_cast<unsigned>(plan.n));
+    if(tiles64 == 0)
+        return CMG_OK;
     KernelTimer timer(ctx);
-    cmg::legendreSeriesOrbitKernel<8, 4><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, dOut);
-    CMG_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    const int masks[3] = {0, 8, 12};
+    for(int m = 0; m < (mode == 0 ? 3 : 1); ++m)
+    {
+        cmg::OrbitPlan plan;
+        cmg::orbitBuildPlan(ctx->nside, mode, mode == 0 ? masks[m] : -1, plan);
+        if(plan.n == 0)
+            continue;
+        const dim3 grid(static_cast<unsigned>(tiles64), static_cast<unsigned>(plan.n));
+        if(mode != 0 || masks[m] == 0)
+            cmg::legendreSeriesOrbitKernel<8, 4, 0><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
+        else if(masks[m] == 8)
+            cmg::legendreSeriesOrbitKernel<8, 4, 8><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
+        else
+            cmg::legendreSeriesOrbitKernel<8, 4, 12><<<grid, cmg::TT_ROWS, 0, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
+        CMG_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
     return timer.finish();
+}
+
+cmg_status ttOrbitReady(cmg_ctx* ctx, const double* a, int lmax)
+{
+    cmg_status s = checkReady(ctx, lmax);
+    if(s != CMG_OK) return s;
+    if(!a) return fail(ctx, CMG_EINVAL, "null argument");
+    if(!ctx->fullSky)
+        return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs the full sky in NESTED order (cmg_set_pixels with good_nest = NULL)");
+    if(ctx->nside < 16)
+        return fail(ctx, CMG_EUNSUPPORTED, "the TT symmetry-orbit path needs nside >= 16 (whole 128 x 16 tiles inside a base face)");
+    if(lmax + 1 > cmg::TT_STATIC_STEPS)
+        return fail(ctx, CMG_EUNSUPPORTED, "lmax exceeds the static coefficient table");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return CMG_OK;
+}
+} // namespace
+
+cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, double* dOut)
+{
+    cmg_status s = ttOrbitReady(ctx, a, lmax);
+    if(s != CMG_OK) return s;
+    if(!dOut) return fail(ctx, CMG_EINVAL, "null argument");
+    const int64_t facePix = ctx->nside * ctx->nside;
+    double* strip[12];
+    for(int f = 0; f < 12; ++f)
+        strip[f] = dOut + cmg::packedOffset(f * facePix);
+    // the single owner takes the plan with transposed images: a quarter of the pairs evaluated
+    return launchTtOrbit(ctx, a, lmax, 0, 0, facePix, strip);
+}
+
+cmg_status cmg_legendre_series_orbit_sharded(cmg_ctx* ctx, const double* a, int lmax, int64_t qBegin, int64_t qEnd, double* const* dStrips)
+{
+    cmg_status s = ttOrbitReady(ctx, a, lmax);
+    if(s != CMG_OK) return s;
+    const int64_t facePix = ctx->nside * ctx->nside;
+    if(!dStrips || qBegin < 0 || qEnd > facePix || qBegin > qEnd || qBegin % cmg::TT_COLS || qEnd % cmg::TT_COLS)
+        return fail(ctx, CMG_EINVAL, "shard range must be multiples of 16 inside [0, nside^2]");
+    for(int f = 0; f < 12 && qEnd > qBegin; ++f)
+        if(!dStrips[f]) return fail(ctx, CMG_EINVAL, "shard: null strip");
+    // without transposed images every entry lands in a column of the rank that evaluated it: no exchange.  A range that is the
+    // whole face is the single owner again and may take them.
+    const int mode = (qBegin == 0 && qEnd == facePix) ? 0 : 1;
+    return launchTtOrbit(ctx, a, lmax, mode, qBegin, qEnd, dStrips);
 }
 
 namespace
@@ -1706,7 +1762,7 @@ cmg_status cholBuffers(cmg_ctx* ctx)
     if(!ctx->dCholInfo)
         CMG_CUDA(ctx, cudaMalloc(&ctx->dCholInfo, sizeof(long long)));
     if(!ctx->dCholRed)
-        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholRed, sizeof(double) * 4));
+        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholRed, sizeof(double) * (4 + cmg::CH_NB)));      // reductions, then 1 / diagonal of a block
     return CMG_OK;
 }
 }
@@ -1718,7 +1774,7 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     cmg_status s = cholBuffers(ctx);
     if(s != CMG_OK) return s;
-    const int diagSmem = cmg::CH_NB * cmg::CH_LD * sizeof(double), panelSmem = cmg::CH_NB * cmg::CH_PANEL_COLS * sizeof(double);
+    const int diagSmem = cmg::CH_NB * cmg::CH_LD * sizeof(double), panelSmem = cmg::CH_PANEL_SMEM_DOUBLES * sizeof(double);
     const int syrkSmem = 2 * (cmg::CH_TILE + cmg::CH_TJ) * cmg::CH_SLD * sizeof(double) + (cmg::CH_TILE + cmg::CH_TJ) * sizeof(long long);
     CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diagSmem));
     CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panelSmem));
@@ -1728,14 +1784,14 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
     for(int64_t k0 = 0; k0 < n; k0 += cmg::CH_NB)
     {
         const int kb = static_cast<int>(std::min<int64_t>(cmg::CH_NB, n - k0));
-        cmg::cholDiagKernel<<<1, 512, diagSmem, ctx->stream>>>(dA, k0, kb, ctx->dCholInfo);
+        cmg::cholDiagKernel<<<1, 512, diagSmem, ctx->stream>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4);
         const int64_t rem = n - k0 - kb;
         ctx->launches += 1;
         if(rem <= 0)
             break;
         // (kb == CH_NB from here on: a short block can only be the last one)
         cmg::cholPanelKernel<<<static_cast<unsigned>((rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS), cmg::CH_PANEL_COLS, panelSmem, ctx->stream>>>(
-            dA, k0, kb, n, ctx->dCholInfo);
+            dA, k0, kb, n, ctx->dCholInfo, ctx->dCholRed + 4);
         const int64_t colBlocks = (rem + cmg::CH_TJ - 1) / cmg::CH_TJ;           // 64-column blocks; block b meets the row tiles 0 .. b / 2
         cmg::cholSyrkKernel<<<static_cast<unsigned>(cmg::chSyrkTilesBefore(colBlocks)), cmg::CH_SYRK_THREADS, syrkSmem, ctx->stream>>>(
             dA, k0, kb, n, ctx->dCholInfo);

@@ -455,22 +455,34 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
 }
 
 // ------------------------------------------------------------------------------------------------
-// TT over symmetry orbits (cmg_legendre_series_orbit; the whole-call TT entry points take it on the full sky).
-// legendreSeriesKernel's tile (128 rows x 16 columns, a thread owns a row
-// and walks the columns R at a time) addressed by (class, tile) of the plan WITHOUT transposed images (mode 1: every image has
-// row pixel < column pixel, so every store is a direct one, lanes along the row): 22.5 of 72 face-pair units, 3.2x less work.
-// out = entry (0, 0) of the whole packed triangle of dimension N.
+// TT over symmetry orbits (cmg_legendre_series_orbit, cmg_legendre_series_orbit_sharded; the whole-call TT entry points take it
+// on the full sky).  legendreSeriesKernel's tile (128 rows x 16 columns, a thread owns a row and walks the columns R at a time)
+// addressed by (class, tile) of the plan.
+//   One owner: the plan WITH transposed images (mode 0: 18 of 72 face-pair units, a quarter of the work).  A straight image is
+//   one direct store per column (lanes along the row: 256-byte runs); a transposed image puts entry (a', b') into column a' --
+//   the thread's R consecutive column pixels are R consecutive rows there: one 64-byte run per thread.  Uncoalesced across the
+//   warp, but a store per 2 (lmax - 1) FMAs of the series: it does not show behind the FP64 pipe.
+//   Several ranks: the plan WITHOUT transposed images (mode 1, 22.5 units) -- every image then has its row pixel before its
+//   column pixel, every entry lands in a column of the rank that computed it, and there is nothing to exchange.
+// SWAPMASK as in tquOrbitKernel (one launch per mask: the flags must be compile-time constants for ptxas to keep the series
+// coefficients in uniform registers).  strip[f] = ADJUSTED base of the packed columns f F + [q0, q1).
 // ------------------------------------------------------------------------------------------------
-template <int R, int MINB>
+struct OrbitTtShardDev
+{
+    int q0, q1;
+    double* strip[12];
+};
+
+template <int R, int MINB, int SWAPMASK>
 __global__ void __launch_bounds__(TT_ROWS, MINB)
 legendreSeriesOrbitKernel(const __grid_constant__ TtStaticTable T, Geometry geo, int entrySlot,
-                          const __grid_constant__ OrbitPlan plan, double* __restrict__ out)
+                          const __grid_constant__ OrbitPlan plan, const __grid_constant__ OrbitTtShardDev sh)
 {
     const OrbitClass& oc = plan.c[blockIdx.y];
     const int facePix = plan.facePix;
     const int tilesPerFaceRows = facePix / TT_ROWS;
     const int qRow0 = static_cast<int>(blockIdx.x % tilesPerFaceRows) * TT_ROWS;
-    const int qCol0 = static_cast<int>(blockIdx.x / tilesPerFaceRows) * TT_COLS;
+    const int qCol0 = sh.q0 + static_cast<int>(blockIdx.x / tilesPerFaceRows) * TT_COLS;
     const int tri = oc.tri;
     if(tri && qRow0 > qCol0 + TT_COLS - 1)
         return;                              // q_row > q_col everywhere
@@ -502,15 +514,29 @@ legendreSeriesOrbitKernel(const __grid_constant__ TtStaticTable T, Geometry geo,
         {
             if(k < nImg)
             {
+                const bool sw = (SWAPMASK >> k) & 1;
                 const long long ip = static_cast<long long>(oc.imgRowFace[k]) * facePix + qRow;
                 const long long jp0 = static_cast<long long>(oc.imgColFace[k]) * facePix + qCol0 + c;
-                double* colPtr = out + packedOffset(jp0) + ip;
-#pragma unroll
-                for(int r = 0; r < R; ++r)
+                if(!sw)
                 {
-                    if(!tri || qRow <= qCol0 + c + r)
-                        __stcs(colPtr, b1[r]);
-                    colPtr += jp0 + r + 1;                     // next column starts (column index + 1) entries further
+                    double* colPtr = sh.strip[oc.imgColFace[k]] + packedOffset(jp0) + ip;
+#pragma unroll
+                    for(int r = 0; r < R; ++r)
+                    {
+                        if(!tri || qRow <= qCol0 + c + r)
+                            __stcs(colPtr, b1[r]);
+                        colPtr += jp0 + r + 1;                     // next column starts (column index + 1) entries further
+                    }
+                }
+                else
+                {
+                    // transposed image: its row pixel a' = ip has the larger index; the q_row == q_col pairs of a q_row <= q_col
+                    // class are image 0's own
+                    double* rowPtr = sh.strip[oc.imgRowFace[k]] + packedOffset(ip) + jp0;
+#pragma unroll
+                    for(int r = 0; r < R; ++r)
+                        if(!tri || qRow < qCol0 + c + r)
+                            __stcs(rowPtr + r, b1[r]);
                 }
             }
         }

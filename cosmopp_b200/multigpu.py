@@ -313,3 +313,43 @@ class OrbitShardedTQU:
         self.inbox = None
         for b in self.pieces():
             b.free()
+
+
+class OrbitShardedTT:
+    """Rank-local storage of a full-sky TT matrix generated over symmetry orbits (cmg_legendre_series_orbit_sharded): the rank
+    owns the in-face column range [q0, q1) of all twelve base faces -- 12 contiguous runs of packed columns.  The sharded form
+    uses the plan without transposed images, so every entry lands in a column of the rank that evaluated it: the strips are
+    complete when the kernel ends, nothing is exchanged."""
+
+    def __init__(self, ctx, nside, rank, world):
+        self.ctx, self.nside, self.rank, self.world = ctx, nside, rank, world
+        self.face_pix = nside * nside
+        self.npix = 12 * self.face_pix
+        self.mode = 0 if world == 1 else 1
+        self.bounds = partition.orbit_partition(nside, world, self.mode, align=16)
+        self.q0, self.q1 = self.bounds[rank], self.bounds[rank + 1]
+        self.sizes = [partition.packed_size(f * self.face_pix + self.q1) - partition.packed_size(f * self.face_pix + self.q0) for f in range(12)]
+        self.strips = DeviceBuffer(ctx, sum(self.sizes))
+        self.ptrs, off = [], 0
+        for f in range(12):
+            self.ptrs.append(self.strips.ptr + 8 * off)
+            off += self.sizes[f]
+        self.pairs = partition.orbit_pairs_in_range(self.q0, self.q1, self.face_pix, self.mode)
+
+    def generate(self, weights):
+        self.ctx.legendre_series_orbit_sharded(weights, self.q0, self.q1, self.ptrs)
+
+    def pieces(self):
+        return [self.strips]
+
+    def place_into(self, full):
+        """this rank's 12 runs into a whole packed triangle on this GPU"""
+        off = 0
+        for f in range(12):
+            if self.sizes[f]:
+                first = partition.packed_size(f * self.face_pix + self.q0)
+                self.ctx.copy_on_device(full[first:first + self.sizes[f]], self.strips.ptr + 8 * off, 8 * self.sizes[f])
+            off += self.sizes[f]
+
+    def close(self):
+        self.strips.free()

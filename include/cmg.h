@@ -252,11 +252,18 @@ cmg_status cmg_orbit_strips_to_host(cmg_ctx* ctx, const cmg_orbit_shard* shard, 
 /* cudaHostRegister / cudaHostUnregister of caller-owned memory (e.g. a shared mapping) */
 cmg_status cmg_host_register(void* ptr, int64_t bytes);
 cmg_status cmg_host_unregister(void* ptr);
-/* The TT matrix of cmg_legendre_series (any series weights: clToCMatrix, getFiducialMatrix) over the same orbits, without
- * transposed images: 22.5 of the 72 face-pair units, 3.2x less recurrence work (Nside=64 lmax=192: 8.7 ms against 27.4 ms).
- * Full sky, nside >= 16, d_out = the whole packed triangle of dimension N.  cmg_cl_to_cmatrix / cmg_fiducial_matrix take this
- * path by themselves on the full sky (any non-zero cmg_set_kernel_variant pins the every-pair kernels). */
+/* The TT matrix of cmg_legendre_series (any series weights: clToCMatrix, getFiducialMatrix) over the same orbits.  One owner:
+ * the plan with transposed images, 18 of the 72 face-pair units -- a quarter of the recurrence work; a transposed image is stored
+ * as one 64-byte run per thread, which does not show behind the series.  Full sky, nside >= 16, d_out = the whole packed triangle
+ * of dimension N.  cmg_cl_to_cmatrix / cmg_fiducial_matrix take this path by themselves on the full sky (any non-zero
+ * cmg_set_kernel_variant pins the every-pair kernels). */
 cmg_status cmg_legendre_series_orbit(cmg_ctx* ctx, const double* a, int lmax, double* d_out);
+/* The same over several GPUs: a rank owns the in-face range [q_begin, q_end) (multiples of 16) of all twelve base faces and
+ * writes the packed columns f nside^2 + [q_begin, q_end) into d_strips[f] (entry (0, first column) first; 12 contiguous pieces of
+ * the packed triangle).  It uses the plan WITHOUT transposed images (22.5 of 72 units): every image then has its row pixel before
+ * its column pixel, so every entry lands in a column of the rank that evaluated it -- no outbox, no exchange, the strips are
+ * complete when the kernel ends. */
+cmg_status cmg_legendre_series_orbit_sharded(cmg_ctx* ctx, const double* a, int lmax, int64_t q_begin, int64_t q_end, double* const* d_strips);
 /* Host half of a full-sky whole call (pure CPU): `packed` is a packed matrix of dimension N (TT) or 3N ([T;Q;U]) in HOST memory
  * whose columns of the last face of every ring of four base faces (faces 3, 7, 11, of each strip) are filled in; the columns
  * of the other faces in [face_begin, face_end), strips [strip_begin, strip_end), are written as their rotated images (runs

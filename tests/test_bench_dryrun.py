@@ -64,7 +64,7 @@ class FakeContext:
     def _launch(self, *a, **k):
         self.launches += 1
 
-    legendre_series = legendre_series_orbit = tqu = tqu_orbit = tqu_orbit_sharded = _launch
+    legendre_series = legendre_series_orbit = legendre_series_orbit_sharded = tqu = tqu_orbit = tqu_orbit_sharded = _launch
     cl_to_cmatrix = cl_to_cmatrix_pol = tqu_orbit_assemble = tqu_scatter_block = tqu_orbit_scatter_inbox = tqu_batched_slab = _launch
 
     def orbit_strips_to_host(self, shard, host, threads=0, direct_mask=0):
@@ -199,3 +199,12 @@ def test_batched_workload_line(fake_gpu, capsys, monkeypatch):
         assert k in line, k
     assert line["config"]["n_batch"] == 40 and line["roofline"]["algorithmic_flop_per_unit"] == 8.0 and line["roofline"]["hbm_write_gbs"] > 0
     assert line["gpu_launches"] == 2 and "element" in line["unit"]
+
+
+def test_tt_rank_of_several_takes_orbit_shards(fake_gpu, capsys, monkeypatch):
+    """BASELINE configs[2] on several GPUs: orbit shards without transposed images, no exchange"""
+    argv = ["--workload", "tt_nside32_lmax96", "--gpus", "8", "--steps", "2", "--warmup", "3"]
+    line = _run(fake_gpu, capsys, monkeypatch, argv, rank=0, world=8)
+    assert line["n_gpus"] == 8 and "symmetry orbits" in line["path"]["method"] and line["exchange"] is None
+    r = line["roofline"]
+    assert r["evaluated_pixel_pairs"] * 8 < 0.4 * r["stored_pixel_pairs_all_ranks"]          # 22.5 / 72 of the pairs, an eighth of them here

@@ -171,6 +171,36 @@ def test_tt_orbit_matches_the_every_pair_kernel(gpu_ctx, oracle_api, nside, lmax
     assert np.abs(got - want).max() <= 1e-13 * want[0]
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_tt_orbit_shards_fill_the_matrix_without_exchange(gpu_ctx, oracle_api, world):
+    """cmg_legendre_series_orbit_sharded: every rank's 12 runs of packed columns (generated one after the other on this GPU)
+    placed into one triangle = the oracle's matrix; nothing but the strips exists"""
+    import torch
+    from cosmopp_b200 import capi, multigpu
+    nside, lmax = 16, 47
+    gpu_ctx.set_kernel_variant(0)
+    gpu_ctx.set_pixels(nside)
+    n = gpu_ctx.npix
+    cl = synthetic_cl(lmax)
+    a = capi.tt_weights(cl, capi.window_beam(lmax, 10.0))
+    full = torch.full((capi.packed_size(n),), float("nan"), dtype=torch.float64, device="cuda")
+    pairs = 0
+    for r in range(world):
+        sh = multigpu.OrbitShardedTT(gpu_ctx, nside, r, world)
+        sh.strips.tensor().fill_(float("nan"))
+        sh.generate(a)
+        sh.place_into(full)
+        torch.cuda.synchronize()
+        pairs += sh.pairs
+        sh.close()
+    got = full.cpu().numpy()
+    assert not np.isnan(got).any()
+    want = oracle_api.cl_to_cmatrix(cl, nside, 10.0)
+    assert np.abs(got - want).max() <= REL_TOL * want[0]
+    f = nside * nside
+    assert abs(pairs - (18.0 if world == 1 else 22.5) * f * f) <= 6 * f
+
+
 def test_tt_whole_call_takes_the_orbit_path_on_the_full_sky(gpu_ctx, oracle_api):
     """cl_to_cmatrix and fiducial_matrix (series weights a_0 = a_1 != 0 as well) against the oracle"""
     import torch

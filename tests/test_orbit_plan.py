@@ -233,35 +233,83 @@ def test_sharded_store_rules_partition_the_triangle(oracle_matrix, mode, world):
     check_sharded_store_rules(nside, n, M, mode, world)
 
 
-def test_tt_orbit_store_rules_fill_the_triangle_exactly_once():
-    """legendreSeriesOrbitKernel (cmg_legendre_series_orbit, not yet run on a GPU): 128 x 16 tiles of the plan without
-    transposed images, one direct store per image."""
-    nside, lmax = 16, 20
-    F, n = nside * nside, 12 * nside * nside
-    M = api.unpack_symmetric(api.cl_to_cmatrix(synthetic_cl(lmax), nside, 10.0), n)
-    size = capi.packed_size(n)
-    out = np.full(size, np.nan)
-    count = np.zeros(size, dtype=np.int32)
+def emulate_tt_stores(plan, nside, M, q0, q1, out, count):
+    """legendreSeriesOrbitKernel: 128 x 16 tiles over the columns [q0, q1) of the plan; a straight image is one direct store per
+    column, a transposed image puts entry (a', b') into column a' (rows = the image of the tile's column pixels)"""
+    F = nside * nside
     rows, cols = 128, 16                  # TT_ROWS, TT_COLS
     il = np.arange(rows)[:, None]
     jl = np.arange(cols)[None, :]
-    for c in capi.orbit_plan(nside, 1):
-        assert not any(swap for _, _, swap in c["images"])
+    for c in plan:
         for tr in range(F // rows):
-            for tc in range(F // cols):
-                q_row0, q_col0 = tr * rows, tc * cols
+            for tc in range((q1 - q0) // cols):
+                q_row0, q_col0 = tr * rows, q0 + tc * cols
                 if c["tri"] and q_row0 > q_col0 + cols - 1:
                     continue
-                live = np.broadcast_to((not c["tri"]) | (q_row0 + il <= q_col0 + jl), (rows, cols))
+                dq = (q_col0 + jl) - (q_row0 + il)
                 val = M[c["row_face"] * F + q_row0 + il + 0 * jl, c["col_face"] * F + q_col0 + jl + 0 * il]
-                for fr, fc, _ in c["images"]:
+                for fr, fc, swap in c["images"]:
+                    ip = fr * F + q_row0 + il + 0 * jl
                     jp = fc * F + q_col0 + jl + 0 * il
-                    pos = jp * (jp + 1) // 2 + fr * F + q_row0 + il
+                    if not swap:
+                        live = np.broadcast_to((not c["tri"]) | (dq >= 0), (rows, cols))
+                        pos = jp * (jp + 1) // 2 + ip
+                    else:
+                        live = np.broadcast_to((not c["tri"]) | (dq > 0), (rows, cols))
+                        assert (ip[live] > jp[live]).all()             # the row image has the larger pixel index
+                        pos = ip * (ip + 1) // 2 + jp
                     np.add.at(count, pos[live], 1)
                     out[pos[live]] = val[live]
+
+
+@pytest.fixture(scope="module")
+def tt_matrix16():
+    nside, lmax = 16, 20
+    n = 12 * nside * nside
+    return nside, n, api.unpack_symmetric(api.cl_to_cmatrix(synthetic_cl(lmax), nside, 10.0), n)
+
+
+def test_tt_orbit_store_rules_fill_the_triangle_exactly_once(tt_matrix16):
+    """one owner: the plan WITH transposed images (18 units), every entry of the triangle stored exactly once"""
+    nside, n, M = tt_matrix16
+    size = capi.packed_size(n)
+    out = np.full(size, np.nan)
+    count = np.zeros(size, dtype=np.int32)
+    plan = capi.orbit_plan(nside, 0)
+    assert any(swap for c in plan for _, _, swap in c["images"])
+    emulate_tt_stores(plan, nside, M, 0, nside * nside, out, count)
     assert count.min() == 1 and count.max() == 1
     want, _ = packed_from_full(M)
     assert np.abs(out - want).max() < 1e-11 * M[0, 0]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tt_orbit_sharded_store_rules(tt_matrix16, world):
+    """several ranks: the plan WITHOUT transposed images; a rank's stores stay inside its own packed columns (no exchange) and
+    the ranks together fill the triangle once"""
+    from cosmopp_b200 import partition
+    nside, n, M = tt_matrix16
+    F = nside * nside
+    size = capi.packed_size(n)
+    plan = capi.orbit_plan(nside, 1)
+    assert not any(swap for c in plan for _, _, swap in c["images"])
+    bounds = partition.orbit_partition(nside, world, 1, align=16)
+    total = np.zeros(size, dtype=np.int32)
+    merged = np.full(size, np.nan)
+    for r in range(world):
+        out = np.full(size, np.nan)
+        count = np.zeros(size, dtype=np.int32)
+        emulate_tt_stores(plan, nside, M, bounds[r], bounds[r + 1], out, count)
+        pos = np.nonzero(count)[0]
+        col = np.floor((np.sqrt(8.0 * pos + 1) - 1) / 2).astype(np.int64)
+        col -= (col * (col + 1) // 2 > pos)
+        q = col % F
+        assert ((q >= bounds[r]) & (q < bounds[r + 1])).all()
+        total += count
+        merged = np.where(count > 0, out, merged)
+    assert total.min() == 1 and total.max() == 1
+    want, _ = packed_from_full(M)
+    assert np.abs(merged - want).max() < 1e-11 * M[0, 0]
 
 
 def test_orbit_plan_rejects_bad_arguments():
