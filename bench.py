@@ -355,7 +355,7 @@ def run_gpu_arm(args):
     # without them, cmg_legendre_series_orbit_sharded: no entry leaves the rank that evaluated it)
     if kind == "tt" and good is None and nside >= 16 and lmax <= 1023 and not args.no_orbit and nside * nside // 16 >= world:
         use_orbit = True
-    orbit_mode = 0 if (kind == "tqu" or world == 1) else 1
+    orbit_mode = 0 if (kind == "tqu" or (world == 1 and nside >= 32)) else 1
     orbit_pairs_all = partition.orbit_pairs_in_range(0, nside * nside, nside * nside, orbit_mode) if use_orbit else None
     if kind == "tqu" and not use_orbit and 2 <= lmax <= 441:
         ctx.set_kernel_variant(142)          # pins the every-pair kernel for the whole-call e2e leg as well (0 = automatic routing)
@@ -650,6 +650,44 @@ def run_gpu_arm(args):
             e2e["host_matrix_max_abs_diff_vs_device"] = max_over_ranks(same)
             shared.close()
 
+    # ---- one GPU, matrices up to 2 GB: the whole chain a sampler step runs with the consumer on the device -- C_l from host
+    # memory in, the matrix generated into device memory, + white noise, packed in-place Cholesky, chi^2 and log det of one map
+    # back (16 bytes); the matrix never crosses PCIe
+    consumer = None
+    dim = npix * (3 if kind == "tqu" else 1)
+    if world == 1 and not args.no_e2e and 8 * capi.packed_size(dim) <= (2 << 30):
+        from cosmopp_b200.likelihood import Likelihood
+        d_mat = torch.empty(capi.packed_size(dim), dtype=torch.float64, device="cuda")
+        noise = np.zeros(capi.packed_size(dim))
+        sig = np.where(np.arange(dim) < npix, 2.0, 0.3)
+        noise[np.arange(dim) * (np.arange(dim) + 1) // 2 + np.arange(dim)] = sig ** 2
+        d_noise = torch.from_numpy(noise).cuda()
+        one_map = np.random.RandomState(3).normal(size=dim) * 5.0
+        cl_in = synthetic_cl(lmax, pol=(kind == "tqu"))
+
+        def chain():
+            if kind == "tqu":
+                ctx.cl_to_cmatrix_pol_dev(*cl_in, FWHM, d_mat)
+            else:
+                ctx.cl_to_cmatrix_dev(cl_in, FWHM, d_mat)
+            like = Likelihood(ctx, d_mat, None, d_noise, dim)
+            out = like.calculate(one_map)
+            like.close()
+            return out
+        chain()
+        torch.cuda.synchronize()
+        reps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            like_val = chain()
+        torch.cuda.synchronize()
+        ms_chain = 1e3 * (time.perf_counter() - t0) / reps
+        consumer = {"ms_per_step": ms_chain, "value": units_total / (ms_chain * 1e-3), "unit": UNIT, "matrix_dim": dim, "h2d_bytes_per_step": h2d_bytes + 8 * dim,
+                    "d2h_bytes_per_step": 16, "minus_two_log_like": like_val[0],
+                    "note": "C_l and one map from host memory in; matrix generated on the device, + white noise, packed in-place Cholesky "
+                            "(cmg_packed_cholesky), chi^2 and log det back: the matrix never crosses PCIe"}
+        del d_mat, d_noise
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = reference_sample(kind, nside, lmax, budget_s=12.0)
@@ -661,7 +699,8 @@ def run_gpu_arm(args):
             "ms_per_step": ms_per_step, "ms_per_matrix": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world, args.shard_mode),
             "path": path_dict(kind, use_orbit, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "fp64_frac_of_peak": achieved / peak_tflops, "exchange": exchange, "gather": gather, "parity_max_err": parity,
+            "fp64_frac_of_peak": achieved / peak_tflops, "exchange": exchange, "gather": gather, "e2e_device_consumer": consumer,
+            "parity_max_err": parity,
             "parity_note": ("max over ranks of |entry - oracle| / diagonal of the block over %d sampled entries of each rank's packed columns "
                             "(oracle/api.py tqu_pairs, untimed; gate 1e-11)" % args.spot_check) if parity is not None else None,
         }

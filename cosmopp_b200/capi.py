@@ -386,6 +386,26 @@ class Context:
         _need(_numel(out_host) >= packed_size(self.npix), "output buffer smaller than npix (npix + 1) / 2")
         self._check(self._L.cmg_fiducial_matrix(self._h, _p(cl), int(lmax), float(fwhm), _p(pixwin), _p(out_host)))
 
+    def cl_to_cmatrix_dev(self, cl, fwhm, d_out, pixwin=None):
+        """clToCMatrix with the packed result left on the device (include/cmg.h)"""
+        cl = _f64(cl)
+        pixwin = _f64(pixwin)
+        _need(len(cl) >= 3, "cl must reach l = 2")
+        _need(pixwin is None or len(pixwin) >= len(cl), "pixel window shorter than cl")
+        _need(_numel(d_out) >= packed_size(self.npix), "output buffer smaller than npix (npix + 1) / 2")
+        self._check(self._L.cmg_cl_to_cmatrix_dev(self._h, _p(cl), len(cl) - 1, float(fwhm), _p(pixwin), _p(d_out)))
+
+    def cl_to_cmatrix_pol_dev(self, ctt, cte, cee, cbb, fwhm, d_out, pixwinT=None, pixwinP=None):
+        """the [T;Q;U] whole call with the packed result left on the device (include/cmg.h)"""
+        ctt, cte, cee, cbb = map(_f64, (ctt, cte, cee, cbb))
+        pixwinT = _f64(pixwinT)
+        pixwinP = _f64(pixwinP)
+        _need(len(ctt) >= 3 and len(cte) == len(ctt) and len(cee) == len(ctt) and len(cbb) == len(ctt), "tt, te, ee, bb must have one length (lmax + 1 >= 3)")
+        _need(all(w is None or len(w) >= len(ctt) for w in (pixwinT, pixwinP)), "pixel window shorter than the spectra")
+        _need(_numel(d_out) >= packed_size(3 * self.npix), "output buffer smaller than 3 npix (3 npix + 1) / 2")
+        self._check(self._L.cmg_cl_to_cmatrix_pol_dev(self._h, _p(ctt), _p(cte), _p(cee), _p(cbb), len(ctt) - 1, float(fwhm),
+                                                      _p(pixwinT), _p(pixwinP), _p(d_out)))
+
     def mask_matrix(self, d_in, npix_in, good, d_out):
         g = np.ascontiguousarray(good, dtype=np.int32)
         self._check(self._L.cmg_mask_matrix(self._h, _p(d_in), npix_in, _p(g), len(g), _p(d_out)))

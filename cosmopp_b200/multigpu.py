@@ -325,7 +325,7 @@ class OrbitShardedTT:
         self.ctx, self.nside, self.rank, self.world = ctx, nside, rank, world
         self.face_pix = nside * nside
         self.npix = 12 * self.face_pix
-        self.mode = 0 if world == 1 else 1
+        self.mode = 0 if (world == 1 and nside >= 32) else 1      # what cmg_legendre_series_orbit_sharded chooses
         self.bounds = partition.orbit_partition(nside, world, self.mode, align=16)
         self.q0, self.q1 = self.bounds[rank], self.bounds[rank + 1]
         self.sizes = [partition.packed_size(f * self.face_pix + self.q1) - partition.packed_size(f * self.face_pix + self.q0) for f in range(12)]

@@ -65,7 +65,7 @@ class FakeContext:
         self.launches += 1
 
     legendre_series = legendre_series_orbit = legendre_series_orbit_sharded = tqu = tqu_orbit = tqu_orbit_sharded = _launch
-    cl_to_cmatrix = cl_to_cmatrix_pol = tqu_orbit_assemble = tqu_scatter_block = tqu_orbit_scatter_inbox = tqu_batched_slab = _launch
+    cl_to_cmatrix = cl_to_cmatrix_pol = cl_to_cmatrix_dev = cl_to_cmatrix_pol_dev = tqu_orbit_assemble = tqu_scatter_block = tqu_orbit_scatter_inbox = tqu_batched_slab = _launch
 
     def orbit_strips_to_host(self, shard, host, threads=0, direct_mask=0):
         self.to_host_calls = getattr(self, "to_host_calls", 0) + 1
@@ -123,6 +123,18 @@ def fake_gpu(monkeypatch):
     monkeypatch.setattr(capi, "host_register", lambda a: None)
     monkeypatch.setattr(capi, "host_unregister", lambda a: None)
     monkeypatch.setattr(bench, "spot_check", lambda *a, **k: 3e-14)
+    import cosmopp_b200.likelihood as lk
+
+    class FakeLike:
+        def __init__(self, *a, **k):
+            pass
+
+        def calculate(self, t):
+            return 1234.5, 1000.0, 234.5
+
+        def close(self):
+            pass
+    monkeypatch.setattr(lk, "Likelihood", FakeLike)
     monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
     monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []})
     monkeypatch.setattr(bench, "reference_sample", lambda *a, **k: {"value": 1.0, "unit": bench.UNIT, "cores": 1, "kind": "reference",
@@ -163,6 +175,8 @@ def test_single_rank_line(fake_gpu, capsys, monkeypatch, workload, extra, orbit,
     e = line["e2e"]
     assert e["value"] > 0 and 0 < e["d2h_bytes_per_step"] <= line["config"]["packed_bytes"] and e["h2d_bytes_per_step"] > 0
     assert (line["parity_max_err"] == 3e-14) == (orbit and workload.startswith("tqu"))
+    if line["config"]["packed_bytes"] <= (2 << 30):
+        assert line["e2e_device_consumer"]["d2h_bytes_per_step"] == 16 and line["e2e_device_consumer"]["ms_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "reference"
     ref = fake_gpu.config_dict(workload, *fake_gpu.workload_geometry(workload)[:3], line["config"]["npix"], 1)
     assert ref == line["config"]                         # the reference arm describes the same workload
