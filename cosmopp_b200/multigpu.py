@@ -202,9 +202,12 @@ class OrbitShardedTQU:
             # the receiver's scatter kernel reads block(r -> this rank) straight out of rank r's outbox over NVLink
             self._sync_streams()
             dist.barrier()                         # every outbox is complete before anyone reads it
-            for r, base in self.peer_outbox.items():
-                if self.recv_counts[r]:
-                    self.ctx.tqu_orbit_scatter_inbox(self.shard, r, base + 8 * self.layouts[r][self.rank], self.mode)
+            # every rank starts with a different peer (rank + 1, rank + 2, ...): with one common order all ranks would read the same
+            # sender at the same time (measured on 8 GPUs: 17.1 ms that way)
+            for k in range(1, self.world):
+                r = (self.rank + k) % self.world
+                if r in self.peer_outbox and self.recv_counts[r]:
+                    self.ctx.tqu_orbit_scatter_inbox(self.shard, r, self.peer_outbox[r] + 8 * self.layouts[r][self.rank], self.mode)
             self._sync_streams()
             dist.barrier()                         # nobody overwrites an outbox a peer is still reading
             return
@@ -280,7 +283,9 @@ class OrbitShardedTQU:
         if self.world > 1 and self.exchange_mode == "pull" and self._map_peers():
             dist.barrier()                         # the peers' strips are complete
             self.assemble_into(full, 1)
-            for r, base in self.peer_strips.items():
+            for k in range(1, self.world):           # a different first peer on every rank (see exchange)
+                r = (self.rank + k) % self.world
+                base = self.peer_strips[r]
                 q0, q1 = self.bounds[r], self.bounds[r + 1]
                 sizes = partition.orbit_strip_sizes(self.nside, q0, q1)
                 off = 0
