@@ -154,6 +154,7 @@ void Utils::readFitsTable(const char* fileName, FitsTable& table)
     std::transform(table.ordering.begin(), table.ordering.end(), table.ordering.begin(), ::toupper);
     table.nSide = h.getLong("NSIDE", 0);
     std::vector<long> repeat(static_cast<size_t>(fields), 1), width(static_cast<size_t>(fields), 0), offset(static_cast<size_t>(fields), 0);
+    std::vector<double> scale, zero;
     long off = 0;
     for(long c = 0; c < fields; ++c)
     {
@@ -177,6 +178,12 @@ void Utils::readFitsTable(const char* fileName, FitsTable& table)
         }
         offset[c] = off;
         off += repeat[c] * width[c];
+        // a scaled column (value = TZERO + TSCAL * stored) would be read wrongly without an error: apply the scaling
+        std::stringstream ks, kz;
+        ks << "TSCAL" << (c + 1);
+        kz << "TZERO" << (c + 1);
+        scale.push_back(h.get(ks.str()).empty() ? 1.0 : std::atof(h.get(ks.str()).c_str()));
+        zero.push_back(h.get(kz.str()).empty() ? 0.0 : std::atof(h.get(kz.str()).c_str()));
     }
     if(off != rowBytes)
     {
@@ -204,9 +211,18 @@ void Utils::readFitsTable(const char* fileName, FitsTable& table)
                 case 'E': v = bigEndianFloat(p); break;
                 case 'J': v = static_cast<std::int32_t>((std::uint32_t(p[0]) << 24) | (std::uint32_t(p[1]) << 16) | (std::uint32_t(p[2]) << 8) | p[3]); break;
                 case 'I': v = static_cast<std::int16_t>((p[0] << 8) | p[1]); break;
-                default: v = p[0]; break;
+                case 'K':
+                {
+                    std::uint64_t u = 0;
+                    for(int b = 0; b < 8; ++b)
+                        u = (u << 8) | p[b];
+                    v = static_cast<double>(static_cast<std::int64_t>(u));
+                    break;
                 }
-                table.columns[c].push_back(v);
+                case 'L': v = (p[0] == 'T') ? 1.0 : 0.0; break;             // logical: 'T' / 'F'
+                default: v = p[0]; break;                                   // 'B' unsigned byte, 'A' character code
+                }
+                table.columns[c].push_back(zero[c] + scale[c] * v);
             }
     }
     std::fclose(f);

@@ -143,6 +143,12 @@ static void cpuTests(const std::string& dir)
         const std::vector<int> want = readInts(dir + "/mask_good.i32");
         EXPECT(nSide == 4 && gp == want);
         EXPECT(throwsStandard([&] { long n; std::vector<int> x; Utils::readMask((dir + "/mask_ring.fits").c_str(), n, x); }));
+        // the same mask as a 64-bit integer column, and as a scaled integer column (TSCAL / TZERO)
+        std::vector<int> gk, gs;
+        long nk = 0, ns = 0;
+        Utils::readMask((dir + "/mask_k.fits").c_str(), nk, gk);
+        Utils::readMask((dir + "/mask_scaled.fits").c_str(), ns, gs);
+        EXPECT(nk == 4 && ns == 4 && gk == want && gs == want);
     }
 
     // Legendre container: on-demand values and the reference's file layout

@@ -12,7 +12,7 @@ from conftest import ROOT, synthetic_cl
 LIB = os.path.join(ROOT, "cosmopp_b200", "lib")
 
 
-def write_healpix_mask_fits(path, mask, ordering):
+def write_healpix_mask_fits(path, mask, ordering, form="D", tscal=None, tzero=None):
     """Minimal HEALPix-style FITS file: empty primary HDU + one BINTABLE with a 1024D column (like the reference's
     slow_test_files/mask1.fits)."""
     def card(key, val, quote=False):
@@ -26,9 +26,10 @@ def write_healpix_mask_fits(path, mask, ordering):
     rows = n // rep
     primary = block([card("SIMPLE", "T"), card("BITPIX", 8), card("NAXIS", 0), card("EXTEND", "T")])
     ext = block([card("XTENSION", "BINTABLE", True), card("BITPIX", 8), card("NAXIS", 2), card("NAXIS1", 8 * rep), card("NAXIS2", rows),
-                 card("PCOUNT", 0), card("GCOUNT", 1), card("TFIELDS", 1), card("TTYPE1", "MASK", True), card("TFORM1", "%dD" % rep, True),
-                 card("PIXTYPE", "HEALPIX", True), card("ORDERING", ordering, True), card("NSIDE", int(round((n / 12) ** 0.5)))])
-    data = np.asarray(mask, dtype=">f8").tobytes()
+                 card("PCOUNT", 0), card("GCOUNT", 1), card("TFIELDS", 1), card("TTYPE1", "MASK", True), card("TFORM1", "%d%s" % (rep, form), True)]
+                + ([card("TSCAL1", tscal)] if tscal is not None else []) + ([card("TZERO1", tzero)] if tzero is not None else [])
+                + [card("PIXTYPE", "HEALPIX", True), card("ORDERING", ordering, True), card("NSIDE", int(round((n / 12) ** 0.5)))])
+    data = np.asarray(mask, dtype=">f8" if form == "D" else ">i8").tobytes()
     data += b"\0" * ((2880 - len(data) % 2880) % 2880)
     with open(path, "wb") as f:
         f.write(primary + ext + data)
@@ -91,6 +92,9 @@ def test_cpp_dropin_host_side(dropin_binary, tmp_path, oracle_api):
     mask = oracle_api.like_low_mask(4)
     write_healpix_mask_fits(str(tmp_path / "mask_nest.fits"), mask, "NESTED")
     write_healpix_mask_fits(str(tmp_path / "mask_ring.fits"), mask, "RING")
+    # 64-bit integer column, and a scaled one (stored 2 m - 1 with TSCAL = 0.5, TZERO = 0.5): the same mask both times
+    write_healpix_mask_fits(str(tmp_path / "mask_k.fits"), np.asarray(mask, dtype=np.int64), "NESTED", form="K")
+    write_healpix_mask_fits(str(tmp_path / "mask_scaled.fits"), 2 * np.asarray(mask, dtype=np.int64) - 1, "NESTED", form="K", tscal=0.5, tzero=0.5)
     oracle_api.good_pixels_from_mask(mask).astype("<i4").tofile(str(tmp_path / "mask_good.i32"))
     # a7: the HEALPix pixel window file, single precision as HEALPix ships it (64 entries: up to l = 4 nside - 1)
     w_t, w_p = window_tables(63, 16)

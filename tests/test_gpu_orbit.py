@@ -223,9 +223,6 @@ def test_tt_whole_call_takes_the_orbit_path_on_the_full_sky(gpu_ctx, oracle_api)
     assert np.abs(again.numpy() - out.numpy()).max() <= 1e-13 * want[0]
 
 
-@pytest.mark.skipif("not __import__('os').environ.get('CMG_TEST_UNVERIFIED')",
-                    reason="mode 2 (store destinations precomputed per tile) was written after the round's GPU time was spent: "
-                           "set CMG_TEST_UNVERIFIED=1 (or run tools/bin/orbit_check full) to try it")
 def test_orbit_mode2_is_bit_identical_to_mode0(gpu_ctx):
     import torch
     from cosmopp_b200 import capi

@@ -374,10 +374,10 @@ def test_batched_slab_dmma_path(gpu_ctx, oracle_api):
         gpu_ctx.tqu_batched_slab(np.zeros((2, 4, 65)), slabs)      # lmax = 64: refused, not silently rerouted
 
 
-def test_batched_slab_at_config4_shape(gpu_ctx):
+def test_batched_slab_at_config4_shape(gpu_ctx, oracle_api):
     """BASELINE config 4's shape (full-sky Nside=16, lmax=47), two slabs with a ragged second one: every element of the
-    slab output against the single-matrix kernel (itself checked against the oracle at this size in
-    test_full_size_*), all 42.5 M entries, to 1e-11 of the block diagonal; plus linearity in the weights."""
+    slab output against the single-matrix kernel, all 42.5 M entries, to 1e-11 of the block diagonal; one element (of the
+    second, ragged slab) DIRECTLY against the CPU oracle; plus linearity in the weights."""
     torch = _torch()
     from cosmopp_b200 import capi
     nside, lmax, nb = 16, 47, 19
@@ -405,6 +405,13 @@ def test_batched_slab_at_config4_shape(gpu_ctx):
         assert float((el - one).abs().max()) <= REL_TOL * min(dT, dP)
         if b in (0, 1):
             keep[b] = el.clone()
+    # element 17 straight against the oracle (not through this library's other kernels)
+    gpu_ctx.slab_unpack(slabs[capi.slab_doubles(3 * n):], 3 * n, el, only_b=17 % 16)
+    torch.cuda.synchronize()
+    want = oracle_api.tqu_matrix(*synthetic_cl(lmax, seed=12345 + 17, pol=True), nside, 10.0)
+    scale = np.full(want.shape, want[i_qq])
+    scale[:capi.packed_size(n)] = want[i_tt]
+    assert (np.abs(el.cpu().numpy() - want) / scale).max() <= REL_TOL
     gpu_ctx.slab_unpack(slabs[capi.slab_doubles(3 * n):], 3 * n, el, only_b=(nb - 1) % 16)
     torch.cuda.synchronize()
     combo = 0.5 * keep[0] - 2.0 * keep[1]
