@@ -44,6 +44,31 @@ class OrbitShard(ctypes.Structure):
     ]
 
 
+CHOL_MAX_RUNS = 36
+CHOL_NB = 128
+
+
+class CholRuns(ctypes.Structure):
+    """cmg_chol_runs: the runs of whole packed columns a rank of the sharded Cholesky factorisation holds (include/cmg.h)."""
+    _fields_ = [
+        ("n_runs", ctypes.c_int32),
+        ("col_begin", _i64 * CHOL_MAX_RUNS),
+        ("col_end", _i64 * CHOL_MAX_RUNS),
+        ("d_run", _vp * CHOL_MAX_RUNS),
+    ]
+
+
+def make_chol_runs(runs):
+    """runs: [(col_begin, col_end, device pointer of entry (0, col_begin))], ascending"""
+    if not 1 <= len(runs) <= CHOL_MAX_RUNS:
+        raise ValueError("1 .. %d runs of columns" % CHOL_MAX_RUNS)
+    c = CholRuns()
+    c.n_runs = len(runs)
+    for k, (b, e, ptr) in enumerate(runs):
+        c.col_begin[k], c.col_end[k], c.d_run[k] = int(b), int(e), int(ptr)
+    return c
+
+
 def library_path():
     return os.path.join(HERE, "lib", "libcosmopp_b200.so")
 
@@ -115,6 +140,14 @@ _SIGNATURES = {
     "cmg_packed_cholesky": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64)]),
     "cmg_packed_cholesky_logdet": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(ctypes.c_double)]),
     "cmg_packed_cholesky_solve": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64]),
+    "cmg_chol_begin": (ctypes.c_int, [_vp]),
+    "cmg_chol_end": (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
+    "cmg_chol_diag": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp]),
+    "cmg_chol_panel": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _vp, _i64]),
+    "cmg_chol_syrk": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _i64]),
+    "cmg_chol_logdet_runs": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), ctypes.POINTER(ctypes.c_double)]),
+    "cmg_chol_solve_diag": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _i64, _vp, _i64]),
+    "cmg_chol_solve_update": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _i64, _vp, _i64]),
     "cmg_packed_sum": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "cmg_set_like_method": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_like_create_ninv": (ctypes.c_int, [_vp, _vp, _vp, _i64, ctypes.c_double, ctypes.POINTER(_vp)]),
@@ -467,6 +500,35 @@ class Context:
 
     def packed_cholesky_solve(self, d_factor, n, d_rhs, n_rhs):
         self._check(self._L.cmg_packed_cholesky_solve(self._h, _p(d_factor), int(n), _p(d_rhs), int(n_rhs)))
+
+    # ---- the factorisation step by step over a rank's runs of columns (include/cmg.h, cmg_chol_runs; multigpu.ShardedCholesky)
+    def chol_begin(self):
+        self._check(self._L.cmg_chol_begin(self._h))
+
+    def chol_end(self):
+        info = _i64()
+        self._check(self._L.cmg_chol_end(self._h, ctypes.byref(info)))
+        return info.value
+
+    def chol_diag(self, runs, k0, kb, d_ukk):
+        self._check(self._L.cmg_chol_diag(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_ukk)))
+
+    def chol_panel(self, runs, k0, kb, d_ukk, d_panel, panel_col0):
+        self._check(self._L.cmg_chol_panel(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_ukk), _p(d_panel), int(panel_col0)))
+
+    def chol_syrk(self, runs, k0, kb, d_panel, panel_col0):
+        self._check(self._L.cmg_chol_syrk(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_panel), int(panel_col0)))
+
+    def chol_logdet_runs(self, runs):
+        v = ctypes.c_double()
+        self._check(self._L.cmg_chol_logdet_runs(self._h, ctypes.byref(runs), ctypes.byref(v)))
+        return v.value
+
+    def chol_solve_diag(self, runs, k0, kb, n, d_rhs, n_rhs):
+        self._check(self._L.cmg_chol_solve_diag(self._h, ctypes.byref(runs), int(k0), int(kb), int(n), _p(d_rhs), int(n_rhs)))
+
+    def chol_solve_update(self, runs, k0, kb, n, d_rhs, n_rhs):
+        self._check(self._L.cmg_chol_solve_update(self._h, ctypes.byref(runs), int(k0), int(kb), int(n), _p(d_rhs), int(n_rhs)))
 
     def packed_sum(self, d_c, d_f, d_n, n, d_out, c_stride=1):
         self._check(self._L.cmg_packed_sum(self._h, _p(d_c), int(c_stride), _p(d_f), _p(d_n), int(n), _p(d_out)))

@@ -29,6 +29,28 @@ constexpr int CH_PANEL_COLS = 128;         // panel solve: columns (threads) per
 
 __host__ __device__ __forceinline__ long long chOff(long long col) { return col * (col + 1) / 2; }
 
+// The columns a launch works on: up to CH_MAX_RUNS runs of whole packed columns [colBegin, colEnd), each somewhere in this GPU's
+// memory -- base[r] + chOff(j) + i is entry (i, j) of a column j of run r.  One GPU holding the whole triangle: one run, base = A.
+// A rank of a sharded factorisation: its 36 orbit-closed runs (cmg_orbit_shard), already clipped to the columns behind the
+// current block.  first[r] = CTAs of the launch in front of run r (the kernels look their run up with it), tile0[r] = tiles in
+// front of the run's first column block in the numbering of chSyrkTilesBefore.
+constexpr int CH_MAX_RUNS = 36;
+struct CholRuns
+{
+    int count;
+    long long colBegin[CH_MAX_RUNS], colEnd[CH_MAX_RUNS];
+    double* base[CH_MAX_RUNS];
+    long long first[CH_MAX_RUNS + 1];
+    long long tile0[CH_MAX_RUNS];
+};
+
+__device__ __forceinline__ int chRunOf(const CholRuns& runs, long long cta)
+{
+    int r = 0;
+    while(r + 1 < runs.count && cta >= runs.first[r + 1]) ++r;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ diagonal block
 // A[k0 .. k0 + kb, k0 .. k0 + kb] -> U_kk, in place: one CTA, the block in shared memory (S(r, c) at chS[c * CH_LD + r], r <= c),
 // factorised in sub-blocks of CH_DB = 16 rows:
@@ -40,7 +62,8 @@ __host__ __device__ __forceinline__ long long chOff(long long col) { return col 
 constexpr int CH_DB = 16;
 
 __global__ void __launch_bounds__(512)
-cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restrict__ info, double* __restrict__ invDiag)
+cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restrict__ info, double* __restrict__ invDiag,
+               double* __restrict__ ukkOut)
 {
     extern __shared__ double chS[];                      // [kb][CH_LD]
     __shared__ int failed;
@@ -149,6 +172,13 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
     }
     if(tid < kb)
         invDiag[tid] = sInv[tid];
+    if(ukkOut)                                           // packed U_kk for the other ranks of a sharded factorisation
+        for(int idx = tid; idx < kb * kb; idx += blockDim.x)
+        {
+            const int cc = idx / kb, r = idx - cc * kb;
+            if(r <= cc)
+                ukkOut[cc * (cc + 1) / 2 + r] = chS[cc * CH_LD + r];
+        }
 }
 
 // ------------------------------------------------------------------------------------------------ panel
@@ -162,8 +192,8 @@ constexpr int CH_PB = 16;
 constexpr int CH_PANEL_SMEM_DOUBLES = CH_NB * CH_PANEL_COLS + CH_NB * (CH_NB + 1) / 2 + CH_NB;
 
 __global__ void __launch_bounds__(CH_PANEL_COLS)
-cholPanelKernel(double* __restrict__ A, long long k0, int kb, long long n, const long long* __restrict__ info,
-                const double* __restrict__ invDiag)
+cholPanelKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, const long long* __restrict__ info,
+                const double* __restrict__ invDiag, const double* __restrict__ ukk, double* __restrict__ panel, long long panelCol0)
 {
     extern __shared__ double chX[];                      // [kb][CH_PANEL_COLS], then U_kk packed, then 1 / diagonal
     if(*info != 0)
@@ -171,14 +201,20 @@ cholPanelKernel(double* __restrict__ A, long long k0, int kb, long long n, const
     double* sU = chX + CH_NB * CH_PANEL_COLS;            // U(s, r) at sU[r (r + 1) / 2 + s]
     double* sInv = sU + CH_NB * (CH_NB + 1) / 2;
     const int tid = threadIdx.x;
-    for(int r = 0; r < kb; ++r)                          // column r of the block: r + 1 contiguous doubles
-        if(tid <= r)
-            sU[r * (r + 1) / 2 + tid] = A[chOff(k0 + r) + k0 + tid];
+    const int run = chRunOf(runs, blockIdx.x);
+    double* const A = runs.base[run];
+    if(ukk)                                              // sharded: the owner's U_kk arrives packed (the block is not in this rank's columns)
+        for(int idx = tid; idx < kb * (kb + 1) / 2; idx += CH_PANEL_COLS)
+            sU[idx] = ukk[idx];
+    else
+        for(int r = 0; r < kb; ++r)                      // column r of the block: r + 1 contiguous doubles
+            if(tid <= r)
+                sU[r * (r + 1) / 2 + tid] = A[chOff(k0 + r) + k0 + tid];
     if(tid < kb)
         sInv[tid] = invDiag[tid];
     __syncthreads();
-    const long long j = k0 + kb + static_cast<long long>(blockIdx.x) * CH_PANEL_COLS + tid;
-    if(j >= n)
+    const long long j = runs.colBegin[run] + (static_cast<long long>(blockIdx.x) - runs.first[run]) * CH_PANEL_COLS + tid;
+    if(j >= runs.colEnd[run])
         return;
     double* col = A + chOff(j) + k0;
     // kb is a multiple of CH_PB here: only the LAST block of a matrix can be short, and nothing lies behind it
@@ -211,6 +247,12 @@ cholPanelKernel(double* __restrict__ A, long long k0, int kb, long long n, const
     }
     for(int r = 0; r < kb; ++r)
         col[r] = chX[r * CH_PANEL_COLS + tid];
+    if(panel)                                            // sharded: the same rows into the dense panel every rank will hold
+    {
+        double* p = panel + (j - panelCol0) * CH_NB;
+        for(int r = 0; r < kb; ++r)
+            p[r] = chX[r * CH_PANEL_COLS + tid];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ trailing update
@@ -245,12 +287,20 @@ __host__ __device__ __forceinline__ long long chSyrkTilesBefore(long long b)
     return b + m * (m - 1) + r * m;
 }
 
+// Sharded form: `panel` != null -- the operands come from the dense panel [column - panelCol0][CH_NB] every rank holds after the
+// all-reduce (rows of OTHER ranks' columns are not in this rank's memory); the C tiles are this rank's runs of columns.  A run's
+// tiles are the column blocks [(colBegin - k1) / 64, (colEnd - k1) / 64) of the numbering below; columns from colEnd on are not
+// this rank's (the tile is cut there like at the edge of the matrix).
 __global__ void __launch_bounds__(CH_SYRK_THREADS, 2)
-cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const long long* __restrict__ info)
+cholSyrkKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, const long long* __restrict__ info,
+               const double* __restrict__ panel, long long panelCol0)
 {
     if(*info != 0)
         return;
-    const long long t = blockIdx.x;
+    const int run = chRunOf(runs, blockIdx.x);
+    double* const A = runs.base[run];
+    const long long n = runs.colEnd[run];
+    const long long t = (static_cast<long long>(blockIdx.x) - runs.first[run]) + runs.tile0[run];
     long long bj = static_cast<long long>(2.0 * sqrt(static_cast<double>(t)));
     while(chSyrkTilesBefore(bj + 1) <= t) ++bj;
     while(chSyrkTilesBefore(bj) > t) --bj;
@@ -262,10 +312,11 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
     const int wi = warp >> 1, wj = warp & 1;             // warp tile: rows wi * 32, columns wj * 32
     constexpr int STAGE = (CH_TILE + CH_TJ) * CH_SLD;
     long long* sOff = reinterpret_cast<long long*>(chSm + 2 * STAGE);     // first element of the panel run of every operand column, -1 = none
+    const double* op = panel ? panel : A;                // operand source (one GPU: the run is the whole triangle)
     if(tid < CH_TILE + CH_TJ)
     {
         const long long x = tid < CH_TILE ? i0 + tid : j0 + (tid - CH_TILE);
-        sOff[tid] = x < n ? chOff(x) + k0 : -1;
+        sOff[tid] = x < n ? (panel ? (x - panelCol0) * CH_NB : chOff(x) + k0) : -1;
     }
     __syncthreads();
 
@@ -289,7 +340,7 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
             {
                 const int x = warp + (m0 + m) * (CH_SYRK_THREADS / 32);
                 const bool l = live && off[m] >= 0;
-                chCpAsync8(sP + x * CH_SLD + lane, l ? A + off[m] + kc + lane : A, l);
+                chCpAsync8(sP + x * CH_SLD + lane, l ? op + off[m] + kc + lane : op, l);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -306,7 +357,7 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
         {
             const int jl = wj * 32 + b * 8 + 2 * (lane & 3) + e;
             const long long j = j0 + jl;
-            const long long cOff = sOff[CH_TILE + jl] - k0;          // chOff(j), or negative when j >= n
+            const long long cOff = j < n ? chOff(j) : -1;
 #pragma unroll
             for(int a = 0; a < 4; ++a)
             {
@@ -354,7 +405,7 @@ cholSyrkKernel(double* __restrict__ A, long long k0, int kb, long long n, const 
         {
             const int jl = wj * 32 + b * 8 + 2 * (lane & 3) + e;
             const long long j = j0 + jl;
-            const long long cOff = sOff[CH_TILE + jl] - k0;
+            const long long cOff = j < n ? chOff(j) : -1;
 #pragma unroll
             for(int a = 0; a < 4; ++a)
             {
@@ -374,6 +425,27 @@ cholLogDetKernel(const double* __restrict__ U, long long n, double* __restrict__
     double s = 0.0;
     for(long long i = threadIdx.x; i < n; i += 256)
         s += log(U[chOff(i) + i]);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for(int w = 128; w > 0; w >>= 1)
+    {
+        if(threadIdx.x < w)
+            red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if(threadIdx.x == 0)
+        *out = 2.0 * red[0];
+}
+
+// the same over the diagonal entries of a rank's runs of columns (sharded factor): the rank's share of log det
+__global__ void __launch_bounds__(256)
+cholLogDetRunsKernel(const __grid_constant__ CholRuns runs, double* __restrict__ out)
+{
+    __shared__ double red[256];
+    double s = 0.0;
+    for(int r = 0; r < runs.count; ++r)
+        for(long long i = runs.colBegin[r] + threadIdx.x; i < runs.colEnd[r]; i += 256)
+            s += log(runs.base[r][chOff(i) + i]);
     red[threadIdx.x] = s;
     __syncthreads();
     for(int w = 128; w > 0; w >>= 1)
@@ -411,13 +483,14 @@ cholSolveDiagKernel(const double* __restrict__ U, long long k0, int kb, long lon
 
 // t_j -= sum_{r < kb} U[k0 + r][j] y_r for every row j behind the block: a warp per column j (its kb entries are contiguous)
 __global__ void __launch_bounds__(256)
-cholSolveUpdateKernel(const double* __restrict__ U, long long k0, int kb, long long n, double* __restrict__ T, int nRhs)
+cholSolveUpdateKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, long long n, double* __restrict__ T, int nRhs)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long j = k0 + kb + static_cast<long long>(blockIdx.x) * 8 + warp;
-    if(j >= n)
+    const int run = chRunOf(runs, blockIdx.x);
+    const long long j = runs.colBegin[run] + (static_cast<long long>(blockIdx.x) - runs.first[run]) * 8 + warp;
+    if(j >= runs.colEnd[run])
         return;
-    const double* u = U + chOff(j) + k0;
+    const double* u = runs.base[run] + chOff(j) + k0;
     double uv[CH_NB / 32];
 #pragma unroll
     for(int q = 0; q < CH_NB / 32; ++q)

@@ -1769,6 +1769,88 @@ cmg_status cholBuffers(cmg_ctx* ctx)
 }
 }
 
+namespace
+{
+constexpr int CH_DIAG_SMEM = cmg::CH_NB * cmg::CH_LD * sizeof(double);
+constexpr int CH_PANEL_SMEM = cmg::CH_PANEL_SMEM_DOUBLES * sizeof(double);
+constexpr int CH_SYRK_SMEM = 2 * (cmg::CH_TILE + cmg::CH_TJ) * cmg::CH_SLD * sizeof(double) + (cmg::CH_TILE + cmg::CH_TJ) * sizeof(long long);
+
+cmg_status cholStepAttributes(cmg_ctx* ctx)
+{
+    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_DIAG_SMEM));
+    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_PANEL_SMEM));
+    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholSyrkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SYRK_SMEM));
+    return CMG_OK;
+}
+
+// one GPU, the whole triangle: a single run of the columns behind the block
+cmg::CholRuns cholWholeRun(double* dA, int64_t colBegin, int64_t n)
+{
+    cmg::CholRuns r{};
+    r.count = 1;
+    r.colBegin[0] = colBegin;
+    r.colEnd[0] = n;
+    r.base[0] = dA;
+    return r;
+}
+
+// A rank's runs clipped to the columns >= from (a multiple of 64 behind k1, or the start of a run), with the CTA prefix of a
+// launch that gives `unit` columns to a CTA (panel: 128, solve update: 8); syrk: the tile counts of chSyrkTilesBefore relative
+// to k1 instead (unit = 0).  Returns the total number of CTAs.
+int64_t cholClipRuns(const cmg_chol_runs* in, int64_t from, int64_t k1, int unit, cmg::CholRuns* out)
+{
+    int64_t total = 0;
+    out->count = 0;
+    for(int r = 0; r < in->n_runs; ++r)
+    {
+        const int64_t c0 = std::max<int64_t>(in->col_begin[r], from), c1 = in->col_end[r];
+        if(c1 <= c0)
+            continue;
+        const int k = out->count++;
+        out->colBegin[k] = c0;
+        out->colEnd[k] = c1;
+        out->base[k] = in->d_run[r] - cmg::chOff(in->col_begin[r]);
+        out->first[k] = total;
+        if(unit > 0)
+        {
+            out->tile0[k] = 0;
+            total += (c1 - c0 + unit - 1) / unit;
+        }
+        else
+        {
+            const int64_t b0 = (c0 - k1) / cmg::CH_TJ, b1 = (c1 - k1 + cmg::CH_TJ - 1) / cmg::CH_TJ;
+            out->tile0[k] = cmg::chSyrkTilesBefore(b0);
+            total += cmg::chSyrkTilesBefore(b1) - out->tile0[k];
+        }
+    }
+    out->first[out->count] = total;
+    return total;
+}
+
+bool cholRunsValid(const cmg_chol_runs* runs)
+{
+    if(!runs || runs->n_runs < 1 || runs->n_runs > CMG_CHOL_MAX_RUNS)
+        return false;
+    for(int r = 0; r < runs->n_runs; ++r)
+    {
+        if(!runs->d_run[r] || runs->col_begin[r] < 0 || runs->col_end[r] < runs->col_begin[r] || runs->col_begin[r] % cmg::CH_NB)
+            return false;
+        if(r > 0 && runs->col_begin[r] < runs->col_end[r - 1])
+            return false;
+    }
+    return true;
+}
+
+// the run that holds column k0 (the owner of block k0), or -1
+int cholRunOfColumn(const cmg_chol_runs* runs, int64_t k0)
+{
+    for(int r = 0; r < runs->n_runs; ++r)
+        if(k0 >= runs->col_begin[r] && k0 < runs->col_end[r])
+            return r;
+    return -1;
+}
+}
+
 cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* info)
 {
     if(!ctx) return CMG_EINVAL;
@@ -1776,27 +1858,26 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     cmg_status s = cholBuffers(ctx);
     if(s != CMG_OK) return s;
-    const int diagSmem = cmg::CH_NB * cmg::CH_LD * sizeof(double), panelSmem = cmg::CH_PANEL_SMEM_DOUBLES * sizeof(double);
-    const int syrkSmem = 2 * (cmg::CH_TILE + cmg::CH_TJ) * cmg::CH_SLD * sizeof(double) + (cmg::CH_TILE + cmg::CH_TJ) * sizeof(long long);
-    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diagSmem));
-    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholPanelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panelSmem));
-    CMG_CUDA(ctx, cudaFuncSetAttribute(cmg::cholSyrkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, syrkSmem));
+    if((s = cholStepAttributes(ctx)) != CMG_OK) return s;
     CMG_CUDA(ctx, cudaMemsetAsync(ctx->dCholInfo, 0, sizeof(long long), ctx->stream));
     KernelTimer timer(ctx);
     for(int64_t k0 = 0; k0 < n; k0 += cmg::CH_NB)
     {
         const int kb = static_cast<int>(std::min<int64_t>(cmg::CH_NB, n - k0));
-        cmg::cholDiagKernel<<<1, 512, diagSmem, ctx->stream>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4);
+        cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, ctx->stream>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr);
         const int64_t rem = n - k0 - kb;
         ctx->launches += 1;
         if(rem <= 0)
             break;
         // (kb == CH_NB from here on: a short block can only be the last one)
-        cmg::cholPanelKernel<<<static_cast<unsigned>((rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS), cmg::CH_PANEL_COLS, panelSmem, ctx->stream>>>(
-            dA, k0, kb, n, ctx->dCholInfo, ctx->dCholRed + 4);
+        cmg::CholRuns runs = cholWholeRun(dA, k0 + kb, n);
+        runs.first[1] = (rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS;
+        cmg::cholPanelKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_PANEL_COLS, CH_PANEL_SMEM, ctx->stream>>>(
+            runs, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr, nullptr, 0);
         const int64_t colBlocks = (rem + cmg::CH_TJ - 1) / cmg::CH_TJ;           // 64-column blocks; block b meets the row tiles 0 .. b / 2
-        cmg::cholSyrkKernel<<<static_cast<unsigned>(cmg::chSyrkTilesBefore(colBlocks)), cmg::CH_SYRK_THREADS, syrkSmem, ctx->stream>>>(
-            dA, k0, kb, n, ctx->dCholInfo);
+        runs.first[1] = cmg::chSyrkTilesBefore(colBlocks);
+        cmg::cholSyrkKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(
+            runs, k0, kb, ctx->dCholInfo, nullptr, 0);
         ctx->launches += 2;
     }
     CMG_CUDA(ctx, cudaGetLastError());
@@ -1805,6 +1886,141 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
     CMG_CUDA(ctx, cudaMemcpyAsync(&hInfo, ctx->dCholInfo, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *info = hInfo;
+    return CMG_OK;
+}
+
+// ---- the same factorisation over several GPUs, step by step (cosmopp_b200/multigpu.py: ShardedCholesky drives it) ----
+// A rank holds runs of whole packed columns (the strips of cmg_orbit_shard after the exchange): cmg_chol_runs.  Block k lives in
+// exactly one run of one rank (run boundaries are multiples of CH_NB).  Step k: the owner factorises the block (cmg_chol_diag)
+// and everyone receives U_kk (66 KB broadcast); every rank solves the 128 rows of its own columns behind the block
+// (cmg_chol_panel) into its packed columns and into a dense panel [column][128] that is zero elsewhere; one all-reduce later
+// every rank holds the whole panel and updates its own columns with it (cmg_chol_syrk).
+
+cmg_status cmg_chol_begin(cmg_ctx* ctx)
+{
+    if(!ctx) return CMG_EINVAL;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_status s = cholBuffers(ctx);
+    if(s != CMG_OK) return s;
+    if((s = cholStepAttributes(ctx)) != CMG_OK) return s;
+    CMG_CUDA(ctx, cudaMemsetAsync(ctx->dCholInfo, 0, sizeof(long long), ctx->stream));
+    return CMG_OK;
+}
+
+cmg_status cmg_chol_end(cmg_ctx* ctx, int64_t* info)
+{
+    if(!ctx || !info) return CMG_EINVAL;
+    if(!ctx->dCholInfo) return fail(ctx, CMG_EINVAL, "cmg_chol_end: no cmg_chol_begin before it");
+    long long hInfo = 0;
+    CMG_CUDA(ctx, cudaMemcpyAsync(&hInfo, ctx->dCholInfo, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *info = hInfo;
+    return CMG_OK;
+}
+
+cmg_status cmg_chol_diag(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, double* dUkk)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!cholRunsValid(runs) || !dUkk || kb < 1 || kb > cmg::CH_NB || k0 % cmg::CH_NB || !ctx->dCholInfo)
+        return fail(ctx, CMG_EINVAL, "cmg_chol_diag: bad arguments (after cmg_chol_begin; k0 a multiple of 128)");
+    const int r = cholRunOfColumn(runs, k0);
+    if(r < 0 || k0 + kb > runs->col_end[r]) return fail(ctx, CMG_EINVAL, "cmg_chol_diag: block k0 is not in this rank's columns");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    // d_ukk: kb (kb + 1) / 2 packed entries of U_kk, then the kb reciprocals of its diagonal
+    cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, ctx->stream>>>(runs->d_run[r] - cmg::chOff(runs->col_begin[r]), k0, kb, ctx->dCholInfo,
+                                                              dUkk + kb * (kb + 1) / 2, dUkk);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
+}
+
+cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* dUkk, double* dPanel, int64_t panelCol0)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!cholRunsValid(runs) || !dUkk || !dPanel || kb != cmg::CH_NB || k0 % cmg::CH_NB || panelCol0 > k0 + kb || !ctx->dCholInfo)
+        return fail(ctx, CMG_EINVAL, "cmg_chol_panel: bad arguments (a full block of 128 rows; panel_col0 <= k0 + 128)");
+    cmg::CholRuns clipped;
+    const int64_t ctas = cholClipRuns(runs, k0 + kb, k0 + kb, cmg::CH_PANEL_COLS, &clipped);
+    if(ctas == 0) return CMG_OK;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg::cholPanelKernel<<<static_cast<unsigned>(ctas), cmg::CH_PANEL_COLS, CH_PANEL_SMEM, ctx->stream>>>(clipped, k0, kb, ctx->dCholInfo,
+                                                                                                         dUkk + kb * (kb + 1) / 2, dUkk, dPanel, panelCol0);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
+}
+
+cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* dPanel, int64_t panelCol0)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!cholRunsValid(runs) || !dPanel || kb != cmg::CH_NB || k0 % cmg::CH_NB || panelCol0 > k0 + kb || !ctx->dCholInfo)
+        return fail(ctx, CMG_EINVAL, "cmg_chol_syrk: bad arguments (a full block of 128 rows; panel_col0 <= k0 + 128)");
+    cmg::CholRuns clipped;
+    const int64_t tiles = cholClipRuns(runs, k0 + kb, k0 + kb, 0, &clipped);
+    if(tiles == 0) return CMG_OK;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(clipped, k0, kb, ctx->dCholInfo, dPanel, panelCol0);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
+}
+
+cmg_status cmg_chol_logdet_runs(cmg_ctx* ctx, const cmg_chol_runs* runs, double* logDetShare)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!cholRunsValid(runs) || !logDetShare) return fail(ctx, CMG_EINVAL, "cmg_chol_logdet_runs: bad arguments");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg_status s = cholBuffers(ctx);
+    if(s != CMG_OK) return s;
+    cmg::CholRuns all;
+    cholClipRuns(runs, 0, 0, cmg::CH_NB, &all);
+    cmg::cholLogDetRunsKernel<<<1, 256, 0, ctx->stream>>>(all, ctx->dCholRed);
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    CMG_CUDA(ctx, cudaMemcpyAsync(logDetShare, ctx->dCholRed, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CMG_OK;
+}
+
+namespace
+{
+void cholSolvePasses(int64_t nRhs, dim3* block, unsigned* passes)
+{
+    const int perPass = static_cast<int>(std::min<int64_t>(8, nRhs));
+    *block = dim3(cmg::CH_NB, perPass);
+    *passes = static_cast<unsigned>((nRhs + perPass - 1) / perPass);
+}
+}
+
+cmg_status cmg_chol_solve_diag(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, int64_t n, double* dT, int64_t nRhs)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!cholRunsValid(runs) || !dT || kb < 1 || kb > cmg::CH_NB || k0 % cmg::CH_NB || nRhs < 1 || nRhs > 65535 || k0 + kb > n)
+        return fail(ctx, CMG_EINVAL, "cmg_chol_solve_diag: bad arguments");
+    const int r = cholRunOfColumn(runs, k0);
+    if(r < 0 || k0 + kb > runs->col_end[r]) return fail(ctx, CMG_EINVAL, "cmg_chol_solve_diag: block k0 is not in this rank's columns");
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    dim3 block;
+    unsigned passes;
+    cholSolvePasses(nRhs, &block, &passes);
+    cmg::cholSolveDiagKernel<<<passes, block, 0, ctx->stream>>>(runs->d_run[r] - cmg::chOff(runs->col_begin[r]), k0, kb, n, dT, static_cast<int>(nRhs));
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return CMG_OK;
+}
+
+cmg_status cmg_chol_solve_update(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, int64_t n, double* dT, int64_t nRhs)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(!cholRunsValid(runs) || !dT || kb < 1 || kb > cmg::CH_NB || k0 % cmg::CH_NB || nRhs < 1 || nRhs > 65535 || k0 + kb > n)
+        return fail(ctx, CMG_EINVAL, "cmg_chol_solve_update: bad arguments");
+    cmg::CholRuns clipped;
+    const int64_t ctas = cholClipRuns(runs, k0 + kb, k0 + kb, 8, &clipped);
+    if(ctas == 0) return CMG_OK;
+    CMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cmg::cholSolveUpdateKernel<<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(clipped, k0, kb, n, dT, static_cast<int>(nRhs));
+    CMG_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
     return CMG_OK;
 }
 
@@ -1839,7 +2055,9 @@ cmg_status cmg_packed_cholesky_solve(cmg_ctx* ctx, const double* dU, int64_t n, 
         const int64_t rem = n - k0 - kb;
         if(rem <= 0)
             break;
-        cmg::cholSolveUpdateKernel<<<static_cast<unsigned>((rem + 7) / 8), 256, 0, ctx->stream>>>(dU, k0, kb, n, dT, static_cast<int>(nRhs));
+        cmg::CholRuns runs = cholWholeRun(const_cast<double*>(dU), k0 + kb, n);
+        runs.first[1] = (rem + 7) / 8;
+        cmg::cholSolveUpdateKernel<<<static_cast<unsigned>(runs.first[1]), 256, 0, ctx->stream>>>(runs, k0, kb, n, dT, static_cast<int>(nRhs));
         ctx->launches += 1;
     }
     CMG_CUDA(ctx, cudaGetLastError());

@@ -136,11 +136,16 @@ class OrbitShardedTQU:
     the sender's outbox through CUDA IPC) and is placed into d's packed columns.  After that a rank holds exactly its columns
     of the matrix: N ranks hold 87 GB between them for the Nside = 64 matrix."""
 
-    def __init__(self, ctx, nside, rank, world, mode=0, exchange="pull"):
+    def __init__(self, ctx, nside, rank, world, mode=0, exchange="pull", bounds=None):
         self.ctx, self.nside, self.rank, self.world, self.mode = ctx, nside, rank, world, mode
         self.face_pix = nside * nside
         self.npix = 12 * self.face_pix
-        self.bounds = partition.orbit_partition(nside, world, mode)
+        # bounds: the in-face ranges of the ranks when not the cost-balanced ones -- partition.orbit_partition_blocks when the
+        # strips go on to ShardedCholesky (its run boundaries lie on the 128-column block grid)
+        self.bounds = list(bounds) if bounds is not None else partition.orbit_partition(nside, world, mode)
+        if len(self.bounds) != world + 1 or self.bounds[0] != 0 or self.bounds[-1] != self.face_pix or any(
+                b % 32 or b < a for a, b in zip(self.bounds, self.bounds[1:])):
+            raise ValueError("bounds: world + 1 ascending multiples of 32 from 0 to nside^2")
         self.q0, self.q1 = self.bounds[rank], self.bounds[rank + 1]
         self.layouts = [capi.orbit_outbox_layout(nside, mode, self.bounds, r) for r in range(world)] if world > 1 else [[0, 0]]
         n_strips, n_outbox = self.sizes_of(rank)
@@ -191,6 +196,17 @@ class OrbitShardedTQU:
 
     def generate(self, weights):
         self.ctx.tqu_orbit_sharded(*weights, self.shard, self.mode)
+
+    def chol_runs(self):
+        """(all_runs, run_ptrs) for ShardedCholesky: the 36 runs of packed columns of every rank, and where this rank's lie"""
+        all_runs = [partition.orbit_column_runs(self.nside, self.bounds[r], self.bounds[r + 1]) for r in range(self.world)]
+        sizes = partition.orbit_strip_sizes(self.nside, self.q0, self.q1)
+        ptrs, off = [], 0
+        for s in range(3):
+            for f in range(12):
+                ptrs.append(self.strips.ptr + 8 * off)
+                off += sizes[s][f]
+        return all_runs, ptrs
 
     def exchange(self):
         """complete this rank's strips with the entries the other ranks computed for its columns.  Collective."""
@@ -318,6 +334,166 @@ class OrbitShardedTQU:
         self.inbox = None
         for b in self.pieces():
             b.free()
+
+
+class TorchComm:
+    """the two exchanges of a sharded Cholesky step over torch.distributed (NCCL on GPUs; gloo in the CPU tests of the plan)"""
+
+    def broadcast(self, tensor, src):
+        import torch.distributed as dist
+        dist.broadcast(tensor, src=src)
+
+    def all_reduce(self, tensor):
+        import torch.distributed as dist
+        dist.all_reduce(tensor)
+
+
+def chol_block_owners(n, all_runs):
+    """owner rank of every 128-row block of an n-dimensional matrix whose columns are spread as `all_runs`:
+    all_runs[rank] = [(col_begin, col_end), ...].  Every boundary must be a multiple of 128 (the end of the matrix excepted)
+    and the runs of all ranks together must tile [0, n) exactly."""
+    nb = capi.CHOL_NB
+    owners = [-1] * ((n + nb - 1) // nb)
+    covered = 0
+    for rank, runs in enumerate(all_runs):
+        for b, e in runs:
+            if e <= b:
+                continue
+            if b % nb or (e % nb and e != n) or b < 0 or e > n:
+                raise ValueError("run [%d, %d) of rank %d: boundaries must be multiples of %d inside [0, %d]" % (b, e, rank, nb, n))
+            for k in range(b // nb, (e + nb - 1) // nb):
+                if owners[k] != -1:
+                    raise ValueError("block %d is in the runs of ranks %d and %d" % (k, owners[k], rank))
+                owners[k] = rank
+            covered += e - b
+    if covered != n or -1 in owners:
+        raise ValueError("the runs do not tile the %d columns of the matrix" % n)
+    return owners
+
+
+class ShardedCholesky:
+    """A = U^T U of a packed symmetric positive definite matrix whose COLUMNS are spread over the GPUs of one box, in place
+    (include/cmg.h, cmg_chol_*; kernels in csrc/cholesky.cuh).  A rank holds runs of whole packed columns -- after
+    OrbitShardedTQU.exchange() its 36 strips are exactly that, so the Nside = 64 matrix (147456-dimensional, 87 GB) is
+    factorised where the generator left it: 11 GB per GPU on eight of them, nothing gathered, nothing redistributed.  The runs
+    of one rank interleave with everyone else's 36 times over the matrix, so the shrinking trailing matrix stays balanced
+    (a block-cyclic distribution with 36 cycles).
+
+    Right-looking, 128 rows per step; the reference runs LAPACK dpptrf on the host (source/matrix_impl.cpp:236-263).  Per step:
+      owner of block k: U_kk (cmg_chol_diag)                       -> broadcast of 66 KB
+      every rank: the 128 rows of its own columns (cmg_chol_panel)  -> all-reduce of the dense panel (<= 151 MB, entries of
+                  other ranks' columns are zero: the sum is a gather that needs no layout agreement between ranks)
+      every rank: trailing update of its own columns (cmg_chol_syrk, FP64 tensor-core tiles, operands from the dense panel)
+    Over the whole factorisation every rank receives the factor once (87 GB over NVLink against n^3 / 3 / G of arithmetic).
+
+    `comm`: broadcast(tensor, src) / all_reduce(tensor) (TorchComm).  The context must run on torch's current stream
+    (ctx.set_stream(torch.cuda.current_stream().cuda_stream)): kernels and collectives alternate 1152 times, fences would
+    serialise the host with the device every time.  `ukk` / `panel`: torch buffers to use (ranks emulated on ONE GPU share
+    them -- tests/test_gpu_cholesky.py); allocated when None."""
+
+    def __init__(self, ctx, n, all_runs, rank, run_ptrs, comm=None, ukk=None, panel=None):
+        import torch
+        self.ctx, self.n, self.rank, self.world = ctx, int(n), rank, len(all_runs)
+        self.owners = chol_block_owners(self.n, all_runs)
+        mine = [(b, e) for b, e in all_runs[rank]]
+        if len(run_ptrs) != len(mine):
+            raise ValueError("one device pointer per run of this rank")
+        live = [(b, e, p) for (b, e), p in zip(mine, run_ptrs) if e > b]
+        self.runs = capi.make_chol_runs(live) if live else None
+        self.comm = comm if comm is not None else TorchComm()
+        nb = capi.CHOL_NB
+        self.ukk = ukk if ukk is not None else torch.empty(nb * (nb + 1) // 2 + nb, dtype=torch.float64, device="cuda")
+        self.panel = panel if panel is not None else torch.empty(max(self.n - nb, 1) * nb, dtype=torch.float64, device="cuda")
+        self.device = self.panel.device
+        self.info = None
+
+    def _check_stream(self):
+        import torch
+        if self.world > 1 and self.device.type == "cuda" and self.ctx.stream_handle != torch.cuda.current_stream().cuda_stream:
+            raise RuntimeError("ShardedCholesky: the context must share torch's current stream (ctx.set_stream(torch.cuda.current_stream().cuda_stream))")
+
+    # ---- the phases of a step (a test drives emulated ranks through them in lock step)
+    def blocks(self):
+        nb = capi.CHOL_NB
+        return [(k0, min(nb, self.n - k0)) for k0 in range(0, self.n, nb)]
+
+    def step_diag(self, k0, kb):
+        """owner only"""
+        self.ctx.chol_diag(self.runs, k0, kb, self.ukk)
+
+    def step_panel(self, k0, kb):
+        if self.runs is not None:
+            self.ctx.chol_panel(self.runs, k0, kb, self.ukk, self.panel, k0 + kb)
+
+    def step_syrk(self, k0, kb):
+        if self.runs is not None:
+            self.ctx.chol_syrk(self.runs, k0, kb, self.panel, k0 + kb)
+
+    def factorise(self):
+        """Collective.  Returns LAPACK's info (0: positive definite; k: the leading minor of order k is not), the same on every rank."""
+        import torch
+        self._check_stream()
+        nb = capi.CHOL_NB
+        self.ctx.chol_begin()
+        for k0, kb in self.blocks():
+            owner = self.owners[k0 // nb]
+            if owner == self.rank:
+                self.step_diag(k0, kb)
+            if k0 + kb >= self.n:
+                break
+            if self.world > 1:
+                self.comm.broadcast(self.ukk, owner)
+            active = self.panel[:(self.n - k0 - kb) * nb]
+            if self.world > 1:
+                active.zero_()
+            self.step_panel(k0, kb)
+            if self.world > 1:
+                self.comm.all_reduce(active)
+            self.step_syrk(k0, kb)
+        info = self.ctx.chol_end()
+        if self.world > 1:                       # the first failing block wins on every rank
+            big = 1 << 62
+            t = torch.tensor([info if info else big], dtype=torch.int64, device=self.device)
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            info = int(t.item())
+            info = 0 if info == big else info
+        self.info = info
+        return info
+
+    def logdet(self):
+        """log det A = 2 sum log U_jj.  Collective."""
+        import torch
+        share = self.ctx.chol_logdet_runs(self.runs) if self.runs is not None else 0.0
+        if self.world == 1:
+            return share
+        t = torch.tensor([share], dtype=torch.float64, device=self.device)
+        self.comm.all_reduce(t)
+        return float(t.item())
+
+    def solve(self, rhs):
+        """y = U^-T t in place: rhs is a (n_rhs, n) float64 cuda tensor (n x n_rhs column-major), the same on every rank going in
+        and coming out; chi^2 of right-hand side m = |y_m|^2.  Collective."""
+        self._check_stream()
+        nb = capi.CHOL_NB
+        if rhs.dim() != 2 or rhs.shape[1] != self.n or not rhs.is_contiguous():
+            raise ValueError("rhs must be a contiguous (n_rhs, n) tensor")
+        n_rhs = rhs.shape[0]
+        for k0, kb in self.blocks():
+            owner = self.owners[k0 // nb]
+            if owner == self.rank:
+                self.ctx.chol_solve_diag(self.runs, k0, kb, self.n, rhs, n_rhs)
+            if self.world > 1:
+                view = rhs[:, k0:k0 + kb]
+                if view.is_contiguous():
+                    self.comm.broadcast(view, owner)
+                else:
+                    tmp = view.contiguous()
+                    self.comm.broadcast(tmp, owner)
+                    view.copy_(tmp)
+            if k0 + kb < self.n and self.runs is not None:
+                self.ctx.chol_solve_update(self.runs, k0, kb, self.n, rhs, n_rhs)
+        return rhs
 
 
 class OrbitShardedTT:

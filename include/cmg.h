@@ -356,6 +356,43 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* d_packed, int64_t n, int64_
 cmg_status cmg_packed_cholesky_logdet(cmg_ctx* ctx, const double* d_factor, int64_t n, double* log_det);
 /* y = U^-T t for n_rhs right-hand sides, in place: d_rhs is n x n_rhs column-major on the device; t^T A^-1 t = |y|^2 */
 cmg_status cmg_packed_cholesky_solve(cmg_ctx* ctx, const double* d_factor, int64_t n, double* d_rhs, int64_t n_rhs);
+
+/* ---- The same factorisation with the columns spread over several GPUs (cosmopp_b200/multigpu.py: ShardedCholesky drives the
+ * steps; the library itself links no collective library -- the two exchanges of a step are the caller's).
+ * A rank holds up to CMG_CHOL_MAX_RUNS runs of WHOLE packed columns [col_begin, col_end), ascending, every boundary a multiple of
+ * 128 (the end of the matrix excepted); d_run[r] = address of entry (0, col_begin[r]).  These are exactly the 36 strips a rank
+ * of cmg_orbit_shard holds after the exchange (partition boundaries rounded to 128), so the Nside = 64 matrix is factorised
+ * where the generator and the exchange left it: no gather, no redistribution.
+ * Step k (k0 = 128 k, kb = min(128, n - k0)):
+ *   cmg_chol_diag   (owner of block k only)  U_kk in place, and packed into d_ukk: kb (kb + 1) / 2 entries, then kb reciprocal
+ *                   pivots.  The caller broadcasts d_ukk (<= 67 KB) from the owner.
+ *   cmg_chol_panel  (every rank, kb = 128)  rows k0 .. k0 + 128 of the rank's own columns behind the block: solved in place and
+ *                   also written to the dense panel d_panel[(column - panel_col0) * 128 + row].  The caller zeroes the panel
+ *                   before and all-reduces (sum) it after: every rank then holds the 128 rows of EVERY column behind the block.
+ *   cmg_chol_syrk   (every rank)  trailing update of the rank's own columns, operands read from the dense panel.
+ * cmg_chol_begin before the first step, cmg_chol_end after the last (*info as cmg_packed_cholesky: the first non-positive pivot
+ * of a block this rank owns, 0 otherwise; the caller takes the minimum of the non-zero values over ranks). */
+#define CMG_CHOL_MAX_RUNS 36
+typedef struct cmg_chol_runs
+{
+    int32_t n_runs;
+    int64_t col_begin[CMG_CHOL_MAX_RUNS];
+    int64_t col_end[CMG_CHOL_MAX_RUNS];
+    double* d_run[CMG_CHOL_MAX_RUNS];
+} cmg_chol_runs;
+cmg_status cmg_chol_begin(cmg_ctx* ctx);
+cmg_status cmg_chol_end(cmg_ctx* ctx, int64_t* info);
+cmg_status cmg_chol_diag(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, double* d_ukk);
+cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* d_ukk, double* d_panel, int64_t panel_col0);
+cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* d_panel, int64_t panel_col0);
+/* this rank's share of log det A: 2 sum log U_jj over its columns (the caller sums over ranks) */
+cmg_status cmg_chol_logdet_runs(cmg_ctx* ctx, const cmg_chol_runs* runs, double* log_det_share);
+/* y = U^-T t on the sharded factor, d_rhs (n x n_rhs, column-major) replicated on every rank.  Step k: the owner of block k solves
+ * its kb rows (cmg_chol_solve_diag; rows k0 .. of d_rhs then hold y) and the caller broadcasts them; every rank subtracts their
+ * contribution from the rows of its OWN columns behind the block (cmg_chol_solve_update) -- the only rows it will ever solve. */
+cmg_status cmg_chol_solve_diag(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, int64_t n, double* d_rhs, int64_t n_rhs);
+cmg_status cmg_chol_solve_update(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, int64_t n, double* d_rhs, int64_t n_rhs);
+
 /* d_out = C + F + N, all packed of dimension n (d_f, d_n may be NULL; element stride c_stride on d_c as in cmg_sum_unpack_strided;
  * d_out may be d_c when c_stride = 1) */
 cmg_status cmg_packed_sum(cmg_ctx* ctx, const double* d_c, int64_t c_stride, const double* d_f, const double* d_n, int64_t n, double* d_out);

@@ -104,3 +104,91 @@ def test_tqu_likelihood_consumer_on_the_packed_factor(gpu_ctx, oracle_api, maske
     assert np.abs(chi2 - want_chi2).max() <= 1e-9 * np.abs(want_chi2).max()
     assert abs(logdet - want_logdet) <= 1e-9 * abs(want_logdet)
     assert np.abs(chi2 - chi2_d).max() <= 1e-9 * np.abs(chi2_d).max() and abs(logdet - logdet_d) <= 1e-9 * abs(logdet_d)
+
+
+class _NoComm:
+    """ranks emulated on one GPU share the U_kk buffer and the dense panel: nothing to exchange"""
+
+    def broadcast(self, tensor, src):
+        pass
+
+    def all_reduce(self, tensor):
+        pass
+
+
+@pytest.mark.parametrize("n, world, cycles", [(1280, 2, 2), (1536 + 77, 3, 2), (2048, 4, 4)])
+def test_sharded_cholesky_ranks_in_lock_step(gpu_ctx, n, world, cycles):
+    """the step functions of the sharded factorisation (cmg_chol_*; multigpu.ShardedCholesky) with `world` ranks emulated on one
+    GPU: the columns are dealt out in runs of 128 ... 384 columns, `cycles` runs per rank interleaved like the strips of
+    cmg_orbit_shard; every rank factorises its own copy of its columns, sharing only U_kk and the dense panel.  Factor, log det
+    and the solves against numpy and against cmg_packed_cholesky on the whole triangle."""
+    import torch
+    from cosmopp_b200 import capi, multigpu
+    A = random_spd(n, 900 + n)
+    packed = pack_upper(A)
+    # runs: cut [0, n) at multiples of 128 into world * cycles pieces of uneven width, dealt round robin
+    nb = capi.CHOL_NB
+    blocks = (n + nb - 1) // nb
+    rs = np.random.RandomState(n)
+    cuts = np.sort(rs.choice(np.arange(1, blocks), size=world * cycles - 1, replace=False)) * nb
+    edges = [0] + [int(c) for c in cuts] + [n]
+    all_runs = [[] for _ in range(world)]
+    for k in range(world * cycles):
+        all_runs[k % world].append((edges[k], edges[k + 1]))
+    off = lambda c: c * (c + 1) // 2
+    bufs = [[torch.from_numpy(packed[off(b):off(e)].copy()).cuda() for b, e in all_runs[r]] for r in range(world)]
+    ukk = torch.zeros(nb * (nb + 1) // 2 + nb, dtype=torch.float64, device="cuda")
+    panel = torch.zeros(max(n - nb, 1) * nb, dtype=torch.float64, device="cuda")
+    ranks = [multigpu.ShardedCholesky(gpu_ctx, n, all_runs, r, [t.data_ptr() for t in bufs[r]], comm=_NoComm(), ukk=ukk, panel=panel)
+             for r in range(world)]
+    assert ranks[0].owners == multigpu.chol_block_owners(n, all_runs)
+    gpu_ctx.chol_begin()
+    for k0, kb in ranks[0].blocks():
+        ranks[ranks[0].owners[k0 // nb]].step_diag(k0, kb)
+        if k0 + kb >= n:
+            break
+        for r in ranks:
+            r.step_panel(k0, kb)
+        for r in ranks:
+            r.step_syrk(k0, kb)
+    assert gpu_ctx.chol_end() == 0
+    got = np.empty_like(packed)
+    for r in range(world):
+        for (b, e), t in zip(all_runs[r], bufs[r]):
+            got[off(b):off(e)] = t.cpu().numpy()
+    whole = torch.from_numpy(packed.copy()).cuda()
+    assert gpu_ctx.packed_cholesky(whole, n) == 0
+    want = np.linalg.cholesky(A).T
+    assert np.abs(unpack_upper(got, n) - want).max() <= 1e-12 * np.abs(want).max()
+    assert np.abs(got - whole.cpu().numpy()).max() <= 1e-13 * np.abs(want).max()
+    logdet = sum(r.logdet() for r in ranks)                  # world == 1 inside each emulated rank: its own share
+    assert abs(logdet - np.linalg.slogdet(A)[1]) <= 1e-12 * abs(np.linalg.slogdet(A)[1])
+    # solves: the right-hand sides are one shared buffer here (replicated + broadcast on real ranks)
+    T = np.random.RandomState(3).normal(size=(3, n))
+    t = torch.from_numpy(T.copy()).cuda()
+    for k0, kb in ranks[0].blocks():
+        gpu_ctx.chol_solve_diag(ranks[ranks[0].owners[k0 // nb]].runs, k0, kb, n, t, 3)
+        if k0 + kb < n:
+            for r in ranks:
+                gpu_ctx.chol_solve_update(r.runs, k0, kb, n, t, 3)
+    want_y = np.linalg.solve(want.T, T.T).T
+    assert np.abs(t.cpu().numpy() - want_y).max() <= 1e-11 * np.abs(want_y).max()
+
+
+def test_sharded_cholesky_single_rank_is_the_whole_call(gpu_ctx):
+    """world = 1 through the class: factorise / logdet / solve without any exchange"""
+    import torch
+    from cosmopp_b200 import multigpu
+    n = 700
+    A = random_spd(n, 41)
+    d = torch.from_numpy(pack_upper(A)).cuda()
+    ch = multigpu.ShardedCholesky(gpu_ctx, n, [[(0, n)]], 0, [d.data_ptr()])
+    assert ch.factorise() == 0
+    want = np.linalg.cholesky(A).T
+    assert np.abs(unpack_upper(d.cpu().numpy(), n) - want).max() <= 1e-12 * np.abs(want).max()
+    assert abs(ch.logdet() - np.linalg.slogdet(A)[1]) <= 1e-12 * abs(np.linalg.slogdet(A)[1])
+    t = torch.from_numpy(np.random.RandomState(2).normal(size=(2, n))).cuda()
+    T = t.cpu().numpy().copy()
+    ch.solve(t)
+    want_y = np.linalg.solve(want.T, T.T).T
+    assert np.abs(t.cpu().numpy() - want_y).max() <= 1e-11 * np.abs(want_y).max()
