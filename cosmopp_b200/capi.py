@@ -46,6 +46,8 @@ class OrbitShard(ctypes.Structure):
 
 CHOL_MAX_RUNS = 36
 CHOL_NB = 128
+CHOL_MAX_GROUP = 4
+CHOL_PLANE_SLACK = 192          # rows a plane of the dense panel has to spare behind the last column
 
 
 class CholRuns(ctypes.Structure):
@@ -144,7 +146,8 @@ _SIGNATURES = {
     "cmg_chol_end": (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
     "cmg_chol_diag": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp]),
     "cmg_chol_panel": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _vp, _i64]),
-    "cmg_chol_syrk": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _i64]),
+    "cmg_chol_syrk": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _i64, _i64, ctypes.c_int]),
+    "cmg_set_cholesky_group": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_chol_logdet_runs": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), ctypes.POINTER(ctypes.c_double)]),
     "cmg_chol_solve_diag": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _i64, _vp, _i64]),
     "cmg_chol_solve_update": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _i64, _vp, _i64]),
@@ -513,11 +516,16 @@ class Context:
     def chol_diag(self, runs, k0, kb, d_ukk):
         self._check(self._L.cmg_chol_diag(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_ukk)))
 
-    def chol_panel(self, runs, k0, kb, d_ukk, d_panel, panel_col0):
-        self._check(self._L.cmg_chol_panel(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_ukk), _p(d_panel), int(panel_col0)))
+    def chol_panel(self, runs, k0, kb, d_ukk, d_plane, panel_col0):
+        self._check(self._L.cmg_chol_panel(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_ukk), _p(d_plane), int(panel_col0)))
 
-    def chol_syrk(self, runs, k0, kb, d_panel, panel_col0):
-        self._check(self._L.cmg_chol_syrk(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_panel), int(panel_col0)))
+    def chol_syrk(self, runs, k0, kb, d_panel, plane_stride, panel_col0, strip_only):
+        self._check(self._L.cmg_chol_syrk(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_panel), int(plane_stride), int(panel_col0),
+                                          int(bool(strip_only))))
+
+    def set_cholesky_group(self, blocks):
+        """blocks of 128 rows per trailing update of cmg_packed_cholesky (1 .. 4)"""
+        self._check(self._L.cmg_set_cholesky_group(self._h, int(blocks)))
 
     def chol_logdet_runs(self, runs):
         v = ctypes.c_double()

@@ -24,7 +24,7 @@ constexpr int CH_NB = 128;                 // block size (rows of U per step)
 constexpr int CH_LD = CH_NB + 1;           // leading dimension of the diagonal block in shared memory
 constexpr int CH_TILE = 128;               // syrk: tile edge
 constexpr int CH_KC = 32;                  // syrk: k-chunk staged in shared memory
-constexpr int CH_SLD = CH_KC + 4;          // its leading dimension: (lane / 4) * 36 + lane % 4 hits 16 distinct 8-byte banks per half-warp
+constexpr int CH_SLD = CH_KC;              // its leading dimension: no padding, the 16-byte chunks of a row are XOR-swizzled (chSwz)
 constexpr int CH_PANEL_COLS = 128;         // panel solve: columns (threads) per CTA
 
 __host__ __device__ __forceinline__ long long chOff(long long col) { return col * (col + 1) / 2; }
@@ -261,23 +261,27 @@ __device__ __forceinline__ void chDmma(double& c0, double& c1, const double a, c
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Tile of the trailing matrix, 128 rows (i) x 64 columns (j): C[i][j] -= sum_{r < kb} P[r][i] P[r][j], P[r][x] = A[chOff(x) + k0 + r]
-// the panel just solved (x >= k1).  8 warps as 4 x 2: a warp owns 32 rows x 32 columns = 4 x 4 m8n8 accumulator tiles, which START
-// as the C entries themselves (loaded while the first operand chunk is in flight); the A fragments enter negated (DMMA's operand
-// modifier), so the tensor-core accumulation leaves C - P^T P and the epilogue is stores only.  The k-chunks of both operands are
-// staged by cp.async as [column][k] with leading dimension 36, double buffered: an A fragment element (row i = lane / 4,
-// k = lane % 4) and a B fragment element (k = lane % 4, column j = lane / 4) are the same access pattern, conflict-free.
-// Two CTAs per SM (110 KB of shared memory, 126 registers each): one CTA's loads of C, its barriers and its stores hide behind
+// Tile of the trailing matrix, 128 rows (i) x 64 columns (j): C[i][j] -= sum_{r < kb} P[r][i] P[r][j], P = the kb rows of U just
+// solved (kb = CH_NB, or a whole group of blocks: up to CH_MAX_GROUP * CH_NB).  8 warps as 4 x 2: a warp owns 32 rows x 32 columns
+// = 4 x 4 m8n8 accumulator tiles, which START as the C entries themselves (loaded while the first operand chunk is in flight);
+// the A fragments enter negated (DMMA's operand modifier), so the tensor-core accumulation leaves C - P^T P and the epilogue is
+// stores only.  The k-chunks (32 rows of U) of both operands are staged by 16-byte cp.async as [column][k], double buffered.
+// Two CTAs per SM (96 KB of shared memory, 128 registers each): one CTA's loads of C, its barriers and its stores hide behind
 // the other's DMMAs -- the first version (one 128 x 128 CTA of 512 threads per SM) left the DMMA pipe idle 46 % of the time
 // (profiles/r2_syrk_v1_metrics.txt: stalls math-pipe throttle AND wait / lg-throttle / barrier: bursts, then drains).
 constexpr int CH_TJ = 64;                  // syrk: columns of a tile
 constexpr int CH_SYRK_THREADS = 256;
 
-__device__ __forceinline__ void chCpAsync8(double* dstShared, const double* src, bool live)
+// Staged row of operand column x: 32 doubles = 16 chunks of 16 bytes, no padding.  A thread (g = lane / 4, t = lane % 4) reads the
+// k pair (2 t, 2 t + 1) of eight consecutive k as ONE 16-byte load and feeds two DMMAs with it (the first contracts the even k
+// of the eight, the second the odd ones -- A and B fragments use the same assignment, so the products pair up correctly).  A
+// 16-byte load is served per quarter warp (rows g = 2 q, 2 q + 1, four chunks each): chunk c of an odd row sits at c ^ 4, which
+// puts the two rows into different halves of the 128-byte bank window.  Half the shared-memory instructions of the 8-byte
+// version with leading dimension 36 (MIO throttle / short scoreboard: profiles/r2_syrk_v2_metrics.txt, then _v3_).
+__device__ __forceinline__ void chCpAsync16(double* dstShared, const double* src)
 {
     const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(dstShared));
-    const int bytes = live ? 8 : 0;                      // 0: nothing is read, the destination is zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
 // tiles behind k1, column block b (64 wide) outermost: it meets the row tiles ti = 0 .. b / 2 (128 high); cumulative count
@@ -287,13 +291,21 @@ __host__ __device__ __forceinline__ long long chSyrkTilesBefore(long long b)
     return b + m * (m - 1) + r * m;
 }
 
-// Sharded form: `panel` != null -- the operands come from the dense panel [column - panelCol0][CH_NB] every rank holds after the
-// all-reduce (rows of OTHER ranks' columns are not in this rank's memory); the C tiles are this rank's runs of columns.  A run's
-// tiles are the column blocks [(colBegin - k1) / 64, (colEnd - k1) / 64) of the numbering below; columns from colEnd on are not
-// this rank's (the tile is cut there like at the edge of the matrix).
+// Operands: the DENSE panel the panel kernel writes next to the packed columns -- plane s (the s-th block of CH_NB rows of a
+// group of blocks, see cmg_packed_cholesky) holds U[k0 + s CH_NB + r][x] at panel[s planeStride + (x - panelCol0) CH_NB + r].
+// Rows of the panel are 1 KB apart and 16-byte aligned whatever the column (a packed column starts at an odd or even double),
+// so a k-chunk of a tile's operands is staged with 16-byte cp.async from plain strided addresses -- no offset table, half the
+// copy instructions.  The sharded factorisation needs the dense form anyway (rows of OTHER ranks' columns are not in this
+// rank's memory; every rank holds the panel after the all-reduce).  The C tiles are the launch's runs of columns: a run's
+// tiles are the column blocks [(colBegin - k1) / 64, (colEnd - k1) / 64) of the numbering above; columns from colEnd on are
+// not this run's (the tile is cut there like at the edge of the matrix).
+// stripOnly: only the first row tile (rows k1 .. k1 + CH_TILE) of every column block -- the catch-up update of the next block
+// of a group before it is factorised (tile t of a run = column block t + tile0).
+// The panel planes are allocated with CH_TILE + CH_TJ rows to spare: operand rows behind the edge of the matrix are read
+// (whatever they hold) and the entries computed from them never stored.
 __global__ void __launch_bounds__(CH_SYRK_THREADS, 2)
 cholSyrkKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, const long long* __restrict__ info,
-               const double* __restrict__ panel, long long panelCol0)
+               const double* __restrict__ panel, long long panelCol0, long long planeStride, int stripOnly)
 {
     if(*info != 0)
         return;
@@ -301,48 +313,39 @@ cholSyrkKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, cons
     double* const A = runs.base[run];
     const long long n = runs.colEnd[run];
     const long long t = (static_cast<long long>(blockIdx.x) - runs.first[run]) + runs.tile0[run];
-    long long bj = static_cast<long long>(2.0 * sqrt(static_cast<double>(t)));
-    while(chSyrkTilesBefore(bj + 1) <= t) ++bj;
-    while(chSyrkTilesBefore(bj) > t) --bj;
-    const int ti = static_cast<int>(t - chSyrkTilesBefore(bj));
-    extern __shared__ double chSm[];                     // [2 stages][CH_TILE + CH_TJ][CH_SLD], then the column offsets
+    long long bj = t;
+    int ti = 0;
+    if(!stripOnly)
+    {
+        bj = static_cast<long long>(2.0 * sqrt(static_cast<double>(t)));
+        while(chSyrkTilesBefore(bj + 1) <= t) ++bj;
+        while(chSyrkTilesBefore(bj) > t) --bj;
+        ti = static_cast<int>(t - chSyrkTilesBefore(bj));
+    }
+    extern __shared__ double chSm[];                     // [2 stages][CH_TILE + CH_TJ][CH_SLD]
     const long long k1 = k0 + kb;
     const long long i0 = k1 + static_cast<long long>(ti) * CH_TILE, j0 = k1 + bj * CH_TJ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wi = warp >> 1, wj = warp & 1;             // warp tile: rows wi * 32, columns wj * 32
     constexpr int STAGE = (CH_TILE + CH_TJ) * CH_SLD;
-    long long* sOff = reinterpret_cast<long long*>(chSm + 2 * STAGE);     // first element of the panel run of every operand column, -1 = none
-    const double* op = panel ? panel : A;                // operand source (one GPU: the run is the whole triangle)
-    if(tid < CH_TILE + CH_TJ)
-    {
-        const long long x = tid < CH_TILE ? i0 + tid : j0 + (tid - CH_TILE);
-        sOff[tid] = x < n ? (panel ? (x - panelCol0) * CH_NB : chOff(x) + k0) : -1;
-    }
-    __syncthreads();
 
+    // staging: a warp instruction copies the 32 k-values of TWO operand columns (2 x 256 bytes, 16 bytes per lane); warp w takes
+    // the row pairs w, w + 8, ... of the stage (rows 0 .. 127 = the tile's rows i, 128 .. 191 = its columns j)
+    const int sRow = 2 * warp + (lane >> 4), sChunk = lane & 15;
+    const double* srcA = panel + (i0 - panelCol0 + sRow) * CH_NB + 2 * sChunk;
+    const double* srcB = panel + (j0 - panelCol0 + sRow) * CH_NB + 2 * sChunk;
+    const int dstOff = sRow * CH_SLD + ((sChunk ^ ((sRow & 1) << 2)) << 1);
     auto stage = [&](int buf, int kc)
     {
-        double* sP = chSm + buf * STAGE;
-        const bool live = kc + lane < kb;
-        // a warp copies the 32 k-values of one panel column (256 contiguous bytes) at a time; the column offsets are read
-        // eight at a time (the first version read one, waited for it, issued one copy: a quarter of the loop's stall samples)
-        constexpr int PER_WARP = (CH_TILE + CH_TJ) / (CH_SYRK_THREADS / 32);
-        static_assert(PER_WARP % 8 == 0, "staging loop is unrolled by eight");
+        double* sP = chSm + buf * STAGE + dstOff;
+        const long long kOff = static_cast<long long>(kc / CH_NB) * planeStride + (kc % CH_NB);
+        constexpr int ROWS_PER_PASS = 2 * (CH_SYRK_THREADS / 32);
 #pragma unroll
-        for(int m0 = 0; m0 < PER_WARP; m0 += 8)
-        {
-            long long off[8];
+        for(int m = 0; m < CH_TILE / ROWS_PER_PASS; ++m)
+            chCpAsync16(sP + m * ROWS_PER_PASS * CH_SLD, srcA + kOff + m * ROWS_PER_PASS * CH_NB);
 #pragma unroll
-            for(int m = 0; m < 8; ++m)
-                off[m] = sOff[warp + (m0 + m) * (CH_SYRK_THREADS / 32)];
-#pragma unroll
-            for(int m = 0; m < 8; ++m)
-            {
-                const int x = warp + (m0 + m) * (CH_SYRK_THREADS / 32);
-                const bool l = live && off[m] >= 0;
-                chCpAsync8(sP + x * CH_SLD + lane, l ? op + off[m] + kc + lane : op, l);
-            }
-        }
+        for(int m = 0; m < CH_TJ / ROWS_PER_PASS; ++m)
+            chCpAsync16(sP + (CH_TILE + m * ROWS_PER_PASS) * CH_SLD, srcB + kOff + m * ROWS_PER_PASS * CH_NB);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     stage(0, 0);
@@ -379,21 +382,28 @@ cholSyrkKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, cons
         __syncthreads();
         const double* sA = chSm + (ch & 1) * STAGE;
         const double* sB = sA + CH_TILE * CH_SLD;
+        const int g = lane >> 2, sw = (g & 1) << 2;      // (row & 1) == (g & 1): the warp's row offsets are even
 #pragma unroll
-        for(int k4 = 0; k4 < CH_KC; k4 += 4)
+        for(int k8 = 0; k8 < CH_KC; k8 += 8)
         {
-            double fa[4], fb[4];
+            const int kOff = (((k8 >> 1) + (lane & 3)) ^ sw) << 1;
+            double2 fa[4], fb[4];
 #pragma unroll
             for(int a = 0; a < 4; ++a)
-                fa[a] = -sA[(wi * 32 + a * 8 + (lane >> 2)) * CH_SLD + k4 + (lane & 3)];
+                fa[a] = *reinterpret_cast<const double2*>(sA + (wi * 32 + a * 8 + g) * CH_SLD + kOff);
 #pragma unroll
             for(int b = 0; b < 4; ++b)
-                fb[b] = sB[(wj * 32 + b * 8 + (lane >> 2)) * CH_SLD + k4 + (lane & 3)];
+                fb[b] = *reinterpret_cast<const double2*>(sB + (wj * 32 + b * 8 + g) * CH_SLD + kOff);
 #pragma unroll
             for(int a = 0; a < 4; ++a)
 #pragma unroll
                 for(int b = 0; b < 4; ++b)
-                    chDmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+                    chDmma(acc[a][b][0], acc[a][b][1], -fa[a].x, fb[b].x);
+#pragma unroll
+            for(int a = 0; a < 4; ++a)
+#pragma unroll
+                for(int b = 0; b < 4; ++b)
+                    chDmma(acc[a][b][0], acc[a][b][1], -fa[a].y, fb[b].y);
         }
         __syncthreads();                                 // the buffer is free for the chunk after next
     }

@@ -69,6 +69,9 @@ struct cmg_ctx
     int64_t bytesH2D = 0, bytesD2H = 0;          // what crossed PCIe through this context (cmg_transfer_counters)
     long long* dCholInfo = nullptr;              // status word of cmg_packed_cholesky
     double* dCholRed = nullptr;                  // log det / reductions of the packed solves
+    double* dCholPanel = nullptr;                // dense panel planes of cmg_packed_cholesky (cholesky.cuh, cholSyrkKernel)
+    size_t cholPanelDoubles = 0;
+    int cholGroup = 2;                           // blocks of 128 rows per trailing update (cmg_set_cholesky_group)
     int likeMethod = 0;                          // cmg_like_create: 0 = this library's packed factorisation, 1 = cuSOLVER on the unpacked matrix
 };
 
@@ -473,6 +476,7 @@ void cmg_destroy(cmg_ctx* ctx)
     if(ctx->dIndex) cudaFree(ctx->dIndex);
     if(ctx->dCholInfo) cudaFree(ctx->dCholInfo);
     if(ctx->dCholRed) cudaFree(ctx->dCholRed);
+    if(ctx->dCholPanel) cudaFree(ctx->dCholPanel);
     for(int k = 0; k < cmg_ctx::kAux; ++k)
     {
         if(ctx->aux[k]) { cudaStreamSynchronize(ctx->aux[k]); cudaStreamDestroy(ctx->aux[k]); }
@@ -1773,7 +1777,9 @@ namespace
 {
 constexpr int CH_DIAG_SMEM = cmg::CH_NB * cmg::CH_LD * sizeof(double);
 constexpr int CH_PANEL_SMEM = cmg::CH_PANEL_SMEM_DOUBLES * sizeof(double);
-constexpr int CH_SYRK_SMEM = 2 * (cmg::CH_TILE + cmg::CH_TJ) * cmg::CH_SLD * sizeof(double) + (cmg::CH_TILE + cmg::CH_TJ) * sizeof(long long);
+constexpr int CH_SYRK_SMEM = 2 * (cmg::CH_TILE + cmg::CH_TJ) * cmg::CH_SLD * sizeof(double);
+constexpr int CH_MAX_GROUP = 4;                  // blocks per trailing update at most
+constexpr int64_t CH_PLANE_SLACK = cmg::CH_TILE + cmg::CH_TJ;      // operand rows a tile may read behind the last column
 
 cmg_status cholStepAttributes(cmg_ctx* ctx)
 {
@@ -1796,7 +1802,7 @@ cmg::CholRuns cholWholeRun(double* dA, int64_t colBegin, int64_t n)
 
 // A rank's runs clipped to the columns >= from (a multiple of 64 behind k1, or the start of a run), with the CTA prefix of a
 // launch that gives `unit` columns to a CTA (panel: 128, solve update: 8); syrk: the tile counts of chSyrkTilesBefore relative
-// to k1 instead (unit = 0).  Returns the total number of CTAs.
+// to k1 instead (unit = 0), or one tile per 64-column block (unit < 0: the strip update).  Returns the total number of CTAs.
 int64_t cholClipRuns(const cmg_chol_runs* in, int64_t from, int64_t k1, int unit, cmg::CholRuns* out)
 {
     int64_t total = 0;
@@ -1819,8 +1825,8 @@ int64_t cholClipRuns(const cmg_chol_runs* in, int64_t from, int64_t k1, int unit
         else
         {
             const int64_t b0 = (c0 - k1) / cmg::CH_TJ, b1 = (c1 - k1 + cmg::CH_TJ - 1) / cmg::CH_TJ;
-            out->tile0[k] = cmg::chSyrkTilesBefore(b0);
-            total += cmg::chSyrkTilesBefore(b1) - out->tile0[k];
+            out->tile0[k] = unit == 0 ? cmg::chSyrkTilesBefore(b0) : b0;                              // unit < 0: first row tile only
+            total += unit == 0 ? cmg::chSyrkTilesBefore(b1) - out->tile0[k] : b1 - b0;
         }
     }
     out->first[out->count] = total;
@@ -1851,6 +1857,18 @@ int cholRunOfColumn(const cmg_chol_runs* runs, int64_t k0)
 }
 }
 
+cmg_status cmg_set_cholesky_group(cmg_ctx* ctx, int blocks)
+{
+    if(!ctx) return CMG_EINVAL;
+    if(blocks < 1 || blocks > CH_MAX_GROUP) return fail(ctx, CMG_EINVAL, "cmg_set_cholesky_group: 1 .. 4 blocks of 128 rows");
+    ctx->cholGroup = blocks;
+    return CMG_OK;
+}
+
+// Right-looking in GROUPS of S blocks of 128 rows: inside a group every block is factorised, its 128 rows solved for all columns
+// behind it (packed in place + dense plane s), and only the NEXT block's 128 rows are brought up to date (strip update, K = 128 s);
+// the trailing matrix behind the group is then updated ONCE with all 128 S rows -- it is read and written n / (128 S) times
+// instead of n / 128, and a tile's loads of C, its barriers and its stores are amortised over S times the DMMAs.
 cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* info)
 {
     if(!ctx) return CMG_EINVAL;
@@ -1859,26 +1877,55 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
     cmg_status s = cholBuffers(ctx);
     if(s != CMG_OK) return s;
     if((s = cholStepAttributes(ctx)) != CMG_OK) return s;
+    const int S = ctx->cholGroup;
+    const int64_t planeStride = (n + CH_PLANE_SLACK) * cmg::CH_NB;
+    if(ctx->cholPanelDoubles < static_cast<size_t>(S * planeStride))
+    {
+        if(ctx->dCholPanel) CMG_CUDA(ctx, cudaFree(ctx->dCholPanel));
+        ctx->dCholPanel = nullptr;
+        ctx->cholPanelDoubles = 0;
+        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholPanel, sizeof(double) * S * planeStride));
+        ctx->cholPanelDoubles = static_cast<size_t>(S * planeStride);
+        CMG_CUDA(ctx, cudaMemsetAsync(ctx->dCholPanel, 0, sizeof(double) * S * planeStride, ctx->stream));   // the slack rows are read
+    }
     CMG_CUDA(ctx, cudaMemsetAsync(ctx->dCholInfo, 0, sizeof(long long), ctx->stream));
     KernelTimer timer(ctx);
-    for(int64_t k0 = 0; k0 < n; k0 += cmg::CH_NB)
+    bool done = false;
+    for(int64_t kBase = 0; kBase < n && !done; kBase += static_cast<int64_t>(S) * cmg::CH_NB)
     {
-        const int kb = static_cast<int>(std::min<int64_t>(cmg::CH_NB, n - k0));
-        cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, ctx->stream>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr);
-        const int64_t rem = n - k0 - kb;
-        ctx->launches += 1;
-        if(rem <= 0)
+        for(int sub = 0; sub < S; ++sub)
+        {
+            const int64_t k0 = kBase + static_cast<int64_t>(sub) * cmg::CH_NB;
+            if(k0 >= n) { done = true; break; }
+            const int kb = static_cast<int>(std::min<int64_t>(cmg::CH_NB, n - k0));
+            if(sub > 0)
+            {
+                // rows k0 .. k0 + 128 of every column from k0 on catch up with the sub blocks already solved
+                cmg::CholRuns runs = cholWholeRun(dA, k0, n);
+                runs.first[1] = (n - k0 + cmg::CH_TJ - 1) / cmg::CH_TJ;
+                cmg::cholSyrkKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(
+                    runs, kBase, sub * cmg::CH_NB, ctx->dCholInfo, ctx->dCholPanel, kBase, planeStride, 1);
+                ctx->launches += 1;
+            }
+            cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, ctx->stream>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr);
+            ctx->launches += 1;
+            const int64_t rem = n - k0 - kb;
+            if(rem <= 0) { done = true; break; }
+            // (kb == CH_NB from here on: a short block can only be the last one)
+            cmg::CholRuns runs = cholWholeRun(dA, k0 + kb, n);
+            runs.first[1] = (rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS;
+            cmg::cholPanelKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_PANEL_COLS, CH_PANEL_SMEM, ctx->stream>>>(
+                runs, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr, ctx->dCholPanel + sub * planeStride, kBase);
+            ctx->launches += 1;
+        }
+        const int64_t kEnd = kBase + static_cast<int64_t>(S) * cmg::CH_NB;
+        if(done || kEnd >= n)
             break;
-        // (kb == CH_NB from here on: a short block can only be the last one)
-        cmg::CholRuns runs = cholWholeRun(dA, k0 + kb, n);
-        runs.first[1] = (rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS;
-        cmg::cholPanelKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_PANEL_COLS, CH_PANEL_SMEM, ctx->stream>>>(
-            runs, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr, nullptr, 0);
-        const int64_t colBlocks = (rem + cmg::CH_TJ - 1) / cmg::CH_TJ;           // 64-column blocks; block b meets the row tiles 0 .. b / 2
-        runs.first[1] = cmg::chSyrkTilesBefore(colBlocks);
+        cmg::CholRuns runs = cholWholeRun(dA, kEnd, n);
+        runs.first[1] = cmg::chSyrkTilesBefore((n - kEnd + cmg::CH_TJ - 1) / cmg::CH_TJ);    // 64-column blocks; block b meets the row tiles 0 .. b / 2
         cmg::cholSyrkKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(
-            runs, k0, kb, ctx->dCholInfo, nullptr, 0);
-        ctx->launches += 2;
+            runs, kBase, S * cmg::CH_NB, ctx->dCholInfo, ctx->dCholPanel, kBase, planeStride, 0);
+        ctx->launches += 1;
     }
     CMG_CUDA(ctx, cudaGetLastError());
     if((s = timer.finish()) != CMG_OK) return s;
@@ -1937,8 +1984,9 @@ cmg_status cmg_chol_diag(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, in
 cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* dUkk, double* dPanel, int64_t panelCol0)
 {
     if(!ctx) return CMG_EINVAL;
-    if(!cholRunsValid(runs) || !dUkk || !dPanel || kb != cmg::CH_NB || k0 % cmg::CH_NB || panelCol0 > k0 + kb || !ctx->dCholInfo)
-        return fail(ctx, CMG_EINVAL, "cmg_chol_panel: bad arguments (a full block of 128 rows; panel_col0 <= k0 + 128)");
+    if(!cholRunsValid(runs) || !dUkk || !dPanel || kb != cmg::CH_NB || k0 % cmg::CH_NB || panelCol0 > k0 + kb || !ctx->dCholInfo ||
+       reinterpret_cast<uintptr_t>(dPanel) % 16)
+        return fail(ctx, CMG_EINVAL, "cmg_chol_panel: bad arguments (a full block of 128 rows; panel_col0 <= k0 + 128; a 16-byte aligned plane)");
     cmg::CholRuns clipped;
     const int64_t ctas = cholClipRuns(runs, k0 + kb, k0 + kb, cmg::CH_PANEL_COLS, &clipped);
     if(ctas == 0) return CMG_OK;
@@ -1950,16 +1998,19 @@ cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, i
     return CMG_OK;
 }
 
-cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* dPanel, int64_t panelCol0)
+cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* dPanel, int64_t planeStride, int64_t panelCol0,
+                         int stripOnly)
 {
     if(!ctx) return CMG_EINVAL;
-    if(!cholRunsValid(runs) || !dPanel || kb != cmg::CH_NB || k0 % cmg::CH_NB || panelCol0 > k0 + kb || !ctx->dCholInfo)
-        return fail(ctx, CMG_EINVAL, "cmg_chol_syrk: bad arguments (a full block of 128 rows; panel_col0 <= k0 + 128)");
+    if(!cholRunsValid(runs) || !dPanel || kb < cmg::CH_NB || kb > CH_MAX_GROUP * cmg::CH_NB || kb % cmg::CH_NB || k0 % cmg::CH_NB || panelCol0 > k0 + cmg::CH_NB ||
+       panelCol0 % 2 || planeStride % 2 || !ctx->dCholInfo)
+        return fail(ctx, CMG_EINVAL, "cmg_chol_syrk: bad arguments (kb = 128 .. 512 rows in whole blocks; panel_col0 <= k0 + 128)");
     cmg::CholRuns clipped;
-    const int64_t tiles = cholClipRuns(runs, k0 + kb, k0 + kb, 0, &clipped);
+    const int64_t tiles = cholClipRuns(runs, k0 + kb, k0 + kb, stripOnly ? -1 : 0, &clipped);
     if(tiles == 0) return CMG_OK;
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
-    cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(clipped, k0, kb, ctx->dCholInfo, dPanel, panelCol0);
+    cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(clipped, k0, kb, ctx->dCholInfo, dPanel, panelCol0,
+                                                                                                         planeStride, stripOnly ? 1 : 0);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return CMG_OK;

@@ -379,11 +379,15 @@ class ShardedCholesky:
     of one rank interleave with everyone else's 36 times over the matrix, so the shrinking trailing matrix stays balanced
     (a block-cyclic distribution with 36 cycles).
 
-    Right-looking, 128 rows per step; the reference runs LAPACK dpptrf on the host (source/matrix_impl.cpp:236-263).  Per step:
-      owner of block k: U_kk (cmg_chol_diag)                       -> broadcast of 66 KB
-      every rank: the 128 rows of its own columns (cmg_chol_panel)  -> all-reduce of the dense panel (<= 151 MB, entries of
-                  other ranks' columns are zero: the sum is a gather that needs no layout agreement between ranks)
-      every rank: trailing update of its own columns (cmg_chol_syrk, FP64 tensor-core tiles, operands from the dense panel)
+    Right-looking, blocks of 128 rows taken in groups of `group` (the reference runs LAPACK dpptrf on the host,
+    source/matrix_impl.cpp:236-263).  Per block:
+      every rank: the block's 128 rows of its own columns catch up with the group's earlier blocks (cmg_chol_syrk, strip)
+      owner of the block: U_kk (cmg_chol_diag)                      -> broadcast of 66 KB
+      every rank: the 128 rows of its own columns (cmg_chol_panel)  -> all-reduce of that plane of the dense panel (<= 151 MB,
+                  entries of other ranks' columns are zero: the sum is a gather that needs no layout agreement between ranks)
+    and per group
+      every rank: trailing update of its own columns with all 128 * group rows (cmg_chol_syrk, FP64 tensor-core tiles,
+                  operands from the dense panel)
     Over the whole factorisation every rank receives the factor once (87 GB over NVLink against n^3 / 3 / G of arithmetic).
 
     `comm`: broadcast(tensor, src) / all_reduce(tensor) (TorchComm).  The context must run on torch's current stream
@@ -391,19 +395,26 @@ class ShardedCholesky:
     serialise the host with the device every time.  `ukk` / `panel`: torch buffers to use (ranks emulated on ONE GPU share
     them -- tests/test_gpu_cholesky.py); allocated when None."""
 
-    def __init__(self, ctx, n, all_runs, rank, run_ptrs, comm=None, ukk=None, panel=None):
+    def __init__(self, ctx, n, all_runs, rank, run_ptrs, comm=None, ukk=None, panel=None, group=2):
         import torch
         self.ctx, self.n, self.rank, self.world = ctx, int(n), rank, len(all_runs)
         self.owners = chol_block_owners(self.n, all_runs)
         mine = [(b, e) for b, e in all_runs[rank]]
         if len(run_ptrs) != len(mine):
             raise ValueError("one device pointer per run of this rank")
+        if not 1 <= group <= capi.CHOL_MAX_GROUP:
+            raise ValueError("group: 1 .. %d blocks" % capi.CHOL_MAX_GROUP)
         live = [(b, e, p) for (b, e), p in zip(mine, run_ptrs) if e > b]
         self.runs = capi.make_chol_runs(live) if live else None
         self.comm = comm if comm is not None else TorchComm()
         nb = capi.CHOL_NB
+        self.group = group
+        self.plane_stride = (self.n + capi.CHOL_PLANE_SLACK) * nb
         self.ukk = ukk if ukk is not None else torch.empty(nb * (nb + 1) // 2 + nb, dtype=torch.float64, device="cuda")
-        self.panel = panel if panel is not None else torch.empty(max(self.n - nb, 1) * nb, dtype=torch.float64, device="cuda")
+        # zeros: the spare rows behind the last column are read (never used)
+        self.panel = panel if panel is not None else torch.zeros(group * self.plane_stride, dtype=torch.float64, device="cuda")
+        if self.panel.numel() < group * self.plane_stride:
+            raise ValueError("panel: group * (n + %d) * %d doubles" % (capi.CHOL_PLANE_SLACK, nb))
         self.device = self.panel.device
         self.info = None
 
@@ -412,44 +423,69 @@ class ShardedCholesky:
         if self.world > 1 and self.device.type == "cuda" and self.ctx.stream_handle != torch.cuda.current_stream().cuda_stream:
             raise RuntimeError("ShardedCholesky: the context must share torch's current stream (ctx.set_stream(torch.cuda.current_stream().cuda_stream))")
 
-    # ---- the phases of a step (a test drives emulated ranks through them in lock step)
+    # ---- the phases (a test drives emulated ranks through them in lock step)
     def blocks(self):
         nb = capi.CHOL_NB
         return [(k0, min(nb, self.n - k0)) for k0 in range(0, self.n, nb)]
 
-    def step_diag(self, k0, kb):
-        """owner only"""
-        self.ctx.chol_diag(self.runs, k0, kb, self.ukk)
+    def schedule(self):
+        """the order of phases, the same on every rank: ("strip", group start, sub) | ("diag", k0, kb, owner) |
+        ("panel", k0, group start, sub) | ("syrk", group start, blocks in the group)"""
+        nb, out = capi.CHOL_NB, []
+        for base in range(0, self.n, nb * self.group):
+            subs = 0
+            for sub in range(self.group):
+                k0 = base + sub * nb
+                if k0 >= self.n:
+                    break
+                kb = min(nb, self.n - k0)
+                if sub:
+                    out.append(("strip", base, sub))
+                out.append(("diag", k0, kb, self.owners[k0 // nb]))
+                if k0 + kb >= self.n:
+                    return out
+                out.append(("panel", k0, base, sub))
+                subs = sub + 1
+            if base + subs * nb < self.n and subs == self.group:
+                out.append(("syrk", base, subs))
+        return out
 
-    def step_panel(self, k0, kb):
-        if self.runs is not None:
-            self.ctx.chol_panel(self.runs, k0, kb, self.ukk, self.panel, k0 + kb)
+    def plane_region(self, k0, base, sub):
+        """the part of plane `sub` the panel step of block k0 fills: the 128 rows of every column behind the block"""
+        nb = capi.CHOL_NB
+        first = sub * self.plane_stride + (k0 + nb - base) * nb
+        return self.panel[first:first + (self.n - k0 - nb) * nb]
 
-    def step_syrk(self, k0, kb):
-        if self.runs is not None:
-            self.ctx.chol_syrk(self.runs, k0, kb, self.panel, k0 + kb)
+    def run_phase(self, ph):
+        """this rank's kernel of a phase (no exchange)"""
+        nb = capi.CHOL_NB
+        if self.runs is None:
+            return
+        if ph[0] == "strip":
+            self.ctx.chol_syrk(self.runs, ph[1], ph[2] * nb, self.panel, self.plane_stride, ph[1], True)
+        elif ph[0] == "diag":
+            if ph[3] == self.rank:
+                self.ctx.chol_diag(self.runs, ph[1], ph[2], self.ukk)
+        elif ph[0] == "panel":
+            self.ctx.chol_panel(self.runs, ph[1], nb, self.ukk, self.panel[ph[3] * self.plane_stride:], ph[2])
+        else:
+            self.ctx.chol_syrk(self.runs, ph[1], ph[2] * nb, self.panel, self.plane_stride, ph[1], False)
 
     def factorise(self):
         """Collective.  Returns LAPACK's info (0: positive definite; k: the leading minor of order k is not), the same on every rank."""
         import torch
         self._check_stream()
-        nb = capi.CHOL_NB
         self.ctx.chol_begin()
-        for k0, kb in self.blocks():
-            owner = self.owners[k0 // nb]
-            if owner == self.rank:
-                self.step_diag(k0, kb)
-            if k0 + kb >= self.n:
-                break
-            if self.world > 1:
-                self.comm.broadcast(self.ukk, owner)
-            active = self.panel[:(self.n - k0 - kb) * nb]
-            if self.world > 1:
-                active.zero_()
-            self.step_panel(k0, kb)
-            if self.world > 1:
-                self.comm.all_reduce(active)
-            self.step_syrk(k0, kb)
+        for ph in self.schedule():
+            if ph[0] == "panel" and self.world > 1:
+                region = self.plane_region(ph[1], ph[2], ph[3])
+                region.zero_()
+                self.run_phase(ph)
+                self.comm.all_reduce(region)
+                continue
+            self.run_phase(ph)
+            if ph[0] == "diag" and self.world > 1 and ph[1] + ph[2] < self.n:
+                self.comm.broadcast(self.ukk, ph[3])
         info = self.ctx.chol_end()
         if self.world > 1:                       # the first failing block wins on every rank
             big = 1 << 62

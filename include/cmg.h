@@ -352,6 +352,9 @@ cmg_status cmg_sum_unpack_strided(cmg_ctx* ctx, const double* d_c, int64_t c_str
  * n (n + 1) / 2 doubles of the matrix itself, so the 147456-dimensional matrix of Nside = 64 is factorised where the generator
  * left it.  *info = 0, or k > 0 when the leading minor of order k is not positive definite (d_packed is then partly overwritten). */
 cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* d_packed, int64_t n, int64_t* info);
+/* blocks of 128 rows per trailing update (1 .. 4, default 2): the trailing matrix is read and written once per GROUP of blocks;
+ * workspace blocks x (n + 192) x 128 doubles on the device (the rows of U of the group in dense form, the operands of the update) */
+cmg_status cmg_set_cholesky_group(cmg_ctx* ctx, int blocks);
 /* log det A = 2 sum_i log U_ii from the factor */
 cmg_status cmg_packed_cholesky_logdet(cmg_ctx* ctx, const double* d_factor, int64_t n, double* log_det);
 /* y = U^-T t for n_rhs right-hand sides, in place: d_rhs is n x n_rhs column-major on the device; t^T A^-1 t = |y|^2 */
@@ -363,13 +366,19 @@ cmg_status cmg_packed_cholesky_solve(cmg_ctx* ctx, const double* d_factor, int64
  * 128 (the end of the matrix excepted); d_run[r] = address of entry (0, col_begin[r]).  These are exactly the 36 strips a rank
  * of cmg_orbit_shard holds after the exchange (partition boundaries rounded to 128), so the Nside = 64 matrix is factorised
  * where the generator and the exchange left it: no gather, no redistribution.
- * Step k (k0 = 128 k, kb = min(128, n - k0)):
- *   cmg_chol_diag   (owner of block k only)  U_kk in place, and packed into d_ukk: kb (kb + 1) / 2 entries, then kb reciprocal
+ * Blocks of 128 rows are taken in groups of S <= 4 (as cmg_packed_cholesky does, cmg_set_cholesky_group).  The dense panel is
+ * S planes of (n + 192) x 128 doubles, d_panel[s * plane_stride + (column - panel_col0) * 128 + row]; panel_col0 = first row of
+ * the group.  Block s of a group (k0 = group start + 128 s, kb = min(128, n - k0)):
+ *   cmg_chol_syrk   (every rank, s > 0, strip_only = 1, k0 = group start, kb = 128 s)  rows of block s of the rank's own columns
+ *                   catch up with the blocks of the group already solved.
+ *   cmg_chol_diag   (owner of the block only)  U_kk in place, and packed into d_ukk: kb (kb + 1) / 2 entries, then kb reciprocal
  *                   pivots.  The caller broadcasts d_ukk (<= 67 KB) from the owner.
  *   cmg_chol_panel  (every rank, kb = 128)  rows k0 .. k0 + 128 of the rank's own columns behind the block: solved in place and
- *                   also written to the dense panel d_panel[(column - panel_col0) * 128 + row].  The caller zeroes the panel
+ *                   also written to plane s (d_plane = d_panel + s * plane_stride).  The caller zeroes that part of the plane
  *                   before and all-reduces (sum) it after: every rank then holds the 128 rows of EVERY column behind the block.
- *   cmg_chol_syrk   (every rank)  trailing update of the rank's own columns, operands read from the dense panel.
+ * and after the last block of the group
+ *   cmg_chol_syrk   (every rank, strip_only = 0, k0 = group start, kb = 128 S)  trailing update of the rank's own columns behind
+ *                   the group, operands read from the S planes.
  * cmg_chol_begin before the first step, cmg_chol_end after the last (*info as cmg_packed_cholesky: the first non-positive pivot
  * of a block this rank owns, 0 otherwise; the caller takes the minimum of the non-zero values over ranks). */
 #define CMG_CHOL_MAX_RUNS 36
@@ -383,8 +392,9 @@ typedef struct cmg_chol_runs
 cmg_status cmg_chol_begin(cmg_ctx* ctx);
 cmg_status cmg_chol_end(cmg_ctx* ctx, int64_t* info);
 cmg_status cmg_chol_diag(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, double* d_ukk);
-cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* d_ukk, double* d_panel, int64_t panel_col0);
-cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* d_panel, int64_t panel_col0);
+cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* d_ukk, double* d_plane, int64_t panel_col0);
+cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* d_panel, int64_t plane_stride,
+                         int64_t panel_col0, int strip_only);
 /* this rank's share of log det A: 2 sum log U_jj over its columns (the caller sums over ranks) */
 cmg_status cmg_chol_logdet_runs(cmg_ctx* ctx, const cmg_chol_runs* runs, double* log_det_share);
 /* y = U^-T t on the sharded factor, d_rhs (n x n_rhs, column-major) replicated on every rank.  Step k: the owner of block k solves

@@ -116,8 +116,24 @@ class _NoComm:
         pass
 
 
-@pytest.mark.parametrize("n, world, cycles", [(1280, 2, 2), (1536 + 77, 3, 2), (2048, 4, 4)])
-def test_sharded_cholesky_ranks_in_lock_step(gpu_ctx, n, world, cycles):
+@pytest.mark.parametrize("group", [1, 2, 3, 4])
+@pytest.mark.parametrize("n", [128, 129, 500, 1153])
+def test_packed_cholesky_groups_of_blocks(gpu_ctx, n, group):
+    """cmg_set_cholesky_group: every group size gives the same factor (strip updates + one trailing update per group)"""
+    import torch
+    A = random_spd(n, 500 + n)
+    d = torch.from_numpy(pack_upper(A)).cuda()
+    gpu_ctx.set_cholesky_group(group)
+    try:
+        assert gpu_ctx.packed_cholesky(d, n) == 0
+    finally:
+        gpu_ctx.set_cholesky_group(2)
+    want = np.linalg.cholesky(A).T
+    assert np.abs(unpack_upper(d.cpu().numpy(), n) - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n, world, cycles, group", [(1280, 2, 2, 1), (1536 + 77, 3, 2, 2), (2048, 4, 4, 2), (2048 + 300, 2, 3, 4)])
+def test_sharded_cholesky_ranks_in_lock_step(gpu_ctx, n, world, cycles, group):
     """the step functions of the sharded factorisation (cmg_chol_*; multigpu.ShardedCholesky) with `world` ranks emulated on one
     GPU: the columns are dealt out in runs of 128 ... 384 columns, `cycles` runs per rank interleaved like the strips of
     cmg_orbit_shard; every rank factorises its own copy of its columns, sharing only U_kk and the dense panel.  Factor, log det
@@ -138,19 +154,14 @@ def test_sharded_cholesky_ranks_in_lock_step(gpu_ctx, n, world, cycles):
     off = lambda c: c * (c + 1) // 2
     bufs = [[torch.from_numpy(packed[off(b):off(e)].copy()).cuda() for b, e in all_runs[r]] for r in range(world)]
     ukk = torch.zeros(nb * (nb + 1) // 2 + nb, dtype=torch.float64, device="cuda")
-    panel = torch.zeros(max(n - nb, 1) * nb, dtype=torch.float64, device="cuda")
-    ranks = [multigpu.ShardedCholesky(gpu_ctx, n, all_runs, r, [t.data_ptr() for t in bufs[r]], comm=_NoComm(), ukk=ukk, panel=panel)
+    panel = torch.zeros(group * (n + capi.CHOL_PLANE_SLACK) * nb, dtype=torch.float64, device="cuda")
+    ranks = [multigpu.ShardedCholesky(gpu_ctx, n, all_runs, r, [t.data_ptr() for t in bufs[r]], comm=_NoComm(), ukk=ukk, panel=panel, group=group)
              for r in range(world)]
     assert ranks[0].owners == multigpu.chol_block_owners(n, all_runs)
     gpu_ctx.chol_begin()
-    for k0, kb in ranks[0].blocks():
-        ranks[ranks[0].owners[k0 // nb]].step_diag(k0, kb)
-        if k0 + kb >= n:
-            break
-        for r in ranks:
-            r.step_panel(k0, kb)
-        for r in ranks:
-            r.step_syrk(k0, kb)
+    for ph in ranks[0].schedule():
+        for r in ranks:                                     # "diag" runs on the owner only (run_phase checks)
+            r.run_phase(ph)
     assert gpu_ctx.chol_end() == 0
     got = np.empty_like(packed)
     for r in range(world):

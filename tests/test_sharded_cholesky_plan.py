@@ -92,9 +92,9 @@ class NumpyStepCtx:
             U[:c + 1, c] = u[off(c):off(c + 1)]
         return U
 
-    def chol_panel(self, runs, k0, kb, ukk, panel, panel_col0):
+    def chol_panel(self, runs, k0, kb, ukk, plane, panel_col0):
         U = self._ukk(ukk, kb)
-        P = panel.numpy()
+        P = plane.numpy()
         for b, e, _ in self._cols(runs):
             for j in range(max(b, k0 + kb), e):
                 col = self._column(runs, j)
@@ -102,13 +102,15 @@ class NumpyStepCtx:
                 col[k0:k0 + kb] = x
                 P[(j - panel_col0) * NB:(j - panel_col0) * NB + kb] = x
 
-    def chol_syrk(self, runs, k0, kb, panel, panel_col0):
+    def chol_syrk(self, runs, k0, kb, panel, plane_stride, panel_col0, strip_only):
         k1 = k0 + kb
-        P = panel.numpy().reshape(-1, NB)
+        planes = [panel.numpy()[s * plane_stride:(s + 1) * plane_stride].reshape(-1, NB) for s in range(kb // NB)]
         for b, e, _ in self._cols(runs):
             for j in range(max(b, k1), e):
                 col = self._column(runs, j)
-                col[k1:j + 1] -= P[k1 - panel_col0:j + 1 - panel_col0] @ P[j - panel_col0]
+                i1 = min(j + 1, k1 + NB) if strip_only else j + 1
+                for P in planes:
+                    col[k1:i1] -= P[k1 - panel_col0:i1 - panel_col0] @ P[j - panel_col0]
 
     def chol_logdet_runs(self, runs):
         return 2.0 * sum(np.log(self._column(runs, j)[j]) for b, e, _ in self._cols(runs) for j in range(b, e))
@@ -141,7 +143,7 @@ def packed_of(A):
     return out
 
 
-def _worker(rank, world, port, n, all_runs, bad, out):
+def _worker(rank, world, port, n, all_runs, bad, group, out):
     import torch
     import torch.distributed as dist
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
@@ -152,8 +154,8 @@ def _worker(rank, world, port, n, all_runs, bad, out):
     arrays = {1000 + k: packed[off(b):off(e)].copy() for k, (b, e) in enumerate(all_runs[rank])}
     ctx = NumpyStepCtx(arrays)
     ukk = torch.zeros(off(NB) + NB, dtype=torch.float64)
-    panel = torch.zeros(max(n - NB, 1) * NB, dtype=torch.float64)
-    ch = multigpu.ShardedCholesky(ctx, n, all_runs, rank, list(arrays.keys()), ukk=ukk, panel=panel)
+    panel = torch.zeros(group * (n + capi.CHOL_PLANE_SLACK) * NB, dtype=torch.float64)
+    ch = multigpu.ShardedCholesky(ctx, n, all_runs, rank, list(arrays.keys()), ukk=ukk, panel=panel, group=group)
     info = ch.factorise()
     res = {"rank": rank, "info": info}
     if not bad:
@@ -174,15 +176,33 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("bad", [0, 300])
-def test_two_ranks_factorise_over_gloo(bad):
+def test_schedule_of_phases():
+    n = 5 * NB + 40
+    all_runs = [[(0, n)]]
+    ch = multigpu.ShardedCholesky(NumpyStepCtx({}), n, all_runs, 0, [1], ukk=np.zeros(1), panel=_zeros(3 * (n + capi.CHOL_PLANE_SLACK) * NB), group=3)
+    kinds = [p[0] for p in ch.schedule()]
+    assert kinds == ["diag", "panel", "strip", "diag", "panel", "strip", "diag", "panel", "syrk",
+                     "diag", "panel", "strip", "diag", "panel", "strip", "diag"]
+    one = multigpu.ShardedCholesky(NumpyStepCtx({}), n, all_runs, 0, [1], ukk=np.zeros(1), panel=_zeros((n + capi.CHOL_PLANE_SLACK) * NB), group=1)
+    assert [p[0] for p in one.schedule()] == ["diag", "panel", "syrk"] * 5 + ["diag"]
+    assert [p[0] for p in multigpu.ShardedCholesky(NumpyStepCtx({}), 256, [[(0, 256)]], 0, [1], ukk=np.zeros(1),
+                                                   panel=_zeros(2 * (256 + capi.CHOL_PLANE_SLACK) * NB), group=2).schedule()] == ["diag", "panel", "strip", "diag"]
+
+
+def _zeros(k):
+    import torch
+    return torch.zeros(k, dtype=torch.float64)
+
+
+@pytest.mark.parametrize("bad, group", [(0, 1), (0, 2), (0, 3), (300, 2)])
+def test_two_ranks_factorise_over_gloo(bad, group):
     import torch.multiprocessing as mp
     n, world = 5 * NB + 40, 2
     all_runs = [[(0, 128), (384, 512)], [(128, 384), (512, n)]]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, all_runs, bad, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, all_runs, bad, group, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda d: d["rank"])

@@ -13,7 +13,8 @@ ctx = cb.Context(0)
 stream = torch.cuda.current_stream()
 ctx.set_stream(stream.cuda_stream)
 peak = ctx.measure_fp64_peak()
-for nside in [int(a) for a in sys.argv[1:]] or [16, 32]:
+groups = [int(g) for a in sys.argv[1:] if a.startswith("--groups=") for g in a.split("=")[1].split(",")] or [2]
+for nside in [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [16, 32]:
     lmax = 3 * nside
     ctx.set_pixels(nside)
     n = 3 * ctx.npix
@@ -39,19 +40,21 @@ for nside in [int(a) for a in sys.argv[1:]] or [16, 32]:
         want_logdet = 2.0 * float(torch.log(torch.diagonal(L)).sum())
         del full, L, iu
         torch.cuda.empty_cache()
-    work = d.clone() if n <= 40000 else d
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if n <= 40000:
-        ctx.packed_cholesky(work, n); work.copy_(d)                    # warm-up
-    torch.cuda.synchronize()
-    e0.record(stream); info = ctx.packed_cholesky(work, n); e1.record(stream); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    logdet = ctx.packed_cholesky_logdet(work, n)
-    flop = n ** 3 / 3.0
-    line = {"nside": nside, "n": n, "packed_gb": capi.packed_size(n) * 8e-9, "info": info, "packed_cholesky_ms": ms,
-            "tflops": flop / (ms * 1e-3) / 1e12, "fp64_peak_tflops": peak, "frac_of_peak": flop / (ms * 1e-3) / 1e12 / peak,
-            "cusolver_potrf_ms_on_unpacked": dense_ms, "logdet": logdet,
-            "logdet_rel_diff_vs_cusolver": (abs(logdet - want_logdet) / abs(want_logdet)) if dense_ms is not None else None}
-    print(json.dumps(line), flush=True)
+    for group in groups:
+        ctx.set_cholesky_group(group)
+        work = d.clone() if n <= 40000 else d
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if n <= 40000:
+            ctx.packed_cholesky(work, n); work.copy_(d)                    # warm-up
+        torch.cuda.synchronize()
+        e0.record(stream); info = ctx.packed_cholesky(work, n); e1.record(stream); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        logdet = ctx.packed_cholesky_logdet(work, n)
+        flop = n ** 3 / 3.0
+        line = {"nside": nside, "n": n, "group": group, "packed_gb": capi.packed_size(n) * 8e-9, "info": info, "packed_cholesky_ms": ms,
+                "tflops": flop / (ms * 1e-3) / 1e12, "fp64_peak_tflops": peak, "frac_of_peak": flop / (ms * 1e-3) / 1e12 / peak,
+                "cusolver_potrf_ms_on_unpacked": dense_ms, "logdet": logdet,
+                "logdet_rel_diff_vs_cusolver": (abs(logdet - want_logdet) / abs(want_logdet)) if dense_ms is not None else None}
+        print(json.dumps(line), flush=True)
     del d, work
     torch.cuda.empty_cache()
