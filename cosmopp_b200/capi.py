@@ -148,6 +148,7 @@ _SIGNATURES = {
     "cmg_chol_panel": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _vp, _i64]),
     "cmg_chol_syrk": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _i64, _i64, ctypes.c_int]),
     "cmg_set_cholesky_group": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "cmg_set_cholesky_lookahead": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_chol_logdet_runs": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), ctypes.POINTER(ctypes.c_double)]),
     "cmg_chol_solve_diag": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _i64, _vp, _i64]),
     "cmg_chol_solve_update": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _i64, _vp, _i64]),
@@ -537,6 +538,10 @@ class Context:
 
     def chol_solve_update(self, runs, k0, kb, n, d_rhs, n_rhs):
         self._check(self._L.cmg_chol_solve_update(self._h, ctypes.byref(runs), int(k0), int(kb), int(n), _p(d_rhs), int(n_rhs)))
+
+    def set_cholesky_lookahead(self, on):
+        """factorise the next group of blocks beside the trailing update (cmg_packed_cholesky; default on)"""
+        self._check(self._L.cmg_set_cholesky_lookahead(self._h, int(bool(on))))
 
     def packed_sum(self, d_c, d_f, d_n, n, d_out, c_stride=1):
         self._check(self._L.cmg_packed_sum(self._h, _p(d_c), int(c_stride), _p(d_f), _p(d_n), int(n), _p(d_out)))

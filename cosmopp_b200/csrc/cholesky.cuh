@@ -300,11 +300,13 @@ __host__ __device__ __forceinline__ long long chSyrkTilesBefore(long long b)
 // tiles are the column blocks [(colBegin - k1) / 64, (colEnd - k1) / 64) of the numbering above; columns from colEnd on are
 // not this run's (the tile is cut there like at the edge of the matrix).
 // stripOnly: only the first row tile (rows k1 .. k1 + CH_TILE) of every column block -- the catch-up update of the next block
-// of a group before it is factorised (tile t of a run = column block t + tile0).
+// of a group before it is factorised (tile t of a run = column block t + tile0).  shift: the launch updates the trailing matrix
+// from row and column k0 + kb + shift on (the update of a group is issued in pieces: the rows the NEXT group factorises first,
+// strip by strip, so that its factorisation can run beside the rest -- cmg_packed_cholesky).
 // The panel planes are allocated with CH_TILE + CH_TJ rows to spare: operand rows behind the edge of the matrix are read
 // (whatever they hold) and the entries computed from them never stored.
 __global__ void __launch_bounds__(CH_SYRK_THREADS, 2)
-cholSyrkKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, const long long* __restrict__ info,
+cholSyrkKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, long long shift, const long long* __restrict__ info,
                const double* __restrict__ panel, long long panelCol0, long long planeStride, int stripOnly)
 {
     if(*info != 0)
@@ -323,7 +325,7 @@ cholSyrkKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, cons
         ti = static_cast<int>(t - chSyrkTilesBefore(bj));
     }
     extern __shared__ double chSm[];                     // [2 stages][CH_TILE + CH_TJ][CH_SLD]
-    const long long k1 = k0 + kb;
+    const long long k1 = k0 + kb + shift;                // first row AND column of the part of the trailing matrix this launch updates
     const long long i0 = k1 + static_cast<long long>(ti) * CH_TILE, j0 = k1 + bj * CH_TJ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wi = warp >> 1, wj = warp & 1;             // warp tile: rows wi * 32, columns wj * 32

@@ -71,7 +71,10 @@ struct cmg_ctx
     double* dCholRed = nullptr;                  // log det / reductions of the packed solves
     double* dCholPanel = nullptr;                // dense panel planes of cmg_packed_cholesky (cholesky.cuh, cholSyrkKernel)
     size_t cholPanelDoubles = 0;
-    int cholGroup = 2;                           // blocks of 128 rows per trailing update (cmg_set_cholesky_group)
+    int cholGroup = 4;                           // blocks of 128 rows per trailing update (cmg_set_cholesky_group)
+    int cholLookAhead = 1;                       // the next group is factorised beside the trailing update (cmg_set_cholesky_lookahead)
+    cudaStream_t cholSide = nullptr;             // high-priority stream of the look-ahead
+    cudaEvent_t cholEvA = nullptr, cholEvF = nullptr;
     int likeMethod = 0;                          // cmg_like_create: 0 = this library's packed factorisation, 1 = cuSOLVER on the unpacked matrix
 };
 
@@ -477,6 +480,9 @@ void cmg_destroy(cmg_ctx* ctx)
     if(ctx->dCholInfo) cudaFree(ctx->dCholInfo);
     if(ctx->dCholRed) cudaFree(ctx->dCholRed);
     if(ctx->dCholPanel) cudaFree(ctx->dCholPanel);
+    if(ctx->cholSide) cudaStreamDestroy(ctx->cholSide);
+    if(ctx->cholEvA) cudaEventDestroy(ctx->cholEvA);
+    if(ctx->cholEvF) cudaEventDestroy(ctx->cholEvF);
     for(int k = 0; k < cmg_ctx::kAux; ++k)
     {
         if(ctx->aux[k]) { cudaStreamSynchronize(ctx->aux[k]); cudaStreamDestroy(ctx->aux[k]); }
@@ -1865,10 +1871,20 @@ cmg_status cmg_set_cholesky_group(cmg_ctx* ctx, int blocks)
     return CMG_OK;
 }
 
+cmg_status cmg_set_cholesky_lookahead(cmg_ctx* ctx, int on)
+{
+    if(!ctx) return CMG_EINVAL;
+    ctx->cholLookAhead = on ? 1 : 0;
+    return CMG_OK;
+}
+
 // Right-looking in GROUPS of S blocks of 128 rows: inside a group every block is factorised, its 128 rows solved for all columns
 // behind it (packed in place + dense plane s), and only the NEXT block's 128 rows are brought up to date (strip update, K = 128 s);
 // the trailing matrix behind the group is then updated ONCE with all 128 S rows -- it is read and written n / (128 S) times
 // instead of n / 128, and a tile's loads of C, its barriers and its stores are amortised over S times the DMMAs.
+// Look-ahead: that update is issued in pieces -- first the S strips of rows the next group will factorise, then the rest -- and
+// the next group's chain of small kernels (diagonal block, panel, strip, ...: latency-bound, a fraction of the SMs) runs on a
+// high-priority side stream BESIDE the rest of the update; its rows of U go to the second set of planes.
 cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* info)
 {
     if(!ctx) return CMG_EINVAL;
@@ -1878,54 +1894,85 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
     if(s != CMG_OK) return s;
     if((s = cholStepAttributes(ctx)) != CMG_OK) return s;
     const int S = ctx->cholGroup;
+    const int64_t groupRows = static_cast<int64_t>(S) * cmg::CH_NB;
+    const bool ahead = ctx->cholLookAhead && n > 2 * groupRows;
     const int64_t planeStride = (n + CH_PLANE_SLACK) * cmg::CH_NB;
-    if(ctx->cholPanelDoubles < static_cast<size_t>(S * planeStride))
+    const int64_t bufStride = S * planeStride;                      // one set of planes; look-ahead alternates between two
+    const size_t need = static_cast<size_t>(bufStride) * (ahead ? 2 : 1);
+    if(ctx->cholPanelDoubles < need)
     {
         if(ctx->dCholPanel) CMG_CUDA(ctx, cudaFree(ctx->dCholPanel));
         ctx->dCholPanel = nullptr;
         ctx->cholPanelDoubles = 0;
-        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholPanel, sizeof(double) * S * planeStride));
-        ctx->cholPanelDoubles = static_cast<size_t>(S * planeStride);
-        CMG_CUDA(ctx, cudaMemsetAsync(ctx->dCholPanel, 0, sizeof(double) * S * planeStride, ctx->stream));   // the slack rows are read
+        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholPanel, sizeof(double) * need));
+        ctx->cholPanelDoubles = need;
+        CMG_CUDA(ctx, cudaMemsetAsync(ctx->dCholPanel, 0, sizeof(double) * need, ctx->stream));   // the slack rows are read
+    }
+    if(ahead && !ctx->cholSide)
+    {
+        int least = 0, greatest = 0;
+        CMG_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CMG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->cholSide, cudaStreamNonBlocking, greatest));
+        CMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->cholEvA, cudaEventDisableTiming));
+        CMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->cholEvF, cudaEventDisableTiming));
     }
     CMG_CUDA(ctx, cudaMemsetAsync(ctx->dCholInfo, 0, sizeof(long long), ctx->stream));
     KernelTimer timer(ctx);
-    bool done = false;
-    for(int64_t kBase = 0; kBase < n && !done; kBase += static_cast<int64_t>(S) * cmg::CH_NB)
+
+    auto syrk = [&](cudaStream_t st, int64_t kBase, int kb, int64_t shift, const double* planes, bool strip)
+    {
+        const int64_t k1 = kBase + kb + shift;
+        if(k1 >= n) return;
+        cmg::CholRuns runs = cholWholeRun(dA, k1, n);
+        const int64_t colBlocks = (n - k1 + cmg::CH_TJ - 1) / cmg::CH_TJ;           // 64-column blocks; block b meets the row tiles 0 .. b / 2
+        runs.first[1] = strip ? colBlocks : cmg::chSyrkTilesBefore(colBlocks);
+        cmg::cholSyrkKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, st>>>(
+            runs, kBase, kb, shift, ctx->dCholInfo, planes, kBase, planeStride, strip ? 1 : 0);
+        ctx->launches += 1;
+    };
+    // the blocks of the group starting at kBase: true when the last block of the matrix has been factorised
+    auto chain = [&](cudaStream_t st, int64_t kBase, double* planes) -> bool
     {
         for(int sub = 0; sub < S; ++sub)
         {
             const int64_t k0 = kBase + static_cast<int64_t>(sub) * cmg::CH_NB;
-            if(k0 >= n) { done = true; break; }
+            if(k0 >= n) return true;
             const int kb = static_cast<int>(std::min<int64_t>(cmg::CH_NB, n - k0));
-            if(sub > 0)
-            {
-                // rows k0 .. k0 + 128 of every column from k0 on catch up with the sub blocks already solved
-                cmg::CholRuns runs = cholWholeRun(dA, k0, n);
-                runs.first[1] = (n - k0 + cmg::CH_TJ - 1) / cmg::CH_TJ;
-                cmg::cholSyrkKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(
-                    runs, kBase, sub * cmg::CH_NB, ctx->dCholInfo, ctx->dCholPanel, kBase, planeStride, 1);
-                ctx->launches += 1;
-            }
-            cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, ctx->stream>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr);
+            if(sub > 0)                          // rows k0 .. k0 + 128 of every column from k0 on catch up with the sub blocks already solved
+                syrk(st, kBase, sub * cmg::CH_NB, 0, planes, true);
+            cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, st>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr);
             ctx->launches += 1;
             const int64_t rem = n - k0 - kb;
-            if(rem <= 0) { done = true; break; }
+            if(rem <= 0) return true;
             // (kb == CH_NB from here on: a short block can only be the last one)
             cmg::CholRuns runs = cholWholeRun(dA, k0 + kb, n);
             runs.first[1] = (rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS;
-            cmg::cholPanelKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_PANEL_COLS, CH_PANEL_SMEM, ctx->stream>>>(
-                runs, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr, ctx->dCholPanel + sub * planeStride, kBase);
+            cmg::cholPanelKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_PANEL_COLS, CH_PANEL_SMEM, st>>>(
+                runs, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr, planes + sub * planeStride, kBase);
             ctx->launches += 1;
         }
-        const int64_t kEnd = kBase + static_cast<int64_t>(S) * cmg::CH_NB;
-        if(done || kEnd >= n)
-            break;
-        cmg::CholRuns runs = cholWholeRun(dA, kEnd, n);
-        runs.first[1] = cmg::chSyrkTilesBefore((n - kEnd + cmg::CH_TJ - 1) / cmg::CH_TJ);    // 64-column blocks; block b meets the row tiles 0 .. b / 2
-        cmg::cholSyrkKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(
-            runs, kBase, S * cmg::CH_NB, ctx->dCholInfo, ctx->dCholPanel, kBase, planeStride, 0);
-        ctx->launches += 1;
+        return kBase + groupRows >= n;
+    };
+
+    bool done = chain(ctx->stream, 0, ctx->dCholPanel);
+    for(int64_t g = 0; !done; ++g)
+    {
+        const int64_t kBase = g * groupRows;
+        double* planes = ctx->dCholPanel + (ahead ? (g & 1) * bufStride : 0);
+        if(!ahead)
+        {
+            syrk(ctx->stream, kBase, S * cmg::CH_NB, 0, planes, false);
+            done = chain(ctx->stream, kBase + groupRows, planes);
+            continue;
+        }
+        for(int r = 0; r < S; ++r)               // the rows of the next group, strip by strip
+            syrk(ctx->stream, kBase, S * cmg::CH_NB, static_cast<int64_t>(r) * cmg::CH_NB, planes, true);
+        CMG_CUDA(ctx, cudaEventRecord(ctx->cholEvA, ctx->stream));
+        CMG_CUDA(ctx, cudaStreamWaitEvent(ctx->cholSide, ctx->cholEvA, 0));
+        done = chain(ctx->cholSide, kBase + groupRows, ctx->dCholPanel + ((g + 1) & 1) * bufStride);
+        CMG_CUDA(ctx, cudaEventRecord(ctx->cholEvF, ctx->cholSide));
+        syrk(ctx->stream, kBase, S * cmg::CH_NB, groupRows, planes, false);          // the rest, beside the next group's chain
+        CMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->cholEvF, 0));
     }
     CMG_CUDA(ctx, cudaGetLastError());
     if((s = timer.finish()) != CMG_OK) return s;
@@ -2009,7 +2056,7 @@ cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, in
     const int64_t tiles = cholClipRuns(runs, k0 + kb, k0 + kb, stripOnly ? -1 : 0, &clipped);
     if(tiles == 0) return CMG_OK;
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
-    cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(clipped, k0, kb, ctx->dCholInfo, dPanel, panelCol0,
+    cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(clipped, k0, kb, 0, ctx->dCholInfo, dPanel, panelCol0,
                                                                                                          planeStride, stripOnly ? 1 : 0);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

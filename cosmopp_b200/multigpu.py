@@ -395,7 +395,7 @@ class ShardedCholesky:
     serialise the host with the device every time.  `ukk` / `panel`: torch buffers to use (ranks emulated on ONE GPU share
     them -- tests/test_gpu_cholesky.py); allocated when None."""
 
-    def __init__(self, ctx, n, all_runs, rank, run_ptrs, comm=None, ukk=None, panel=None, group=2):
+    def __init__(self, ctx, n, all_runs, rank, run_ptrs, comm=None, ukk=None, panel=None, group=4):
         import torch
         self.ctx, self.n, self.rank, self.world = ctx, int(n), rank, len(all_runs)
         self.owners = chol_block_owners(self.n, all_runs)

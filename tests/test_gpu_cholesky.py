@@ -116,18 +116,22 @@ class _NoComm:
         pass
 
 
+@pytest.mark.parametrize("lookahead", [True, False])
 @pytest.mark.parametrize("group", [1, 2, 3, 4])
-@pytest.mark.parametrize("n", [128, 129, 500, 1153])
-def test_packed_cholesky_groups_of_blocks(gpu_ctx, n, group):
-    """cmg_set_cholesky_group: every group size gives the same factor (strip updates + one trailing update per group)"""
+@pytest.mark.parametrize("n", [128, 129, 500, 1153, 2100])
+def test_packed_cholesky_groups_of_blocks(gpu_ctx, n, group, lookahead):
+    """cmg_set_cholesky_group / cmg_set_cholesky_lookahead: every group size gives the same factor (strip updates + one trailing
+    update per group), with the next group factorised beside the trailing update or after it"""
     import torch
     A = random_spd(n, 500 + n)
     d = torch.from_numpy(pack_upper(A)).cuda()
     gpu_ctx.set_cholesky_group(group)
+    gpu_ctx.set_cholesky_lookahead(lookahead)
     try:
         assert gpu_ctx.packed_cholesky(d, n) == 0
     finally:
-        gpu_ctx.set_cholesky_group(2)
+        gpu_ctx.set_cholesky_lookahead(True)
+        gpu_ctx.set_cholesky_group(4)
     want = np.linalg.cholesky(A).T
     assert np.abs(unpack_upper(d.cpu().numpy(), n) - want).max() <= 1e-12 * np.abs(want).max()
 

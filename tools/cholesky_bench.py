@@ -13,7 +13,8 @@ ctx = cb.Context(0)
 stream = torch.cuda.current_stream()
 ctx.set_stream(stream.cuda_stream)
 peak = ctx.measure_fp64_peak()
-groups = [int(g) for a in sys.argv[1:] if a.startswith("--groups=") for g in a.split("=")[1].split(",")] or [2]
+groups = [int(g) for a in sys.argv[1:] if a.startswith("--groups=") for g in a.split("=")[1].split(",")] or [4]
+ctx.set_cholesky_lookahead("--no-lookahead" not in sys.argv)
 for nside in [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [16, 32]:
     lmax = 3 * nside
     ctx.set_pixels(nside)
@@ -51,7 +52,7 @@ for nside in [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [16, 32
         ms = e0.elapsed_time(e1)
         logdet = ctx.packed_cholesky_logdet(work, n)
         flop = n ** 3 / 3.0
-        line = {"nside": nside, "n": n, "group": group, "packed_gb": capi.packed_size(n) * 8e-9, "info": info, "packed_cholesky_ms": ms,
+        line = {"nside": nside, "n": n, "group": group, "lookahead": "--no-lookahead" not in sys.argv, "packed_gb": capi.packed_size(n) * 8e-9, "info": info, "packed_cholesky_ms": ms,
                 "tflops": flop / (ms * 1e-3) / 1e12, "fp64_peak_tflops": peak, "frac_of_peak": flop / (ms * 1e-3) / 1e12 / peak,
                 "cusolver_potrf_ms_on_unpacked": dense_ms, "logdet": logdet,
                 "logdet_rel_diff_vs_cusolver": (abs(logdet - want_logdet) / abs(want_logdet)) if dense_ms is not None else None}

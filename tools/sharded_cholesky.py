@@ -34,7 +34,7 @@ def main():
     peak = ctx.measure_fp64_peak()
     whole_check = "--whole" in sys.argv
     nsides = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [16]
-    group = ([int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--group=")] or [2])[0]
+    group = ([int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--group=")] or [4])[0]
 
     def timed(fn):
         """ms on the device, max over ranks; barriers on both sides"""
