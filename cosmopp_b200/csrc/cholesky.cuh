@@ -25,7 +25,7 @@ constexpr int CH_LD = CH_NB + 1;           // leading dimension of the diagonal 
 constexpr int CH_TILE = 128;               // syrk: tile edge
 constexpr int CH_KC = 32;                  // syrk: k-chunk staged in shared memory
 constexpr int CH_SLD = CH_KC;              // its leading dimension: no padding, the 16-byte chunks of a row are XOR-swizzled (chSwz)
-constexpr int CH_PANEL_COLS = 128;         // panel solve: columns (threads) per CTA
+constexpr int CH_PANEL_COLS = 64;          // panel solve: columns per CTA
 
 __host__ __device__ __forceinline__ long long chOff(long long col) { return col * (col + 1) / 2; }
 
@@ -52,24 +52,49 @@ __device__ __forceinline__ int chRunOf(const CholRuns& runs, long long cta)
 }
 
 // ------------------------------------------------------------------------------------------------ diagonal block
-// A[k0 .. k0 + kb, k0 .. k0 + kb] -> U_kk, in place: one CTA, the block in shared memory (S(r, c) at chS[c * CH_LD + r], r <= c),
-// factorised in sub-blocks of CH_DB = 16 rows:
-//   (a) warp 0 factorises the 16 x 16 diagonal sub-block (a lane per column, 16 dependent steps);
-//   (b) a thread per column behind it solves its 16 rows against that triangle (registers);
-//   (c) all threads apply the rank-16 update to the rest: thread (column c, row group g) keeps its 16 row-block entries in
-//       registers and walks its rows r = g, g + G, ... <= c -- 16 FMAs per entry read and written.
+__device__ __forceinline__ void chDmma(double& c0, double& c1, const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void chCpAsync8(double* dstShared, const double* src)
+{
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(dstShared));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void chCpAsync16(double* dstShared, const double* src)
+{
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(dstShared));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// A[k0 .. k0 + kb, k0 .. k0 + kb] -> U_kk, in place: one CTA, the block in shared memory (S(r, c) at chS[c * CH_LD + r], r <= c;
+// fetched with cp.async: every load of the block in flight at once), factorised in sub-blocks of CH_DB = 16 rows:
+//   (a) 256 threads hold one element of the 16 x 16 diagonal sub-block each.  Pivot j: the threads of row j publish the row as it
+//       stands (double-buffered, ONE 256-thread barrier per pivot); everyone updates its element with S(j, r) S(j, c) / S(j, j);
+//       the row's own threads turn it into U(j, .) off the critical path (reciprocal square root + a Newton step: a double sqrt
+//       followed by a division costs ~250 cycles).
+//   (b) a thread per column behind it solves its 16 rows against that triangle (registers), multiplying by the reciprocal pivots;
+//       the result also goes to chP[column][16], the operand layout of (c).
+//   (c) the rank-16 update of the rest on the FP64 tensor path: 8 x 8 tiles of the upper triangle dealt to the 16 warps, K = 16.
+// U_kk also leaves packed (entry (r <= c) at ukkOut[c (c + 1) / 2 + r]) with the reciprocals of its diagonal behind it: the panel
+// kernel -- and, sharded, every other rank -- takes it from there in one stream of 16-byte copies.
 // *info = k0 + j + 1 when pivot j is not positive (LAPACK's convention; the first failing block wins).
+// (History: one step per row with the row in shared memory 0.169 ms; two barriers, sqrt and division per pivot, rank-16 update
+// with one shared-memory load per FMA: 0.108 ms; reciprocal square roots: 0.087 ms.)
 constexpr int CH_DB = 16;
+constexpr int CH_DP_LD = CH_DB + 4;        // chP: 16 k-values of a column, leading dimension 20 (conflict-free DMMA fragments)
+constexpr int CH_DIAG_SMEM_DOUBLES = CH_NB * CH_LD + CH_NB * CH_DP_LD;
 
 __global__ void __launch_bounds__(512)
-cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restrict__ info, double* __restrict__ invDiag,
-               double* __restrict__ ukkOut)
+cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restrict__ info, double* __restrict__ ukkOut)
 {
-    extern __shared__ double chS[];                      // [kb][CH_LD]
+    extern __shared__ double chS[];                      // [CH_NB][CH_LD], then chP [CH_NB][CH_DP_LD]
+    double* chP = chS + CH_NB * CH_LD;
     __shared__ int failed;
-    __shared__ double sPivot, sRow[CH_DB], sInv[CH_NB];   // sInv[r] = 1 / U(r, r): the solves multiply, a double division is ~300 cycles
-    const int tid = threadIdx.x;
-    const int c = tid % CH_NB, g = tid / CH_NB, G = blockDim.x / CH_NB;
+    __shared__ double sRow[2][CH_DB], sInv[CH_NB];       // sInv[r] = 1 / U(r, r): the solves multiply
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if(*info != 0)
         return;                                          // an earlier block already failed
     if(tid == 0)
@@ -78,43 +103,44 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
     {
         const int cc = idx / kb, r = idx - cc * kb;
         if(r <= cc)
-            chS[cc * CH_LD + r] = A[chOff(k0 + cc) + k0 + r];
+            chCpAsync8(chS + cc * CH_LD + r, A + chOff(k0 + cc) + k0 + r);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     for(int jb = 0; jb < kb; jb += CH_DB)
     {
         const int wb = min(CH_DB, kb - jb);
         if(tid < CH_DB * CH_DB)
         {
-            // (a) thread (r, c) keeps element S(jb + r, jb + c) of the sub-block in a register; step j: the pivot and then row j
-            // go through shared memory to everyone, every element of the remaining triangle is updated at once -- 16 steps of
-            // two (256-thread) barriers instead of a dependent walk through shared memory per lane
             const int r = tid >> 4, cc = tid & (CH_DB - 1);
             const bool mine = r <= cc && cc < wb;
             double v = mine ? chS[(jb + cc) * CH_LD + jb + r] : 0.0;
             for(int j = 0; j < wb; ++j)
             {
-                if(r == j && cc == j)
-                    sPivot = v;
+                double* row = sRow[j & 1];
+                if(r == j && cc >= j)
+                    row[cc] = v;                         // row j as it stands (not yet divided by the pivot's root)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                const double d = sPivot;
+                const double d = row[j];
                 if(!(d > 0.0))
                 {
                     if(tid == 0)
                         failed = jb + j + 1;
                     break;                               // the same in all 256 threads
                 }
-                if(r == j && cc >= j && cc < wb)
-                {
-                    const double root = sqrt(d);
-                    v = cc == j ? root : v / root;
-                    sRow[cc] = v;
-                    if(cc == j)
-                        sInv[jb + j] = 1.0 / root;
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if(mine && r > j)
-                    v = fma(-sRow[r], sRow[cc], v);
+                    v = fma(-(row[r] * __drcp_rn(d)), row[cc], v);
+                else if(mine && r == j)
+                {
+                    double inv = rsqrt(d);
+                    double root = d * inv;
+                    root = fma(fma(-root, root, d), 0.5 * inv, root);
+                    inv = fma(fma(-root, inv, 1.0), inv, inv);
+                    v = cc == j ? root : v * inv;
+                    if(cc == j)
+                        sInv[jb + j] = inv;
+                }
             }
             if(mine)
                 chS[(jb + cc) * CH_LD + jb + r] = v;
@@ -126,40 +152,51 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
                 *info = k0 + failed;
             return;
         }
-        // (b) rows jb .. jb + wb of the columns behind the sub-block: x = U_bb^-T b
-        if(tid < kb && tid >= jb + wb)
+        const int first = jb + wb;
+        if(first >= kb)
+            break;
+        // (b) rows jb .. jb + wb of the columns behind the sub-block: x = U_bb^-T b   (wb == CH_DB here: a short sub-block is the last)
+        if(tid < kb && tid >= first)
         {
             double x[CH_DB];
 #pragma unroll
             for(int i = 0; i < CH_DB; ++i)
-            {
-                if(i < wb)
-                {
-                    double acc = chS[tid * CH_LD + jb + i];
+                x[i] = chS[tid * CH_LD + jb + i];
 #pragma unroll
-                    for(int q = 0; q < i; ++q)
-                        acc = fma(-chS[(jb + i) * CH_LD + jb + q], x[q], acc);
-                    x[i] = acc * sInv[jb + i];
-                    chS[tid * CH_LD + jb + i] = x[i];
-                }
+            for(int i = 0; i < CH_DB; ++i)
+            {
+                x[i] *= sInv[jb + i];                    // every later row is updated at once: the chain is 16 x (multiply + FMA) long
+#pragma unroll
+                for(int i2 = i + 1; i2 < CH_DB; ++i2)
+                    x[i2] = fma(-chS[(jb + i2) * CH_LD + jb + i], x[i], x[i2]);
+            }
+#pragma unroll
+            for(int i = 0; i < CH_DB; ++i)
+            {
+                chS[tid * CH_LD + jb + i] = x[i];
+                chP[tid * CH_DP_LD + i] = x[i];
             }
         }
         __syncthreads();
-        // (c) rank-wb update of everything behind the sub-block
-        if(c < kb && c >= jb + wb)
+        // (c) S(r, c) -= sum_k U(jb + k, r) U(jb + k, c) for first <= r <= c < kb: 8 x 8 tiles (tr <= tc) over the warps
         {
-            double uc[CH_DB];
-#pragma unroll
-            for(int i = 0; i < CH_DB; ++i)
-                uc[i] = i < wb ? chS[c * CH_LD + jb + i] : 0.0;
-            const int first = jb + wb;
-            for(int r = first + ((g - first) % G + G) % G; r <= c; r += G)
+            const int nT = (kb - first + 7) >> 3;
+            const int g = lane >> 2, t = lane & 3;
+            for(int p = warp; p < nT * (nT + 1) / 2; p += 16)
             {
-                double acc = chS[c * CH_LD + r];
+                int tc = static_cast<int>((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
+                while((tc + 1) * (tc + 2) / 2 <= p) ++tc;
+                while(tc * (tc + 1) / 2 > p) --tc;
+                const int tr = p - tc * (tc + 1) / 2;
+                const int rA = min(first + tr * 8 + g, CH_NB - 1), cB = min(first + tc * 8 + g, CH_NB - 1);   // fragment rows (clamped: masked at the store)
+                const int r = first + tr * 8 + g, c = first + tc * 8 + 2 * t;
+                const bool ok0 = r <= c && c < kb, ok1 = r <= c + 1 && c + 1 < kb;
+                double c0 = ok0 ? chS[c * CH_LD + r] : 0.0, c1 = ok1 ? chS[(c + 1) * CH_LD + r] : 0.0;
 #pragma unroll
-                for(int i = 0; i < CH_DB; ++i)
-                    acc = fma(-chS[r * CH_LD + jb + i], uc[i], acc);         // entries i >= wb of a short last sub-block meet uc = 0
-                chS[c * CH_LD + r] = acc;
+                for(int kk = 0; kk < CH_DB; kk += 4)
+                    chDmma(c0, c1, -chP[rA * CH_DP_LD + kk + t], chP[cB * CH_DP_LD + kk + t]);
+                if(ok0) chS[c * CH_LD + r] = c0;
+                if(ok1) chS[(c + 1) * CH_LD + r] = c1;
             }
         }
         __syncthreads();
@@ -168,99 +205,154 @@ cholDiagKernel(double* __restrict__ A, long long k0, int kb, long long* __restri
     {
         const int cc = idx / kb, r = idx - cc * kb;
         if(r <= cc)
-            A[chOff(k0 + cc) + k0 + r] = chS[cc * CH_LD + r];
+        {
+            const double v = chS[cc * CH_LD + r];
+            A[chOff(k0 + cc) + k0 + r] = v;
+            ukkOut[cc * (cc + 1) / 2 + r] = v;
+        }
     }
     if(tid < kb)
-        invDiag[tid] = sInv[tid];
-    if(ukkOut)                                           // packed U_kk for the other ranks of a sharded factorisation
-        for(int idx = tid; idx < kb * kb; idx += blockDim.x)
-        {
-            const int cc = idx / kb, r = idx - cc * kb;
-            if(r <= cc)
-                ukkOut[cc * (cc + 1) / 2 + r] = chS[cc * CH_LD + r];
-        }
+        ukkOut[kb * (kb + 1) / 2 + tid] = sInv[tid];
 }
 
 // ------------------------------------------------------------------------------------------------ panel
-// Column j >= k1 = k0 + kb: x = U_kk^-T b with b = A[k0 .. k0 + kb, j] (one contiguous run of the packed column), in place; one
-// column per thread.  Forward substitution in blocks of 16 rows: the contributions of the rows already solved are 16 independent
-// FMA chains per thread, then the 16 x 16 triangle in registers.  U_kk (packed, 66 KB), the reciprocals of its diagonal and the
-// solved x (128 KB) all live in shared memory: every operand of the inner loop is a shared-memory read, U at a warp-uniform
-// address.  (First version: one dependent chain per row, 0.4 - 0.8 ms per step; second: U through L1 and divisions,
-// 0.23 ms, stall long_scoreboard 9 cycles per instruction -- profiles/r2_chol_panel_v2_metrics.txt.)
+// Columns j >= k1 = k0 + kb: X = U_kk^-T B with B = A[k0 .. k0 + kb, j] (one contiguous run of each packed column), in place, and
+// also into the dense panel plane the trailing update reads.  A CTA takes 64 columns, a warp 16 of them -- and only its own: the
+// warps never wait for each other after the load.  Forward substitution in blocks of 16 rows; for block rb
+//   C = B[rb .. rb + 16] - U[0 .. rb, rb .. rb + 16]^T X[0 .. rb]      16 x rb x 16 per warp on the FP64 tensor path
+//                                                                      (mma.sync.m8n8k4.f64: the accumulators start as B, the
+//                                                                      U fragments enter negated)
+//   X[rb .. rb + 16] = T^-T C, T the 16 x 16 triangle of U_kk           a lane per column, 16 values in registers, U at a
+//                                                                      warp-uniform shared-memory address, reciprocal pivots
+// X lives in shared memory column by column (leading dimension 132: the B fragment -- k = lane % 4 along a column, column
+// = lane / 4 -- is then conflict-free, and so are the loads and stores of whole columns); U_kk packed (66 KB) and the
+// reciprocals of its diagonal next to it.
+// (History: one dependent chain per row, 0.4 - 0.8 ms per step; U through L1 and divisions, 0.23 ms, long-scoreboard stalls
+// -- profiles/r2_chol_panel_v2_metrics.txt; a thread per column with 16 FMA chains fed from shared memory, 0.108 ms per wave of
+// 128 columns per SM, bound by one shared-memory load per FMA.)
 constexpr int CH_PB = 16;
-constexpr int CH_PANEL_SMEM_DOUBLES = CH_NB * CH_PANEL_COLS + CH_NB * (CH_NB + 1) / 2 + CH_NB;
+constexpr int CH_PANEL_THREADS = 128;
+constexpr int CH_PX_LD = CH_NB + 4;
+constexpr int CH_PANEL_SMEM_DOUBLES = CH_PANEL_COLS * CH_PX_LD + CH_NB * (CH_NB + 1) / 2 + CH_NB;
+constexpr int CH_UKK_DOUBLES = CH_NB * (CH_NB + 1) / 2 + CH_NB;      // packed U_kk + reciprocal pivots
 
-__global__ void __launch_bounds__(CH_PANEL_COLS)
+__global__ void __launch_bounds__(CH_PANEL_THREADS)
 cholPanelKernel(const __grid_constant__ CholRuns runs, long long k0, int kb, const long long* __restrict__ info,
-                const double* __restrict__ invDiag, const double* __restrict__ ukk, double* __restrict__ panel, long long panelCol0)
+                const double* __restrict__ ukk, double* __restrict__ panel, long long panelCol0)
 {
-    extern __shared__ double chX[];                      // [kb][CH_PANEL_COLS], then U_kk packed, then 1 / diagonal
+    extern __shared__ double chX[];                      // [CH_PANEL_COLS][CH_PX_LD], then U_kk packed + 1 / diagonal (as cholDiagKernel left them)
     if(*info != 0)
         return;
-    double* sU = chX + CH_NB * CH_PANEL_COLS;            // U(s, r) at sU[r (r + 1) / 2 + s]
-    double* sInv = sU + CH_NB * (CH_NB + 1) / 2;
-    const int tid = threadIdx.x;
+    double* sU = chX + CH_PANEL_COLS * CH_PX_LD;         // U(s, r) at sU[r (r + 1) / 2 + s]
+    const int nU = kb * (kb + 1) / 2;
+    double* sInv = sU + nU;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int run = chRunOf(runs, blockIdx.x);
     double* const A = runs.base[run];
-    if(ukk)                                              // sharded: the owner's U_kk arrives packed (the block is not in this rank's columns)
-        for(int idx = tid; idx < kb * (kb + 1) / 2; idx += CH_PANEL_COLS)
-            sU[idx] = ukk[idx];
-    else
-        for(int r = 0; r < kb; ++r)                      // column r of the block: r + 1 contiguous doubles
-            if(tid <= r)
-                sU[r * (r + 1) / 2 + tid] = A[chOff(k0 + r) + k0 + tid];
-    if(tid < kb)
-        sInv[tid] = invDiag[tid];
-    __syncthreads();
-    const long long j = runs.colBegin[run] + (static_cast<long long>(blockIdx.x) - runs.first[run]) * CH_PANEL_COLS + tid;
-    if(j >= runs.colEnd[run])
-        return;
-    double* col = A + chOff(j) + k0;
-    // kb is a multiple of CH_PB here: only the LAST block of a matrix can be short, and nothing lies behind it
-    for(int rb = 0; rb < kb; rb += CH_PB)
+    // everything this CTA reads, in flight at once: U_kk and the reciprocal pivots (one contiguous piece, 16 bytes a copy) ...
+    for(int idx = 2 * tid; idx < nU + kb; idx += 2 * CH_PANEL_THREADS)       // kb = CH_NB here: an even count
+        chCpAsync16(sU + idx, ukk + idx);
+    const long long j0 = runs.colBegin[run] + (static_cast<long long>(blockIdx.x) - runs.first[run]) * CH_PANEL_COLS;
+    const long long colEnd = runs.colEnd[run];
+    constexpr int WCOLS = CH_PANEL_COLS / (CH_PANEL_THREADS / 32);      // 16 columns per warp
+    const int col0 = warp * WCOLS;
+    // ... and the kb rows of the warp's own 16 columns (a packed column starts at any multiple of 8 bytes)
+    // kb is a multiple of CH_PB here (CH_NB in fact): only the LAST block of a matrix can be short, and nothing lies behind it
+#pragma unroll 4
+    for(int c = 0; c < WCOLS; ++c)
     {
-        double acc[CH_PB];
-        const double* ucol[CH_PB];                       // U(0 .., rb + i): column rb + i of the diagonal block
+        const long long j = j0 + col0 + c;
+        const double* src = A + chOff(j) + k0;
 #pragma unroll
-        for(int i = 0; i < CH_PB; ++i)
+        for(int q = 0; q < CH_NB / 32; ++q)
         {
-            acc[i] = col[rb + i];
-            ucol[i] = sU + (rb + i) * (rb + i + 1) / 2;
-        }
-        for(int s = 0; s < rb; ++s)
-        {
-            const double xs = chX[s * CH_PANEL_COLS + tid];
-#pragma unroll
-            for(int i = 0; i < CH_PB; ++i)
-                acc[i] = fma(-ucol[i][s], xs, acc[i]);
-        }
-#pragma unroll
-        for(int i = 0; i < CH_PB; ++i)
-        {
-            const double x = acc[i] * sInv[rb + i];
-            chX[(rb + i) * CH_PANEL_COLS + tid] = x;
-#pragma unroll
-            for(int i2 = i + 1; i2 < CH_PB; ++i2)
-                acc[i2] = fma(-ucol[i2][rb + i], x, acc[i2]);
+            if(j < colEnd && q * 32 + lane < kb)
+                chCpAsync8(chX + (col0 + c) * CH_PX_LD + q * 32 + lane, src + q * 32 + lane);
+            else
+                chX[(col0 + c) * CH_PX_LD + q * 32 + lane] = 0.0;
         }
     }
-    for(int r = 0; r < kb; ++r)
-        col[r] = chX[r * CH_PANEL_COLS + tid];
-    if(panel)                                            // sharded: the same rows into the dense panel every rank will hold
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                     // U_kk and the reciprocals are in place (the columns are the warp's own)
+
+    const int g = lane >> 2, t = lane & 3;
+    for(int rb = 0; rb < kb; rb += CH_PB)
     {
-        double* p = panel + (j - panelCol0) * CH_NB;
-        for(int r = 0; r < kb; ++r)
-            p[r] = chX[r * CH_PANEL_COLS + tid];
+        if(rb > 0)
+        {
+            double acc[2][2][2];
+#pragma unroll
+            for(int m = 0; m < 2; ++m)
+#pragma unroll
+                for(int nn = 0; nn < 2; ++nn)
+#pragma unroll
+                    for(int e = 0; e < 2; ++e)
+                        acc[m][nn][e] = chX[(col0 + nn * 8 + 2 * t + e) * CH_PX_LD + rb + m * 8 + g];
+            const double* uA0 = sU + (rb + g) * (rb + g + 1) / 2 + t;                  // U(s + t, rb + g)
+            const double* uA1 = sU + (rb + 8 + g) * (rb + 8 + g + 1) / 2 + t;          // U(s + t, rb + 8 + g)
+            const double* xB0 = chX + (col0 + g) * CH_PX_LD + t;                       // X(s + t, col0 + g)
+            const double* xB1 = xB0 + 8 * CH_PX_LD;
+#pragma unroll 4
+            for(int s0 = 0; s0 < rb; s0 += 4)
+            {
+                const double a0 = -uA0[s0], a1 = -uA1[s0], b0 = xB0[s0], b1 = xB1[s0];
+                chDmma(acc[0][0][0], acc[0][0][1], a0, b0);
+                chDmma(acc[0][1][0], acc[0][1][1], a0, b1);
+                chDmma(acc[1][0][0], acc[1][0][1], a1, b0);
+                chDmma(acc[1][1][0], acc[1][1][1], a1, b1);
+            }
+#pragma unroll
+            for(int m = 0; m < 2; ++m)
+#pragma unroll
+                for(int nn = 0; nn < 2; ++nn)
+#pragma unroll
+                    for(int e = 0; e < 2; ++e)
+                        chX[(col0 + nn * 8 + 2 * t + e) * CH_PX_LD + rb + m * 8 + g] = acc[m][nn][e];
+            __syncwarp();
+        }
+        if(lane < WCOLS)
+        {
+            double* xc = chX + (col0 + lane) * CH_PX_LD + rb;
+            double x[CH_PB];
+#pragma unroll
+            for(int i = 0; i < CH_PB; ++i)
+                x[i] = xc[i];
+#pragma unroll
+            for(int i = 0; i < CH_PB; ++i)
+            {
+                x[i] *= sInv[rb + i];
+#pragma unroll
+                for(int i2 = i + 1; i2 < CH_PB; ++i2)
+                    x[i2] = fma(-sU[(rb + i2) * (rb + i2 + 1) / 2 + rb + i], x[i], x[i2]);
+            }
+#pragma unroll
+            for(int i = 0; i < CH_PB; ++i)
+                xc[i] = x[i];
+        }
+        __syncwarp();
+    }
+#pragma unroll 2
+    for(int c = 0; c < WCOLS; ++c)
+    {
+        const long long j = j0 + col0 + c;
+        if(j >= colEnd)
+            break;
+        double* dst = A + chOff(j) + k0;
+        double* p = panel ? panel + (j - panelCol0) * CH_NB : nullptr;
+#pragma unroll
+        for(int q = 0; q < CH_NB / 32; ++q)
+            if(q * 32 + lane < kb)
+            {
+                const double v = chX[(col0 + c) * CH_PX_LD + q * 32 + lane];
+                dst[q * 32 + lane] = v;
+                if(p)
+                    p[q * 32 + lane] = v;
+            }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ trailing update
-__device__ __forceinline__ void chDmma(double& c0, double& c1, const double a, const double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
 // Tile of the trailing matrix, 128 rows (i) x 64 columns (j): C[i][j] -= sum_{r < kb} P[r][i] P[r][j], P = the kb rows of U just
 // solved (kb = CH_NB, or a whole group of blocks: up to CH_MAX_GROUP * CH_NB).  8 warps as 4 x 2: a warp owns 32 rows x 32 columns
 // = 4 x 4 m8n8 accumulator tiles, which START as the C entries themselves (loaded while the first operand chunk is in flight);
@@ -278,12 +370,6 @@ constexpr int CH_SYRK_THREADS = 256;
 // 16-byte load is served per quarter warp (rows g = 2 q, 2 q + 1, four chunks each): chunk c of an odd row sits at c ^ 4, which
 // puts the two rows into different halves of the 128-byte bank window.  Half the shared-memory instructions of the 8-byte
 // version with leading dimension 36 (MIO throttle / short scoreboard: profiles/r2_syrk_v2_metrics.txt, then _v3_).
-__device__ __forceinline__ void chCpAsync16(double* dstShared, const double* src)
-{
-    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(dstShared));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
 // tiles behind k1, column block b (64 wide) outermost: it meets the row tiles ti = 0 .. b / 2 (128 high); cumulative count
 __host__ __device__ __forceinline__ long long chSyrkTilesBefore(long long b)
 {

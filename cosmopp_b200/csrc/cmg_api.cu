@@ -1774,14 +1774,14 @@ cmg_status cholBuffers(cmg_ctx* ctx)
     if(!ctx->dCholInfo)
         CMG_CUDA(ctx, cudaMalloc(&ctx->dCholInfo, sizeof(long long)));
     if(!ctx->dCholRed)
-        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholRed, sizeof(double) * (4 + cmg::CH_NB)));      // reductions, then 1 / diagonal of a block
+        CMG_CUDA(ctx, cudaMalloc(&ctx->dCholRed, sizeof(double) * (4 + cmg::CH_UKK_DOUBLES)));      // reductions, then packed U_kk + 1 / diagonal of a block
     return CMG_OK;
 }
 }
 
 namespace
 {
-constexpr int CH_DIAG_SMEM = cmg::CH_NB * cmg::CH_LD * sizeof(double);
+constexpr int CH_DIAG_SMEM = cmg::CH_DIAG_SMEM_DOUBLES * sizeof(double);
 constexpr int CH_PANEL_SMEM = cmg::CH_PANEL_SMEM_DOUBLES * sizeof(double);
 constexpr int CH_SYRK_SMEM = 2 * (cmg::CH_TILE + cmg::CH_TJ) * cmg::CH_SLD * sizeof(double);
 constexpr int CH_MAX_GROUP = 4;                  // blocks per trailing update at most
@@ -1940,15 +1940,15 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
             const int kb = static_cast<int>(std::min<int64_t>(cmg::CH_NB, n - k0));
             if(sub > 0)                          // rows k0 .. k0 + 128 of every column from k0 on catch up with the sub blocks already solved
                 syrk(st, kBase, sub * cmg::CH_NB, 0, planes, true);
-            cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, st>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr);
+            cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, st>>>(dA, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4);
             ctx->launches += 1;
             const int64_t rem = n - k0 - kb;
             if(rem <= 0) return true;
             // (kb == CH_NB from here on: a short block can only be the last one)
             cmg::CholRuns runs = cholWholeRun(dA, k0 + kb, n);
             runs.first[1] = (rem + cmg::CH_PANEL_COLS - 1) / cmg::CH_PANEL_COLS;
-            cmg::cholPanelKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_PANEL_COLS, CH_PANEL_SMEM, st>>>(
-                runs, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, nullptr, planes + sub * planeStride, kBase);
+            cmg::cholPanelKernel<<<static_cast<unsigned>(runs.first[1]), cmg::CH_PANEL_THREADS, CH_PANEL_SMEM, st>>>(
+                runs, k0, kb, ctx->dCholInfo, ctx->dCholRed + 4, planes + sub * planeStride, kBase);
             ctx->launches += 1;
         }
         return kBase + groupRows >= n;
@@ -2021,8 +2021,7 @@ cmg_status cmg_chol_diag(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, in
     if(r < 0 || k0 + kb > runs->col_end[r]) return fail(ctx, CMG_EINVAL, "cmg_chol_diag: block k0 is not in this rank's columns");
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
     // d_ukk: kb (kb + 1) / 2 packed entries of U_kk, then the kb reciprocals of its diagonal
-    cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, ctx->stream>>>(runs->d_run[r] - cmg::chOff(runs->col_begin[r]), k0, kb, ctx->dCholInfo,
-                                                              dUkk + kb * (kb + 1) / 2, dUkk);
+    cmg::cholDiagKernel<<<1, 512, CH_DIAG_SMEM, ctx->stream>>>(runs->d_run[r] - cmg::chOff(runs->col_begin[r]), k0, kb, ctx->dCholInfo, dUkk);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return CMG_OK;
@@ -2032,14 +2031,14 @@ cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, i
 {
     if(!ctx) return CMG_EINVAL;
     if(!cholRunsValid(runs) || !dUkk || !dPanel || kb != cmg::CH_NB || k0 % cmg::CH_NB || panelCol0 > k0 + kb || !ctx->dCholInfo ||
-       reinterpret_cast<uintptr_t>(dPanel) % 16)
+       reinterpret_cast<uintptr_t>(dPanel) % 16 || reinterpret_cast<uintptr_t>(dUkk) % 16)
         return fail(ctx, CMG_EINVAL, "cmg_chol_panel: bad arguments (a full block of 128 rows; panel_col0 <= k0 + 128; a 16-byte aligned plane)");
     cmg::CholRuns clipped;
     const int64_t ctas = cholClipRuns(runs, k0 + kb, k0 + kb, cmg::CH_PANEL_COLS, &clipped);
     if(ctas == 0) return CMG_OK;
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
-    cmg::cholPanelKernel<<<static_cast<unsigned>(ctas), cmg::CH_PANEL_COLS, CH_PANEL_SMEM, ctx->stream>>>(clipped, k0, kb, ctx->dCholInfo,
-                                                                                                         dUkk + kb * (kb + 1) / 2, dUkk, dPanel, panelCol0);
+    cmg::cholPanelKernel<<<static_cast<unsigned>(ctas), cmg::CH_PANEL_THREADS, CH_PANEL_SMEM, ctx->stream>>>(clipped, k0, kb, ctx->dCholInfo, dUkk, dPanel,
+                                                                                                           panelCol0);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return CMG_OK;
