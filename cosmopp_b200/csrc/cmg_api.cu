@@ -71,7 +71,7 @@ struct cmg_ctx
     double* dCholRed = nullptr;                  // log det / reductions of the packed solves
     double* dCholPanel = nullptr;                // dense panel planes of cmg_packed_cholesky (cholesky.cuh, cholSyrkKernel)
     size_t cholPanelDoubles = 0;
-    int cholGroup = 4;                           // blocks of 128 rows per trailing update (cmg_set_cholesky_group)
+    int cholGroup = 0;                           // blocks of 128 rows per trailing update (cmg_set_cholesky_group); 0 = by size
     int cholLookAhead = 1;                       // the next group is factorised beside the trailing update (cmg_set_cholesky_lookahead)
     cudaStream_t cholSide = nullptr;             // high-priority stream of the look-ahead
     cudaEvent_t cholEvA = nullptr, cholEvF = nullptr;
@@ -1866,7 +1866,7 @@ int cholRunOfColumn(const cmg_chol_runs* runs, int64_t k0)
 cmg_status cmg_set_cholesky_group(cmg_ctx* ctx, int blocks)
 {
     if(!ctx) return CMG_EINVAL;
-    if(blocks < 1 || blocks > CH_MAX_GROUP) return fail(ctx, CMG_EINVAL, "cmg_set_cholesky_group: 1 .. 4 blocks of 128 rows");
+    if(blocks < 0 || blocks > CH_MAX_GROUP) return fail(ctx, CMG_EINVAL, "cmg_set_cholesky_group: 1 .. 4 blocks of 128 rows, or 0 = chosen by size");
     ctx->cholGroup = blocks;
     return CMG_OK;
 }
@@ -1893,7 +1893,9 @@ cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* dA, int64_t n, int64_t* inf
     cmg_status s = cholBuffers(ctx);
     if(s != CMG_OK) return s;
     if((s = cholStepAttributes(ctx)) != CMG_OK) return s;
-    const int S = ctx->cholGroup;
+    // measured (profiles/r2_cholesky_bench_v9.log): n = 9216: 13.0 ms with groups of 2, 14.4 with 4 (the chain of small kernels
+    // dominates and every block of a group adds a strip update to it); n = 36864: 536 / 510 ms
+    const int S = ctx->cholGroup > 0 ? ctx->cholGroup : (n >= 16384 ? 4 : 2);
     const int64_t groupRows = static_cast<int64_t>(S) * cmg::CH_NB;
     const bool ahead = ctx->cholLookAhead && n > 2 * groupRows;
     const int64_t planeStride = (n + CH_PLANE_SLACK) * cmg::CH_NB;

@@ -352,7 +352,7 @@ cmg_status cmg_sum_unpack_strided(cmg_ctx* ctx, const double* d_c, int64_t c_str
  * n (n + 1) / 2 doubles of the matrix itself, so the 147456-dimensional matrix of Nside = 64 is factorised where the generator
  * left it.  *info = 0, or k > 0 when the leading minor of order k is not positive definite (d_packed is then partly overwritten). */
 cmg_status cmg_packed_cholesky(cmg_ctx* ctx, double* d_packed, int64_t n, int64_t* info);
-/* blocks of 128 rows per trailing update (1 .. 4, default 4): the trailing matrix is read and written once per GROUP of blocks;
+/* blocks of 128 rows per trailing update (1 .. 4; 0 = default: 2 below n = 16384, 4 from there on): the trailing matrix is read and written once per GROUP of blocks;
  * workspace blocks x (n + 192) x 128 doubles on the device (the rows of U of the group in dense form, the operands of the update) */
 cmg_status cmg_set_cholesky_group(cmg_ctx* ctx, int blocks);
 /* look-ahead (default on): the next group's diagonal blocks and panels are factorised on a high-priority side stream beside the

@@ -131,7 +131,7 @@ def test_packed_cholesky_groups_of_blocks(gpu_ctx, n, group, lookahead):
         assert gpu_ctx.packed_cholesky(d, n) == 0
     finally:
         gpu_ctx.set_cholesky_lookahead(True)
-        gpu_ctx.set_cholesky_group(4)
+        gpu_ctx.set_cholesky_group(0)
     want = np.linalg.cholesky(A).T
     assert np.abs(unpack_upper(d.cpu().numpy(), n) - want).max() <= 1e-12 * np.abs(want).max()
 

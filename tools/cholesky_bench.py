@@ -13,7 +13,7 @@ ctx = cb.Context(0)
 stream = torch.cuda.current_stream()
 ctx.set_stream(stream.cuda_stream)
 peak = ctx.measure_fp64_peak()
-groups = [int(g) for a in sys.argv[1:] if a.startswith("--groups=") for g in a.split("=")[1].split(",")] or [4]
+groups = [int(g) for a in sys.argv[1:] if a.startswith("--groups=") for g in a.split("=")[1].split(",")] or [0]
 ctx.set_cholesky_lookahead("--no-lookahead" not in sys.argv)
 for nside in [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [16, 32]:
     lmax = 3 * nside

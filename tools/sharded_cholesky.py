@@ -96,7 +96,6 @@ def main():
             strips_match = float((strips - mine_before).abs().max())
             del mine_before
         ch = multigpu.ShardedCholesky(ctx, n, all_runs, rank, ptrs, group=group)
-        ctx.set_cholesky_group(group)
         launches0 = ctx.launches
         fact_ms, info = timed(ch.factorise)
         launches = ctx.launches - launches0
