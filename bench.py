@@ -324,6 +324,70 @@ def spot_check(ctx, sharded, spectra, nside, n_samples, seed):
     return float((np.abs(got - want) / scale).max())
 
 
+def cholesky_leg(ctx, torch, dist, nside, weights, rank, world, peak_tflops):
+    """--cholesky: the step behind the generator on the matrix where it lies.  The [T;Q;U] matrix is
+    generated over orbit shards whose in-face ranges sit on the 128-column block grid, exchanged, given white noise on the
+    diagonal (the signal matrix alone is rank deficient), and factorised IN PLACE on every rank's 36 strips by
+    multigpu.ShardedCholesky (one GPU: the same kernels on one run of columns).  Device time, max over ranks; U^T U = A is
+    checked on sampled entries of every rank's own columns (saved before the factorisation)."""
+    from cosmopp_b200 import capi, multigpu, partition
+    stream = torch.cuda.current_stream()
+    npix = 12 * nside * nside
+    n = 3 * npix
+    sh = multigpu.OrbitShardedTQU(ctx, nside, rank, world, bounds=partition.orbit_partition_blocks(nside, world))
+    sh.generate(weights)
+    sh.exchange()
+    all_runs, ptrs = sh.chol_runs()
+    mine = all_runs[rank]
+    strips = sh.strips.tensor()
+    ar = lambda b, e: torch.arange(b, e, device="cuda", dtype=torch.int64)
+    run_off, at = [], 0
+    for b, e in mine:
+        run_off.append(at)
+        at += partition.packed_size(e) - partition.packed_size(b)
+    cols = torch.cat([ar(b, e) for b, e in mine])
+    col_start = torch.cat([run_off[k] + (ar(b, e) * (ar(b, e) + 1) // 2 - partition.packed_size(b)) for k, (b, e) in enumerate(mine)])
+    strips[col_start + cols] += torch.where(cols < npix, 4.0, 0.09).double()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4321 + rank)
+    ns = 128
+    a = torch.randint(0, cols.numel(), (ns,), device="cuda", generator=g)
+    b_ = torch.randint(0, cols.numel(), (ns,), device="cuda", generator=g)
+    ia, ib = torch.minimum(a, b_), torch.maximum(a, b_)
+    si, sj = cols[ia], cols[ib]
+    a_ij, a_ii, a_jj = strips[col_start[ib] + si].clone(), strips[col_start[ia] + si].clone(), strips[col_start[ib] + sj].clone()
+    ch = multigpu.ShardedCholesky(ctx, n, all_runs, rank, ptrs)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launches
+    e0.record(stream)
+    info = ch.factorise()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    err = 0.0
+    for k in range(ns):
+        ci, cj, m = int(col_start[ia[k]]), int(col_start[ib[k]]), int(si[k]) + 1
+        err = max(err, float(abs(torch.dot(strips[ci:ci + m], strips[cj:cj + m]) - a_ij[k]) / torch.sqrt(a_ii[k] * a_jj[k])))
+    e = torch.tensor([err], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out = {"matrix_dim": n, "packed_bytes": 8 * capi.packed_size(n), "strip_bytes_this_rank": 8 * strips.numel(), "info": info, "ms": ms,
+           "tflops_all_gpus": n ** 3 / 3.0 / (ms * 1e-3) / 1e12, "frac_of_fp64_peak": n ** 3 / 3.0 / (ms * 1e-3) / 1e12 / (peak_tflops * world),
+           "kernel_launches_this_rank": ctx.launches - launches0, "log_det": ch.logdet(), "utu_max_rel_err": float(e.item()),
+           "utu_samples_per_rank": ns,
+           "how": "multigpu.ShardedCholesky on the rank's 36 orbit strips in place (cmg_chol_*: per block a 67 KB broadcast of U_kk and an all-reduce "
+                  "of one plane of the dense panel; FP64 tensor-core trailing update per group of 4 blocks); nothing gathered"}
+    del ch, strips
+    sh.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -688,6 +752,17 @@ def run_gpu_arm(args):
                             "(cmg_packed_cholesky), chi^2 and log det back: the matrix never crosses PCIe"}
         del d_mat, d_noise
 
+    chol = None
+    if args.cholesky and orbit_sharded and (nside * nside) % 128 == 0 and nside * nside // 128 >= world:
+        if not (world == 1 and not args.no_e2e):      # (the one-GPU e2e leg has closed the shards already)
+            try:
+                del pieces
+                sharded.close()
+            except Exception:
+                pass
+        torch.cuda.empty_cache()
+        chol = cholesky_leg(ctx, torch, dist, nside, weights, rank, world, peak_tflops)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = reference_sample(kind, nside, lmax, budget_s=12.0)
@@ -699,7 +774,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_per_step, "ms_per_matrix": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kind, nside, lmax, npix, world, args.shard_mode),
             "path": path_dict(kind, use_orbit, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "fp64_frac_of_peak": achieved / peak_tflops, "exchange": exchange, "gather": gather, "e2e_device_consumer": consumer,
+            "fp64_frac_of_peak": achieved / peak_tflops, "exchange": exchange, "gather": gather, "e2e_device_consumer": consumer, "consumer_cholesky": chol,
             "parity_max_err": parity,
             "parity_note": ("max over ranks of |entry - oracle| / diagonal of the block over %d sampled entries of each rank's packed columns "
                             "(oracle/api.py tqu_pairs, untimed; gate 1e-11)" % args.spot_check) if parity is not None else None,
@@ -850,6 +925,8 @@ def main():
     ap.add_argument("--host-expand", type=int, default=-1, metavar="THREADS",
                     help="N=1, full sky, e2e leg: copy back only the last-face columns (27 %% of the matrix) and fill in the rotated images "
                          "on THREADS host threads (cmg_set_host_expand); -1 = the library's default (automatic), 0 = one plain copy of the whole matrix")
+    ap.add_argument("--cholesky", action="store_true", help="full-sky T,Q,U over orbits: also factorise the matrix in place on the shards "
+                    "(multigpu.ShardedCholesky; key consumer_cholesky; ~40 s on one GPU, ~5 s on eight for the Nside = 64 matrix)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
