@@ -139,6 +139,7 @@ _SIGNATURES = {
     "cmg_fiducial_matrix_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp]),
     "cmg_cl_to_cmatrix_pol_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp]),
     "cmg_matrix_to_host": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _vp]),
+    "cmg_tqu_orbit_plan_mirror": (ctypes.c_int, [_i64, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cmg_packed_cholesky": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64)]),
     "cmg_packed_cholesky_logdet": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(ctypes.c_double)]),
     "cmg_packed_cholesky_solve": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64]),
@@ -238,11 +239,17 @@ def orbit_plan(nside, mode=0):
     st = library().cmg_tqu_orbit_plan(int(nside), int(mode), _p(out), ctypes.byref(n))
     if st:
         raise CmgError(st, "cmg_tqu_orbit_plan: bad nside / mode")
+    mir = np.zeros((24, 5), dtype=np.int32)
+    st = library().cmg_tqu_orbit_plan_mirror(int(nside), int(mode), _p(mir), ctypes.byref(n))
+    if st:
+        raise CmgError(st, "cmg_tqu_orbit_plan_mirror: bad nside / mode")
     plan = []
-    for row in out[:n.value]:
+    for row, m in zip(out[:n.value], mir[:n.value]):
         imgs = [(int(row[5 + 3 * k]), int(row[6 + 3 * k]), bool(row[7 + 3 * k])) for k in range(int(row[4]))]
+        # mirror images (mode 3): (row face, column face) of the four rotations of the pair's image under the meridian mirror
+        mirror = [(int(m[1 + k]), int(row[6 + 3 * k])) for k in range(4)] if m[0] else []
         plan.append(dict(row_face=int(row[0]), col_face=int(row[1]), tri=bool(row[2]), same_face=bool(row[3]), images=imgs,
-                         combo_base=[int(row[17 + k]) for k in range(int(row[4]))]))
+                         combo_base=[int(row[17 + k]) for k in range(int(row[4]))], mirror_images=mirror))
     return plan
 
 

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -1081,7 +1082,7 @@ cmg_status cmg_tqu_dev(cmg_ctx* ctx, const double* dA, int lmax, const cmg_tqu_l
 
 cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* nClasses)
 {
-    if(!out || !nClasses || !cmg::validNside(nside) || (mode != 0 && mode != 1))
+    if(!out || !nClasses || !cmg::validNside(nside) || (mode != 0 && mode != 1 && mode != 3))
         return CMG_EINVAL;
     cmg::OrbitPlan plan;
     cmg::orbitBuildPlan(nside, mode, -1, plan);
@@ -1098,6 +1099,22 @@ cmg_status cmg_tqu_orbit_plan(int64_t nside, int mode, int32_t* out, int32_t* nC
             o[7 + 3 * k] = oc.imgSwap[k];
             o[17 + k] = oc.comboBase[k];
         }
+    }
+    return CMG_OK;
+}
+
+cmg_status cmg_tqu_orbit_plan_mirror(int64_t nside, int mode, int32_t* out, int32_t* nClasses)
+{
+    if(!out || !nClasses || !cmg::validNside(nside) || (mode != 0 && mode != 1 && mode != 3))
+        return CMG_EINVAL;
+    cmg::OrbitPlan plan;
+    cmg::orbitBuildPlan(nside, mode, -1, plan);
+    *nClasses = plan.n;
+    for(int c = 0; c < plan.n; ++c)
+    {
+        out[c * 5] = plan.c[c].mirror;
+        for(int k = 0; k < cmg::ORB_MAX_IMAGES; ++k)
+            out[c * 5 + 1 + k] = plan.c[c].mirRowFace[k];
     }
     return CMG_OK;
 }
@@ -1139,7 +1156,10 @@ cmg_status orbitCheckBounds(cmg_ctx* ctx, int64_t nside, int nRanks, const int64
 cmg_status orbitShardDev(cmg_ctx* ctx, const cmg_orbit_shard* shard, int mode, cmg::OrbitShardDev& sh)
 {
     if(!shard) return fail(ctx, CMG_EINVAL, "null shard");
-    if(mode < 0 || mode > 2) return fail(ctx, CMG_EINVAL, "orbit mode must be 0 (transposed images), 1 (none) or 2 (0 without the row-pointer table)");
+    if(mode < 0 || mode > 3)
+        return fail(ctx, CMG_EINVAL, "orbit mode must be 0 (transposed images), 1 (none), 2 (0 without the row-pointer table) or 3 (0 + the meridian mirror)");
+    if(mode == 3 && shard->n_ranks != 1)
+        return fail(ctx, CMG_EUNSUPPORTED, "orbit mode 3 (meridian mirror) needs a single owner: the mirror image of a rank's columns are another rank's");
     if(mode == 2) mode = 0;                          // same classes, same storage
     if(!ctx->fullSky)
         return fail(ctx, CMG_EUNSUPPORTED, "the symmetry-orbit path needs the full sky in NESTED order (cmg_set_pixels with good_nest = NULL)");
@@ -1198,8 +1218,8 @@ cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* att, const double* 
     const unsigned tiles = static_cast<unsigned>(tiles64);
 
     KernelTimer timer(ctx);
-    const int masks[3] = {0, 8, 12};                 // classes by their transposed images: none, (3,0), (2,0) + (3,1)
-    for(int m = 0; m < 3; ++m)
+    const int masks[4] = {0, 8, 12, 16};             // classes by their transposed images: none, (3,0), (2,0) + (3,1); 16: with mirror images (mode 3)
+    for(int m = 0; m < 4; ++m)
     {
         cmg::OrbitPlan plan;
         cmg::orbitBuildPlan(ctx->nside, mode == 2 ? 0 : mode, masks[m], plan);
@@ -1213,7 +1233,15 @@ cmg_status cmg_tqu_orbit_sharded(cmg_ctx* ctx, const double* att, const double* 
             CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));       \
             kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);                          \
         }
-        if(masks[m] == 0 && mode == 0)
+        if(masks[m] == 16)
+        {
+            // whole face pairs of different rings + the four rotations of their mirror image: eight images per evaluated pair
+            auto kernel = cmg::tquOrbitKernel<4, 2, 0, true, true>;
+            const size_t smem = sizeof(double) * cmg::orbitSmemDoubles<false, true, true>();
+            CMG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kernel<<<grid, cmg::PQ_THREADS, smem, ctx->stream>>>(T, geometryOf(ctx), entrySlot, plan, sh);
+        }
+        else if(masks[m] == 0 && (mode == 0 || mode == 3))
         {
             // classes without transposed images: store destinations from a per-tile table in shared memory (36.2 against 36.8 ms)
             auto kernel = cmg::tquOrbitKernel<4, 2, 0, true>;

@@ -37,6 +37,8 @@ struct OrbitClass
     int imgColFace[ORB_MAX_IMAGES];
     int imgSwap[ORB_MAX_IMAGES];           // 1: the image of the rows has the LARGER pixel index
     int comboBase[ORB_MAX_IMAGES];         // outbox numbering of (this class, image k, staged kind 0): see OrbitShardDev
+    int mirror;                            // 1 (mode 3): the class also stores its image under the meridian mirror, 4 rotations of it
+    int mirRowFace[ORB_MAX_IMAGES];        // faces of mirror image k (the column faces are imgColFace[k]: the mirror fixes the column face)
 };
 
 struct OrbitPlan
@@ -47,11 +49,24 @@ struct OrbitPlan
     OrbitClass c[ORB_MAX_CLASSES];
 };
 
-inline int orbitRotateFace(int f, int k) { return (f & ~3) | ((f + k) & 3); }
+__host__ __device__ inline int orbitRotateFace(int f, int k) { return (f & ~3) | ((f + k) & 3); }
+// (ix, iy) -> (iy, ix) inside a face: the even and the odd bits of the NESTED in-face index change places
+__host__ __device__ inline unsigned orbitSwapBits(unsigned q) { return ((q & 0x55555555u) << 1) | ((q & 0xAAAAAAAAu) >> 1); }
 
+// mode 3 = mode 0 + the meridian mirror (single owner only).  The grid is also invariant under the reflection phi -> pi/2 - phi:
+// polar face position p -> -p, equatorial p -> 1 - p, in-face (ix, iy) -> (iy, ix) = the even and odd bits of the NESTED in-face
+// index swapped (orbitSwapBits); a reflection flips the sign of every entry with exactly one U index
+// (tests/test_orbit_plan.py::test_mirror_symmetries_of_the_oracle_matrix).  Composed with the rotation there is, for every pair of
+// rings, a reflection that FIXES the column face at position 0 and maps the row faces p -> p': north rows, equatorial columns
+// p' = -p - 1; north rows, south columns p' = -p; equatorial rows, south columns p' = 1 - p.  Of the twelve cross-ring classes
+// five are the mirror images of five others (N0|N3, N1|N2 against E0; E0|E1, E2|E3 against S0; N1|N3 against S0) and are not
+// evaluated: 13 of 72 face-pair units instead of 18.  (N0, S0) and (N2, S0) map to themselves and are kept whole.  A mirror
+// image's 64 row pixels are a permutation of an aligned 64-run and its 32 column pixels two 16-runs 32 apart: every warp
+// store is still made of whole 128-byte segments.  The image's columns are in general ANOTHER rank's, which is why only the
+// single owner uses it.
 // mode 0: transposed images allowed (18 units); mode 1: none (22.5 units).  swapMask selects the classes to emit by
 // their mask of transposed images (bit k = image k): 0 = none transposed, 8 = the (0,1) classes, 12 = the (0,2) classes,
-// -1 = all.  The mask is a template parameter of the kernel: with the flags read from the plan at run time ptxas no longer
+// 16 = the classes that carry mirror images (mode 3; they have no transposed ones), -1 = all.  The mask is a template parameter of the kernel: with the flags read from the plan at run time ptxas no longer
 // proves the series loop warp-uniform and drops its uniform-register coefficient operands (0.84 instead of 1.0 of the FP64
 // issue rate in the loop).
 inline void orbitBuildPlan(int64_t nside, int mode, int swapMask, OrbitPlan& plan)
@@ -61,9 +76,9 @@ inline void orbitBuildPlan(int64_t nside, int mode, int swapMask, OrbitPlan& pla
     plan.nComboA = plan.nComboB = 0;
     // the numbering of the (class, image, staged kind) combinations runs over ALL classes of the mode, whatever swapMask
     // selects: whole-face-pair classes first (0 .. nComboA), q_row <= q_col classes behind them (fixed up below)
-    auto add = [&](int rowFace, int colFace, int tri, int sameFace, int nImg, const int* rot, const int* swap)
+    auto add = [&](int rowFace, int colFace, int tri, int sameFace, int nImg, const int* rot, const int* swap, int mirrorRowFace = -1)
     {
-        int mask = 0, base[ORB_MAX_IMAGES] = {0, 0, 0, 0};
+        int mask = mirrorRowFace >= 0 ? 16 : 0, base[ORB_MAX_IMAGES] = {0, 0, 0, 0};
         int& counter = tri ? plan.nComboB : plan.nComboA;
         for(int k = 0; k < nImg; ++k)
         {
@@ -74,6 +89,9 @@ inline void orbitBuildPlan(int64_t nside, int mode, int swapMask, OrbitPlan& pla
         if(swapMask >= 0 && swapMask != mask)
             return;
         OrbitClass& c = plan.c[plan.n++];
+        c.mirror = mirrorRowFace >= 0 ? 1 : 0;
+        for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+            c.mirRowFace[k] = mirrorRowFace >= 0 ? orbitRotateFace(mirrorRowFace, k) : 0;
         for(int k = 0; k < ORB_MAX_IMAGES; ++k)
             c.comboBase[k] = base[k];
         c.rowFace = rowFace;
@@ -94,11 +112,24 @@ inline void orbitBuildPlan(int64_t nside, int mode, int swapMask, OrbitPlan& pla
     for(int gRow = 0; gRow < 3; ++gRow)
         for(int gCol = gRow + 1; gCol < 3; ++gCol)
             for(int p = 0; p < 4; ++p)
-                add(4 * gRow + p, 4 * gCol, 0, 0, 4, rot4, none);
+            {
+                if(mode != 3)
+                {
+                    add(4 * gRow + p, 4 * gCol, 0, 0, 4, rot4, none);
+                    continue;
+                }
+                // the reflection that fixes the column face: partner position of the row face
+                const int partner = gCol == 1 ? ((-p - 1) & 3) : (gRow == 1 ? ((1 - p) & 3) : ((-p) & 3));
+                if(partner == p)
+                    add(4 * gRow + p, 4 * gCol, 0, 0, 4, rot4, none);             // its own mirror image: kept whole
+                else if(p < partner)
+                    add(4 * gRow + p, 4 * gCol, 0, 0, 4, rot4, none, 4 * gRow + partner);
+                // else: stored as the mirror image of class (partner)
+            }
     for(int g = 0; g < 3; ++g)
     {
         add(4 * g, 4 * g, 1, 1, 4, rot4, none);                                  // the same face
-        if(mode == 0)
+        if(mode == 0 || mode == 3)
         {
             const int swap01[4] = {0, 0, 0, 1};                                  // (3,0) is stored as (0,3) transposed
             add(4 * g, 4 * g + 1, 0, 0, 4, rot4, swap01);
@@ -156,10 +187,11 @@ __host__ __device__ inline int orbitOwnerOfHalfTile(const OrbitShardDev& sh, int
 }
 
 // shared memory of tquOrbitKernel: frames of rows and columns, staged entries, column pointers of every image
-template <bool SWAP, bool ROWPTR = false>
+template <bool SWAP, bool ROWPTR = false, bool MIRROR = false>
 constexpr int orbitSmemDoubles()
 {
-    return 8 * PQ_TI + 8 * PQ_TJ + (SWAP ? 6 : 3) * PQ_TI * PQ_STAGE_LD + ORB_MAX_IMAGES * 3 * PQ_TJ + (ROWPTR ? ORB_MAX_IMAGES * 3 * PQ_TI : 0);
+    constexpr int IMAGES = MIRROR ? 2 * ORB_MAX_IMAGES : ORB_MAX_IMAGES;
+    return 8 * PQ_TI + 8 * PQ_TJ + (SWAP ? 6 : 3) * PQ_TI * PQ_STAGE_LD + IMAGES * 3 * PQ_TJ + (ROWPTR ? IMAGES * 3 * PQ_TI : 0);
 }
 
 // staged kind t -> (column strip X, row strip Y) of the entry <X a', Y b'>
@@ -192,7 +224,11 @@ __device__ __forceinline__ bool orbitTile(const OrbitPlan& plan, const OrbitShar
 // ROWPTR (SWAPMASK == 0 only; NOT YET RUN ON A GPU, selected by mode 2 of the API): the destination of every (image, kind, row)
 // of the store phase is computed once per tile into shared memory by all threads in parallel, as tquKernel does, instead of
 // ~25 instructions per warp store in the store loop.
-template <int R, int MINB, int SWAPMASK, bool ROWPTR = false>
+// MIRROR (mode 3, single owner, classes of mask 16: whole face pairs of different rings, no transposed images; needs ROWPTR):
+// images 4 .. 7 are the four rotations of the pair's mirror image -- row pixel (mirRowFace[k], swapped bits of q_row), column pixel
+// (imgColFace[k], swapped bits of q_col), the entries with exactly one U index negated.  The thread's row offset and the lane's
+// offset inside a staged row become orbitSwapBits(il) and orbitSwapBits(lane): a warp store is two 128-byte segments.
+template <int R, int MINB, int SWAPMASK, bool ROWPTR = false, bool MIRROR = false>
 __global__ void __launch_bounds__(PQ_THREADS, MINB)
 tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entrySlot,
                const __grid_constant__ OrbitPlan plan, const __grid_constant__ OrbitShardDev sh)
@@ -200,12 +236,14 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     extern __shared__ double4 orbSmem[];
     constexpr bool SWAP = SWAPMASK != 0;
     constexpr int SLOTS = SWAP ? 6 : 3;
+    constexpr int IMAGES = MIRROR ? 2 * ORB_MAX_IMAGES : ORB_MAX_IMAGES;
     double* sI = reinterpret_cast<double*>(orbSmem);                  // [8][PQ_TI]
     double* sJ = sI + 8 * PQ_TI;                                     // [8][PQ_TJ]
     double* stage = sJ + 8 * PQ_TJ;                                  // [SLOTS][PQ_TI][PQ_STAGE_LD]
     double** sColPtr = reinterpret_cast<double**>(stage + SLOTS * PQ_TI * PQ_STAGE_LD);   // [image][3][PQ_TJ]
-    double** sRowPtr = sColPtr + ORB_MAX_IMAGES * 3 * PQ_TJ;                              // [image][3][PQ_TI]  (ROWPTR only)
+    double** sRowPtr = sColPtr + IMAGES * 3 * PQ_TJ;                                      // [image][3][PQ_TI]  (ROWPTR only)
     static_assert(!ROWPTR || SWAPMASK == 0, "the row-pointer table is sized for three staged kinds");
+    static_assert(!MIRROR || ROWPTR, "mirror images are stored through the row-pointer table");
 
     int qRow0, qCol0;
     if(!orbitTile(plan, sh, qRow0, qCol0))
@@ -225,17 +263,19 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
     // phase reads nothing but this table: no kernel parameter is referenced behind the series loop, so ptxas has nothing to
     // hoist above it -- uniform values kept live across the loop cost it its uniform-register coefficient operands
     // (tests/test_sass_guard.py; a third of the DFMAs then read three vector registers).
-    __shared__ OrbitStoreRow sStore[ORB_MAX_IMAGES * 6];
+    __shared__ OrbitStoreRow sStore[IMAGES * 6];
     __shared__ int sRange[2];
-    if(tid < ORB_MAX_IMAGES * 6)
+    if(tid < IMAGES * 6)
     {
         const int k = tid / 6, t = tid - 6 * k;
-        const bool swapped = (SWAPMASK >> k) & 1;
-        if(k < nImg && t < (swapped ? 6 : 3))
+        const bool mirrored = MIRROR && k >= ORB_MAX_IMAGES;
+        const bool swapped = !mirrored && ((SWAPMASK >> k) & 1);
+        if((mirrored || k < nImg) && t < (swapped ? 6 : 3))
         {
-            const int rowFace = oc.imgRowFace[k], colFace = oc.imgColFace[k];
-            const long long rowPix0 = static_cast<long long>(rowFace) * facePix + qRow0;
-            const long long colPix0 = static_cast<long long>(colFace) * facePix + qCol0;
+            const int rowFace = mirrored ? oc.mirRowFace[k - ORB_MAX_IMAGES] : oc.imgRowFace[k];
+            const int colFace = oc.imgColFace[k & (ORB_MAX_IMAGES - 1)];
+            const long long rowPix0 = static_cast<long long>(rowFace) * facePix + (mirrored ? static_cast<int>(orbitSwapBits(qRow0)) : qRow0);
+            const long long colPix0 = static_cast<long long>(colFace) * facePix + (mirrored ? static_cast<int>(orbitSwapBits(qCol0)) : qCol0);
             const long long c = orbitStripX(t) * npix + rowPix0;                 // < 2^32 for every valid nside
             OrbitStoreRow e;
             e.own = sh.strip[orbitStripX(t)][rowFace] + packedOffset(c) + (orbitStripY(t) * npix + colPix0);
@@ -278,26 +318,34 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
         dst[7 * ld + loc] = geo.py[pix];
     }
     // row 0 of columns b', N + b', 2N + b' for the column pixels b' of every image (always this rank's own strips)
-    for(int idx = tid; idx < ORB_MAX_IMAGES * 3 * PQ_TJ; idx += PQ_THREADS)
+    for(int idx = tid; idx < IMAGES * 3 * PQ_TJ; idx += PQ_THREADS)
     {
         const int k = idx / (3 * PQ_TJ);
         const int rem = idx - k * 3 * PQ_TJ;
         const int strip = rem / PQ_TJ;
-        const int face = oc.imgColFace[k];
-        const long long col = strip * npix + static_cast<long long>(face) * facePix + qCol0 + (rem - strip * PQ_TJ);
+        const int face = oc.imgColFace[k & (ORB_MAX_IMAGES - 1)];
+        const int qc = qCol0 + (rem - strip * PQ_TJ);
+        const long long col = strip * npix + static_cast<long long>(face) * facePix + (MIRROR && k >= ORB_MAX_IMAGES ? static_cast<int>(orbitSwapBits(qc)) : qc);
         sColPtr[idx] = sh.strip[strip][face] + packedOffset(col);
     }
     if(ROWPTR)
     {
         // where row (image k, kind t, a') of the store phase starts: the rank's own strip, or its outbox sub-tile
         __syncthreads();
-        for(int idx = tid; idx < ORB_MAX_IMAGES * 3 * PQ_TI; idx += PQ_THREADS)
+        for(int idx = tid; idx < IMAGES * 3 * PQ_TI; idx += PQ_THREADS)
         {
             const int k = idx / (3 * PQ_TI);
             const int rem = idx - k * 3 * PQ_TI;
             const int t = rem / PQ_TI;
             const unsigned ilr = static_cast<unsigned>(rem - t * PQ_TI);
-            if(k < nImg)
+            if(MIRROR && k >= ORB_MAX_IMAGES)
+            {
+                // tile row ilr is row orbitSwapBits(ilr) of the image's 64-run (single owner: always the rank's own strips)
+                const OrbitStoreRow e = sStore[k * 6 + t];
+                const unsigned rm = orbitSwapBits(ilr);
+                sRowPtr[idx] = e.own + (static_cast<unsigned long long>(rm) * e.c + (rm * (rm + 1)) / 2);
+            }
+            else if(k < nImg)
             {
                 const OrbitStoreRow e = sStore[k * 6 + t];
                 const int qa = qRow0 + static_cast<int>(ilr);
@@ -393,6 +441,25 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
                         __stcs(colU + 2 * npix, vUU);
                     }
                 }
+                if(MIRROR)
+                {
+                    // the mirror image of the pair, four rotations of it: <T U> and <Q U> change sign (whole face pairs: every pair is live)
+                    const long long ilM = static_cast<long long>(orbitSwapBits(static_cast<unsigned>(qRow0 + il)));
+#pragma unroll
+                    for(int k = 0; k < ORB_MAX_IMAGES; ++k)
+                    {
+                        const long long ip = static_cast<long long>(oc.mirRowFace[k]) * facePix + ilM;
+                        double* colT = sColPtr[((ORB_MAX_IMAGES + k) * 3 + 0) * PQ_TJ + jl] + ip;
+                        double* colQ = sColPtr[((ORB_MAX_IMAGES + k) * 3 + 1) * PQ_TJ + jl] + ip;
+                        double* colU = sColPtr[((ORB_MAX_IMAGES + k) * 3 + 2) * PQ_TJ + jl] + ip;
+                        __stcs(colQ, vTQ);
+                        __stcs(colU, -vTU);
+                        __stcs(colU + npix, -vQU);
+                        __stcs(colT, vTT);
+                        __stcs(colQ + npix, vQQ);
+                        __stcs(colU + 2 * npix, vUU);
+                    }
+                }
                 stage[(0 * PQ_TI + il) * PQ_STAGE_LD + jl] = xt * fma(ai, ai, -bi * bi);   // Q_a T_b
                 stage[(1 * PQ_TI + il) * PQ_STAGE_LD + jl] = xt * (2.0 * ai * bi);         // U_a T_b
                 stage[(2 * PQ_TI + il) * PQ_STAGE_LD + jl] = aIm + bIm;                    // U_a Q_b
@@ -425,6 +492,21 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
                 const int ilr = row & (PQ_TI - 1);
                 if(qColLane - (qRow0 + ilr) >= minGap)
                     __stcs(sRowPtr[k * 3 * PQ_TI + row] + lane, stage[row * PQ_STAGE_LD + lane]);
+            }
+        }
+        if(MIRROR)
+        {
+            // <Q_a T_b>, <U_a T_b>, <U_a Q_b> of the mirror images: the 32 column pixels of the tile are two 16-runs of rows of
+            // column (X a'); kinds 1 and 2 carry exactly one U index
+            const unsigned laneM = orbitSwapBits(static_cast<unsigned>(lane));
+            for(int k = ORB_MAX_IMAGES; k < 2 * ORB_MAX_IMAGES; ++k)
+            {
+#pragma unroll 4
+                for(int row = warp; row < 3 * PQ_TI; row += PQ_THREADS / 32)
+                {
+                    const double v = stage[row * PQ_STAGE_LD + lane];
+                    __stcs(sRowPtr[k * 3 * PQ_TI + row] + laneM, row >= PQ_TI ? -v : v);
+                }
             }
         }
         return;

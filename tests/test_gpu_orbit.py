@@ -29,7 +29,7 @@ def _inputs(ctx, nside, lmax):
 
 
 @pytest.mark.parametrize("nside,lmax", [(8, 20), (16, 47)])
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_orbit_matches_oracle(gpu_ctx, oracle_api, nside, lmax, mode):
     import torch
     from cosmopp_b200 import capi
@@ -234,3 +234,17 @@ def test_orbit_mode2_is_bit_identical_to_mode0(gpu_ctx):
     gpu_ctx.tqu_orbit(*w, b, 2)
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
+
+def test_orbit_mode3_refuses_several_owners(gpu_ctx):
+    """the meridian mirror puts images into columns of other ranks: single owner only"""
+    from cosmopp_b200 import capi, multigpu
+    gpu_ctx.set_pixels(16)
+    f = capi.window_beam(20, 10.0)
+    w = capi.tqu_weights(*synthetic_cl(20, pol=True), f, f)
+    sh = multigpu.OrbitShardedTQU(gpu_ctx, 16, 0, 2)
+    try:
+        with pytest.raises(capi.CmgError):
+            gpu_ctx.tqu_orbit_sharded(*w, sh.shard, 3)
+    finally:
+        sh.close()

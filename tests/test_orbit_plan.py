@@ -121,6 +121,7 @@ def emulate_kernel_stores(plan, nside, n, M, bounds=None, rank=0):
                         put(col[1] + ip, cols[1], v[0, 1], strict)
                         put(col[2] + ip, cols[2], v[0, 2], strict)
                         put(col[2] + n + ip, cols[2], v[1, 2], strict)
+                    # (mirror images: below, after the loop over the rotation images)
                     min_gap = -(1 << 30) if not c["tri"] else (1 if (c["same_face"] or swap) else 0)
                     staged = [(1, 0), (2, 0), (2, 1)] + ([(0, 0), (1, 1), (2, 2)] if swap else [])
                     qa = q_row0 + il + 0 * jl
@@ -135,7 +136,30 @@ def emulate_kernel_stores(plan, nside, n, M, bounds=None, rank=0):
                             np.add.at(box_count, e, 1)
                             box_out[e] = v[X, Y][far]
                             box_pos[e] = pos[far]
+                # mode 3: the four rotations of the pair's image under the meridian mirror -- both in-face indices with their even
+                # and odd bits swapped, entries with exactly one U index negated (single owner; whole face pairs of different rings)
+                for fr, fc in c.get("mirror_images", []):
+                    assert not c["tri"] and world_is_one(bounds)
+                    ip = fr * F + swapbits(q_row0 + il + 0 * jl)
+                    jp = fc * F + swapbits(q_col0 + jl + 0 * il)
+                    assert (ip < jp).all()
+                    every = np.ones((TI, TJ), dtype=bool)
+                    for X in range(3):
+                        for Y in range(3):
+                            sign = -1.0 if (X == 2) != (Y == 2) else 1.0
+                            if X <= Y:                       # direct stores: column (Y b'), row (X a')
+                                put(po(Y * n + jp) + X * n + ip, Y * n + jp, sign * v[X, Y], every)
+                            else:                            # staged: column (X a'), row (Y b')
+                                put(po(X * n + ip) + Y * n + jp, X * n + ip, sign * v[X, Y], every)
     return out, count, box_out, box_count, box_pos
+
+
+def swapbits(q):
+    return ((q & 0x55555555) << 1) | ((q & 0xAAAAAAAA) >> 1)
+
+
+def world_is_one(bounds):
+    return len(bounds) == 2
 
 
 def emulate_inbox_scatter(plan, nside, n, bounds, sender, receiver, block):
@@ -173,7 +197,16 @@ def packed_from_full(M):
     return want, iu
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+def test_mirror_plan_evaluates_thirteen_units():
+    plan = capi.orbit_plan(8, 3)
+    units = sum(0.5 if c["tri"] else 1.0 for c in plan)
+    assert units == 13.0
+    with_mirror = [c for c in plan if c["mirror_images"]]
+    assert len(with_mirror) == 5 and all(not c["tri"] and len(c["mirror_images"]) == 4 for c in with_mirror)
+    assert all(not c["mirror_images"] for c in capi.orbit_plan(8, 0))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_store_rules_fill_the_packed_triangle_exactly_once(oracle_matrix, mode):
     nside, n, M = oracle_matrix
     out, count, _, box_count, _ = emulate_kernel_stores(capi.orbit_plan(nside, mode), nside, n, M)

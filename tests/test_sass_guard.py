@@ -14,8 +14,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-KERNELS = ["tquKernelILi4ELb1ELi2E", "tquOrbitKernelILi4ELi2ELi0ELb0E", "tquOrbitKernelILi4ELi2ELi8ELb0E", "tquOrbitKernelILi4ELi2ELi12ELb0E",
-           "tquOrbitKernelILi4ELi2ELi0ELb1E"]
+KERNELS = ["tquKernelILi4ELb1ELi2E", "tquOrbitKernelILi4ELi2ELi0ELb0ELb0E", "tquOrbitKernelILi4ELi2ELi8ELb0ELb0E", "tquOrbitKernelILi4ELi2ELi12ELb0ELb0E",
+           "tquOrbitKernelILi4ELi2ELi0ELb1ELb0E", "tquOrbitKernelILi4ELi2ELi0ELb1ELb1E"]
 
 
 @pytest.fixture(scope="module")

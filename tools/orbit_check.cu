@@ -142,6 +142,29 @@ int main(int argc, char** argv)
         return rc;
     }
 
+    if(what == "time")    // Nside 64: modes 3 and 0 on one GPU, best of 3
+    {
+        const int nside = 64, lmax = 192;
+        OK(cmg_set_pixels(ctx, nside, nullptr, 0));
+        const int64_t n = cmg_npix(ctx), packed = cmg_packed_size(3 * n);
+        std::vector<double> tt, te, ee, bb;
+        weights(lmax, tt, te, ee, bb);
+        double* dA = nullptr;
+        OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
+        for(int mode = 3; mode >= 0; mode -= 3)
+        {
+            double best = 1e30;
+            for(int rep = 0; rep < 3; ++rep)
+            {
+                OK(cmg_tqu_orbit(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, dA, mode));
+                double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
+                best = std::min(best, ms);
+            }
+            std::printf("nside 64 lmax 192 mode %d: %.2f ms\n", mode, best);
+        }
+        cmg_destroy(ctx);
+        return 0;
+    }
     if(what == "prof" || what == "ranks")
     {
         const int nside = 64, lmax = 192;
@@ -153,16 +176,17 @@ int main(int argc, char** argv)
         {
             double* dA = nullptr;
             OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
-            OK(cmg_tqu_orbit(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, dA, 0));
+            const int profMode = argc > 2 ? std::atoi(argv[2]) : 0;
+            OK(cmg_tqu_orbit(ctx, tt.data(), te.data(), ee.data(), bb.data(), lmax, dA, profMode));
             double ms = 0; OK(cmg_last_kernel_ms(ctx, &ms));
-            std::printf("prof: nside 64 lmax 192 mode 0: %.2f ms\n", ms);
+            std::printf("prof: nside 64 lmax 192 mode %d: %.2f ms\n", profMode, ms);
             cmg_destroy(ctx);
             return 0;
         }
         {
             double* dA = nullptr;
             OK(cmg_device_malloc(ctx, packed * 8, (void**) &dA));
-            for(int mode = 2; mode >= 0; --mode)
+            for(int mode = 3; mode >= 0; --mode)
             {
                 double best = 1e30;
                 for(int rep = 0; rep < 4; ++rep)
@@ -236,7 +260,7 @@ int main(int argc, char** argv)
         OK(cmg_copy_to_host(ctx, hA.data(), dA, packed * 8));
         OK(cmg_synchronize(ctx));
         const double dT = hA[0], dQ = hA[cmg_packed_index(n, n)];
-        for(int mode = 2; mode >= 0; --mode)
+        for(int mode = 3; mode >= 0; --mode)
         {
             cudaMemset(dB, 0xFF, packed * 8);                      // NaN pattern: an entry nobody writes shows up
             cudaDeviceSynchronize();
@@ -387,7 +411,7 @@ int main(int argc, char** argv)
         for(int w = 0; w < 3; ++w) OK(cmg_copy_to_host(ctx, ref.data() + w * win, dA + starts[w], win * 8));
         OK(cmg_synchronize(ctx));
         std::printf("nside 64 lmax 192: cmg_tqu %.2f ms\n", best);
-        for(int mode = 2; mode >= 0; --mode)
+        for(int mode = 3; mode >= 0; --mode)
         {
             cudaMemset(dA, 0xFF, packed * 8);
             cudaDeviceSynchronize();
