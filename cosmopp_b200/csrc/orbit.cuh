@@ -56,7 +56,7 @@ __host__ __device__ inline unsigned orbitSwapBits(unsigned q) { return ((q & 0x5
 // mode 3 = mode 0 + the meridian mirror (single owner only).  The grid is also invariant under the reflection phi -> pi/2 - phi:
 // polar face position p -> -p, equatorial p -> 1 - p, in-face (ix, iy) -> (iy, ix) = the even and odd bits of the NESTED in-face
 // index swapped (orbitSwapBits); a reflection flips the sign of every entry with exactly one U index
-// (tests/test_orbit_plan.py::test_mirror_symmetries_of_the_oracle_matrix).  Composed with the rotation there is, for every pair of
+// (checked in tests/test_orbit_plan.py).  Composed with the rotation there is, for every pair of
 // rings, a reflection that FIXES the column face at position 0 and maps the row faces p -> p': north rows, equatorial columns
 // p' = -p - 1; north rows, south columns p' = -p; equatorial rows, south columns p' = 1 - p.  Of the twelve cross-ring classes
 // five are the mirror images of five others (N0|N3, N1|N2 against E0; E0|E1, E2|E3 against S0; N1|N3 against S0) and are not
