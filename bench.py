@@ -452,7 +452,10 @@ def run_gpu_arm(args):
         spectra = synthetic_cl(lmax, pol=True)
         weights = capi.tqu_weights(*spectra, f, f)
         if use_orbit:
-            sharded = multigpu.OrbitShardedTQU(ctx, nside, rank, world, mode=0, exchange=args.exchange)
+            # --orbit-mode 3 (one GPU): the meridian mirror on top of the rotation, 13 instead of 18 face-pair units evaluated
+            orbit_mode = args.orbit_mode if world == 1 else 0
+            orbit_pairs_all = partition.orbit_pairs_in_range(0, nside * nside, nside * nside, orbit_mode)
+            sharded = multigpu.OrbitShardedTQU(ctx, nside, rank, world, mode=orbit_mode, exchange=args.exchange)
             launch = lambda: sharded.generate(weights)
             lay = None
             my_pairs = sharded.pairs                      # pixel pairs this rank EVALUATES (a quarter of those it stores)
@@ -927,6 +930,8 @@ def main():
                          "on THREADS host threads (cmg_set_host_expand); -1 = the library's default (automatic), 0 = one plain copy of the whole matrix")
     ap.add_argument("--cholesky", action="store_true", help="full-sky T,Q,U over orbits: also factorise the matrix in place on the shards "
                     "(multigpu.ShardedCholesky; key consumer_cholesky; ~40 s on one GPU, ~5 s on eight for the Nside = 64 matrix)")
+    ap.add_argument("--orbit-mode", type=int, default=0, choices=[0, 1, 2, 3], help="full-sky T,Q,U on one GPU: mode of cmg_tqu_orbit "
+                    "(3 = with the meridian mirror: fewer evaluations, store-pattern bound; DESIGN.md)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

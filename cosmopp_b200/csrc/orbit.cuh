@@ -228,6 +228,14 @@ __device__ __forceinline__ bool orbitTile(const OrbitPlan& plan, const OrbitShar
 // images 4 .. 7 are the four rotations of the pair's mirror image -- row pixel (mirRowFace[k], swapped bits of q_row), column pixel
 // (imgColFace[k], swapped bits of q_col), the entries with exactly one U index negated.  The thread's row offset and the lane's
 // offset inside a staged row become orbitSwapBits(il) and orbitSwapBits(lane): a warp store is two 128-byte segments.
+// store policy of tquOrbitKernel: streaming (evict-first) by default; -DCMG_ORBIT_STORE_WB builds it with plain write-back
+// stores for the comparison
+#ifdef CMG_ORBIT_STORE_WB
+#define ORB_ST(p, v) (*(p) = (v))
+#else
+#define ORB_ST(p, v) __stcs((p), (v))
+#endif
+
 template <int R, int MINB, int SWAPMASK, bool ROWPTR = false, bool MIRROR = false>
 __global__ void __launch_bounds__(PQ_THREADS, MINB)
 tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entrySlot,
@@ -430,15 +438,15 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
                     double* colU = sColPtr[(k * 3 + 2) * PQ_TJ + jl] + ip;
                     if(some)
                     {
-                        __stcs(colQ, vTQ);
-                        __stcs(colU, vTU);
-                        __stcs(colU + npix, vQU);
+                        ORB_ST(colQ, vTQ);
+                        ORB_ST(colU, vTU);
+                        ORB_ST(colU + npix, vQU);
                     }
                     if(all)
                     {
-                        __stcs(colT, vTT);
-                        __stcs(colQ + npix, vQQ);
-                        __stcs(colU + 2 * npix, vUU);
+                        ORB_ST(colT, vTT);
+                        ORB_ST(colQ + npix, vQQ);
+                        ORB_ST(colU + 2 * npix, vUU);
                     }
                 }
                 if(MIRROR)
@@ -452,12 +460,12 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
                         double* colT = sColPtr[((ORB_MAX_IMAGES + k) * 3 + 0) * PQ_TJ + jl] + ip;
                         double* colQ = sColPtr[((ORB_MAX_IMAGES + k) * 3 + 1) * PQ_TJ + jl] + ip;
                         double* colU = sColPtr[((ORB_MAX_IMAGES + k) * 3 + 2) * PQ_TJ + jl] + ip;
-                        __stcs(colQ, vTQ);
-                        __stcs(colU, -vTU);
-                        __stcs(colU + npix, -vQU);
-                        __stcs(colT, vTT);
-                        __stcs(colQ + npix, vQQ);
-                        __stcs(colU + 2 * npix, vUU);
+                        ORB_ST(colQ, vTQ);
+                        ORB_ST(colU, -vTU);
+                        ORB_ST(colU + npix, -vQU);
+                        ORB_ST(colT, vTT);
+                        ORB_ST(colQ + npix, vQQ);
+                        ORB_ST(colU + 2 * npix, vUU);
                     }
                 }
                 stage[(0 * PQ_TI + il) * PQ_STAGE_LD + jl] = xt * fma(ai, ai, -bi * bi);   // Q_a T_b
@@ -491,7 +499,7 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
             {
                 const int ilr = row & (PQ_TI - 1);
                 if(qColLane - (qRow0 + ilr) >= minGap)
-                    __stcs(sRowPtr[k * 3 * PQ_TI + row] + lane, stage[row * PQ_STAGE_LD + lane]);
+                    ORB_ST(sRowPtr[k * 3 * PQ_TI + row] + lane, stage[row * PQ_STAGE_LD + lane]);
             }
         }
         if(MIRROR)
@@ -505,7 +513,7 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
                 for(int row = warp; row < 3 * PQ_TI; row += PQ_THREADS / 32)
                 {
                     const double v = stage[row * PQ_STAGE_LD + lane];
-                    __stcs(sRowPtr[k * 3 * PQ_TI + row] + laneM, row >= PQ_TI ? -v : v);
+                    ORB_ST(sRowPtr[k * 3 * PQ_TI + row] + laneM, row >= PQ_TI ? -v : v);
                 }
             }
         }
@@ -530,11 +538,13 @@ tquOrbitKernel(const __grid_constant__ TquStaticTable T, Geometry geo, int entry
                                                      : static_cast<unsigned long long>(r % ORB_SUB) * ORB_SUB;
                 double* dst = (local ? e.own : e.box[u / HALF_U]) + off + lane;
                 if(qColLane - qa >= e.minGap)
-                    __stcs(dst, src[r * PQ_STAGE_LD]);
+                    ORB_ST(dst, src[r * PQ_STAGE_LD]);
             }
         }
     }
 }
+
+#undef ORB_ST
 
 // ------------------------------------------------------------------------------------------------
 // TT over symmetry orbits (cmg_legendre_series_orbit, cmg_legendre_series_orbit_sharded; the whole-call TT entry points take it

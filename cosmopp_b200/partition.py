@@ -90,10 +90,15 @@ def batch_partition(n_batch, n_parts, slab=16):
 
 # ---------------------------------------------------------------- symmetry-orbit path (cmg_tqu_orbit_sharded)
 
+# (whole-face-pair classes, q_row <= q_col classes) of cmg_tqu_orbit's plan: mode 0 / 2 with transposed images, 1 without,
+# 3 with the meridian mirror on top of mode 0 (five whole-face-pair classes stored as mirror images; single owner only)
+ORBIT_UNITS = {0: (15, 6), 1: (21, 3), 2: (15, 6), 3: (10, 6)}
+
+
 def orbit_column_cost(q, face_pix, mode=0):
     """source pixel pairs evaluated for the in-face column index q: whole-face classes contribute face_pix rows each,
     q_row <= q_col classes q + 1 (cosmopp_b200/csrc/orbit.cuh: 15 + 6 classes with transposed images, 21 + 3 without)"""
-    full, tri = (15, 6) if mode == 0 else (21, 3)
+    full, tri = ORBIT_UNITS[mode]
     return full * face_pix + tri * (q + 1)
 
 
@@ -103,7 +108,7 @@ def orbit_partition(nside, n_parts, mode=0, align=32):
     face_pix = nside * nside
     if n_parts < 1 or face_pix % align:
         raise ValueError("n_parts must be >= 1 and nside^2 a multiple of the column tile")
-    full, tri = (15, 6) if mode == 0 else (21, 3)
+    full, tri = ORBIT_UNITS[mode]
     total = full * face_pix * face_pix + tri * face_pix * (face_pix + 1) // 2
     b = [0]
     for k in range(1, n_parts):
@@ -134,7 +139,7 @@ def orbit_partition_blocks(nside, n_parts, block=128):
 
 def orbit_pairs_in_range(q0, q1, face_pix, mode=0):
     """source pixel pairs a rank owning [q0, q1) evaluates"""
-    full, tri = (15, 6) if mode == 0 else (21, 3)
+    full, tri = ORBIT_UNITS[mode]
     return full * face_pix * (q1 - q0) + tri * (q1 * (q1 + 1) - q0 * (q0 + 1)) // 2
 
 
