@@ -88,5 +88,49 @@ for mode in (0, 1, 2):
     for rk in ranks:
         rk.close()
 ctx.legendre_series_orbit(capi.tt_weights(synthetic_cl(20), f16), torch.empty(capi.packed_size(n16), dtype=torch.float64, device="cuda"))
+ctx.tqu_orbit(*w16, full16, 3)                      # meridian mirror: eight images per evaluated pair of five classes
+torch.cuda.synchronize()
+# packed Cholesky: groups of blocks with and without look-ahead, ragged last block; solves, log det; the step functions with
+# three ranks emulated in lock step (runs of columns, shared U_kk buffer and dense panel)
+def spd_packed(m, seed):
+    rs = np.random.RandomState(seed)
+    B = rs.normal(size=(m, m // 2 + 3))
+    A = B @ B.T + 0.5 * m * np.eye(m)
+    iu = np.triu_indices(m)
+    p_ = np.empty(m * (m + 1) // 2)
+    p_[iu[1] * (iu[1] + 1) // 2 + iu[0]] = A[iu]
+    return p_
+for m, group, ahead in ((300, 1, False), (700, 2, True), (1153, 4, True), (1153, 3, False)):
+    ctx.set_cholesky_group(group); ctx.set_cholesky_lookahead(ahead)
+    d_a = torch.from_numpy(spd_packed(m, m)).cuda()
+    assert ctx.packed_cholesky(d_a, m) == 0
+    ctx.packed_cholesky_logdet(d_a, m)
+    ctx.packed_cholesky_solve(d_a, m, torch.ones((3, m), dtype=torch.float64, device="cuda"), 3)
+ctx.set_cholesky_group(0); ctx.set_cholesky_lookahead(True)
+m = 128 * 7 + 50
+packed = spd_packed(m, 5)
+edges = [0, 128, 384, 512, 768, 896, m]
+all_runs = [[(edges[k], edges[k + 1]) for k in range(r, 6, 3)] for r in range(3)]
+po = lambda c: c * (c + 1) // 2
+bufs = [[torch.from_numpy(packed[po(b):po(e)].copy()).cuda() for b, e in all_runs[r]] for r in range(3)]
+ukk = torch.zeros(capi.CHOL_NB * (capi.CHOL_NB + 1) // 2 + capi.CHOL_NB, dtype=torch.float64, device="cuda")
+panel = torch.zeros(2 * (m + capi.CHOL_PLANE_SLACK) * capi.CHOL_NB, dtype=torch.float64, device="cuda")
+class _NoComm:
+    def broadcast(self, t, src): pass
+    def all_reduce(self, t): pass
+rk = [multigpu.ShardedCholesky(ctx, m, all_runs, r, [t.data_ptr() for t in bufs[r]], comm=_NoComm(), ukk=ukk, panel=panel, group=2) for r in range(3)]
+ctx.chol_begin()
+for ph in rk[0].schedule():
+    for r_ in rk:
+        r_.run_phase(ph)
+assert ctx.chol_end() == 0
+rhs = torch.ones((2, m), dtype=torch.float64, device="cuda")
+for k0, kb in rk[0].blocks():
+    ctx.chol_solve_diag(rk[rk[0].owners[k0 // capi.CHOL_NB]].runs, k0, kb, m, rhs, 2)
+    if k0 + kb < m:
+        for r_ in rk:
+            ctx.chol_solve_update(r_.runs, k0, kb, m, rhs, 2)
+for r_ in rk:
+    ctx.chol_logdet_runs(r_.runs)
 torch.cuda.synchronize()
 print("sanitize_run: all kernels launched, no error reported by the runtime")
