@@ -147,7 +147,7 @@ _SIGNATURES = {
     "cmg_chol_end": (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
     "cmg_chol_diag": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp]),
     "cmg_chol_panel": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _vp, _i64]),
-    "cmg_chol_syrk": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _vp, _i64, _i64, ctypes.c_int]),
+    "cmg_chol_syrk": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), _i64, ctypes.c_int, _i64, _vp, _i64, _i64, ctypes.c_int]),
     "cmg_set_cholesky_group": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_set_cholesky_lookahead": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cmg_chol_logdet_runs": (ctypes.c_int, [_vp, ctypes.POINTER(CholRuns), ctypes.POINTER(ctypes.c_double)]),
@@ -527,8 +527,8 @@ class Context:
     def chol_panel(self, runs, k0, kb, d_ukk, d_plane, panel_col0):
         self._check(self._L.cmg_chol_panel(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_ukk), _p(d_plane), int(panel_col0)))
 
-    def chol_syrk(self, runs, k0, kb, d_panel, plane_stride, panel_col0, strip_only):
-        self._check(self._L.cmg_chol_syrk(self._h, ctypes.byref(runs), int(k0), int(kb), _p(d_panel), int(plane_stride), int(panel_col0),
+    def chol_syrk(self, runs, k0, kb, d_panel, plane_stride, panel_col0, strip_only, shift=0):
+        self._check(self._L.cmg_chol_syrk(self._h, ctypes.byref(runs), int(k0), int(kb), int(shift), _p(d_panel), int(plane_stride), int(panel_col0),
                                           int(bool(strip_only))))
 
     def set_cholesky_group(self, blocks):

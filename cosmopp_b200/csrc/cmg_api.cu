@@ -2074,18 +2074,19 @@ cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, i
     return CMG_OK;
 }
 
-cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* dPanel, int64_t planeStride, int64_t panelCol0,
-                         int stripOnly)
+cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, int64_t shift, const double* dPanel, int64_t planeStride,
+                         int64_t panelCol0, int stripOnly)
 {
     if(!ctx) return CMG_EINVAL;
     if(!cholRunsValid(runs) || !dPanel || kb < cmg::CH_NB || kb > CH_MAX_GROUP * cmg::CH_NB || kb % cmg::CH_NB || k0 % cmg::CH_NB || panelCol0 > k0 + cmg::CH_NB ||
-       panelCol0 % 2 || planeStride % 2 || !ctx->dCholInfo)
-        return fail(ctx, CMG_EINVAL, "cmg_chol_syrk: bad arguments (kb = 128 .. 512 rows in whole blocks; panel_col0 <= k0 + 128)");
+       panelCol0 % 2 || planeStride % 2 || shift < 0 || shift % cmg::CH_NB || !ctx->dCholInfo)
+        return fail(ctx, CMG_EINVAL, "cmg_chol_syrk: bad arguments (kb = 128 .. 512 rows and shift in whole blocks; panel_col0 <= k0 + 128)");
     cmg::CholRuns clipped;
-    const int64_t tiles = cholClipRuns(runs, k0 + kb, k0 + kb, stripOnly ? -1 : 0, &clipped);
+    const int64_t k1 = k0 + kb + shift;
+    const int64_t tiles = cholClipRuns(runs, k1, k1, stripOnly ? -1 : 0, &clipped);
     if(tiles == 0) return CMG_OK;
     CMG_CUDA(ctx, cudaSetDevice(ctx->device));
-    cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(clipped, k0, kb, 0, ctx->dCholInfo, dPanel, panelCol0,
+    cmg::cholSyrkKernel<<<static_cast<unsigned>(tiles), cmg::CH_SYRK_THREADS, CH_SYRK_SMEM, ctx->stream>>>(clipped, k0, kb, shift, ctx->dCholInfo, dPanel, panelCol0,
                                                                                                          planeStride, stripOnly ? 1 : 0);
     CMG_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

@@ -412,7 +412,8 @@ class ShardedCholesky:
         self.plane_stride = (self.n + capi.CHOL_PLANE_SLACK) * nb
         self.ukk = ukk if ukk is not None else torch.empty(nb * (nb + 1) // 2 + nb, dtype=torch.float64, device="cuda")
         # zeros: the spare rows behind the last column are read (never used)
-        self.panel = panel if panel is not None else torch.zeros(group * self.plane_stride, dtype=torch.float64, device="cuda")
+        # two sets of planes: the look-ahead writes the next group's rows while the update still reads this group's
+        self.panel = panel if panel is not None else torch.zeros(2 * group * self.plane_stride, dtype=torch.float64, device="cuda")
         if self.panel.numel() < group * self.plane_stride:
             raise ValueError("panel: group * (n + %d) * %d doubles" % (capi.CHOL_PLANE_SLACK, nb))
         self.device = self.panel.device
@@ -450,42 +451,58 @@ class ShardedCholesky:
                 out.append(("syrk", base, subs))
         return out
 
-    def plane_region(self, k0, base, sub):
-        """the part of plane `sub` the panel step of block k0 fills: the 128 rows of every column behind the block"""
+    def plane_region(self, k0, base, sub, buf=0):
+        """the part of plane `sub` (of plane set `buf`) the panel step of block k0 fills: the 128 rows of every column behind the block"""
         nb = capi.CHOL_NB
-        first = sub * self.plane_stride + (k0 + nb - base) * nb
+        first = (buf * self.group + sub) * self.plane_stride + (k0 + nb - base) * nb
         return self.panel[first:first + (self.n - k0 - nb) * nb]
 
-    def run_phase(self, ph):
-        """this rank's kernel of a phase (no exchange)"""
+    def run_phase(self, ph, buf=0):
+        """this rank's kernel of a phase (no exchange); buf: which of the two sets of planes (look-ahead alternates)"""
         nb = capi.CHOL_NB
         if self.runs is None:
             return
+        planes = self.panel[buf * self.group * self.plane_stride:]
         if ph[0] == "strip":
-            self.ctx.chol_syrk(self.runs, ph[1], ph[2] * nb, self.panel, self.plane_stride, ph[1], True)
+            self.ctx.chol_syrk(self.runs, ph[1], ph[2] * nb, planes, self.plane_stride, ph[1], True)
         elif ph[0] == "diag":
             if ph[3] == self.rank:
                 self.ctx.chol_diag(self.runs, ph[1], ph[2], self.ukk)
         elif ph[0] == "panel":
-            self.ctx.chol_panel(self.runs, ph[1], nb, self.ukk, self.panel[ph[3] * self.plane_stride:], ph[2])
+            self.ctx.chol_panel(self.runs, ph[1], nb, self.ukk, planes[ph[3] * self.plane_stride:], ph[2])
         else:
-            self.ctx.chol_syrk(self.runs, ph[1], ph[2] * nb, self.panel, self.plane_stride, ph[1], False)
+            self.ctx.chol_syrk(self.runs, ph[1], ph[2] * nb, planes, self.plane_stride, ph[1], False)
 
-    def factorise(self):
-        """Collective.  Returns LAPACK's info (0: positive definite; k: the leading minor of order k is not), the same on every rank."""
+    def _run_with_exchanges(self, ph, buf=0):
+        """a phase with the exchange that belongs to it (on torch's current stream)"""
+        if ph[0] == "panel" and self.world > 1:
+            region = self.plane_region(ph[1], ph[2], ph[3], buf)
+            region.zero_()
+            self.run_phase(ph, buf)
+            self.comm.all_reduce(region)
+            return
+        self.run_phase(ph, buf)
+        if ph[0] == "diag" and self.world > 1 and ph[1] + ph[2] < self.n:
+            self.comm.broadcast(self.ukk, ph[3])
+
+    def factorise(self, lookahead=None):
+        """Collective.  Returns LAPACK's info (0: positive definite; k: the leading minor of order k is not), the same on every rank.
+        lookahead (default: on a GPU when the panel buffer holds two sets of planes): the trailing update of a group is issued
+        in pieces -- first, strip by strip, the rows the next group will factorise, then the rest -- and the next group's blocks
+        (diagonal block, broadcast, panel, all-reduce, ...) run on a second, high-priority stream beside the rest."""
         import torch
         self._check_stream()
+        two_sets = self.panel.numel() >= 2 * self.group * self.plane_stride
+        if lookahead is None:
+            lookahead = self.device.type == "cuda" and two_sets and self.n > 2 * self.group * capi.CHOL_NB
+        if lookahead and not two_sets:
+            raise ValueError("look-ahead needs a panel buffer of 2 * group * (n + %d) * %d doubles" % (capi.CHOL_PLANE_SLACK, capi.CHOL_NB))
         self.ctx.chol_begin()
-        for ph in self.schedule():
-            if ph[0] == "panel" and self.world > 1:
-                region = self.plane_region(ph[1], ph[2], ph[3])
-                region.zero_()
-                self.run_phase(ph)
-                self.comm.all_reduce(region)
-                continue
-            self.run_phase(ph)
-            if ph[0] == "diag" and self.world > 1 and ph[1] + ph[2] < self.n:
-                self.comm.broadcast(self.ukk, ph[3])
+        if lookahead:
+            self._factorise_lookahead()
+        else:
+            for ph in self.schedule():
+                self._run_with_exchanges(ph)
         info = self.ctx.chol_end()
         if self.world > 1:                       # the first failing block wins on every rank
             big = 1 << 62
@@ -496,6 +513,53 @@ class ShardedCholesky:
             info = 0 if info == big else info
         self.info = info
         return info
+
+    def _factorise_lookahead(self):
+        import torch
+        nb = capi.CHOL_NB
+        rows = nb * self.group
+        # the phases of the schedule, group by group (without the trailing updates: those are issued in pieces here)
+        groups, cur = [], []
+        for ph in self.schedule():
+            if ph[0] == "syrk":
+                groups.append(cur)
+                cur = []
+            else:
+                cur.append(ph)
+        groups.append(cur)
+        # (host buffers -- the tests of the order of calls -- have no streams: the same order, one call after the other)
+        streams = self.device.type == "cuda"
+        if streams:
+            main = torch.cuda.current_stream()
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(priority=-1)
+            side = self._side
+            ev_a, ev_f = torch.cuda.Event(), torch.cuda.Event()
+        for ph in groups[0]:
+            self._run_with_exchanges(ph, 0)
+        for g in range(len(groups) - 1):
+            base, planes = g * rows, self.panel[(g & 1) * self.group * self.plane_stride:]
+            if self.runs is not None:
+                for r in range(self.group):          # the rows of the next group, strip by strip
+                    self.ctx.chol_syrk(self.runs, base, rows, planes, self.plane_stride, base, True, shift=r * nb)
+            if streams:
+                ev_a.record(main)
+                side.wait_event(ev_a)
+                self.ctx.set_stream(side.cuda_stream)
+                try:
+                    with torch.cuda.stream(side):
+                        for ph in groups[g + 1]:
+                            self._run_with_exchanges(ph, (g + 1) & 1)
+                        ev_f.record(side)
+                finally:
+                    self.ctx.set_stream(main.cuda_stream)
+            else:
+                for ph in groups[g + 1]:
+                    self._run_with_exchanges(ph, (g + 1) & 1)
+            if self.runs is not None:                # the rest of the update, beside the next group's blocks
+                self.ctx.chol_syrk(self.runs, base, rows, planes, self.plane_stride, base, False, shift=rows)
+            if streams:
+                main.wait_event(ev_f)
 
     def logdet(self):
         """log det A = 2 sum log U_jj.  Collective."""

@@ -391,6 +391,9 @@ cmg_status cmg_packed_cholesky_solve(cmg_ctx* ctx, const double* d_factor, int64
  * and after the last block of the group
  *   cmg_chol_syrk   (every rank, strip_only = 0, k0 = group start, kb = 128 S)  trailing update of the rank's own columns behind
  *                   the group, operands read from the S planes.
+ * shift (a multiple of 128, normally 0): the update starts at row and column k0 + kb + shift -- the update of a group can be issued
+ * in pieces, first strip by strip the rows the NEXT group factorises (strip_only = 1, shift = 0, 128, ...), then the rest
+ * (shift = 128 S) while the next group's blocks are factorised on another stream (multigpu.ShardedCholesky, look-ahead).
  * cmg_chol_begin before the first step, cmg_chol_end after the last (*info as cmg_packed_cholesky: the first non-positive pivot
  * of a block this rank owns, 0 otherwise; the caller takes the minimum of the non-zero values over ranks). */
 #define CMG_CHOL_MAX_RUNS 36
@@ -405,7 +408,7 @@ cmg_status cmg_chol_begin(cmg_ctx* ctx);
 cmg_status cmg_chol_end(cmg_ctx* ctx, int64_t* info);
 cmg_status cmg_chol_diag(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, double* d_ukk);
 cmg_status cmg_chol_panel(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* d_ukk, double* d_plane, int64_t panel_col0);
-cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, const double* d_panel, int64_t plane_stride,
+cmg_status cmg_chol_syrk(cmg_ctx* ctx, const cmg_chol_runs* runs, int64_t k0, int kb, int64_t shift, const double* d_panel, int64_t plane_stride,
                          int64_t panel_col0, int strip_only);
 /* this rank's share of log det A: 2 sum log U_jj over its columns (the caller sums over ranks) */
 cmg_status cmg_chol_logdet_runs(cmg_ctx* ctx, const cmg_chol_runs* runs, double* log_det_share);

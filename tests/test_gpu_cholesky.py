@@ -190,15 +190,17 @@ def test_sharded_cholesky_ranks_in_lock_step(gpu_ctx, n, world, cycles, group):
     assert np.abs(t.cpu().numpy() - want_y).max() <= 1e-11 * np.abs(want_y).max()
 
 
-def test_sharded_cholesky_single_rank_is_the_whole_call(gpu_ctx):
-    """world = 1 through the class: factorise / logdet / solve without any exchange"""
+@pytest.mark.parametrize("n, group, ahead", [(700, 4, None), (2100, 2, True), (2100, 3, True), (1700, 4, False)])
+def test_sharded_cholesky_single_rank_is_the_whole_call(gpu_ctx, n, group, ahead):
+    """world = 1 through the class: factorise / logdet / solve without any exchange; with the look-ahead the next group's
+    blocks run on a second stream beside the rest of the trailing update (two sets of panel planes)"""
     import torch
     from cosmopp_b200 import multigpu
-    n = 700
     A = random_spd(n, 41)
     d = torch.from_numpy(pack_upper(A)).cuda()
-    ch = multigpu.ShardedCholesky(gpu_ctx, n, [[(0, n)]], 0, [d.data_ptr()])
-    assert ch.factorise() == 0
+    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ch = multigpu.ShardedCholesky(gpu_ctx, n, [[(0, n)]], 0, [d.data_ptr()], group=group)
+    assert ch.factorise(lookahead=ahead) == 0
     want = np.linalg.cholesky(A).T
     assert np.abs(unpack_upper(d.cpu().numpy(), n) - want).max() <= 1e-12 * np.abs(want).max()
     assert abs(ch.logdet() - np.linalg.slogdet(A)[1]) <= 1e-12 * abs(np.linalg.slogdet(A)[1])

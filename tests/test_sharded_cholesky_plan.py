@@ -102,8 +102,8 @@ class NumpyStepCtx:
                 col[k0:k0 + kb] = x
                 P[(j - panel_col0) * NB:(j - panel_col0) * NB + kb] = x
 
-    def chol_syrk(self, runs, k0, kb, panel, plane_stride, panel_col0, strip_only):
-        k1 = k0 + kb
+    def chol_syrk(self, runs, k0, kb, panel, plane_stride, panel_col0, strip_only, shift=0):
+        k1 = k0 + kb + shift
         planes = [panel.numpy()[s * plane_stride:(s + 1) * plane_stride].reshape(-1, NB) for s in range(kb // NB)]
         for b, e, _ in self._cols(runs):
             for j in range(max(b, k1), e):
@@ -143,7 +143,7 @@ def packed_of(A):
     return out
 
 
-def _worker(rank, world, port, n, all_runs, bad, group, out):
+def _worker(rank, world, port, n, all_runs, bad, group, ahead, out):
     import torch
     import torch.distributed as dist
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
@@ -154,9 +154,9 @@ def _worker(rank, world, port, n, all_runs, bad, group, out):
     arrays = {1000 + k: packed[off(b):off(e)].copy() for k, (b, e) in enumerate(all_runs[rank])}
     ctx = NumpyStepCtx(arrays)
     ukk = torch.zeros(off(NB) + NB, dtype=torch.float64)
-    panel = torch.zeros(group * (n + capi.CHOL_PLANE_SLACK) * NB, dtype=torch.float64)
+    panel = torch.zeros((2 if ahead else 1) * group * (n + capi.CHOL_PLANE_SLACK) * NB, dtype=torch.float64)
     ch = multigpu.ShardedCholesky(ctx, n, all_runs, rank, list(arrays.keys()), ukk=ukk, panel=panel, group=group)
-    info = ch.factorise()
+    info = ch.factorise(lookahead=ahead)
     res = {"rank": rank, "info": info}
     if not bad:
         res["logdet"] = ch.logdet()
@@ -194,15 +194,15 @@ def _zeros(k):
     return torch.zeros(k, dtype=torch.float64)
 
 
-@pytest.mark.parametrize("bad, group", [(0, 1), (0, 2), (0, 3), (300, 2)])
-def test_two_ranks_factorise_over_gloo(bad, group):
+@pytest.mark.parametrize("bad, group, ahead", [(0, 1, False), (0, 2, False), (0, 3, False), (300, 2, False), (0, 1, True), (0, 2, True), (300, 2, True)])
+def test_two_ranks_factorise_over_gloo(bad, group, ahead):
     import torch.multiprocessing as mp
     n, world = 5 * NB + 40, 2
     all_runs = [[(0, 128), (384, 512)], [(128, 384), (512, n)]]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, all_runs, bad, group, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, all_runs, bad, group, ahead, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda d: d["rank"])

@@ -97,7 +97,8 @@ def main():
             del mine_before
         ch = multigpu.ShardedCholesky(ctx, n, all_runs, rank, ptrs, group=group)
         launches0 = ctx.launches
-        fact_ms, info = timed(ch.factorise)
+        ahead = False if "--no-lookahead" in sys.argv else None
+        fact_ms, info = timed(lambda: ch.factorise(lookahead=ahead))
         launches = ctx.launches - launches0
         logdet = ch.logdet()
         rhs = torch.from_numpy(np.random.RandomState(77).normal(size=(2, n))).cuda()
@@ -117,7 +118,7 @@ def main():
         t = torch.tensor([err], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        line = {"nside": nside, "n": n, "n_gpus": world, "group": group, "packed_gb": capi.packed_size(n) * 8e-9, "strips_gb_this_rank": strips.numel() * 8e-9,
+        line = {"nside": nside, "n": n, "n_gpus": world, "group": group, "lookahead": "--no-lookahead" not in sys.argv, "packed_gb": capi.packed_size(n) * 8e-9, "strips_gb_this_rank": strips.numel() * 8e-9,
                 "blocks_per_rank": int(np.bincount(ch.owners, minlength=world)[rank]), "info": info,
                 "generate_ms": gen_ms, "exchange_ms": exch_ms, "factorise_ms": fact_ms, "solve_2rhs_ms": solve_ms,
                 "kernel_launches_this_rank": launches, "tflops_all_gpus": n ** 3 / 3.0 / (fact_ms * 1e-3) / 1e12, "fp64_peak_tflops_per_gpu": peak,
