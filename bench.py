@@ -381,7 +381,7 @@ def cholesky_leg(ctx, torch, dist, nside, weights, rank, world, peak_tflops):
            "kernel_launches_this_rank": ctx.launches - launches0, "log_det": ch.logdet(), "utu_max_rel_err": float(e.item()),
            "utu_samples_per_rank": ns,
            "how": "multigpu.ShardedCholesky on the rank's 36 orbit strips in place (cmg_chol_*: per block a 67 KB broadcast of U_kk and an all-reduce "
-                  "of one plane of the dense panel; FP64 tensor-core trailing update per group of 4 blocks); nothing gathered"}
+                  "of one plane of the dense panel; FP64 tensor-core trailing update per group of 4 blocks, the next group's blocks and collectives on a second stream beside it); nothing gathered"}
     del ch, strips
     sh.close()
     torch.cuda.empty_cache()
@@ -929,7 +929,7 @@ def main():
                     help="N=1, full sky, e2e leg: copy back only the last-face columns (27 %% of the matrix) and fill in the rotated images "
                          "on THREADS host threads (cmg_set_host_expand); -1 = the library's default (automatic), 0 = one plain copy of the whole matrix")
     ap.add_argument("--cholesky", action="store_true", help="full-sky T,Q,U over orbits: also factorise the matrix in place on the shards "
-                    "(multigpu.ShardedCholesky; key consumer_cholesky; ~40 s on one GPU, ~5 s on eight for the Nside = 64 matrix)")
+                    "(multigpu.ShardedCholesky; key consumer_cholesky; ~31 s on one GPU, ~4.2 s on eight for the Nside = 64 matrix)")
     ap.add_argument("--orbit-mode", type=int, default=0, choices=[0, 1, 2, 3], help="full-sky T,Q,U on one GPU: mode of cmg_tqu_orbit "
                     "(3 = with the meridian mirror: fewer evaluations, store-pattern bound; DESIGN.md)")
     ap.add_argument("--no-e2e", action="store_true")
